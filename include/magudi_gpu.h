@@ -1,0 +1,199 @@
+/* libmagudi_gpu -- C ABI of the B200-native RHS / adjoint / RK4 engine for magudi.
+ *
+ * Drop-in boundary for ONE hot path of dreamer2368/magudi: the per-stage right-hand-side evaluation
+ * of the compressible Navier-Stokes equations and of its discrete adjoint, advanced by RK4.
+ * The reference has no FFI seam for this path (everything is Fortran type-bound procedures); each
+ * entry point below replaces one of them and is what a thin `iso_c_binding` layer in the Fortran
+ * host binds.  All paths cited are relative to the reference repository root.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative code on error; mg_last_error() then holds
+ *     the message (the Fortran shim turns that into `gracefulExit`, src/ErrorHandlerImpl.f90:162-204);
+ *   - arrays are Fortran-ordered `A(N, nComp)`: point index i + nx*(j + ny*k) fastest, fp64
+ *     (`SCALAR_TYPE` real64, include/config.h.in:53-60); N is the LOCAL point count of the rank;
+ *   - indices in extents are 1-based and inclusive like bc.dat (negative values already resolved);
+ *   - one host thread per handle; the library owns device-resident mirrors of all fields, host
+ *     arrays are only touched by the *_set / *_get calls;
+ *   - there is NO CPU fallback: every numerical entry point runs CUDA kernels on the current device
+ *     and fails if none is available.
+ */
+#ifndef MAGUDI_GPU_H
+#define MAGUDI_GPU_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mg_stencil mg_stencil;   /* t_StencilOperator, include/StencilOperator.f90:9-30 */
+typedef struct mg_grid mg_grid;         /* t_Grid,            include/Grid.f90:32-73          */
+typedef struct mg_state mg_state;       /* t_State,           include/State.f90:51-87         */
+typedef struct mg_patch mg_patch;       /* t_Patch family,    include/Patch.f90:9-59          */
+typedef struct mg_region mg_region;     /* t_Region,          include/Region.f90:29-64        */
+
+/* Region_enum, include/Region.f90:8-11 */
+#define MG_MODE_FORWARD 1
+#define MG_MODE_ADJOINT (-1)
+#define MG_MODE_LINEARIZED 0
+
+/* Grid_enum periodicity types, include/Grid.f90:17-20 */
+#define MG_NONE 0
+#define MG_PLANE 1
+#define MG_OVERLAP 2
+
+/* patch types: the keys of PatchFactoryImpl.f90:43-87 that lie on the hot path */
+#define MG_SAT_FAR_FIELD 1
+#define MG_SPONGE 2
+#define MG_SAT_SLIP_WALL 3
+#define MG_SAT_ISOTHERMAL_WALL 4
+#define MG_COST_TARGET 5
+#define MG_ACTUATOR 6
+
+/* field ids for mg_state_set / mg_state_get (t_State members, include/State.f90:59-62) and
+ * mg_grid_get / mg_grid_set (t_Grid members, include/Grid.f90:38-40) */
+enum {
+  MG_Q_CONSERVED = 0, MG_Q_ADJOINT = 1, MG_Q_TARGET = 2, MG_Q_RHS = 3,
+  MG_Q_SPECIFIC_VOLUME = 4, MG_Q_VELOCITY = 5, MG_Q_PRESSURE = 6, MG_Q_TEMPERATURE = 7,
+  MG_Q_DYNAMIC_VISCOSITY = 8, MG_Q_SECOND_VISCOSITY = 9, MG_Q_THERMAL_DIFFUSIVITY = 10,
+  MG_Q_STRESS_TENSOR = 11, MG_Q_HEAT_FLUX = 12,
+  MG_G_COORDINATES = 100, MG_G_METRICS = 101, MG_G_JACOBIAN = 102, MG_G_NORM = 103,
+  MG_G_ARC_LENGTHS = 104, MG_G_TARGET_MOLLIFIER = 105, MG_G_CONTROL_MOLLIFIER = 106
+};
+
+/* t_SolverOptions / t_SimulationFlags members read by the hot path
+ * (src/SolverOptionsImpl.f90:46-136, src/SimulationFlagsImpl.f90:24-44) */
+typedef struct mg_options {
+  double ratioOfSpecificHeats;
+  int viscosityOn;
+  double reynoldsNumberInverse;
+  double prandtlNumberInverse;
+  double powerLawExponent;
+  double bulkViscosityRatio;
+  int dissipationOn;
+  int compositeDissipation;
+  double dissipationAmount;
+  int useTargetState;
+  int useContinuousAdjoint;
+} mg_options;
+
+/* ------------------------------------------------------------------ library */
+int mg_init(int device);                      /* select the CUDA device of this rank */
+const char* mg_last_error(void);
+int mg_version(void);
+int mg_synchronize(void);
+
+/* ------------------------------------------------------------------ t_StencilOperator */
+/* %setup(scheme): src/StencilOperatorImpl.f90:1111-2193 */
+int mg_stencil_create(const char* scheme, mg_stencil** out);
+/* %update(cartesianCommunicator, direction, isPeriodicityOverlapping): :2195-2256.  The Cartesian
+ * communicator is replaced by explicit process-grid dims / coordinates / periodicity. */
+int mg_stencil_update(mg_stencil* s, int direction, const int procDims[3], const int procCoords[3],
+                      const int periodic[3], int overlap);
+/* %getAdjoint(adjointOperator): :2285-2372 */
+int mg_stencil_get_adjoint(const mg_stencil* s, mg_stencil** out);
+/* %cleanup: :2258-2283 */
+int mg_stencil_destroy(mg_stencil* s);
+/* members: info = {symmetryType, interiorWidth, boundaryWidth, boundaryDepth, nGhost(1:2),
+ * periodicOffset(1:2), hasDomainBoundary(1:2), lbound(rhsInterior), size(rhsInterior)} */
+int mg_stencil_info(const mg_stencil* s, int info[12]);
+/* rhsInterior(size), rhsBoundary1/2(boundaryWidth, boundaryDepth) column-major, normBoundary */
+int mg_stencil_coefficients(const mg_stencil* s, double* rhsInterior, double* rhsBoundary1,
+                            double* rhsBoundary2, double* normBoundary);
+/* %apply(x, gridSize): :2374-2410 -> :35-252.  In place on x(N, nComp); x may be a host or a device
+ * pointer.  Ghost points come from this rank itself (single-rank fillGhostPoints). */
+int mg_stencil_apply(mg_stencil* s, double* x, int nComp, const int gridSize[3]);
+/* %apply with the fillGhostPoints exchange (src/MPIHelperImpl.f90:113-389) done by the caller:
+ * ghostPrev / ghostNext are the received buffers (nGhost, normalPlaneSize, nComp), NULL where the
+ * operator has no ghost points on that side. */
+int mg_stencil_apply_ghosted(mg_stencil* s, double* x, int nComp, const int gridSize[3],
+                             const double* ghostPrev, const double* ghostNext);
+/* %applyAtInteriorPoints: :254-457 (closure rows of x are left untouched) */
+int mg_stencil_apply_interior(mg_stencil* s, double* x, int nComp, const int gridSize[3]);
+/* %applyNorm / %applyNormInverse: :838-1107 */
+int mg_stencil_apply_norm(mg_stencil* s, double* x, int nComp, const int gridSize[3]);
+int mg_stencil_apply_norm_inverse(mg_stencil* s, double* x, int nComp, const int gridSize[3]);
+/* %applyAndProjectOnBoundary / %projectOnBoundaryAndApply: :459-836 */
+int mg_stencil_apply_and_project_on_boundary(mg_stencil* s, double* x, int nComp, const int gridSize[3],
+                                             int faceOrientation);
+int mg_stencil_project_on_boundary_and_apply(mg_stencil* s, double* x, int nComp, const int gridSize[3],
+                                             int faceOrientation);
+
+/* ------------------------------------------------------------------ t_Grid */
+/* %setup: src/GridImpl.f90:142-291.  localSize/offset follow pigeonhole (src/MPIHelperImpl.f90:3-19);
+ * only slab decompositions along direction 3 are accepted (procDims = {1,1,P}). */
+int mg_grid_create(int index, int nDimensions, const int globalSize[3], const int localSize[3],
+                   const int offset[3], const int periodicityType[3], const double periodicLength[3],
+                   int isCurvilinear, const int procDims[3], const int procCoords[3], mg_grid** out);
+int mg_grid_destroy(mg_grid* g);
+/* %setupSpatialDiscretization: :487-619; scheme[d] is e.g. "SBP 3-6" */
+int mg_grid_setup_spatial_discretization(mg_grid* g, const char* scheme1, const char* scheme2,
+                                         const char* scheme3, int dissipationOn, int compositeDissipation,
+                                         int useContinuousAdjoint);
+int mg_grid_set(mg_grid* g, int field, const double* host);     /* coordinates, mollifiers */
+int mg_grid_get(mg_grid* g, int field, double* host);           /* metrics, jacobian, norm, ... */
+int mg_grid_set_iblank(mg_grid* g, const int* iblank);
+/* %update: :746-1065 (metrics, Jacobian, norm; jacobian holds 1/det afterwards, :1063) */
+int mg_grid_update(mg_grid* g, int* hasNegativeJacobian);
+/* %computeGradient: :1172-1421.  f(N, nComp) -> gradF(N, nD*nComp); host or device pointers */
+int mg_grid_gradient(mg_grid* g, const double* f, int nComp, double* gradF);
+/* %computeInnerProduct: :1067-1170 (local sum; the caller reduces across ranks) */
+int mg_grid_inner_product(mg_grid* g, const double* f, const double* gvec, const double* weight,
+                          int nComp, double* result);
+mg_stencil* mg_grid_operator(mg_grid* g, int which, int direction);   /* 0 first, 1 adjoint, 2 diss, 3 dissT */
+/* ghost planes of a slab-decomposed grid: pack the `width` interior planes next to a k-face of a
+ * grid/state field into a contiguous device buffer (nComp*width*nx*ny doubles), or unpack a received
+ * buffer into the ghost planes of that face.  side 0 = low k, 1 = high k. */
+int mg_halo_pack(mg_grid* g, void* owner, int field, int side, int width, double* deviceBuffer);
+int mg_halo_unpack(mg_grid* g, void* owner, int field, int side, int width, const double* deviceBuffer);
+
+/* ------------------------------------------------------------------ t_State */
+/* %setup: src/StateImpl.f90:71-170 */
+int mg_state_create(mg_grid* g, const mg_options* options, mg_state** out);
+int mg_state_destroy(mg_state* s);
+int mg_state_set(mg_state* s, int field, const double* host);
+int mg_state_get(mg_state* s, int field, double* host);
+int mg_state_set_time(mg_state* s, double time);
+/* acoustic sources: src/StateImpl.f90:135-148, src/AcousticSourceImpl.f90:3-32 */
+int mg_state_add_acoustic_source(mg_state* s, const double location[3], double amplitude, double frequency,
+                                 double radius, double phase);
+/* %update: src/StateImpl.f90:466-537 */
+int mg_state_update(mg_state* s);
+
+/* ------------------------------------------------------------------ t_Patch */
+/* %setup: src/PatchImpl.f90:3-151 and the derived types' setup; amounts are the magudi.inp values
+ * (defaults/inviscid_penalty_amount, .../viscous_penalty_amount); sign and 1/normBoundary(1) are
+ * applied here as in src/FarFieldPatchImpl.f90:53-69. */
+int mg_patch_create(mg_state* s, int type, const char* name, int normalDirection, const int extent[6],
+                    double inviscidPenaltyAmount, double viscousPenaltyAmount, mg_patch** out);
+int mg_patch_num_points(const mg_patch* p, int* nPatchPoints, int localSize[3], int patchOffset[3]);
+/* named patch arrays (nPatchPoints, nComp): "spongeStrength", "temperature", "adjointForcing",
+ * "controlForcing", "targetViscousFluxes", ... */
+int mg_patch_set_array(mg_patch* p, const char* name, int nComp, const double* host);
+int mg_patch_get_array(mg_patch* p, const char* name, int nComp, double* host);
+/* %collect: src/PatchImpl.f90:187-316 -- grid field of the owning state -> patch array */
+int mg_patch_collect(mg_patch* p, int field, const char* name);
+
+/* ------------------------------------------------------------------ t_Region / t_RK4Integrator */
+int mg_region_create(mg_region** out);
+int mg_region_destroy(mg_region* r);
+int mg_region_add_state(mg_region* r, mg_state* s);
+/* updatePatchFactories: src/PatchFactoryImpl.f90:446-574 (target viscous fluxes of far-field patches) */
+int mg_region_update_patches(mg_region* r);
+/* %computeRhs(mode, timestep, stage): src/RegionImpl.f90:1877-2027 */
+int mg_region_compute_rhs(mg_region* r, int mode, int timestep, int stage);
+/* t_RK4Integrator%substepForward / %substepAdjoint: src/RK4IntegratorImpl.f90:65-270.  Includes the
+ * states%update the reference's drivers issue after every substep (src/SolverImpl.f90:831-834) when
+ * updateStates != 0. */
+int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep, int stage, int updateStates);
+/* select the implementation: 0 = general operator-by-operator path, 1 = fused sweeps (default when
+ * the configuration is covered) */
+int mg_region_set_fused(mg_region* r, int enable);
+int mg_region_uses_fused(mg_region* r, int mode);
+/* number of kernels this library has launched since mg_init (bench accounting) */
+long long mg_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGUDI_GPU_H */

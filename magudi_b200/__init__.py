@@ -1,0 +1,6 @@
+"""magudi_b200: B200-native RHS / adjoint / RK4 engine behind magudi's Region/Grid/State/Patch API."""
+from .core import (ADJOINT, FORWARD, LINEARIZED, NONE, OVERLAP, PLANE, Grid, Patch, Region, RK4Integrator,
+                   SolverOptions, State, StencilOperator, pigeonhole)
+
+__all__ = ["ADJOINT", "FORWARD", "LINEARIZED", "NONE", "OVERLAP", "PLANE", "Grid", "Patch", "Region",
+           "RK4Integrator", "SolverOptions", "State", "StencilOperator", "pigeonhole"]

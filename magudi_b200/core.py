@@ -1,0 +1,419 @@
+"""Host-side mirror of magudi's Region / Grid / State / StencilOperator / Patch / RK4Integrator
+types for the RHS hot path.  Each class forwards to the C ABI of ``libmagudi_gpu`` -- there is no
+numerical work and no CPU fallback on this side.
+
+Reference interfaces mirrored (paths relative to the reference repository root):
+``include/StencilOperator.f90:9-30``, ``include/Grid.f90:32-73``, ``include/State.f90:51-87``,
+``include/Patch.f90:9-59``, ``include/Region.f90:29-64``, ``include/TimeIntegrator.f90:7-23``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import Options, check
+
+FORWARD, ADJOINT, LINEARIZED = +1, -1, 0
+NONE, PLANE, OVERLAP = 0, 1, 2
+SYMMETRIC, SKEW_SYMMETRIC, ASYMMETRIC = 0, 1, 2
+
+# field ids (include/magudi_gpu.h)
+Q_CONSERVED, Q_ADJOINT, Q_TARGET, Q_RHS = 0, 1, 2, 3
+Q_SPECIFIC_VOLUME, Q_VELOCITY, Q_PRESSURE, Q_TEMPERATURE = 4, 5, 6, 7
+Q_DYNAMIC_VISCOSITY, Q_SECOND_VISCOSITY, Q_THERMAL_DIFFUSIVITY, Q_STRESS_TENSOR, Q_HEAT_FLUX = 8, 9, 10, 11, 12
+G_COORDINATES, G_METRICS, G_JACOBIAN, G_NORM, G_ARC_LENGTHS = 100, 101, 102, 103, 104
+G_TARGET_MOLLIFIER, G_CONTROL_MOLLIFIER = 105, 106
+
+PATCH_TYPES = {"SAT_FAR_FIELD": 1, "SPONGE": 2, "SAT_SLIP_WALL": 3, "SAT_ISOTHERMAL_WALL": 4,
+               "COST_TARGET": 5, "ACTUATOR": 6}
+
+
+def pigeonhole(nPigeons, nHoles, holeIndex):
+    """Block partition rule of the reference (``src/MPIHelperImpl.f90:3-19``): (offset, count)."""
+    offset = holeIndex * (nPigeons // nHoles) + min(holeIndex, nPigeons % nHoles)
+    n = nPigeons // nHoles + (1 if holeIndex < nPigeons % nHoles else 0)
+    return offset, n
+
+
+class StencilOperator:
+    """``t_StencilOperator``: ``setup`` / ``update`` / ``getAdjoint`` / ``apply`` / ``applyNorm`` ..."""
+
+    def __init__(self, handle=None, owned=True):
+        self._h = handle
+        self._owned = owned
+        self.direction = 1
+
+    @classmethod
+    def setup(cls, scheme: str) -> "StencilOperator":
+        h = C.c_void_p()
+        check(L.load().mg_stencil_create(scheme.encode(), C.byref(h)))
+        return cls(h)
+
+    def update(self, procDims, procCoords, periodic, direction, overlap=False):
+        check(L.load().mg_stencil_update(self._h, int(direction), L.i3(procDims), L.i3(procCoords),
+                                         L.i3([1 if p else 0 for p in periodic] + [0, 0, 0]), int(bool(overlap))))
+        self.direction = int(direction)
+        return self
+
+    def getAdjoint(self) -> "StencilOperator":
+        h = C.c_void_p()
+        check(L.load().mg_stencil_get_adjoint(self._h, C.byref(h)))
+        return StencilOperator(h)
+
+    # --- members
+    def _info(self):
+        a = (C.c_int * 12)()
+        check(L.load().mg_stencil_info(self._h, a))
+        return list(a)
+
+    symmetryType = property(lambda s: s._info()[0])
+    interiorWidth = property(lambda s: s._info()[1])
+    boundaryWidth = property(lambda s: s._info()[2])
+    boundaryDepth = property(lambda s: s._info()[3])
+    nGhost = property(lambda s: s._info()[4:6])
+    periodicOffset = property(lambda s: s._info()[6:8])
+    hasDomainBoundary = property(lambda s: [bool(v) for v in s._info()[8:10]])
+
+    def coefficients(self):
+        info = self._info()
+        bw, bd, lo, nint = info[2], info[3], info[10], info[11]
+        ri = np.zeros(max(nint, 1))
+        b1 = np.zeros((bw, bd), order="F")
+        b2 = np.zeros((bw, bd), order="F")
+        nb = np.zeros(bd)
+        check(L.load().mg_stencil_coefficients(
+            self._h, ri.ctypes.data_as(L._D), b1.ctypes.data_as(L._D), b2.ctypes.data_as(L._D),
+            nb.ctypes.data_as(L._D)))
+        return {"lo": lo, "rhsInterior": ri[:nint], "rhsBoundary1": b1, "rhsBoundary2": b2, "normBoundary": nb}
+
+    # --- application (in place in the reference; returns the result here)
+    def _call(self, fn, x, gridSize, *extra):
+        x = np.asarray(x, dtype=np.float64)
+        one_d = x.ndim == 1
+        N = int(np.prod(gridSize))
+        y = np.array(x.reshape(N, -1, order="F"), order="F", copy=True)
+        check(fn(self._h, L.fptr(y), y.shape[1], L.i3(gridSize), *extra))
+        return y[:, 0] if one_d else y
+
+    def apply(self, x, gridSize):
+        return self._call(L.lib().mg_stencil_apply, x, gridSize)
+
+    def applyWithGhosts(self, x, gridSize, ghostPrev, ghostNext):
+        gp = None if ghostPrev is None else np.asfortranarray(ghostPrev, dtype=np.float64)
+        gn = None if ghostNext is None else np.asfortranarray(ghostNext, dtype=np.float64)
+        return self._call(L.lib().mg_stencil_apply_ghosted, x, gridSize,
+                          None if gp is None else L.fptr(gp), None if gn is None else L.fptr(gn))
+
+    def applyAtInteriorPoints(self, x, gridSize):
+        return self._call(L.lib().mg_stencil_apply_interior, x, gridSize)
+
+    def applyNorm(self, x, gridSize):
+        return self._call(L.lib().mg_stencil_apply_norm, x, gridSize)
+
+    def applyNormInverse(self, x, gridSize):
+        return self._call(L.lib().mg_stencil_apply_norm_inverse, x, gridSize)
+
+    def applyAndProjectOnBoundary(self, x, gridSize, faceOrientation):
+        return self._call(L.lib().mg_stencil_apply_and_project_on_boundary, x, gridSize, int(faceOrientation))
+
+    def projectOnBoundaryAndApply(self, x, gridSize, faceOrientation):
+        return self._call(L.lib().mg_stencil_project_on_boundary_and_apply, x, gridSize, int(faceOrientation))
+
+    def cleanup(self):
+        if self._h is not None and self._owned:
+            L.load().mg_stencil_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.cleanup()
+        except Exception:
+            pass
+
+
+class SolverOptions:
+    """The ``t_SolverOptions`` / ``t_SimulationFlags`` members the hot path reads, with the
+    reference's defaults (``src/SolverOptionsImpl.f90:46-136``, ``src/SimulationFlagsImpl.f90:24-44``)."""
+
+    def __init__(self, **kw):
+        self.ratioOfSpecificHeats = 1.4
+        self.viscosityOn = False
+        self.reynoldsNumberInverse = 0.0
+        self.prandtlNumberInverse = 1.0 / 0.72
+        self.powerLawExponent = 0.666
+        self.bulkViscosityRatio = 0.6
+        self.dissipationOn = False
+        self.compositeDissipation = True
+        self.dissipationAmount = 0.0
+        self.useTargetState = True
+        self.useContinuousAdjoint = False
+        self.discretizationType = "SBP 4-8"
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError(f"unknown solver option '{k}'")
+            setattr(self, k, v)
+
+    def c_struct(self):
+        return Options(self.ratioOfSpecificHeats, int(self.viscosityOn), self.reynoldsNumberInverse,
+                       self.prandtlNumberInverse, self.powerLawExponent, self.bulkViscosityRatio,
+                       int(self.dissipationOn), int(self.compositeDissipation), self.dissipationAmount,
+                       int(self.useTargetState), int(self.useContinuousAdjoint))
+
+
+class Grid:
+    """``t_Grid``: one rank's brick of a structured block.  ``procDims=(1,1,P)`` slabs only."""
+
+    def __init__(self, index, globalSize, periodicityType=(NONE, NONE, NONE), periodicLength=(0.0, 0.0, 0.0),
+                 isCurvilinear=True, procDims=(1, 1, 1), procCoords=(0, 0, 0)):
+        gs = [int(v) for v in globalSize] + [1] * (3 - len(globalSize))
+        nd = 3
+        while nd > 1 and gs[nd - 1] == 1:
+            nd -= 1
+        self.index = index
+        self.nDimensions = nd
+        self.globalSize = tuple(gs)
+        self.procDims = tuple(procDims)
+        self.procCoords = tuple(procCoords)
+        off, loc = [], []
+        for d in range(3):
+            o, n = pigeonhole(gs[d], self.procDims[d], self.procCoords[d])
+            off.append(o)
+            loc.append(n)
+        self.offset, self.localSize = tuple(off), tuple(loc)
+        self.nGridPoints = int(np.prod(loc))
+        self.periodicityType = tuple(periodicityType) + (NONE,) * (3 - len(periodicityType))
+        self.periodicLength = tuple(periodicLength) + (0.0,) * (3 - len(periodicLength))
+        self.isCurvilinear = bool(isCurvilinear)
+        h = C.c_void_p()
+        check(L.lib().mg_grid_create(index, nd, L.i3(gs), L.i3(loc), L.i3(off), L.i3(self.periodicityType),
+                                     L.d3(self.periodicLength), int(self.isCurvilinear), L.i3(self.procDims),
+                                     L.i3(self.procCoords), C.byref(h)))
+        self._h = h
+
+    def setupSpatialDiscretization(self, scheme="SBP 4-8", compositeDissipation=True, useContinuousAdjoint=False,
+                                   dissipationOn=True, perDirectionScheme=None):
+        s = list(perDirectionScheme) if perDirectionScheme else [scheme] * 3
+        s += [scheme] * (3 - len(s))
+        check(L.lib().mg_grid_setup_spatial_discretization(
+            self._h, s[0].encode(), s[1].encode(), s[2].encode(), int(dissipationOn), int(compositeDissipation),
+            int(useContinuousAdjoint)))
+
+    def operator(self, which, direction):
+        kinds = {"firstDerivative": 0, "adjointFirstDerivative": 1, "dissipation": 2, "dissipationTranspose": 3}
+        h = L.lib().mg_grid_operator(self._h, kinds[which], int(direction))
+        if not h:
+            raise L.MagudiGpuError(f"operator {which}({direction}) is not set up")
+        op = StencilOperator(C.c_void_p(h), owned=False)
+        op.direction = direction
+        return op
+
+    def _ncomp(self, field):
+        nd = self.nDimensions
+        return {G_COORDINATES: nd, G_METRICS: nd * nd, G_JACOBIAN: 1, G_NORM: 1, G_ARC_LENGTHS: nd,
+                G_TARGET_MOLLIFIER: 1, G_CONTROL_MOLLIFIER: 1}[field]
+
+    def set(self, field, a):
+        a = L.as_f(a, (self.nGridPoints, self._ncomp(field)))
+        check(L.lib().mg_grid_set(self._h, field, L.fptr(a)))
+
+    def get(self, field):
+        a = np.zeros((self.nGridPoints, self._ncomp(field)), order="F")
+        check(L.lib().mg_grid_get(self._h, field, L.fptr(a)))
+        return a
+
+    def setCoordinates(self, xyz):
+        self.set(G_COORDINATES, xyz)
+
+    def setIblank(self, iblank):
+        ib = np.ascontiguousarray(iblank, dtype=np.int32)
+        check(L.lib().mg_grid_set_iblank(self._h, ib.ctypes.data_as(L._I3)))
+
+    def update(self):
+        """``t_Grid%update``; returns True when a non-positive Jacobian exists."""
+        flag = C.c_int(0)
+        check(L.lib().mg_grid_update(self._h, C.byref(flag)))
+        return bool(flag.value)
+
+    coordinates = property(lambda s: s.get(G_COORDINATES))
+    metrics = property(lambda s: s.get(G_METRICS))
+    jacobian = property(lambda s: s.get(G_JACOBIAN))
+    norm = property(lambda s: s.get(G_NORM))
+    arcLengths = property(lambda s: s.get(G_ARC_LENGTHS))
+
+    def computeGradient(self, f):
+        f = L.as_f(np.asarray(f, dtype=np.float64).reshape(self.nGridPoints, -1, order="F"))
+        out = np.zeros((self.nGridPoints, self.nDimensions * f.shape[1]), order="F")
+        check(L.lib().mg_grid_gradient(self._h, L.fptr(f), f.shape[1], L.fptr(out)))
+        return out
+
+    def computeInnerProduct(self, f, g, weight=None):
+        f = L.as_f(np.asarray(f, dtype=np.float64).reshape(self.nGridPoints, -1, order="F"))
+        g = L.as_f(np.asarray(g, dtype=np.float64).reshape(self.nGridPoints, -1, order="F"))
+        w = None if weight is None else L.as_f(np.asarray(weight, dtype=np.float64).reshape(-1))
+        r = C.c_double(0.0)
+        check(L.lib().mg_grid_inner_product(self._h, L.fptr(f), L.fptr(g), None if w is None else L.fptr(w),
+                                            f.shape[1], C.byref(r)))
+        return r.value
+
+    def cleanup(self):
+        if self._h is not None:
+            L.load().mg_grid_destroy(self._h)
+            self._h = None
+
+
+class State:
+    """``t_State``: device-resident fields of one grid."""
+
+    def __init__(self, grid: Grid, options: SolverOptions):
+        self.grid = grid
+        self.options = options
+        self.nDimensions = grid.nDimensions
+        self.nUnknowns = grid.nDimensions + 2
+        h = C.c_void_p()
+        o = options.c_struct()
+        check(L.lib().mg_state_create(grid._h, C.byref(o), C.byref(h)))
+        self._h = h
+        self.patches = []
+
+    def _ncomp(self, field):
+        nd, nu = self.nDimensions, self.nUnknowns
+        if field in (Q_CONSERVED, Q_ADJOINT, Q_TARGET, Q_RHS):
+            return nu
+        if field in (Q_VELOCITY, Q_HEAT_FLUX):
+            return nd
+        if field == Q_STRESS_TENSOR:
+            return nd * nd
+        return 1
+
+    def set(self, field, a):
+        a = L.as_f(a, (self.grid.nGridPoints, self._ncomp(field)))
+        check(L.lib().mg_state_set(self._h, field, L.fptr(a)))
+
+    def get(self, field):
+        a = np.zeros((self.grid.nGridPoints, self._ncomp(field)), order="F")
+        check(L.lib().mg_state_get(self._h, field, L.fptr(a)))
+        return a
+
+    conservedVariables = property(lambda s: s.get(Q_CONSERVED), lambda s, v: s.set(Q_CONSERVED, v))
+    adjointVariables = property(lambda s: s.get(Q_ADJOINT), lambda s, v: s.set(Q_ADJOINT, v))
+    targetState = property(lambda s: s.get(Q_TARGET), lambda s, v: s.set(Q_TARGET, v))
+    rightHandSide = property(lambda s: s.get(Q_RHS), lambda s, v: s.set(Q_RHS, v))
+    velocity = property(lambda s: s.get(Q_VELOCITY))
+    pressure = property(lambda s: s.get(Q_PRESSURE))
+    temperature = property(lambda s: s.get(Q_TEMPERATURE))
+    specificVolume = property(lambda s: s.get(Q_SPECIFIC_VOLUME))
+    stressTensor = property(lambda s: s.get(Q_STRESS_TENSOR))
+    heatFlux = property(lambda s: s.get(Q_HEAT_FLUX))
+
+    def setTime(self, t):
+        check(L.lib().mg_state_set_time(self._h, float(t)))
+
+    def addAcousticSource(self, location, amplitude, frequency, radius, phase=0.0):
+        check(L.lib().mg_state_add_acoustic_source(self._h, L.d3(location), amplitude, frequency, radius, phase))
+
+    def update(self):
+        """``t_State%update`` (dependent variables, transport, stress tensor, heat flux)."""
+        check(L.lib().mg_state_update(self._h))
+
+    def addPatch(self, patchType, name, normalDirection, extent, inviscidPenaltyAmount=1.0,
+                 viscousPenaltyAmount=1.0):
+        p = Patch(self, patchType, name, normalDirection, extent, inviscidPenaltyAmount, viscousPenaltyAmount)
+        self.patches.append(p)
+        return p
+
+    def cleanup(self):
+        if self._h is not None:
+            L.load().mg_state_destroy(self._h)
+            self._h = None
+
+
+class Patch:
+    """``t_Patch`` family member attached to a state; ``extent`` is 1-based inclusive (bc.dat)."""
+
+    def __init__(self, state, patchType, name, normalDirection, extent, inviscidPenaltyAmount=1.0,
+                 viscousPenaltyAmount=1.0):
+        self.state = state
+        self.patchType = patchType
+        self.name = name
+        self.normalDirection = int(normalDirection)
+        self.extent = tuple(int(e) for e in extent)
+        h = C.c_void_p()
+        ext = (C.c_int * 6)(*self.extent)
+        check(L.lib().mg_patch_create(state._h, PATCH_TYPES[patchType], name.encode(), self.normalDirection, ext,
+                                      float(inviscidPenaltyAmount), float(viscousPenaltyAmount), C.byref(h)))
+        self._h = h
+        n = C.c_int(0)
+        ls = (C.c_int * 3)()
+        po = (C.c_int * 3)()
+        check(L.lib().mg_patch_num_points(h, C.byref(n), ls, po))
+        self.nPatchPoints = n.value
+        self.localSize = tuple(ls)
+        self.patchOffset = tuple(po)
+
+    def setArray(self, name, a):
+        a = L.as_f(np.asarray(a, dtype=np.float64).reshape(max(self.nPatchPoints, 0), -1, order="F"))
+        check(L.lib().mg_patch_set_array(self._h, name.encode(), a.shape[1], L.fptr(a)))
+
+    def getArray(self, name, nComp):
+        a = np.zeros((self.nPatchPoints, nComp), order="F")
+        check(L.lib().mg_patch_get_array(self._h, name.encode(), nComp, L.fptr(a)))
+        return a
+
+    def collect(self, field, name):
+        check(L.lib().mg_patch_collect(self._h, field, name.encode()))
+
+
+class Region:
+    """``t_Region`` restricted to the hot path: a list of (grid, state) pairs and ``computeRhs``."""
+
+    def __init__(self):
+        h = C.c_void_p()
+        check(L.lib().mg_region_create(C.byref(h)))
+        self._h = h
+        self.states = []
+        self.grids = []
+
+    def addState(self, state: State):
+        check(L.lib().mg_region_add_state(self._h, state._h))
+        self.states.append(state)
+        self.grids.append(state.grid)
+
+    def updatePatches(self):
+        check(L.lib().mg_region_update_patches(self._h))
+
+    def computeRhs(self, mode, timestep=0, stage=1):
+        check(L.lib().mg_region_compute_rhs(self._h, int(mode), int(timestep), int(stage)))
+
+    def setFused(self, enable=True):
+        check(L.lib().mg_region_set_fused(self._h, int(bool(enable))))
+
+    def usesFused(self, mode=FORWARD):
+        return bool(L.lib().mg_region_uses_fused(self._h, int(mode)))
+
+    def cleanup(self):
+        if self._h is not None:
+            L.load().mg_region_destroy(self._h)
+            self._h = None
+
+
+class RK4Integrator:
+    """``t_RK4Integrator``: ``substepForward`` / ``substepAdjoint`` (``src/RK4IntegratorImpl.f90``)."""
+    nStages = 4
+    norm = (1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0)
+
+    def __init__(self, region: Region):
+        self.region = region
+
+    def substepForward(self, time, timeStepSize, timestep, stage, updateStates=True):
+        t = C.c_double(time)
+        check(L.lib().mg_rk4_substep(self.region._h, FORWARD, C.byref(t), float(timeStepSize), int(timestep),
+                                     int(stage), int(updateStates)))
+        return t.value
+
+    def substepAdjoint(self, time, timeStepSize, timestep, stage):
+        t = C.c_double(time)
+        check(L.lib().mg_rk4_substep(self.region._h, ADJOINT, C.byref(t), float(timeStepSize), int(timestep),
+                                     int(stage), 0))
+        return t.value

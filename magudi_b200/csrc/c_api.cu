@@ -1,0 +1,508 @@
+// extern "C" entry points of libmagudi_gpu (declared in include/magudi_gpu.h).
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/magudi_gpu.h"
+#include "grid.h"
+#include "patches.h"
+#include "rhs_fused.h"
+#include "stencil_apply.h"
+
+namespace {
+thread_local std::string g_error;
+cudaStream_t g_stream = nullptr;
+int g_device = -1;
+int g_sms = 0;
+std::atomic<long long> g_launches{0};
+}  // namespace
+
+void mg_set_error(const std::string& msg) { g_error = msg; }
+int mg_cuda_fail(cudaError_t e, const char* file, int line) {
+  g_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + file + ":" + std::to_string(line);
+  return -2;
+}
+cudaStream_t mg_stream() { return g_stream; }
+int mg_num_sms() { return g_sms; }
+void mg_count_launches(int n) { g_launches += n; }
+
+struct mg_region {
+  std::vector<mg_state*> states;
+  int fused = 1;
+};
+
+static bool is_device_pointer(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Stage x(N, nComp) on the device (copy if it is a host array), run f(dev_in, dev_out), copy back.
+template <typename F>
+static int with_device_array(double* x, size_t count, bool needOut, F f) {
+  if (g_device < 0) MG_FAIL("libmagudi_gpu: mg_init has not been called (no CUDA device selected)");
+  const bool dev = is_device_pointer(x);
+  double *din = nullptr, *dout = nullptr;
+  const size_t bytes = count * sizeof(double);
+  if (dev) din = x;
+  else {
+    MG_CUDA(cudaMalloc(&din, bytes));
+    MG_CUDA(cudaMemcpyAsync(din, x, bytes, cudaMemcpyHostToDevice, g_stream));
+  }
+  if (needOut) MG_CUDA(cudaMalloc(&dout, bytes));
+  int rc = f(din, dout);
+  if (rc == 0) {
+    const double* src = needOut ? dout : din;
+    if (!dev || needOut) {
+      cudaError_t e = cudaMemcpyAsync(x, src, bytes, cudaMemcpyDefault, g_stream);
+      if (e != cudaSuccess) rc = mg_cuda_fail(e, __FILE__, __LINE__);
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(g_stream);
+  if (rc == 0 && e != cudaSuccess) rc = mg_cuda_fail(e, __FILE__, __LINE__);
+  if (!dev) cudaFree(din);
+  if (dout) cudaFree(dout);
+  return rc;
+}
+
+extern "C" {
+
+int mg_init(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    MG_FAIL("mg_init: no CUDA device available (libmagudi_gpu has no CPU fallback)");
+  }
+  if (device < 0 || device >= count) MG_FAIL("mg_init: invalid device index");
+  MG_CUDA(cudaSetDevice(device));
+  if (g_stream && g_device != device) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+  if (!g_stream) MG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop;
+  MG_CUDA(cudaGetDeviceProperties(&prop, device));
+  g_sms = prop.multiProcessorCount;
+  g_device = device;
+  return 0;
+}
+
+const char* mg_last_error(void) { return g_error.c_str(); }
+int mg_version(void) { return 100; }
+int mg_synchronize(void) {
+  if (g_device < 0) MG_FAIL("mg_synchronize: mg_init has not been called");
+  MG_CUDA(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+long long mg_kernel_launch_count(void) { return g_launches.load(); }
+
+// ----------------------------------------------------------------------------- stencil
+int mg_stencil_create(const char* scheme, mg_stencil** out) { return mg_stencil_create_impl(scheme, out); }
+int mg_stencil_update(mg_stencil* s, int direction, const int procDims[3], const int procCoords[3],
+                      const int periodic[3], int overlap) {
+  return mg_stencil_update_impl(s, direction, procDims, procCoords, periodic, overlap);
+}
+int mg_stencil_get_adjoint(const mg_stencil* s, mg_stencil** out) { return mg_stencil_get_adjoint_impl(s, out); }
+int mg_stencil_destroy(mg_stencil* s) {
+  if (!s) return 0;
+  if (s->d_op) cudaFree(s->d_op);
+  delete s;
+  return 0;
+}
+int mg_stencil_info(const mg_stencil* s, int info[12]) {
+  if (!s) MG_FAIL("mg_stencil_info: null handle");
+  const MgDevOp& o = s->op;
+  const int v[12] = {o.symmetryType, o.interiorWidth, o.boundaryWidth, o.boundaryDepth, o.nGhost[0], o.nGhost[1],
+                     o.periodicOffset[0], o.periodicOffset[1], o.hasDomainBoundary[0], o.hasDomainBoundary[1],
+                     o.lo, o.nInterior};
+  std::memcpy(info, v, sizeof(v));
+  return 0;
+}
+int mg_stencil_coefficients(const mg_stencil* s, double* rhsInterior, double* b1, double* b2, double* norm) {
+  if (!s) MG_FAIL("mg_stencil_coefficients: null handle");
+  const MgDevOp& o = s->op;
+  if (rhsInterior) for (int k = 0; k < o.nInterior; ++k) rhsInterior[k] = o.interior[k];
+  for (int m = 0; m < o.boundaryDepth; ++m)
+    for (int i = 0; i < o.boundaryWidth; ++i) {
+      if (b1) b1[i + o.boundaryWidth * m] = o.b1[m][i];
+      if (b2) b2[i + o.boundaryWidth * m] = o.b2[m][i];
+    }
+  if (norm) for (int m = 0; m < o.normDepth; ++m) norm[m] = o.normBoundary[m];
+  return 0;
+}
+
+static int stencil_apply_common(mg_stencil* s, double* x, int nComp, const int n[3], int interiorOnly,
+                                const double* ghostPrev, const double* ghostNext) {
+  if (!s || !x) MG_FAIL("mg_stencil_apply: null argument");
+  if (nComp <= 0 || n[0] <= 0 || n[1] <= 0 || n[2] <= 0) MG_FAIL("mg_stencil_apply: invalid sizes");
+  const size_t N = (size_t)n[0] * n[1] * n[2];
+  const size_t plane = N / n[s->direction - 1];
+  // explicit ghost buffers may be host arrays
+  double *dPrev = nullptr, *dNext = nullptr;
+  bool freePrev = false, freeNext = false;
+  auto stage = [&](const double* h, int g, double** d, bool* owned) -> int {
+    if (!h || g <= 0) return 0;
+    if (is_device_pointer(h)) { *d = const_cast<double*>(h); return 0; }
+    const size_t bytes = sizeof(double) * (size_t)g * plane * nComp;
+    MG_CUDA(cudaMalloc(d, bytes));
+    MG_CUDA(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, g_stream));
+    *owned = true;
+    return 0;
+  };
+  if (g_device < 0) MG_FAIL("libmagudi_gpu: mg_init has not been called (no CUDA device selected)");
+  MG_TRY(stage(ghostPrev, s->op.nGhost[0], &dPrev, &freePrev));
+  MG_TRY(stage(ghostNext, s->op.nGhost[1], &dNext, &freeNext));
+  int rc = with_device_array(x, N * nComp, true, [&](double* din, double* dout) -> int {
+    MG_CUDA(cudaMemcpyAsync(dout, din, N * nComp * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+    ApplyArgs a;
+    a.in = din;
+    a.out = dout;
+    a.inCompStride = a.outCompStride = N;
+    a.nComp = nComp;
+    for (int i = 0; i < 3; ++i) a.n[i] = n[i];
+    a.interiorOnly = interiorOnly;
+    a.ghostPrev = dPrev;
+    a.ghostNext = dNext;
+    return mg_apply_launch(s, a);
+  });
+  if (freePrev) cudaFree(dPrev);
+  if (freeNext) cudaFree(dNext);
+  return rc;
+}
+
+int mg_stencil_apply(mg_stencil* s, double* x, int nComp, const int gridSize[3]) {
+  if (s && s->procDim > 1) MG_FAIL("mg_stencil_apply: operator spans several ranks; use mg_stencil_apply_ghosted");
+  return stencil_apply_common(s, x, nComp, gridSize, 0, nullptr, nullptr);
+}
+int mg_stencil_apply_ghosted(mg_stencil* s, double* x, int nComp, const int gridSize[3], const double* ghostPrev,
+                             const double* ghostNext) {
+  if (s && ((s->op.nGhost[0] > 0 && !ghostPrev) || (s->op.nGhost[1] > 0 && !ghostNext)))
+    MG_FAIL("mg_stencil_apply_ghosted: missing ghost buffer");
+  return stencil_apply_common(s, x, nComp, gridSize, 0, ghostPrev, ghostNext);
+}
+int mg_stencil_apply_interior(mg_stencil* s, double* x, int nComp, const int gridSize[3]) {
+  return stencil_apply_common(s, x, nComp, gridSize, 1, nullptr, nullptr);
+}
+static int norm_common(mg_stencil* s, double* x, int nComp, const int n[3], int inverse) {
+  if (!s || !x) MG_FAIL("mg_stencil_apply_norm: null argument");
+  const size_t N = (size_t)n[0] * n[1] * n[2];
+  return with_device_array(x, N * nComp, false, [&](double* din, double*) -> int {
+    return mg_norm_launch(s, din, N, nComp, n, inverse, g_stream);
+  });
+}
+int mg_stencil_apply_norm(mg_stencil* s, double* x, int nComp, const int n[3]) { return norm_common(s, x, nComp, n, 0); }
+int mg_stencil_apply_norm_inverse(mg_stencil* s, double* x, int nComp, const int n[3]) { return norm_common(s, x, nComp, n, 1); }
+static int boundary_common(mg_stencil* s, double* x, int nComp, const int n[3], int face, int applyThenProject) {
+  if (!s || !x) MG_FAIL("mg_stencil boundary apply: null argument");
+  if (face == 0) MG_FAIL("mg_stencil boundary apply: faceOrientation must be non-zero");
+  const size_t N = (size_t)n[0] * n[1] * n[2];
+  return with_device_array(x, N * nComp, true, [&](double* din, double* dout) -> int {
+    return mg_boundary_launch(s, din, dout, N, nComp, n, face, applyThenProject, g_stream);
+  });
+}
+int mg_stencil_apply_and_project_on_boundary(mg_stencil* s, double* x, int nComp, const int n[3], int face) {
+  return boundary_common(s, x, nComp, n, face, 1);
+}
+int mg_stencil_project_on_boundary_and_apply(mg_stencil* s, double* x, int nComp, const int n[3], int face) {
+  return boundary_common(s, x, nComp, n, face, 0);
+}
+
+// -------------------------------------------------------------------------------- grid
+int mg_grid_create(int index, int nD, const int globalSize[3], const int localSize[3], const int offset[3],
+                   const int periodicityType[3], const double periodicLength[3], int isCurvilinear,
+                   const int procDims[3], const int procCoords[3], mg_grid** out) {
+  if (g_device < 0) MG_FAIL("libmagudi_gpu: mg_init has not been called (no CUDA device selected)");
+  return mg_grid_create_impl(index, nD, globalSize, localSize, offset, periodicityType, periodicLength,
+                             isCurvilinear, procDims, procCoords, out);
+}
+int mg_grid_destroy(mg_grid* g) { mg_grid_destroy_impl(g); return 0; }
+int mg_grid_setup_spatial_discretization(mg_grid* g, const char* s1, const char* s2, const char* s3,
+                                         int dissipationOn, int compositeDissipation, int useContinuousAdjoint) {
+  if (!g) MG_FAIL("mg_grid_setup_spatial_discretization: null handle");
+  const char* sch[3] = {s1 ? s1 : "SBP 4-8", s2 ? s2 : (s1 ? s1 : "SBP 4-8"), s3 ? s3 : (s1 ? s1 : "SBP 4-8")};
+  return mg_grid_setup_discretization_impl(g, sch, dissipationOn, compositeDissipation, useContinuousAdjoint);
+}
+
+static MgField* grid_field(mg_grid* g, int field, int* nComp, bool alloc) {
+  MgField* f = nullptr;
+  int nc = 0;
+  switch (field) {
+    case MG_G_COORDINATES: f = &g->coordinates; nc = g->nD; break;
+    case MG_G_METRICS: f = &g->metrics; nc = g->nD * g->nD; break;
+    case MG_G_JACOBIAN: f = &g->jacobian; nc = 1; break;
+    case MG_G_NORM: f = &g->norm; nc = 1; break;
+    case MG_G_ARC_LENGTHS: f = &g->arcLengths; nc = g->nD; break;
+    case MG_G_TARGET_MOLLIFIER: f = &g->targetMollifier; nc = 1; break;
+    case MG_G_CONTROL_MOLLIFIER: f = &g->controlMollifier; nc = 1; break;
+    default: return nullptr;
+  }
+  if (!f->p && alloc) { if (mg_field_alloc(g, nc, f) != 0) return nullptr; }
+  *nComp = nc;
+  return f->p ? f : nullptr;
+}
+
+int mg_grid_set(mg_grid* g, int field, const double* host) {
+  int nc = 0;
+  MgField* f = g ? grid_field(g, field, &nc, true) : nullptr;
+  if (!f) MG_FAIL("mg_grid_set: unknown field or null handle");
+  if (field == MG_G_COORDINATES) g->updated = false;
+  return mg_field_upload(g, f, host);
+}
+int mg_grid_get(mg_grid* g, int field, double* host) {
+  int nc = 0;
+  MgField* f = g ? grid_field(g, field, &nc, false) : nullptr;
+  if (!f) MG_FAIL("mg_grid_get: unknown or unset field");
+  return mg_field_download(g, f, host);
+}
+int mg_grid_set_iblank(mg_grid* g, const int* iblank) {
+  if (!g) MG_FAIL("mg_grid_set_iblank: null handle");
+  bool holes = false;
+  for (size_t p = 0; p < g->N; ++p) holes = holes || iblank[p] == 0;
+  if (!holes) { if (g->iblank) { cudaFree(g->iblank); g->iblank = nullptr; } return 0; }
+  if (!g->iblank) MG_CUDA(cudaMalloc(&g->iblank, g->N * sizeof(int)));
+  MG_CUDA(cudaMemcpy(g->iblank, iblank, g->N * sizeof(int), cudaMemcpyHostToDevice));
+  g->updated = false;
+  return 0;
+}
+int mg_grid_update(mg_grid* g, int* hasNegativeJacobian) {
+  if (!g) MG_FAIL("mg_grid_update: null handle");
+  return mg_grid_update_impl(g, hasNegativeJacobian);
+}
+int mg_grid_gradient(mg_grid* g, const double* f, int nComp, double* gradF) {
+  if (!g || !f || !gradF) MG_FAIL("mg_grid_gradient: null argument");
+  if (!g->updated) MG_FAIL("mg_grid_gradient: grid metrics have not been computed");
+  MgField in, out, scratch;
+  MG_TRY(mg_field_alloc(g, nComp, &in));
+  MG_TRY(mg_field_alloc(g, g->nD * nComp, &out));
+  MG_TRY(mg_field_alloc(g, g->nD * nComp, &scratch));
+  int rc = mg_field_upload(g, &in, f);
+  if (rc == 0) rc = mg_grid_gradient_dev(g, in.comp(0), in.compStride, nComp, &out, &scratch);
+  if (rc == 0) rc = mg_field_download(g, &out, gradF);
+  mg_field_free(&in);
+  mg_field_free(&out);
+  mg_field_free(&scratch);
+  return rc;
+}
+int mg_grid_inner_product(mg_grid* g, const double* f, const double* gv, const double* weight, int nComp,
+                          double* result) {
+  if (!g || !f || !gv || !result) MG_FAIL("mg_grid_inner_product: null argument");
+  MgField a, b, w;
+  MG_TRY(mg_field_alloc(g, nComp, &a));
+  MG_TRY(mg_field_alloc(g, nComp, &b));
+  int rc = mg_field_upload(g, &a, f);
+  if (rc == 0) rc = mg_field_upload(g, &b, gv);
+  if (rc == 0 && weight) {
+    rc = mg_field_alloc(g, 1, &w);
+    if (rc == 0) rc = mg_field_upload(g, &w, weight);
+  }
+  if (rc == 0)
+    rc = mg_grid_inner_product_dev(g, a.comp(0), b.comp(0), weight ? w.comp(0) : nullptr, a.compStride, nComp, result);
+  mg_field_free(&a);
+  mg_field_free(&b);
+  mg_field_free(&w);
+  return rc;
+}
+mg_stencil* mg_grid_operator(mg_grid* g, int which, int direction) {
+  if (!g || direction < 1 || direction > 3) return nullptr;
+  switch (which) {
+    case 0: return g->firstDerivative[direction - 1];
+    case 1: return g->adjointFirstDerivative[direction - 1];
+    case 2: return g->dissipation[direction - 1];
+    case 3: return g->dissipationTranspose[direction - 1];
+  }
+  return nullptr;
+}
+
+// ------------------------------------------------------------------------------- state
+static MgField* state_field(mg_state* s, int field) {
+  switch (field) {
+    case MG_Q_CONSERVED: return &s->Q[s->cur];
+    case MG_Q_ADJOINT: return &s->W[s->curW];
+    case MG_Q_TARGET: return &s->target;
+    case MG_Q_RHS: return &s->rhs;
+    case MG_Q_SPECIFIC_VOLUME: return &s->specificVolume;
+    case MG_Q_VELOCITY: return &s->velocity;
+    case MG_Q_PRESSURE: return &s->pressure;
+    case MG_Q_TEMPERATURE: return &s->temperature;
+    case MG_Q_DYNAMIC_VISCOSITY: return &s->mu;
+    case MG_Q_SECOND_VISCOSITY: return &s->lambda;
+    case MG_Q_THERMAL_DIFFUSIVITY: return &s->kappa;
+    case MG_Q_STRESS_TENSOR: return &s->stressTensor;
+    case MG_Q_HEAT_FLUX: return &s->heatFlux;
+  }
+  return nullptr;
+}
+
+int mg_state_create(mg_grid* g, const mg_options* o, mg_state** out) {
+  if (!g || !o || !out) MG_FAIL("mg_state_create: null argument");
+  mg_options_t t;
+  t.ratioOfSpecificHeats = o->ratioOfSpecificHeats;
+  t.viscosityOn = o->viscosityOn;
+  t.reynoldsNumberInverse = o->reynoldsNumberInverse;
+  t.prandtlNumberInverse = o->prandtlNumberInverse;
+  t.powerLawExponent = o->powerLawExponent;
+  t.bulkViscosityRatio = o->bulkViscosityRatio;
+  t.dissipationOn = o->dissipationOn;
+  t.compositeDissipation = o->compositeDissipation;
+  t.dissipationAmount = o->dissipationAmount;
+  t.useTargetState = o->useTargetState;
+  t.useContinuousAdjoint = o->useContinuousAdjoint;
+  if (!(t.ratioOfSpecificHeats > 1.0)) MG_FAIL("mg_state_create: ratio of specific heats must exceed 1");
+  if (t.viscosityOn && !(t.reynoldsNumberInverse > 0.0)) MG_FAIL("mg_state_create: viscous terms need a positive Reynolds number");
+  if (t.dissipationOn != g->dissipationOn || (t.dissipationOn && t.compositeDissipation != g->compositeDissipation))
+    MG_FAIL("mg_state_create: dissipation flags differ from the grid's spatial discretization");
+  return mg_state_create_impl(g, &t, out);
+}
+int mg_state_destroy(mg_state* s) {
+  if (!s) return 0;
+  for (mg_patch* p : s->patches) mg_patch_destroy_impl(p);
+  mg_state_destroy_impl(s);
+  return 0;
+}
+int mg_state_set(mg_state* s, int field, const double* host) {
+  MgField* f = s ? state_field(s, field) : nullptr;
+  if (!f || !f->p) MG_FAIL("mg_state_set: unknown or unallocated field");
+  if (field == MG_Q_CONSERVED) s->dependentValid = false;
+  if (field == MG_Q_TARGET)
+    for (mg_patch* p : s->patches) p->AplusReady = false;
+  return mg_field_upload(s->grid, f, host);
+}
+int mg_state_get(mg_state* s, int field, double* host) {
+  MgField* f = s ? state_field(s, field) : nullptr;
+  if (!f || !f->p) MG_FAIL("mg_state_get: unknown or unallocated field");
+  return mg_field_download(s->grid, f, host);
+}
+int mg_state_set_time(mg_state* s, double time) {
+  if (!s) MG_FAIL("mg_state_set_time: null handle");
+  s->time = time;
+  return 0;
+}
+int mg_state_add_acoustic_source(mg_state* s, const double location[3], double amplitude, double frequency,
+                                 double radius, double phase) {
+  if (!s) MG_FAIL("mg_state_add_acoustic_source: null handle");
+  mg_state::Source src;
+  for (int i = 0; i < 3; ++i) src.loc[i] = location[i];
+  src.amplitude = amplitude;
+  src.angularFrequency = 2.0 * (4.0 * atan(1.0)) * frequency;
+  src.gaussianFactor = 9.0 / (2.0 * radius * radius);
+  src.phase = phase;
+  s->acousticSources.push_back(src);
+  return 0;
+}
+int mg_state_update(mg_state* s) {
+  if (!s) MG_FAIL("mg_state_update: null handle");
+  if (!s->grid->updated) MG_FAIL("mg_state_update: grid metrics have not been computed");
+  return mg_state_update_impl(s, nullptr);
+}
+
+// ------------------------------------------------------------------------------- patch
+int mg_patch_create(mg_state* s, int type, const char* name, int normalDirection, const int extent[6],
+                    double inviscidPenaltyAmount, double viscousPenaltyAmount, mg_patch** out) {
+  if (!s || !out) MG_FAIL("mg_patch_create: null argument");
+  MG_TRY(mg_patch_create_impl(s, type, name, normalDirection, extent, out));
+  mg_patch* p = *out;
+  const int ad = std::abs(normalDirection);
+  if (ad >= 1 && ad <= s->nD && s->grid->firstDerivative[ad - 1]) {
+    const double h = s->grid->firstDerivative[ad - 1]->op.normBoundary[0];
+    const double sgn = normalDirection > 0 ? 1.0 : -1.0;
+    p->inviscidPenaltyAmount = sgn * std::fabs(inviscidPenaltyAmount) / h;
+    if (type == MG_PATCH_ISOTHERMAL_WALL)   // src/IsothermalWallImpl.f90:61-72: unsigned, times 1/Re
+      p->viscousPenaltyAmount = s->opt.viscosityOn ? viscousPenaltyAmount / h * s->opt.reynoldsNumberInverse : 0.0;
+    else
+      p->viscousPenaltyAmount = s->opt.viscosityOn ? sgn * std::fabs(viscousPenaltyAmount) / h : 0.0;
+  }
+  return 0;
+}
+int mg_patch_num_points(const mg_patch* p, int* n, int localSize[3], int patchOffset[3]) {
+  if (!p) MG_FAIL("mg_patch_num_points: null handle");
+  if (n) *n = p->nPatchPoints;
+  for (int i = 0; i < 3; ++i) {
+    if (localSize) localSize[i] = p->localSize[i];
+    if (patchOffset) patchOffset[i] = p->patchOffset[i];
+  }
+  return 0;
+}
+int mg_patch_set_array(mg_patch* p, const char* name, int nComp, const double* host) {
+  if (!p || !name || !host) MG_FAIL("mg_patch_set_array: null argument");
+  return mg_patch_set_array_impl(p, name, nComp, host);
+}
+int mg_patch_get_array(mg_patch* p, const char* name, int nComp, double* host) {
+  if (!p || !name || !host) MG_FAIL("mg_patch_get_array: null argument");
+  return mg_patch_get_array_impl(p, name, nComp, host);
+}
+int mg_patch_collect(mg_patch* p, int field, const char* name) {
+  if (!p || !name) MG_FAIL("mg_patch_collect: null argument");
+  MgField* f = state_field(p->state, field);
+  int nc = 0;
+  if (!f) f = grid_field(p->state->grid, field, &nc, false);
+  if (!f || !f->p) MG_FAIL("mg_patch_collect: unknown or unallocated field");
+  return mg_patch_collect_impl(p, f, f->nComp, name);
+}
+
+// ------------------------------------------------------------------------------ region
+int mg_region_create(mg_region** out) { *out = new mg_region(); return 0; }
+int mg_region_destroy(mg_region* r) { delete r; return 0; }
+int mg_region_add_state(mg_region* r, mg_state* s) {
+  if (!r || !s) MG_FAIL("mg_region_add_state: null argument");
+  r->states.push_back(s);
+  return 0;
+}
+int mg_region_update_patches(mg_region* r) {
+  if (!r) MG_FAIL("mg_region_update_patches: null handle");
+  for (mg_state* s : r->states) MG_TRY(mg_patches_update_impl(s));
+  return 0;
+}
+int mg_region_set_fused(mg_region* r, int enable) { if (!r) MG_FAIL("null region"); r->fused = enable; return 0; }
+int mg_region_uses_fused(mg_region* r, int mode) {
+  if (!r) return 0;
+  if (!r->fused) return 0;
+  for (mg_state* s : r->states) if (!mg_fused_supported(s, mode)) return 0;
+  return 1;
+}
+int mg_region_compute_rhs(mg_region* r, int mode, int timestep, int stage) {
+  (void)timestep; (void)stage;
+  if (!r) MG_FAIL("mg_region_compute_rhs: null handle");
+  for (mg_state* s : r->states) MG_TRY(mg_state_compute_rhs_impl(s, mode));
+  return 0;
+}
+int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep, int stage, int updateStates) {
+  if (!r || !time) MG_FAIL("mg_rk4_substep: null argument");
+  double t = *time;
+  for (mg_state* s : r->states) {
+    t = *time;
+    MG_TRY(mg_rk4_substep_impl(s, mode, &t, dt, timestep, stage));
+    if (updateStates && mode == MG_FORWARD) MG_TRY(mg_state_update_impl(s, nullptr));
+  }
+  *time = t;
+  return 0;
+}
+
+int mg_halo_pack(mg_grid* g, void* owner, int field, int side, int width, double* buf) {
+  if (!g || !buf) MG_FAIL("mg_halo_pack: null argument");
+  int nc = 0;
+  MgField* f = field >= 100 ? grid_field(g, field, &nc, false) : state_field((mg_state*)owner, field);
+  if (!f || !f->p) MG_FAIL("mg_halo_pack: unknown field");
+  if (width > g->gk || width > g->localSize[2]) MG_FAIL("mg_halo_pack: width exceeds ghost capacity");
+  const size_t chunk = g->plane * (size_t)width;
+  for (int c = 0; c < f->nComp; ++c) {
+    const double* src = f->comp(c) + (side == 0 ? 0 : g->plane * (size_t)(g->localSize[2] - width));
+    MG_CUDA(cudaMemcpyAsync(buf + chunk * c, src, chunk * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+  }
+  MG_CUDA(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+int mg_halo_unpack(mg_grid* g, void* owner, int field, int side, int width, const double* buf) {
+  if (!g || !buf) MG_FAIL("mg_halo_unpack: null argument");
+  int nc = 0;
+  MgField* f = field >= 100 ? grid_field(g, field, &nc, false) : state_field((mg_state*)owner, field);
+  if (!f || !f->p) MG_FAIL("mg_halo_unpack: unknown field");
+  if (width > g->gk) MG_FAIL("mg_halo_unpack: width exceeds ghost capacity");
+  const size_t chunk = g->plane * (size_t)width;
+  for (int c = 0; c < f->nComp; ++c) {
+    double* dst = f->comp(c) + (side == 0 ? -(ptrdiff_t)chunk : (ptrdiff_t)(g->plane * (size_t)g->localSize[2]));
+    MG_CUDA(cudaMemcpyAsync(dst, buf + chunk * c, chunk * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+  }
+  MG_CUDA(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,314 @@
+// Pointwise gas dynamics shared by the general and the fused RHS kernels: the device-function
+// counterpart of CNSHelper (reference: src/CNSHelperImpl.f90).  Everything is templated on the
+// number of dimensions ND (NU = ND + 2 unknowns) and operates on registers.
+#pragma once
+#include <cuda_runtime.h>
+
+struct PhysParams {
+  double gamma;
+  double ReInv, PrInv, powerLaw, bulkRatio;
+  int viscous;
+};
+
+template <int ND>
+struct Prim {          // dependent variables at one point
+  double v;            // specific volume
+  double u[ND];
+  double p, T;
+};
+
+// computeDependentVariables (reference :3-87)
+template <int ND>
+__device__ __forceinline__ void dependent(const double* Q, double gamma, Prim<ND>& s) {
+  s.v = 1.0 / Q[0];
+  double usq = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    s.u[i] = s.v * Q[i + 1];
+    usq = (i == 0) ? s.u[i] * s.u[i] : usq + s.u[i] * s.u[i];
+  }
+  s.p = (gamma - 1.0) * (Q[ND + 1] - 0.5 * Q[0] * usq);
+  s.T = gamma * s.p / (gamma - 1.0) * s.v;
+}
+
+// computeTransportVariables (reference :89-177)
+__device__ __forceinline__ void transport(double T, const PhysParams& pp, double& mu, double& lam, double& kap) {
+  if (pp.powerLaw <= 0.0) {
+    mu = pp.ReInv;
+    lam = (pp.bulkRatio - 2.0 / 3.0) * pp.ReInv;
+    kap = pp.ReInv * pp.PrInv;
+  } else {
+    mu = pow((pp.gamma - 1.0) * T, pp.powerLaw) * pp.ReInv;
+    lam = (pp.bulkRatio - 2.0 / 3.0) * mu;
+    kap = mu * pp.PrInv;
+  }
+}
+
+// computeStressTensor, in-place form (reference :412-452).  g[j + ND*c] = d u_c / d x_j.
+template <int ND>
+__device__ __forceinline__ void stress_from_gradient(const double* g, double mu, double lam, double* s) {
+  if (ND == 1) {
+    s[0] = (2.0 * mu + lam) * g[0];
+  } else if (ND == 2) {
+    const double div = lam * (g[0] + g[3]);
+    s[0] = 2.0 * mu * g[0] + div;
+    s[1] = mu * (g[1] + g[2]);
+    s[2] = s[1];
+    s[3] = 2.0 * mu * g[3] + div;
+  } else {
+    const double div = lam * (g[0] + g[4] + g[8]);
+    s[0] = 2.0 * mu * g[0] + div;
+    s[1] = mu * (g[1] + g[3]);
+    s[2] = mu * (g[2] + g[6]);
+    s[3] = s[1];
+    s[4] = 2.0 * mu * g[4] + div;
+    s[5] = mu * (g[5] + g[7]);
+    s[6] = s[2];
+    s[7] = s[5];
+    s[8] = 2.0 * mu * g[8] + div;
+  }
+}
+
+// Cartesian total flux in direction l: inviscid (reference :563-619) minus viscous (:621-689).
+// tau[l + ND*c] is the stress tensor in the reference layout, q the heat flux.
+template <int ND>
+__device__ __forceinline__ void cartesian_flux(int l, const double* Q, const Prim<ND>& s, bool viscous,
+                                               const double* tau, const double* q, double* F, double* Fv) {
+  F[0] = Q[l + 1];
+#pragma unroll
+  for (int c = 0; c < ND; ++c) {
+    if (c == l) F[c + 1] = Q[l + 1] * s.u[l] + s.p;
+    else {
+      const int lo = c < l ? c : l, hi = c < l ? l : c;
+      F[c + 1] = Q[lo + 1] * s.u[hi];
+    }
+  }
+  F[ND + 1] = s.u[l] * (Q[ND + 1] + s.p);
+  if (viscous) {
+    double acc = 0.0;
+    Fv[0] = 0.0;
+#pragma unroll
+    for (int c = 0; c < ND; ++c) {
+      const double t = tau[l + ND * c];
+      Fv[c + 1] = t;
+      acc = (c == 0) ? s.u[c] * t : acc + s.u[c] * t;
+    }
+    Fv[ND + 1] = acc - q[l];
+#pragma unroll
+    for (int c = 0; c < ND + 2; ++c) F[c] = F[c] - Fv[c];
+  }
+}
+
+// y += A^T x with A = Jacobian of the inviscid flux along metrics m (reference :984-1444), minus
+// (if viscous) the first-partial viscous Jacobian (:2344-2600).  x, y have NU entries.
+template <int ND>
+__device__ __forceinline__ void add_flux_jacobian_transpose(const double* Q, const Prim<ND>& s, const double* m,
+                                                            double gamma, bool viscous, double powerLaw,
+                                                            const double* tau, const double* q, const double* x,
+                                                            double* y, double scale = 1.0) {
+  constexpr int NU = ND + 2;
+  double A[NU][NU];
+  double uh = 0.0, usq = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    uh = (i == 0) ? m[0] * s.u[0] : uh + m[i] * s.u[i];
+    usq = (i == 0) ? s.u[0] * s.u[0] : usq + s.u[i] * s.u[i];
+  }
+  const double phi2 = 0.5 * (gamma - 1.0) * usq;
+  A[0][0] = 0.0;
+#pragma unroll
+  for (int a = 0; a < ND; ++a) A[a + 1][0] = phi2 * m[a] - uh * s.u[a];
+  A[NU - 1][0] = uh * ((gamma - 2.0) / (gamma - 1.0) * phi2 - s.T);
+#pragma unroll
+  for (int b = 0; b < ND; ++b) {
+    A[0][b + 1] = m[b];
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+      if (a == b) A[a + 1][b + 1] = uh - (gamma - 2.0) * s.u[a] * m[a];
+      else A[a + 1][b + 1] = s.u[a] * m[b] - (gamma - 1.0) * s.u[b] * m[a];
+    }
+    A[NU - 1][b + 1] = (s.T + phi2 / (gamma - 1.0)) * m[b] - (gamma - 1.0) * uh * s.u[b];
+  }
+  A[0][NU - 1] = 0.0;
+#pragma unroll
+  for (int a = 0; a < ND; ++a) A[a + 1][NU - 1] = (gamma - 1.0) * m[a];
+  A[NU - 1][NU - 1] = gamma * uh;
+  if (viscous) {
+    double cst[ND];
+    double chf = 0.0, ucst = 0.0;
+#pragma unroll
+    for (int c = 0; c < ND; ++c) {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = 0; l < ND; ++l) acc = (l == 0) ? m[0] * tau[0 + ND * c] : acc + m[l] * tau[l + ND * c];
+      cst[c] = acc;
+    }
+#pragma unroll
+    for (int l = 0; l < ND; ++l) chf = (l == 0) ? m[0] * q[0] : chf + m[l] * q[l];
+#pragma unroll
+    for (int c = 0; c < ND; ++c) ucst = (c == 0) ? s.u[0] * cst[0] : ucst + s.u[c] * cst[c];
+    const double temp1 = ucst - chf;
+    double temp2 = powerLaw * gamma * s.v / s.T * (phi2 / (gamma - 1.0) - s.T / gamma);
+#pragma unroll
+    for (int c = 0; c < ND; ++c) A[c + 1][0] -= temp2 * cst[c];
+    A[NU - 1][0] -= temp2 * temp1 - s.v * ucst;
+#pragma unroll
+    for (int b = 0; b < ND; ++b) {
+      temp2 = -powerLaw * gamma * s.v / s.T * s.u[b];
+#pragma unroll
+      for (int c = 0; c < ND; ++c) A[c + 1][b + 1] -= temp2 * cst[c];
+      A[NU - 1][b + 1] -= temp2 * temp1 + s.v * cst[b];
+    }
+    temp2 = powerLaw * gamma * s.v / s.T;
+#pragma unroll
+    for (int c = 0; c < ND; ++c) A[c + 1][NU - 1] -= temp2 * cst[c];
+    A[NU - 1][NU - 1] -= temp2 * temp1;
+  }
+#pragma unroll
+  for (int j = 0; j < NU; ++j) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NU; ++i) acc += A[i][j] * x[i];
+    y[j] += scale * acc;
+  }
+}
+
+// y += B^T x with B the second-partial viscous Jacobian for metric rows m1 (first direction) and m2
+// (second direction), already times the inverse Jacobian (reference :2602-2756). x, y: ND+1 entries.
+template <int ND>
+__device__ __forceinline__ void add_second_partial_transpose(const double* u, double mu, double lam, double kap,
+                                                             double jac, const double* m1, const double* m2,
+                                                             const double* x, double* y, double scale = 1.0) {
+  double temp1 = 0.0, d1 = 0.0, d2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    temp1 = (i == 0) ? m1[0] * m2[0] : temp1 + m1[i] * m2[i];
+    d2 = (i == 0) ? m2[0] * u[0] : d2 + m2[i] * u[i];
+    d1 = (i == 0) ? m1[0] * u[0] : d1 + m1[i] * u[i];
+  }
+  const double temp2 = mu * d2, temp3 = lam * d1;
+#pragma unroll
+  for (int b = 0; b < ND; ++b) {
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+      const double Bab = (a == b) ? mu * temp1 + (mu + lam) * m1[a] * m2[a]
+                                  : mu * m1[b] * m2[a] + lam * m1[a] * m2[b];
+      acc += jac * Bab * x[a];
+    }
+    const double Blast = mu * temp1 * u[b] + m1[b] * temp2 + m2[b] * temp3;
+    acc += jac * Blast * x[ND];
+    y[b] += scale * acc;
+  }
+  y[ND] += scale * (jac * (kap * temp1) * x[ND]);
+}
+
+// Incoming part of the inviscid flux Jacobian, A+ = R max/min(Lambda,0) L (reference :1446-2342).
+template <int ND>
+__device__ void incoming_jacobian(const double* Q, const double* m, double gamma, int incomingDirection,
+                                  double (*A)[ND + 2]) {
+  constexpr int NU = ND + 2;
+  Prim<ND> s;
+  // the reference recomputes T as gamma*(v*rhoE - |u|^2/2) here (no pressure intermediate)
+  s.v = 1.0 / Q[0];
+  double usq = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    s.u[i] = s.v * Q[i + 1];
+    usq = (i == 0) ? s.u[i] * s.u[i] : usq + s.u[i] * s.u[i];
+  }
+  s.T = gamma * (s.v * Q[ND + 1] - 0.5 * usq);
+  double arc = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) arc = (i == 0) ? m[0] * m[0] : arc + m[i] * m[i];
+  arc = (ND == 1) ? fabs(m[0]) : sqrt(arc);
+  double n[ND];
+  double uh = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    n[i] = m[i] / arc;
+    uh = (i == 0) ? n[0] * s.u[0] : uh + n[i] * s.u[i];
+  }
+  const double c = sqrt((gamma - 1.0) * s.T);
+  const double phi2 = 0.5 * (gamma - 1.0) * usq;
+  const double g1 = gamma - 1.0;
+  const double rho = Q[0], v = s.v, T = s.T;
+  double ev[NU];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) ev[i] = uh;
+  ev[ND] = uh + c;
+  ev[ND + 1] = uh - c;
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+    ev[i] = arc * ev[i];
+    if (incomingDirection * ev[i] < 0.0) ev[i] = 0.0;
+  }
+  double R[NU][NU], L[NU][NU];
+  const double* u = s.u;
+  if (ND == 1) {
+    R[0][0] = 1.0; R[1][0] = u[0]; R[2][0] = phi2 / g1;
+    R[0][1] = 1.0; R[1][1] = u[0] + n[0] * c; R[2][1] = T + phi2 / g1 + c * uh;
+    R[0][2] = 1.0; R[1][2] = u[0] - n[0] * c; R[2][2] = T + phi2 / g1 - c * uh;
+    L[0][0] = 1.0 - phi2 / (c * c);
+    L[1][0] = 0.5 * (phi2 / (c * c) - uh / c);
+    L[2][0] = 0.5 * (phi2 / (c * c) + uh / c);
+    L[0][1] = u[0] / T;
+    L[1][1] = -0.5 * (u[0] / T - n[0] / c);
+    L[2][1] = -0.5 * (u[0] / T + n[0] / c);
+    L[0][2] = -1.0 / T; L[1][2] = 0.5 / T; L[2][2] = 0.5 / T;
+  } else if (ND == 2) {
+    const double n1 = n[0], n2 = n[ND > 1 ? 1 : 0], u1 = u[0], u2 = u[ND > 1 ? 1 : 0];
+    R[0][0] = 1.0; R[1][0] = u1; R[2][0] = u2; R[3 % NU][0] = phi2 / g1;
+    R[0][1] = 0.0; R[1][1] = n2 * rho; R[2][1] = -n1 * rho; R[3 % NU][1] = rho * (n2 * u1 - n1 * u2);
+    R[0][2] = 1.0; R[1][2] = u1 + n1 * c; R[2][2] = u2 + n2 * c; R[3 % NU][2] = T + phi2 / g1 + c * uh;
+    R[0][3 % NU] = 1.0; R[1][3 % NU] = u1 - n1 * c; R[2][3 % NU] = u2 - n2 * c;
+    R[3 % NU][3 % NU] = T + phi2 / g1 - c * uh;
+    L[0][0] = 1.0 - phi2 / (c * c);
+    L[1][0] = -v * (n2 * u1 - n1 * u2);
+    L[2][0] = 0.5 * (phi2 / (c * c) - uh / c);
+    L[3 % NU][0] = 0.5 * (phi2 / (c * c) + uh / c);
+    L[0][1] = u1 / T; L[1][1] = v * n2;
+    L[2][1] = -0.5 * (u1 / T - n1 / c);
+    L[3 % NU][1] = -0.5 * (u1 / T + n1 / c);
+    L[0][2] = u2 / T; L[1][2] = -v * n1;
+    L[2][2] = -0.5 * (u2 / T - n2 / c);
+    L[3 % NU][2] = -0.5 * (u2 / T + n2 / c);
+    L[0][3 % NU] = -1.0 / T; L[1][3 % NU] = 0.0; L[2][3 % NU] = 0.5 / T; L[3 % NU][3 % NU] = 0.5 / T;
+  } else {
+    constexpr int I3 = 3 % NU, I4 = 4 % NU;
+    const double n1 = n[0], n2 = n[1 % ND], n3 = n[2 % ND];
+    const double u1 = u[0], u2 = u[1 % ND], u3 = u[2 % ND];
+    R[0][0] = n1; R[1][0] = n1 * u1; R[2][0] = n1 * u2 + rho * n3; R[I3][0] = n1 * u3 - rho * n2;
+    R[I4][0] = rho * (n3 * u2 - n2 * u3) + phi2 / g1 * n1;
+    R[0][1] = n2; R[1][1] = n2 * u1 - rho * n3; R[2][1] = n2 * u2; R[I3][1] = n2 * u3 + rho * n1;
+    R[I4][1] = rho * (n1 * u3 - n3 * u1) + phi2 / g1 * n2;
+    R[0][2] = n3; R[1][2] = n3 * u1 + rho * n2; R[2][2] = n3 * u2 - rho * n1; R[I3][2] = n3 * u3;
+    R[I4][2] = rho * (n2 * u1 - n1 * u2) + phi2 / g1 * n3;
+    R[0][I3] = 1.0; R[1][I3] = u1 + n1 * c; R[2][I3] = u2 + n2 * c; R[I3][I3] = u3 + n3 * c;
+    R[I4][I3] = T + phi2 / g1 + c * uh;
+    R[0][I4] = 1.0; R[1][I4] = u1 - n1 * c; R[2][I4] = u2 - n2 * c; R[I3][I4] = u3 - n3 * c;
+    R[I4][I4] = T + phi2 / g1 - c * uh;
+    const double w = 1.0 - phi2 / (c * c);
+    L[0][0] = n1 * w - v * (n3 * u2 - n2 * u3);
+    L[1][0] = n2 * w - v * (n1 * u3 - n3 * u1);
+    L[2][0] = n3 * w - v * (n2 * u1 - n1 * u2);
+    L[I3][0] = 0.5 * (phi2 / (c * c) - uh / c);
+    L[I4][0] = 0.5 * (phi2 / (c * c) + uh / c);
+    L[0][1] = n1 * u1 / T; L[1][1] = n2 * u1 / T - v * n3; L[2][1] = n3 * u1 / T + v * n2;
+    L[I3][1] = -0.5 * (u1 / T - n1 / c); L[I4][1] = -0.5 * (u1 / T + n1 / c);
+    L[0][2] = n1 * u2 / T + v * n3; L[1][2] = n2 * u2 / T; L[2][2] = n3 * u2 / T - v * n1;
+    L[I3][2] = -0.5 * (u2 / T - n2 / c); L[I4][2] = -0.5 * (u2 / T + n2 / c);
+    L[0][I3] = n1 * u3 / T - v * n2; L[1][I3] = n2 * u3 / T + v * n1; L[2][I3] = n3 * u3 / T;
+    L[I3][I3] = -0.5 * (u3 / T - n3 / c); L[I4][I3] = -0.5 * (u3 / T + n3 / c);
+    L[0][I4] = -n1 / T; L[1][I4] = -n2 / T; L[2][I4] = -n3 / T; L[I3][I4] = 0.5 / T; L[I4][I4] = 0.5 / T;
+  }
+#pragma unroll
+  for (int j = 0; j < NU; ++j)
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < NU; ++k) acc += R[i][k] * ev[k] * L[k][j];
+      A[i][j] = acc;
+    }
+}

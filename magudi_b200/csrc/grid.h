@@ -1,0 +1,61 @@
+// Internal grid / state / region interfaces (host side).
+#pragma once
+#include "mg_common.h"
+#include "cns_device.cuh"
+
+int mg_grid_create_impl(int index, int nD, const int globalSize[3], const int localSize[3], const int offset[3],
+                        const int periodicityType[3], const double periodicLength[3], int isCurvilinear,
+                        const int procDims[3], const int procCoords[3], mg_grid** out);
+void mg_grid_destroy_impl(mg_grid* g);
+int mg_grid_setup_discretization_impl(mg_grid* g, const char* const schemes[3], int dissipationOn,
+                                      int compositeDissipation, int useContinuousAdjoint);
+int mg_grid_update_impl(mg_grid* g, int* hasNegativeJacobian);
+int mg_grid_apply(mg_grid* g, mg_stencil* op, const double* in, size_t inCs, double* out, size_t outCs,
+                  int nComp);
+int mg_grid_gradient_dev(mg_grid* g, const double* f, size_t fCs, int nComp, MgField* out, MgField* scratch);
+int mg_grid_inner_product_dev(mg_grid* g, const double* f, const double* gg, const double* weight, size_t cs,
+                              int nComp, double* result);
+
+struct mg_patch;
+
+struct mg_state {
+  mg_grid* grid = nullptr;
+  mg_options_t opt;
+  int nD = 3, nU = 5;
+  MgField Q[2];                 // conserved variables, double-buffered (fused RK writes the other one)
+  int cur = 0;
+  MgField W[2];                 // adjoint variables
+  int curW = 0;
+  MgField target, rhs;
+  MgField specificVolume, velocity, pressure, temperature, mu, lambda, kappa, stressTensor, heatFlux;
+  MgField rk1, rk2;             // RK4 buffers (reference RK4IntegratorImpl.f90:32-35)
+  MgField viscFluxCart;         // Cartesian viscous fluxes (nU*nD), kept only when a patch needs them
+  bool keepViscousFluxes = false;
+  double time = 0.0, timeProgressive = 0.0, adjointForcingFactor = 1.0;
+  struct Source { double loc[3], amplitude, angularFrequency, gaussianFactor, phase; };
+  std::vector<Source> acousticSources;
+  std::vector<mg_patch*> patches;
+  bool dependentValid = false;
+  PhysParams phys() const {
+    PhysParams p;
+    p.gamma = opt.ratioOfSpecificHeats;
+    p.ReInv = opt.reynoldsNumberInverse;
+    p.PrInv = opt.prandtlNumberInverse;
+    p.powerLaw = opt.powerLawExponent;
+    p.bulkRatio = opt.bulkViscosityRatio;
+    p.viscous = opt.viscosityOn;
+    return p;
+  }
+};
+
+int mg_state_create_impl(mg_grid* g, const mg_options_t* opt, mg_state** out);
+void mg_state_destroy_impl(mg_state* s);
+int mg_state_update_impl(mg_state* s, const MgField* Qoverride);
+int mg_state_rhs_forward_general(mg_state* s);
+int mg_state_rhs_adjoint_general(mg_state* s);
+int mg_state_compute_rhs_impl(mg_state* s, int mode);
+int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int timestep, int stage);
+int mg_patches_apply(mg_state* s, int mode);
+int mg_patches_collect_viscous(mg_state* s);
+int mg_patches_farfield_adjoint_sources(mg_state* s, MgField* temp1);
+bool mg_patches_have_farfield(const mg_state* s);

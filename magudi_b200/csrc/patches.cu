@@ -1,0 +1,651 @@
+// SAT penalty / sponge / forcing patches on the device (t_Patch family).
+// Reference: src/PatchImpl.f90:3-151 (extents), src/FarFieldPatchImpl.f90:93-286,
+// src/RhsHelperImpl.f90:89-250 (viscous far-field adjoint sources), src/SpongePatchImpl.f90:65-165,
+// src/ImpenetrableWallImpl.f90:60-207, src/IsothermalWallImpl.f90:103-337,
+// src/CostTargetPatchImpl.f90:72-136, src/ActuatorPatchImpl.f90:108-181.
+//
+// One thread per patch point; patch points are numbered in the patch-local Fortran order of the
+// reference (i fastest inside the part of the patch owned by this rank).
+#include <cstring>
+
+#include "grid.h"
+#include "patches.h"
+
+namespace {
+
+inline unsigned nblocks(size_t n) { return (unsigned)((n + 127) / 128); }
+
+struct PatchGeom {
+  int lo[3], sz[3];      // local 0-based start inside the rank's brick, local patch extents
+  int nx, ny;
+  int n;
+  __device__ size_t gridIndex(int q) const {
+    const int i = q % sz[0], j = (q / sz[0]) % sz[1], k = q / (sz[0] * sz[1]);
+    return (size_t)(lo[0] + i) + (size_t)nx * ((size_t)(lo[1] + j) + (size_t)ny * (size_t)(lo[2] + k));
+  }
+};
+
+struct FFArgs {
+  PatchGeom g;
+  const double *Q, *W, *target, *m, *jac, *v, *u, *T, *tau, *q;
+  const int* iblank;
+  double* rhs;
+  const double* Aplus;          // (NU*NU) per patch point, row-major A[i][j], point fastest
+  const double *Fv, *FvTarget;  // (NU*ND) per patch point: component c + NU*l, point fastest
+  size_t csQ, csW, cs;
+  int dir, mode, viscous, continuousAdjoint;
+  double sigmaI, sigmaV, gamma, powerLaw;
+};
+
+template <int ND>
+__global__ void k_farfield_setup(PatchGeom g, const double* target, size_t cs, const double* m, size_t csm,
+                                 int dir, double gamma, int incoming, double* Aplus) {
+  constexpr int NU = ND + 2;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= g.n) return;
+  const size_t p = g.gridIndex(q);
+  double Q[NU], mm[ND], A[NU][NU];
+#pragma unroll
+  for (int c = 0; c < NU; ++c) Q[c] = target[(size_t)c * cs + p];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) mm[i] = m[(size_t)(i + ND * dir) * csm + p];
+  incoming_jacobian<ND>(Q, mm, gamma, incoming, A);
+#pragma unroll
+  for (int i = 0; i < NU; ++i)
+#pragma unroll
+    for (int j = 0; j < NU; ++j) Aplus[(size_t)(i * NU + j) * g.n + q] = A[i][j];
+}
+
+// addFarFieldPenalty (reference src/FarFieldPatchImpl.f90:93-286)
+template <int ND>
+__global__ void k_farfield(FFArgs a) {
+  constexpr int NU = ND + 2;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.g.n) return;
+  const size_t p = a.g.gridIndex(q);
+  if (a.iblank && a.iblank[p] == 0) return;
+  const double jac = a.jac[p];
+  double mm[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) mm[i] = a.m[(size_t)(i + ND * a.dir) * a.cs + p];
+  double r[NU];
+  if (a.mode == MG_FORWARD) {
+    double dq[NU];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) dq[c] = a.Q[(size_t)c * a.csQ + p] - a.target[(size_t)c * a.cs + p];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < NU; ++j) acc += a.Aplus[(size_t)(i * NU + j) * a.g.n + q] * dq[j];
+      r[i] = -a.sigmaI * jac * acc;
+    }
+    if (a.viscous) {
+#pragma unroll
+      for (int c = 0; c < NU; ++c) {
+        double acc = 0.0;
+#pragma unroll
+        for (int l = 0; l < ND; ++l)
+          acc += (a.Fv[(size_t)(c + NU * l) * a.g.n + q] - a.FvTarget[(size_t)(c + NU * l) * a.g.n + q]) * mm[l];
+        r[c] += a.sigmaV * jac * acc;
+      }
+    }
+  } else {
+    double w[NU];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) w[c] = a.W[(size_t)c * a.csW + p];
+    const double sgn = a.continuousAdjoint ? -1.0 : 1.0;
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < NU; ++i) acc += a.Aplus[(size_t)(i * NU + j) * a.g.n + q] * w[i];
+      r[j] = sgn * a.sigmaI * jac * acc;
+    }
+    if (a.viscous) {
+      // - sigmaV (1/J) B^T w with B the first-partial viscous Jacobian: obtained from the shared
+      // helper as  -(A - B)^T w + A^T w  would waste work, so evaluate (A-B)^T and A^T explicitly.
+      double Q[NU], tau[ND * ND], qq[ND], y1[NU], y2[NU];
+      Prim<ND> s;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) { Q[c] = a.Q[(size_t)c * a.csQ + p]; y1[c] = 0.0; y2[c] = 0.0; }
+      s.v = a.v[p];
+      s.T = a.T[p];
+#pragma unroll
+      for (int i = 0; i < ND; ++i) { s.u[i] = a.u[(size_t)i * a.cs + p]; qq[i] = a.q[(size_t)i * a.cs + p]; }
+#pragma unroll
+      for (int c = 0; c < ND * ND; ++c) tau[c] = a.tau[(size_t)c * a.cs + p];
+      add_flux_jacobian_transpose<ND>(Q, s, mm, a.gamma, true, a.powerLaw, tau, qq, w, y1);    // (A-B)^T w
+      add_flux_jacobian_transpose<ND>(Q, s, mm, a.gamma, false, a.powerLaw, tau, qq, w, y2);   // A^T w
+#pragma unroll
+      for (int c = 0; c < NU; ++c) r[c] -= a.sigmaV * jac * (y2[c] - y1[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NU; ++c) a.rhs[(size_t)c * a.cs + p] += r[c];
+}
+
+struct FFSrcArgs {
+  PatchGeom g;
+  const double *W, *u, *mu, *lam, *kap, *m, *jac;
+  const int* iblank;
+  double* temp1;     // component c + (NU-1)*l
+  size_t csW, cs;
+  int dir;
+  double sigmaV;
+};
+
+// Source of addFarFieldAdjointPenalty (reference src/RhsHelperImpl.f90:137-207)
+template <int ND>
+__global__ void k_farfield_adjoint_source(FFSrcArgs a) {
+  constexpr int NU = ND + 2;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.g.n) return;
+  const size_t p = a.g.gridIndex(q);
+  if (a.iblank && a.iblank[p] == 0) return;
+  double u[ND], M[ND * ND], w[ND + 1];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) u[i] = a.u[(size_t)i * a.cs + p];
+#pragma unroll
+  for (int c = 0; c < ND * ND; ++c) M[c] = a.m[(size_t)c * a.cs + p];
+#pragma unroll
+  for (int c = 0; c < ND + 1; ++c) w[c] = a.W[(size_t)(c + 1) * a.csW + p];
+  const double mu = a.mu[p], lam = a.lam[p], kap = a.kap[p], jac = a.jac[p];
+#pragma unroll
+  for (int l = 0; l < ND; ++l) {
+    double d[ND + 1];
+#pragma unroll
+    for (int c = 0; c < ND + 1; ++c) d[c] = 0.0;
+    add_second_partial_transpose<ND>(u, mu, lam, kap, jac, &M[ND * a.dir], &M[ND * l], w, d);
+#pragma unroll
+    for (int c = 0; c < ND + 1; ++c) a.temp1[(size_t)(c + (NU - 1) * l) * a.cs + p] -= a.sigmaV * d[c];
+  }
+}
+
+struct SpongeArgs {
+  PatchGeom g;
+  const double *X, *target, *strength;
+  const int* iblank;
+  double* rhs;
+  size_t csX, cs;
+  int nU, mode;
+};
+
+// addDamping (reference src/SpongePatchImpl.f90:65-165)
+__global__ void k_sponge(SpongeArgs a) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.g.n) return;
+  const size_t p = a.g.gridIndex(q);
+  if (a.iblank && a.iblank[p] == 0) return;
+  const double s = a.strength[q];
+  for (int c = 0; c < a.nU; ++c) {
+    if (a.mode == MG_FORWARD)
+      a.rhs[(size_t)c * a.cs + p] -= s * (a.X[(size_t)c * a.csX + p] - a.target[(size_t)c * a.cs + p]);
+    else
+      a.rhs[(size_t)c * a.cs + p] += s * a.X[(size_t)c * a.csX + p];
+  }
+}
+
+struct WallArgs {
+  PatchGeom g;
+  const double *Q, *W, *m, *jac, *v, *u, *pr, *T, *wallT;
+  const int* iblank;
+  double* rhs;
+  size_t csQ, csW, cs;
+  int dir, mode, isothermal, viscous;
+  double sigmaI, sigmaV1, gamma;
+};
+
+// addImpenetrableWallPenalty (reference src/ImpenetrableWallImpl.f90:60-207) followed, for isothermal
+// walls, by addIsothermalWallPenalty (src/IsothermalWallImpl.f90:103-337).
+template <int ND>
+__global__ void k_wall(WallArgs a) {
+  constexpr int NU = ND + 2;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.g.n) return;
+  const size_t p = a.g.gridIndex(q);
+  if (a.iblank && a.iblank[p] == 0) return;
+  const double jac = a.jac[p];
+  double Q[NU], mm[ND], u[ND], r[NU];
+#pragma unroll
+  for (int c = 0; c < NU; ++c) Q[c] = a.Q[(size_t)c * a.csQ + p];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    mm[i] = a.m[(size_t)(i + ND * a.dir) * a.cs + p];
+    u[i] = a.u[(size_t)i * a.cs + p];
+  }
+  const double v = a.v[p];
+  if (a.mode == MG_FORWARD) {
+    double nm = 0.0;
+#pragma unroll
+    for (int l = 0; l < ND; ++l) nm = (l == 0) ? Q[1] * mm[0] : nm + Q[l + 1] * mm[l];
+    r[0] = nm;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r[i + 1] = nm * u[i];
+    r[NU - 1] = nm * v * (Q[NU - 1] + a.pr[p]);
+#pragma unroll
+    for (int c = 0; c < NU; ++c) r[c] = -a.sigmaI * jac * r[c];
+    if (a.isothermal && a.viscous) {
+      double pen[NU];
+      pen[0] = 0.0;
+#pragma unroll
+      for (int c = 1; c < NU; ++c) pen[c] = Q[c];
+      pen[NU - 1] = pen[NU - 1] - Q[0] * a.wallT[q] / a.gamma;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) r[c] -= a.sigmaV1 * (jac * pen[c]);
+    }
+  } else {
+    double w[NU];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) { w[c] = a.W[(size_t)c * a.csW + p]; r[c] = 0.0; }
+    // deltaInviscidPenalty = A(Q, m) with the pressure rows removed (reference :143-172)
+    Prim<ND> s;
+    s.v = v;
+    s.T = a.T[p];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) s.u[i] = v * Q[i + 1];     // velocity not passed: recomputed (:150-166)
+    double y[NU];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) y[c] = 0.0;
+    add_flux_jacobian_transpose<ND>(Q, s, mm, a.gamma, false, 0.0, nullptr, nullptr, w, y);
+    double dp[NU];
+    double usq = 0.0;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) usq = (i == 0) ? u[0] * u[0] : usq + u[i] * u[i];
+    dp[0] = 0.5 * usq;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) dp[i + 1] = -u[i];
+    dp[NU - 1] = 1.0;
+    double mw = 0.0;
+#pragma unroll
+    for (int l = 0; l < ND; ++l) mw += mm[l] * w[l + 1];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) {
+      y[c] -= (dp[c] * (a.gamma - 1.0)) * mw;
+      r[c] = a.sigmaI * jac * y[c];
+    }
+    if (a.isothermal && a.viscous) {
+      double ap[NU];
+      ap[0] = -w[NU - 1] * a.wallT[q] / a.gamma;
+#pragma unroll
+      for (int c = 1; c < NU; ++c) ap[c] = w[c];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) r[c] += a.sigmaV1 * (jac * ap[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NU; ++c) a.rhs[(size_t)c * a.cs + p] += r[c];
+}
+
+struct AddArgs {
+  PatchGeom g;
+  const double* data;      // (nComp) per patch point, point fastest
+  const double* mollifier; // grid field or null
+  const int* iblank;
+  double* rhs;
+  size_t cs;
+  int nComp;
+  double factor;
+};
+
+// addAdjointForcing / updateActuatorPatch (reference CostTargetPatchImpl.f90:72-136, ActuatorPatchImpl.f90:108-181)
+__global__ void k_patch_add(AddArgs a) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.g.n) return;
+  const size_t p = a.g.gridIndex(q);
+  if (a.iblank && a.iblank[p] == 0) return;
+  const double f = a.mollifier ? a.factor * a.mollifier[p] : a.factor;
+  for (int c = 0; c < a.nComp; ++c) a.rhs[(size_t)c * a.cs + p] += f * a.data[(size_t)c * a.g.n + q];
+}
+
+__global__ void k_collect(PatchGeom g, const double* field, size_t cs, int nComp, double* out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= g.n) return;
+  const size_t p = g.gridIndex(q);
+  for (int c = 0; c < nComp; ++c) out[(size_t)c * g.n + q] = field[(size_t)c * cs + p];
+}
+
+__global__ void k_disperse(PatchGeom g, const double* in, size_t cs, int nComp, double* field) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= g.n) return;
+  const size_t p = g.gridIndex(q);
+  for (int c = 0; c < nComp; ++c) field[(size_t)c * cs + p] = in[(size_t)c * g.n + q];
+}
+
+PatchGeom geom(const mg_patch* pt) {
+  PatchGeom g;
+  for (int i = 0; i < 3; ++i) { g.lo[i] = pt->localLo[i]; g.sz[i] = pt->localSize[i]; }
+  g.nx = pt->state->grid->localSize[0];
+  g.ny = pt->state->grid->localSize[1];
+  g.n = pt->nPatchPoints;
+  return g;
+}
+
+template <typename F>
+int dispatch_nd(int nD, F f) {
+  if (nD == 1) return f(std::integral_constant<int, 1>());
+  if (nD == 2) return f(std::integral_constant<int, 2>());
+  return f(std::integral_constant<int, 3>());
+}
+
+}  // namespace
+
+// setupPatch (reference src/PatchImpl.f90:3-151): intersect the global extent with this rank's brick.
+int mg_patch_create_impl(mg_state* s, int type, const char* name, int normalDirection, const int extent[6],
+                         mg_patch** out) {
+  mg_grid* g = s->grid;
+  auto* p = new mg_patch();
+  p->state = s;
+  p->type = type;
+  p->name = name ? name : "";
+  p->normalDirection = normalDirection;
+  for (int i = 0; i < 6; ++i) p->extent[i] = extent[i];
+  bool empty = false;
+  for (int d = 0; d < 3; ++d) {
+    const int lo = extent[2 * d], hi = extent[2 * d + 1];     // 1-based inclusive, global
+    if (lo < 1 || hi > g->globalSize[d] || lo > hi) { delete p; MG_FAIL("mg_patch_create: invalid extent"); }
+    p->globalSize[d] = hi - lo + 1;
+    const int a = std::max(lo, g->offset[d] + 1), b = std::min(hi, g->offset[d] + g->localSize[d]);
+    if (b < a) empty = true;
+    p->localLo[d] = a - 1 - g->offset[d];
+    p->localSize[d] = b - a + 1;
+    p->patchOffset[d] = a - lo;          // offset of the local part inside the global patch
+  }
+  if (empty) { for (int d = 0; d < 3; ++d) { p->localLo[d] = 0; p->localSize[d] = 0; } }
+  p->nPatchPoints = p->localSize[0] * p->localSize[1] * p->localSize[2];
+  const int ad = std::abs(normalDirection);
+  if (type != MG_PATCH_SPONGE && type != MG_PATCH_ACTUATOR && type != MG_PATCH_COST_TARGET) {
+    if (ad < 1 || ad > g->nD) { delete p; MG_FAIL("mg_patch_create: normal direction is invalid"); }
+    if (extent[2 * (ad - 1)] != extent[2 * (ad - 1) + 1]) {
+      delete p;
+      MG_FAIL("mg_patch_create: patch extends more than 1 grid point along normal direction");
+    }
+  }
+  if (type == MG_PATCH_FARFIELD || type == MG_PATCH_SPONGE) {
+    if (!s->opt.useTargetState) { delete p; MG_FAIL("mg_patch_create: no target state available for this patch type"); }
+  }
+  s->patches.push_back(p);
+  if (type == MG_PATCH_FARFIELD && s->opt.viscosityOn) s->keepViscousFluxes = true;
+  *out = p;
+  return 0;
+}
+
+void mg_patch_destroy_impl(mg_patch* p) {
+  if (!p) return;
+  for (auto& kv : p->arrays) cudaFree(kv.second.p);
+  delete p;
+}
+
+int mg_patch_alloc_array(mg_patch* p, const std::string& name, int nComp, double** out) {
+  auto it = p->arrays.find(name);
+  if (it != p->arrays.end() && it->second.nComp == nComp) { *out = it->second.p; return 0; }
+  if (it != p->arrays.end()) { cudaFree(it->second.p); p->arrays.erase(it); }
+  mg_patch::Array a;
+  a.nComp = nComp;
+  const size_t bytes = sizeof(double) * (size_t)std::max(1, p->nPatchPoints) * nComp;
+  MG_CUDA(cudaMalloc(&a.p, bytes));
+  MG_CUDA(cudaMemsetAsync(a.p, 0, bytes, mg_stream()));
+  p->arrays[name] = a;
+  *out = a.p;
+  return 0;
+}
+
+int mg_patch_set_array_impl(mg_patch* p, const char* name, int nComp, const double* host) {
+  double* d = nullptr;
+  MG_TRY(mg_patch_alloc_array(p, name, nComp, &d));
+  if (p->nPatchPoints > 0)
+    MG_CUDA(cudaMemcpyAsync(d, host, sizeof(double) * (size_t)p->nPatchPoints * nComp, cudaMemcpyDefault, mg_stream()));
+  MG_CUDA(cudaStreamSynchronize(mg_stream()));
+  if (std::string(name) == "Aplus") p->AplusReady = true;
+  return 0;
+}
+
+int mg_patch_get_array_impl(mg_patch* p, const char* name, int nComp, double* host) {
+  auto it = p->arrays.find(name);
+  if (it == p->arrays.end() || it->second.nComp != nComp) MG_FAIL(std::string("mg_patch_get_array: no array '") + name + "'");
+  if (p->nPatchPoints > 0)
+    MG_CUDA(cudaMemcpyAsync(host, it->second.p, sizeof(double) * (size_t)p->nPatchPoints * nComp, cudaMemcpyDefault, mg_stream()));
+  MG_CUDA(cudaStreamSynchronize(mg_stream()));
+  return 0;
+}
+
+// collect (reference src/PatchImpl.f90:187-316): grid field -> patch array
+int mg_patch_collect_impl(mg_patch* p, const MgField* f, int nComp, const char* name) {
+  double* d = nullptr;
+  MG_TRY(mg_patch_alloc_array(p, name, nComp, &d));
+  if (p->nPatchPoints == 0) return 0;
+  k_collect<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), f->comp(0), f->compStride, nComp, d);
+  MG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mg_patch_disperse_impl(mg_patch* p, const char* name, int nComp, MgField* f) {
+  auto it = p->arrays.find(name);
+  if (it == p->arrays.end() || it->second.nComp != nComp) MG_FAIL(std::string("mg_patch_disperse: no array '") + name + "'");
+  if (p->nPatchPoints == 0) return 0;
+  k_disperse<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), it->second.p, f->compStride, nComp, f->comp(0));
+  MG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+bool mg_patches_have_farfield(const mg_state* s) {
+  for (const mg_patch* p : s->patches)
+    if (p->type == MG_PATCH_FARFIELD) return true;
+  return false;
+}
+
+int mg_patches_collect_viscous(mg_state* s) {
+  for (mg_patch* p : s->patches)
+    if (p->type == MG_PATCH_FARFIELD)
+      MG_TRY(mg_patch_collect_impl(p, &s->viscFluxCart, s->nU * s->nD, "viscousFluxes"));
+  return 0;
+}
+
+// updatePatchFactories, far-field part (reference src/PatchFactoryImpl.f90:531-560): target viscous
+// fluxes from the target state.  NB: like the reference this leaves the state's dependent variables
+// evaluated at the target state; callers update the state afterwards.
+int mg_patches_update_impl(mg_state* s) {
+  if (!(s->opt.viscosityOn && s->opt.useTargetState) || !mg_patches_have_farfield(s)) return 0;
+  MG_TRY(mg_state_update_impl(s, &s->target));
+  // Cartesian viscous fluxes of the target state via the general flux kernel
+  const bool keep = s->keepViscousFluxes;
+  s->keepViscousFluxes = true;
+  MgField saveQ = s->Q[s->cur];
+  s->Q[s->cur] = s->target;             // shallow view swap: k_flux reads Q only for the inviscid part
+  s->Q[s->cur].owned = false;
+  int rc = mg_state_rhs_forward_general(s);
+  s->Q[s->cur] = saveQ;
+  s->keepViscousFluxes = keep;
+  MG_TRY(rc);
+  for (mg_patch* p : s->patches)
+    if (p->type == MG_PATCH_FARFIELD)
+      MG_TRY(mg_patch_collect_impl(p, &s->viscFluxCart, s->nU * s->nD, "targetViscousFluxes"));
+  s->dependentValid = false;
+  return 0;
+}
+
+int mg_patches_farfield_adjoint_sources(mg_state* s, MgField* temp1) {
+  mg_grid* g = s->grid;
+  for (mg_patch* p : s->patches) {
+    if (p->type != MG_PATCH_FARFIELD || p->nPatchPoints == 0) continue;
+    FFSrcArgs a;
+    a.g = geom(p);
+    a.W = s->W[s->curW].comp(0);
+    a.csW = s->W[s->curW].compStride;
+    a.u = s->velocity.comp(0);
+    a.mu = s->mu.comp(0);
+    a.lam = s->lambda.comp(0);
+    a.kap = s->kappa.comp(0);
+    a.m = g->metrics.comp(0);
+    a.jac = g->jacobian.comp(0);
+    a.iblank = g->iblank;
+    a.temp1 = temp1->comp(0);
+    a.cs = temp1->compStride;
+    a.dir = std::abs(p->normalDirection) - 1;
+    a.sigmaV = p->viscousPenaltyAmount;
+    MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
+      k_farfield_adjoint_source<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a);
+      return 0;
+    }));
+    MG_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// patch%updateRhs for every patch of the state, in creation (bc.dat) order
+// (reference src/RegionImpl.f90:1985-1995)
+int mg_patches_apply(mg_state* s, int mode) {
+  mg_grid* g = s->grid;
+  cudaStream_t st = mg_stream();
+  const MgField& Q = s->Q[s->cur];
+  const MgField& W = s->W[s->curW];
+  for (mg_patch* p : s->patches) {
+    if (p->nPatchPoints == 0) continue;
+    const int dir = std::abs(p->normalDirection) - 1;
+    switch (p->type) {
+      case MG_PATCH_FARFIELD: {
+        double* Aplus = nullptr;
+        MG_TRY(mg_patch_alloc_array(p, "Aplus", s->nU * s->nU, &Aplus));
+        const int incoming = (mode == MG_ADJOINT && s->opt.useContinuousAdjoint) ? -p->normalDirection : p->normalDirection;
+        if (!p->AplusReady || p->AplusIncoming != incoming) {
+          MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
+            k_farfield_setup<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, st>>>(
+                geom(p), s->target.comp(0), s->target.compStride, g->metrics.comp(0), g->metrics.compStride, dir,
+                s->opt.ratioOfSpecificHeats, incoming, Aplus);
+            return 0;
+          }));
+          p->AplusReady = true;
+          p->AplusIncoming = incoming;
+        }
+        FFArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.g = geom(p);
+        a.Q = Q.comp(0); a.csQ = Q.compStride;
+        a.W = W.comp(0); a.csW = W.compStride;
+        a.target = s->target.comp(0);
+        a.m = g->metrics.comp(0);
+        a.jac = g->jacobian.comp(0);
+        a.v = s->specificVolume.comp(0);
+        a.u = s->velocity.comp(0);
+        a.T = s->temperature.comp(0);
+        a.iblank = g->iblank;
+        a.rhs = s->rhs.comp(0);
+        a.cs = s->rhs.compStride;
+        a.Aplus = Aplus;
+        a.dir = dir;
+        a.mode = mode;
+        a.viscous = s->opt.viscosityOn;
+        a.continuousAdjoint = s->opt.useContinuousAdjoint;
+        a.sigmaI = p->inviscidPenaltyAmount;
+        a.sigmaV = p->viscousPenaltyAmount;
+        a.gamma = s->opt.ratioOfSpecificHeats;
+        a.powerLaw = s->opt.powerLawExponent;
+        if (s->opt.viscosityOn) {
+          a.tau = s->stressTensor.comp(0);
+          a.q = s->heatFlux.comp(0);
+          if (mode == MG_FORWARD) {
+            auto fv = p->arrays.find("viscousFluxes"), ft = p->arrays.find("targetViscousFluxes");
+            if (fv == p->arrays.end() || ft == p->arrays.end())
+              MG_FAIL("far-field patch: viscous fluxes missing (call mg_region_update_patches after setting the target state)");
+            a.Fv = fv->second.p;
+            a.FvTarget = ft->second.p;
+          }
+        }
+        MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
+          k_farfield<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, st>>>(a);
+          return 0;
+        }));
+        break;
+      }
+      case MG_PATCH_SPONGE: {
+        auto it = p->arrays.find("spongeStrength");
+        if (it == p->arrays.end()) MG_FAIL("sponge patch: spongeStrength has not been set");
+        SpongeArgs a;
+        a.g = geom(p);
+        const MgField& X = mode == MG_FORWARD ? Q : W;
+        a.X = X.comp(0); a.csX = X.compStride;
+        a.target = s->target.comp(0);
+        a.strength = it->second.p;
+        a.iblank = g->iblank;
+        a.rhs = s->rhs.comp(0);
+        a.cs = s->rhs.compStride;
+        a.nU = s->nU;
+        a.mode = mode;
+        k_sponge<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a);
+        break;
+      }
+      case MG_PATCH_SLIP_WALL:
+      case MG_PATCH_ISOTHERMAL_WALL: {
+        if (mode == MG_ADJOINT && s->opt.useContinuousAdjoint) break;
+        WallArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.g = geom(p);
+        a.Q = Q.comp(0); a.csQ = Q.compStride;
+        a.W = W.comp(0); a.csW = W.compStride;
+        a.m = g->metrics.comp(0);
+        a.jac = g->jacobian.comp(0);
+        a.v = s->specificVolume.comp(0);
+        a.u = s->velocity.comp(0);
+        a.pr = s->pressure.comp(0);
+        a.T = s->temperature.comp(0);
+        a.iblank = g->iblank;
+        a.rhs = s->rhs.comp(0);
+        a.cs = s->rhs.compStride;
+        a.dir = dir;
+        a.mode = mode;
+        a.isothermal = p->type == MG_PATCH_ISOTHERMAL_WALL;
+        a.viscous = s->opt.viscosityOn;
+        a.sigmaI = p->inviscidPenaltyAmount;
+        a.sigmaV1 = p->viscousPenaltyAmount;
+        a.gamma = s->opt.ratioOfSpecificHeats;
+        if (a.isothermal && a.viscous) {
+          auto it = p->arrays.find("temperature");
+          if (it == p->arrays.end()) MG_FAIL("isothermal wall patch: temperature has not been set");
+          a.wallT = it->second.p;
+        }
+        MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
+          k_wall<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, st>>>(a);
+          return 0;
+        }));
+        break;
+      }
+      case MG_PATCH_COST_TARGET: {
+        if (mode == MG_FORWARD) break;
+        auto it = p->arrays.find("adjointForcing");
+        if (it == p->arrays.end()) break;
+        AddArgs a;
+        a.g = geom(p);
+        a.data = it->second.p;
+        a.mollifier = nullptr;
+        a.iblank = g->iblank;
+        a.rhs = s->rhs.comp(0);
+        a.cs = s->rhs.compStride;
+        a.nComp = s->nU;
+        a.factor = s->opt.useContinuousAdjoint ? 1.0 : s->adjointForcingFactor;
+        k_patch_add<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a);
+        break;
+      }
+      case MG_PATCH_ACTUATOR: {
+        if (mode != MG_FORWARD) break;
+        auto it = p->arrays.find("controlForcing");
+        if (it == p->arrays.end()) break;
+        if (!g->controlMollifier.p) MG_FAIL("actuator patch: control mollifier has not been set");
+        AddArgs a;
+        a.g = geom(p);
+        a.data = it->second.p;
+        a.mollifier = g->controlMollifier.comp(0);
+        a.iblank = g->iblank;
+        a.rhs = s->rhs.comp(0);
+        a.cs = s->rhs.compStride;
+        a.nComp = s->nU;
+        a.factor = 1.0;
+        k_patch_add<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a);
+        break;
+      }
+      default:
+        MG_FAIL("patch: unknown type");
+    }
+    MG_CUDA(cudaGetLastError());
+  }
+  return 0;
+}

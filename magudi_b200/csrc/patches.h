@@ -1,0 +1,43 @@
+// Patch handle (t_Patch family).  Public constants mirror include/magudi_gpu.h.
+#pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <string>
+
+#include "grid.h"
+
+enum {
+  MG_PATCH_FARFIELD = 1,
+  MG_PATCH_SPONGE = 2,
+  MG_PATCH_SLIP_WALL = 3,
+  MG_PATCH_ISOTHERMAL_WALL = 4,
+  MG_PATCH_COST_TARGET = 5,
+  MG_PATCH_ACTUATOR = 6,
+};
+
+struct mg_patch {
+  struct Array { double* p = nullptr; int nComp = 0; };
+  mg_state* state = nullptr;
+  int type = 0;
+  std::string name;
+  int normalDirection = 0;
+  int extent[6] = {1, 1, 1, 1, 1, 1};
+  int globalSize[3] = {1, 1, 1};
+  int localLo[3] = {0, 0, 0}, localSize[3] = {0, 0, 0}, patchOffset[3] = {0, 0, 0};
+  int nPatchPoints = 0;
+  double inviscidPenaltyAmount = 0.0, viscousPenaltyAmount = 0.0;   // signed, already / normBoundary(1)
+  std::map<std::string, Array> arrays;     // patch-point arrays, (nPatchPoints, nComp) point fastest
+  bool AplusReady = false;
+  int AplusIncoming = 0;
+};
+
+int mg_patch_create_impl(mg_state* s, int type, const char* name, int normalDirection, const int extent[6],
+                         mg_patch** out);
+void mg_patch_destroy_impl(mg_patch* p);
+int mg_patch_alloc_array(mg_patch* p, const std::string& name, int nComp, double** out);
+int mg_patch_set_array_impl(mg_patch* p, const char* name, int nComp, const double* host);
+int mg_patch_get_array_impl(mg_patch* p, const char* name, int nComp, double* host);
+int mg_patch_collect_impl(mg_patch* p, const MgField* f, int nComp, const char* name);
+int mg_patch_disperse_impl(mg_patch* p, const char* name, int nComp, MgField* f);
+int mg_patches_update_impl(mg_state* s);

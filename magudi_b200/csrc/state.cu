@@ -1,0 +1,627 @@
+// t_State on the device and the GENERAL (operator-by-operator) right-hand-side path: a direct GPU
+// restatement of the reference call structure, valid for every scheme / boundary / dimension.
+// The fused hot path lives in rhs_fused.cu; this path is its fallback for configurations the fused
+// kernels do not cover yet and its device-side cross-check.
+//
+// Reference: src/StateImpl.f90:466-537 (updateState), src/RhsHelperImpl.f90:10-87 (addDissipation),
+// :254-354 (computeRhsForward), :356-596 (computeRhsAdjoint), src/RegionImpl.f90:1877-2027 (computeRhs),
+// src/RK4IntegratorImpl.f90:65-270.
+#include <cstring>
+
+#include "grid.h"
+#include "stencil_apply.h"
+#include "rhs_fused.h"
+
+namespace {
+
+inline unsigned nblocks(size_t n) { return (unsigned)((n + 255) / 256); }
+
+struct PtrSet {
+  const double* Q; size_t csQ;
+  double *v, *u, *p, *T, *mu, *lam, *kap;
+  size_t cs;
+  size_t N;
+};
+
+template <int ND>
+__global__ void k_dependent(PtrSet a, PhysParams pp) {
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= a.N) return;
+  double Q[ND + 2];
+#pragma unroll
+  for (int c = 0; c < ND + 2; ++c) Q[c] = a.Q[(size_t)c * a.csQ + p];
+  Prim<ND> s;
+  dependent<ND>(Q, pp.gamma, s);
+  a.v[p] = s.v;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) a.u[(size_t)i * a.cs + p] = s.u[i];
+  a.p[p] = s.p;
+  a.T[p] = s.T;
+  if (pp.viscous) {
+    double mu, lam, kap;
+    transport(s.T, pp, mu, lam, kap);
+    a.mu[p] = mu;
+    a.lam[p] = lam;
+    a.kap[p] = kap;
+  }
+}
+
+template <int ND>
+__global__ void k_stress(double* g, size_t cs, const double* mu, const double* lam, size_t N) {
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  double gr[ND * ND], s[ND * ND];
+#pragma unroll
+  for (int q = 0; q < ND * ND; ++q) gr[q] = g[(size_t)q * cs + p];
+  stress_from_gradient<ND>(gr, mu[p], lam[p], s);
+#pragma unroll
+  for (int q = 0; q < ND * ND; ++q) g[(size_t)q * cs + p] = s[q];
+}
+
+__global__ void k_heatflux(double* q, size_t cs, int nD, const double* kap, size_t N) {
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  for (int i = 0; i < nD; ++i) q[(size_t)i * cs + p] = -kap[p] * q[(size_t)i * cs + p];
+}
+
+struct FluxArgs {
+  const double *Q, *u, *pr, *tau, *q, *m;
+  double* Fhat;      // component c + NU*i  (flux direction i)
+  double* Fv;        // Cartesian viscous flux, component c + NU*l (may be null)
+  size_t csQ, cs, N;
+  int viscous, curvilinear;
+};
+
+// computeCartesianInviscid/ViscousFluxes + transformFluxes (reference CNSHelperImpl.f90:563-689, :772-840)
+template <int ND>
+__global__ void k_flux(FluxArgs a) {
+  constexpr int NU = ND + 2;
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= a.N) return;
+  double Q[NU], tau[ND * ND], q[ND], M[ND * ND];
+  Prim<ND> s;
+#pragma unroll
+  for (int c = 0; c < NU; ++c) Q[c] = a.Q[(size_t)c * a.csQ + p];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) s.u[i] = a.u[(size_t)i * a.cs + p];
+  s.p = a.pr[p];
+  if (a.viscous) {
+#pragma unroll
+    for (int c = 0; c < ND * ND; ++c) tau[c] = a.tau[(size_t)c * a.cs + p];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) q[i] = a.q[(size_t)i * a.cs + p];
+  }
+#pragma unroll
+  for (int c = 0; c < ND * ND; ++c) M[c] = a.m[(size_t)c * a.cs + p];
+  double F[ND][NU], Fv[NU];
+#pragma unroll
+  for (int l = 0; l < ND; ++l) {
+    cartesian_flux<ND>(l, Q, s, a.viscous, tau, q, F[l], Fv);
+    if (a.Fv && a.viscous) {
+#pragma unroll
+      for (int c = 0; c < NU; ++c) a.Fv[(size_t)(c + NU * l) * a.cs + p] = Fv[c];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ND; ++i)
+#pragma unroll
+    for (int c = 0; c < NU; ++c) {
+      double r;
+      if (a.curvilinear) {
+        r = M[0 + ND * i] * F[0][c];
+#pragma unroll
+        for (int j = 1; j < ND; ++j) r += M[j + ND * i] * F[j][c];
+      } else {
+        r = M[i + ND * i] * F[i][c];
+      }
+      a.Fhat[(size_t)(c + NU * i) * a.cs + p] = r;
+    }
+}
+
+// rhs = -(d0 + d1 + d2)   (reference RhsHelperImpl.f90:344)
+__global__ void k_neg_sum(double* rhs, const double* d, size_t cs, int nU, int nD, size_t N) {
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  for (int c = 0; c < nU; ++c) {
+    double s = d[(size_t)c * cs + p];
+    for (int i = 1; i < nD; ++i) s += d[(size_t)(c + nU * i) * cs + p];
+    rhs[(size_t)c * cs + p] = 0.0 - s;
+  }
+}
+
+__global__ void k_scale_by(double* t, size_t cs, int nComp, const double* a, double sign, size_t N) {
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  for (int c = 0; c < nComp; ++c) t[(size_t)c * cs + p] = sign * a[p] * t[(size_t)c * cs + p];
+}
+
+__global__ void k_axpy(double* y, const double* x, size_t cs, size_t csx, int nComp, double a, size_t N) {
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  for (int c = 0; c < nComp; ++c) y[(size_t)c * cs + p] += a * x[(size_t)c * csx + p];
+}
+
+struct AdjArgs {
+  const double *Q, *W, *v, *u, *T, *tau, *q, *mu, *lam, *kap, *m, *jac;
+  const double* dW;   // adjoint derivative: component c + NU*i
+  double* rhs;
+  double* diff;       // adjoint diffusion: component c + (NU-1)*j
+  size_t csQ, cs, N;
+  int viscous, curvilinear;
+  double gamma, powerLaw;
+};
+
+// Pointwise part of computeRhsAdjoint (reference RhsHelperImpl.f90:431-553)
+template <int ND>
+__global__ void k_adjoint_point(AdjArgs a) {
+  constexpr int NU = ND + 2;
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= a.N) return;
+  double Q[NU], tau[ND * ND], q[ND], M[ND * ND];
+  Prim<ND> s;
+#pragma unroll
+  for (int c = 0; c < NU; ++c) Q[c] = a.Q[(size_t)c * a.csQ + p];
+  s.v = a.v[p];
+  s.T = a.T[p];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) s.u[i] = a.u[(size_t)i * a.cs + p];
+#pragma unroll
+  for (int c = 0; c < ND * ND; ++c) M[c] = a.m[(size_t)c * a.cs + p];
+  if (a.viscous) {
+#pragma unroll
+    for (int c = 0; c < ND * ND; ++c) tau[c] = a.tau[(size_t)c * a.cs + p];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) q[i] = a.q[(size_t)i * a.cs + p];
+  }
+  double dW[ND][NU];
+#pragma unroll
+  for (int i = 0; i < ND; ++i)
+#pragma unroll
+    for (int c = 0; c < NU; ++c) dW[i][c] = a.dW[(size_t)(c + NU * i) * a.cs + p];
+  double r[NU];
+#pragma unroll
+  for (int c = 0; c < NU; ++c) r[c] = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i)
+    add_flux_jacobian_transpose<ND>(Q, s, &M[ND * i], a.gamma, a.viscous, a.powerLaw, tau, q, dW[i], r);
+#pragma unroll
+  for (int c = 0; c < NU; ++c) a.rhs[(size_t)c * a.cs + p] = r[c];
+  if (a.viscous) {
+    const double mu = a.mu[p], lam = a.lam[p], kap = a.kap[p], jac = a.jac[p];
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      double d[ND + 1];
+#pragma unroll
+      for (int c = 0; c < ND + 1; ++c) d[c] = 0.0;
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+        add_second_partial_transpose<ND>(s.u, mu, lam, kap, jac, &M[ND * i], &M[ND * j], &dW[i][1], d);
+#pragma unroll
+      for (int c = 0; c < ND + 1; ++c) a.diff[(size_t)(c + (NU - 1) * j) * a.cs + p] = d[c];
+    }
+  }
+}
+
+struct AdjFinishArgs {
+  const double *Q, *v, *u;
+  const double* d;    // derivative of adjoint diffusion: component c + (NU-1)*j
+  double* rhs;
+  size_t csQ, cs, N;
+  double gamma, sign;
+};
+
+// Variable change after the second viscous sweep (reference RhsHelperImpl.f90:558-570; the far-field
+// adjoint penalty reuses it with the opposite sign, :228-240).
+template <int ND>
+__global__ void k_adjoint_finish(AdjFinishArgs a) {
+  constexpr int NU = ND + 2;
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= a.N) return;
+  double t[ND + 1];
+#pragma unroll
+  for (int c = 0; c < ND + 1; ++c) {
+    double s = a.d[(size_t)c * a.cs + p];
+#pragma unroll
+    for (int j = 1; j < ND; ++j) s += a.d[(size_t)(c + (NU - 1) * j) * a.cs + p];
+    t[c] = s;
+  }
+  const double v = a.v[p];
+  double u[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) u[i] = a.u[(size_t)i * a.cs + p];
+  t[ND] = a.gamma * v * t[ND];
+  double ut = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    t[i] = v * t[i] - u[i] * t[ND];
+    ut = (i == 0) ? u[0] * t[0] : ut + u[i] * t[i];
+  }
+#pragma unroll
+  for (int c = 0; c < ND + 1; ++c) a.rhs[(size_t)(c + 1) * a.cs + p] -= a.sign * t[c];
+  a.rhs[p] += a.sign * (v * a.Q[(size_t)(ND + 1) * a.csQ + p] * t[ND] + ut);
+}
+
+__global__ void k_mul_jacobian(double* rhs, size_t cs, int nU, const double* jac, size_t N) {
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  for (int c = 0; c < nU; ++c) rhs[(size_t)c * cs + p] *= jac[p];
+}
+
+__global__ void k_mask_holes(double* rhs, size_t cs, int nU, const int* iblank, size_t N) {
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  if (iblank[p] == 0)
+    for (int c = 0; c < nU; ++c) rhs[(size_t)c * cs + p] = 0.0;
+}
+
+struct SrcArgs {
+  double* rhsE;
+  const double* x[3];
+  const int* iblank;
+  double loc[3], a, gaussianFactor;
+  int nD;
+  size_t N;
+};
+
+// addAcousticSource (reference src/AcousticSourceImpl.f90:34-64)
+__global__ void k_acoustic(SrcArgs a) {
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= a.N) return;
+  if (a.iblank && a.iblank[p] == 0) return;
+  double r = 0.0;
+  for (int i = 0; i < a.nD; ++i) {
+    const double d = a.x[i][p] - a.loc[i];
+    r = (i == 0) ? d * d : r + d * d;
+  }
+  a.rhsE[p] += a.a * exp(-a.gaussianFactor * r);
+}
+
+struct RkArgs {
+  const double* R;
+  const double* Qin;   // state the RHS was evaluated at
+  double *b1, *b2, *Qout;
+  size_t cs, N;
+  int nU, stage;
+  double dt;           // signed: +dt forward, -dt adjoint
+};
+
+// substepForward / substepAdjoint axpys (reference src/RK4IntegratorImpl.f90:106-158, :205-264)
+__global__ void k_rk4(RkArgs a) {
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= a.N) return;
+  for (int c = 0; c < a.nU; ++c) {
+    const size_t q = (size_t)c * a.cs + p;
+    const double R = a.R[q];
+    if (a.stage == 1) {
+      const double Q0 = a.Qin[q];
+      a.b1[q] = Q0;
+      a.b2[q] = Q0 + a.dt * R / 6.0;
+      a.Qout[q] = Q0 + a.dt * R / 2.0;
+    } else if (a.stage == 2) {
+      a.b2[q] = a.b2[q] + a.dt * R / 3.0;
+      a.Qout[q] = a.b1[q] + a.dt * R / 2.0;
+    } else if (a.stage == 3) {
+      a.b2[q] = a.b2[q] + a.dt * R / 3.0;
+      a.Qout[q] = a.b1[q] + a.dt * R;
+    } else {
+      a.Qout[q] = a.b2[q] + a.dt * R / 6.0;
+    }
+  }
+}
+
+template <typename F>
+int dispatch_nd(int nD, F f) {
+  if (nD == 1) return f(std::integral_constant<int, 1>());
+  if (nD == 2) return f(std::integral_constant<int, 2>());
+  return f(std::integral_constant<int, 3>());
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ state
+int mg_state_create_impl(mg_grid* g, const mg_options_t* opt, mg_state** out) {
+  auto* s = new mg_state();
+  s->grid = g;
+  s->opt = *opt;
+  s->nD = g->nD;
+  s->nU = g->nD + 2;
+  const int nD = s->nD, nU = s->nU;
+  MG_TRY(mg_field_alloc(g, nU, &s->Q[0]));
+  MG_TRY(mg_field_alloc(g, nU, &s->Q[1]));
+  MG_TRY(mg_field_alloc(g, nU, &s->W[0]));
+  MG_TRY(mg_field_alloc(g, nU, &s->W[1]));
+  MG_TRY(mg_field_alloc(g, nU, &s->target));
+  MG_TRY(mg_field_alloc(g, nU, &s->rhs));
+  MG_TRY(mg_field_alloc(g, 1, &s->specificVolume));
+  MG_TRY(mg_field_alloc(g, nD, &s->velocity));
+  MG_TRY(mg_field_alloc(g, 1, &s->pressure));
+  MG_TRY(mg_field_alloc(g, 1, &s->temperature));
+  MG_TRY(mg_field_alloc(g, nU, &s->rk1));
+  MG_TRY(mg_field_alloc(g, nU, &s->rk2));
+  if (opt->viscosityOn) {
+    MG_TRY(mg_field_alloc(g, 1, &s->mu));
+    MG_TRY(mg_field_alloc(g, 1, &s->lambda));
+    MG_TRY(mg_field_alloc(g, 1, &s->kappa));
+    MG_TRY(mg_field_alloc(g, nD * nD, &s->stressTensor));
+    MG_TRY(mg_field_alloc(g, nD, &s->heatFlux));
+  }
+  // scratch shared by the general path: two fields of nU*nD components
+  if (g->scratchA.nComp < nU * nD) MG_TRY(mg_field_alloc(g, nU * nD, &g->scratchA));
+  if (g->scratchB.nComp < nU * nD) MG_TRY(mg_field_alloc(g, nU * nD, &g->scratchB));
+  *out = s;
+  return 0;
+}
+
+void mg_state_destroy_impl(mg_state* s) {
+  if (!s) return;
+  for (MgField* f : {&s->Q[0], &s->Q[1], &s->W[0], &s->W[1], &s->target, &s->rhs, &s->specificVolume,
+                     &s->velocity, &s->pressure, &s->temperature, &s->mu, &s->lambda, &s->kappa,
+                     &s->stressTensor, &s->heatFlux, &s->rk1, &s->rk2, &s->viscFluxCart})
+    mg_field_free(f);
+  delete s;
+}
+
+// updateState (reference src/StateImpl.f90:466-537)
+int mg_state_update_impl(mg_state* s, const MgField* Qoverride) {
+  mg_grid* g = s->grid;
+  const MgField& Q = Qoverride ? *Qoverride : s->Q[s->cur];
+  const size_t N = g->N;
+  cudaStream_t st = mg_stream();
+  PtrSet a;
+  a.Q = Q.comp(0);
+  a.csQ = Q.compStride;
+  a.v = s->specificVolume.comp(0);
+  a.u = s->velocity.comp(0);
+  a.p = s->pressure.comp(0);
+  a.T = s->temperature.comp(0);
+  a.mu = s->opt.viscosityOn ? s->mu.comp(0) : nullptr;
+  a.lam = s->opt.viscosityOn ? s->lambda.comp(0) : nullptr;
+  a.kap = s->opt.viscosityOn ? s->kappa.comp(0) : nullptr;
+  a.cs = s->velocity.compStride;
+  a.N = N;
+  const PhysParams pp = s->phys();
+  MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
+    k_dependent<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a, pp);
+    return 0;
+  }));
+  MG_CUDA(cudaGetLastError());
+  if (s->opt.viscosityOn) {
+    MG_TRY(mg_grid_gradient_dev(g, s->velocity.comp(0), s->velocity.compStride, s->nD, &s->stressTensor,
+                                &g->scratchA));
+    MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
+      k_stress<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(s->stressTensor.comp(0), s->stressTensor.compStride,
+                                                               s->mu.comp(0), s->lambda.comp(0), N);
+      return 0;
+    }));
+    MG_TRY(mg_grid_gradient_dev(g, s->temperature.comp(0), s->temperature.compStride, 1, &s->heatFlux,
+                                &g->scratchA));
+    k_heatflux<<<nblocks(N), 256, 0, st>>>(s->heatFlux.comp(0), s->heatFlux.compStride, s->nD, s->kappa.comp(0), N);
+    MG_CUDA(cudaGetLastError());
+  }
+  s->dependentValid = true;
+  return 0;
+}
+
+// addDissipation (reference src/RhsHelperImpl.f90:10-87)
+static int add_dissipation_general(mg_state* s, int mode) {
+  mg_grid* g = s->grid;
+  if (!s->opt.dissipationOn) return 0;
+  const size_t N = g->N;
+  cudaStream_t st = mg_stream();
+  const double amount = mode == MG_ADJOINT ? -s->opt.dissipationAmount : s->opt.dissipationAmount;
+  const MgField& X = mode == MG_FORWARD ? s->Q[s->cur] : s->W[s->curW];
+  MgField& A = g->scratchA;
+  MgField& B = g->scratchB;
+  for (int i = 0; i < s->nD; ++i) {
+    MG_TRY(mg_grid_apply(g, g->dissipation[i], X.comp(0), X.compStride, A.comp(0), A.compStride, s->nU));
+    const double* result = A.comp(0);
+    if (!g->compositeDissipation) {
+      k_scale_by<<<nblocks(N), 256, 0, st>>>(A.comp(0), A.compStride, s->nU, g->arcLengths.comp(i), -1.0, N);
+      if (g->procDims[2] > 1 && i == 2) MG_FAIL("general path: slab-decomposed dissipation needs the fused path");
+      MG_TRY(mg_grid_apply(g, g->dissipationTranspose[i], A.comp(0), A.compStride, B.comp(0), B.compStride, s->nU));
+      MG_TRY(mg_norm_launch(g->firstDerivative[i], B.comp(0), B.compStride, s->nU, g->localSize, 1, st));
+      result = B.comp(0);
+    }
+    k_axpy<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), result, s->rhs.compStride, A.compStride, s->nU, amount, N);
+    MG_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// computeRhsForward (reference src/RhsHelperImpl.f90:254-354)
+int mg_state_rhs_forward_general(mg_state* s) {
+  mg_grid* g = s->grid;
+  const size_t N = g->N;
+  cudaStream_t st = mg_stream();
+  const int nD = s->nD, nU = s->nU;
+  MgField& Fh = g->scratchA;
+  MgField& Dv = g->scratchB;
+  if (s->keepViscousFluxes && s->opt.viscosityOn && s->viscFluxCart.nComp < nU * nD)
+    MG_TRY(mg_field_alloc(g, nU * nD, &s->viscFluxCart));
+  FluxArgs a;
+  const MgField& Q = s->Q[s->cur];
+  a.Q = Q.comp(0);
+  a.csQ = Q.compStride;
+  a.u = s->velocity.comp(0);
+  a.pr = s->pressure.comp(0);
+  a.tau = s->opt.viscosityOn ? s->stressTensor.comp(0) : nullptr;
+  a.q = s->opt.viscosityOn ? s->heatFlux.comp(0) : nullptr;
+  a.m = g->metrics.comp(0);
+  a.Fhat = Fh.comp(0);
+  a.Fv = (s->keepViscousFluxes && s->opt.viscosityOn) ? s->viscFluxCart.comp(0) : nullptr;
+  a.cs = Fh.compStride;
+  a.N = N;
+  a.viscous = s->opt.viscosityOn;
+  a.curvilinear = g->isCurvilinear;
+  MG_TRY(dispatch_nd(nD, [&](auto nd) {
+    k_flux<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a);
+    return 0;
+  }));
+  MG_CUDA(cudaGetLastError());
+  if (s->keepViscousFluxes && s->opt.viscosityOn) MG_TRY(mg_patches_collect_viscous(s));
+  for (int i = 0; i < nD; ++i) {
+    if (g->procDims[2] > 1 && i == 2) MG_FAIL("general path: slab-decomposed flux derivative needs the fused path");
+    MG_TRY(mg_grid_apply(g, g->firstDerivative[i], Fh.comp(nU * i), Fh.compStride, Dv.comp(nU * i), Dv.compStride, nU));
+  }
+  k_neg_sum<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), Dv.comp(0), Dv.compStride, nU, nD, N);
+  MG_CUDA(cudaGetLastError());
+  return add_dissipation_general(s, MG_FORWARD);
+}
+
+// computeRhsAdjoint (reference src/RhsHelperImpl.f90:356-596)
+int mg_state_rhs_adjoint_general(mg_state* s) {
+  mg_grid* g = s->grid;
+  const size_t N = g->N;
+  cudaStream_t st = mg_stream();
+  const int nD = s->nD, nU = s->nU;
+  MgField& A = g->scratchA;
+  MgField& B = g->scratchB;
+  const MgField& W = s->W[s->curW];
+  const MgField& Q = s->Q[s->cur];
+  if (g->procDims[2] > 1) MG_FAIL("general path: slab-decomposed adjoint needs the fused path");
+  for (int i = 0; i < nD; ++i)
+    MG_TRY(mg_grid_apply(g, g->adjointFirstDerivative[i], W.comp(0), W.compStride, A.comp(nU * i), A.compStride, nU));
+  AdjArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.Q = Q.comp(0);
+  a.csQ = Q.compStride;
+  a.v = s->specificVolume.comp(0);
+  a.u = s->velocity.comp(0);
+  a.T = s->temperature.comp(0);
+  if (s->opt.viscosityOn) {
+    a.tau = s->stressTensor.comp(0);
+    a.q = s->heatFlux.comp(0);
+    a.mu = s->mu.comp(0);
+    a.lam = s->lambda.comp(0);
+    a.kap = s->kappa.comp(0);
+  }
+  a.m = g->metrics.comp(0);
+  a.jac = g->jacobian.comp(0);
+  a.dW = A.comp(0);
+  a.rhs = s->rhs.comp(0);
+  a.diff = B.comp(0);
+  a.cs = A.compStride;
+  a.N = N;
+  a.viscous = s->opt.viscosityOn;
+  a.curvilinear = g->isCurvilinear;
+  a.gamma = s->opt.ratioOfSpecificHeats;
+  a.powerLaw = s->opt.powerLawExponent;
+  MG_TRY(dispatch_nd(nD, [&](auto nd) {
+    k_adjoint_point<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a);
+    return 0;
+  }));
+  MG_CUDA(cudaGetLastError());
+  auto finish = [&](MgField& src, double sign) -> int {
+    // derivative of src(:, :, j) along j into A, then the variable change
+    for (int j = 0; j < nD; ++j)
+      MG_TRY(mg_grid_apply(g, g->adjointFirstDerivative[j], src.comp((nU - 1) * j), src.compStride,
+                           A.comp((nU - 1) * j), A.compStride, nU - 1));
+    AdjFinishArgs f;
+    f.Q = Q.comp(0);
+    f.csQ = Q.compStride;
+    f.v = s->specificVolume.comp(0);
+    f.u = s->velocity.comp(0);
+    f.d = A.comp(0);
+    f.rhs = s->rhs.comp(0);
+    f.cs = A.compStride;
+    f.N = N;
+    f.gamma = s->opt.ratioOfSpecificHeats;
+    f.sign = sign;
+    MG_TRY(dispatch_nd(nD, [&](auto nd) {
+      k_adjoint_finish<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(f);
+      return 0;
+    }));
+    MG_CUDA(cudaGetLastError());
+    return 0;
+  };
+  if (s->opt.viscosityOn) MG_TRY(finish(B, 1.0));
+  MG_TRY(add_dissipation_general(s, MG_ADJOINT));
+  if (s->opt.viscosityOn && mg_patches_have_farfield(s)) {
+    // addFarFieldAdjointPenalty (reference src/RhsHelperImpl.f90:89-250)
+    MG_TRY(mg_field_zero(g, &B));
+    MG_TRY(mg_patches_farfield_adjoint_sources(s, &B));
+    MG_TRY(finish(B, -1.0));
+  }
+  return 0;
+}
+
+// computeRhs for one grid/state (reference src/RegionImpl.f90:1877-2027)
+int mg_state_compute_rhs_impl(mg_state* s, int mode) {
+  mg_grid* g = s->grid;
+  const size_t N = g->N;
+  cudaStream_t st = mg_stream();
+  if (!g->updated) MG_FAIL("computeRhs: grid metrics have not been computed (mg_grid_update)");
+  if (!s->dependentValid) MG_FAIL("computeRhs: dependent variables are stale (mg_state_update)");
+  if (mode == MG_FORWARD) MG_TRY(mg_state_rhs_forward_general(s));
+  else if (mode == MG_ADJOINT) MG_TRY(mg_state_rhs_adjoint_general(s));
+  else MG_FAIL("computeRhs: LINEARIZED mode is not implemented");
+  k_mul_jacobian<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), s->rhs.compStride, s->nU, g->jacobian.comp(0), N);
+  MG_CUDA(cudaGetLastError());
+  MG_TRY(mg_patches_apply(s, mode));
+  if (mode == MG_FORWARD) {
+    for (const auto& src : s->acousticSources) {
+      SrcArgs a;
+      a.rhsE = s->rhs.comp(s->nD + 1);
+      for (int i = 0; i < 3; ++i) {
+        a.x[i] = i < s->nD ? g->coordinates.comp(i) : nullptr;
+        a.loc[i] = src.loc[i];
+      }
+      a.iblank = g->iblank;
+      a.a = src.amplitude * cos(src.angularFrequency * s->time + src.phase);
+      a.gaussianFactor = src.gaussianFactor;
+      a.nD = s->nD;
+      a.N = N;
+      k_acoustic<<<nblocks(N), 256, 0, st>>>(a);
+    }
+  }
+  if (g->iblank)
+    k_mask_holes<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), s->rhs.compStride, s->nU, g->iblank, N);
+  MG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// substepForward / substepAdjoint (reference src/RK4IntegratorImpl.f90:65-270).  The state update that
+// the reference's callers issue after every substep (src/SolverImpl.f90:831-834) stays with the caller.
+int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int timestep, int stage) {
+  (void)timestep;
+  mg_grid* g = s->grid;
+  const size_t N = g->N;
+  cudaStream_t st = mg_stream();
+  if (stage < 1 || stage > 4) MG_FAIL("rk4 substep: stage must be 1..4");
+  RkArgs a;
+  a.cs = s->rhs.compStride;
+  a.N = N;
+  a.nU = s->nU;
+  a.b1 = s->rk1.comp(0);
+  a.b2 = s->rk2.comp(0);
+  if (mode == MG_FORWARD) {
+    if (stage == 1) s->timeProgressive = *time + dt / 2.0;
+    if (stage == 2 || stage == 4) { *time += dt / 2.0; s->time = *time; }
+    if (stage == 3) s->timeProgressive = *time + dt / 2.0;
+    MG_TRY(mg_state_compute_rhs_impl(s, MG_FORWARD));
+    a.R = s->rhs.comp(0);
+    a.Qin = s->Q[s->cur].comp(0);
+    a.Qout = s->Q[s->cur].comp(0);     // in place: the RHS is already materialised
+    a.stage = stage;
+    a.dt = dt;
+    k_rk4<<<nblocks(N), 256, 0, st>>>(a);
+    s->dependentValid = false;
+  } else if (mode == MG_ADJOINT) {
+    const double factor[5] = {0.0, 1.0, 0.5, 1.0, 2.0};
+    s->adjointForcingFactor = factor[stage];
+    if (stage == 4) s->timeProgressive = *time - dt / 2.0;
+    MG_TRY(mg_state_compute_rhs_impl(s, MG_ADJOINT));
+    a.R = s->rhs.comp(0);
+    a.Qin = s->W[s->curW].comp(0);
+    a.Qout = s->W[s->curW].comp(0);
+    a.stage = 5 - stage;               // adjoint stage 4 plays the role of RK stage 1, etc.
+    a.dt = -dt;
+    k_rk4<<<nblocks(N), 256, 0, st>>>(a);
+    if (stage == 4 || stage == 2) s->timeProgressive = *time;
+    if (stage == 3 || stage == 1) { *time -= dt / 2.0; s->time = *time; }
+  } else {
+    MG_FAIL("rk4 substep: LINEARIZED mode is not implemented");
+  }
+  MG_CUDA(cudaGetLastError());
+  return 0;
+}
