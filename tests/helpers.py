@@ -77,3 +77,10 @@ def relerr(a, b):
     scale = np.max(np.abs(b), axis=0, keepdims=True) if b.ndim > 1 else np.max(np.abs(b))
     scale = np.where(scale == 0, 1.0, scale)
     return float(np.max(np.abs(a - b) / scale))
+
+
+def relerr_global(a, b):
+    """Max-norm error scaled by the max of the whole array (entries of one tensor share a scale)."""
+    b = np.asarray(b)
+    scale = np.max(np.abs(b))
+    return float(np.max(np.abs(np.asarray(a) - b)) / (scale if scale > 0 else 1.0))
