@@ -57,6 +57,8 @@ enum {
   MG_Q_SPECIFIC_VOLUME = 4, MG_Q_VELOCITY = 5, MG_Q_PRESSURE = 6, MG_Q_TEMPERATURE = 7,
   MG_Q_DYNAMIC_VISCOSITY = 8, MG_Q_SECOND_VISCOSITY = 9, MG_Q_THERMAL_DIFFUSIVITY = 10,
   MG_Q_STRESS_TENSOR = 11, MG_Q_HEAT_FLUX = 12,
+  /* outputs of the fused sweep A: unique stress entries + heat flux (nD(nD+1)/2 + nD), dissipation term (nU) */
+  MG_Q_FUSED_TAUQ = 13, MG_Q_FUSED_DISSIPATION = 14,
   MG_G_COORDINATES = 100, MG_G_METRICS = 101, MG_G_JACOBIAN = 102, MG_G_NORM = 103,
   MG_G_ARC_LENGTHS = 104, MG_G_TARGET_MOLLIFIER = 105, MG_G_CONTROL_MOLLIFIER = 106
 };

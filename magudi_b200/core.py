@@ -23,6 +23,7 @@ SYMMETRIC, SKEW_SYMMETRIC, ASYMMETRIC = 0, 1, 2
 Q_CONSERVED, Q_ADJOINT, Q_TARGET, Q_RHS = 0, 1, 2, 3
 Q_SPECIFIC_VOLUME, Q_VELOCITY, Q_PRESSURE, Q_TEMPERATURE = 4, 5, 6, 7
 Q_DYNAMIC_VISCOSITY, Q_SECOND_VISCOSITY, Q_THERMAL_DIFFUSIVITY, Q_STRESS_TENSOR, Q_HEAT_FLUX = 8, 9, 10, 11, 12
+Q_FUSED_TAUQ, Q_FUSED_DISSIPATION = 13, 14
 G_COORDINATES, G_METRICS, G_JACOBIAN, G_NORM, G_ARC_LENGTHS = 100, 101, 102, 103, 104
 G_TARGET_MOLLIFIER, G_CONTROL_MOLLIFIER = 105, 106
 
@@ -285,6 +286,10 @@ class State:
             return nd
         if field == Q_STRESS_TENSOR:
             return nd * nd
+        if field == Q_FUSED_TAUQ:
+            return nd * (nd + 1) // 2 + nd
+        if field == Q_FUSED_DISSIPATION:
+            return nu
         return 1
 
     def set(self, field, a):

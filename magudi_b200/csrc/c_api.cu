@@ -328,6 +328,8 @@ static MgField* state_field(mg_state* s, int field) {
     case MG_Q_THERMAL_DIFFUSIVITY: return &s->kappa;
     case MG_Q_STRESS_TENSOR: return &s->stressTensor;
     case MG_Q_HEAT_FLUX: return &s->heatFlux;
+    case MG_Q_FUSED_TAUQ: return &s->tauq;
+    case MG_Q_FUSED_DISSIPATION: return &s->dissTerm;
   }
   return nullptr;
 }
@@ -361,7 +363,7 @@ int mg_state_destroy(mg_state* s) {
 int mg_state_set(mg_state* s, int field, const double* host) {
   MgField* f = s ? state_field(s, field) : nullptr;
   if (!f || !f->p) MG_FAIL("mg_state_set: unknown or unallocated field");
-  if (field == MG_Q_CONSERVED) s->dependentValid = false;
+  if (field == MG_Q_CONSERVED) { s->dependentValid = false; s->fusedValid = false; }
   if (field == MG_Q_TARGET)
     for (mg_patch* p : s->patches) p->AplusReady = false;
   return mg_field_upload(s->grid, f, host);
@@ -391,6 +393,7 @@ int mg_state_add_acoustic_source(mg_state* s, const double location[3], double a
 int mg_state_update(mg_state* s) {
   if (!s) MG_FAIL("mg_state_update: null handle");
   if (!s->grid->updated) MG_FAIL("mg_state_update: grid metrics have not been computed");
+  if (s->useFused && mg_fused_supported(s, MG_FORWARD)) return mg_fused_sweepA(s);
   return mg_state_update_impl(s, nullptr);
 }
 
@@ -444,6 +447,7 @@ int mg_region_destroy(mg_region* r) { delete r; return 0; }
 int mg_region_add_state(mg_region* r, mg_state* s) {
   if (!r || !s) MG_FAIL("mg_region_add_state: null argument");
   r->states.push_back(s);
+  s->useFused = r->fused;
   return 0;
 }
 int mg_region_update_patches(mg_region* r) {
@@ -451,7 +455,12 @@ int mg_region_update_patches(mg_region* r) {
   for (mg_state* s : r->states) MG_TRY(mg_patches_update_impl(s));
   return 0;
 }
-int mg_region_set_fused(mg_region* r, int enable) { if (!r) MG_FAIL("null region"); r->fused = enable; return 0; }
+int mg_region_set_fused(mg_region* r, int enable) {
+  if (!r) MG_FAIL("mg_region_set_fused: null handle");
+  r->fused = enable;
+  for (mg_state* s : r->states) s->useFused = enable;
+  return 0;
+}
 int mg_region_uses_fused(mg_region* r, int mode) {
   if (!r) return 0;
   if (!r->fused) return 0;
@@ -470,7 +479,10 @@ int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep
   for (mg_state* s : r->states) {
     t = *time;
     MG_TRY(mg_rk4_substep_impl(s, mode, &t, dt, timestep, stage));
-    if (updateStates && mode == MG_FORWARD) MG_TRY(mg_state_update_impl(s, nullptr));
+    if (updateStates && mode == MG_FORWARD) {
+      if (s->useFused && mg_fused_supported(s, MG_FORWARD)) MG_TRY(mg_fused_sweepA(s));
+      else MG_TRY(mg_state_update_impl(s, nullptr));
+    }
   }
   *time = t;
   return 0;

@@ -31,6 +31,10 @@ struct mg_state {
   MgField rk1, rk2;             // RK4 buffers (reference RK4IntegratorImpl.f90:32-35)
   MgField viscFluxCart;         // Cartesian viscous fluxes (nU*nD), kept only when a patch needs them
   bool keepViscousFluxes = false;
+  // fused path: outputs of sweep A (unique stress entries + heat flux; dissipation term)
+  MgField tauq, dissTerm;
+  bool fusedValid = false;
+  int useFused = 1;
   double time = 0.0, timeProgressive = 0.0, adjointForcingFactor = 1.0;
   struct Source { double loc[3], amplitude, angularFrequency, gaussianFactor, phase; };
   std::vector<Source> acousticSources;
@@ -59,3 +63,6 @@ int mg_patches_apply(mg_state* s, int mode);
 int mg_patches_collect_viscous(mg_state* s);
 int mg_patches_farfield_adjoint_sources(mg_state* s, MgField* temp1);
 bool mg_patches_have_farfield(const mg_state* s);
+int mg_fused_sweepA(mg_state* s);
+int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt);
+void mg_count_launches(int n);

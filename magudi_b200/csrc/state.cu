@@ -356,7 +356,7 @@ void mg_state_destroy_impl(mg_state* s) {
   if (!s) return;
   for (MgField* f : {&s->Q[0], &s->Q[1], &s->W[0], &s->W[1], &s->target, &s->rhs, &s->specificVolume,
                      &s->velocity, &s->pressure, &s->temperature, &s->mu, &s->lambda, &s->kappa,
-                     &s->stressTensor, &s->heatFlux, &s->rk1, &s->rk2, &s->viscFluxCart})
+                     &s->stressTensor, &s->heatFlux, &s->rk1, &s->rk2, &s->viscFluxCart, &s->tauq, &s->dissTerm})
     mg_field_free(f);
   delete s;
 }
@@ -551,10 +551,17 @@ int mg_state_compute_rhs_impl(mg_state* s, int mode) {
   const size_t N = g->N;
   cudaStream_t st = mg_stream();
   if (!g->updated) MG_FAIL("computeRhs: grid metrics have not been computed (mg_grid_update)");
-  if (!s->dependentValid) MG_FAIL("computeRhs: dependent variables are stale (mg_state_update)");
+  if (mode != MG_FORWARD && mode != MG_ADJOINT) MG_FAIL("computeRhs: LINEARIZED mode is not implemented");
+  if (s->useFused && mg_fused_supported(s, mode)) {
+    // fused sweeps: the dependent variables live in the sweep-A outputs (no patches on this path)
+    if (!s->fusedValid) MG_TRY(mg_fused_sweepA(s));
+    return mg_fused_sweepB(s, 0, 0, 0.0);
+  }
+  // The reference's callers run state%update after every substep (src/SolverImpl.f90:831-834); here
+  // it is refreshed on demand.
+  if (!s->dependentValid) MG_TRY(mg_state_update_impl(s, nullptr));
   if (mode == MG_FORWARD) MG_TRY(mg_state_rhs_forward_general(s));
-  else if (mode == MG_ADJOINT) MG_TRY(mg_state_rhs_adjoint_general(s));
-  else MG_FAIL("computeRhs: LINEARIZED mode is not implemented");
+  else MG_TRY(mg_state_rhs_adjoint_general(s));
   k_mul_jacobian<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), s->rhs.compStride, s->nU, g->jacobian.comp(0), N);
   MG_CUDA(cudaGetLastError());
   MG_TRY(mg_patches_apply(s, mode));
@@ -598,6 +605,10 @@ int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int time
     if (stage == 1) s->timeProgressive = *time + dt / 2.0;
     if (stage == 2 || stage == 4) { *time += dt / 2.0; s->time = *time; }
     if (stage == 3) s->timeProgressive = *time + dt / 2.0;
+    if (s->useFused && mg_fused_supported(s, MG_FORWARD)) {
+      if (!s->fusedValid) MG_TRY(mg_fused_sweepA(s));
+      return mg_fused_sweepB(s, 1, stage, dt);
+    }
     MG_TRY(mg_state_compute_rhs_impl(s, MG_FORWARD));
     a.R = s->rhs.comp(0);
     a.Qin = s->Q[s->cur].comp(0);
@@ -606,6 +617,7 @@ int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int time
     a.dt = dt;
     k_rk4<<<nblocks(N), 256, 0, st>>>(a);
     s->dependentValid = false;
+    s->fusedValid = false;
   } else if (mode == MG_ADJOINT) {
     const double factor[5] = {0.0, 1.0, 0.5, 1.0, 2.0};
     s->adjointForcingFactor = factor[stage];
