@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Headline benchmark: grid-point RHS evaluations per second (fp64, forward + adjoint, RK4) on the
+C3 workload of BASELINE.json (3-D periodic viscous box, SBP 3-6, 16.8 M points per GPU).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference
+
+One "step" = one RK4 time step of the forward solve (4 RHS evaluations + state updates, storing the
+substep states for the adjoint) followed by one RK4 time step of the discrete adjoint (4 adjoint RHS
+evaluations, each after restoring + updating the stored forward substep state) = 8 RHS evaluations per
+grid point.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "grid-point RHS evals/sec (fp64, fwd+adjoint)"
+UNIT = "point-stages/s"
+# algorithmic bytes per grid point per RK stage (rectilinear, nU = 5, G = 4)
+BYTES_FORWARD = 448.0           # two sweeps: (5+4+9) + (5+9+4+20) doubles
+BYTES_ADJOINT = 912.0           # three sweeps + checkpoint store/load
+BYTES_SWEEP_A = (5 + 4 + 9) * 8.0
+BYTES_SWEEP_B = (5 + 9 + 4 + 20) * 8.0
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_port_rate(n=48, steps=1, warmup=0):
+    """Time the oracle (NumPy port of the reference algorithm, reference-faithful loop structure incl.
+    per-apply ghost copies) on a bounded sample of the same workload: an n^3 periodic box, forward +
+    adjoint RK4 step.  Returns (point-stages/s, seconds per step, description)."""
+    from oracle import grid as og
+    from oracle import rhs as orhs
+    from magudi_b200 import workload as wl
+    shape = (n, n, n)
+    g = og.Grid(shape, (og.PLANE,) * 3, (2 * np.pi,) * 3, isCurvilinear=False)
+    g.coordinates[:, :] = wl.c3_coordinates(shape, (0, 0, 0), shape)
+    o = wl.c3_options()
+    opt = orhs.SolverOptions(ratioOfSpecificHeats=o.ratioOfSpecificHeats, viscosityOn=True,
+                             reynoldsNumberInverse=o.reynoldsNumberInverse,
+                             prandtlNumberInverse=o.prandtlNumberInverse, powerLawExponent=o.powerLawExponent,
+                             bulkViscosityRatio=o.bulkViscosityRatio, dissipationOn=True,
+                             compositeDissipation=False, dissipationAmount=o.dissipationAmount,
+                             useTargetState=False, discretizationType="SBP 3-6")
+    g.setupSpatialDiscretization("SBP 3-6", False)
+    g.update()
+    s = orhs.State(g, opt)
+    s.conservedVariables[:, :] = wl.c3_initial_condition(g.coordinates)
+    s.adjointVariables[:, :] = wl.c3_adjoint_field(g.nGridPoints)
+    s.update(g, opt)
+    integ = orhs.RK4Integrator(s)
+    rhs_fn = lambda mode, ts, stage: orhs.computeRhs(mode, opt, g, s)
+    dt = 1e-3
+
+    def one_step(t):
+        stored = []
+        for stage in range(1, 5):
+            stored.append(s.conservedVariables.copy())
+            t = integ.substepForward(rhs_fn, s, t, dt, 0, stage)
+            s.update(g, opt)
+        for stage in range(4, 0, -1):
+            s.conservedVariables[:, :] = stored[stage - 1]
+            s.update(g, opt)
+            t = integ.substepAdjoint(rhs_fn, s, t, dt, 0, stage)
+        return t
+
+    t = 0.0
+    for _ in range(warmup):
+        t = one_step(t)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        t = one_step(t)
+    el = (time.perf_counter() - t0) / steps
+    return 8.0 * g.nGridPoints / el, el, f"{n}^3 periodic box, 1 forward + 1 adjoint RK4 step (8 RHS evals/point), NumPy port"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_size
+    rate, sec, sample = cpu_port_rate(n, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": max(1, args.steps), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3 3-D periodic viscous box (KolmogorovFlow flags), SBP 3-6, forward+adjoint RK4",
+                   "sample": sample, "note": "the Fortran/MPI reference cannot be built in this image (no Fortran "
+                   "compiler, no MPI): this arm times the oracle port of its algorithm"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_native(args):
+    import torch
+    import magudi_b200 as mb
+    from magudi_b200 import _lib, core, workload as wl
+    from magudi_b200 import parallel as par
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.init(local_rank)
+
+    shape = wl.WEAK_SCALING_SHAPES.get(world)
+    if args.size:
+        shape = (args.size, args.size, args.size * world)
+    if shape is None:
+        shape = (256, 256, 256 * world)
+    opt, grid, state, region, xyz = wl.build_c3(shape, (1, 1, world), (0, 0, rank), rank)
+    halo = par.GpuHalo(grid, rank, world, dev) if world > 1 else None
+    R = 3
+    if halo:
+        halo.exchange(None, core.G_COORDINATES, 3, R)
+    assert not grid.update()
+    if halo:
+        halo.exchange(None, core.G_METRICS, 9, R)
+        halo.exchange(None, core.G_JACOBIAN, 1, R)
+        halo.exchange(None, core.G_ARC_LENGTHS, 3, R)
+    N = grid.nGridPoints
+    Q0 = wl.c3_initial_condition(xyz, rank=rank)
+    W0 = wl.c3_adjoint_field(N, rank=rank)
+    state.conservedVariables = Q0
+    state.adjointVariables = W0
+    integ = mb.RK4Integrator(region)
+    fused_fwd = region.usesFused(mb.FORWARD)
+    fused_adj = region.usesFused(mb.ADJOINT)
+    if not fused_fwd:
+        raise SystemExit("bench.py: the fused forward path does not cover the benchmark configuration")
+    dt = 1e-3
+
+    def update_state():
+        if halo:
+            halo.exchange(state, core.Q_CONSERVED, 5, R)
+        state.update()
+        if halo:
+            halo.exchange(state, core.Q_FUSED_TAUQ, 9, R)
+
+    def forward_step(t, step):
+        for stage in range(1, 5):
+            state.checkpointStore(stage - 1)
+            t = integ.substepForward(t, dt, step, stage, updateStates=False)
+            update_state()
+        return t
+
+    def adjoint_step(t, step):
+        for stage in range(4, 0, -1):
+            state.checkpointLoad(stage - 1)
+            update_state()
+            t = integ.substepAdjoint(t, dt, step, stage)
+        return t
+
+    do_adjoint = (world == 1) or fused_adj      # the general adjoint path is single-rank
+
+    def one_step(t, step):
+        t = forward_step(t, step)
+        if do_adjoint:
+            t = adjoint_step(t, step)
+        return t
+
+    update_state()
+    stream = torch.cuda.ExternalStream(lib.mg_stream_handle(), device=dev)
+
+    def barrier():
+        _lib.check(lib.mg_synchronize())
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    t = 0.0
+    for w in range(args.warmup):
+        t = one_step(t, w)
+    barrier()
+
+    # ---- timed region: device time with CUDA events on the launching stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.mg_profile_enable(1)
+    launches0 = lib.mg_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ef = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e0.record(stream)
+    wall0 = time.perf_counter()
+    fwd_ms = 0.0
+    for k in range(args.steps):
+        t = forward_step(t, args.warmup + k)
+        ef[k].record(stream)
+        if do_adjoint:
+            t = adjoint_step(t, args.warmup + k)
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    total_ms = e0.elapsed_time(e1)
+    launches = lib.mg_kernel_launch_count() - launches0
+    import ctypes as C
+    prof = {}
+    for name in ("sweepA", "sweepB", "adjointA", "adjointB", "adjointC"):
+        ms, n = C.c_double(0), C.c_longlong(0)
+        _lib.check(lib.mg_profile_get(name.encode(), C.byref(ms), C.byref(n)))
+        if n.value:
+            prof[name] = {"ms": ms.value, "launches": n.value, "avg_ms": ms.value / n.value}
+    lib.mg_profile_enable(0)
+
+    # max over ranks
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    evals_per_point = 8 if do_adjoint else 4
+    n_global = N * world
+    value = evals_per_point * n_global * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end leg: host (pinned) buffers in, host buffers out, through the public API
+    e2e = None
+    if rank == 0 or world > 1:
+        hQ = torch.from_numpy(np.asfortranarray(Q0).T.copy()).pin_memory()     # (5, N) contiguous == (N,5) Fortran
+        hW = torch.from_numpy(np.asfortranarray(W0).T.copy()).pin_memory()
+        oQ = torch.empty_like(hQ).pin_memory()
+        oW = torch.empty_like(hW).pin_memory()
+        esteps = max(1, min(args.steps, 3))
+        barrier()
+        c0 = time.perf_counter()
+        for k in range(esteps):
+            state.setFromPointer(core.Q_CONSERVED, hQ.data_ptr())
+            state.setFromPointer(core.Q_ADJOINT, hW.data_ptr())
+            update_state()
+            tt_ = one_step(0.0, k)
+            state.getToPointer(core.Q_CONSERVED, oQ.data_ptr())
+            state.getToPointer(core.Q_ADJOINT, oW.data_ptr())
+        barrier()
+        esec = (time.perf_counter() - c0) / esteps
+        if world > 1:
+            import torch.distributed as dist
+            tt = torch.tensor([esec], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            esec = float(tt.item())
+        e2e = {"value": evals_per_point * n_global / esec, "unit": UNIT,
+               "h2d_bytes_per_step": int(2 * N * 5 * 8 * world), "d2h_bytes_per_step": int(2 * N * 5 * 8 * world),
+               "ms_per_step": esec * 1e3, "timer": "host wall clock around set(pinned)->step->get, max over ranks"}
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    # dominant kernel: the one with the largest share of device time
+    roofline = None
+    if prof:
+        dom = max(prof, key=lambda k: prof[k]["ms"])
+        bytes_per_launch = {"sweepA": BYTES_SWEEP_A, "sweepB": BYTES_SWEEP_B}.get(dom, BYTES_SWEEP_B) * N
+        achieved = bytes_per_launch / (prof[dom]["avg_ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "share_of_step": prof[dom]["ms"] / total_ms,
+                    "algorithmic_bytes_per_point": bytes_per_launch / N}
+    fwd_total_ms = sum(prof[k]["ms"] for k in ("sweepA", "sweepB") if k in prof)
+    path = {}
+    if fwd_total_ms > 0:
+        fwd_rate = 4 * N * args.steps / (fwd_total_ms * 1e-3)
+        path["forward"] = {"point_stages_per_s_per_gpu": fwd_rate, "bytes_model": BYTES_FORWARD,
+                           "frac_of_hbm_peak": fwd_rate * BYTES_FORWARD / 1e9 / peak}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, sec, sample = cpu_port_rate(args.cpu_size, steps=1, warmup=0)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C3 3-D periodic viscous box {shape[0]}x{shape[1]}x{shape[2]} "
+                               f"({N} points/GPU), KolmogorovFlow flags, SBP 3-6, non-composite dissipation",
+                   "evals_per_point_per_step": evals_per_point,
+                   "forward_path": "fused sweeps A+B" if fused_fwd else "general",
+                   "adjoint_path": ("fused" if fused_adj else "general operator-by-operator") if do_adjoint else "not run (multi-rank adjoint needs the fused adjoint)",
+                   "parallelism": f"slab decomposition along k over {world} GPU(s)",
+                   "l2_policy": "inputs larger than L2 (every field >= 134 MB per component set)"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "roofline_path": path, "kernels": prof, "cpu_baseline": cpu,
+        "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--size", type=int, default=0, help="override: size^3 points per GPU")
+    ap.add_argument("--cpu-size", type=int, default=64, help="edge of the bounded CPU sample box")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -161,6 +161,11 @@ int mg_state_add_acoustic_source(mg_state* s, const double location[3], double a
                                  double radius, double phase);
 /* %update: src/StateImpl.f90:466-537 */
 int mg_state_update(mg_state* s);
+/* device-resident substep buffer of the UniformCheckpointer (src/UniformCheckpointerImpl.f90:78-208):
+ * keep / restore the conserved variables of a substep in HBM instead of host RAM */
+int mg_state_checkpoint_store(mg_state* s, int slot);
+int mg_state_checkpoint_load(mg_state* s, int slot);
+int mg_state_checkpoint_clear(mg_state* s);
 
 /* ------------------------------------------------------------------ t_Patch */
 /* %setup: src/PatchImpl.f90:3-151 and the derived types' setup; amounts are the magudi.inp values
@@ -192,8 +197,14 @@ int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep
  * the configuration is covered) */
 int mg_region_set_fused(mg_region* r, int enable);
 int mg_region_uses_fused(mg_region* r, int mode);
-/* number of kernels this library has launched since mg_init (bench accounting) */
+/* number of hot-path kernels this library has launched since mg_init (bench accounting) */
 long long mg_kernel_launch_count(void);
+/* the CUDA stream (cudaStream_t) all kernels of this rank are launched on, for event timing */
+void* mg_stream_handle(void);
+/* per-kernel device timing with CUDA events on that stream: enable, run, then query the summed
+ * duration (ms) and launch count of one kernel family ("sweepA", "sweepB", ...); reset with enable */
+int mg_profile_enable(int enable);
+int mg_profile_get(const char* name, double* milliseconds, long long* launches);
 
 #ifdef __cplusplus
 }

@@ -46,6 +46,9 @@ SIGNATURES = {
     "mg_version": (C.c_int, []),
     "mg_synchronize": (C.c_int, []),
     "mg_kernel_launch_count": (C.c_longlong, []),
+    "mg_stream_handle": (C.c_void_p, []),
+    "mg_profile_enable": (C.c_int, [C.c_int]),
+    "mg_profile_get": (C.c_int, [C.c_char_p, _D, C.POINTER(C.c_longlong)]),
     "mg_stencil_create": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "mg_stencil_update": (C.c_int, [_P, C.c_int, _I3, _I3, _I3, C.c_int]),
     "mg_stencil_get_adjoint": (C.c_int, [_P, C.POINTER(_P)]),
@@ -78,6 +81,9 @@ SIGNATURES = {
     "mg_state_set_time": (C.c_int, [_P, C.c_double]),
     "mg_state_add_acoustic_source": (C.c_int, [_P, _D, C.c_double, C.c_double, C.c_double, C.c_double]),
     "mg_state_update": (C.c_int, [_P]),
+    "mg_state_checkpoint_store": (C.c_int, [_P, C.c_int]),
+    "mg_state_checkpoint_load": (C.c_int, [_P, C.c_int]),
+    "mg_state_checkpoint_clear": (C.c_int, [_P]),
     "mg_patch_create": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, _I3, C.c_double, C.c_double, C.POINTER(_P)]),
     "mg_patch_num_points": (C.c_int, [_P, _I3, _I3, _I3]),
     "mg_patch_set_array": (C.c_int, [_P, C.c_char_p, C.c_int, _P]),

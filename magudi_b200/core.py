@@ -322,6 +322,23 @@ class State:
         """``t_State%update`` (dependent variables, transport, stress tensor, heat flux)."""
         check(L.lib().mg_state_update(self._h))
 
+    def checkpointStore(self, slot):
+        """Keep the conserved variables of a substep in HBM (device-resident UniformCheckpointer buffer)."""
+        check(L.lib().mg_state_checkpoint_store(self._h, int(slot)))
+
+    def checkpointLoad(self, slot):
+        check(L.lib().mg_state_checkpoint_load(self._h, int(slot)))
+
+    def checkpointClear(self):
+        check(L.lib().mg_state_checkpoint_clear(self._h))
+
+    def setFromPointer(self, field, ptr):
+        """``mg_state_set`` from a raw host (e.g. pinned) or device pointer holding (N, nComp) fp64."""
+        check(L.lib().mg_state_set(self._h, field, C.c_void_p(ptr)))
+
+    def getToPointer(self, field, ptr):
+        check(L.lib().mg_state_get(self._h, field, C.c_void_p(ptr)))
+
     def addPatch(self, patchType, name, normalDirection, extent, inviscidPenaltyAmount=1.0,
                  viscousPenaltyAmount=1.0):
         p = Patch(self, patchType, name, normalDirection, extent, inviscidPenaltyAmount, viscousPenaltyAmount)

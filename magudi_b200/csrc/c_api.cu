@@ -27,6 +27,27 @@ cudaStream_t mg_stream() { return g_stream; }
 int mg_num_sms() { return g_sms; }
 void mg_count_launches(int n) { g_launches += n; }
 
+// ---- optional per-kernel event timing (bench.py roofline accounting)
+namespace {
+struct ProfEntry { std::string name; cudaEvent_t e0, e1; };
+std::vector<ProfEntry> g_prof;
+bool g_profOn = false;
+}  // namespace
+bool mg_profile_on() { return g_profOn; }
+void mg_profile_begin(const char* name) {
+  if (!g_profOn) return;
+  ProfEntry p;
+  p.name = name;
+  cudaEventCreate(&p.e0);
+  cudaEventCreate(&p.e1);
+  cudaEventRecord(p.e0, g_stream);
+  g_prof.push_back(p);
+}
+void mg_profile_end() {
+  if (!g_profOn || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().e1, g_stream);
+}
+
 struct mg_region {
   std::vector<mg_state*> states;
   int fused = 1;
@@ -94,6 +115,30 @@ int mg_synchronize(void) {
   return 0;
 }
 long long mg_kernel_launch_count(void) { return g_launches.load(); }
+void* mg_stream_handle(void) { return (void*)g_stream; }
+int mg_profile_enable(int enable) {
+  for (auto& p : g_prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+  g_prof.clear();
+  g_profOn = enable != 0;
+  return 0;
+}
+int mg_profile_get(const char* name, double* ms, long long* launches) {
+  if (!name || !ms || !launches) MG_FAIL("mg_profile_get: null argument");
+  if (g_device < 0) MG_FAIL("mg_profile_get: mg_init has not been called");
+  MG_CUDA(cudaStreamSynchronize(g_stream));
+  double total = 0.0;
+  long long n = 0;
+  for (auto& p : g_prof)
+    if (p.name == name) {
+      float t = 0.f;
+      MG_CUDA(cudaEventElapsedTime(&t, p.e0, p.e1));
+      total += t;
+      ++n;
+    }
+  *ms = total;
+  *launches = n;
+  return 0;
+}
 
 // ----------------------------------------------------------------------------- stencil
 int mg_stencil_create(const char* scheme, mg_stencil** out) { return mg_stencil_create_impl(scheme, out); }
@@ -357,6 +402,7 @@ int mg_state_create(mg_grid* g, const mg_options* o, mg_state** out) {
 int mg_state_destroy(mg_state* s) {
   if (!s) return 0;
   for (mg_patch* p : s->patches) mg_patch_destroy_impl(p);
+  for (MgField& f : s->checkpoints) mg_field_free(&f);
   mg_state_destroy_impl(s);
   return 0;
 }
@@ -395,6 +441,32 @@ int mg_state_update(mg_state* s) {
   if (!s->grid->updated) MG_FAIL("mg_state_update: grid metrics have not been computed");
   if (s->useFused && mg_fused_supported(s, MG_FORWARD)) return mg_fused_sweepA(s);
   return mg_state_update_impl(s, nullptr);
+}
+
+int mg_state_checkpoint_store(mg_state* s, int slot) {
+  if (!s || slot < 0) MG_FAIL("mg_state_checkpoint_store: invalid argument");
+  if ((size_t)slot >= s->checkpoints.size()) s->checkpoints.resize(slot + 1);
+  MgField& f = s->checkpoints[slot];
+  if (!f.p) MG_TRY(mg_field_alloc(s->grid, s->nU, &f));
+  const MgField& Q = s->Q[s->cur];
+  MG_CUDA(cudaMemcpyAsync(f.p, Q.p, Q.compStride * (size_t)s->nU * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+  return 0;
+}
+int mg_state_checkpoint_load(mg_state* s, int slot) {
+  if (!s || slot < 0 || (size_t)slot >= s->checkpoints.size() || !s->checkpoints[slot].p)
+    MG_FAIL("mg_state_checkpoint_load: empty slot");
+  const MgField& f = s->checkpoints[slot];
+  MgField& Q = s->Q[s->cur];
+  MG_CUDA(cudaMemcpyAsync(Q.p, f.p, Q.compStride * (size_t)s->nU * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+  s->dependentValid = false;
+  s->fusedValid = false;
+  return 0;
+}
+int mg_state_checkpoint_clear(mg_state* s) {
+  if (!s) MG_FAIL("mg_state_checkpoint_clear: null handle");
+  for (MgField& f : s->checkpoints) mg_field_free(&f);
+  s->checkpoints.clear();
+  return 0;
 }
 
 // ------------------------------------------------------------------------------- patch

@@ -33,6 +33,7 @@ struct mg_state {
   bool keepViscousFluxes = false;
   // fused path: outputs of sweep A (unique stress entries + heat flux; dissipation term)
   MgField tauq, dissTerm;
+  std::vector<MgField> checkpoints;   // device-resident forward substep states (adjoint replay)
   bool fusedValid = false;
   int useFused = 1;
   double time = 0.0, timeProgressive = 0.0, adjointForcingFactor = 1.0;
@@ -66,3 +67,5 @@ bool mg_patches_have_farfield(const mg_state* s);
 int mg_fused_sweepA(mg_state* s);
 int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt);
 void mg_count_launches(int n);
+void mg_profile_begin(const char* name);
+void mg_profile_end();

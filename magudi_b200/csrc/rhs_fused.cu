@@ -637,7 +637,9 @@ int launchA(const FusedArgs& a, dim3 grid, cudaStream_t st) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
+  mg_profile_begin("sweepA");
   kern<<<grid, NT, smem, st>>>(a);
+  mg_profile_end();
   MG_CUDA(cudaGetLastError());
   mg_count_launches(1);
   return 0;
@@ -655,7 +657,9 @@ int launchB(const FusedArgs& a, dim3 grid, cudaStream_t st) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
+  mg_profile_begin("sweepB");
   kern<<<grid, NT, smem, st>>>(a);
+  mg_profile_end();
   MG_CUDA(cudaGetLastError());
   mg_count_launches(1);
   return 0;

@@ -1,0 +1,105 @@
+"""Slab (direction-3) domain decomposition across the GPUs of one box: one process per GPU,
+``torch.distributed`` for the plumbing.  Replaces ``fillGhostPoints`` (reference
+``src/MPIHelperImpl.f90:113-389``) for the fused sweeps: ghost planes are contiguous per component,
+exchanged once per sweep with the two k-neighbours (periodic wrap included), and scalar reductions
+(``MPI_Allreduce`` in ``src/GridImpl.f90:1112,1166``) become ``all_reduce``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from ._lib import check
+
+
+class HaloExchanger:
+    """Exchange ``width`` ghost planes of a field with the previous / next rank along k.
+
+    ``pack(side, width, buffer)`` must fill ``buffer`` with the interior planes next to face ``side``
+    (0 = low k, 1 = high k); ``unpack(side, width, buffer)`` must store a received buffer into the ghost
+    planes of that face.  Message order is fixed so that it also works when prev == next (2 ranks):
+    each rank first sends its LOW planes (to prev) then its HIGH planes (to next), and first receives
+    the HIGH ghost (next's low planes) then the LOW ghost (prev's high planes).
+    """
+
+    def __init__(self, rank, world, periodic=True, device=None, group=None):
+        self.rank, self.world, self.periodic = rank, world, periodic
+        self.device = device
+        self.group = group
+        self.prev = (rank - 1) % world if (periodic or rank > 0) else None
+        self.next = (rank + 1) % world if (periodic or rank < world - 1) else None
+        self._buffers = {}
+
+    def _bufs(self, key, count, dtype=torch.float64):
+        b = self._buffers.get((key, count))
+        if b is None:
+            b = [torch.empty(count, dtype=dtype, device=self.device) for _ in range(4)]
+            self._buffers[(key, count)] = b
+        return b
+
+    def exchange(self, key, count, width, pack, unpack):
+        if self.world == 1:
+            return
+        send_lo, send_hi, recv_hi, recv_lo = self._bufs(key, count)
+        pack(0, width, send_lo)
+        pack(1, width, send_hi)
+        ops = []
+        if self.prev is not None:
+            ops.append(dist.P2POp(dist.isend, send_lo, self.prev, group=self.group))
+        if self.next is not None:
+            ops.append(dist.P2POp(dist.isend, send_hi, self.next, group=self.group))
+        if self.next is not None:
+            ops.append(dist.P2POp(dist.irecv, recv_hi, self.next, group=self.group))
+        if self.prev is not None:
+            ops.append(dist.P2POp(dist.irecv, recv_lo, self.prev, group=self.group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        if self.device is not None and torch.device(self.device).type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        if self.next is not None:
+            unpack(1, width, recv_hi)
+        if self.prev is not None:
+            unpack(0, width, recv_lo)
+
+
+class GpuHalo:
+    """Halo exchange of library-owned fields (``mg_halo_pack`` / ``mg_halo_unpack``)."""
+
+    def __init__(self, grid, rank, world, device):
+        self.grid = grid
+        periodic = grid.periodicityType[2] != 0
+        self.ex = HaloExchanger(rank, world, periodic, device)
+        self.plane = grid.localSize[0] * grid.localSize[1]
+
+    def exchange(self, owner, field, ncomp, width=3):
+        lib = L.lib()
+        g = self.grid._h
+        oh = owner._h if owner is not None else None
+
+        def pack(side, w, buf):
+            check(lib.mg_halo_pack(g, oh, field, side, w, C.c_void_p(buf.data_ptr())))
+
+        def unpack(side, w, buf):
+            check(lib.mg_halo_unpack(g, oh, field, side, w, C.c_void_p(buf.data_ptr())))
+
+        self.ex.exchange(field, ncomp * width * self.plane, width, pack, unpack)
+
+
+def all_reduce_sum(value, device=None):
+    """Sum a host scalar over ranks (inner products, cost functional)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def all_reduce_max(value, device=None):
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
