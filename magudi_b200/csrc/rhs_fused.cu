@@ -120,15 +120,21 @@ __device__ __forceinline__ bool owns(int c, int n, int T, bool isLast) {
 }
 
 // ------------------------------------------------------------------------------- sweep A
-// Shared tile: NF fields on a (TY+2R) x (TX+2R) box (corners unused).
+// Shared memory: an in-plane tile of NF fields on a (TY+2R) x (TX+2R) box (corners unused) for the
+// output plane, plus the k-queue of (u, T) for the 2R+1 planes in flight.  Q's k-queue is in registers.
 template <int ND, int R, bool COMPOSITE, int DLO, int DN, int TLO, int TN>
-__global__ void __launch_bounds__(NT, 1) k_sweepA(FusedArgs a) {
+__global__ void __launch_bounds__(NT, 2) k_sweepA(FusedArgs a) {
   constexpr int NU = ND + 2;
   constexpr int NTAU = ND * (ND + 1) / 2;
   constexpr int W = TX + 2 * R, H = TY + 2 * R;
-  constexpr int NF = NU + ND + 1 + 2;          // Q, u, T, arc_i, arc_j
+  constexpr int NP = ND + 1;                   // u_0..u_{ND-1}, T
+  constexpr int NF = NP + NU + 2;              // (u,T), Q, arc_i, arc_j
+  constexpr int FQ = NP, FA = NP + NU;         // first field index of Q / arc in the tile
   constexpr int RK = (ND == 3) ? R : 0;        // k half-width
+  constexpr int NQ = 2 * RK + 1;
   extern __shared__ double smem[];
+  double* const T0 = smem;                                   // [NF][H][W]
+  double* const KQ = smem + (size_t)NF * H * W;              // [NQ][NP][NT]
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   int i0, j0;
   bool lastI, lastJ;
@@ -139,6 +145,19 @@ __global__ void __launch_bounds__(NT, 1) k_sweepA(FusedArgs a) {
   const bool inside = i < a.nx && j < a.ny;
   const long pij = (long)i + (long)a.nx * j;
   const double gamma = a.pp.gamma;
+  // widest closure block among the operators used along a direction
+  auto touches = [&](int d, int c0, int T, int n) {
+    int depth = a.D[d].depth;
+    if (a.diss) {
+      depth = max(depth, a.Dd[d].depth);
+      if (!COMPOSITE) depth = max(depth, max(a.Dt[d].depth + a.Dd[d].width, a.dir[d].normDepth));
+    }
+    return (a.dir[d].hasB0 && c0 < depth) || (a.dir[d].hasB1 && c0 + T > n - depth);
+  };
+  const bool fastI = !touches(0, i0, TX, a.nx);
+  const bool fastJ = !touches(1, j0, TY, a.ny);
+  double* const tc = T0 + (ty + R) * W + tx + R;             // own point; field stride H*W, row stride W
+  double* const kqc = KQ + threadIdx.x;                      // slot stride NP*NT, field stride NT
 
   // halo point handled by this thread (at most one): hk 0 none, 1 i-halo, 2 j-halo
   int hcol = 0, hrow = 0, hk = 0;
@@ -165,203 +184,307 @@ __global__ void __launch_bounds__(NT, 1) k_sweepA(FusedArgs a) {
 
   const int kc0 = a.kBeg + blockIdx.z * a.kChunk;
   const int kc1 = min(kc0 + a.kChunk, a.kEnd);
-  auto planeOf = [&](int k) -> long {
-    if (ND < 3) return 0;
-    int kk = k;
-    if (a.wrapK) kk = (k % a.nz + a.nz) % a.nz;
-    return (long)kk * a.plane;
+  auto wrapPlane = [&](int k) -> int {
+    if (ND < 3 || !a.wrapK) return k;
+    int kk = k % a.nz;
+    return kk < 0 ? kk + a.nz : kk;
   };
+  int ks = wrapPlane(kc0 - RK);
+  int slot = 0;                    // queue slot of the arriving plane s
 
-  double qq[2 * RK + 1][NU];       // Q at planes p-RK .. p+RK once the queue is primed
+  double qq[NQ][NU];               // Q at planes p-RK .. p+RK once the queue is primed
+  // The rotation below reads every entry each iteration: start from defined values (reading
+  // indeterminate registers is undefined behaviour and lets the optimiser break the rotation).
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int c = 0; c < NU; ++c) qq[q][c] = 0.0;
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
     // ---- arrival of plane s
 #pragma unroll
-    for (int q = 0; q < 2 * RK; ++q)
+    for (int q = 0; q < NQ - 1; ++q)
 #pragma unroll
       for (int c = 0; c < NU; ++c) qq[q][c] = qq[q + 1][c];
     if (inside) {
-      const long off = planeOf(s) + pij;
+      const double* __restrict__ Qp = a.Q + ((ND == 3) ? (long)ks * a.plane : 0) + pij;
 #pragma unroll
-      for (int c = 0; c < NU; ++c) qq[2 * RK][c] = a.Q[(size_t)c * a.cs + off];
+      for (int c = 0; c < NU; ++c) qq[NQ - 1][c] = Qp[(size_t)c * a.cs];
+      Prim<ND> sa;
+      dependent<ND>(qq[NQ - 1], gamma, sa);
+#pragma unroll
+      for (int d = 0; d < ND; ++d) kqc[((size_t)slot * NP + d) * NT] = sa.u[d];
+      kqc[((size_t)slot * NP + ND) * NT] = sa.T;
     }
     const int p = s - RK;
+    int sp0 = slot - RK;             // slot of plane p
+    if (sp0 < 0) sp0 += NQ;
+    int kp = ks - RK;                // storage plane of p
+    if (ND == 3 && a.wrapK && kp < 0) kp += a.nz;
+    if (ND == 3) {
+      ++ks;
+      if (a.wrapK && ks >= a.nz) ks -= a.nz;
+      if (++slot >= NQ) slot = 0;
+    }
     if (p < kc0) continue;
-    // ---- output plane p: build the in-plane tile
-    double* S = smem + (size_t)((p - kc0) & 1) * NF * H * W;
-    auto at = [&](int f, int row, int col) -> double& { return S[((size_t)f * H + row) * W + col]; };
-    const long poff = planeOf(p);
-    Prim<ND> sc;
+    // ---- output plane p: in-plane tile (own point from the queues, halo from global memory)
+    const long poff = (ND == 3) ? (long)kp * a.plane : 0;
+    double uT[NP];
     if (inside) {
-      dependent<ND>(qq[RK], gamma, sc);
 #pragma unroll
-      for (int c = 0; c < NU; ++c) at(c, ty + R, tx + R) = qq[RK][c];
+      for (int f = 0; f < NP; ++f) { uT[f] = kqc[((size_t)sp0 * NP + f) * NT]; tc[f * H * W] = uT[f]; }
 #pragma unroll
-      for (int d = 0; d < ND; ++d) at(NU + d, ty + R, tx + R) = sc.u[d];
-      at(NU + ND, ty + R, tx + R) = sc.T;
-      if (!COMPOSITE) {
-        at(NU + ND + 1, ty + R, tx + R) = a.arc[(size_t)0 * a.cs + poff + pij];
-        at(NU + ND + 2, ty + R, tx + R) = a.arc[(size_t)1 * a.cs + poff + pij];
+      for (int c = 0; c < NU; ++c) tc[(FQ + c) * H * W] = qq[RK][c];
+      if (!COMPOSITE && a.diss) {
+        tc[(FA + 0) * H * W] = a.arc[(size_t)0 * a.cs + poff + pij];
+        tc[(FA + 1) * H * W] = a.arc[(size_t)1 * a.cs + poff + pij];
       }
     }
     if (hk) {
       double Qh[NU];
       const long off = poff + hp;
+      double* const th = T0 + hrow * W + hcol;
 #pragma unroll
-      for (int c = 0; c < NU; ++c) { Qh[c] = a.Q[(size_t)c * a.cs + off]; at(c, hrow, hcol) = Qh[c]; }
+      for (int c = 0; c < NU; ++c) { Qh[c] = a.Q[(size_t)c * a.cs + off]; th[(FQ + c) * H * W] = Qh[c]; }
       Prim<ND> sh;
       dependent<ND>(Qh, gamma, sh);
 #pragma unroll
-      for (int d = 0; d < ND; ++d) at(NU + d, hrow, hcol) = sh.u[d];
-      at(NU + ND, hrow, hcol) = sh.T;
-      if (!COMPOSITE) at(NU + ND + hk, hrow, hcol) = a.arc[(size_t)(hk - 1) * a.cs + off];
+      for (int d = 0; d < ND; ++d) th[d * H * W] = sh.u[d];
+      th[ND * H * W] = sh.T;
+      if (!COMPOSITE && a.diss) th[(FA + hk - 1) * H * W] = a.arc[(size_t)(hk - 1) * a.cs + off];
     }
     __syncthreads();
-    if (!mine) continue;       // NB: no barrier after this point inside the iteration (double-buffered tile)
-
-    // ---- derivatives of (u, T) along xi, eta, zeta
-    double dxi[ND][ND + 1];    // dxi[direction][field]: fields u_0..u_{ND-1}, T
+    if (mine) {
+      auto at = [&](int f, int row, int col) -> double { return T0[((size_t)f * H + row) * W + col]; };
+      // ---- derivatives of (u, T) along xi, eta, zeta
+      double dxi[ND][NP];
 #pragma unroll
-    for (int f = 0; f < ND + 1; ++f) {
-      dxi[0][f] = line_apply(a.D[0], i, a.nx, [&](int cc) { return at(NU + f, ty + R, cc - i0 + R); });
-      dxi[1][f] = line_apply(a.D[1], j, a.ny, [&](int cc) { return at(NU + f, cc - j0 + R, tx + R); });
-    }
-    if constexpr (ND == 3) {
-      double acc[ND + 1];
+      for (int f = 0; f < NP; ++f) {
+        if (fastI) {
+          double r = 0.0;
 #pragma unroll
-      for (int f = 0; f < ND + 1; ++f) acc[f] = 0.0;
-#pragma unroll
-      for (int q = 1; q <= RK; ++q) {
-        Prim<ND> sp, sm;
-        dependent<ND>(qq[RK + q], gamma, sp);
-        dependent<ND>(qq[RK - q], gamma, sm);
-        const double cq = a.D[2].c[q - a.D[2].lo];
-#pragma unroll
-        for (int d = 0; d < ND; ++d) acc[d] += cq * (sp.u[d] - sm.u[d]);
-        acc[ND] += cq * (sp.T - sm.T);
-      }
-#pragma unroll
-      for (int f = 0; f < ND + 1; ++f) dxi[ND - 1][f] = acc[f];
-    }
-    // ---- gradient in physical space (reference src/GridImpl.f90:1357-1413), stress tensor, heat flux
-    const long off = poff + pij;
-    const double jac = a.jac[off];
-    double M[ND * ND];
-    if (a.curvilinear) {
-#pragma unroll
-      for (int c = 0; c < ND * ND; ++c) M[c] = a.m[(size_t)c * a.cs + off];
-    } else {
-#pragma unroll
-      for (int c = 0; c < ND * ND; ++c) M[c] = 0.0;
-#pragma unroll
-      for (int d = 0; d < ND; ++d) M[d + ND * d] = a.m[(size_t)(d + ND * d) * a.cs + off];
-    }
-    if (a.viscous) {
-      double g[ND * ND], gT[ND];
-#pragma unroll
-      for (int c = 0; c < ND; ++c)
-#pragma unroll
-        for (int jx = 0; jx < ND; ++jx) {
-          double r;
-          if (a.curvilinear) {
-            r = M[jx] * dxi[0][c];
-#pragma unroll
-            for (int d = 1; d < ND; ++d) r += M[jx + ND * d] * dxi[d][c];
-            r = jac * r;
-          } else {
-            r = jac * M[jx + ND * jx] * dxi[jx][c];
-          }
-          g[jx + ND * c] = r;
-        }
-#pragma unroll
-      for (int jx = 0; jx < ND; ++jx) {
-        double r;
-        if (a.curvilinear) {
-          r = M[jx] * dxi[0][ND];
-#pragma unroll
-          for (int d = 1; d < ND; ++d) r += M[jx + ND * d] * dxi[d][ND];
-          r = jac * r;
+          for (int q = 1; q <= R; ++q) r += a.D[0].c[R + q] * (tc[f * H * W + q] - tc[f * H * W - q]);
+          dxi[0][f] = r;
         } else {
-          r = jac * M[jx + ND * jx] * dxi[jx][ND];
+          dxi[0][f] = line_apply(a.D[0], i, a.nx, [&](int cc) { return at(f, ty + R, cc - i0 + R); });
         }
-        gT[jx] = r;
-      }
-      double mu, lam, kap, tau[ND * ND];
-      transport(sc.T, a.pp, mu, lam, kap);
-      stress_from_gradient<ND>(g, mu, lam, tau);
-      // unique entries: (0,0),(0,1)[,(0,2)],(1,1)[,(1,2),(2,2)] in row-major upper order
-      int t = 0;
+        if (fastJ) {
+          double r = 0.0;
 #pragma unroll
-      for (int r0 = 0; r0 < ND; ++r0)
-#pragma unroll
-        for (int c0 = r0; c0 < ND; ++c0) a.tauq[(size_t)(t++) * a.cs + off] = tau[c0 + ND * r0];
-#pragma unroll
-      for (int d = 0; d < ND; ++d) a.tauq[(size_t)(NTAU + d) * a.cs + off] = -kap * gT[d];
-    }
-    // ---- dissipation term  sum_dir Diss_dir(Q)   (reference src/RhsHelperImpl.f90:58-81)
-    if (a.diss) {
-      double dz[NU];
-#pragma unroll
-      for (int c = 0; c < NU; ++c) {
-        double r;
-        if (COMPOSITE) {
-          r = line_apply(a.Dd[0], i, a.nx, [&](int cc) { return at(c, ty + R, cc - i0 + R); });
-          r += line_apply(a.Dd[1], j, a.ny, [&](int cc) { return at(c, cc - j0 + R, tx + R); });
+          for (int q = 1; q <= R; ++q) r += a.D[1].c[R + q] * (tc[f * H * W + q * W] - tc[f * H * W - q * W]);
+          dxi[1][f] = r;
         } else {
-          r = line_dissipation(a.Dd[0], a.Dt[0], a.dir[0], i,
-                               [&](int cc) { return at(c, ty + R, cc - i0 + R); },
-                               [&](int cc) { return at(NU + ND + 1, ty + R, cc - i0 + R); });
-          r += line_dissipation(a.Dd[1], a.Dt[1], a.dir[1], j,
-                                [&](int cc) { return at(c, cc - j0 + R, tx + R); },
-                                [&](int cc) { return at(NU + ND + 2, cc - j0 + R, tx + R); });
+          dxi[1][f] = line_apply(a.D[1], j, a.ny, [&](int cc) { return at(f, cc - j0 + R, tx + R); });
         }
-        dz[c] = r;
       }
       if constexpr (ND == 3) {
-        if (COMPOSITE) {
 #pragma unroll
-          for (int c = 0; c < NU; ++c) {
-            double r = a.Dd[2].c[0 - a.Dd[2].lo] * qq[RK][c];
+        for (int f = 0; f < NP; ++f) dxi[ND - 1][f] = 0.0;
 #pragma unroll
-            for (int q = 1; q <= RK; ++q) r += a.Dd[2].c[q - a.Dd[2].lo] * (qq[RK + q][c] + qq[RK - q][c]);
-            dz[c] += r;
-          }
+        for (int q = 1; q <= RK; ++q) {
+          int sp = sp0 + q, sm = sp0 - q;
+          if (sp >= NQ) sp -= NQ;
+          if (sm < 0) sm += NQ;
+          const double cq = a.D[2].c[RK + q];
+#pragma unroll
+          for (int f = 0; f < NP; ++f)
+            dxi[ND - 1][f] += cq * (kqc[((size_t)sp * NP + f) * NT] - kqc[((size_t)sm * NP + f) * NT]);
+        }
+      }
+      // ---- gradient in physical space (reference src/GridImpl.f90:1357-1413), stress tensor, heat flux
+      const long off = poff + pij;
+      if (a.viscous) {
+        const double jac = a.jac[off];
+        double g[ND * ND], gT[ND];
+        if (a.curvilinear) {
+          double M[ND * ND];
+#pragma unroll
+          for (int c = 0; c < ND * ND; ++c) M[c] = a.m[(size_t)c * a.cs + off];
+#pragma unroll
+          for (int c = 0; c < NP; ++c)
+#pragma unroll
+            for (int jx = 0; jx < ND; ++jx) {
+              double r = M[jx] * dxi[0][c];
+#pragma unroll
+              for (int d = 1; d < ND; ++d) r += M[jx + ND * d] * dxi[d][c];
+              r = jac * r;
+              if (c < ND) g[jx + ND * c] = r; else gT[jx] = r;
+            }
         } else {
-          double tz[TN][NU];
 #pragma unroll
-          for (int e = 0; e < TN; ++e) {
-            const int ko = TLO + e;         // plane offset of this t sample
-            const double arc = a.arc[(size_t)2 * a.cs + planeOf(p + ko) + pij];
+          for (int jx = 0; jx < ND; ++jx) {
+            const double mj = jac * a.m[(size_t)(jx + ND * jx) * a.cs + off];
+#pragma unroll
+            for (int c = 0; c < ND; ++c) g[jx + ND * c] = mj * dxi[jx][c];
+            gT[jx] = mj * dxi[jx][ND];
+          }
+        }
+        double mu, lam, kap, tau[ND * ND];
+        transport(uT[ND], a.pp, mu, lam, kap);
+        stress_from_gradient<ND>(g, mu, lam, tau);
+        int t = 0;
+#pragma unroll
+        for (int r0 = 0; r0 < ND; ++r0)
+#pragma unroll
+          for (int c0 = r0; c0 < ND; ++c0) a.tauq[(size_t)(t++) * a.cs + off] = tau[c0 + ND * r0];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) a.tauq[(size_t)(NTAU + d) * a.cs + off] = -kap * gT[d];
+      }
+      // ---- dissipation term  sum_dir Diss_dir(Q)   (reference src/RhsHelperImpl.f90:58-81)
+      if (a.diss) {
+        double dz[NU];
+#pragma unroll
+        for (int c = 0; c < NU; ++c) dz[c] = 0.0;
+        // in-plane directions
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const bool fast = d == 0 ? fastI : fastJ;
+          const int st = d == 0 ? 1 : W;                 // tile stride along the direction
+          if (fast) {
+            double e[2 * R + 1];
+            if (COMPOSITE) {
+#pragma unroll
+              for (int m = 0; m < 2 * R + 1; ++m) e[m] = a.Dd[d].c[m];
+            } else {
+#pragma unroll
+              for (int m = 0; m < 2 * R + 1; ++m) e[m] = 0.0;
+#pragma unroll
+              for (int ea = 0; ea < TN; ++ea) {
+                const double w = -a.Dt[d].c[ea] * tc[(FA + d) * H * W + (TLO + ea) * st];
+#pragma unroll
+                for (int eb = 0; eb < DN; ++eb) e[TLO + ea + DLO + eb + R] += w * a.Dd[d].c[eb];
+              }
+            }
 #pragma unroll
             for (int c = 0; c < NU; ++c) {
               double r = 0.0;
 #pragma unroll
-              for (int b = 0; b < DN; ++b) r += a.Dd[2].c[b] * qq[RK + ko + DLO + b][c];
-              tz[e][c] = -arc * r;
+              for (int m = 0; m < 2 * R + 1; ++m) r += e[m] * tc[(FQ + c) * H * W + (m - R) * st];
+              dz[c] += r;
+            }
+          } else {
+            const int cd = d == 0 ? i : j, nd = d == 0 ? a.nx : a.ny;
+#pragma unroll
+            for (int c = 0; c < NU; ++c) {
+              auto getq = [&](int cc) { return d == 0 ? at(FQ + c, ty + R, cc - i0 + R) : at(FQ + c, cc - j0 + R, tx + R); };
+              auto geta = [&](int cc) { return d == 0 ? at(FA, ty + R, cc - i0 + R) : at(FA + 1, cc - j0 + R, tx + R); };
+              dz[c] += COMPOSITE ? line_apply(a.Dd[d], cd, nd, getq)
+                                 : line_dissipation(a.Dd[d], a.Dt[d], a.dir[d], cd, getq, geta);
+            }
+          }
+        }
+        if constexpr (ND == 3) {
+          double e[2 * RK + 1];
+          if (COMPOSITE) {
+#pragma unroll
+            for (int m = 0; m < 2 * RK + 1; ++m) e[m] = a.Dd[2].c[m];
+          } else {
+#pragma unroll
+            for (int m = 0; m < 2 * RK + 1; ++m) e[m] = 0.0;
+#pragma unroll
+            for (int ea = 0; ea < TN; ++ea) {
+              int kk = kp + TLO + ea;
+              if (a.wrapK) { if (kk < 0) kk += a.nz; else if (kk >= a.nz) kk -= a.nz; }
+              const double w = -a.Dt[2].c[ea] * a.arc[(size_t)2 * a.cs + (long)kk * a.plane + pij];
+#pragma unroll
+              for (int eb = 0; eb < DN; ++eb) e[TLO + ea + DLO + eb + RK] += w * a.Dd[2].c[eb];
             }
           }
 #pragma unroll
           for (int c = 0; c < NU; ++c) {
             double r = 0.0;
 #pragma unroll
-            for (int e = 0; e < TN; ++e) r += a.Dt[2].c[e] * tz[e][c];
+            for (int m = 0; m < 2 * RK + 1; ++m) r += e[m] * qq[m][c];
             dz[c] += r;
           }
         }
-      }
 #pragma unroll
-      for (int c = 0; c < NU; ++c) a.diss[(size_t)c * a.cs + off] = dz[c];
+        for (int c = 0; c < NU; ++c) a.diss[(size_t)c * a.cs + off] = dz[c];
+      }
     }
+    __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------------------- sweep B
+// index of the unique stress entry (l, c) in the compact layout written by sweep A
+template <int ND>
+__device__ __forceinline__ constexpr int tau_index(int l, int c) {
+  const int r0 = l < c ? l : c, c0 = l < c ? c : l;
+  return r0 * ND - r0 * (r0 - 1) / 2 + (c0 - r0);
+}
+
+// Contravariant total fluxes at one point.  DIRS: bit d set -> compute direction d.
+// (reference CNSHelperImpl.f90:563-689 Cartesian inviscid - viscous, :772-840 metric transform)
+template <int ND, int DIRS>
+__device__ __forceinline__ void point_fluxes(const FusedArgs& a, long off, double (*Fh)[ND + 2]) {
+  constexpr int NU = ND + 2;
+  constexpr int NTAU = ND * (ND + 1) / 2;
+  const double* __restrict__ Qp = a.Q + off;
+  double Q[NU];
+#pragma unroll
+  for (int c = 0; c < NU; ++c) Q[c] = Qp[(size_t)c * a.cs];
+  Prim<ND> s;
+  dependent<ND>(Q, a.pp.gamma, s);
+  if (!a.curvilinear) {
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      if (!((DIRS >> d) & 1)) continue;
+      double F[NU];
+      F[0] = Q[d + 1];
+#pragma unroll
+      for (int c = 0; c < ND; ++c) {
+        if (c == d) F[c + 1] = Q[d + 1] * s.u[d] + s.p;
+        else F[c + 1] = Q[(c < d ? c : d) + 1] * s.u[c < d ? d : c];
+      }
+      F[NU - 1] = s.u[d] * (Q[NU - 1] + s.p);
+      if (a.viscous) {
+        const double* __restrict__ tq = a.tauqIn + off;
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < ND; ++c) {
+          const double t = tq[(size_t)tau_index<ND>(d, c) * a.cs];
+          F[c + 1] = F[c + 1] - t;
+          acc = (c == 0) ? s.u[0] * t : acc + s.u[c] * t;
+        }
+        F[NU - 1] = F[NU - 1] - (acc - tq[(size_t)(NTAU + d) * a.cs]);
+      }
+      const double md = a.m[(size_t)(d + ND * d) * a.cs + off];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) Fh[d][c] = md * F[c];
+    }
+  } else {
+    double tau[ND * ND], q[ND], Fc[ND][NU], Fv[NU];
+    if (a.viscous) {
+      const double* __restrict__ tq = a.tauqIn + off;
+#pragma unroll
+      for (int l = 0; l < ND; ++l)
+#pragma unroll
+        for (int c = 0; c < ND; ++c) tau[l + ND * c] = tq[(size_t)tau_index<ND>(l, c) * a.cs];
+#pragma unroll
+      for (int e = 0; e < ND; ++e) q[e] = tq[(size_t)(NTAU + e) * a.cs];
+    }
+#pragma unroll
+    for (int l = 0; l < ND; ++l) cartesian_flux<ND>(l, Q, s, a.viscous, tau, q, Fc[l], Fv);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      if (!((DIRS >> d) & 1)) continue;
+#pragma unroll
+      for (int l = 0; l < ND; ++l) {
+        const double ml = a.m[(size_t)(l + ND * d) * a.cs + off];
+#pragma unroll
+        for (int c = 0; c < NU; ++c) Fh[d][c] = (l == 0) ? ml * Fc[0][c] : Fh[d][c] + ml * Fc[l][c];
+      }
+    }
+  }
+}
+
 template <int ND, int R>
 __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
   constexpr int NU = ND + 2;
-  constexpr int NTAU = ND * (ND + 1) / 2;
   constexpr int W = TX + 2 * R, H = TY + 2 * R;
   constexpr int RK = (ND == 3) ? R : 0;
   constexpr int NQ = 2 * RK + 1;
+  constexpr int ALLDIRS = (1 << ND) - 1;
   extern __shared__ double smem[];
   double* F1 = smem;                               // [NU][TY][W]   contravariant flux along xi
   double* F2 = F1 + (size_t)NU * TY * W;           // [NU][H][TX]   contravariant flux along eta
@@ -375,7 +498,12 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
   const bool mine = owns(i, a.nx, TX, lastI) && owns(j, a.ny, TY, lastJ);
   const bool inside = i < a.nx && j < a.ny;
   const long pij = (long)i + (long)a.nx * j;
-  const double gamma = a.pp.gamma;
+  // fast interior stencils unless the tile touches a closure block of that direction
+  const bool fastI = !((a.D[0].hasB0 && i0 < a.D[0].depth) || (a.D[0].hasB1 && i0 + TX > a.nx - a.D[0].depth));
+  const bool fastJ = !((a.D[1].hasB0 && j0 < a.D[1].depth) || (a.D[1].hasB1 && j0 + TY > a.ny - a.D[1].depth));
+  double* const f1c = F1 + ty * W + tx + R;        // component stride TY*W
+  double* const f2c = F2 + (ty + R) * TX + tx;     // component stride H*TX, row stride TX
+  double* const f3c = F3 + threadIdx.x;            // slot stride NU*NT, component stride NT
 
   int hcol = 0, hrow = 0, hk = 0;
   long hp = -1;
@@ -400,82 +528,51 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
   }
   const int kc0 = a.kBeg + blockIdx.z * a.kChunk;
   const int kc1 = min(kc0 + a.kChunk, a.kEnd);
-  auto planeOf = [&](int k) -> long {
-    if (ND < 3) return 0;
-    int kk = k;
-    if (a.wrapK) kk = (k % a.nz + a.nz) % a.nz;
-    return (long)kk * a.plane;
+  // plane offsets advance incrementally (no division in the loop)
+  auto wrapPlane = [&](int k) -> int {
+    if (ND < 3 || !a.wrapK) return k;
+    int kk = k % a.nz;
+    return kk < 0 ? kk + a.nz : kk;
   };
+  int ks = wrapPlane(kc0 - RK);                    // storage plane of the arriving plane s
+  int kp = wrapPlane(kc0 - 2 * RK);                // storage plane of the output plane p = s - RK
+  int slot = 0;                                    // queue slot of plane s
 
-  // contravariant flux along direction d at a point (reference CNSHelperImpl.f90:563-689, :772-840)
-  auto flux_dir = [&](int d, long off, double* Fh) {
-    double Q[NU], tau[ND * ND], q[ND], Fc[NU], Fv[NU];
+  double rxy[RK + 1][NU];          // in-plane part of div(F) for planes s-RK .. s
 #pragma unroll
-    for (int c = 0; c < NU; ++c) Q[c] = a.Q[(size_t)c * a.cs + off];
-    Prim<ND> s;
-    dependent<ND>(Q, gamma, s);
-    if (a.viscous) {
-      int t = 0;
+  for (int q = 0; q < RK + 1; ++q)
 #pragma unroll
-      for (int r0 = 0; r0 < ND; ++r0)
-#pragma unroll
-        for (int c0 = r0; c0 < ND; ++c0) {
-          const double v = a.tauqIn[(size_t)(t++) * a.cs + off];
-          tau[c0 + ND * r0] = v;
-          tau[r0 + ND * c0] = v;
-        }
-#pragma unroll
-      for (int e = 0; e < ND; ++e) q[e] = a.tauqIn[(size_t)(NTAU + e) * a.cs + off];
-    }
-    if (a.curvilinear) {
-#pragma unroll
-      for (int c = 0; c < NU; ++c) Fh[c] = 0.0;
-#pragma unroll
-      for (int l = 0; l < ND; ++l) {
-        cartesian_flux<ND>(l, Q, s, a.viscous, tau, q, Fc, Fv);
-        const double ml = a.m[(size_t)(l + ND * d) * a.cs + off];
-#pragma unroll
-        for (int c = 0; c < NU; ++c) Fh[c] = (l == 0) ? ml * Fc[c] : Fh[c] + ml * Fc[c];
-      }
-    } else {
-      cartesian_flux<ND>(d, Q, s, a.viscous, tau, q, Fc, Fv);
-      const double md = a.m[(size_t)(d + ND * d) * a.cs + off];
-#pragma unroll
-      for (int c = 0; c < NU; ++c) Fh[c] = md * Fc[c];
-    }
-  };
-
-  double rxy[RK + 1][NU];          // in-plane part of -div(F) for planes s-RK .. s
+    for (int c = 0; c < NU; ++c) rxy[q][c] = 0.0;
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
-    const long soff = planeOf(s);
+    const long soff = (ND == 3) ? (long)ks * a.plane : 0;
     const bool planeActive = s >= kc0 && s < kc1;
-    // ---- arrival of plane s: fluxes at the own point
+    // ---- arrival of plane s: fluxes at the own point, xi/eta halos
     if (inside) {
-      double Fh[NU];
+      double Fh[ND][NU];
+      if (planeActive) point_fluxes<ND, ALLDIRS>(a, soff + pij, Fh);
+      else point_fluxes<ND, (ND == 3 ? 4 : 0)>(a, soff + pij, Fh);
       if constexpr (ND == 3) {
-        flux_dir(2, soff + pij, Fh);
-        const int slot = ((s % NQ) + NQ) % NQ;
 #pragma unroll
-        for (int c = 0; c < NU; ++c) F3[((size_t)slot * NU + c) * NT + threadIdx.x] = Fh[c];
+        for (int c = 0; c < NU; ++c) f3c[((size_t)slot * NU + c) * NT] = Fh[ND - 1][c];
       }
       if (planeActive) {
-        flux_dir(0, soff + pij, Fh);
 #pragma unroll
-        for (int c = 0; c < NU; ++c) F1[((size_t)c * TY + ty) * W + tx + R] = Fh[c];
-        flux_dir(1, soff + pij, Fh);
-#pragma unroll
-        for (int c = 0; c < NU; ++c) F2[((size_t)c * H + ty + R) * TX + tx] = Fh[c];
+        for (int c = 0; c < NU; ++c) {
+          f1c[c * TY * W] = Fh[0][c];
+          f2c[c * H * TX] = Fh[1][c];
+        }
       }
     }
     if (planeActive && hk) {
-      double Fh[NU];
-      flux_dir(hk - 1, soff + hp, Fh);
+      double Fh[ND][NU];
       if (hk == 1) {
+        point_fluxes<ND, 1>(a, soff + hp, Fh);
 #pragma unroll
-        for (int c = 0; c < NU; ++c) F1[((size_t)c * TY + hrow) * W + hcol] = Fh[c];
+        for (int c = 0; c < NU; ++c) F1[((size_t)c * TY + hrow) * W + hcol] = Fh[0][c];
       } else {
+        point_fluxes<ND, 2>(a, soff + hp, Fh);
 #pragma unroll
-        for (int c = 0; c < NU; ++c) F2[((size_t)c * H + hrow) * TX + hcol] = Fh[c];
+        for (int c = 0; c < NU; ++c) F2[((size_t)c * H + hrow) * TX + hcol] = Fh[1][c];
       }
     }
     __syncthreads();
@@ -486,26 +583,46 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
     if (planeActive && mine) {
 #pragma unroll
       for (int c = 0; c < NU; ++c) {
-        double r = line_apply(a.D[0], i, a.nx, [&](int cc) { return F1[((size_t)c * TY + ty) * W + cc - i0 + R]; });
-        r += line_apply(a.D[1], j, a.ny, [&](int cc) { return F2[((size_t)c * H + cc - j0 + R) * TX + tx]; });
+        double r;
+        if (fastI) {
+          r = 0.0;
+#pragma unroll
+          for (int q = 1; q <= R; ++q) r += a.D[0].c[R + q] * (f1c[c * TY * W + q] - f1c[c * TY * W - q]);
+        } else {
+          r = line_apply(a.D[0], i, a.nx, [&](int cc) { return F1[((size_t)c * TY + ty) * W + cc - i0 + R]; });
+        }
+        if (fastJ) {
+          double r2 = 0.0;
+#pragma unroll
+          for (int q = 1; q <= R; ++q)
+            r2 += a.D[1].c[R + q] * (f2c[c * H * TX + q * TX] - f2c[c * H * TX - q * TX]);
+          r += r2;
+        } else {
+          r += line_apply(a.D[1], j, a.ny, [&](int cc) { return F2[((size_t)c * H + cc - j0 + R) * TX + tx]; });
+        }
         rxy[RK][c] = r;
       }
     }
-    // ---- output plane p
+    // ---- output plane p = s - RK
     const int p = s - RK;
     if (p >= kc0 && mine) {
-      const long off = planeOf(p) + pij;
+      const long off = ((ND == 3) ? (long)kp * a.plane : 0) + pij;
       double r[NU];
 #pragma unroll
       for (int c = 0; c < NU; ++c) r[c] = rxy[0][c];
       if constexpr (ND == 3) {
+        // slot of plane p is slot - RK (mod NQ)
+        int sp0 = slot - RK;
+        if (sp0 < 0) sp0 += NQ;
 #pragma unroll
         for (int q = 1; q <= RK; ++q) {
-          const int sp = (((p + q) % NQ) + NQ) % NQ, sm = (((p - q) % NQ) + NQ) % NQ;
-          const double cq = a.D[2].c[q - a.D[2].lo];
+          int sp = sp0 + q, sm = sp0 - q;
+          if (sp >= NQ) sp -= NQ;
+          if (sm < 0) sm += NQ;
+          const double cq = a.D[2].c[RK + q];
 #pragma unroll
           for (int c = 0; c < NU; ++c)
-            r[c] += cq * (F3[((size_t)sp * NU + c) * NT + threadIdx.x] - F3[((size_t)sm * NU + c) * NT + threadIdx.x]);
+            r[c] += cq * (f3c[((size_t)sp * NU + c) * NT] - f3c[((size_t)sm * NU + c) * NT]);
         }
       }
       const double jac = a.jac[off];
@@ -540,6 +657,12 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
       }
     }
     __syncthreads();
+    // advance plane bookkeeping
+    if (ND == 3) {
+      ++ks; ++kp;
+      if (a.wrapK) { if (ks >= a.nz) ks -= a.nz; if (kp >= a.nz) kp -= a.nz; }
+      if (++slot >= NQ) slot = 0;
+    }
   }
 }
 
@@ -630,7 +753,8 @@ int fill_args(mg_state* s, FusedArgs* a) {
 template <int ND, int R, bool COMP, int DLO, int DN, int TLO, int TN>
 int launchA(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NF = (ND + 2) + ND + 1 + 2;
-  const size_t smem = 2 * sizeof(double) * NF * (TY + 2 * R) * (TX + 2 * R);
+  constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
+  const size_t smem = sizeof(double) * ((size_t)NF * (TY + 2 * R) * (TX + 2 * R) + (size_t)NQ * (ND + 1) * NT);
   auto kern = k_sweepA<ND, R, COMP, DLO, DN, TLO, TN>;
   static bool configured = false;
   if (!configured) {
