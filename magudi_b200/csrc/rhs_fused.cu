@@ -15,6 +15,8 @@
 // neighbours come from a shared-memory tile (with halo, periodic wrap or SBP boundary closures),
 // k-neighbours from a per-thread queue (registers in A, shared memory in B) so every field is read
 // from HBM once per sweep.  HBM-bound fp64 stencil/pointwise work: no tensor cores.
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "grid.h"
@@ -58,7 +60,14 @@ struct FusedArgs {
   const double *b1in; double *b1out, *b2, *Qout;
   int fuseRk, stage;
   double dt;
+  int prefetch;                 // planes of L2 prefetch distance (0 = off)
 };
+
+// L2 prefetch of the 128-byte line holding p: used to pull the planes the march will need two steps
+// ahead while the current plane is being processed (costs no registers, unlike a software pipeline).
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 __device__ __forceinline__ int wrap_index(int c, const DirInfo& d) {
   if (c >= 0 && c < d.n) return c;
@@ -122,8 +131,8 @@ __device__ __forceinline__ bool owns(int c, int n, int T, bool isLast) {
 // ------------------------------------------------------------------------------- sweep A
 // Shared memory: an in-plane tile of NF fields on a (TY+2R) x (TX+2R) box (corners unused) for the
 // output plane, plus the k-queue of (u, T) for the 2R+1 planes in flight.  Q's k-queue is in registers.
-template <int ND, int R, bool COMPOSITE, int DLO, int DN, int TLO, int TN>
-__global__ void __launch_bounds__(NT, 2) k_sweepA(FusedArgs a) {
+template <int ND, int R, bool COMPOSITE, int DLO, int DN, int TLO, int TN, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_sweepA(FusedArgs a) {
   constexpr int NU = ND + 2;
   constexpr int NTAU = ND * (ND + 1) / 2;
   constexpr int W = TX + 2 * R, H = TY + 2 * R;
@@ -201,6 +210,26 @@ __global__ void __launch_bounds__(NT, 2) k_sweepA(FusedArgs a) {
     for (int c = 0; c < NU; ++c) qq[q][c] = 0.0;
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
     // ---- arrival of plane s
+    if (ND == 3 && a.prefetch && inside && (tx & 15) == 0) {
+      int kf = ks + a.prefetch;
+      if (a.wrapK && kf >= a.nz) kf -= a.nz;
+      if (a.wrapK || s + a.prefetch < a.nz + RK) {
+        const long fo = (long)kf * a.plane + pij;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) prefetch_l2(a.Q + (size_t)c * a.cs + fo);
+      }
+      int kq = ks - RK + a.prefetch;
+      if (a.wrapK) { if (kq < 0) kq += a.nz; else if (kq >= a.nz) kq -= a.nz; }
+      if (a.wrapK || (kq >= 0 && kq < a.nz)) {
+        const long qo = (long)kq * a.plane + pij;
+        prefetch_l2(a.jac + qo);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+          prefetch_l2(a.m + (size_t)(d + ND * d) * a.cs + qo);
+          if (!COMPOSITE && a.diss) prefetch_l2(a.arc + (size_t)d * a.cs + qo);
+        }
+      }
+    }
 #pragma unroll
     for (int q = 0; q < NQ - 1; ++q)
 #pragma unroll
@@ -413,16 +442,61 @@ __device__ __forceinline__ constexpr int tau_index(int l, int c) {
   return r0 * ND - r0 * (r0 - 1) / 2 + (c0 - r0);
 }
 
-// Contravariant total fluxes at one point.  DIRS: bit d set -> compute direction d.
-// (reference CNSHelperImpl.f90:563-689 Cartesian inviscid - viscous, :772-840 metric transform)
+// Raw inputs of the flux evaluation at one point; loading and computing are separate so that all
+// global loads of an iteration are issued back to back (one exposed memory latency, not one per use).
+template <int ND>
+struct RawPoint {
+  double Q[ND + 2];
+  double tq[ND * (ND + 1) / 2 + ND];
+  double m[ND * ND];
+};
+
 template <int ND, int DIRS>
-__device__ __forceinline__ void point_fluxes(const FusedArgs& a, long off, double (*Fh)[ND + 2]) {
+__device__ __forceinline__ constexpr bool needs_tq(int e) {
+  constexpr int NTAU = ND * (ND + 1) / 2;
+  for (int d = 0; d < ND; ++d) {
+    if (!((DIRS >> d) & 1)) continue;
+    if (e == NTAU + d) return true;
+    for (int c = 0; c < ND; ++c)
+      if (tau_index<ND>(d, c) == e) return true;
+  }
+  return false;
+}
+
+// DIRS: bit d set -> the flux along direction d will be needed.
+template <int ND, int DIRS>
+__device__ __forceinline__ void load_raw(const FusedArgs& a, long off, RawPoint<ND>& r) {
+  constexpr int NU = ND + 2;
+  constexpr int NTQ = ND * (ND + 1) / 2 + ND;
+  const double* __restrict__ Qp = a.Q + off;
+#pragma unroll
+  for (int c = 0; c < NU; ++c) r.Q[c] = __ldg(Qp + (size_t)c * a.cs);
+  if (a.viscous) {
+    const double* __restrict__ tq = a.tauqIn + off;
+#pragma unroll
+    for (int e = 0; e < NTQ; ++e)
+      if (a.curvilinear || needs_tq<ND, DIRS>(e)) r.tq[e] = __ldg(tq + (size_t)e * a.cs);
+  }
+  const double* __restrict__ mp = a.m + off;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    if (!((DIRS >> d) & 1)) continue;
+    if (a.curvilinear) {
+#pragma unroll
+      for (int l = 0; l < ND; ++l) r.m[l + ND * d] = __ldg(mp + (size_t)(l + ND * d) * a.cs);
+    } else {
+      r.m[d + ND * d] = __ldg(mp + (size_t)(d + ND * d) * a.cs);
+    }
+  }
+}
+
+// Contravariant total fluxes from the raw inputs (reference CNSHelperImpl.f90:563-689 Cartesian
+// inviscid - viscous, :772-840 metric transform).
+template <int ND, int DIRS>
+__device__ __forceinline__ void fluxes_from_raw(const FusedArgs& a, const RawPoint<ND>& r, double (*Fh)[ND + 2]) {
   constexpr int NU = ND + 2;
   constexpr int NTAU = ND * (ND + 1) / 2;
-  const double* __restrict__ Qp = a.Q + off;
-  double Q[NU];
-#pragma unroll
-  for (int c = 0; c < NU; ++c) Q[c] = Qp[(size_t)c * a.cs];
+  const double* Q = r.Q;
   Prim<ND> s;
   dependent<ND>(Q, a.pp.gamma, s);
   if (!a.curvilinear) {
@@ -438,30 +512,28 @@ __device__ __forceinline__ void point_fluxes(const FusedArgs& a, long off, doubl
       }
       F[NU - 1] = s.u[d] * (Q[NU - 1] + s.p);
       if (a.viscous) {
-        const double* __restrict__ tq = a.tauqIn + off;
         double acc = 0.0;
 #pragma unroll
         for (int c = 0; c < ND; ++c) {
-          const double t = tq[(size_t)tau_index<ND>(d, c) * a.cs];
+          const double t = r.tq[tau_index<ND>(d, c)];
           F[c + 1] = F[c + 1] - t;
           acc = (c == 0) ? s.u[0] * t : acc + s.u[c] * t;
         }
-        F[NU - 1] = F[NU - 1] - (acc - tq[(size_t)(NTAU + d) * a.cs]);
+        F[NU - 1] = F[NU - 1] - (acc - r.tq[NTAU + d]);
       }
-      const double md = a.m[(size_t)(d + ND * d) * a.cs + off];
+      const double md = r.m[d + ND * d];
 #pragma unroll
       for (int c = 0; c < NU; ++c) Fh[d][c] = md * F[c];
     }
   } else {
     double tau[ND * ND], q[ND], Fc[ND][NU], Fv[NU];
     if (a.viscous) {
-      const double* __restrict__ tq = a.tauqIn + off;
 #pragma unroll
       for (int l = 0; l < ND; ++l)
 #pragma unroll
-        for (int c = 0; c < ND; ++c) tau[l + ND * c] = tq[(size_t)tau_index<ND>(l, c) * a.cs];
+        for (int c = 0; c < ND; ++c) tau[l + ND * c] = r.tq[tau_index<ND>(l, c)];
 #pragma unroll
-      for (int e = 0; e < ND; ++e) q[e] = tq[(size_t)(NTAU + e) * a.cs];
+      for (int e = 0; e < ND; ++e) q[e] = r.tq[NTAU + e];
     }
 #pragma unroll
     for (int l = 0; l < ND; ++l) cartesian_flux<ND>(l, Q, s, a.viscous, tau, q, Fc[l], Fv);
@@ -470,7 +542,7 @@ __device__ __forceinline__ void point_fluxes(const FusedArgs& a, long off, doubl
       if (!((DIRS >> d) & 1)) continue;
 #pragma unroll
       for (int l = 0; l < ND; ++l) {
-        const double ml = a.m[(size_t)(l + ND * d) * a.cs + off];
+        const double ml = r.m[l + ND * d];
 #pragma unroll
         for (int c = 0; c < NU; ++c) Fh[d][c] = (l == 0) ? ml * Fc[0][c] : Fh[d][c] + ml * Fc[l][c];
       }
@@ -478,8 +550,8 @@ __device__ __forceinline__ void point_fluxes(const FusedArgs& a, long off, doubl
   }
 }
 
-template <int ND, int R>
-__global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
+template <int ND, int R, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_sweepB(FusedArgs a) {
   constexpr int NU = ND + 2;
   constexpr int W = TX + 2 * R, H = TY + 2 * R;
   constexpr int RK = (ND == 3) ? R : 0;
@@ -546,11 +618,51 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
     const long soff = (ND == 3) ? (long)ks * a.plane : 0;
     const bool planeActive = s >= kc0 && s < kc1;
-    // ---- arrival of plane s: fluxes at the own point, xi/eta halos
+    if (ND == 3 && a.prefetch && inside && (tx & 15) == 0) {
+      // one lane per 128-byte row segment prefetches the lines of plane s + PF (inputs) / p + PF (outputs)
+      int kf = ks + a.prefetch, kq = kp + a.prefetch;
+      if (a.wrapK) { if (kf >= a.nz) kf -= a.nz; if (kq >= a.nz) kq -= a.nz; }
+      if (a.wrapK || s + a.prefetch < a.nz + RK) {
+        const long fo = (long)kf * a.plane + pij;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) prefetch_l2(a.Q + (size_t)c * a.cs + fo);
+        if (a.viscous) {
+#pragma unroll
+          for (int c = 0; c < ND * (ND + 1) / 2 + ND; ++c) prefetch_l2(a.tauqIn + (size_t)c * a.cs + fo);
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d) prefetch_l2(a.m + (size_t)(d + ND * d) * a.cs + fo);
+      }
+      if (a.wrapK || (kq >= 0 && kq < a.nz)) {
+        const long qo = (long)kq * a.plane + pij;
+        prefetch_l2(a.jac + qo);
+        if (a.dissIn) {
+#pragma unroll
+          for (int c = 0; c < NU; ++c) prefetch_l2(a.dissIn + (size_t)c * a.cs + qo);
+        }
+        if (a.fuseRk) {
+#pragma unroll
+          for (int c = 0; c < NU; ++c) {
+            if (a.stage != 1) prefetch_l2(a.b2 + (size_t)c * a.cs + qo);
+            if (a.stage == 2 || a.stage == 3) prefetch_l2(a.b1in + (size_t)c * a.cs + qo);
+          }
+        }
+      }
+    }
+    // ---- arrival of plane s: issue every global load of this phase first (own point + halo point)
+    RawPoint<ND> rawOwn, rawHalo;
+    if (inside) {
+      if (planeActive) load_raw<ND, ALLDIRS>(a, soff + pij, rawOwn);
+      else load_raw<ND, (ND == 3 ? 4 : 0)>(a, soff + pij, rawOwn);
+    }
+    if (planeActive && hk) {
+      if (hk == 1) load_raw<ND, 1>(a, soff + hp, rawHalo);
+      else load_raw<ND, 2>(a, soff + hp, rawHalo);
+    }
     if (inside) {
       double Fh[ND][NU];
-      if (planeActive) point_fluxes<ND, ALLDIRS>(a, soff + pij, Fh);
-      else point_fluxes<ND, (ND == 3 ? 4 : 0)>(a, soff + pij, Fh);
+      if (planeActive) fluxes_from_raw<ND, ALLDIRS>(a, rawOwn, Fh);
+      else fluxes_from_raw<ND, (ND == 3 ? 4 : 0)>(a, rawOwn, Fh);
       if constexpr (ND == 3) {
 #pragma unroll
         for (int c = 0; c < NU; ++c) f3c[((size_t)slot * NU + c) * NT] = Fh[ND - 1][c];
@@ -566,11 +678,11 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
     if (planeActive && hk) {
       double Fh[ND][NU];
       if (hk == 1) {
-        point_fluxes<ND, 1>(a, soff + hp, Fh);
+        fluxes_from_raw<ND, 1>(a, rawHalo, Fh);
 #pragma unroll
         for (int c = 0; c < NU; ++c) F1[((size_t)c * TY + hrow) * W + hcol] = Fh[0][c];
       } else {
-        point_fluxes<ND, 2>(a, soff + hp, Fh);
+        fluxes_from_raw<ND, 2>(a, rawHalo, Fh);
 #pragma unroll
         for (int c = 0; c < NU; ++c) F2[((size_t)c * H + hrow) * TX + hcol] = Fh[1][c];
       }
@@ -607,6 +719,19 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
     const int p = s - RK;
     if (p >= kc0 && mine) {
       const long off = ((ND == 3) ? (long)kp * a.plane : 0) + pij;
+      // batch every global load of the output phase before any store (loads cannot be hoisted across
+      // the stores by the compiler: the buffers may alias as far as it knows)
+      const double jac = __ldg(a.jac + off);
+      double dss[NU], vb1[NU], vb2[NU];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) {
+        const size_t qi = (size_t)c * a.cs + off;
+        dss[c] = a.dissIn ? __ldg(a.dissIn + qi) : 0.0;
+        if (a.fuseRk) {
+          vb1[c] = (a.stage == 1) ? a.Q[qi] : ((a.stage == 4) ? 0.0 : a.b1in[qi]);
+          vb2[c] = (a.stage == 1) ? 0.0 : a.b2[qi];
+        }
+      }
       double r[NU];
 #pragma unroll
       for (int c = 0; c < NU; ++c) r[c] = rxy[0][c];
@@ -625,33 +750,32 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
             r[c] += cq * (f3c[((size_t)sp * NU + c) * NT] - f3c[((size_t)sm * NU + c) * NT]);
         }
       }
-      const double jac = a.jac[off];
 #pragma unroll
       for (int c = 0; c < NU; ++c) {
         double rhs = 0.0 - r[c];
-        if (a.dissIn) rhs += a.dissAmount * a.dissIn[(size_t)c * a.cs + off];
+        if (a.dissIn) rhs += a.dissAmount * dss[c];
         r[c] = rhs * jac;
       }
       if (!a.fuseRk) {
 #pragma unroll
         for (int c = 0; c < NU; ++c) a.rhs[(size_t)c * a.cs + off] = r[c];
       } else {
-        // RK4 substep (reference src/RK4IntegratorImpl.f90:106-158) fused into the last RHS kernel
+        // RK4 substep (reference src/RK4IntegratorImpl.f90:106-158) fused into the last RHS kernel;
+        // in stage 1 buffer1 is the input Q buffer itself (vb1 = Q)
 #pragma unroll
         for (int c = 0; c < NU; ++c) {
           const size_t qi = (size_t)c * a.cs + off;
           if (a.stage == 1) {
-            const double Q0 = a.Q[qi];                  // buffer1 is the input Q buffer itself
-            a.b2[qi] = Q0 + a.dt * r[c] / 6.0;
-            a.Qout[qi] = Q0 + a.dt * r[c] / 2.0;
+            a.b2[qi] = vb1[c] + a.dt * r[c] / 6.0;
+            a.Qout[qi] = vb1[c] + a.dt * r[c] / 2.0;
           } else if (a.stage == 2) {
-            a.b2[qi] = a.b2[qi] + a.dt * r[c] / 3.0;
-            a.Qout[qi] = a.b1in[qi] + a.dt * r[c] / 2.0;
+            a.b2[qi] = vb2[c] + a.dt * r[c] / 3.0;
+            a.Qout[qi] = vb1[c] + a.dt * r[c] / 2.0;
           } else if (a.stage == 3) {
-            a.b2[qi] = a.b2[qi] + a.dt * r[c] / 3.0;
-            a.Qout[qi] = a.b1in[qi] + a.dt * r[c];
+            a.b2[qi] = vb2[c] + a.dt * r[c] / 3.0;
+            a.Qout[qi] = vb1[c] + a.dt * r[c];
           } else {
-            a.Qout[qi] = a.b2[qi] + a.dt * r[c] / 6.0;
+            a.Qout[qi] = vb2[c] + a.dt * r[c] / 6.0;
           }
         }
       }
@@ -743,6 +867,8 @@ int fill_args(mg_state* s, FusedArgs* a) {
     }
   }
   a->pp = s->phys();
+  static const int pf = getenv("MG_PREFETCH") ? atoi(getenv("MG_PREFETCH")) : 2;
+  a->prefetch = pf;
   a->dissAmount = s->opt.dissipationAmount;
   a->m = g->metrics.comp(0);
   a->jac = g->jacobian.comp(0);
@@ -755,7 +881,8 @@ int launchA(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NF = (ND + 2) + ND + 1 + 2;
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
   const size_t smem = sizeof(double) * ((size_t)NF * (TY + 2 * R) * (TX + 2 * R) + (size_t)NQ * (ND + 1) * NT);
-  auto kern = k_sweepA<ND, R, COMP, DLO, DN, TLO, TN>;
+  static const int minb = getenv("MG_MINB_A") ? atoi(getenv("MG_MINB_A")) : 2;
+  auto kern = minb == 1 ? k_sweepA<ND, R, COMP, DLO, DN, TLO, TN, 1> : k_sweepA<ND, R, COMP, DLO, DN, TLO, TN, 2>;
   static bool configured = false;
   if (!configured) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -775,7 +902,8 @@ int launchB(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
   const size_t smem = sizeof(double) * ((size_t)NU * TY * (TX + 2 * R) + (size_t)NU * (TY + 2 * R) * TX +
                                         (size_t)NQ * NU * NT);
-  auto kern = k_sweepB<ND, R>;
+  static const int minb = getenv("MG_MINB_B") ? atoi(getenv("MG_MINB_B")) : 2;
+  auto kern = minb == 1 ? k_sweepB<ND, R, 1> : k_sweepB<ND, R, 2>;
   static bool configured = false;
   if (!configured) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -787,6 +915,30 @@ int launchB(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   MG_CUDA(cudaGetLastError());
   mg_count_launches(1);
   return 0;
+}
+
+// Split k into chunks so that the CTA count fills whole waves of (SMs x resident CTAs); every chunk
+// re-streams 2R warm-up planes, so fewer, longer chunks are preferred when the fill is equal.
+int choose_chunks(FusedArgs* a, int R, int residentPerSm) {
+  const int tilesXY = ((a->nx + TX - 1) / TX) * ((a->ny + TY - 1) / TY);
+  int best = 1;
+  if (a->nz > 1) {
+    static const int forced = getenv("MG_CHUNKS") ? atoi(getenv("MG_CHUNKS")) : 0;
+    if (forced > 0) best = forced;
+    else {
+      const double slots = (double)mg_num_sms() * residentPerSm;
+      double bestScore = -1.0;
+      for (int n = 1; n <= 32 && n * 4 * R <= a->nz; ++n) {
+        const int chunk = (a->nz + n - 1) / n;
+        const double waves = tilesXY * (double)n / slots;
+        const double fill = waves / ceil(waves);
+        const double score = fill * chunk / (chunk + 0.6 * 2 * R);
+        if (score > bestScore + 1e-9) { bestScore = score; best = n; }
+      }
+    }
+  }
+  a->kChunk = (a->nz + best - 1) / best;
+  return (a->nz + a->kChunk - 1) / a->kChunk;
 }
 
 dim3 tiles(const FusedArgs& a, int nChunks) {
@@ -837,7 +989,7 @@ int mg_fused_sweepA(mg_state* s) {
   if (!a.viscous && !a.diss) { s->fusedValid = true; return 0; }
   SchemeInfo si;
   scheme_of(g, &si);
-  const dim3 grid = tiles(a, 1);
+  const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
   cudaStream_t st = mg_stream();
   const bool comp = g->compositeDissipation || !g->dissipationOn;
   int rc = -1;
@@ -884,7 +1036,7 @@ int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
   }
   SchemeInfo si;
   scheme_of(g, &si);
-  const dim3 grid = tiles(a, 1);
+  const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
   cudaStream_t st = mg_stream();
   int rc = -1;
   if (s->nD == 2 && si.R == 2) rc = launchB<2, 2>(a, grid, st);
