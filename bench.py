@@ -32,6 +32,8 @@ BYTES_FORWARD = 448.0           # two sweeps: (5+4+9) + (5+9+4+20) doubles
 BYTES_ADJOINT = 912.0           # three sweeps + checkpoint store/load
 BYTES_SWEEP_A = (5 + 4 + 9) * 8.0
 BYTES_SWEEP_B = (5 + 9 + 4 + 20) * 8.0
+BYTES_ADJ1 = (5 + 5 + 9 + 4 + 5 + 12) * 8.0     # read Q, w, tau/q, G; write partial R 5 + adjoint diffusion 12
+BYTES_ADJ2 = (12 + 5 + 5 + 4 + 20) * 8.0        # read diffusion 12, partial R 5, Q 5, G + RK 20
 
 
 def measured_peaks():
@@ -225,7 +227,13 @@ def run_native(args):
         for stage in range(4, 0, -1):
             state.checkpointLoad(stage - 1)
             update_state()
-            t = integ.substepAdjoint(t, dt, step, stage)
+            if halo:
+                halo.exchange(state, core.Q_ADJOINT, 5, R)
+                integ.substepAdjointPhase(1, t, dt, step, stage)
+                halo.exchange(state, core.Q_FUSED_ADJOINT_DIFFUSION3, 4, R)
+                t = integ.substepAdjointPhase(2, t, dt, step, stage)
+            else:
+                t = integ.substepAdjoint(t, dt, step, stage)
         return t
 
     do_adjoint = (world == 1) or fused_adj      # the general adjoint path is single-rank
@@ -257,24 +265,29 @@ def run_native(args):
     lib.mg_profile_enable(1)
     launches0 = lib.mg_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ef = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ea = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record(stream)
     wall0 = time.perf_counter()
-    fwd_ms = 0.0
     for k in range(args.steps):
+        es[k].record(stream)
         t = forward_step(t, args.warmup + k)
         ef[k].record(stream)
         if do_adjoint:
             t = adjoint_step(t, args.warmup + k)
+        ea[k].record(stream)
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     total_ms = e0.elapsed_time(e1)
+    fwd_ms = sum(es[k].elapsed_time(ef[k]) for k in range(args.steps))
+    adj_ms = sum(ef[k].elapsed_time(ea[k]) for k in range(args.steps))
     launches = lib.mg_kernel_launch_count() - launches0
     import ctypes as C
     prof = {}
-    for name in ("sweepA", "sweepB", "adjointA", "adjointB", "adjointC"):
+    for name in ("sweepA", "sweepB", "adjoint1", "adjoint2"):
         ms, n = C.c_double(0), C.c_longlong(0)
         _lib.check(lib.mg_profile_get(name.encode(), C.byref(ms), C.byref(n)))
         if n.value:
@@ -326,18 +339,24 @@ def run_native(args):
     roofline = None
     if prof:
         dom = max(prof, key=lambda k: prof[k]["ms"])
-        bytes_per_launch = {"sweepA": BYTES_SWEEP_A, "sweepB": BYTES_SWEEP_B}.get(dom, BYTES_SWEEP_B) * N
+        bytes_per_launch = {"sweepA": BYTES_SWEEP_A, "sweepB": BYTES_SWEEP_B, "adjoint1": BYTES_ADJ1,
+                            "adjoint2": BYTES_ADJ2}.get(dom, BYTES_SWEEP_B) * N
         achieved = bytes_per_launch / (prof[dom]["avg_ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "share_of_step": prof[dom]["ms"] / total_ms,
                     "algorithmic_bytes_per_point": bytes_per_launch / N}
-    fwd_total_ms = sum(prof[k]["ms"] for k in ("sweepA", "sweepB") if k in prof)
+    # whole-path rates (device time of the forward / adjoint legs incl. checkpoint copies and halos)
     path = {}
-    if fwd_total_ms > 0:
-        fwd_rate = 4 * N * args.steps / (fwd_total_ms * 1e-3)
-        path["forward"] = {"point_stages_per_s_per_gpu": fwd_rate, "bytes_model": BYTES_FORWARD,
-                           "frac_of_hbm_peak": fwd_rate * BYTES_FORWARD / 1e9 / peak}
+    fwd_rate = 4 * N * args.steps / (fwd_ms * 1e-3)
+    path["forward"] = {"point_stages_per_s_per_gpu": fwd_rate, "bytes_model": BYTES_FORWARD,
+                       "frac_of_hbm_peak": fwd_rate * BYTES_FORWARD / 1e9 / peak, "ms_per_step": fwd_ms / args.steps}
+    if do_adjoint:
+        adj_rate = 4 * N * args.steps / (adj_ms * 1e-3)
+        path["adjoint"] = {"point_stages_per_s_per_gpu": adj_rate, "bytes_model": BYTES_ADJOINT,
+                           "frac_of_hbm_peak": adj_rate * BYTES_ADJOINT / 1e9 / peak,
+                           "ms_per_step": adj_ms / args.steps,
+                           "note": "each adjoint stage also restores the stored forward substep state and runs sweep A on it"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rate, sec, sample = cpu_port_rate(args.cpu_size, steps=1, warmup=0)
@@ -350,7 +369,7 @@ def run_native(args):
                                f"({N} points/GPU), KolmogorovFlow flags, SBP 3-6, non-composite dissipation",
                    "evals_per_point_per_step": evals_per_point,
                    "forward_path": "fused sweeps A+B" if fused_fwd else "general",
-                   "adjoint_path": ("fused" if fused_adj else "general operator-by-operator") if do_adjoint else "not run (multi-rank adjoint needs the fused adjoint)",
+                   "adjoint_path": ("fused adjoint sweeps 1+2 (+ sweep A on the restored state)" if fused_adj else "general operator-by-operator") if do_adjoint else "not run (multi-rank adjoint needs the fused adjoint)",
                    "parallelism": f"slab decomposition along k over {world} GPU(s)",
                    "l2_policy": "inputs larger than L2 (every field >= 134 MB per component set)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,

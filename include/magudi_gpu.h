@@ -59,6 +59,8 @@ enum {
   MG_Q_STRESS_TENSOR = 11, MG_Q_HEAT_FLUX = 12,
   /* outputs of the fused sweep A: unique stress entries + heat flux (nD(nD+1)/2 + nD), dissipation term (nU) */
   MG_Q_FUSED_TAUQ = 13, MG_Q_FUSED_DISSIPATION = 14,
+  /* direction-3 block of the adjoint diffusion written by the first fused adjoint sweep (nU-1 comps) */
+  MG_Q_FUSED_ADJOINT_DIFFUSION3 = 15,
   MG_G_COORDINATES = 100, MG_G_METRICS = 101, MG_G_JACOBIAN = 102, MG_G_NORM = 103,
   MG_G_ARC_LENGTHS = 104, MG_G_TARGET_MOLLIFIER = 105, MG_G_CONTROL_MOLLIFIER = 106
 };
@@ -193,6 +195,10 @@ int mg_region_compute_rhs(mg_region* r, int mode, int timestep, int stage);
  * states%update the reference's drivers issue after every substep (src/SolverImpl.f90:831-834) when
  * updateStates != 0. */
 int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep, int stage, int updateStates);
+/* the adjoint substep in two phases, so that a slab-decomposed host can exchange ghost planes in between:
+ * phase 1 = first adjoint sweep (needs ghost planes of the adjoint variables), phase 2 = second sweep +
+ * RK4 update (needs ghost planes of MG_Q_FUSED_ADJOINT_DIFFUSION3).  Fused path only. */
+int mg_rk4_substep_adjoint_phase(mg_region* r, int phase, double* time, double dt, int timestep, int stage);
 /* select the implementation: 0 = general operator-by-operator path, 1 = fused sweeps (default when
  * the configuration is covered) */
 int mg_region_set_fused(mg_region* r, int enable);

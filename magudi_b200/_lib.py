@@ -95,6 +95,7 @@ SIGNATURES = {
     "mg_region_update_patches": (C.c_int, [_P]),
     "mg_region_compute_rhs": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "mg_rk4_substep": (C.c_int, [_P, C.c_int, _D, C.c_double, C.c_int, C.c_int, C.c_int]),
+    "mg_rk4_substep_adjoint_phase": (C.c_int, [_P, C.c_int, _D, C.c_double, C.c_int, C.c_int]),
     "mg_region_set_fused": (C.c_int, [_P, C.c_int]),
     "mg_region_uses_fused": (C.c_int, [_P, C.c_int]),
 }

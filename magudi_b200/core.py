@@ -23,7 +23,7 @@ SYMMETRIC, SKEW_SYMMETRIC, ASYMMETRIC = 0, 1, 2
 Q_CONSERVED, Q_ADJOINT, Q_TARGET, Q_RHS = 0, 1, 2, 3
 Q_SPECIFIC_VOLUME, Q_VELOCITY, Q_PRESSURE, Q_TEMPERATURE = 4, 5, 6, 7
 Q_DYNAMIC_VISCOSITY, Q_SECOND_VISCOSITY, Q_THERMAL_DIFFUSIVITY, Q_STRESS_TENSOR, Q_HEAT_FLUX = 8, 9, 10, 11, 12
-Q_FUSED_TAUQ, Q_FUSED_DISSIPATION = 13, 14
+Q_FUSED_TAUQ, Q_FUSED_DISSIPATION, Q_FUSED_ADJOINT_DIFFUSION3 = 13, 14, 15
 G_COORDINATES, G_METRICS, G_JACOBIAN, G_NORM, G_ARC_LENGTHS = 100, 101, 102, 103, 104
 G_TARGET_MOLLIFIER, G_CONTROL_MOLLIFIER = 105, 106
 
@@ -290,6 +290,8 @@ class State:
             return nd * (nd + 1) // 2 + nd
         if field == Q_FUSED_DISSIPATION:
             return nu
+        if field == Q_FUSED_ADJOINT_DIFFUSION3:
+            return nu - 1
         return 1
 
     def set(self, field, a):
@@ -432,6 +434,13 @@ class RK4Integrator:
         t = C.c_double(time)
         check(L.lib().mg_rk4_substep(self.region._h, FORWARD, C.byref(t), float(timeStepSize), int(timestep),
                                      int(stage), int(updateStates)))
+        return t.value
+
+    def substepAdjointPhase(self, phase, time, timeStepSize, timestep, stage):
+        """Fused adjoint substep split in two phases (ghost-plane exchanges happen in between)."""
+        t = C.c_double(time)
+        check(L.lib().mg_rk4_substep_adjoint_phase(self.region._h, int(phase), C.byref(t), float(timeStepSize),
+                                                   int(timestep), int(stage)))
         return t.value
 
     def substepAdjoint(self, time, timeStepSize, timestep, stage):

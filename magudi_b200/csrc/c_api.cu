@@ -375,6 +375,15 @@ static MgField* state_field(mg_state* s, int field) {
     case MG_Q_HEAT_FLUX: return &s->heatFlux;
     case MG_Q_FUSED_TAUQ: return &s->tauq;
     case MG_Q_FUSED_DISSIPATION: return &s->dissTerm;
+    case MG_Q_FUSED_ADJOINT_DIFFUSION3: {
+      static thread_local MgField view;
+      view = s->grid->scratchA;
+      view.owned = false;
+      if (!view.p || s->nD != 3) return nullptr;
+      view.p += (size_t)(2 * (s->nU - 1)) * view.compStride;
+      view.nComp = s->nU - 1;
+      return &view;
+    }
   }
   return nullptr;
 }
@@ -554,6 +563,30 @@ int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep
     if (updateStates && mode == MG_FORWARD) {
       if (s->useFused && mg_fused_supported(s, MG_FORWARD)) MG_TRY(mg_fused_sweepA(s));
       else MG_TRY(mg_state_update_impl(s, nullptr));
+    }
+  }
+  *time = t;
+  return 0;
+}
+
+int mg_rk4_substep_adjoint_phase(mg_region* r, int phase, double* time, double dt, int timestep, int stage) {
+  (void)timestep;
+  if (!r || !time) MG_FAIL("mg_rk4_substep_adjoint_phase: null argument");
+  if (stage < 1 || stage > 4) MG_FAIL("mg_rk4_substep_adjoint_phase: stage must be 1..4");
+  double t = *time;
+  for (mg_state* s : r->states) {
+    if (!(s->useFused && mg_fused_supported(s, MG_ADJOINT)))
+      MG_FAIL("mg_rk4_substep_adjoint_phase: the fused adjoint path does not cover this configuration");
+    t = *time;
+    if (phase == 1) {
+      const double factor[5] = {0.0, 1.0, 0.5, 1.0, 2.0};
+      s->adjointForcingFactor = factor[stage];
+      if (stage == 4) s->timeProgressive = t - dt / 2.0;
+      MG_TRY(mg_fused_adjoint1(s));
+    } else {
+      MG_TRY(mg_fused_adjoint2(s, 1, stage, dt));
+      if (stage == 4 || stage == 2) s->timeProgressive = t;
+      if (stage == 3 || stage == 1) { t -= dt / 2.0; s->time = t; }
     }
   }
   *time = t;

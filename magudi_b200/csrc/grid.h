@@ -33,6 +33,7 @@ struct mg_state {
   bool keepViscousFluxes = false;
   // fused path: outputs of sweep A (unique stress entries + heat flux; dissipation term)
   MgField tauq, dissTerm;
+  void* fusedOps[2] = {nullptr, nullptr};   // device operator tables of the fused closure path (fwd, adjoint)
   std::vector<MgField> checkpoints;   // device-resident forward substep states (adjoint replay)
   bool fusedValid = false;
   int useFused = 1;
@@ -66,6 +67,8 @@ int mg_patches_farfield_adjoint_sources(mg_state* s, MgField* temp1);
 bool mg_patches_have_farfield(const mg_state* s);
 int mg_fused_sweepA(mg_state* s);
 int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt);
+int mg_fused_adjoint1(mg_state* s);
+int mg_fused_adjoint2(mg_state* s, int fuseRk, int stage, double dt);
 void mg_count_launches(int n);
 void mg_profile_begin(const char* name);
 void mg_profile_end();

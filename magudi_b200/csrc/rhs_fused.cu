@@ -41,6 +41,8 @@ struct DirInfo {
   double norm[MG_MAX_BDEPTH];   // first-derivative norm (applyNormInverse in the dissipation)
 };
 
+struct DevOps;
+
 struct FusedArgs {
   int nx, ny, nz;
   long plane;
@@ -61,6 +63,12 @@ struct FusedArgs {
   int fuseRk, stage;
   double dt;
   int prefetch;                 // planes of L2 prefetch distance (0 = off)
+  int composite;                // composite dissipation (single operator) instead of Dt(-arc Dd)
+  const struct DevOps* ops;     // device copy of the operators for the (out-of-line) closure path
+  // adjoint sweeps
+  const double *Win, *diffIn, *rhsIn;
+  double* diffOut;
+  int dissOn;
 };
 
 // L2 prefetch of the 128-byte line holding p: used to pull the planes the march will need two steps
@@ -115,6 +123,54 @@ __device__ __forceinline__ double line_dissipation(const LineOp& Dd, const LineO
   return r;
 }
 
+// Device-resident copy of the operator tables, used by the out-of-line closure path below (keeps the
+// boundary-tile code out of the hot kernels' instruction stream and register allocation).
+struct DevOps {
+  LineOp D[3], Dd[3], Dt[3];
+  DirInfo dir[3];
+};
+
+// buf[k] holds the value at coordinate c0 + k of the line.
+__device__ __noinline__ double g_line_apply(const LineOp* op, int c, int n, const double* buf, int c0) {
+  return line_apply(*op, c, n, [&](int cc) { return buf[cc - c0]; });
+}
+__device__ __noinline__ double g_line_dissipation(const LineOp* Dd, const LineOp* Dt, const DirInfo* di, int c,
+                                                  const double* q, const double* arc, int c0) {
+  return line_dissipation(*Dd, *Dt, *di, c, [&](int cc) { return q[cc - c0]; },
+                          [&](int cc) { return arc[cc - c0]; });
+}
+
+// Gather one line of a shared-memory tile into a local buffer and apply an operator out of line.
+// Tile layout [field][H][W]; dirIdx 0: along columns (i), 1: along rows (j); c0 = coordinate of index 0.
+template <int W, int H>
+__device__ __forceinline__ double tile_line_apply(const LineOp* op, int c, int n, const double* T0, int f, int row,
+                                                  int col, int dirIdx, int c0) {
+  constexpr int L = W > H ? W : H;
+  double buf[L];
+  if (dirIdx == 0) { for (int k = 0; k < W; ++k) buf[k] = T0[((size_t)f * H + row) * W + k]; }
+  else { for (int k = 0; k < H; ++k) buf[k] = T0[((size_t)f * H + k) * W + col]; }
+  return g_line_apply(op, c, n, buf, c0);
+}
+template <int W, int H>
+__device__ __forceinline__ double tile_line_dissipation(const DevOps* ops, int d, int c, const double* T0, int fq,
+                                                        int fa, int row, int col, int c0) {
+  constexpr int L = W > H ? W : H;
+  double q[L], arc[L];
+  if (d == 0) {
+    for (int k = 0; k < W; ++k) { q[k] = T0[((size_t)fq * H + row) * W + k]; arc[k] = T0[((size_t)fa * H + row) * W + k]; }
+  } else {
+    for (int k = 0; k < H; ++k) { q[k] = T0[((size_t)fq * H + k) * W + col]; arc[k] = T0[((size_t)fa * H + k) * W + col]; }
+  }
+  return g_line_dissipation(&ops->Dd[d], &ops->Dt[d], &ops->dir[d], c, q, arc, c0);
+}
+template <int L>
+__device__ __forceinline__ double strided_line_apply(const LineOp* op, int c, int n, const double* line, int stride,
+                                                     int c0) {
+  double buf[L];
+  for (int k = 0; k < L; ++k) buf[k] = line[(size_t)k * stride];
+  return g_line_apply(op, c, n, buf, c0);
+}
+
 // Tile placement: tiles are anchored at the origin except the last one of a direction, which is
 // anchored at the far boundary so that it always contains the whole right closure block.
 __device__ __forceinline__ void tile_origin(int t, int n, int T, int& c0, bool& isLast) {
@@ -131,8 +187,9 @@ __device__ __forceinline__ bool owns(int c, int n, int T, bool isLast) {
 // ------------------------------------------------------------------------------- sweep A
 // Shared memory: an in-plane tile of NF fields on a (TY+2R) x (TX+2R) box (corners unused) for the
 // output plane, plus the k-queue of (u, T) for the 2R+1 planes in flight.  Q's k-queue is in registers.
-template <int ND, int R, bool COMPOSITE, int DLO, int DN, int TLO, int TN, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_sweepA(FusedArgs a) {
+template <int ND, int R, int DLO, int DN, int TLO, int TN>
+__global__ void __launch_bounds__(NT, 2) k_sweepA(FusedArgs a) {
+  const bool COMPOSITE = a.composite != 0;
   constexpr int NU = ND + 2;
   constexpr int NTAU = ND * (ND + 1) / 2;
   constexpr int W = TX + 2 * R, H = TY + 2 * R;
@@ -283,7 +340,6 @@ __global__ void __launch_bounds__(NT, MINB) k_sweepA(FusedArgs a) {
     }
     __syncthreads();
     if (mine) {
-      auto at = [&](int f, int row, int col) -> double { return T0[((size_t)f * H + row) * W + col]; };
       // ---- derivatives of (u, T) along xi, eta, zeta
       double dxi[ND][NP];
 #pragma unroll
@@ -294,7 +350,7 @@ __global__ void __launch_bounds__(NT, MINB) k_sweepA(FusedArgs a) {
           for (int q = 1; q <= R; ++q) r += a.D[0].c[R + q] * (tc[f * H * W + q] - tc[f * H * W - q]);
           dxi[0][f] = r;
         } else {
-          dxi[0][f] = line_apply(a.D[0], i, a.nx, [&](int cc) { return at(f, ty + R, cc - i0 + R); });
+          dxi[0][f] = tile_line_apply<W, H>(&a.ops->D[0], i, a.nx, T0, f, ty + R, tx + R, 0, i0 - R);
         }
         if (fastJ) {
           double r = 0.0;
@@ -302,7 +358,7 @@ __global__ void __launch_bounds__(NT, MINB) k_sweepA(FusedArgs a) {
           for (int q = 1; q <= R; ++q) r += a.D[1].c[R + q] * (tc[f * H * W + q * W] - tc[f * H * W - q * W]);
           dxi[1][f] = r;
         } else {
-          dxi[1][f] = line_apply(a.D[1], j, a.ny, [&](int cc) { return at(f, cc - j0 + R, tx + R); });
+          dxi[1][f] = tile_line_apply<W, H>(&a.ops->D[1], j, a.ny, T0, f, ty + R, tx + R, 1, j0 - R);
         }
       }
       if constexpr (ND == 3) {
@@ -394,10 +450,8 @@ __global__ void __launch_bounds__(NT, MINB) k_sweepA(FusedArgs a) {
             const int cd = d == 0 ? i : j, nd = d == 0 ? a.nx : a.ny;
 #pragma unroll
             for (int c = 0; c < NU; ++c) {
-              auto getq = [&](int cc) { return d == 0 ? at(FQ + c, ty + R, cc - i0 + R) : at(FQ + c, cc - j0 + R, tx + R); };
-              auto geta = [&](int cc) { return d == 0 ? at(FA, ty + R, cc - i0 + R) : at(FA + 1, cc - j0 + R, tx + R); };
-              dz[c] += COMPOSITE ? line_apply(a.Dd[d], cd, nd, getq)
-                                 : line_dissipation(a.Dd[d], a.Dt[d], a.dir[d], cd, getq, geta);
+              dz[c] += COMPOSITE ? tile_line_apply<W, H>(&a.ops->Dd[d], cd, nd, T0, FQ + c, ty + R, tx + R, d, (d == 0 ? i0 : j0) - R)
+                                 : tile_line_dissipation<W, H>(a.ops, d, cd, T0, FQ + c, FA + d, ty + R, tx + R, (d == 0 ? i0 : j0) - R);
             }
           }
         }
@@ -550,8 +604,8 @@ __device__ __forceinline__ void fluxes_from_raw(const FusedArgs& a, const RawPoi
   }
 }
 
-template <int ND, int R, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_sweepB(FusedArgs a) {
+template <int ND, int R>
+__global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
   constexpr int NU = ND + 2;
   constexpr int W = TX + 2 * R, H = TY + 2 * R;
   constexpr int RK = (ND == 3) ? R : 0;
@@ -701,7 +755,7 @@ __global__ void __launch_bounds__(NT, MINB) k_sweepB(FusedArgs a) {
 #pragma unroll
           for (int q = 1; q <= R; ++q) r += a.D[0].c[R + q] * (f1c[c * TY * W + q] - f1c[c * TY * W - q]);
         } else {
-          r = line_apply(a.D[0], i, a.nx, [&](int cc) { return F1[((size_t)c * TY + ty) * W + cc - i0 + R]; });
+          r = strided_line_apply<W>(&a.ops->D[0], i, a.nx, F1 + ((size_t)c * TY + ty) * W, 1, i0 - R);
         }
         if (fastJ) {
           double r2 = 0.0;
@@ -710,7 +764,7 @@ __global__ void __launch_bounds__(NT, MINB) k_sweepB(FusedArgs a) {
             r2 += a.D[1].c[R + q] * (f2c[c * H * TX + q * TX] - f2c[c * H * TX - q * TX]);
           r += r2;
         } else {
-          r += line_apply(a.D[1], j, a.ny, [&](int cc) { return F2[((size_t)c * H + cc - j0 + R) * TX + tx]; });
+          r += strided_line_apply<H>(&a.ops->D[1], j, a.ny, F2 + (size_t)c * H * TX + tx, TX, j0 - R);
         }
         rxy[RK][c] = r;
       }
@@ -782,6 +836,474 @@ __global__ void __launch_bounds__(NT, MINB) k_sweepB(FusedArgs a) {
     }
     __syncthreads();
     // advance plane bookkeeping
+    if (ND == 3) {
+      ++ks; ++kp;
+      if (a.wrapK) { if (ks >= a.nz) ks -= a.nz; if (kp >= a.nz) kp -= a.nz; }
+      if (++slot >= NQ) slot = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------- adjoint sweep 1
+// computeRhsAdjoint, first half (reference src/RhsHelperImpl.f90:408-553) + addDissipation(ADJOINT):
+//   dW_d = D+_d w (adjoint first derivative, all directions)        -> in-plane tile + k register queue
+//   rhs  = sum_d (A_d - B_d)^T dW_d  - sigma * Diss(w)               -> written to `rhs`
+//   diffusion_j = sum_i B2(i,j)^T dW_i(2:)   (viscous)               -> written to `diffOut` (4 x nD comps)
+// Same 2.5-D streaming structure as sweep A with X = w.  a.D = adjoint first derivative operators.
+template <int ND, int R, int DLO, int DN, int TLO, int TN>
+__global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
+  const bool COMPOSITE = a.composite != 0;
+  constexpr int NU = ND + 2;
+  constexpr int NTAU = ND * (ND + 1) / 2;
+  constexpr int W = TX + 2 * R, H = TY + 2 * R;
+  constexpr int NF = NU + 2;                   // w, arc_i, arc_j
+  constexpr int FA = NU;
+  constexpr int RK = (ND == 3) ? R : 0;
+  constexpr int NQ = 2 * RK + 1;
+  extern __shared__ double smem[];
+  double* const T0 = smem;                                   // [NF][H][W]
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  int i0, j0;
+  bool lastI, lastJ;
+  tile_origin(blockIdx.x, a.nx, TX, i0, lastI);
+  tile_origin(blockIdx.y, a.ny, TY, j0, lastJ);
+  const int i = i0 + tx, j = j0 + ty;
+  const bool mine = owns(i, a.nx, TX, lastI) && owns(j, a.ny, TY, lastJ);
+  const bool inside = i < a.nx && j < a.ny;
+  const long pij = (long)i + (long)a.nx * j;
+  auto touches = [&](int d, int c0, int T, int n) {
+    int depth = a.D[d].depth;
+    if (a.dissOn) {
+      depth = max(depth, a.Dd[d].depth);
+      if (!COMPOSITE) depth = max(depth, max(a.Dt[d].depth + a.Dd[d].width, a.dir[d].normDepth));
+    }
+    return (a.dir[d].hasB0 && c0 < depth) || (a.dir[d].hasB1 && c0 + T > n - depth);
+  };
+  const bool dissOn = a.dissOn != 0;
+  const bool fastI = !touches(0, i0, TX, a.nx);
+  const bool fastJ = !touches(1, j0, TY, a.ny);
+  double* const tc = T0 + (ty + R) * W + tx + R;
+
+  int hcol = 0, hrow = 0, hk = 0;
+  long hp = -1;
+  {
+    const int h = threadIdx.x;
+    if (h < 2 * R * TY) {
+      const int ii = h % (2 * R), row = h / (2 * R);
+      const int lc = ii < R ? ii : TX + ii;
+      const int gi = wrap_index(i0 - R + lc, a.dir[0]);
+      const int gj = j0 + row;
+      hcol = lc; hrow = row + R;
+      if (gi >= 0 && gj < a.ny) { hk = 1; hp = (long)gi + (long)a.nx * gj; }
+    } else if (h < 2 * R * TY + 2 * R * TX) {
+      const int h2 = h - 2 * R * TY;
+      const int col = h2 % TX, jj = h2 / TX;
+      const int lr = jj < R ? jj : TY + jj;
+      const int gj = wrap_index(j0 - R + lr, a.dir[1]);
+      const int gi = i0 + col;
+      hcol = col + R; hrow = lr;
+      if (gj >= 0 && gi < a.nx) { hk = 2; hp = (long)gi + (long)a.nx * gj; }
+    }
+  }
+  const int kc0 = a.kBeg + blockIdx.z * a.kChunk;
+  const int kc1 = min(kc0 + a.kChunk, a.kEnd);
+  auto wrapPlane = [&](int k) -> int {
+    if (ND < 3 || !a.wrapK) return k;
+    int kk = k % a.nz;
+    return kk < 0 ? kk + a.nz : kk;
+  };
+  int ks = wrapPlane(kc0 - RK);
+
+  double qq[NQ][NU];               // w at planes p-RK .. p+RK
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int c = 0; c < NU; ++c) qq[q][c] = 0.0;
+  for (int s = kc0 - RK; s < kc1 + RK; ++s) {
+#pragma unroll
+    for (int q = 0; q < NQ - 1; ++q)
+#pragma unroll
+      for (int c = 0; c < NU; ++c) qq[q][c] = qq[q + 1][c];
+    if (inside) {
+      const double* __restrict__ Wp = a.Win + ((ND == 3) ? (long)ks * a.plane : 0) + pij;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) qq[NQ - 1][c] = __ldg(Wp + (size_t)c * a.cs);
+    }
+    const int p = s - RK;
+    int kp = ks - RK;
+    if (ND == 3 && a.wrapK && kp < 0) kp += a.nz;
+    if (ND == 3) {
+      ++ks;
+      if (a.wrapK && ks >= a.nz) ks -= a.nz;
+    }
+    if (p < kc0) continue;
+    const long poff = (ND == 3) ? (long)kp * a.plane : 0;
+    const long off = poff + pij;
+    // own-point inputs of the pointwise part: issue the loads before the tile is built
+    double Q[NU], tq[NTAU + ND], M[ND * ND], jac = 0.0;
+    if (mine) {
+#pragma unroll
+      for (int c = 0; c < NU; ++c) Q[c] = __ldg(a.Q + (size_t)c * a.cs + off);
+      if (a.viscous) {
+#pragma unroll
+        for (int e = 0; e < NTAU + ND; ++e) tq[e] = __ldg(a.tauqIn + (size_t)e * a.cs + off);
+        jac = __ldg(a.jac + off);
+      }
+#pragma unroll
+      for (int c = 0; c < ND * ND; ++c) {
+        const bool diag = (c % ND) == (c / ND);
+        M[c] = (a.curvilinear || diag) ? __ldg(a.m + (size_t)c * a.cs + off) : 0.0;
+      }
+    }
+    if (inside) {
+#pragma unroll
+      for (int c = 0; c < NU; ++c) tc[c * H * W] = qq[RK][c];
+      if (!COMPOSITE && dissOn) {
+        tc[(FA + 0) * H * W] = a.arc[(size_t)0 * a.cs + off];
+        tc[(FA + 1) * H * W] = a.arc[(size_t)1 * a.cs + off];
+      }
+    }
+    if (hk) {
+      const long hoff = poff + hp;
+      double* const th = T0 + hrow * W + hcol;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) th[c * H * W] = __ldg(a.Win + (size_t)c * a.cs + hoff);
+      if (!COMPOSITE && dissOn) th[(FA + hk - 1) * H * W] = a.arc[(size_t)(hk - 1) * a.cs + hoff];
+    }
+    __syncthreads();
+    if (mine) {
+      double dW[ND][NU];
+#pragma unroll
+      for (int f = 0; f < NU; ++f) {
+        if (fastI) {
+          double r = 0.0;
+#pragma unroll
+          for (int q = 1; q <= R; ++q) r += a.D[0].c[R + q] * (tc[f * H * W + q] - tc[f * H * W - q]);
+          dW[0][f] = r;
+        } else {
+          dW[0][f] = tile_line_apply<W, H>(&a.ops->D[0], i, a.nx, T0, f, ty + R, tx + R, 0, i0 - R);
+        }
+        if (fastJ) {
+          double r = 0.0;
+#pragma unroll
+          for (int q = 1; q <= R; ++q) r += a.D[1].c[R + q] * (tc[f * H * W + q * W] - tc[f * H * W - q * W]);
+          dW[1][f] = r;
+        } else {
+          dW[1][f] = tile_line_apply<W, H>(&a.ops->D[1], j, a.ny, T0, f, ty + R, tx + R, 1, j0 - R);
+        }
+      }
+      if constexpr (ND == 3) {
+#pragma unroll
+        for (int f = 0; f < NU; ++f) {
+          double r = 0.0;
+#pragma unroll
+          for (int q = 1; q <= RK; ++q) r += a.D[2].c[RK + q] * (qq[RK + q][f] - qq[RK - q][f]);
+          dW[ND - 1][f] = r;
+        }
+      }
+      // ---- pointwise Jacobian-transpose products
+      Prim<ND> sp;
+      dependent<ND>(Q, a.pp.gamma, sp);
+      double tau[ND * ND], qh[ND];
+      if (a.viscous) {
+#pragma unroll
+        for (int l = 0; l < ND; ++l)
+#pragma unroll
+          for (int c = 0; c < ND; ++c) tau[l + ND * c] = tq[tau_index<ND>(l, c)];
+#pragma unroll
+        for (int e = 0; e < ND; ++e) qh[e] = tq[NTAU + e];
+      }
+      double r[NU];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) r[c] = 0.0;
+#pragma unroll
+      for (int d = 0; d < ND; ++d)
+        add_flux_jacobian_transpose<ND>(Q, sp, &M[ND * d], a.pp.gamma, a.viscous, a.pp.powerLaw, tau, qh, dW[d], r);
+      if (a.viscous) {
+        double mu, lam, kap;
+        transport(sp.T, a.pp, mu, lam, kap);
+#pragma unroll
+        for (int jj = 0; jj < ND; ++jj) {
+          double dd[ND + 1];
+#pragma unroll
+          for (int c = 0; c < ND + 1; ++c) dd[c] = 0.0;
+#pragma unroll
+          for (int ii = 0; ii < ND; ++ii)
+            add_second_partial_transpose<ND>(sp.u, mu, lam, kap, jac, &M[ND * ii], &M[ND * jj], &dW[ii][1], dd);
+#pragma unroll
+          for (int c = 0; c < ND + 1; ++c) a.diffOut[(size_t)(c + (NU - 1) * jj) * a.cs + off] = dd[c];
+        }
+      }
+      // ---- adjoint dissipation: - sigma * sum_dir Diss_dir(w)
+      if (dissOn) {
+        double dz[NU];
+#pragma unroll
+        for (int c = 0; c < NU; ++c) dz[c] = 0.0;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const bool fast = d == 0 ? fastI : fastJ;
+          const int st = d == 0 ? 1 : W;
+          if (fast) {
+            double e[2 * R + 1];
+            if (COMPOSITE) {
+#pragma unroll
+              for (int m = 0; m < 2 * R + 1; ++m) e[m] = a.Dd[d].c[m];
+            } else {
+#pragma unroll
+              for (int m = 0; m < 2 * R + 1; ++m) e[m] = 0.0;
+#pragma unroll
+              for (int ea = 0; ea < TN; ++ea) {
+                const double w = -a.Dt[d].c[ea] * tc[(FA + d) * H * W + (TLO + ea) * st];
+#pragma unroll
+                for (int eb = 0; eb < DN; ++eb) e[TLO + ea + DLO + eb + R] += w * a.Dd[d].c[eb];
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < NU; ++c) {
+              double rr = 0.0;
+#pragma unroll
+              for (int m = 0; m < 2 * R + 1; ++m) rr += e[m] * tc[c * H * W + (m - R) * st];
+              dz[c] += rr;
+            }
+          } else {
+            const int cd = d == 0 ? i : j, nd = d == 0 ? a.nx : a.ny;
+#pragma unroll
+            for (int c = 0; c < NU; ++c) {
+              dz[c] += COMPOSITE ? tile_line_apply<W, H>(&a.ops->Dd[d], cd, nd, T0, c, ty + R, tx + R, d, (d == 0 ? i0 : j0) - R)
+                                 : tile_line_dissipation<W, H>(a.ops, d, cd, T0, c, FA + d, ty + R, tx + R, (d == 0 ? i0 : j0) - R);
+            }
+          }
+        }
+        if constexpr (ND == 3) {
+          double e[2 * RK + 1];
+          if (COMPOSITE) {
+#pragma unroll
+            for (int m = 0; m < 2 * RK + 1; ++m) e[m] = a.Dd[2].c[m];
+          } else {
+#pragma unroll
+            for (int m = 0; m < 2 * RK + 1; ++m) e[m] = 0.0;
+#pragma unroll
+            for (int ea = 0; ea < TN; ++ea) {
+              int kk = kp + TLO + ea;
+              if (a.wrapK) { if (kk < 0) kk += a.nz; else if (kk >= a.nz) kk -= a.nz; }
+              const double w = -a.Dt[2].c[ea] * a.arc[(size_t)2 * a.cs + (long)kk * a.plane + pij];
+#pragma unroll
+              for (int eb = 0; eb < DN; ++eb) e[TLO + ea + DLO + eb + RK] += w * a.Dd[2].c[eb];
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < NU; ++c) {
+            double rr = 0.0;
+#pragma unroll
+            for (int m = 0; m < 2 * RK + 1; ++m) rr += e[m] * qq[m][c];
+            dz[c] += rr;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NU; ++c) r[c] -= a.dissAmount * dz[c];
+      }
+#pragma unroll
+      for (int c = 0; c < NU; ++c) a.rhs[(size_t)c * a.cs + off] = r[c];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------- adjoint sweep 2
+// computeRhsAdjoint, second half (reference src/RhsHelperImpl.f90:555-570) + x 1/J + substepAdjointRK4:
+//   t = sum_j D+_j diffusion_j ; variable change ; rhs = (rhsPartial -/+ t) / J ; RK4 substep on w.
+// Same structure as sweep B with G_d = diffusion_d (NU-1 components, read from memory).
+template <int ND, int R>
+__global__ void __launch_bounds__(NT, 2) k_adjoint2(FusedArgs a) {
+  constexpr int NU = ND + 2;
+  constexpr int NG = NU - 1;
+  constexpr int W = TX + 2 * R, H = TY + 2 * R;
+  constexpr int RK = (ND == 3) ? R : 0;
+  constexpr int NQ = 2 * RK + 1;
+  extern __shared__ double smem[];
+  double* F1 = smem;                               // [NG][TY][W]
+  double* F2 = F1 + (size_t)NG * TY * W;           // [NG][H][TX]
+  double* F3 = F2 + (size_t)NG * H * TX;           // [NQ][NG][NT]
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  int i0, j0;
+  bool lastI, lastJ;
+  tile_origin(blockIdx.x, a.nx, TX, i0, lastI);
+  tile_origin(blockIdx.y, a.ny, TY, j0, lastJ);
+  const int i = i0 + tx, j = j0 + ty;
+  const bool mine = owns(i, a.nx, TX, lastI) && owns(j, a.ny, TY, lastJ);
+  const bool inside = i < a.nx && j < a.ny;
+  const long pij = (long)i + (long)a.nx * j;
+  const bool fastI = !((a.D[0].hasB0 && i0 < a.D[0].depth) || (a.D[0].hasB1 && i0 + TX > a.nx - a.D[0].depth));
+  const bool fastJ = !((a.D[1].hasB0 && j0 < a.D[1].depth) || (a.D[1].hasB1 && j0 + TY > a.ny - a.D[1].depth));
+  double* const f1c = F1 + ty * W + tx + R;
+  double* const f2c = F2 + (ty + R) * TX + tx;
+  double* const f3c = F3 + threadIdx.x;
+  int hcol = 0, hrow = 0, hk = 0;
+  long hp = -1;
+  {
+    const int h = threadIdx.x;
+    if (h < 2 * R * TY) {
+      const int ii = h % (2 * R), row = h / (2 * R);
+      const int lc = ii < R ? ii : TX + ii;
+      const int gi = wrap_index(i0 - R + lc, a.dir[0]);
+      const int gj = j0 + row;
+      hcol = lc; hrow = row;
+      if (gi >= 0 && gj < a.ny) { hk = 1; hp = (long)gi + (long)a.nx * gj; }
+    } else if (h < 2 * R * TY + 2 * R * TX) {
+      const int h2 = h - 2 * R * TY;
+      const int col = h2 % TX, jj = h2 / TX;
+      const int lr = jj < R ? jj : TY + jj;
+      const int gj = wrap_index(j0 - R + lr, a.dir[1]);
+      const int gi = i0 + col;
+      hcol = col; hrow = lr;
+      if (gj >= 0 && gi < a.nx) { hk = 2; hp = (long)gi + (long)a.nx * gj; }
+    }
+  }
+  const int kc0 = a.kBeg + blockIdx.z * a.kChunk;
+  const int kc1 = min(kc0 + a.kChunk, a.kEnd);
+  auto wrapPlane = [&](int k) -> int {
+    if (ND < 3 || !a.wrapK) return k;
+    int kk = k % a.nz;
+    return kk < 0 ? kk + a.nz : kk;
+  };
+  int ks = wrapPlane(kc0 - RK);
+  int kp = wrapPlane(kc0 - 2 * RK);
+  int slot = 0;
+  double rxy[RK + 1][NG];
+#pragma unroll
+  for (int q = 0; q < RK + 1; ++q)
+#pragma unroll
+    for (int c = 0; c < NG; ++c) rxy[q][c] = 0.0;
+  for (int s = kc0 - RK; s < kc1 + RK; ++s) {
+    const long soff = (ND == 3) ? (long)ks * a.plane : 0;
+    const bool planeActive = s >= kc0 && s < kc1;
+    if (a.viscous) {
+      if (inside) {
+        const double* __restrict__ dp = a.diffIn + soff + pij;
+        if constexpr (ND == 3) {
+#pragma unroll
+          for (int c = 0; c < NG; ++c) f3c[((size_t)slot * NG + c) * NT] = __ldg(dp + (size_t)(c + NG * 2) * a.cs);
+        }
+        if (planeActive) {
+#pragma unroll
+          for (int c = 0; c < NG; ++c) {
+            f1c[c * TY * W] = __ldg(dp + (size_t)(c + NG * 0) * a.cs);
+            f2c[c * H * TX] = __ldg(dp + (size_t)(c + NG * 1) * a.cs);
+          }
+        }
+      }
+      if (planeActive && hk) {
+        const double* __restrict__ dp = a.diffIn + soff + hp;
+        if (hk == 1) {
+#pragma unroll
+          for (int c = 0; c < NG; ++c) F1[((size_t)c * TY + hrow) * W + hcol] = __ldg(dp + (size_t)(c + NG * 0) * a.cs);
+        } else {
+#pragma unroll
+          for (int c = 0; c < NG; ++c) F2[((size_t)c * H + hrow) * TX + hcol] = __ldg(dp + (size_t)(c + NG * 1) * a.cs);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < RK; ++q)
+#pragma unroll
+      for (int c = 0; c < NG; ++c) rxy[q][c] = rxy[q + 1][c];
+    if (a.viscous && planeActive && mine) {
+#pragma unroll
+      for (int c = 0; c < NG; ++c) {
+        double r;
+        if (fastI) {
+          r = 0.0;
+#pragma unroll
+          for (int q = 1; q <= R; ++q) r += a.D[0].c[R + q] * (f1c[c * TY * W + q] - f1c[c * TY * W - q]);
+        } else {
+          r = strided_line_apply<W>(&a.ops->D[0], i, a.nx, F1 + ((size_t)c * TY + ty) * W, 1, i0 - R);
+        }
+        if (fastJ) {
+          double r2 = 0.0;
+#pragma unroll
+          for (int q = 1; q <= R; ++q)
+            r2 += a.D[1].c[R + q] * (f2c[c * H * TX + q * TX] - f2c[c * H * TX - q * TX]);
+          r += r2;
+        } else {
+          r += strided_line_apply<H>(&a.ops->D[1], j, a.ny, F2 + (size_t)c * H * TX + tx, TX, j0 - R);
+        }
+        rxy[RK][c] = r;
+      }
+    }
+    const int p = s - RK;
+    if (p >= kc0 && mine) {
+      const long off = ((ND == 3) ? (long)kp * a.plane : 0) + pij;
+      const double jac = __ldg(a.jac + off);
+      double rp[NU], vb1[NU], vb2[NU], Q[NU];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) {
+        const size_t qi = (size_t)c * a.cs + off;
+        rp[c] = a.rhsIn[qi];
+        if (a.viscous) Q[c] = __ldg(a.Q + qi);
+        if (a.fuseRk) {
+          vb1[c] = (a.stage == 1) ? a.Win[qi] : ((a.stage == 4) ? 0.0 : a.b1in[qi]);
+          vb2[c] = (a.stage == 1) ? 0.0 : a.b2[qi];
+        }
+      }
+      if (a.viscous) {
+        double t[NG];
+#pragma unroll
+        for (int c = 0; c < NG; ++c) t[c] = rxy[0][c];
+        if constexpr (ND == 3) {
+          int sp0 = slot - RK;
+          if (sp0 < 0) sp0 += NQ;
+#pragma unroll
+          for (int q = 1; q <= RK; ++q) {
+            int sp = sp0 + q, sm = sp0 - q;
+            if (sp >= NQ) sp -= NQ;
+            if (sm < 0) sm += NQ;
+            const double cq = a.D[2].c[RK + q];
+#pragma unroll
+            for (int c = 0; c < NG; ++c)
+              t[c] += cq * (f3c[((size_t)sp * NG + c) * NT] - f3c[((size_t)sm * NG + c) * NT]);
+          }
+        }
+        // variable change (reference src/RhsHelperImpl.f90:560-570)
+        Prim<ND> sq;
+        dependent<ND>(Q, a.pp.gamma, sq);
+        t[ND] = a.pp.gamma * sq.v * t[ND];
+        double ut = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+          t[d] = sq.v * t[d] - sq.u[d] * t[ND];
+          ut = (d == 0) ? sq.u[0] * t[0] : ut + sq.u[d] * t[d];
+        }
+#pragma unroll
+        for (int c = 0; c < NG; ++c) rp[c + 1] -= t[c];
+        rp[0] += sq.v * Q[NU - 1] * t[ND] + ut;
+      }
+      double r[NU];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) r[c] = rp[c] * jac;
+      if (!a.fuseRk) {
+#pragma unroll
+        for (int c = 0; c < NU; ++c) a.rhs[(size_t)c * a.cs + off] = r[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < NU; ++c) {
+          const size_t qi = (size_t)c * a.cs + off;
+          if (a.stage == 1) {
+            a.b2[qi] = vb1[c] + a.dt * r[c] / 6.0;
+            a.Qout[qi] = vb1[c] + a.dt * r[c] / 2.0;
+          } else if (a.stage == 2) {
+            a.b2[qi] = vb2[c] + a.dt * r[c] / 3.0;
+            a.Qout[qi] = vb1[c] + a.dt * r[c] / 2.0;
+          } else if (a.stage == 3) {
+            a.b2[qi] = vb2[c] + a.dt * r[c] / 3.0;
+            a.Qout[qi] = vb1[c] + a.dt * r[c];
+          } else {
+            a.Qout[qi] = vb2[c] + a.dt * r[c] / 6.0;
+          }
+        }
+      }
+    }
+    __syncthreads();
     if (ND == 3) {
       ++ks; ++kp;
       if (a.wrapK) { if (ks >= a.nz) ks -= a.nz; if (kp >= a.nz) kp -= a.nz; }
@@ -866,6 +1388,7 @@ int fill_args(mg_state* s, FusedArgs* a) {
       if (!g->compositeDissipation) MG_TRY(fill_lineop(g->dissipationTranspose[d], &a->Dt[d]));
     }
   }
+  a->composite = (g->compositeDissipation || !g->dissipationOn) ? 1 : 0;
   a->pp = s->phys();
   static const int pf = getenv("MG_PREFETCH") ? atoi(getenv("MG_PREFETCH")) : 2;
   a->prefetch = pf;
@@ -876,13 +1399,25 @@ int fill_args(mg_state* s, FusedArgs* a) {
   return 0;
 }
 
-template <int ND, int R, bool COMP, int DLO, int DN, int TLO, int TN>
+// Device copy of the operator tables for the out-of-line closure path (built once per state and mode).
+int upload_ops(mg_state* s, int which, FusedArgs* a) {
+  if (!s->fusedOps[which]) {
+    DevOps h;
+    std::memset(&h, 0, sizeof(h));
+    for (int d = 0; d < 3; ++d) { h.D[d] = a->D[d]; h.Dd[d] = a->Dd[d]; h.Dt[d] = a->Dt[d]; h.dir[d] = a->dir[d]; }
+    MG_CUDA(cudaMalloc(&s->fusedOps[which], sizeof(DevOps)));
+    MG_CUDA(cudaMemcpy(s->fusedOps[which], &h, sizeof(DevOps), cudaMemcpyHostToDevice));
+  }
+  a->ops = (const DevOps*)s->fusedOps[which];
+  return 0;
+}
+
+template <int ND, int R, int DLO, int DN, int TLO, int TN>
 int launchA(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NF = (ND + 2) + ND + 1 + 2;
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
   const size_t smem = sizeof(double) * ((size_t)NF * (TY + 2 * R) * (TX + 2 * R) + (size_t)NQ * (ND + 1) * NT);
-  static const int minb = getenv("MG_MINB_A") ? atoi(getenv("MG_MINB_A")) : 2;
-  auto kern = minb == 1 ? k_sweepA<ND, R, COMP, DLO, DN, TLO, TN, 1> : k_sweepA<ND, R, COMP, DLO, DN, TLO, TN, 2>;
+  auto kern = k_sweepA<ND, R, DLO, DN, TLO, TN>;
   static bool configured = false;
   if (!configured) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -902,8 +1437,7 @@ int launchB(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
   const size_t smem = sizeof(double) * ((size_t)NU * TY * (TX + 2 * R) + (size_t)NU * (TY + 2 * R) * TX +
                                         (size_t)NQ * NU * NT);
-  static const int minb = getenv("MG_MINB_B") ? atoi(getenv("MG_MINB_B")) : 2;
-  auto kern = minb == 1 ? k_sweepB<ND, R, 1> : k_sweepB<ND, R, 2>;
+  auto kern = k_sweepB<ND, R>;
   static bool configured = false;
   if (!configured) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -949,7 +1483,7 @@ dim3 tiles(const FusedArgs& a, int nChunks) {
 
 int mg_fused_supported(const mg_state* s, int mode) {
   const mg_grid* g = s->grid;
-  if (mode != MG_FORWARD) return 0;
+  if (mode != MG_FORWARD && mode != MG_ADJOINT) return 0;
   if (g->nD < 2) return 0;
   if (g->iblank) return 0;
   if (!s->patches.empty() || !s->acousticSources.empty()) return 0;
@@ -960,7 +1494,7 @@ int mg_fused_supported(const mg_state* s, int mode) {
   for (int d = 0; d < 2; ++d)
     if (g->periodicityType[d] == MG_PERIODIC_NONE) {
       // a closure block (and its adjoint-free forward operators) must fit in one 16-wide tile + halo
-      const MgDevOp& o = g->firstDerivative[d]->op;
+      const MgDevOp& o = (mode == MG_ADJOINT ? g->adjointFirstDerivative[d] : g->firstDerivative[d])->op;
       if (o.boundaryWidth > TX + si.R || o.boundaryDepth > TX || g->localSize[d] < 2 * o.boundaryDepth) return 0;
     } else if (g->localSize[d] < si.R + 1) {
       return 0;
@@ -983,6 +1517,7 @@ int mg_fused_sweepA(mg_state* s) {
   MG_TRY(mg_fused_alloc(s));
   FusedArgs a;
   MG_TRY(fill_args(s, &a));
+  MG_TRY(upload_ops(s, 0, &a));
   a.Q = s->Q[s->cur].comp(0);
   a.tauq = s->opt.viscosityOn ? s->tauq.comp(0) : nullptr;
   a.diss = s->opt.dissipationOn ? s->dissTerm.comp(0) : nullptr;
@@ -991,12 +1526,10 @@ int mg_fused_sweepA(mg_state* s) {
   scheme_of(g, &si);
   const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
   cudaStream_t st = mg_stream();
-  const bool comp = g->compositeDissipation || !g->dissipationOn;
   int rc = -1;
 #define MG_A(ND_, R_, DLO, DN, TLO, TN)                                                 \
   if (s->nD == ND_ && si.R == R_)                                                       \
-    rc = comp ? launchA<ND_, R_, true, DLO, DN, TLO, TN>(a, grid, st)                   \
-              : launchA<ND_, R_, false, DLO, DN, TLO, TN>(a, grid, st);
+    rc = launchA<ND_, R_, DLO, DN, TLO, TN>(a, grid, st);
   MG_A(2, 2, -1, 3, -1, 3)
   MG_A(2, 3, -2, 4, -1, 4)
   MG_A(2, 4, -2, 5, -2, 5)
@@ -1015,6 +1548,7 @@ int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
   if (!s->fusedValid) MG_FAIL("fused sweep B: state has not been updated (sweep A)");
   FusedArgs a;
   MG_TRY(fill_args(s, &a));
+  MG_TRY(upload_ops(s, 0, &a));
   a.Q = s->Q[s->cur].comp(0);
   a.tauqIn = s->opt.viscosityOn ? s->tauq.comp(0) : nullptr;
   a.dissIn = s->opt.dissipationOn ? s->dissTerm.comp(0) : nullptr;
@@ -1057,6 +1591,135 @@ int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
     }
     s->fusedValid = false;
     s->dependentValid = false;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ adjoint host side
+namespace {
+
+template <int ND, int R, int DLO, int DN, int TLO, int TN>
+int launchAdj1(const FusedArgs& a, dim3 grid, cudaStream_t st) {
+  constexpr int NF = (ND + 2) + 2;
+  const size_t smem = sizeof(double) * (size_t)NF * (TY + 2 * R) * (TX + 2 * R);
+  auto kern = k_adjoint1<ND, R, DLO, DN, TLO, TN>;
+  static bool configured = false;
+  if (!configured) {
+    MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  mg_profile_begin("adjoint1");
+  kern<<<grid, NT, smem, st>>>(a);
+  mg_profile_end();
+  MG_CUDA(cudaGetLastError());
+  mg_count_launches(1);
+  return 0;
+}
+
+template <int ND, int R>
+int launchAdj2(const FusedArgs& a, dim3 grid, cudaStream_t st) {
+  constexpr int NG = ND + 1;
+  constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
+  const size_t smem = sizeof(double) * ((size_t)NG * TY * (TX + 2 * R) + (size_t)NG * (TY + 2 * R) * TX +
+                                        (size_t)NQ * NG * NT);
+  auto kern = k_adjoint2<ND, R>;
+  static bool configured = false;
+  if (!configured) {
+    MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  mg_profile_begin("adjoint2");
+  kern<<<grid, NT, smem, st>>>(a);
+  mg_profile_end();
+  MG_CUDA(cudaGetLastError());
+  mg_count_launches(1);
+  return 0;
+}
+
+int fill_args_adjoint(mg_state* s, FusedArgs* a) {
+  mg_grid* g = s->grid;
+  MG_TRY(fill_args(s, a));
+  for (int d = 0; d < g->nD; ++d) MG_TRY(fill_lineop(g->adjointFirstDerivative[d], &a->D[d]));
+  a->Q = s->Q[s->cur].comp(0);
+  a->Win = s->W[s->curW].comp(0);
+  a->tauqIn = s->opt.viscosityOn ? s->tauq.comp(0) : nullptr;
+  a->dissOn = s->opt.dissipationOn;
+  MG_TRY(upload_ops(s, 1, a));
+  return 0;
+}
+
+}  // namespace
+
+// Adjoint sweep 1: rhs (partial) and adjoint diffusion.  Needs the forward state's sweep-A outputs.
+int mg_fused_adjoint1(mg_state* s) {
+  mg_grid* g = s->grid;
+  if (!s->fusedValid) MG_TRY(mg_fused_sweepA(s));
+  FusedArgs a;
+  MG_TRY(fill_args_adjoint(s, &a));
+  a.rhs = s->rhs.comp(0);
+  a.diffOut = g->scratchA.comp(0);
+  if (g->scratchA.compStride != a.cs) MG_FAIL("fused adjoint: scratch stride mismatch");
+  SchemeInfo si;
+  scheme_of(g, &si);
+  const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
+  cudaStream_t st = mg_stream();
+  int rc = -1;
+#define MG_J(ND_, R_, DLO, DN, TLO, TN)                                                 \
+  if (s->nD == ND_ && si.R == R_)                                                       \
+    rc = launchAdj1<ND_, R_, DLO, DN, TLO, TN>(a, grid, st);
+  MG_J(2, 2, -1, 3, -1, 3)
+  MG_J(2, 3, -2, 4, -1, 4)
+  MG_J(2, 4, -2, 5, -2, 5)
+  MG_J(3, 2, -1, 3, -1, 3)
+  MG_J(3, 3, -2, 4, -1, 4)
+  MG_J(3, 4, -2, 5, -2, 5)
+#undef MG_J
+  return rc;
+}
+
+// Adjoint sweep 2: second derivative sweep, variable change, x 1/J (+ RK4 substep on w when fuseRk).
+// `stage` is the reference's adjoint stage (4 -> 1); dt > 0.
+int mg_fused_adjoint2(mg_state* s, int fuseRk, int stage, double dt) {
+  mg_grid* g = s->grid;
+  FusedArgs a;
+  MG_TRY(fill_args_adjoint(s, &a));
+  a.rhsIn = s->rhs.comp(0);
+  a.rhs = s->rhs.comp(0);
+  a.diffIn = g->scratchA.comp(0);
+  a.fuseRk = fuseRk;
+  const int rkStage = 5 - stage;        // adjoint stage 4 plays the role of RK stage 1, ...
+  a.stage = rkStage;
+  a.dt = -dt;
+  if (fuseRk) {
+    if (rkStage == 1) {
+      a.b1in = a.Win;
+      a.Qout = s->rk1.comp(0);
+    } else {
+      a.b1in = s->rk1.comp(0);
+      a.Qout = s->W[1 - s->curW].comp(0);
+    }
+    a.b2 = s->rk2.comp(0);
+  }
+  SchemeInfo si;
+  scheme_of(g, &si);
+  const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
+  cudaStream_t st = mg_stream();
+  int rc = -1;
+  if (s->nD == 2 && si.R == 2) rc = launchAdj2<2, 2>(a, grid, st);
+  if (s->nD == 2 && si.R == 3) rc = launchAdj2<2, 3>(a, grid, st);
+  if (s->nD == 2 && si.R == 4) rc = launchAdj2<2, 4>(a, grid, st);
+  if (s->nD == 3 && si.R == 2) rc = launchAdj2<3, 2>(a, grid, st);
+  if (s->nD == 3 && si.R == 3) rc = launchAdj2<3, 3>(a, grid, st);
+  if (s->nD == 3 && si.R == 4) rc = launchAdj2<3, 4>(a, grid, st);
+  if (rc != 0) return rc;
+  if (fuseRk) {
+    if (rkStage == 1) {
+      MgField tmp = s->rk1;
+      s->rk1 = s->W[s->curW];
+      s->W[s->curW] = tmp;
+    } else {
+      s->curW = 1 - s->curW;
+    }
   }
   return 0;
 }

@@ -358,6 +358,7 @@ void mg_state_destroy_impl(mg_state* s) {
                      &s->velocity, &s->pressure, &s->temperature, &s->mu, &s->lambda, &s->kappa,
                      &s->stressTensor, &s->heatFlux, &s->rk1, &s->rk2, &s->viscFluxCart, &s->tauq, &s->dissTerm})
     mg_field_free(f);
+  for (void* p : s->fusedOps) if (p) cudaFree(p);
   delete s;
 }
 
@@ -555,7 +556,9 @@ int mg_state_compute_rhs_impl(mg_state* s, int mode) {
   if (s->useFused && mg_fused_supported(s, mode)) {
     // fused sweeps: the dependent variables live in the sweep-A outputs (no patches on this path)
     if (!s->fusedValid) MG_TRY(mg_fused_sweepA(s));
-    return mg_fused_sweepB(s, 0, 0, 0.0);
+    if (mode == MG_FORWARD) return mg_fused_sweepB(s, 0, 0, 0.0);
+    MG_TRY(mg_fused_adjoint1(s));
+    return mg_fused_adjoint2(s, 0, 1, 0.0);
   }
   // The reference's callers run state%update after every substep (src/SolverImpl.f90:831-834); here
   // it is refreshed on demand.
@@ -622,6 +625,14 @@ int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int time
     const double factor[5] = {0.0, 1.0, 0.5, 1.0, 2.0};
     s->adjointForcingFactor = factor[stage];
     if (stage == 4) s->timeProgressive = *time - dt / 2.0;
+    if (s->useFused && mg_fused_supported(s, MG_ADJOINT)) {
+      if (!s->fusedValid) MG_TRY(mg_fused_sweepA(s));
+      MG_TRY(mg_fused_adjoint1(s));
+      MG_TRY(mg_fused_adjoint2(s, 1, stage, dt));
+      if (stage == 4 || stage == 2) s->timeProgressive = *time;
+      if (stage == 3 || stage == 1) { *time -= dt / 2.0; s->time = *time; }
+      return 0;
+    }
     MG_TRY(mg_state_compute_rhs_impl(s, MG_ADJOINT));
     a.R = s->rhs.comp(0);
     a.Qin = s->W[s->curW].comp(0);

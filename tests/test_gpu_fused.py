@@ -76,3 +76,43 @@ def test_fused_falls_back_when_patches_present():
     assert region.usesFused(mb.FORWARD)
     st.addPatch("SPONGE", "sp", 1, [1, 6, 1, 28, 1, 1])
     assert not region.usesFused(mb.FORWARD)
+
+
+ADJ_CASES = [
+    ((40, 37), (True, True), False, True, False, "SBP 3-6"),
+    ((40, 37), (True, True), True, True, True, "SBP 3-6"),
+    ((33, 49), (False, False), True, True, False, "SBP 3-6"),
+    ((41, 40), (False, True), True, False, False, "SBP 2-4"),
+    ((40, 41), (False, False), True, True, False, "SBP 4-8"),
+    ((20, 19, 18), (True, True, True), False, True, False, "SBP 3-6"),
+    ((20, 19, 18), (True, True, True), True, True, True, "SBP 3-6"),
+    ((36, 33, 9), (False, False, True), True, True, False, "SBP 3-6"),
+    ((18, 17, 16), (True, True, True), True, True, False, "SBP 2-4"),
+    ((34, 18, 12), (False, True, True), True, True, True, "SBP 4-8"),
+]
+
+
+@pytest.mark.parametrize("shape,periodic,curv,visc,composite,scheme", ADJ_CASES)
+def test_fused_adjoint_rhs_and_rk4(shape, periodic, curv, visc, composite, scheme):
+    import magudi_b200 as mb
+    from oracle import rhs as orhs
+    g, opt, s, rng = oracle_case(shape, periodic, curv, visc, composite, scheme)
+    gg, o, st = gpu_case_from_oracle(g, opt, s)
+    region = mb.Region()
+    region.addState(st)
+    assert region.usesFused(mb.ADJOINT), "fused adjoint path should cover this configuration"
+    s.update(g, opt)
+    st.update()
+    orhs.computeRhs(orhs.ADJOINT, opt, g, s)
+    region.computeRhs(mb.ADJOINT)
+    assert relerr(st.rightHandSide, s.rightHandSide) <= TOL_RHS
+    integ = mb.RK4Integrator(region)
+    oint = orhs.RK4Integrator(s)
+    dt, t, tg = 1e-3, 0.4, 0.4
+    rhs_fn = lambda mode, ts, stage: orhs.computeRhs(mode, opt, g, s)
+    for step in range(2):
+        for stage in range(4, 0, -1):
+            t = oint.substepAdjoint(rhs_fn, s, t, dt, step, stage)
+            tg = integ.substepAdjoint(tg, dt, step, stage)
+    assert abs(t - tg) < 1e-15
+    assert relerr(st.adjointVariables, s.adjointVariables) <= TOL_RHS
