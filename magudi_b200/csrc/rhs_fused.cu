@@ -130,45 +130,36 @@ struct DevOps {
   DirInfo dir[3];
 };
 
-// buf[k] holds the value at coordinate c0 + k of the line.
-__device__ __noinline__ double g_line_apply(const LineOp* op, int c, int n, const double* buf, int c0) {
-  return line_apply(*op, c, n, [&](int cc) { return buf[cc - c0]; });
+// line[(cc - c0) * stride] holds the value at coordinate cc of the line (shared-memory tile, read
+// through generic addresses: this is the slow, rarely taken path).
+__device__ __noinline__ double g_line_apply(const LineOp* op, int c, int n, const double* line, int stride, int c0) {
+  return line_apply(*op, c, n, [&](int cc) { return line[(long)(cc - c0) * stride]; });
 }
 __device__ __noinline__ double g_line_dissipation(const LineOp* Dd, const LineOp* Dt, const DirInfo* di, int c,
-                                                  const double* q, const double* arc, int c0) {
-  return line_dissipation(*Dd, *Dt, *di, c, [&](int cc) { return q[cc - c0]; },
-                          [&](int cc) { return arc[cc - c0]; });
+                                                  const double* q, const double* arc, int stride, int c0) {
+  return line_dissipation(*Dd, *Dt, *di, c, [&](int cc) { return q[(long)(cc - c0) * stride]; },
+                          [&](int cc) { return arc[(long)(cc - c0) * stride]; });
 }
 
-// Gather one line of a shared-memory tile into a local buffer and apply an operator out of line.
 // Tile layout [field][H][W]; dirIdx 0: along columns (i), 1: along rows (j); c0 = coordinate of index 0.
 template <int W, int H>
 __device__ __forceinline__ double tile_line_apply(const LineOp* op, int c, int n, const double* T0, int f, int row,
                                                   int col, int dirIdx, int c0) {
-  constexpr int L = W > H ? W : H;
-  double buf[L];
-  if (dirIdx == 0) { for (int k = 0; k < W; ++k) buf[k] = T0[((size_t)f * H + row) * W + k]; }
-  else { for (int k = 0; k < H; ++k) buf[k] = T0[((size_t)f * H + k) * W + col]; }
-  return g_line_apply(op, c, n, buf, c0);
+  return dirIdx == 0 ? g_line_apply(op, c, n, T0 + ((size_t)f * H + row) * W, 1, c0)
+                     : g_line_apply(op, c, n, T0 + (size_t)f * H * W + col, W, c0);
 }
 template <int W, int H>
 __device__ __forceinline__ double tile_line_dissipation(const DevOps* ops, int d, int c, const double* T0, int fq,
                                                         int fa, int row, int col, int c0) {
-  constexpr int L = W > H ? W : H;
-  double q[L], arc[L];
-  if (d == 0) {
-    for (int k = 0; k < W; ++k) { q[k] = T0[((size_t)fq * H + row) * W + k]; arc[k] = T0[((size_t)fa * H + row) * W + k]; }
-  } else {
-    for (int k = 0; k < H; ++k) { q[k] = T0[((size_t)fq * H + k) * W + col]; arc[k] = T0[((size_t)fa * H + k) * W + col]; }
-  }
-  return g_line_dissipation(&ops->Dd[d], &ops->Dt[d], &ops->dir[d], c, q, arc, c0);
+  return d == 0 ? g_line_dissipation(&ops->Dd[d], &ops->Dt[d], &ops->dir[d], c, T0 + ((size_t)fq * H + row) * W,
+                                     T0 + ((size_t)fa * H + row) * W, 1, c0)
+                : g_line_dissipation(&ops->Dd[d], &ops->Dt[d], &ops->dir[d], c, T0 + (size_t)fq * H * W + col,
+                                     T0 + (size_t)fa * H * W + col, W, c0);
 }
 template <int L>
 __device__ __forceinline__ double strided_line_apply(const LineOp* op, int c, int n, const double* line, int stride,
                                                      int c0) {
-  double buf[L];
-  for (int k = 0; k < L; ++k) buf[k] = line[(size_t)k * stride];
-  return g_line_apply(op, c, n, buf, c0);
+  return g_line_apply(op, c, n, line, stride, c0);
 }
 
 // Tile placement: tiles are anchored at the origin except the last one of a direction, which is
@@ -703,20 +694,17 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
         }
       }
     }
-    // ---- arrival of plane s: issue every global load of this phase first (own point + halo point)
-    RawPoint<ND> rawOwn, rawHalo;
+    // ---- arrival of plane s: own point (loads issued back to back, then the flux evaluation) ...
     if (inside) {
-      if (planeActive) load_raw<ND, ALLDIRS>(a, soff + pij, rawOwn);
-      else load_raw<ND, (ND == 3 ? 4 : 0)>(a, soff + pij, rawOwn);
-    }
-    if (planeActive && hk) {
-      if (hk == 1) load_raw<ND, 1>(a, soff + hp, rawHalo);
-      else load_raw<ND, 2>(a, soff + hp, rawHalo);
-    }
-    if (inside) {
+      RawPoint<ND> raw;
       double Fh[ND][NU];
-      if (planeActive) fluxes_from_raw<ND, ALLDIRS>(a, rawOwn, Fh);
-      else fluxes_from_raw<ND, (ND == 3 ? 4 : 0)>(a, rawOwn, Fh);
+      if (planeActive) {
+        load_raw<ND, ALLDIRS>(a, soff + pij, raw);
+        fluxes_from_raw<ND, ALLDIRS>(a, raw, Fh);
+      } else {
+        load_raw<ND, (ND == 3 ? 4 : 0)>(a, soff + pij, raw);
+        fluxes_from_raw<ND, (ND == 3 ? 4 : 0)>(a, raw, Fh);
+      }
       if constexpr (ND == 3) {
 #pragma unroll
         for (int c = 0; c < NU; ++c) f3c[((size_t)slot * NU + c) * NT] = Fh[ND - 1][c];
@@ -729,14 +717,18 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
         }
       }
     }
+    // ... then the halo point of this thread (xi- or eta-halo)
     if (planeActive && hk) {
+      RawPoint<ND> raw;
       double Fh[ND][NU];
       if (hk == 1) {
-        fluxes_from_raw<ND, 1>(a, rawHalo, Fh);
+        load_raw<ND, 1>(a, soff + hp, raw);
+        fluxes_from_raw<ND, 1>(a, raw, Fh);
 #pragma unroll
         for (int c = 0; c < NU; ++c) F1[((size_t)c * TY + hrow) * W + hcol] = Fh[0][c];
       } else {
-        fluxes_from_raw<ND, 2>(a, rawHalo, Fh);
+        load_raw<ND, 2>(a, soff + hp, raw);
+        fluxes_from_raw<ND, 2>(a, raw, Fh);
 #pragma unroll
         for (int c = 0; c < NU; ++c) F2[((size_t)c * H + hrow) * TX + hcol] = Fh[1][c];
       }
