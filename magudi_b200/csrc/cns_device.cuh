@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 struct PhysParams {
   double gamma;
   double ReInv, PrInv, powerLaw, bulkRatio;
@@ -201,6 +203,125 @@ __device__ __forceinline__ void add_second_partial_transpose(const double* u, do
     y[b] += scale * acc;
   }
   y[ND] += scale * (jac * (kap * temp1) * x[ND]);
+}
+
+// ---- rectilinear specialisations: the metric row of direction D is md * e_D, so most entries of the
+// Jacobians vanish.  Same arithmetic as the general forms above with the zero terms dropped.
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (N > 0) {
+    static_for<N - 1>(f);
+    f(std::integral_constant<int, N - 1>{});
+  }
+}
+
+template <int ND, int D>
+__device__ __forceinline__ void add_flux_jacobian_transpose_rect(const Prim<ND>& s, double md, double gamma,
+                                                                 bool viscous, double powerLaw, const double* tau,
+                                                                 const double* q, const double* x, double* y) {
+  constexpr int NU = ND + 2;
+  const double g1 = gamma - 1.0;
+  double usq = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) usq = (i == 0) ? s.u[0] * s.u[0] : usq + s.u[i] * s.u[i];
+  const double uh = md * s.u[D];
+  const double phi2 = 0.5 * g1 * usq;
+  double cst[ND], temp1 = 0.0, ucst = 0.0, pw = 0.0;
+  if (viscous) {
+#pragma unroll
+    for (int c = 0; c < ND; ++c) cst[c] = md * tau[D + ND * c];
+    const double chf = md * q[D];
+#pragma unroll
+    for (int c = 0; c < ND; ++c) ucst = (c == 0) ? s.u[0] * cst[0] : ucst + s.u[c] * cst[c];
+    temp1 = ucst - chf;
+    pw = powerLaw * gamma * s.v / s.T;
+  }
+  {  // column 0
+    const double t2 = pw * (phi2 / g1 - s.T / gamma);
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+      double A = (a == D) ? phi2 * md - uh * s.u[a] : -(uh * s.u[a]);
+      if (viscous) A -= t2 * cst[a];
+      acc += A * x[a + 1];
+    }
+    double Al = uh * ((gamma - 2.0) / g1 * phi2 - s.T);
+    if (viscous) Al -= t2 * temp1 - s.v * ucst;
+    acc += Al * x[NU - 1];
+    y[0] += acc;
+  }
+#pragma unroll
+  for (int b = 0; b < ND; ++b) {  // columns 1..ND
+    const double t2 = -pw * s.u[b];
+    double acc = (b == D) ? md * x[0] : 0.0;
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+      double A = 0.0;
+      bool has = true;
+      if (a == b) A = (a == D) ? uh - (gamma - 2.0) * s.u[a] * md : uh;
+      else if (b == D) A = s.u[a] * md;
+      else if (a == D) A = -(g1 * s.u[b] * md);
+      else has = false;
+      if (viscous) A = has ? A - t2 * cst[a] : -(t2 * cst[a]);
+      if (has || viscous) acc += A * x[a + 1];
+    }
+    double Al = (b == D) ? (s.T + phi2 / g1) * md - g1 * uh * s.u[b] : -(g1 * uh * s.u[b]);
+    if (viscous) Al -= t2 * temp1 + s.v * cst[b];
+    acc += Al * x[NU - 1];
+    y[b + 1] += acc;
+  }
+  {  // column NU-1
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+      if (a == D) {
+        double A = g1 * md;
+        if (viscous) A -= pw * cst[a];
+        acc += A * x[a + 1];
+      } else if (viscous) {
+        acc += -(pw * cst[a]) * x[a + 1];
+      }
+    }
+    double Al = gamma * uh;
+    if (viscous) Al -= pw * temp1;
+    acc += Al * x[NU - 1];
+    y[NU - 1] += acc;
+  }
+}
+
+// Second-partial viscous Jacobian transpose for m1 = M1 e_II, m2 = M2 e_JJ.
+template <int ND, int II, int JJ>
+__device__ __forceinline__ void add_second_partial_transpose_rect(const double* u, double mu, double lam, double kap,
+                                                                  double jac, double M1, double M2, const double* x,
+                                                                  double* y) {
+  constexpr bool SAME = II == JJ;
+  const double temp1 = SAME ? M1 * M2 : 0.0;
+  const double temp2 = mu * (M2 * u[JJ]), temp3 = lam * (M1 * u[II]);
+#pragma unroll
+  for (int b = 0; b < ND; ++b) {
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+      if (a == b) {
+        if (SAME) {
+          const double Bab = (a == II) ? mu * temp1 + (mu + lam) * M1 * M2 : mu * temp1;
+          acc += jac * Bab * x[a];
+        }
+      } else if (b == II && a == JJ) {
+        acc += jac * (mu * M1 * M2) * x[a];
+      } else if (a == II && b == JJ) {
+        acc += jac * (lam * M1 * M2) * x[a];
+      }
+    }
+    double Blast = 0.0;
+    bool has = false;
+    if (SAME) { Blast = mu * temp1 * u[b]; has = true; }
+    if (b == II) { Blast = has ? Blast + M1 * temp2 : M1 * temp2; has = true; }
+    if (b == JJ) { Blast = has ? Blast + M2 * temp3 : M2 * temp3; has = true; }
+    if (has) acc += jac * Blast * x[ND];
+    y[b] += acc;
+  }
+  if (SAME) y[ND] += jac * (kap * temp1) * x[ND];
 }
 
 // Incoming part of the inviscid flux Jacobian, A+ = R max/min(Lambda,0) L (reference :1446-2342).

@@ -178,7 +178,7 @@ __device__ __forceinline__ bool owns(int c, int n, int T, bool isLast) {
 // ------------------------------------------------------------------------------- sweep A
 // Shared memory: an in-plane tile of NF fields on a (TY+2R) x (TX+2R) box (corners unused) for the
 // output plane, plus the k-queue of (u, T) for the 2R+1 planes in flight.  Q's k-queue is in registers.
-template <int ND, int R, int DLO, int DN, int TLO, int TN>
+template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV>
 __global__ void __launch_bounds__(NT, 2) k_sweepA(FusedArgs a) {
   const bool COMPOSITE = a.composite != 0;
   constexpr int NU = ND + 2;
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweepA(FusedArgs a) {
       if (a.viscous) {
         const double jac = a.jac[off];
         double g[ND * ND], gT[ND];
-        if (a.curvilinear) {
+        if constexpr (CURV) {
           double M[ND * ND];
 #pragma unroll
           for (int c = 0; c < ND * ND; ++c) M[c] = a.m[(size_t)c * a.cs + off];
@@ -509,7 +509,7 @@ __device__ __forceinline__ constexpr bool needs_tq(int e) {
 }
 
 // DIRS: bit d set -> the flux along direction d will be needed.
-template <int ND, int DIRS>
+template <int ND, int DIRS, bool CURV>
 __device__ __forceinline__ void load_raw(const FusedArgs& a, long off, RawPoint<ND>& r) {
   constexpr int NU = ND + 2;
   constexpr int NTQ = ND * (ND + 1) / 2 + ND;
@@ -520,13 +520,13 @@ __device__ __forceinline__ void load_raw(const FusedArgs& a, long off, RawPoint<
     const double* __restrict__ tq = a.tauqIn + off;
 #pragma unroll
     for (int e = 0; e < NTQ; ++e)
-      if (a.curvilinear || needs_tq<ND, DIRS>(e)) r.tq[e] = __ldg(tq + (size_t)e * a.cs);
+      if (CURV || needs_tq<ND, DIRS>(e)) r.tq[e] = __ldg(tq + (size_t)e * a.cs);
   }
   const double* __restrict__ mp = a.m + off;
 #pragma unroll
   for (int d = 0; d < ND; ++d) {
     if (!((DIRS >> d) & 1)) continue;
-    if (a.curvilinear) {
+    if constexpr (CURV) {
 #pragma unroll
       for (int l = 0; l < ND; ++l) r.m[l + ND * d] = __ldg(mp + (size_t)(l + ND * d) * a.cs);
     } else {
@@ -537,14 +537,14 @@ __device__ __forceinline__ void load_raw(const FusedArgs& a, long off, RawPoint<
 
 // Contravariant total fluxes from the raw inputs (reference CNSHelperImpl.f90:563-689 Cartesian
 // inviscid - viscous, :772-840 metric transform).
-template <int ND, int DIRS>
+template <int ND, int DIRS, bool CURV>
 __device__ __forceinline__ void fluxes_from_raw(const FusedArgs& a, const RawPoint<ND>& r, double (*Fh)[ND + 2]) {
   constexpr int NU = ND + 2;
   constexpr int NTAU = ND * (ND + 1) / 2;
   const double* Q = r.Q;
   Prim<ND> s;
   dependent<ND>(Q, a.pp.gamma, s);
-  if (!a.curvilinear) {
+  if constexpr (!CURV) {
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       if (!((DIRS >> d) & 1)) continue;
@@ -595,7 +595,7 @@ __device__ __forceinline__ void fluxes_from_raw(const FusedArgs& a, const RawPoi
   }
 }
 
-template <int ND, int R>
+template <int ND, int R, bool CURV>
 __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
   constexpr int NU = ND + 2;
   constexpr int W = TX + 2 * R, H = TY + 2 * R;
@@ -699,11 +699,11 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
       RawPoint<ND> raw;
       double Fh[ND][NU];
       if (planeActive) {
-        load_raw<ND, ALLDIRS>(a, soff + pij, raw);
-        fluxes_from_raw<ND, ALLDIRS>(a, raw, Fh);
+        load_raw<ND, ALLDIRS, CURV>(a, soff + pij, raw);
+        fluxes_from_raw<ND, ALLDIRS, CURV>(a, raw, Fh);
       } else {
-        load_raw<ND, (ND == 3 ? 4 : 0)>(a, soff + pij, raw);
-        fluxes_from_raw<ND, (ND == 3 ? 4 : 0)>(a, raw, Fh);
+        load_raw<ND, (ND == 3 ? 4 : 0), CURV>(a, soff + pij, raw);
+        fluxes_from_raw<ND, (ND == 3 ? 4 : 0), CURV>(a, raw, Fh);
       }
       if constexpr (ND == 3) {
 #pragma unroll
@@ -722,13 +722,13 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
       RawPoint<ND> raw;
       double Fh[ND][NU];
       if (hk == 1) {
-        load_raw<ND, 1>(a, soff + hp, raw);
-        fluxes_from_raw<ND, 1>(a, raw, Fh);
+        load_raw<ND, 1, CURV>(a, soff + hp, raw);
+        fluxes_from_raw<ND, 1, CURV>(a, raw, Fh);
 #pragma unroll
         for (int c = 0; c < NU; ++c) F1[((size_t)c * TY + hrow) * W + hcol] = Fh[0][c];
       } else {
-        load_raw<ND, 2>(a, soff + hp, raw);
-        fluxes_from_raw<ND, 2>(a, raw, Fh);
+        load_raw<ND, 2, CURV>(a, soff + hp, raw);
+        fluxes_from_raw<ND, 2, CURV>(a, raw, Fh);
 #pragma unroll
         for (int c = 0; c < NU; ++c) F2[((size_t)c * H + hrow) * TX + hcol] = Fh[1][c];
       }
@@ -842,7 +842,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
 //   rhs  = sum_d (A_d - B_d)^T dW_d  - sigma * Diss(w)               -> written to `rhs`
 //   diffusion_j = sum_i B2(i,j)^T dW_i(2:)   (viscous)               -> written to `diffOut` (4 x nD comps)
 // Same 2.5-D streaming structure as sweep A with X = w.  a.D = adjoint first derivative operators.
-template <int ND, int R, int DLO, int DN, int TLO, int TN>
+template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV>
 __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
   const bool COMPOSITE = a.composite != 0;
   constexpr int NU = ND + 2;
@@ -854,6 +854,7 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
   constexpr int NQ = 2 * RK + 1;
   extern __shared__ double smem[];
   double* const T0 = smem;                                   // [NF][H][W]
+  double* const WQ = smem + (size_t)NF * H * W;              // [NQ][NU][NT] k-queue of w (thread-private columns)
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   int i0, j0;
   bool lastI, lastJ;
@@ -875,6 +876,7 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
   const bool fastI = !touches(0, i0, TX, a.nx);
   const bool fastJ = !touches(1, j0, TY, a.ny);
   double* const tc = T0 + (ty + R) * W + tx + R;
+  double* const wqc = WQ + threadIdx.x;                      // slot stride NU*NT, component stride NT
 
   int hcol = 0, hrow = 0, hk = 0;
   long hp = -1;
@@ -905,28 +907,26 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
     return kk < 0 ? kk + a.nz : kk;
   };
   int ks = wrapPlane(kc0 - RK);
+  int slot = 0;                    // queue slot of the arriving plane s
 
-  double qq[NQ][NU];               // w at planes p-RK .. p+RK
-#pragma unroll
-  for (int q = 0; q < NQ; ++q)
-#pragma unroll
-    for (int c = 0; c < NU; ++c) qq[q][c] = 0.0;
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
-#pragma unroll
-    for (int q = 0; q < NQ - 1; ++q)
-#pragma unroll
-      for (int c = 0; c < NU; ++c) qq[q][c] = qq[q + 1][c];
     if (inside) {
       const double* __restrict__ Wp = a.Win + ((ND == 3) ? (long)ks * a.plane : 0) + pij;
+      double wv[NU];
 #pragma unroll
-      for (int c = 0; c < NU; ++c) qq[NQ - 1][c] = __ldg(Wp + (size_t)c * a.cs);
+      for (int c = 0; c < NU; ++c) wv[c] = __ldg(Wp + (size_t)c * a.cs);
+#pragma unroll
+      for (int c = 0; c < NU; ++c) wqc[((size_t)slot * NU + c) * NT] = wv[c];
     }
     const int p = s - RK;
+    int sp0 = slot - RK;             // slot of plane p
+    if (sp0 < 0) sp0 += NQ;
     int kp = ks - RK;
     if (ND == 3 && a.wrapK && kp < 0) kp += a.nz;
     if (ND == 3) {
       ++ks;
       if (a.wrapK && ks >= a.nz) ks -= a.nz;
+      if (++slot >= NQ) slot = 0;
     }
     if (p < kc0) continue;
     const long poff = (ND == 3) ? (long)kp * a.plane : 0;
@@ -944,12 +944,12 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
 #pragma unroll
       for (int c = 0; c < ND * ND; ++c) {
         const bool diag = (c % ND) == (c / ND);
-        M[c] = (a.curvilinear || diag) ? __ldg(a.m + (size_t)c * a.cs + off) : 0.0;
+        if (CURV || diag) M[c] = __ldg(a.m + (size_t)c * a.cs + off);
       }
     }
     if (inside) {
 #pragma unroll
-      for (int c = 0; c < NU; ++c) tc[c * H * W] = qq[RK][c];
+      for (int c = 0; c < NU; ++c) tc[c * H * W] = wqc[((size_t)sp0 * NU + c) * NT];
       if (!COMPOSITE && dissOn) {
         tc[(FA + 0) * H * W] = a.arc[(size_t)0 * a.cs + off];
         tc[(FA + 1) * H * W] = a.arc[(size_t)1 * a.cs + off];
@@ -986,11 +986,16 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
       }
       if constexpr (ND == 3) {
 #pragma unroll
-        for (int f = 0; f < NU; ++f) {
-          double r = 0.0;
+        for (int f = 0; f < NU; ++f) dW[ND - 1][f] = 0.0;
 #pragma unroll
-          for (int q = 1; q <= RK; ++q) r += a.D[2].c[RK + q] * (qq[RK + q][f] - qq[RK - q][f]);
-          dW[ND - 1][f] = r;
+        for (int q = 1; q <= RK; ++q) {
+          int sp = sp0 + q, sm = sp0 - q;
+          if (sp >= NQ) sp -= NQ;
+          if (sm < 0) sm += NQ;
+          const double cq = a.D[2].c[RK + q];
+#pragma unroll
+          for (int f = 0; f < NU; ++f)
+            dW[ND - 1][f] += cq * (wqc[((size_t)sp * NU + f) * NT] - wqc[((size_t)sm * NU + f) * NT]);
         }
       }
       // ---- pointwise Jacobian-transpose products
@@ -1008,22 +1013,44 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
       double r[NU];
 #pragma unroll
       for (int c = 0; c < NU; ++c) r[c] = 0.0;
+      if constexpr (CURV) {
 #pragma unroll
-      for (int d = 0; d < ND; ++d)
-        add_flux_jacobian_transpose<ND>(Q, sp, &M[ND * d], a.pp.gamma, a.viscous, a.pp.powerLaw, tau, qh, dW[d], r);
+        for (int d = 0; d < ND; ++d)
+          add_flux_jacobian_transpose<ND>(Q, sp, &M[ND * d], a.pp.gamma, a.viscous, a.pp.powerLaw, tau, qh, dW[d], r);
+      } else {
+        static_for<ND>([&](auto d) {
+          add_flux_jacobian_transpose_rect<ND, d.value>(sp, M[d.value + ND * d.value], a.pp.gamma, a.viscous,
+                                                        a.pp.powerLaw, tau, qh, dW[d.value], r);
+        });
+      }
       if (a.viscous) {
         double mu, lam, kap;
         transport(sp.T, a.pp, mu, lam, kap);
+        if constexpr (CURV) {
 #pragma unroll
-        for (int jj = 0; jj < ND; ++jj) {
-          double dd[ND + 1];
+          for (int jj = 0; jj < ND; ++jj) {
+            double dd[ND + 1];
 #pragma unroll
-          for (int c = 0; c < ND + 1; ++c) dd[c] = 0.0;
+            for (int c = 0; c < ND + 1; ++c) dd[c] = 0.0;
 #pragma unroll
-          for (int ii = 0; ii < ND; ++ii)
-            add_second_partial_transpose<ND>(sp.u, mu, lam, kap, jac, &M[ND * ii], &M[ND * jj], &dW[ii][1], dd);
+            for (int ii = 0; ii < ND; ++ii)
+              add_second_partial_transpose<ND>(sp.u, mu, lam, kap, jac, &M[ND * ii], &M[ND * jj], &dW[ii][1], dd);
 #pragma unroll
-          for (int c = 0; c < ND + 1; ++c) a.diffOut[(size_t)(c + (NU - 1) * jj) * a.cs + off] = dd[c];
+            for (int c = 0; c < ND + 1; ++c) a.diffOut[(size_t)(c + (NU - 1) * jj) * a.cs + off] = dd[c];
+          }
+        } else {
+          static_for<ND>([&](auto jj) {
+            double dd[ND + 1];
+#pragma unroll
+            for (int c = 0; c < ND + 1; ++c) dd[c] = 0.0;
+            static_for<ND>([&](auto ii) {
+              add_second_partial_transpose_rect<ND, ii.value, jj.value>(sp.u, mu, lam, kap, jac,
+                                                                        M[ii.value + ND * ii.value],
+                                                                        M[jj.value + ND * jj.value], &dW[ii.value][1], dd);
+            });
+#pragma unroll
+            for (int c = 0; c < ND + 1; ++c) a.diffOut[(size_t)(c + (NU - 1) * jj.value) * a.cs + off] = dd[c];
+          });
         }
       }
       // ---- adjoint dissipation: - sigma * sum_dir Diss_dir(w)
@@ -1084,11 +1111,11 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
             }
           }
 #pragma unroll
-          for (int c = 0; c < NU; ++c) {
-            double rr = 0.0;
+          for (int m = 0; m < 2 * RK + 1; ++m) {
+            int sm = sp0 + m - RK;
+            if (sm < 0) sm += NQ; else if (sm >= NQ) sm -= NQ;
 #pragma unroll
-            for (int m = 0; m < 2 * RK + 1; ++m) rr += e[m] * qq[m][c];
-            dz[c] += rr;
+            for (int c = 0; c < NU; ++c) dz[c] += e[m] * wqc[((size_t)sm * NU + c) * NT];
           }
         }
 #pragma unroll
@@ -1404,12 +1431,12 @@ int upload_ops(mg_state* s, int which, FusedArgs* a) {
   return 0;
 }
 
-template <int ND, int R, int DLO, int DN, int TLO, int TN>
+template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV>
 int launchA(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NF = (ND + 2) + ND + 1 + 2;
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
   const size_t smem = sizeof(double) * ((size_t)NF * (TY + 2 * R) * (TX + 2 * R) + (size_t)NQ * (ND + 1) * NT);
-  auto kern = k_sweepA<ND, R, DLO, DN, TLO, TN>;
+  auto kern = k_sweepA<ND, R, DLO, DN, TLO, TN, CURV>;
   static bool configured = false;
   if (!configured) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1423,13 +1450,13 @@ int launchA(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   return 0;
 }
 
-template <int ND, int R>
+template <int ND, int R, bool CURV>
 int launchB(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NU = ND + 2;
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
   const size_t smem = sizeof(double) * ((size_t)NU * TY * (TX + 2 * R) + (size_t)NU * (TY + 2 * R) * TX +
                                         (size_t)NQ * NU * NT);
-  auto kern = k_sweepB<ND, R>;
+  auto kern = k_sweepB<ND, R, CURV>;
   static bool configured = false;
   if (!configured) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1521,7 +1548,8 @@ int mg_fused_sweepA(mg_state* s) {
   int rc = -1;
 #define MG_A(ND_, R_, DLO, DN, TLO, TN)                                                 \
   if (s->nD == ND_ && si.R == R_)                                                       \
-    rc = launchA<ND_, R_, DLO, DN, TLO, TN>(a, grid, st);
+    rc = a.curvilinear ? launchA<ND_, R_, DLO, DN, TLO, TN, true>(a, grid, st)                  \
+                       : launchA<ND_, R_, DLO, DN, TLO, TN, false>(a, grid, st);
   MG_A(2, 2, -1, 3, -1, 3)
   MG_A(2, 3, -2, 4, -1, 4)
   MG_A(2, 4, -2, 5, -2, 5)
@@ -1565,12 +1593,12 @@ int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
   const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
   cudaStream_t st = mg_stream();
   int rc = -1;
-  if (s->nD == 2 && si.R == 2) rc = launchB<2, 2>(a, grid, st);
-  if (s->nD == 2 && si.R == 3) rc = launchB<2, 3>(a, grid, st);
-  if (s->nD == 2 && si.R == 4) rc = launchB<2, 4>(a, grid, st);
-  if (s->nD == 3 && si.R == 2) rc = launchB<3, 2>(a, grid, st);
-  if (s->nD == 3 && si.R == 3) rc = launchB<3, 3>(a, grid, st);
-  if (s->nD == 3 && si.R == 4) rc = launchB<3, 4>(a, grid, st);
+  if (s->nD == 2 && si.R == 2) rc = a.curvilinear ? launchB<2, 2, true>(a, grid, st) : launchB<2, 2, false>(a, grid, st);
+  if (s->nD == 2 && si.R == 3) rc = a.curvilinear ? launchB<2, 3, true>(a, grid, st) : launchB<2, 3, false>(a, grid, st);
+  if (s->nD == 2 && si.R == 4) rc = a.curvilinear ? launchB<2, 4, true>(a, grid, st) : launchB<2, 4, false>(a, grid, st);
+  if (s->nD == 3 && si.R == 2) rc = a.curvilinear ? launchB<3, 2, true>(a, grid, st) : launchB<3, 2, false>(a, grid, st);
+  if (s->nD == 3 && si.R == 3) rc = a.curvilinear ? launchB<3, 3, true>(a, grid, st) : launchB<3, 3, false>(a, grid, st);
+  if (s->nD == 3 && si.R == 4) rc = a.curvilinear ? launchB<3, 4, true>(a, grid, st) : launchB<3, 4, false>(a, grid, st);
   if (rc != 0) return rc;
   if (fuseRk) {
     if (stage == 1) {
@@ -1590,11 +1618,12 @@ int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
 // ------------------------------------------------------------------------------ adjoint host side
 namespace {
 
-template <int ND, int R, int DLO, int DN, int TLO, int TN>
+template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV>
 int launchAdj1(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NF = (ND + 2) + 2;
-  const size_t smem = sizeof(double) * (size_t)NF * (TY + 2 * R) * (TX + 2 * R);
-  auto kern = k_adjoint1<ND, R, DLO, DN, TLO, TN>;
+  constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
+  const size_t smem = sizeof(double) * ((size_t)NF * (TY + 2 * R) * (TX + 2 * R) + (size_t)NQ * (ND + 2) * NT);
+  auto kern = k_adjoint1<ND, R, DLO, DN, TLO, TN, CURV>;
   static bool configured = false;
   if (!configured) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1658,7 +1687,8 @@ int mg_fused_adjoint1(mg_state* s) {
   int rc = -1;
 #define MG_J(ND_, R_, DLO, DN, TLO, TN)                                                 \
   if (s->nD == ND_ && si.R == R_)                                                       \
-    rc = launchAdj1<ND_, R_, DLO, DN, TLO, TN>(a, grid, st);
+    rc = a.curvilinear ? launchAdj1<ND_, R_, DLO, DN, TLO, TN, true>(a, grid, st)               \
+                       : launchAdj1<ND_, R_, DLO, DN, TLO, TN, false>(a, grid, st);
   MG_J(2, 2, -1, 3, -1, 3)
   MG_J(2, 3, -2, 4, -1, 4)
   MG_J(2, 4, -2, 5, -2, 5)
