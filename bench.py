@@ -31,6 +31,7 @@ UNIT = "point-stages/s"
 BYTES_FORWARD = 448.0           # two sweeps: (5+4+9) + (5+9+4+20) doubles
 BYTES_ADJOINT = 912.0           # three sweeps + checkpoint store/load
 BYTES_SWEEP_A = (5 + 4 + 9) * 8.0
+BYTES_DISS = (5 + 3 + 5) * 8.0                  # read Q 5 + arc lengths 3, write the dissipation term 5
 BYTES_SWEEP_B = (5 + 9 + 4 + 20) * 8.0
 BYTES_ADJ1 = (5 + 5 + 9 + 4 + 5 + 12) * 8.0     # read Q, w, tau/q, G; write partial R 5 + adjoint diffusion 12
 BYTES_ADJ2 = (12 + 5 + 5 + 4 + 20) * 8.0        # read diffusion 12, partial R 5, Q 5, G + RK 20
@@ -287,7 +288,7 @@ def run_native(args):
     launches = lib.mg_kernel_launch_count() - launches0
     import ctypes as C
     prof = {}
-    for name in ("sweepA", "sweepB", "adjoint1", "adjoint2"):
+    for name in ("sweepA", "dissipation", "sweepB", "adjoint1", "adjoint2"):
         ms, n = C.c_double(0), C.c_longlong(0)
         _lib.check(lib.mg_profile_get(name.encode(), C.byref(ms), C.byref(n)))
         if n.value:
@@ -339,7 +340,7 @@ def run_native(args):
     roofline = None
     if prof:
         dom = max(prof, key=lambda k: prof[k]["ms"])
-        bytes_per_launch = {"sweepA": BYTES_SWEEP_A, "sweepB": BYTES_SWEEP_B, "adjoint1": BYTES_ADJ1,
+        bytes_per_launch = {"sweepA": BYTES_SWEEP_A, "dissipation": BYTES_DISS, "sweepB": BYTES_SWEEP_B, "adjoint1": BYTES_ADJ1,
                             "adjoint2": BYTES_ADJ2}.get(dom, BYTES_SWEEP_B) * N
         achieved = bytes_per_launch / (prof[dom]["avg_ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -368,7 +369,7 @@ def run_native(args):
         "config": {"workload": f"C3 3-D periodic viscous box {shape[0]}x{shape[1]}x{shape[2]} "
                                f"({N} points/GPU), KolmogorovFlow flags, SBP 3-6, non-composite dissipation",
                    "evals_per_point_per_step": evals_per_point,
-                   "forward_path": "fused sweeps A+B" if fused_fwd else "general",
+                   "forward_path": "fused sweeps A + dissipation + B" if fused_fwd else "general",
                    "adjoint_path": ("fused adjoint sweeps 1+2 (+ sweep A on the restored state)" if fused_adj else "general operator-by-operator") if do_adjoint else "not run (multi-rank adjoint needs the fused adjoint)",
                    "parallelism": f"slab decomposition along k over {world} GPU(s)",
                    "l2_policy": "inputs larger than L2 (every field >= 134 MB per component set)"},

@@ -374,7 +374,9 @@ static MgField* state_field(mg_state* s, int field) {
     case MG_Q_STRESS_TENSOR: return &s->stressTensor;
     case MG_Q_HEAT_FLUX: return &s->heatFlux;
     case MG_Q_FUSED_TAUQ: return &s->tauq;
-    case MG_Q_FUSED_DISSIPATION: return &s->dissTerm;
+    case MG_Q_FUSED_DISSIPATION:
+      if (s->fusedValid && !s->dissValid) mg_fused_dissipation(s);
+      return &s->dissTerm;
     case MG_Q_FUSED_ADJOINT_DIFFUSION3: {
       static thread_local MgField view;
       view = s->grid->scratchA;

@@ -36,6 +36,7 @@ struct mg_state {
   void* fusedOps[2] = {nullptr, nullptr};   // device operator tables of the fused closure path (fwd, adjoint)
   std::vector<MgField> checkpoints;   // device-resident forward substep states (adjoint replay)
   bool fusedValid = false;
+  bool dissValid = false;      // dissTerm holds the dissipation of the current Q
   int useFused = 1;
   double time = 0.0, timeProgressive = 0.0, adjointForcingFactor = 1.0;
   struct Source { double loc[3], amplitude, angularFrequency, gaussianFactor, phase; };
@@ -66,6 +67,7 @@ int mg_patches_collect_viscous(mg_state* s);
 int mg_patches_farfield_adjoint_sources(mg_state* s, MgField* temp1);
 bool mg_patches_have_farfield(const mg_state* s);
 int mg_fused_sweepA(mg_state* s);
+int mg_fused_dissipation(mg_state* s);
 int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt);
 int mg_fused_adjoint1(mg_state* s);
 int mg_fused_adjoint2(mg_state* s, int fuseRk, int stage, double dt);

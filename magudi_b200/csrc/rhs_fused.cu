@@ -176,22 +176,21 @@ __device__ __forceinline__ bool owns(int c, int n, int T, bool isLast) {
 }
 
 // ------------------------------------------------------------------------------- sweep A
-// Shared memory: an in-plane tile of NF fields on a (TY+2R) x (TX+2R) box (corners unused) for the
-// output plane, plus the k-queue of (u, T) for the 2R+1 planes in flight.  Q's k-queue is in registers.
-template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV>
-__global__ void __launch_bounds__(NT, 2) k_sweepA(FusedArgs a) {
-  const bool COMPOSITE = a.composite != 0;
+// t_State%update: (u, T) -> gradient -> stress tensor + heat flux.  Shared memory: an in-plane tile of
+// (u, T) on a (TY+2R) x (TX+2R) box (corners unused) for the output plane, plus the k-queue of (u, T) for
+// the 2R+1 planes in flight (thread-private columns).  Nothing of the queue lives in registers, so three
+// CTAs fit per SM.
+template <int ND, int R, bool CURV>
+__global__ void __launch_bounds__(NT, 3) k_sweepA(FusedArgs a) {
   constexpr int NU = ND + 2;
   constexpr int NTAU = ND * (ND + 1) / 2;
   constexpr int W = TX + 2 * R, H = TY + 2 * R;
   constexpr int NP = ND + 1;                   // u_0..u_{ND-1}, T
-  constexpr int NF = NP + NU + 2;              // (u,T), Q, arc_i, arc_j
-  constexpr int FQ = NP, FA = NP + NU;         // first field index of Q / arc in the tile
   constexpr int RK = (ND == 3) ? R : 0;        // k half-width
   constexpr int NQ = 2 * RK + 1;
   extern __shared__ double smem[];
-  double* const T0 = smem;                                   // [NF][H][W]
-  double* const KQ = smem + (size_t)NF * H * W;              // [NQ][NP][NT]
+  double* const T0 = smem;                                   // [NP][H][W]
+  double* const KQ = smem + (size_t)NP * H * W;              // [NQ][NP][NT]
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   int i0, j0;
   bool lastI, lastJ;
@@ -202,22 +201,13 @@ __global__ void __launch_bounds__(NT, 2) k_sweepA(FusedArgs a) {
   const bool inside = i < a.nx && j < a.ny;
   const long pij = (long)i + (long)a.nx * j;
   const double gamma = a.pp.gamma;
-  // widest closure block among the operators used along a direction
-  auto touches = [&](int d, int c0, int T, int n) {
-    int depth = a.D[d].depth;
-    if (a.diss) {
-      depth = max(depth, a.Dd[d].depth);
-      if (!COMPOSITE) depth = max(depth, max(a.Dt[d].depth + a.Dd[d].width, a.dir[d].normDepth));
-    }
-    return (a.dir[d].hasB0 && c0 < depth) || (a.dir[d].hasB1 && c0 + T > n - depth);
-  };
-  const bool fastI = !touches(0, i0, TX, a.nx);
-  const bool fastJ = !touches(1, j0, TY, a.ny);
+  const bool fastI = !((a.D[0].hasB0 && i0 < a.D[0].depth) || (a.D[0].hasB1 && i0 + TX > a.nx - a.D[0].depth));
+  const bool fastJ = !((a.D[1].hasB0 && j0 < a.D[1].depth) || (a.D[1].hasB1 && j0 + TY > a.ny - a.D[1].depth));
   double* const tc = T0 + (ty + R) * W + tx + R;             // own point; field stride H*W, row stride W
   double* const kqc = KQ + threadIdx.x;                      // slot stride NP*NT, field stride NT
 
   // halo point handled by this thread (at most one): hk 0 none, 1 i-halo, 2 j-halo
-  int hcol = 0, hrow = 0, hk = 0;
+  int hoff = 0, hk = 0;
   long hp = -1;
   {
     const int h = threadIdx.x;
@@ -226,7 +216,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweepA(FusedArgs a) {
       const int lc = ii < R ? ii : TX + ii;               // local column in the box
       const int gi = wrap_index(i0 - R + lc, a.dir[0]);
       const int gj = j0 + row;
-      hcol = lc; hrow = row + R;
+      hoff = (row + R) * W + lc;
       if (gi >= 0 && gj < a.ny) { hk = 1; hp = (long)gi + (long)a.nx * gj; }
     } else if (h < 2 * R * TY + 2 * R * TX) {
       const int h2 = h - 2 * R * TY;
@@ -234,7 +224,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweepA(FusedArgs a) {
       const int lr = jj < R ? jj : TY + jj;
       const int gj = wrap_index(j0 - R + lr, a.dir[1]);
       const int gi = i0 + col;
-      hcol = col + R; hrow = lr;
+      hoff = lr * W + col + R;
       if (gj >= 0 && gi < a.nx) { hk = 2; hp = (long)gi + (long)a.nx * gj; }
     }
   }
@@ -249,13 +239,6 @@ __global__ void __launch_bounds__(NT, 2) k_sweepA(FusedArgs a) {
   int ks = wrapPlane(kc0 - RK);
   int slot = 0;                    // queue slot of the arriving plane s
 
-  double qq[NQ][NU];               // Q at planes p-RK .. p+RK once the queue is primed
-  // The rotation below reads every entry each iteration: start from defined values (reading
-  // indeterminate registers is undefined behaviour and lets the optimiser break the rotation).
-#pragma unroll
-  for (int q = 0; q < NQ; ++q)
-#pragma unroll
-    for (int c = 0; c < NU; ++c) qq[q][c] = 0.0;
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
     // ---- arrival of plane s
     if (ND == 3 && a.prefetch && inside && (tx & 15) == 0) {
@@ -272,65 +255,68 @@ __global__ void __launch_bounds__(NT, 2) k_sweepA(FusedArgs a) {
         const long qo = (long)kq * a.plane + pij;
         prefetch_l2(a.jac + qo);
 #pragma unroll
-        for (int d = 0; d < ND; ++d) {
-          prefetch_l2(a.m + (size_t)(d + ND * d) * a.cs + qo);
-          if (!COMPOSITE && a.diss) prefetch_l2(a.arc + (size_t)d * a.cs + qo);
-        }
+        for (int d = 0; d < ND; ++d) prefetch_l2(a.m + (size_t)(d + ND * d) * a.cs + qo);
       }
-    }
-#pragma unroll
-    for (int q = 0; q < NQ - 1; ++q)
-#pragma unroll
-      for (int c = 0; c < NU; ++c) qq[q][c] = qq[q + 1][c];
-    if (inside) {
-      const double* __restrict__ Qp = a.Q + ((ND == 3) ? (long)ks * a.plane : 0) + pij;
-#pragma unroll
-      for (int c = 0; c < NU; ++c) qq[NQ - 1][c] = Qp[(size_t)c * a.cs];
-      Prim<ND> sa;
-      dependent<ND>(qq[NQ - 1], gamma, sa);
-#pragma unroll
-      for (int d = 0; d < ND; ++d) kqc[((size_t)slot * NP + d) * NT] = sa.u[d];
-      kqc[((size_t)slot * NP + ND) * NT] = sa.T;
     }
     const int p = s - RK;
     int sp0 = slot - RK;             // slot of plane p
     if (sp0 < 0) sp0 += NQ;
     int kp = ks - RK;                // storage plane of p
     if (ND == 3 && a.wrapK && kp < 0) kp += a.nz;
+    const long poff = (ND == 3) ? (long)kp * a.plane : 0;
+    // issue the loads of the arriving own point and of the halo point of plane p together
+    double Qs[NU], Qh[NU];
+    const bool doHalo = hk && p >= kc0;
+    if (inside) {
+      const double* __restrict__ Qp = a.Q + ((ND == 3) ? (long)ks * a.plane : 0) + pij;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) Qs[c] = __ldg(Qp + (size_t)c * a.cs);
+    }
+    if (doHalo) {
+      const double* __restrict__ Qp = a.Q + poff + hp;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) Qh[c] = __ldg(Qp + (size_t)c * a.cs);
+    }
+    if (inside) {
+      Prim<ND> sa;
+      dependent<ND>(Qs, gamma, sa);
+#pragma unroll
+      for (int d = 0; d < ND; ++d) kqc[((size_t)slot * NP + d) * NT] = sa.u[d];
+      kqc[((size_t)slot * NP + ND) * NT] = sa.T;
+    }
     if (ND == 3) {
       ++ks;
       if (a.wrapK && ks >= a.nz) ks -= a.nz;
       if (++slot >= NQ) slot = 0;
     }
     if (p < kc0) continue;
-    // ---- output plane p: in-plane tile (own point from the queues, halo from global memory)
-    const long poff = (ND == 3) ? (long)kp * a.plane : 0;
-    double uT[NP];
+    // ---- output plane p: in-plane tile (own point from the queue, halo from global memory)
+    double Tp = 0.0;
     if (inside) {
 #pragma unroll
-      for (int f = 0; f < NP; ++f) { uT[f] = kqc[((size_t)sp0 * NP + f) * NT]; tc[f * H * W] = uT[f]; }
-#pragma unroll
-      for (int c = 0; c < NU; ++c) tc[(FQ + c) * H * W] = qq[RK][c];
-      if (!COMPOSITE && a.diss) {
-        tc[(FA + 0) * H * W] = a.arc[(size_t)0 * a.cs + poff + pij];
-        tc[(FA + 1) * H * W] = a.arc[(size_t)1 * a.cs + poff + pij];
+      for (int f = 0; f < NP; ++f) {
+        const double v = kqc[((size_t)sp0 * NP + f) * NT];
+        tc[f * H * W] = v;
+        if (f == ND) Tp = v;
       }
     }
-    if (hk) {
-      double Qh[NU];
-      const long off = poff + hp;
-      double* const th = T0 + hrow * W + hcol;
-#pragma unroll
-      for (int c = 0; c < NU; ++c) { Qh[c] = a.Q[(size_t)c * a.cs + off]; th[(FQ + c) * H * W] = Qh[c]; }
+    if (doHalo) {
+      double* const th = T0 + hoff;
       Prim<ND> sh;
       dependent<ND>(Qh, gamma, sh);
 #pragma unroll
       for (int d = 0; d < ND; ++d) th[d * H * W] = sh.u[d];
       th[ND * H * W] = sh.T;
-      if (!COMPOSITE && a.diss) th[(FA + hk - 1) * H * W] = a.arc[(size_t)(hk - 1) * a.cs + off];
     }
     __syncthreads();
-    if (mine) {
+    if (mine && a.viscous) {
+      const long off = poff + pij;
+      // geometry loads first (latency overlaps the stencil arithmetic)
+      const double jac = __ldg(a.jac + off);
+      double M[ND * ND];
+#pragma unroll
+      for (int c = 0; c < ND * ND; ++c)
+        if (CURV || (c % ND) == (c / ND)) M[c] = __ldg(a.m + (size_t)c * a.cs + off);
       // ---- derivatives of (u, T) along xi, eta, zeta
       double dxi[ND][NP];
 #pragma unroll
@@ -367,113 +353,246 @@ __global__ void __launch_bounds__(NT, 2) k_sweepA(FusedArgs a) {
         }
       }
       // ---- gradient in physical space (reference src/GridImpl.f90:1357-1413), stress tensor, heat flux
-      const long off = poff + pij;
-      if (a.viscous) {
-        const double jac = a.jac[off];
-        double g[ND * ND], gT[ND];
-        if constexpr (CURV) {
-          double M[ND * ND];
+      double g[ND * ND], gT[ND];
+      if constexpr (CURV) {
 #pragma unroll
-          for (int c = 0; c < ND * ND; ++c) M[c] = a.m[(size_t)c * a.cs + off];
-#pragma unroll
-          for (int c = 0; c < NP; ++c)
-#pragma unroll
-            for (int jx = 0; jx < ND; ++jx) {
-              double r = M[jx] * dxi[0][c];
-#pragma unroll
-              for (int d = 1; d < ND; ++d) r += M[jx + ND * d] * dxi[d][c];
-              r = jac * r;
-              if (c < ND) g[jx + ND * c] = r; else gT[jx] = r;
-            }
-        } else {
+        for (int c = 0; c < NP; ++c)
 #pragma unroll
           for (int jx = 0; jx < ND; ++jx) {
-            const double mj = jac * a.m[(size_t)(jx + ND * jx) * a.cs + off];
+            double r = M[jx] * dxi[0][c];
 #pragma unroll
-            for (int c = 0; c < ND; ++c) g[jx + ND * c] = mj * dxi[jx][c];
-            gT[jx] = mj * dxi[jx][ND];
+            for (int d = 1; d < ND; ++d) r += M[jx + ND * d] * dxi[d][c];
+            r = jac * r;
+            if (c < ND) g[jx + ND * c] = r; else gT[jx] = r;
           }
+      } else {
+#pragma unroll
+        for (int jx = 0; jx < ND; ++jx) {
+          const double mj = jac * M[jx + ND * jx];
+#pragma unroll
+          for (int c = 0; c < ND; ++c) g[jx + ND * c] = mj * dxi[jx][c];
+          gT[jx] = mj * dxi[jx][ND];
         }
-        double mu, lam, kap, tau[ND * ND];
-        transport(uT[ND], a.pp, mu, lam, kap);
-        stress_from_gradient<ND>(g, mu, lam, tau);
-        int t = 0;
-#pragma unroll
-        for (int r0 = 0; r0 < ND; ++r0)
-#pragma unroll
-          for (int c0 = r0; c0 < ND; ++c0) a.tauq[(size_t)(t++) * a.cs + off] = tau[c0 + ND * r0];
-#pragma unroll
-        for (int d = 0; d < ND; ++d) a.tauq[(size_t)(NTAU + d) * a.cs + off] = -kap * gT[d];
       }
-      // ---- dissipation term  sum_dir Diss_dir(Q)   (reference src/RhsHelperImpl.f90:58-81)
-      if (a.diss) {
-        double dz[NU];
+      double mu, lam, kap, tau[ND * ND];
+      transport(Tp, a.pp, mu, lam, kap);
+      stress_from_gradient<ND>(g, mu, lam, tau);
+      int t = 0;
 #pragma unroll
-        for (int c = 0; c < NU; ++c) dz[c] = 0.0;
-        // in-plane directions
+      for (int r0 = 0; r0 < ND; ++r0)
 #pragma unroll
-        for (int d = 0; d < 2; ++d) {
-          const bool fast = d == 0 ? fastI : fastJ;
-          const int st = d == 0 ? 1 : W;                 // tile stride along the direction
-          if (fast) {
-            double e[2 * R + 1];
-            if (COMPOSITE) {
+        for (int c0 = r0; c0 < ND; ++c0) a.tauq[(size_t)(t++) * a.cs + off] = tau[c0 + ND * r0];
 #pragma unroll
-              for (int m = 0; m < 2 * R + 1; ++m) e[m] = a.Dd[d].c[m];
-            } else {
+      for (int d = 0; d < ND; ++d) a.tauq[(size_t)(NTAU + d) * a.cs + off] = -kap * gT[d];
+    }
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------------------- dissipation sweep
+// State-only part of addDissipation (reference src/RhsHelperImpl.f90:58-81): out = sum_dir Diss_dir(X),
+// X = a.Q (NU components).  In-plane neighbours from a shared-memory tile of X and the arc lengths, the k
+// neighbours from a register queue of X.  Kept apart from sweep A so that neither kernel has to hold both
+// the (u, T) and the X queue on chip (the fused version spilled to local memory).
+template <int ND, int R, int DLO, int DN, int TLO, int TN>
+__global__ void __launch_bounds__(NT, 2) k_diss(FusedArgs a) {
+  const bool COMPOSITE = a.composite != 0;
+  constexpr int NU = ND + 2;
+  constexpr int W = TX + 2 * R, H = TY + 2 * R;
+  constexpr int NF = NU + 2;                   // X, arc_i, arc_j
+  constexpr int FA = NU;
+  constexpr int RK = (ND == 3) ? R : 0;
+  constexpr int NQ = 2 * RK + 1;
+  extern __shared__ double smem[];
+  double* const T0 = smem;                                   // [NF][H][W]
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  int i0, j0;
+  bool lastI, lastJ;
+  tile_origin(blockIdx.x, a.nx, TX, i0, lastI);
+  tile_origin(blockIdx.y, a.ny, TY, j0, lastJ);
+  const int i = i0 + tx, j = j0 + ty;
+  const bool mine = owns(i, a.nx, TX, lastI) && owns(j, a.ny, TY, lastJ);
+  const bool inside = i < a.nx && j < a.ny;
+  const long pij = (long)i + (long)a.nx * j;
+  auto touches = [&](int d, int c0, int T, int n) {
+    int depth = a.Dd[d].depth;
+    if (!COMPOSITE) depth = max(depth, max(a.Dt[d].depth + a.Dd[d].width, a.dir[d].normDepth));
+    return (a.dir[d].hasB0 && c0 < depth) || (a.dir[d].hasB1 && c0 + T > n - depth);
+  };
+  const bool fastI = !touches(0, i0, TX, a.nx);
+  const bool fastJ = !touches(1, j0, TY, a.ny);
+  double* const tc = T0 + (ty + R) * W + tx + R;
+
+  int hoff = 0, hk = 0;
+  long hp = -1;
+  {
+    const int h = threadIdx.x;
+    if (h < 2 * R * TY) {
+      const int ii = h % (2 * R), row = h / (2 * R);
+      const int lc = ii < R ? ii : TX + ii;
+      const int gi = wrap_index(i0 - R + lc, a.dir[0]);
+      const int gj = j0 + row;
+      hoff = (row + R) * W + lc;
+      if (gi >= 0 && gj < a.ny) { hk = 1; hp = (long)gi + (long)a.nx * gj; }
+    } else if (h < 2 * R * TY + 2 * R * TX) {
+      const int h2 = h - 2 * R * TY;
+      const int col = h2 % TX, jj = h2 / TX;
+      const int lr = jj < R ? jj : TY + jj;
+      const int gj = wrap_index(j0 - R + lr, a.dir[1]);
+      const int gi = i0 + col;
+      hoff = lr * W + col + R;
+      if (gj >= 0 && gi < a.nx) { hk = 2; hp = (long)gi + (long)a.nx * gj; }
+    }
+  }
+  const int kc0 = a.kBeg + blockIdx.z * a.kChunk;
+  const int kc1 = min(kc0 + a.kChunk, a.kEnd);
+  auto wrapPlane = [&](int k) -> int {
+    if (ND < 3 || !a.wrapK) return k;
+    int kk = k % a.nz;
+    return kk < 0 ? kk + a.nz : kk;
+  };
+  int ks = wrapPlane(kc0 - RK);
+
+  double qq[NQ][NU];               // X at planes p-RK .. p+RK once the queue is primed
 #pragma unroll
-              for (int m = 0; m < 2 * R + 1; ++m) e[m] = 0.0;
+  for (int q = 0; q < NQ; ++q)
 #pragma unroll
-              for (int ea = 0; ea < TN; ++ea) {
-                const double w = -a.Dt[d].c[ea] * tc[(FA + d) * H * W + (TLO + ea) * st];
+    for (int c = 0; c < NU; ++c) qq[q][c] = 0.0;
+  for (int s = kc0 - RK; s < kc1 + RK; ++s) {
+    if (ND == 3 && a.prefetch && inside && (tx & 15) == 0) {
+      int kf = ks + a.prefetch;
+      if (a.wrapK && kf >= a.nz) kf -= a.nz;
+      if (a.wrapK || s + a.prefetch < a.nz + RK) {
+        const long fo = (long)kf * a.plane + pij;
 #pragma unroll
-                for (int eb = 0; eb < DN; ++eb) e[TLO + ea + DLO + eb + R] += w * a.Dd[d].c[eb];
-              }
-            }
+        for (int c = 0; c < NU; ++c) prefetch_l2(a.Q + (size_t)c * a.cs + fo);
+      }
+      if (!COMPOSITE) {
+        int kq = ks - RK + a.prefetch;
+        if (a.wrapK) { if (kq < 0) kq += a.nz; else if (kq >= a.nz) kq -= a.nz; }
+        if (a.wrapK || (kq >= 0 && kq < a.nz)) {
+          const long qo = (long)kq * a.plane + pij;
 #pragma unroll
-            for (int c = 0; c < NU; ++c) {
-              double r = 0.0;
-#pragma unroll
-              for (int m = 0; m < 2 * R + 1; ++m) r += e[m] * tc[(FQ + c) * H * W + (m - R) * st];
-              dz[c] += r;
-            }
-          } else {
-            const int cd = d == 0 ? i : j, nd = d == 0 ? a.nx : a.ny;
-#pragma unroll
-            for (int c = 0; c < NU; ++c) {
-              dz[c] += COMPOSITE ? tile_line_apply<W, H>(&a.ops->Dd[d], cd, nd, T0, FQ + c, ty + R, tx + R, d, (d == 0 ? i0 : j0) - R)
-                                 : tile_line_dissipation<W, H>(a.ops, d, cd, T0, FQ + c, FA + d, ty + R, tx + R, (d == 0 ? i0 : j0) - R);
-            }
-          }
+          for (int d = 0; d < ND; ++d) prefetch_l2(a.arc + (size_t)d * a.cs + qo);
         }
-        if constexpr (ND == 3) {
-          double e[2 * RK + 1];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ - 1; ++q)
+#pragma unroll
+      for (int c = 0; c < NU; ++c) qq[q][c] = qq[q + 1][c];
+    const int p = s - RK;
+    int kp = ks - RK;                // storage plane of p
+    if (ND == 3 && a.wrapK && kp < 0) kp += a.nz;
+    const long poff = (ND == 3) ? (long)kp * a.plane : 0;
+    const bool out = p >= kc0;
+    if (inside) {
+      const double* __restrict__ Xp = a.Q + ((ND == 3) ? (long)ks * a.plane : 0) + pij;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) qq[NQ - 1][c] = __ldg(Xp + (size_t)c * a.cs);
+    }
+    if (ND == 3) {
+      ++ks;
+      if (a.wrapK && ks >= a.nz) ks -= a.nz;
+    }
+    if (!out) continue;
+    // ---- output plane p: in-plane tile (halo and arc lengths from global memory)
+    double xh[NU], ah = 0.0, a0 = 0.0, a1 = 0.0, ak[TN];
+    if (hk) {
+      const long off = poff + hp;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) xh[c] = __ldg(a.Q + (size_t)c * a.cs + off);
+      if (!COMPOSITE) ah = __ldg(a.arc + (size_t)(hk - 1) * a.cs + off);
+    }
+    if (inside && !COMPOSITE) {
+      a0 = __ldg(a.arc + (size_t)0 * a.cs + poff + pij);
+      a1 = __ldg(a.arc + (size_t)1 * a.cs + poff + pij);
+      if constexpr (ND == 3) {
+#pragma unroll
+        for (int ea = 0; ea < TN; ++ea) {
+          int kk = kp + TLO + ea;
+          if (a.wrapK) { if (kk < 0) kk += a.nz; else if (kk >= a.nz) kk -= a.nz; }
+          ak[ea] = __ldg(a.arc + (size_t)2 * a.cs + (long)kk * a.plane + pij);
+        }
+      }
+    }
+    if (inside) {
+#pragma unroll
+      for (int c = 0; c < NU; ++c) tc[c * H * W] = qq[RK][c];
+      if (!COMPOSITE) { tc[(FA + 0) * H * W] = a0; tc[(FA + 1) * H * W] = a1; }
+    }
+    if (hk) {
+      double* const th = T0 + hoff;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) th[c * H * W] = xh[c];
+      if (!COMPOSITE) th[(FA + hk - 1) * H * W] = ah;
+    }
+    __syncthreads();
+    if (mine) {
+      double dz[NU];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) dz[c] = 0.0;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const bool fast = d == 0 ? fastI : fastJ;
+        const int st = d == 0 ? 1 : W;                 // tile stride along the direction
+        if (fast) {
+          double e[2 * R + 1];
           if (COMPOSITE) {
 #pragma unroll
-            for (int m = 0; m < 2 * RK + 1; ++m) e[m] = a.Dd[2].c[m];
+            for (int m = 0; m < 2 * R + 1; ++m) e[m] = a.Dd[d].c[m];
           } else {
 #pragma unroll
-            for (int m = 0; m < 2 * RK + 1; ++m) e[m] = 0.0;
+            for (int m = 0; m < 2 * R + 1; ++m) e[m] = 0.0;
 #pragma unroll
             for (int ea = 0; ea < TN; ++ea) {
-              int kk = kp + TLO + ea;
-              if (a.wrapK) { if (kk < 0) kk += a.nz; else if (kk >= a.nz) kk -= a.nz; }
-              const double w = -a.Dt[2].c[ea] * a.arc[(size_t)2 * a.cs + (long)kk * a.plane + pij];
+              const double w = -a.Dt[d].c[ea] * tc[(FA + d) * H * W + (TLO + ea) * st];
 #pragma unroll
-              for (int eb = 0; eb < DN; ++eb) e[TLO + ea + DLO + eb + RK] += w * a.Dd[2].c[eb];
+              for (int eb = 0; eb < DN; ++eb) e[TLO + ea + DLO + eb + R] += w * a.Dd[d].c[eb];
             }
           }
 #pragma unroll
           for (int c = 0; c < NU; ++c) {
             double r = 0.0;
 #pragma unroll
-            for (int m = 0; m < 2 * RK + 1; ++m) r += e[m] * qq[m][c];
+            for (int m = 0; m < 2 * R + 1; ++m) r += e[m] * tc[c * H * W + (m - R) * st];
             dz[c] += r;
+          }
+        } else {
+          const int cd = d == 0 ? i : j, nd = d == 0 ? a.nx : a.ny;
+#pragma unroll
+          for (int c = 0; c < NU; ++c) {
+            dz[c] += COMPOSITE ? tile_line_apply<W, H>(&a.ops->Dd[d], cd, nd, T0, c, ty + R, tx + R, d, (d == 0 ? i0 : j0) - R)
+                               : tile_line_dissipation<W, H>(a.ops, d, cd, T0, c, FA + d, ty + R, tx + R, (d == 0 ? i0 : j0) - R);
+          }
+        }
+      }
+      if constexpr (ND == 3) {
+        double e[2 * RK + 1];
+        if (COMPOSITE) {
+#pragma unroll
+          for (int m = 0; m < 2 * RK + 1; ++m) e[m] = a.Dd[2].c[m];
+        } else {
+#pragma unroll
+          for (int m = 0; m < 2 * RK + 1; ++m) e[m] = 0.0;
+#pragma unroll
+          for (int ea = 0; ea < TN; ++ea) {
+            const double w = -a.Dt[2].c[ea] * ak[ea];
+#pragma unroll
+            for (int eb = 0; eb < DN; ++eb) e[TLO + ea + DLO + eb + RK] += w * a.Dd[2].c[eb];
           }
         }
 #pragma unroll
-        for (int c = 0; c < NU; ++c) a.diss[(size_t)c * a.cs + off] = dz[c];
+        for (int c = 0; c < NU; ++c) {
+          double r = 0.0;
+#pragma unroll
+          for (int m = 0; m < 2 * RK + 1; ++m) r += e[m] * qq[m][c];
+          dz[c] += r;
+        }
       }
+      const long off = poff + pij;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) a.diss[(size_t)c * a.cs + off] = dz[c];
     }
     __syncthreads();
   }
@@ -655,11 +774,60 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
   int kp = wrapPlane(kc0 - 2 * RK);                // storage plane of the output plane p = s - RK
   int slot = 0;                                    // queue slot of plane s
 
-  double rxy[RK + 1][NU];          // in-plane part of div(F) for planes s-RK .. s
+  // The queue holds, for every plane in flight, the running sum of div(F): the in-plane part is added when
+  // the plane arrives, the k-derivative contributions c_q (F3(p+q) - F3(p-q)) as the neighbouring planes
+  // arrive (thread-private columns of shared memory: no register queue).
+  if (inside) {
 #pragma unroll
-  for (int q = 0; q < RK + 1; ++q)
+    for (int q = 0; q < NQ; ++q)
 #pragma unroll
-    for (int c = 0; c < NU; ++c) rxy[q][c] = 0.0;
+      for (int c = 0; c < NU; ++c) f3c[((size_t)q * NU + c) * NT] = 0.0;
+  }
+  // output of plane p (storage plane kpl, queue slot sp): x 1/J, dissipation, RK4 substep
+  auto emit = [&](int kpl, int sp, const double* extra) {
+    const long off = ((ND == 3) ? (long)kpl * a.plane : 0) + pij;
+    const double jac = __ldg(a.jac + off);
+    double dss[NU], vb1[NU], vb2[NU];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) {
+      const size_t qi = (size_t)c * a.cs + off;
+      dss[c] = a.dissIn ? __ldg(a.dissIn + qi) : 0.0;
+      if (a.fuseRk) {
+        vb1[c] = (a.stage == 1) ? a.Q[qi] : ((a.stage == 4) ? 0.0 : a.b1in[qi]);
+        vb2[c] = (a.stage == 1) ? 0.0 : a.b2[qi];
+      }
+    }
+    double r[NU];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) {
+      double rhs = 0.0 - (f3c[((size_t)sp * NU + c) * NT] + extra[c]);
+      if (a.dissIn) rhs += a.dissAmount * dss[c];
+      r[c] = rhs * jac;
+    }
+    if (!a.fuseRk) {
+#pragma unroll
+      for (int c = 0; c < NU; ++c) a.rhs[(size_t)c * a.cs + off] = r[c];
+    } else {
+      // RK4 substep (reference src/RK4IntegratorImpl.f90:106-158) fused into the last RHS kernel;
+      // in stage 1 buffer1 is the input Q buffer itself (vb1 = Q)
+#pragma unroll
+      for (int c = 0; c < NU; ++c) {
+        const size_t qi = (size_t)c * a.cs + off;
+        if (a.stage == 1) {
+          a.b2[qi] = vb1[c] + a.dt * r[c] / 6.0;
+          a.Qout[qi] = vb1[c] + a.dt * r[c] / 2.0;
+        } else if (a.stage == 2) {
+          a.b2[qi] = vb2[c] + a.dt * r[c] / 3.0;
+          a.Qout[qi] = vb1[c] + a.dt * r[c] / 2.0;
+        } else if (a.stage == 3) {
+          a.b2[qi] = vb2[c] + a.dt * r[c] / 3.0;
+          a.Qout[qi] = vb1[c] + a.dt * r[c];
+        } else {
+          a.Qout[qi] = vb2[c] + a.dt * r[c] / 6.0;
+        }
+      }
+    }
+  };
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
     const long soff = (ND == 3) ? (long)ks * a.plane : 0;
     const bool planeActive = s >= kc0 && s < kc1;
@@ -695,26 +863,44 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
       }
     }
     // ---- arrival of plane s: own point (loads issued back to back, then the flux evaluation) ...
+    double f3[NU];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) f3[c] = 0.0;
     if (inside) {
       RawPoint<ND> raw;
       double Fh[ND][NU];
       if (planeActive) {
         load_raw<ND, ALLDIRS, CURV>(a, soff + pij, raw);
         fluxes_from_raw<ND, ALLDIRS, CURV>(a, raw, Fh);
-      } else {
-        load_raw<ND, (ND == 3 ? 4 : 0), CURV>(a, soff + pij, raw);
-        fluxes_from_raw<ND, (ND == 3 ? 4 : 0), CURV>(a, raw, Fh);
-      }
-      if constexpr (ND == 3) {
-#pragma unroll
-        for (int c = 0; c < NU; ++c) f3c[((size_t)slot * NU + c) * NT] = Fh[ND - 1][c];
-      }
-      if (planeActive) {
 #pragma unroll
         for (int c = 0; c < NU; ++c) {
           f1c[c * TY * W] = Fh[0][c];
           f2c[c * H * TX] = Fh[1][c];
         }
+      } else {
+        load_raw<ND, (ND == 3 ? 4 : 0), CURV>(a, soff + pij, raw);
+        fluxes_from_raw<ND, (ND == 3 ? 4 : 0), CURV>(a, raw, Fh);
+      }
+      if constexpr (ND == 3) {
+        // scatter c_q F3(s) to the planes s-q (+) and s+q (-); plane s+RK is touched for the first time
+#pragma unroll
+        for (int c = 0; c < NU; ++c) f3[c] = Fh[ND - 1][c];
+#pragma unroll
+        for (int q = 1; q <= RK; ++q) {
+          int sp = slot + q, sm = slot - q;
+          if (sp >= NQ) sp -= NQ;
+          if (sm < 0) sm += NQ;
+          const double cq = a.D[2].c[RK + q];
+#pragma unroll
+          for (int c = 0; c < NU; ++c) {
+            if (q == RK) f3c[((size_t)sp * NU + c) * NT] = 0.0 - cq * f3[c];
+            else f3c[((size_t)sp * NU + c) * NT] -= cq * f3[c];
+            if (q < RK) f3c[((size_t)sm * NU + c) * NT] += cq * f3[c];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NU; ++c) f3c[c * NT] = 0.0;
       }
     }
     // ... then the halo point of this thread (xi- or eta-halo)
@@ -733,11 +919,19 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
         for (int c = 0; c < NU; ++c) F2[((size_t)c * H + hrow) * TX + hcol] = Fh[1][c];
       }
     }
+    // ---- output plane p = s - RK (3-D): every contribution but the last (c_RK F3(s), still in registers)
+    // is already in the queue
+    if constexpr (ND == 3) {
+      if (s - RK >= kc0 && mine) {
+        int sp0 = slot - RK;
+        if (sp0 < 0) sp0 += NQ;
+        double last[NU];
+#pragma unroll
+        for (int c = 0; c < NU; ++c) last[c] = a.D[2].c[2 * RK] * f3[c];
+        emit(kp, sp0, last);
+      }
+    }
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < RK; ++q)
-#pragma unroll
-      for (int c = 0; c < NU; ++c) rxy[q][c] = rxy[q + 1][c];
     if (planeActive && mine) {
 #pragma unroll
       for (int c = 0; c < NU; ++c) {
@@ -758,73 +952,9 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
         } else {
           r += strided_line_apply<H>(&a.ops->D[1], j, a.ny, F2 + (size_t)c * H * TX + tx, TX, j0 - R);
         }
-        rxy[RK][c] = r;
+        f3c[((size_t)slot * NU + c) * NT] += r;
       }
-    }
-    // ---- output plane p = s - RK
-    const int p = s - RK;
-    if (p >= kc0 && mine) {
-      const long off = ((ND == 3) ? (long)kp * a.plane : 0) + pij;
-      // batch every global load of the output phase before any store (loads cannot be hoisted across
-      // the stores by the compiler: the buffers may alias as far as it knows)
-      const double jac = __ldg(a.jac + off);
-      double dss[NU], vb1[NU], vb2[NU];
-#pragma unroll
-      for (int c = 0; c < NU; ++c) {
-        const size_t qi = (size_t)c * a.cs + off;
-        dss[c] = a.dissIn ? __ldg(a.dissIn + qi) : 0.0;
-        if (a.fuseRk) {
-          vb1[c] = (a.stage == 1) ? a.Q[qi] : ((a.stage == 4) ? 0.0 : a.b1in[qi]);
-          vb2[c] = (a.stage == 1) ? 0.0 : a.b2[qi];
-        }
-      }
-      double r[NU];
-#pragma unroll
-      for (int c = 0; c < NU; ++c) r[c] = rxy[0][c];
-      if constexpr (ND == 3) {
-        // slot of plane p is slot - RK (mod NQ)
-        int sp0 = slot - RK;
-        if (sp0 < 0) sp0 += NQ;
-#pragma unroll
-        for (int q = 1; q <= RK; ++q) {
-          int sp = sp0 + q, sm = sp0 - q;
-          if (sp >= NQ) sp -= NQ;
-          if (sm < 0) sm += NQ;
-          const double cq = a.D[2].c[RK + q];
-#pragma unroll
-          for (int c = 0; c < NU; ++c)
-            r[c] += cq * (f3c[((size_t)sp * NU + c) * NT] - f3c[((size_t)sm * NU + c) * NT]);
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < NU; ++c) {
-        double rhs = 0.0 - r[c];
-        if (a.dissIn) rhs += a.dissAmount * dss[c];
-        r[c] = rhs * jac;
-      }
-      if (!a.fuseRk) {
-#pragma unroll
-        for (int c = 0; c < NU; ++c) a.rhs[(size_t)c * a.cs + off] = r[c];
-      } else {
-        // RK4 substep (reference src/RK4IntegratorImpl.f90:106-158) fused into the last RHS kernel;
-        // in stage 1 buffer1 is the input Q buffer itself (vb1 = Q)
-#pragma unroll
-        for (int c = 0; c < NU; ++c) {
-          const size_t qi = (size_t)c * a.cs + off;
-          if (a.stage == 1) {
-            a.b2[qi] = vb1[c] + a.dt * r[c] / 6.0;
-            a.Qout[qi] = vb1[c] + a.dt * r[c] / 2.0;
-          } else if (a.stage == 2) {
-            a.b2[qi] = vb2[c] + a.dt * r[c] / 3.0;
-            a.Qout[qi] = vb1[c] + a.dt * r[c] / 2.0;
-          } else if (a.stage == 3) {
-            a.b2[qi] = vb2[c] + a.dt * r[c] / 3.0;
-            a.Qout[qi] = vb1[c] + a.dt * r[c];
-          } else {
-            a.Qout[qi] = vb2[c] + a.dt * r[c] / 6.0;
-          }
-        }
-      }
+      if constexpr (ND == 2) emit(0, 0, f3);       // f3 == 0 in 2-D
     }
     __syncthreads();
     // advance plane bookkeeping
@@ -1431,18 +1561,36 @@ int upload_ops(mg_state* s, int which, FusedArgs* a) {
   return 0;
 }
 
-template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV>
+template <int ND, int R, bool CURV>
 int launchA(const FusedArgs& a, dim3 grid, cudaStream_t st) {
-  constexpr int NF = (ND + 2) + ND + 1 + 2;
+  constexpr int NP = ND + 1;
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
-  const size_t smem = sizeof(double) * ((size_t)NF * (TY + 2 * R) * (TX + 2 * R) + (size_t)NQ * (ND + 1) * NT);
-  auto kern = k_sweepA<ND, R, DLO, DN, TLO, TN, CURV>;
+  const size_t smem = sizeof(double) * ((size_t)NP * (TY + 2 * R) * (TX + 2 * R) + (size_t)NQ * NP * NT);
+  auto kern = k_sweepA<ND, R, CURV>;
   static bool configured = false;
   if (!configured) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   mg_profile_begin("sweepA");
+  kern<<<grid, NT, smem, st>>>(a);
+  mg_profile_end();
+  MG_CUDA(cudaGetLastError());
+  mg_count_launches(1);
+  return 0;
+}
+
+template <int ND, int R, int DLO, int DN, int TLO, int TN>
+int launchD(const FusedArgs& a, dim3 grid, cudaStream_t st) {
+  constexpr int NF = (ND + 2) + 2;
+  const size_t smem = sizeof(double) * (size_t)NF * (TY + 2 * R) * (TX + 2 * R);
+  auto kern = k_diss<ND, R, DLO, DN, TLO, TN>;
+  static bool configured = false;
+  if (!configured) {
+    MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  mg_profile_begin("dissipation");
   kern<<<grid, NT, smem, st>>>(a);
   mg_profile_end();
   MG_CUDA(cudaGetLastError());
@@ -1530,35 +1678,64 @@ int mg_fused_alloc(mg_state* s) {
   return 0;
 }
 
-// Sweep A: state update + dissipation term
+// Sweep A: state update (stress tensor + heat flux).  The dissipation term is computed on demand by
+// mg_fused_dissipation (the adjoint path never needs it for the forward state).
 int mg_fused_sweepA(mg_state* s) {
   mg_grid* g = s->grid;
   MG_TRY(mg_fused_alloc(s));
+  s->dissValid = false;
   FusedArgs a;
   MG_TRY(fill_args(s, &a));
   MG_TRY(upload_ops(s, 0, &a));
   a.Q = s->Q[s->cur].comp(0);
   a.tauq = s->opt.viscosityOn ? s->tauq.comp(0) : nullptr;
-  a.diss = s->opt.dissipationOn ? s->dissTerm.comp(0) : nullptr;
-  if (!a.viscous && !a.diss) { s->fusedValid = true; return 0; }
+  if (!a.viscous) { s->fusedValid = true; return 0; }
+  SchemeInfo si;
+  scheme_of(g, &si);
+  const dim3 grid = tiles(a, choose_chunks(&a, si.R, 3));
+  cudaStream_t st = mg_stream();
+  int rc = -1;
+#define MG_A(ND_, R_)                                                                                     \
+  if (s->nD == ND_ && si.R == R_)                                                                         \
+    rc = a.curvilinear ? launchA<ND_, R_, true>(a, grid, st) : launchA<ND_, R_, false>(a, grid, st);
+  MG_A(2, 2)
+  MG_A(2, 3)
+  MG_A(2, 4)
+  MG_A(3, 2)
+  MG_A(3, 3)
+  MG_A(3, 4)
+#undef MG_A
+  if (rc != 0) return rc < 0 && rc != -2 ? (mg_set_error("fused sweep A: unsupported configuration"), -1) : rc;
+  s->fusedValid = true;
+  return 0;
+}
+
+// Dissipation sweep: dissTerm = sum_dir Diss_dir(Q) for the current conserved variables.
+int mg_fused_dissipation(mg_state* s) {
+  mg_grid* g = s->grid;
+  if (!s->opt.dissipationOn) { s->dissValid = true; return 0; }
+  MG_TRY(mg_fused_alloc(s));
+  FusedArgs a;
+  MG_TRY(fill_args(s, &a));
+  MG_TRY(upload_ops(s, 0, &a));
+  a.Q = s->Q[s->cur].comp(0);
+  a.diss = s->dissTerm.comp(0);
   SchemeInfo si;
   scheme_of(g, &si);
   const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
   cudaStream_t st = mg_stream();
   int rc = -1;
-#define MG_A(ND_, R_, DLO, DN, TLO, TN)                                                 \
-  if (s->nD == ND_ && si.R == R_)                                                       \
-    rc = a.curvilinear ? launchA<ND_, R_, DLO, DN, TLO, TN, true>(a, grid, st)                  \
-                       : launchA<ND_, R_, DLO, DN, TLO, TN, false>(a, grid, st);
-  MG_A(2, 2, -1, 3, -1, 3)
-  MG_A(2, 3, -2, 4, -1, 4)
-  MG_A(2, 4, -2, 5, -2, 5)
-  MG_A(3, 2, -1, 3, -1, 3)
-  MG_A(3, 3, -2, 4, -1, 4)
-  MG_A(3, 4, -2, 5, -2, 5)
-#undef MG_A
-  if (rc != 0) return rc < 0 && rc != -2 ? (mg_set_error("fused sweep A: unsupported configuration"), -1) : rc;
-  s->fusedValid = true;
+#define MG_D(ND_, R_, DLO, DN, TLO, TN)                                                 \
+  if (s->nD == ND_ && si.R == R_) rc = launchD<ND_, R_, DLO, DN, TLO, TN>(a, grid, st);
+  MG_D(2, 2, -1, 3, -1, 3)
+  MG_D(2, 3, -2, 4, -1, 4)
+  MG_D(2, 4, -2, 5, -2, 5)
+  MG_D(3, 2, -1, 3, -1, 3)
+  MG_D(3, 3, -2, 4, -1, 4)
+  MG_D(3, 4, -2, 5, -2, 5)
+#undef MG_D
+  if (rc != 0) return rc < 0 && rc != -2 ? (mg_set_error("fused dissipation: unsupported configuration"), -1) : rc;
+  s->dissValid = true;
   return 0;
 }
 
@@ -1566,6 +1743,7 @@ int mg_fused_sweepA(mg_state* s) {
 int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
   mg_grid* g = s->grid;
   if (!s->fusedValid) MG_FAIL("fused sweep B: state has not been updated (sweep A)");
+  if (s->opt.dissipationOn && !s->dissValid) MG_TRY(mg_fused_dissipation(s));
   FusedArgs a;
   MG_TRY(fill_args(s, &a));
   MG_TRY(upload_ops(s, 0, &a));
