@@ -180,7 +180,7 @@ __device__ __forceinline__ bool owns(int c, int n, int T, bool isLast) {
 // (u, T) on a (TY+2R) x (TX+2R) box (corners unused) for the output plane, plus the k-queue of (u, T) for
 // the 2R+1 planes in flight (thread-private columns).  Nothing of the queue lives in registers, so three
 // CTAs fit per SM.
-template <int ND, int R, bool CURV>
+template <int ND, int R, bool CURV, bool CLOS>
 __global__ void __launch_bounds__(NT, 3) k_sweepA(FusedArgs a) {
   constexpr int NU = ND + 2;
   constexpr int NTAU = ND * (ND + 1) / 2;
@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(NT, 3) k_sweepA(FusedArgs a) {
   const bool inside = i < a.nx && j < a.ny;
   const long pij = (long)i + (long)a.nx * j;
   const double gamma = a.pp.gamma;
-  const bool fastI = !((a.D[0].hasB0 && i0 < a.D[0].depth) || (a.D[0].hasB1 && i0 + TX > a.nx - a.D[0].depth));
-  const bool fastJ = !((a.D[1].hasB0 && j0 < a.D[1].depth) || (a.D[1].hasB1 && j0 + TY > a.ny - a.D[1].depth));
+  const bool fastI = !CLOS || !((a.D[0].hasB0 && i0 < a.D[0].depth) || (a.D[0].hasB1 && i0 + TX > a.nx - a.D[0].depth));
+  const bool fastJ = !CLOS || !((a.D[1].hasB0 && j0 < a.D[1].depth) || (a.D[1].hasB1 && j0 + TY > a.ny - a.D[1].depth));
   double* const tc = T0 + (ty + R) * W + tx + R;             // own point; field stride H*W, row stride W
   double* const kqc = KQ + threadIdx.x;                      // slot stride NP*NT, field stride NT
 
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(NT, 3) k_sweepA(FusedArgs a) {
 // X = a.Q (NU components).  In-plane neighbours from a shared-memory tile of X and the arc lengths, the k
 // neighbours from a register queue of X.  Kept apart from sweep A so that neither kernel has to hold both
 // the (u, T) and the X queue on chip (the fused version spilled to local memory).
-template <int ND, int R, int DLO, int DN, int TLO, int TN>
+template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CLOS>
 __global__ void __launch_bounds__(NT, 2) k_diss(FusedArgs a) {
   const bool COMPOSITE = a.composite != 0;
   constexpr int NU = ND + 2;
@@ -419,8 +419,8 @@ __global__ void __launch_bounds__(NT, 2) k_diss(FusedArgs a) {
     if (!COMPOSITE) depth = max(depth, max(a.Dt[d].depth + a.Dd[d].width, a.dir[d].normDepth));
     return (a.dir[d].hasB0 && c0 < depth) || (a.dir[d].hasB1 && c0 + T > n - depth);
   };
-  const bool fastI = !touches(0, i0, TX, a.nx);
-  const bool fastJ = !touches(1, j0, TY, a.ny);
+  const bool fastI = !CLOS || !touches(0, i0, TX, a.nx);
+  const bool fastJ = !CLOS || !touches(1, j0, TY, a.ny);
   double* const tc = T0 + (ty + R) * W + tx + R;
 
   int hoff = 0, hk = 0;
@@ -714,7 +714,7 @@ __device__ __forceinline__ void fluxes_from_raw(const FusedArgs& a, const RawPoi
   }
 }
 
-template <int ND, int R, bool CURV>
+template <int ND, int R, bool CURV, bool CLOS>
 __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
   constexpr int NU = ND + 2;
   constexpr int W = TX + 2 * R, H = TY + 2 * R;
@@ -735,8 +735,8 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
   const bool inside = i < a.nx && j < a.ny;
   const long pij = (long)i + (long)a.nx * j;
   // fast interior stencils unless the tile touches a closure block of that direction
-  const bool fastI = !((a.D[0].hasB0 && i0 < a.D[0].depth) || (a.D[0].hasB1 && i0 + TX > a.nx - a.D[0].depth));
-  const bool fastJ = !((a.D[1].hasB0 && j0 < a.D[1].depth) || (a.D[1].hasB1 && j0 + TY > a.ny - a.D[1].depth));
+  const bool fastI = !CLOS || !((a.D[0].hasB0 && i0 < a.D[0].depth) || (a.D[0].hasB1 && i0 + TX > a.nx - a.D[0].depth));
+  const bool fastJ = !CLOS || !((a.D[1].hasB0 && j0 < a.D[1].depth) || (a.D[1].hasB1 && j0 + TY > a.ny - a.D[1].depth));
   double* const f1c = F1 + ty * W + tx + R;        // component stride TY*W
   double* const f2c = F2 + (ty + R) * TX + tx;     // component stride H*TX, row stride TX
   double* const f3c = F3 + threadIdx.x;            // slot stride NU*NT, component stride NT
@@ -972,7 +972,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
 //   rhs  = sum_d (A_d - B_d)^T dW_d  - sigma * Diss(w)               -> written to `rhs`
 //   diffusion_j = sum_i B2(i,j)^T dW_i(2:)   (viscous)               -> written to `diffOut` (4 x nD comps)
 // Same 2.5-D streaming structure as sweep A with X = w.  a.D = adjoint first derivative operators.
-template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV>
+template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV, bool CLOS>
 __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
   const bool COMPOSITE = a.composite != 0;
   constexpr int NU = ND + 2;
@@ -1003,8 +1003,8 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
     return (a.dir[d].hasB0 && c0 < depth) || (a.dir[d].hasB1 && c0 + T > n - depth);
   };
   const bool dissOn = a.dissOn != 0;
-  const bool fastI = !touches(0, i0, TX, a.nx);
-  const bool fastJ = !touches(1, j0, TY, a.ny);
+  const bool fastI = !CLOS || !touches(0, i0, TX, a.nx);
+  const bool fastJ = !CLOS || !touches(1, j0, TY, a.ny);
   double* const tc = T0 + (ty + R) * W + tx + R;
   double* const wqc = WQ + threadIdx.x;                      // slot stride NU*NT, component stride NT
 
@@ -1040,6 +1040,32 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
   int slot = 0;                    // queue slot of the arriving plane s
 
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
+    if (ND == 3 && a.prefetch && inside && (tx & 15) == 0) {
+      int kf = ks + a.prefetch;
+      if (a.wrapK && kf >= a.nz) kf -= a.nz;
+      if (a.wrapK || s + a.prefetch < a.nz + RK) {
+        const long fo = (long)kf * a.plane + pij;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) prefetch_l2(a.Win + (size_t)c * a.cs + fo);
+      }
+      int kq = ks - RK + a.prefetch;
+      if (a.wrapK) { if (kq < 0) kq += a.nz; else if (kq >= a.nz) kq -= a.nz; }
+      if (a.wrapK || (kq >= 0 && kq < a.nz)) {
+        const long qo = (long)kq * a.plane + pij;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) prefetch_l2(a.Q + (size_t)c * a.cs + qo);
+        if (a.viscous) {
+#pragma unroll
+          for (int c = 0; c < NTAU + ND; ++c) prefetch_l2(a.tauqIn + (size_t)c * a.cs + qo);
+          prefetch_l2(a.jac + qo);
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+          prefetch_l2(a.m + (size_t)(d + ND * d) * a.cs + qo);
+          if (!COMPOSITE && dissOn) prefetch_l2(a.arc + (size_t)d * a.cs + qo);
+        }
+      }
+    }
     if (inside) {
       const double* __restrict__ Wp = a.Win + ((ND == 3) ? (long)ks * a.plane : 0) + pij;
       double wv[NU];
@@ -1061,22 +1087,6 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
     if (p < kc0) continue;
     const long poff = (ND == 3) ? (long)kp * a.plane : 0;
     const long off = poff + pij;
-    // own-point inputs of the pointwise part: issue the loads before the tile is built
-    double Q[NU], tq[NTAU + ND], M[ND * ND], jac = 0.0;
-    if (mine) {
-#pragma unroll
-      for (int c = 0; c < NU; ++c) Q[c] = __ldg(a.Q + (size_t)c * a.cs + off);
-      if (a.viscous) {
-#pragma unroll
-        for (int e = 0; e < NTAU + ND; ++e) tq[e] = __ldg(a.tauqIn + (size_t)e * a.cs + off);
-        jac = __ldg(a.jac + off);
-      }
-#pragma unroll
-      for (int c = 0; c < ND * ND; ++c) {
-        const bool diag = (c % ND) == (c / ND);
-        if (CURV || diag) M[c] = __ldg(a.m + (size_t)c * a.cs + off);
-      }
-    }
     if (inside) {
 #pragma unroll
       for (int c = 0; c < NU; ++c) tc[c * H * W] = wqc[((size_t)sp0 * NU + c) * NT];
@@ -1094,96 +1104,8 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
     }
     __syncthreads();
     if (mine) {
-      double dW[ND][NU];
-#pragma unroll
-      for (int f = 0; f < NU; ++f) {
-        if (fastI) {
-          double r = 0.0;
-#pragma unroll
-          for (int q = 1; q <= R; ++q) r += a.D[0].c[R + q] * (tc[f * H * W + q] - tc[f * H * W - q]);
-          dW[0][f] = r;
-        } else {
-          dW[0][f] = tile_line_apply<W, H>(&a.ops->D[0], i, a.nx, T0, f, ty + R, tx + R, 0, i0 - R);
-        }
-        if (fastJ) {
-          double r = 0.0;
-#pragma unroll
-          for (int q = 1; q <= R; ++q) r += a.D[1].c[R + q] * (tc[f * H * W + q * W] - tc[f * H * W - q * W]);
-          dW[1][f] = r;
-        } else {
-          dW[1][f] = tile_line_apply<W, H>(&a.ops->D[1], j, a.ny, T0, f, ty + R, tx + R, 1, j0 - R);
-        }
-      }
-      if constexpr (ND == 3) {
-#pragma unroll
-        for (int f = 0; f < NU; ++f) dW[ND - 1][f] = 0.0;
-#pragma unroll
-        for (int q = 1; q <= RK; ++q) {
-          int sp = sp0 + q, sm = sp0 - q;
-          if (sp >= NQ) sp -= NQ;
-          if (sm < 0) sm += NQ;
-          const double cq = a.D[2].c[RK + q];
-#pragma unroll
-          for (int f = 0; f < NU; ++f)
-            dW[ND - 1][f] += cq * (wqc[((size_t)sp * NU + f) * NT] - wqc[((size_t)sm * NU + f) * NT]);
-        }
-      }
-      // ---- pointwise Jacobian-transpose products
-      Prim<ND> sp;
-      dependent<ND>(Q, a.pp.gamma, sp);
-      double tau[ND * ND], qh[ND];
-      if (a.viscous) {
-#pragma unroll
-        for (int l = 0; l < ND; ++l)
-#pragma unroll
-          for (int c = 0; c < ND; ++c) tau[l + ND * c] = tq[tau_index<ND>(l, c)];
-#pragma unroll
-        for (int e = 0; e < ND; ++e) qh[e] = tq[NTAU + e];
-      }
       double r[NU];
-#pragma unroll
-      for (int c = 0; c < NU; ++c) r[c] = 0.0;
-      if constexpr (CURV) {
-#pragma unroll
-        for (int d = 0; d < ND; ++d)
-          add_flux_jacobian_transpose<ND>(Q, sp, &M[ND * d], a.pp.gamma, a.viscous, a.pp.powerLaw, tau, qh, dW[d], r);
-      } else {
-        static_for<ND>([&](auto d) {
-          add_flux_jacobian_transpose_rect<ND, d.value>(sp, M[d.value + ND * d.value], a.pp.gamma, a.viscous,
-                                                        a.pp.powerLaw, tau, qh, dW[d.value], r);
-        });
-      }
-      if (a.viscous) {
-        double mu, lam, kap;
-        transport(sp.T, a.pp, mu, lam, kap);
-        if constexpr (CURV) {
-#pragma unroll
-          for (int jj = 0; jj < ND; ++jj) {
-            double dd[ND + 1];
-#pragma unroll
-            for (int c = 0; c < ND + 1; ++c) dd[c] = 0.0;
-#pragma unroll
-            for (int ii = 0; ii < ND; ++ii)
-              add_second_partial_transpose<ND>(sp.u, mu, lam, kap, jac, &M[ND * ii], &M[ND * jj], &dW[ii][1], dd);
-#pragma unroll
-            for (int c = 0; c < ND + 1; ++c) a.diffOut[(size_t)(c + (NU - 1) * jj) * a.cs + off] = dd[c];
-          }
-        } else {
-          static_for<ND>([&](auto jj) {
-            double dd[ND + 1];
-#pragma unroll
-            for (int c = 0; c < ND + 1; ++c) dd[c] = 0.0;
-            static_for<ND>([&](auto ii) {
-              add_second_partial_transpose_rect<ND, ii.value, jj.value>(sp.u, mu, lam, kap, jac,
-                                                                        M[ii.value + ND * ii.value],
-                                                                        M[jj.value + ND * jj.value], &dW[ii.value][1], dd);
-            });
-#pragma unroll
-            for (int c = 0; c < ND + 1; ++c) a.diffOut[(size_t)(c + (NU - 1) * jj.value) * a.cs + off] = dd[c];
-          });
-        }
-      }
-      // ---- adjoint dissipation: - sigma * sum_dir Diss_dir(w)
+      // ---- adjoint dissipation first: r = - sigma * sum_dir Diss_dir(w)  (needs only the tile and the queue)
       if (dissOn) {
         double dz[NU];
 #pragma unroll
@@ -1249,8 +1171,122 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
           }
         }
 #pragma unroll
-        for (int c = 0; c < NU; ++c) r[c] -= a.dissAmount * dz[c];
+        for (int c = 0; c < NU; ++c) r[c] = 0.0 - a.dissAmount * dz[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < NU; ++c) r[c] = 0.0;
       }
+      // own-point inputs of the pointwise part
+      double Q[NU], tq[NTAU + ND], M[ND * ND], jac = 0.0;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) Q[c] = __ldg(a.Q + (size_t)c * a.cs + off);
+      if (a.viscous) jac = __ldg(a.jac + off);
+#pragma unroll
+      for (int c = 0; c < ND * ND; ++c) {
+        const bool diag = (c % ND) == (c / ND);
+        if (CURV || diag) M[c] = __ldg(a.m + (size_t)c * a.cs + off);
+      }
+      asm volatile("" ::: "memory");   // scheduling fence: keep the phases' live ranges apart
+      // ---- pointwise Jacobian-transpose products, one direction at a time
+      Prim<ND> sp;
+      dependent<ND>(Q, a.pp.gamma, sp);
+      double mu = 0.0, lam = 0.0, kap = 0.0;
+      if (a.viscous) transport(sp.T, a.pp, mu, lam, kap);
+      // adjoint first derivative of w along direction d at this point (tile for xi/eta, queue for zeta)
+      auto deriv = [&](auto dI, double* dW) {
+        constexpr int d = dI.value;
+        if (d == 0) {
+#pragma unroll
+          for (int f = 0; f < NU; ++f) {
+            if (fastI) {
+              double t = 0.0;
+#pragma unroll
+              for (int q = 1; q <= R; ++q) t += a.D[0].c[R + q] * (tc[f * H * W + q] - tc[f * H * W - q]);
+              dW[f] = t;
+            } else {
+              dW[f] = tile_line_apply<W, H>(&a.ops->D[0], i, a.nx, T0, f, ty + R, tx + R, 0, i0 - R);
+            }
+          }
+        } else if (d == 1) {
+#pragma unroll
+          for (int f = 0; f < NU; ++f) {
+            if (fastJ) {
+              double t = 0.0;
+#pragma unroll
+              for (int q = 1; q <= R; ++q) t += a.D[1].c[R + q] * (tc[f * H * W + q * W] - tc[f * H * W - q * W]);
+              dW[f] = t;
+            } else {
+              dW[f] = tile_line_apply<W, H>(&a.ops->D[1], j, a.ny, T0, f, ty + R, tx + R, 1, j0 - R);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int f = 0; f < NU; ++f) dW[f] = 0.0;
+#pragma unroll
+          for (int q = 1; q <= RK; ++q) {
+            int sq = sp0 + q, sm = sp0 - q;
+            if (sq >= NQ) sq -= NQ;
+            if (sm < 0) sm += NQ;
+            const double cq = a.D[2].c[RK + q];
+#pragma unroll
+            for (int f = 0; f < NU; ++f)
+              dW[f] += cq * (wqc[((size_t)sq * NU + f) * NT] - wqc[((size_t)sm * NU + f) * NT]);
+          }
+        }
+      };
+      // pass 1: adjoint diffusion_j = sum_i B2(i,j)^T dW_i(2:)  (needs u, mu, lambda, kappa, 1/J, metrics only)
+      if (a.viscous) {
+        double dd[ND][ND + 1];
+#pragma unroll
+        for (int jj = 0; jj < ND; ++jj)
+#pragma unroll
+          for (int c = 0; c < ND + 1; ++c) dd[jj][c] = 0.0;
+        static_for<ND>([&](auto dI) {
+          constexpr int d = dI.value;
+          double dW[NU];
+          deriv(dI, dW);
+          if constexpr (CURV) {
+#pragma unroll
+            for (int jj = 0; jj < ND; ++jj)
+              add_second_partial_transpose<ND>(sp.u, mu, lam, kap, jac, &M[ND * d], &M[ND * jj], &dW[1], dd[jj]);
+          } else {
+            static_for<ND>([&](auto jj) {
+              add_second_partial_transpose_rect<ND, d, jj.value>(sp.u, mu, lam, kap, jac, M[d + ND * d],
+                                                                 M[jj.value + ND * jj.value], &dW[1], dd[jj.value]);
+            });
+          }
+          asm volatile("" ::: "memory");
+        });
+#pragma unroll
+        for (int jj = 0; jj < ND; ++jj)
+#pragma unroll
+          for (int c = 0; c < ND + 1; ++c) a.diffOut[(size_t)(c + (NU - 1) * jj) * a.cs + off] = dd[jj][c];
+        asm volatile("" ::: "memory");
+      }
+      // pass 2: r += sum_d (A_d - B_d)^T dW_d
+      double tau[ND * ND], qh[ND];
+      if (a.viscous) {
+#pragma unroll
+        for (int e = 0; e < NTAU + ND; ++e) tq[e] = __ldg(a.tauqIn + (size_t)e * a.cs + off);
+#pragma unroll
+        for (int l = 0; l < ND; ++l)
+#pragma unroll
+          for (int c = 0; c < ND; ++c) tau[l + ND * c] = tq[tau_index<ND>(l, c)];
+#pragma unroll
+        for (int e = 0; e < ND; ++e) qh[e] = tq[NTAU + e];
+      }
+      static_for<ND>([&](auto dI) {
+        constexpr int d = dI.value;
+        double dW[NU];
+        deriv(dI, dW);
+        if constexpr (CURV) {
+          add_flux_jacobian_transpose<ND>(Q, sp, &M[ND * d], a.pp.gamma, a.viscous, a.pp.powerLaw, tau, qh, dW, r);
+        } else {
+          add_flux_jacobian_transpose_rect<ND, d>(sp, M[d + ND * d], a.pp.gamma, a.viscous, a.pp.powerLaw, tau, qh,
+                                                  dW, r);
+        }
+        asm volatile("" ::: "memory");
+      });
 #pragma unroll
       for (int c = 0; c < NU; ++c) a.rhs[(size_t)c * a.cs + off] = r[c];
     }
@@ -1262,7 +1298,7 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
 // computeRhsAdjoint, second half (reference src/RhsHelperImpl.f90:555-570) + x 1/J + substepAdjointRK4:
 //   t = sum_j D+_j diffusion_j ; variable change ; rhs = (rhsPartial -/+ t) / J ; RK4 substep on w.
 // Same structure as sweep B with G_d = diffusion_d (NU-1 components, read from memory).
-template <int ND, int R>
+template <int ND, int R, bool CLOS>
 __global__ void __launch_bounds__(NT, 2) k_adjoint2(FusedArgs a) {
   constexpr int NU = ND + 2;
   constexpr int NG = NU - 1;
@@ -1282,8 +1318,8 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint2(FusedArgs a) {
   const bool mine = owns(i, a.nx, TX, lastI) && owns(j, a.ny, TY, lastJ);
   const bool inside = i < a.nx && j < a.ny;
   const long pij = (long)i + (long)a.nx * j;
-  const bool fastI = !((a.D[0].hasB0 && i0 < a.D[0].depth) || (a.D[0].hasB1 && i0 + TX > a.nx - a.D[0].depth));
-  const bool fastJ = !((a.D[1].hasB0 && j0 < a.D[1].depth) || (a.D[1].hasB1 && j0 + TY > a.ny - a.D[1].depth));
+  const bool fastI = !CLOS || !((a.D[0].hasB0 && i0 < a.D[0].depth) || (a.D[0].hasB1 && i0 + TX > a.nx - a.D[0].depth));
+  const bool fastJ = !CLOS || !((a.D[1].hasB0 && j0 < a.D[1].depth) || (a.D[1].hasB1 && j0 + TY > a.ny - a.D[1].depth));
   double* const f1c = F1 + ty * W + tx + R;
   double* const f2c = F2 + (ty + R) * TX + tx;
   double* const f3c = F3 + threadIdx.x;
@@ -1561,12 +1597,12 @@ int upload_ops(mg_state* s, int which, FusedArgs* a) {
   return 0;
 }
 
-template <int ND, int R, bool CURV>
+template <int ND, int R, bool CURV, bool CLOS>
 int launchA(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NP = ND + 1;
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
   const size_t smem = sizeof(double) * ((size_t)NP * (TY + 2 * R) * (TX + 2 * R) + (size_t)NQ * NP * NT);
-  auto kern = k_sweepA<ND, R, CURV>;
+  auto kern = k_sweepA<ND, R, CURV, CLOS>;
   static bool configured = false;
   if (!configured) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1580,11 +1616,11 @@ int launchA(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   return 0;
 }
 
-template <int ND, int R, int DLO, int DN, int TLO, int TN>
+template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CLOS>
 int launchD(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NF = (ND + 2) + 2;
   const size_t smem = sizeof(double) * (size_t)NF * (TY + 2 * R) * (TX + 2 * R);
-  auto kern = k_diss<ND, R, DLO, DN, TLO, TN>;
+  auto kern = k_diss<ND, R, DLO, DN, TLO, TN, CLOS>;
   static bool configured = false;
   if (!configured) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1598,13 +1634,13 @@ int launchD(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   return 0;
 }
 
-template <int ND, int R, bool CURV>
+template <int ND, int R, bool CURV, bool CLOS>
 int launchB(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NU = ND + 2;
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
   const size_t smem = sizeof(double) * ((size_t)NU * TY * (TX + 2 * R) + (size_t)NU * (TY + 2 * R) * TX +
                                         (size_t)NQ * NU * NT);
-  auto kern = k_sweepB<ND, R, CURV>;
+  auto kern = k_sweepB<ND, R, CURV, CLOS>;
   static bool configured = false;
   if (!configured) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1644,6 +1680,19 @@ int choose_chunks(FusedArgs* a, int R, int residentPerSm) {
 
 dim3 tiles(const FusedArgs& a, int nChunks) {
   return dim3((a.nx + TX - 1) / TX, (a.ny + TY - 1) / TY, nChunks);
+}
+
+// true when an in-plane direction has a domain boundary (SBP closures): selects the kernel variant that
+// carries the out-of-line closure path; fully periodic in-plane grids run the variant without it.
+bool has_closures(const FusedArgs& a) {
+  return a.dir[0].hasB0 || a.dir[0].hasB1 || a.dir[1].hasB0 || a.dir[1].hasB1;
+}
+
+template <int ND, int R>
+int launchB_(const FusedArgs& a, dim3 grid, cudaStream_t st) {
+  const bool clos = has_closures(a);
+  return a.curvilinear ? (clos ? launchB<ND, R, true, true>(a, grid, st) : launchB<ND, R, true, false>(a, grid, st))
+                       : (clos ? launchB<ND, R, false, true>(a, grid, st) : launchB<ND, R, false, false>(a, grid, st));
 }
 
 }  // namespace
@@ -1695,15 +1744,28 @@ int mg_fused_sweepA(mg_state* s) {
   const dim3 grid = tiles(a, choose_chunks(&a, si.R, 3));
   cudaStream_t st = mg_stream();
   int rc = -1;
+  const bool clos = has_closures(a);
+  (void)clos;
 #define MG_A(ND_, R_)                                                                                     \
   if (s->nD == ND_ && si.R == R_)                                                                         \
-    rc = a.curvilinear ? launchA<ND_, R_, true>(a, grid, st) : launchA<ND_, R_, false>(a, grid, st);
+    rc = a.curvilinear ? (clos ? launchA<ND_, R_, true, true>(a, grid, st) : launchA<ND_, R_, true, false>(a, grid, st))  \
+                       : (clos ? launchA<ND_, R_, false, true>(a, grid, st) : launchA<ND_, R_, false, false>(a, grid, st));
+#ifndef MG_DEV_ONLY_33
   MG_A(2, 2)
+#endif
+#ifndef MG_DEV_ONLY_33
   MG_A(2, 3)
+#endif
+#ifndef MG_DEV_ONLY_33
   MG_A(2, 4)
+#endif
+#ifndef MG_DEV_ONLY_33
   MG_A(3, 2)
+#endif
   MG_A(3, 3)
+#ifndef MG_DEV_ONLY_33
   MG_A(3, 4)
+#endif
 #undef MG_A
   if (rc != 0) return rc < 0 && rc != -2 ? (mg_set_error("fused sweep A: unsupported configuration"), -1) : rc;
   s->fusedValid = true;
@@ -1725,14 +1787,27 @@ int mg_fused_dissipation(mg_state* s) {
   const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
   cudaStream_t st = mg_stream();
   int rc = -1;
+  const bool clos = has_closures(a);
+  (void)clos;
 #define MG_D(ND_, R_, DLO, DN, TLO, TN)                                                 \
-  if (s->nD == ND_ && si.R == R_) rc = launchD<ND_, R_, DLO, DN, TLO, TN>(a, grid, st);
+  if (s->nD == ND_ && si.R == R_)                                                       \
+    rc = clos ? launchD<ND_, R_, DLO, DN, TLO, TN, true>(a, grid, st) : launchD<ND_, R_, DLO, DN, TLO, TN, false>(a, grid, st);
+#ifndef MG_DEV_ONLY_33
   MG_D(2, 2, -1, 3, -1, 3)
+#endif
+#ifndef MG_DEV_ONLY_33
   MG_D(2, 3, -2, 4, -1, 4)
+#endif
+#ifndef MG_DEV_ONLY_33
   MG_D(2, 4, -2, 5, -2, 5)
+#endif
+#ifndef MG_DEV_ONLY_33
   MG_D(3, 2, -1, 3, -1, 3)
+#endif
   MG_D(3, 3, -2, 4, -1, 4)
+#ifndef MG_DEV_ONLY_33
   MG_D(3, 4, -2, 5, -2, 5)
+#endif
 #undef MG_D
   if (rc != 0) return rc < 0 && rc != -2 ? (mg_set_error("fused dissipation: unsupported configuration"), -1) : rc;
   s->dissValid = true;
@@ -1771,12 +1846,24 @@ int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
   const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
   cudaStream_t st = mg_stream();
   int rc = -1;
-  if (s->nD == 2 && si.R == 2) rc = a.curvilinear ? launchB<2, 2, true>(a, grid, st) : launchB<2, 2, false>(a, grid, st);
-  if (s->nD == 2 && si.R == 3) rc = a.curvilinear ? launchB<2, 3, true>(a, grid, st) : launchB<2, 3, false>(a, grid, st);
-  if (s->nD == 2 && si.R == 4) rc = a.curvilinear ? launchB<2, 4, true>(a, grid, st) : launchB<2, 4, false>(a, grid, st);
-  if (s->nD == 3 && si.R == 2) rc = a.curvilinear ? launchB<3, 2, true>(a, grid, st) : launchB<3, 2, false>(a, grid, st);
-  if (s->nD == 3 && si.R == 3) rc = a.curvilinear ? launchB<3, 3, true>(a, grid, st) : launchB<3, 3, false>(a, grid, st);
-  if (s->nD == 3 && si.R == 4) rc = a.curvilinear ? launchB<3, 4, true>(a, grid, st) : launchB<3, 4, false>(a, grid, st);
+  const bool clos = has_closures(a);
+  (void)clos;
+#ifndef MG_DEV_ONLY_33
+  if (s->nD == 2 && si.R == 2) rc = launchB_<2, 2>(a, grid, st);
+#endif
+#ifndef MG_DEV_ONLY_33
+  if (s->nD == 2 && si.R == 3) rc = launchB_<2, 3>(a, grid, st);
+#endif
+#ifndef MG_DEV_ONLY_33
+  if (s->nD == 2 && si.R == 4) rc = launchB_<2, 4>(a, grid, st);
+#endif
+#ifndef MG_DEV_ONLY_33
+  if (s->nD == 3 && si.R == 2) rc = launchB_<3, 2>(a, grid, st);
+#endif
+  if (s->nD == 3 && si.R == 3) rc = launchB_<3, 3>(a, grid, st);
+#ifndef MG_DEV_ONLY_33
+  if (s->nD == 3 && si.R == 4) rc = launchB_<3, 4>(a, grid, st);
+#endif
   if (rc != 0) return rc;
   if (fuseRk) {
     if (stage == 1) {
@@ -1796,12 +1883,12 @@ int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
 // ------------------------------------------------------------------------------ adjoint host side
 namespace {
 
-template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV>
+template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV, bool CLOS>
 int launchAdj1(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NF = (ND + 2) + 2;
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
   const size_t smem = sizeof(double) * ((size_t)NF * (TY + 2 * R) * (TX + 2 * R) + (size_t)NQ * (ND + 2) * NT);
-  auto kern = k_adjoint1<ND, R, DLO, DN, TLO, TN, CURV>;
+  auto kern = k_adjoint1<ND, R, DLO, DN, TLO, TN, CURV, CLOS>;
   static bool configured = false;
   if (!configured) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1815,13 +1902,13 @@ int launchAdj1(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   return 0;
 }
 
-template <int ND, int R>
+template <int ND, int R, bool CLOS>
 int launchAdj2(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NG = ND + 1;
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
   const size_t smem = sizeof(double) * ((size_t)NG * TY * (TX + 2 * R) + (size_t)NG * (TY + 2 * R) * TX +
                                         (size_t)NQ * NG * NT);
-  auto kern = k_adjoint2<ND, R>;
+  auto kern = k_adjoint2<ND, R, CLOS>;
   static bool configured = false;
   if (!configured) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1863,16 +1950,30 @@ int mg_fused_adjoint1(mg_state* s) {
   const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
   cudaStream_t st = mg_stream();
   int rc = -1;
+  const bool clos = has_closures(a);
+  (void)clos;
 #define MG_J(ND_, R_, DLO, DN, TLO, TN)                                                 \
   if (s->nD == ND_ && si.R == R_)                                                       \
-    rc = a.curvilinear ? launchAdj1<ND_, R_, DLO, DN, TLO, TN, true>(a, grid, st)               \
-                       : launchAdj1<ND_, R_, DLO, DN, TLO, TN, false>(a, grid, st);
+    rc = a.curvilinear ? (clos ? launchAdj1<ND_, R_, DLO, DN, TLO, TN, true, true>(a, grid, st)                      \
+                               : launchAdj1<ND_, R_, DLO, DN, TLO, TN, true, false>(a, grid, st))                    \
+                       : (clos ? launchAdj1<ND_, R_, DLO, DN, TLO, TN, false, true>(a, grid, st)                     \
+                               : launchAdj1<ND_, R_, DLO, DN, TLO, TN, false, false>(a, grid, st));
+#ifndef MG_DEV_ONLY_33
   MG_J(2, 2, -1, 3, -1, 3)
+#endif
+#ifndef MG_DEV_ONLY_33
   MG_J(2, 3, -2, 4, -1, 4)
+#endif
+#ifndef MG_DEV_ONLY_33
   MG_J(2, 4, -2, 5, -2, 5)
+#endif
+#ifndef MG_DEV_ONLY_33
   MG_J(3, 2, -1, 3, -1, 3)
+#endif
   MG_J(3, 3, -2, 4, -1, 4)
+#ifndef MG_DEV_ONLY_33
   MG_J(3, 4, -2, 5, -2, 5)
+#endif
 #undef MG_J
   return rc;
 }
@@ -1905,12 +2006,24 @@ int mg_fused_adjoint2(mg_state* s, int fuseRk, int stage, double dt) {
   const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
   cudaStream_t st = mg_stream();
   int rc = -1;
-  if (s->nD == 2 && si.R == 2) rc = launchAdj2<2, 2>(a, grid, st);
-  if (s->nD == 2 && si.R == 3) rc = launchAdj2<2, 3>(a, grid, st);
-  if (s->nD == 2 && si.R == 4) rc = launchAdj2<2, 4>(a, grid, st);
-  if (s->nD == 3 && si.R == 2) rc = launchAdj2<3, 2>(a, grid, st);
-  if (s->nD == 3 && si.R == 3) rc = launchAdj2<3, 3>(a, grid, st);
-  if (s->nD == 3 && si.R == 4) rc = launchAdj2<3, 4>(a, grid, st);
+  const bool clos = has_closures(a);
+  (void)clos;
+#ifndef MG_DEV_ONLY_33
+  if (s->nD == 2 && si.R == 2) rc = clos ? launchAdj2<2, 2, true>(a, grid, st) : launchAdj2<2, 2, false>(a, grid, st);
+#endif
+#ifndef MG_DEV_ONLY_33
+  if (s->nD == 2 && si.R == 3) rc = clos ? launchAdj2<2, 3, true>(a, grid, st) : launchAdj2<2, 3, false>(a, grid, st);
+#endif
+#ifndef MG_DEV_ONLY_33
+  if (s->nD == 2 && si.R == 4) rc = clos ? launchAdj2<2, 4, true>(a, grid, st) : launchAdj2<2, 4, false>(a, grid, st);
+#endif
+#ifndef MG_DEV_ONLY_33
+  if (s->nD == 3 && si.R == 2) rc = clos ? launchAdj2<3, 2, true>(a, grid, st) : launchAdj2<3, 2, false>(a, grid, st);
+#endif
+  if (s->nD == 3 && si.R == 3) rc = clos ? launchAdj2<3, 3, true>(a, grid, st) : launchAdj2<3, 3, false>(a, grid, st);
+#ifndef MG_DEV_ONLY_33
+  if (s->nD == 3 && si.R == 4) rc = clos ? launchAdj2<3, 4, true>(a, grid, st) : launchAdj2<3, 4, false>(a, grid, st);
+#endif
   if (rc != 0) return rc;
   if (fuseRk) {
     if (rkStage == 1) {
