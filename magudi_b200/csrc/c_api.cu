@@ -420,7 +420,8 @@ int mg_state_destroy(mg_state* s) {
 int mg_state_set(mg_state* s, int field, const double* host) {
   MgField* f = s ? state_field(s, field) : nullptr;
   if (!f || !f->p) MG_FAIL("mg_state_set: unknown or unallocated field");
-  if (field == MG_Q_CONSERVED) { s->dependentValid = false; s->fusedValid = false; }
+  if (field == MG_Q_CONSERVED) { s->dependentValid = false; s->fusedValid = false; s->dissValid = false; }
+  if (field == MG_Q_CONSERVED || field == MG_Q_ADJOINT) MG_TRY(mg_state_make_exclusive(s, f, false));
   if (field == MG_Q_TARGET)
     for (mg_patch* p : s->patches) p->AplusReady = false;
   return mg_field_upload(s->grid, f, host);
@@ -457,29 +458,27 @@ int mg_state_update(mg_state* s) {
 int mg_state_checkpoint_store(mg_state* s, int slot) {
   if (!s || slot < 0) MG_FAIL("mg_state_checkpoint_store: invalid argument");
   if ((size_t)slot >= s->checkpoints.size()) s->checkpoints.resize(slot + 1);
-  MgField& f = s->checkpoints[slot];
-  if (!f.p) MG_TRY(mg_field_alloc(s->grid, s->nU, &f));
-  const MgField& Q = s->Q[s->cur];
-  MG_CUDA(cudaMemcpyAsync(f.p, Q.p, Q.compStride * (size_t)s->nU * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+  // no copy: the slot becomes a view of the buffer holding Q; that buffer is never written again while the
+  // slot refers to it (mg_state_make_exclusive swaps in a free buffer first)
+  s->checkpoints[slot] = s->Q[s->cur];
+  s->checkpoints[slot].owned = false;
   return 0;
 }
 int mg_state_checkpoint_load(mg_state* s, int slot) {
   if (!s || slot < 0 || (size_t)slot >= s->checkpoints.size() || !s->checkpoints[slot].p)
     MG_FAIL("mg_state_checkpoint_load: empty slot");
-  const MgField& f = s->checkpoints[slot];
-  MgField& Q = s->Q[s->cur];
-  MG_CUDA(cudaMemcpyAsync(Q.p, f.p, Q.compStride * (size_t)s->nU * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+  s->Q[s->cur] = s->checkpoints[slot];
   s->dependentValid = false;
   s->fusedValid = false;
+  s->dissValid = false;
   return 0;
 }
 int mg_state_checkpoint_clear(mg_state* s) {
   if (!s) MG_FAIL("mg_state_checkpoint_clear: null handle");
-  for (MgField& f : s->checkpoints) mg_field_free(&f);
   s->checkpoints.clear();
+  mg_state_pool_trim(s);
   return 0;
 }
-
 // ------------------------------------------------------------------------------- patch
 int mg_patch_create(mg_state* s, int type, const char* name, int normalDirection, const int extent[6],
                     double inviscidPenaltyAmount, double viscousPenaltyAmount, mg_patch** out) {

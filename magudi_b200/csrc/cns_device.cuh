@@ -30,7 +30,9 @@ __device__ __forceinline__ void dependent(const double* Q, double gamma, Prim<ND
     usq = (i == 0) ? s.u[i] * s.u[i] : usq + s.u[i] * s.u[i];
   }
   s.p = (gamma - 1.0) * (Q[ND + 1] - 0.5 * Q[0] * usq);
-  s.T = gamma * s.p / (gamma - 1.0) * s.v;
+  // gamma / (gamma - 1) is loop invariant: one division per kernel instead of one per point
+  const double gg1 = gamma / (gamma - 1.0);
+  s.T = gg1 * s.p * s.v;
 }
 
 // computeTransportVariables (reference :89-177)

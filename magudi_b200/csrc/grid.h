@@ -34,7 +34,12 @@ struct mg_state {
   // fused path: outputs of sweep A (unique stress entries + heat flux; dissipation term)
   MgField tauq, dissTerm;
   void* fusedOps[2] = {nullptr, nullptr};   // device operator tables of the fused closure path (fwd, adjoint)
-  std::vector<MgField> checkpoints;   // device-resident forward substep states (adjoint replay)
+  // Device-resident forward substep states (adjoint replay).  A slot is a VIEW of the nU-component buffer
+  // that held Q when it was stored: Q, W, rk1 and the slots draw their storage from `pool`, storing / loading
+  // a checkpoint is a pointer assignment, and a shared buffer is replaced by a free one right before anything
+  // writes to it (mg_state_make_exclusive).
+  std::vector<MgField> checkpoints;
+  std::vector<double*> pool;
   bool fusedValid = false;
   bool dissValid = false;      // dissTerm holds the dissipation of the current Q
   int useFused = 1;
@@ -58,6 +63,8 @@ struct mg_state {
 int mg_state_create_impl(mg_grid* g, const mg_options_t* opt, mg_state** out);
 void mg_state_destroy_impl(mg_state* s);
 int mg_state_update_impl(mg_state* s, const MgField* Qoverride);
+int mg_state_make_exclusive(mg_state* s, MgField* f, bool keepContents);
+void mg_state_pool_trim(mg_state* s);
 int mg_state_rhs_forward_general(mg_state* s);
 int mg_state_rhs_adjoint_general(mg_state* s);
 int mg_state_compute_rhs_impl(mg_state* s, int mode);

@@ -338,6 +338,11 @@ int mg_state_create_impl(mg_grid* g, const mg_options_t* opt, mg_state** out) {
   MG_TRY(mg_field_alloc(g, 1, &s->temperature));
   MG_TRY(mg_field_alloc(g, nU, &s->rk1));
   MG_TRY(mg_field_alloc(g, nU, &s->rk2));
+  // Q, W and rk1 exchange roles with each other and with the checkpoint slots: pooled storage
+  for (MgField* f : {&s->Q[0], &s->Q[1], &s->W[0], &s->W[1], &s->rk1}) {
+    s->pool.push_back(f->p);
+    f->owned = false;
+  }
   if (opt->viscosityOn) {
     MG_TRY(mg_field_alloc(g, 1, &s->mu));
     MG_TRY(mg_field_alloc(g, 1, &s->lambda));
@@ -352,6 +357,47 @@ int mg_state_create_impl(mg_grid* g, const mg_options_t* opt, mg_state** out) {
   return 0;
 }
 
+// ---- pooled nU-component buffers (Q, W, rk1, checkpoint slots)
+namespace {
+template <class F>
+void for_each_pooled(mg_state* s, F&& fn) {
+  for (MgField* f : {&s->Q[0], &s->Q[1], &s->W[0], &s->W[1], &s->rk1}) fn(f);
+  for (MgField& c : s->checkpoints) fn(&c);
+}
+bool pool_referenced(mg_state* s, const double* p, const MgField* except) {
+  bool used = false;
+  for_each_pooled(s, [&](MgField* f) { if (f != except && f->p == p) used = true; });
+  return used;
+}
+}  // namespace
+
+// Give `f` storage that no other pooled field refers to (a shared buffer keeps serving the others).
+int mg_state_make_exclusive(mg_state* s, MgField* f, bool keepContents) {
+  if (!f->p || !pool_referenced(s, f->p, f)) return 0;
+  double* fresh = nullptr;
+  for (double* p : s->pool)
+    if (!pool_referenced(s, p, nullptr)) { fresh = p; break; }
+  const size_t bytes = f->compStride * (size_t)f->nComp * sizeof(double);
+  if (!fresh) {
+    MG_CUDA(cudaMalloc(&fresh, bytes));
+    MG_CUDA(cudaMemsetAsync(fresh, 0, bytes, mg_stream()));
+    s->pool.push_back(fresh);
+  }
+  if (keepContents) MG_CUDA(cudaMemcpyAsync(fresh, f->p, bytes, cudaMemcpyDeviceToDevice, mg_stream()));
+  f->p = fresh;
+  return 0;
+}
+
+// Release pooled buffers nothing refers to any more.
+void mg_state_pool_trim(mg_state* s) {
+  std::vector<double*> keep;
+  for (double* p : s->pool) {
+    if (pool_referenced(s, p, nullptr)) keep.push_back(p);
+    else cudaFree(p);
+  }
+  s->pool.swap(keep);
+}
+
 void mg_state_destroy_impl(mg_state* s) {
   if (!s) return;
   for (MgField* f : {&s->Q[0], &s->Q[1], &s->W[0], &s->W[1], &s->target, &s->rhs, &s->specificVolume,
@@ -359,6 +405,7 @@ void mg_state_destroy_impl(mg_state* s) {
                      &s->stressTensor, &s->heatFlux, &s->rk1, &s->rk2, &s->viscFluxCart, &s->tauq, &s->dissTerm})
     mg_field_free(f);
   for (void* p : s->fusedOps) if (p) cudaFree(p);
+  for (double* p : s->pool) cudaFree(p);
   delete s;
 }
 
@@ -613,6 +660,9 @@ int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int time
       return mg_fused_sweepB(s, 1, stage, dt);
     }
     MG_TRY(mg_state_compute_rhs_impl(s, MG_FORWARD));
+    MG_TRY(mg_state_make_exclusive(s, &s->Q[s->cur], true));
+    MG_TRY(mg_state_make_exclusive(s, &s->rk1, true));
+    a.b1 = s->rk1.comp(0);
     a.R = s->rhs.comp(0);
     a.Qin = s->Q[s->cur].comp(0);
     a.Qout = s->Q[s->cur].comp(0);     // in place: the RHS is already materialised
@@ -634,6 +684,9 @@ int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int time
       return 0;
     }
     MG_TRY(mg_state_compute_rhs_impl(s, MG_ADJOINT));
+    MG_TRY(mg_state_make_exclusive(s, &s->W[s->curW], true));
+    MG_TRY(mg_state_make_exclusive(s, &s->rk1, true));
+    a.b1 = s->rk1.comp(0);
     a.R = s->rhs.comp(0);
     a.Qin = s->W[s->curW].comp(0);
     a.Qout = s->W[s->curW].comp(0);

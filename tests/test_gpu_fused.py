@@ -116,3 +116,51 @@ def test_fused_adjoint_rhs_and_rk4(shape, periodic, curv, visc, composite, schem
             tg = integ.substepAdjoint(tg, dt, step, stage)
     assert abs(t - tg) < 1e-15
     assert relerr(st.adjointVariables, s.adjointVariables) <= TOL_RHS
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_checkpoint_slots_survive_forward_steps_and_replay(fused):
+    """UniformCheckpointer semantics (reference src/UniformCheckpointerImpl.f90:78-208): substep states stored
+    during the forward march are the states the adjoint march linearises about.  Slots are zero-copy views, so
+    this also checks that no later forward/adjoint substep overwrites a stored state."""
+    import magudi_b200 as mb
+    from oracle import rhs as orhs
+    g, opt, s, rng = oracle_case((20, 19, 18), (True, True, True), False, True, False, "SBP 3-6")
+    gg, o, st = gpu_case_from_oracle(g, opt, s)
+    region = mb.Region()
+    region.addState(st)
+    region.setFused(fused)
+    integ = mb.RK4Integrator(region)
+    oint = orhs.RK4Integrator(s)
+    rhs_fn = lambda mode, ts, stage: orhs.computeRhs(mode, opt, g, s)
+    dt, t, tg = 1e-3, 0.0, 0.0
+    stored = {}
+    s.update(g, opt)
+    st.update()
+    for step in range(2):
+        for stage in range(1, 5):
+            slot = 4 * step + stage - 1
+            stored[slot] = s.conservedVariables.copy()
+            st.checkpointStore(slot)
+            t = oint.substepForward(rhs_fn, s, t, dt, step, stage)
+            s.update(g, opt)
+            tg = integ.substepForward(tg, dt, step, stage)
+    final = s.conservedVariables.copy()
+    assert relerr(st.conservedVariables, final) <= TOL_RHS
+    for step in (1, 0):
+        for stage in range(4, 0, -1):
+            slot = 4 * step + stage - 1
+            st.checkpointLoad(slot)
+            assert relerr(st.conservedVariables, stored[slot]) <= TOL_RHS
+            s.conservedVariables[:, :] = stored[slot]
+            s.update(g, opt)
+            st.update()
+            t = oint.substepAdjoint(rhs_fn, s, t, dt, step, stage)
+            tg = integ.substepAdjoint(tg, dt, step, stage)
+    assert relerr(st.adjointVariables, s.adjointVariables) <= TOL_RHS
+    # every slot still holds its state after the whole adjoint march, and setting Q does not touch a slot
+    st.conservedVariables = final
+    for slot, ref in stored.items():
+        st.checkpointLoad(slot)
+        assert relerr(st.conservedVariables, ref) <= TOL_RHS
+    st.checkpointClear()
