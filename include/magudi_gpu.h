@@ -150,6 +150,20 @@ mg_stencil* mg_grid_operator(mg_grid* g, int which, int direction);   /* 0 first
  * buffer into the ghost planes of that face.  side 0 = low k, 1 = high k. */
 int mg_halo_pack(mg_grid* g, void* owner, int field, int side, int width, double* deviceBuffer);
 int mg_halo_unpack(mg_grid* g, void* owner, int field, int side, int width, const double* deviceBuffer);
+/* Direct peer-to-peer ghost-plane exchange over NVLink (replaces fillGhostPoints, src/MPIHelperImpl.f90:113-389,
+ * for the slab decomposition): each rank creates an exchanger, publishes its CUDA IPC handle
+ * (mg_p2p_handle_size bytes), connects to the previous (side 0) / next (side 1) rank's handle (NULL = no
+ * neighbour on that side; sameAsOther = 1 when both neighbours are the same rank), and then calls
+ * mg_p2p_exchange for every field whose ghost planes are needed.  Exchanges are asynchronous on the library
+ * stream and synchronise with the neighbours on the device (sequence flags); mg_p2p_check reports a timeout. */
+typedef struct mg_p2p mg_p2p;
+int mg_p2p_create(mg_grid* g, int maxComp, int width, mg_p2p** out);
+int mg_p2p_handle_size(void);
+int mg_p2p_get_handle(mg_p2p* h, void* handleOut);
+int mg_p2p_connect(mg_p2p* h, int side, const void* peerHandle, int sameAsOther);
+int mg_p2p_exchange(mg_p2p* h, void* owner, int field, int width);
+int mg_p2p_check(mg_p2p* h);
+int mg_p2p_destroy(mg_p2p* h);
 
 /* ------------------------------------------------------------------ t_State */
 /* %setup: src/StateImpl.f90:71-170 */

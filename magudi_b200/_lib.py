@@ -74,6 +74,13 @@ SIGNATURES = {
     "mg_grid_operator": (_P, [_P, C.c_int, C.c_int]),
     "mg_halo_pack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "mg_halo_unpack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "mg_p2p_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "mg_p2p_handle_size": (C.c_int, []),
+    "mg_p2p_get_handle": (C.c_int, [_P, _P]),
+    "mg_p2p_connect": (C.c_int, [_P, C.c_int, _P, C.c_int]),
+    "mg_p2p_exchange": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "mg_p2p_check": (C.c_int, [_P]),
+    "mg_p2p_destroy": (C.c_int, [_P]),
     "mg_state_create": (C.c_int, [_P, C.POINTER(Options), C.POINTER(_P)]),
     "mg_state_destroy": (C.c_int, [_P]),
     "mg_state_set": (C.c_int, [_P, C.c_int, _P]),

@@ -594,6 +594,12 @@ int mg_rk4_substep_adjoint_phase(mg_region* r, int phase, double* time, double d
   return 0;
 }
 
+MgField* mg_lookup_field(mg_grid* g, void* owner, int field) {
+  int nc = 0;
+  if (field >= 100) return g ? grid_field(g, field, &nc, false) : nullptr;
+  return owner ? state_field((mg_state*)owner, field) : nullptr;
+}
+
 int mg_halo_pack(mg_grid* g, void* owner, int field, int side, int width, double* buf) {
   if (!g || !buf) MG_FAIL("mg_halo_pack: null argument");
   int nc = 0;
@@ -605,8 +611,7 @@ int mg_halo_pack(mg_grid* g, void* owner, int field, int side, int width, double
     const double* src = f->comp(c) + (side == 0 ? 0 : g->plane * (size_t)(g->localSize[2] - width));
     MG_CUDA(cudaMemcpyAsync(buf + chunk * c, src, chunk * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
   }
-  MG_CUDA(cudaStreamSynchronize(g_stream));
-  return 0;
+  return 0;   // asynchronous on the library stream (mg_stream_handle): the exchange is ordered on that stream
 }
 int mg_halo_unpack(mg_grid* g, void* owner, int field, int side, int width, const double* buf) {
   if (!g || !buf) MG_FAIL("mg_halo_unpack: null argument");
@@ -619,7 +624,6 @@ int mg_halo_unpack(mg_grid* g, void* owner, int field, int side, int width, cons
     double* dst = f->comp(c) + (side == 0 ? -(ptrdiff_t)chunk : (ptrdiff_t)(g->plane * (size_t)g->localSize[2]));
     MG_CUDA(cudaMemcpyAsync(dst, buf + chunk * c, chunk * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
   }
-  MG_CUDA(cudaStreamSynchronize(g_stream));
   return 0;
 }
 

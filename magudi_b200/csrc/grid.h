@@ -79,5 +79,6 @@ int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt);
 int mg_fused_adjoint1(mg_state* s);
 int mg_fused_adjoint2(mg_state* s, int fuseRk, int stage, double dt);
 void mg_count_launches(int n);
+#define MG_P2P_MAX_COMP 16
 void mg_profile_begin(const char* name);
 void mg_profile_end();

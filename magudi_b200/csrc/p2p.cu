@@ -1,0 +1,279 @@
+// Direct peer-to-peer halo exchange over NVLink for the slab (direction-3) decomposition: the replacement of
+// fillGhostPoints (reference src/MPIHelperImpl.f90:113-389) on the hot path.
+//
+// Every rank owns one IPC-shared device allocation holding, per k-face, two staging buffers (double
+// buffering) and the flags that sequence them.  An exchange is two kernels on the library stream and no
+// host synchronisation at all (push and unpack are one launch each, blockIdx.y = face):
+//   push   : read my boundary planes from the field and STORE them straight into the neighbour's staging
+//            buffer (remote NVLink stores), then release a sequence flag in the neighbour's memory;
+//   unpack : spin until the neighbour's flag for this exchange has arrived (acquire, system scope), copy the
+//            staging buffer into my ghost planes, then tell the sender the buffer is free (ack flag).
+// The host only enqueues; the GPUs synchronise pairwise through the flags, so ranks may run ahead of each
+// other by up to two exchanges per face.
+#include <cstdint>
+#include <cstring>
+
+#include "../../include/magudi_gpu.h"
+#include "grid.h"
+#include "mg_common.h"
+
+extern "C" MgField* mg_lookup_field(mg_grid* g, void* owner, int field);   // c_api.cu
+
+namespace {
+
+constexpr int P2P_BLOCKS = 144, P2P_THREADS = 256;
+constexpr long long SPIN_LIMIT_CYCLES = 20LL * 1000 * 1000 * 1000;   // ~10 s: turn a protocol bug into an error
+
+struct Shared {                         // layout of the flag block at the head of the shared allocation
+  unsigned long long data[2][2];        // [my ghost face][parity]: uses of recv[face][parity] completed by the sender
+  unsigned long long ack[2][2];         // [my send direction][parity]: uses consumed by that receiver
+  unsigned long long pad[8];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// thread 0 of the block spins until *flag >= want; returns false on timeout
+__device__ __forceinline__ bool block_wait(const unsigned long long* flag, unsigned long long want, int* error) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    ok = 1;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < want) {
+      if (clock64() - t0 > SPIN_LIMIT_CYCLES) { ok = 0; atomicExch(error, 1); break; }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  return ok != 0;
+}
+
+struct PushArgs {
+  const double* src[MG_P2P_MAX_COMP];   // first boundary plane of every component
+  int nComp;
+  size_t chunk;                         // doubles per component (width * plane)
+  double* dst;                          // neighbour's staging buffer
+  unsigned long long* dstFlag;          // neighbour's data flag for this buffer
+  const unsigned long long* ackFlag;    // my ack flag for this buffer (written by the neighbour)
+  unsigned long long use;               // number of earlier uses of this buffer
+  unsigned int* counter;                // local block counter
+  int* error;
+  int vec;                              // every pointer 16-byte aligned and chunk even: double2 copies
+};
+
+__device__ __forceinline__ void copy_chunk(double* d, const double* s, size_t n, bool vec, bool viaL2) {
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+  if (vec) {
+    const double2* s2 = reinterpret_cast<const double2*>(s);
+    double2* d2 = reinterpret_cast<double2*>(d);
+    for (size_t i = t0; i < n / 2; i += nt) d2[i] = viaL2 ? __ldcg(s2 + i) : s2[i];
+  } else {
+    for (size_t i = t0; i < n; i += nt) d[i] = viaL2 ? __ldcg(s + i) : s[i];
+  }
+}
+
+struct PushPair { PushArgs s[2]; };
+
+__global__ void __launch_bounds__(P2P_THREADS) k_push(const __grid_constant__ PushPair pp) {
+  const PushArgs& a = pp.s[blockIdx.y];
+  if (!a.dst) return;
+  // the previous use of this staging buffer must have been consumed by the neighbour
+  if (!block_wait(a.ackFlag, a.use, a.error)) return;
+  for (int c = 0; c < a.nComp; ++c) copy_chunk(a.dst + (size_t)c * a.chunk, a.src[c], a.chunk, a.vec != 0, false);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(a.counter, 1u);
+    if (done == gridDim.x - 1) {
+      *a.counter = 0;
+      __threadfence_system();
+      st_release_sys(a.dstFlag, a.use + 1);
+    }
+  }
+}
+
+struct UnpackArgs {
+  double* dst[MG_P2P_MAX_COMP];         // first ghost plane of every component
+  int nComp;
+  size_t chunk;
+  const double* src;                    // my staging buffer
+  const unsigned long long* dataFlag;   // my data flag for this buffer
+  unsigned long long* ackFlag;          // the sender's ack flag
+  unsigned long long use;
+  unsigned int* counter;
+  int* error;
+  int vec;
+};
+
+struct UnpackPair { UnpackArgs s[2]; };
+
+__global__ void __launch_bounds__(P2P_THREADS) k_unpack(const __grid_constant__ UnpackPair pp) {
+  const UnpackArgs& a = pp.s[blockIdx.y];
+  if (!a.src) return;
+  if (!block_wait(a.dataFlag, a.use + 1, a.error)) return;
+  // the staging buffer was written by the peer: read it through L2 (bypass L1)
+  for (int c = 0; c < a.nComp; ++c) copy_chunk(a.dst[c], a.src + (size_t)c * a.chunk, a.chunk, a.vec != 0, true);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(a.counter, 1u);
+    if (done == gridDim.x - 1) {
+      *a.counter = 0;
+      __threadfence_system();
+      st_release_sys(a.ackFlag, a.use + 1);
+    }
+  }
+}
+
+}  // namespace
+
+struct mg_p2p {
+  mg_grid* grid = nullptr;
+  size_t capacity = 0;                  // doubles per staging buffer
+  char* base = nullptr;                 // my shared allocation
+  char* peer[2] = {nullptr, nullptr};   // mapped allocations of prev (0) / next (1)
+  bool peerMapped[2] = {false, false};
+  unsigned long long uses[2] = {0, 0};  // exchanges done so far (same count on both faces)
+  unsigned int* counters = nullptr;     // [4] local block counters
+  int* error = nullptr;                 // device error flag (spin timeout)
+  size_t bytes = 0;
+  Shared* flags() const { return reinterpret_cast<Shared*>(base); }
+  static size_t bufOffset(size_t cap, int face, int parity) {
+    return sizeof(Shared) + ((size_t)face * 2 + parity) * cap * sizeof(double);
+  }
+};
+
+int mg_p2p_create(mg_grid* g, int maxComp, int width, mg_p2p** out) {
+  if (!g || !out) MG_FAIL("mg_p2p_create: null argument");
+  if (maxComp < 1 || maxComp > MG_P2P_MAX_COMP) MG_FAIL("mg_p2p_create: component count out of range");
+  if (width < 1 || width > g->gk) MG_FAIL("mg_p2p_create: width exceeds the ghost capacity");
+  mg_p2p* h = new mg_p2p;
+  h->grid = g;
+  h->capacity = g->plane * (size_t)width * (size_t)maxComp;
+  h->capacity += h->capacity % 2;       // keeps every staging buffer 16-byte aligned
+  h->bytes = sizeof(Shared) + 4 * h->capacity * sizeof(double);
+  MG_CUDA(cudaMalloc(&h->base, h->bytes));
+  MG_CUDA(cudaMemset(h->base, 0, h->bytes));
+  MG_CUDA(cudaMalloc(&h->counters, 4 * sizeof(unsigned int)));
+  MG_CUDA(cudaMemset(h->counters, 0, 4 * sizeof(unsigned int)));
+  MG_CUDA(cudaMalloc(&h->error, sizeof(int)));
+  MG_CUDA(cudaMemset(h->error, 0, sizeof(int)));
+  MG_CUDA(cudaDeviceSynchronize());
+  *out = h;
+  return 0;
+}
+
+int mg_p2p_handle_size(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int mg_p2p_get_handle(mg_p2p* h, void* handleOut) {
+  if (!h || !handleOut) MG_FAIL("mg_p2p_get_handle: null argument");
+  cudaIpcMemHandle_t mh;
+  MG_CUDA(cudaIpcGetMemHandle(&mh, h->base));
+  std::memcpy(handleOut, &mh, sizeof(mh));
+  return 0;
+}
+
+// side 0: the previous rank along k, 1: the next one.  `sameAsOther` != 0 when both neighbours are the same
+// process (two ranks, periodic): the mapping of the other side is reused.
+int mg_p2p_connect(mg_p2p* h, int side, const void* peerHandle, int sameAsOther) {
+  if (!h || side < 0 || side > 1) MG_FAIL("mg_p2p_connect: invalid argument");
+  if (!peerHandle) { h->peer[side] = nullptr; return 0; }
+  if (sameAsOther && h->peer[1 - side]) { h->peer[side] = h->peer[1 - side]; return 0; }
+  cudaIpcMemHandle_t mh;
+  std::memcpy(&mh, peerHandle, sizeof(mh));
+  void* p = nullptr;
+  MG_CUDA(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+  h->peer[side] = (char*)p;
+  h->peerMapped[side] = true;
+  return 0;
+}
+
+// Exchange `width` ghost planes of a field with both k-neighbours.  Asynchronous on the library stream.
+int mg_p2p_exchange(mg_p2p* h, void* owner, int field, int width) {
+  if (!h) MG_FAIL("mg_p2p_exchange: null handle");
+  mg_grid* g = h->grid;
+  MgField* f = mg_lookup_field(g, owner, field);
+  if (!f || !f->p) MG_FAIL("mg_p2p_exchange: unknown field");
+  const size_t chunk = g->plane * (size_t)width;
+  if (width > g->gk || width > g->localSize[2]) MG_FAIL("mg_p2p_exchange: width exceeds ghost capacity");
+  if (f->nComp > MG_P2P_MAX_COMP || chunk * (size_t)f->nComp > h->capacity)
+    MG_FAIL("mg_p2p_exchange: field exceeds the staging capacity");
+  cudaStream_t st = mg_stream();
+  const unsigned long long n = h->uses[0];
+  const int parity = (int)(n & 1);
+  const unsigned long long use = n >> 1;
+  // push my low planes to prev's HIGH-ghost staging, my high planes to next's LOW-ghost staging (one launch,
+  // blockIdx.y = side)
+  PushPair pp;
+  std::memset(&pp, 0, sizeof(pp));
+  for (int side = 0; side < 2; ++side) {
+    if (!h->peer[side]) continue;
+    PushArgs& a = pp.s[side];
+    a.nComp = f->nComp;
+    a.chunk = chunk;
+    for (int c = 0; c < f->nComp; ++c)
+      a.src[c] = f->comp(c) + (side == 0 ? 0 : g->plane * (size_t)(g->localSize[2] - width));
+    const int peerFace = 1 - side;
+    a.dst = reinterpret_cast<double*>(h->peer[side] + mg_p2p::bufOffset(h->capacity, peerFace, parity));
+    a.dstFlag = &reinterpret_cast<Shared*>(h->peer[side])->data[peerFace][parity];
+    a.ackFlag = &h->flags()->ack[side][parity];
+    a.use = use;
+    a.counter = h->counters + side;
+    a.error = h->error;
+    a.vec = (chunk % 2 == 0) && ((uintptr_t)a.dst % 16 == 0);
+    for (int c = 0; c < f->nComp; ++c) a.vec = a.vec && ((uintptr_t)a.src[c] % 16 == 0);
+  }
+  k_push<<<dim3(P2P_BLOCKS, 2), P2P_THREADS, 0, st>>>(pp);
+  UnpackPair up;
+  std::memset(&up, 0, sizeof(up));
+  for (int face = 0; face < 2; ++face) {
+    if (!h->peer[face]) continue;      // ghost face `face` is filled by neighbour `face`
+    UnpackArgs& a = up.s[face];
+    a.nComp = f->nComp;
+    a.chunk = chunk;
+    for (int c = 0; c < f->nComp; ++c)
+      a.dst[c] = f->comp(c) + (face == 0 ? -(ptrdiff_t)chunk : (ptrdiff_t)(g->plane * (size_t)g->localSize[2]));
+    a.src = reinterpret_cast<const double*>(h->base + mg_p2p::bufOffset(h->capacity, face, parity));
+    a.dataFlag = &h->flags()->data[face][parity];
+    // the sender pushed through its side (1 - face): that is where it waits for the acknowledgement
+    a.ackFlag = &reinterpret_cast<Shared*>(h->peer[face])->ack[1 - face][parity];
+    a.use = use;
+    a.counter = h->counters + 2 + face;
+    a.error = h->error;
+    a.vec = (chunk % 2 == 0) && ((uintptr_t)a.src % 16 == 0);
+    for (int c = 0; c < f->nComp; ++c) a.vec = a.vec && ((uintptr_t)a.dst[c] % 16 == 0);
+  }
+  k_unpack<<<dim3(P2P_BLOCKS, 2), P2P_THREADS, 0, st>>>(up);
+  MG_CUDA(cudaGetLastError());
+  mg_count_launches(2);
+  h->uses[0] = h->uses[1] = n + 1;
+  return 0;
+}
+
+// 0 when no spin-wait timed out so far (synchronises the library stream)
+int mg_p2p_check(mg_p2p* h) {
+  if (!h) MG_FAIL("mg_p2p_check: null handle");
+  int e = 0;
+  MG_CUDA(cudaStreamSynchronize(mg_stream()));
+  MG_CUDA(cudaMemcpy(&e, h->error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) MG_FAIL("mg_p2p: a halo exchange timed out waiting for its neighbour");
+  return 0;
+}
+
+int mg_p2p_destroy(mg_p2p* h) {
+  if (!h) return 0;
+  cudaDeviceSynchronize();
+  for (int s = 0; s < 2; ++s)
+    if (h->peerMapped[s] && h->peer[s]) cudaIpcCloseMemHandle(h->peer[s]);
+  cudaFree(h->base);
+  cudaFree(h->counters);
+  cudaFree(h->error);
+  delete h;
+  return 0;
+}

@@ -25,10 +25,13 @@ class HaloExchanger:
     the HIGH ghost (next's low planes) then the LOW ghost (prev's high planes).
     """
 
-    def __init__(self, rank, world, periodic=True, device=None, group=None):
+    def __init__(self, rank, world, periodic=True, device=None, group=None, stream=None):
         self.rank, self.world, self.periodic = rank, world, periodic
         self.device = device
         self.group = group
+        # CUDA stream that pack/unpack run on.  When given, the whole exchange is stream-ordered on it (NCCL
+        # waits for the packs, the unpacks wait for NCCL) and the host never blocks.
+        self.stream = stream
         self.prev = (rank - 1) % world if (periodic or rank > 0) else None
         self.next = (rank + 1) % world if (periodic or rank < world - 1) else None
         self._buffers = {}
@@ -43,6 +46,13 @@ class HaloExchanger:
     def exchange(self, key, count, width, pack, unpack):
         if self.world == 1:
             return
+        if self.stream is not None:
+            with torch.cuda.stream(self.stream):
+                self._exchange(key, count, width, pack, unpack, host_sync=False)
+        else:
+            self._exchange(key, count, width, pack, unpack, host_sync=True)
+
+    def _exchange(self, key, count, width, pack, unpack, host_sync):
         send_lo, send_hi, recv_hi, recv_lo = self._bufs(key, count)
         pack(0, width, send_lo)
         pack(1, width, send_hi)
@@ -57,7 +67,7 @@ class HaloExchanger:
             ops.append(dist.P2POp(dist.irecv, recv_lo, self.prev, group=self.group))
         for req in dist.batch_isend_irecv(ops):
             req.wait()
-        if self.device is not None and torch.device(self.device).type == "cuda":
+        if host_sync and self.device is not None and torch.device(self.device).type == "cuda":
             torch.cuda.current_stream().synchronize()
         if self.next is not None:
             unpack(1, width, recv_hi)
@@ -66,18 +76,63 @@ class HaloExchanger:
 
 
 class GpuHalo:
-    """Halo exchange of library-owned fields (``mg_halo_pack`` / ``mg_halo_unpack``)."""
+    """Halo exchange of library-owned fields along k.
 
-    def __init__(self, grid, rank, world, device):
+    mode "p2p" (default on CUDA): direct peer-to-peer stores over NVLink into the neighbour's IPC-mapped
+    staging buffers, sequenced by device-side flags (``mg_p2p_*``): three kernels per exchange on the
+    library stream, no NCCL call and no host synchronisation.  ``torch.distributed`` is only used once, to
+    swap the IPC handles.  mode "nccl" (``MG_HALO=nccl``): ``mg_halo_pack`` -> NCCL send/recv -> ``mg_halo_unpack``.
+    """
+
+    MAX_COMP = 12
+
+    def __init__(self, grid, rank, world, device, mode=None):
+        import os
         self.grid = grid
+        self.rank, self.world = rank, world
         periodic = grid.periodicityType[2] != 0
-        self.ex = HaloExchanger(rank, world, periodic, device)
+        self.mode = mode or os.environ.get("MG_HALO", "p2p")
         self.plane = grid.localSize[0] * grid.localSize[1]
+        self._p2p = None
+        if self.mode == "p2p" and world > 1:
+            self._setup_p2p(periodic, device)
+        else:
+            self.mode = "nccl"
+            # the library stream is made torch's current stream during an exchange: no host synchronisation
+            stream = torch.cuda.ExternalStream(L.lib().mg_stream_handle(), device=device)
+            self.ex = HaloExchanger(rank, world, periodic, device, stream=stream)
+
+    def _setup_p2p(self, periodic, device):
+        lib = L.lib()
+        h = C.c_void_p()
+        check(lib.mg_p2p_create(self.grid._h, self.MAX_COMP, min(4, self.grid.localSize[2]), C.byref(h)))
+        self._p2p = h
+        n = lib.mg_p2p_handle_size()
+        buf = C.create_string_buffer(n)
+        check(lib.mg_p2p_get_handle(h, buf))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(buf.raw))
+        rank, world = self.rank, self.world
+        prev = (rank - 1) % world if (periodic or rank > 0) else None
+        nxt = (rank + 1) % world if (periodic or rank < world - 1) else None
+        self._keep = []
+        for side, peer in ((0, prev), (1, nxt)):
+            if peer is None:
+                check(lib.mg_p2p_connect(h, side, None, 0))
+                continue
+            hb = C.create_string_buffer(handles[peer], n)
+            self._keep.append(hb)
+            same = 1 if (side == 1 and prev is not None and prev == nxt) else 0
+            check(lib.mg_p2p_connect(h, side, hb, same))
+        dist.barrier()
 
     def exchange(self, owner, field, ncomp, width=3):
         lib = L.lib()
         g = self.grid._h
         oh = owner._h if owner is not None else None
+        if self._p2p is not None:
+            check(lib.mg_p2p_exchange(self._p2p, oh, field, width))
+            return
 
         def pack(side, w, buf):
             check(lib.mg_halo_pack(g, oh, field, side, w, C.c_void_p(buf.data_ptr())))
@@ -86,6 +141,17 @@ class GpuHalo:
             check(lib.mg_halo_unpack(g, oh, field, side, w, C.c_void_p(buf.data_ptr())))
 
         self.ex.exchange(field, ncomp * width * self.plane, width, pack, unpack)
+
+    def check(self):
+        """Raise if a device-side wait of the p2p exchange timed out (synchronises the library stream)."""
+        if self._p2p is not None:
+            check(L.lib().mg_p2p_check(self._p2p))
+
+    def close(self):
+        if self._p2p is not None:
+            dist.barrier()
+            check(L.lib().mg_p2p_destroy(self._p2p))
+            self._p2p = None
 
 
 def all_reduce_sum(value, device=None):

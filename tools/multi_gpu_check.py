@@ -46,6 +46,8 @@ def run(shape, world, rank, dev, steps=2):
         for stage in range(1, 5):
             t = integ.substepForward(t, 1e-3, step, stage, updateStates=False)
             update()
+    if halo:
+        halo.check()
     return state.conservedVariables, grid
 
 
