@@ -368,8 +368,16 @@ def run_native(args):
         bytes_per_launch = {"sweepA": BYTES_SWEEP_A, "dissipation": BYTES_DISS, "sweepB": BYTES_SWEEP_B, "adjoint1": BYTES_ADJ1,
                             "adjoint2": BYTES_ADJ2}.get(dom, BYTES_SWEEP_B) * N
         achieved = bytes_per_launch / (prof[dom]["avg_ms"] * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")) as f:
+                traffic = json.load(f)[dom]["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": "ncu dram__bytes_read+write per launch (profiles/r1_kernel_traffic.json)" if traffic else None,
+                    "peak_source": peak_src,
                     "share_of_step": prof[dom]["ms"] / total_ms,
                     "algorithmic_bytes_per_point": bytes_per_launch / N}
     # whole-path rates (device time of the forward / adjoint legs incl. checkpoint copies and halos)
