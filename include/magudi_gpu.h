@@ -171,6 +171,16 @@ int mg_state_create(mg_grid* g, const mg_options* options, mg_state** out);
 int mg_state_destroy(mg_state* s);
 int mg_state_set(mg_state* s, int field, const double* host);
 int mg_state_get(mg_state* s, int field, double* host);
+/* Transfers that overlap the sweeps (the reference keeps its arrays in host RAM, so it has no counterpart):
+ * _async variants run on a separate copy stream, ordered after everything enqueued so far on the compute
+ * stream.  set_async: call mg_transfer_fence() before the first sweep that uses the field.  get_async /
+ * checkpoint_get_async: the source must stay unmodified until mg_transfer_wait() (a checkpoint slot always
+ * does).  Host buffers should be pinned. */
+int mg_state_set_async(mg_state* s, int field, const double* pinnedHost);
+int mg_state_get_async(mg_state* s, int field, double* pinnedHost);
+int mg_state_checkpoint_get_async(mg_state* s, int slot, double* pinnedHost);
+int mg_transfer_fence(void);   /* compute stream waits for the transfers issued so far */
+int mg_transfer_wait(void);    /* host waits for the transfers issued so far */
 int mg_state_set_time(mg_state* s, double time);
 /* acoustic sources: src/StateImpl.f90:135-148, src/AcousticSourceImpl.f90:3-32 */
 int mg_state_add_acoustic_source(mg_state* s, const double location[3], double amplitude, double frequency,

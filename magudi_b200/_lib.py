@@ -85,6 +85,11 @@ SIGNATURES = {
     "mg_state_destroy": (C.c_int, [_P]),
     "mg_state_set": (C.c_int, [_P, C.c_int, _P]),
     "mg_state_get": (C.c_int, [_P, C.c_int, _P]),
+    "mg_state_set_async": (C.c_int, [_P, C.c_int, _P]),
+    "mg_state_get_async": (C.c_int, [_P, C.c_int, _P]),
+    "mg_state_checkpoint_get_async": (C.c_int, [_P, C.c_int, _P]),
+    "mg_transfer_fence": (C.c_int, []),
+    "mg_transfer_wait": (C.c_int, []),
     "mg_state_set_time": (C.c_int, [_P, C.c_double]),
     "mg_state_add_acoustic_source": (C.c_int, [_P, _D, C.c_double, C.c_double, C.c_double, C.c_double]),
     "mg_state_update": (C.c_int, [_P]),

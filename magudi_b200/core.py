@@ -341,6 +341,16 @@ class State:
     def getToPointer(self, field, ptr):
         check(L.lib().mg_state_get(self._h, field, C.c_void_p(ptr)))
 
+    # transfers on the copy stream (overlap the sweeps); see include/magudi_gpu.h
+    def setFromPointerAsync(self, field, ptr):
+        check(L.lib().mg_state_set_async(self._h, field, C.c_void_p(ptr)))
+
+    def getToPointerAsync(self, field, ptr):
+        check(L.lib().mg_state_get_async(self._h, field, C.c_void_p(ptr)))
+
+    def checkpointGetToPointerAsync(self, slot, ptr):
+        check(L.lib().mg_state_checkpoint_get_async(self._h, int(slot), C.c_void_p(ptr)))
+
     def addPatch(self, patchType, name, normalDirection, extent, inviscidPenaltyAmount=1.0,
                  viscousPenaltyAmount=1.0):
         p = Patch(self, patchType, name, normalDirection, extent, inviscidPenaltyAmount, viscousPenaltyAmount)
@@ -448,3 +458,13 @@ class RK4Integrator:
         check(L.lib().mg_rk4_substep(self.region._h, ADJOINT, C.byref(t), float(timeStepSize), int(timestep),
                                      int(stage), 0))
         return t.value
+
+
+def transferFence():
+    """The compute stream waits for the asynchronous transfers issued so far."""
+    check(L.lib().mg_transfer_fence())
+
+
+def transferWait():
+    """The host waits for the asynchronous transfers issued so far."""
+    check(L.lib().mg_transfer_wait())

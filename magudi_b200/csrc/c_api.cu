@@ -13,6 +13,7 @@
 namespace {
 thread_local std::string g_error;
 cudaStream_t g_stream = nullptr;
+cudaStream_t g_copyStream = nullptr;   // host <-> device transfers that overlap the sweeps (mg_state_*_async)
 int g_device = -1;
 int g_sms = 0;
 std::atomic<long long> g_launches{0};
@@ -100,6 +101,8 @@ int mg_init(int device) {
   MG_CUDA(cudaSetDevice(device));
   if (g_stream && g_device != device) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
   if (!g_stream) MG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  if (g_copyStream && g_device != device) { cudaStreamDestroy(g_copyStream); g_copyStream = nullptr; }
+  if (!g_copyStream) MG_CUDA(cudaStreamCreateWithFlags(&g_copyStream, cudaStreamNonBlocking));
   cudaDeviceProp prop;
   MG_CUDA(cudaGetDeviceProperties(&prop, device));
   g_sms = prop.multiProcessorCount;
@@ -431,6 +434,58 @@ int mg_state_get(mg_state* s, int field, double* host) {
   if (!f || !f->p) MG_FAIL("mg_state_get: unknown or unallocated field");
   return mg_field_download(s->grid, f, host);
 }
+// ---- transfers on the copy stream, overlapping the sweeps ------------------------------------------------
+namespace {
+// make stream `waiter` wait for everything enqueued so far on stream `on`
+int stream_wait(cudaStream_t waiter, cudaStream_t on) {
+  cudaEvent_t e;
+  MG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  MG_CUDA(cudaEventRecord(e, on));
+  MG_CUDA(cudaStreamWaitEvent(waiter, e, 0));
+  MG_CUDA(cudaEventDestroy(e));     // released once the event has completed
+  return 0;
+}
+int copy_field_async(const mg_grid* g, MgField* f, double* host, bool toDevice) {
+  MG_TRY(stream_wait(g_copyStream, g_stream));
+  for (int c = 0; c < f->nComp; ++c) {
+    if (toDevice)
+      MG_CUDA(cudaMemcpyAsync(f->comp(c), host + (size_t)c * g->N, g->N * sizeof(double), cudaMemcpyDefault, g_copyStream));
+    else
+      MG_CUDA(cudaMemcpyAsync(host + (size_t)c * g->N, f->comp(c), g->N * sizeof(double), cudaMemcpyDefault, g_copyStream));
+  }
+  return 0;
+}
+}  // namespace
+
+int mg_state_set_async(mg_state* s, int field, const double* pinnedHost) {
+  MgField* f = s ? state_field(s, field) : nullptr;
+  if (!f || !f->p || !pinnedHost) MG_FAIL("mg_state_set_async: unknown or unallocated field");
+  if (field == MG_Q_CONSERVED) { s->dependentValid = false; s->fusedValid = false; s->dissValid = false; }
+  if (field == MG_Q_CONSERVED || field == MG_Q_ADJOINT) MG_TRY(mg_state_make_exclusive(s, f, false));
+  if (field == MG_Q_TARGET)
+    for (mg_patch* p : s->patches) p->AplusReady = false;
+  return copy_field_async(s->grid, f, const_cast<double*>(pinnedHost), true);
+}
+int mg_state_get_async(mg_state* s, int field, double* pinnedHost) {
+  MgField* f = s ? state_field(s, field) : nullptr;
+  if (!f || !f->p || !pinnedHost) MG_FAIL("mg_state_get_async: unknown or unallocated field");
+  return copy_field_async(s->grid, f, pinnedHost, false);
+}
+int mg_state_checkpoint_get_async(mg_state* s, int slot, double* pinnedHost) {
+  if (!s || !pinnedHost || slot < 0 || (size_t)slot >= s->checkpoints.size() || !s->checkpoints[slot].p)
+    MG_FAIL("mg_state_checkpoint_get_async: empty slot");
+  return copy_field_async(s->grid, &s->checkpoints[slot], pinnedHost, false);
+}
+int mg_transfer_fence(void) {
+  if (g_device < 0) MG_FAIL("mg_transfer_fence: mg_init has not been called");
+  return stream_wait(g_stream, g_copyStream);
+}
+int mg_transfer_wait(void) {
+  if (g_device < 0) MG_FAIL("mg_transfer_wait: mg_init has not been called");
+  MG_CUDA(cudaStreamSynchronize(g_copyStream));
+  return 0;
+}
+
 int mg_state_set_time(mg_state* s, double time) {
   if (!s) MG_FAIL("mg_state_set_time: null handle");
   s->time = time;

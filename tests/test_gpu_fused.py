@@ -164,3 +164,32 @@ def test_checkpoint_slots_survive_forward_steps_and_replay(fused):
         st.checkpointLoad(slot)
         assert relerr(st.conservedVariables, ref) <= TOL_RHS
     st.checkpointClear()
+
+
+def test_async_transfers_match_blocking_ones():
+    """mg_state_set_async / get_async / checkpoint_get_async (copy stream) move the same bytes as set / get."""
+    import magudi_b200 as mb
+    from magudi_b200 import core
+    g, opt, s, rng = oracle_case((20, 19, 18), (True, True, True), False, True, False, "SBP 3-6")
+    gg, o, st = gpu_case_from_oracle(g, opt, s)
+    region = mb.Region()
+    region.addState(st)
+    N = g.nGridPoints
+    w_in = np.asfortranarray(rng.random((N, 5)))
+    st.setFromPointerAsync(core.Q_ADJOINT, w_in.ctypes.data)
+    core.transferFence()
+    assert np.array_equal(st.adjointVariables, w_in)
+    q0 = st.conservedVariables.copy()
+    st.update()
+    st.checkpointStore(0)
+    integ = mb.RK4Integrator(region)
+    integ.substepForward(0.0, 1e-3, 0, 1)          # moves Q on; slot 0 must still hold q0
+    out = np.asfortranarray(np.zeros((N, 5)))
+    st.checkpointGetToPointerAsync(0, out.ctypes.data)
+    out2 = np.asfortranarray(np.zeros((N, 5)))
+    st.getToPointerAsync(core.Q_CONSERVED, out2.ctypes.data)
+    core.transferWait()
+    assert np.array_equal(out, q0)
+    assert np.array_equal(out2, st.conservedVariables)
+    assert not np.array_equal(out2, q0)
+    st.checkpointClear()
