@@ -15,6 +15,7 @@
 // neighbours come from a shared-memory tile (with halo, periodic wrap or SBP boundary closures),
 // k-neighbours from a per-thread queue (registers in A, shared memory in B) so every field is read
 // from HBM once per sweep.  HBM-bound fp64 stencil/pointwise work: no tensor cores.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -1661,7 +1662,23 @@ int mg_fused_supported(const mg_state* s, int mode) {
       // a closure block (and its adjoint-free forward operators) must fit in one 16-wide tile + halo
       const MgDevOp& o = (mode == MG_ADJOINT ? g->adjointFirstDerivative[d] : g->firstDerivative[d])->op;
       if (o.boundaryWidth > TX + si.R || o.boundaryDepth > TX || g->localSize[d] < 2 * o.boundaryDepth) return 0;
-    } else if (g->localSize[d] < si.R + 1) {
+      // The last tile of a direction is anchored at the far boundary; when the line is not a multiple of the
+      // tile it takes over the points >= n - 16 from the first tile.  Every point of the LEFT closure region
+      // (widest operator used along the direction) must stay with the first tile, whose halo holds the block.
+      int depth = std::max(o.boundaryDepth, g->firstDerivative[d]->op.boundaryDepth);
+      if (g->dissipationOn) {
+        const MgDevOp& dd = g->dissipation[d]->op;
+        depth = std::max(depth, dd.boundaryDepth);
+        if (!g->compositeDissipation) {
+          const MgDevOp& dt = g->dissipationTranspose[d]->op;
+          depth = std::max(depth, std::max(dt.boundaryDepth + dd.boundaryWidth, g->firstDerivative[d]->op.normDepth));
+        }
+      }
+      const int n = g->localSize[d];
+      if (n > TX && n % TX != 0 && n - TX < depth) return 0;
+      if (depth > TX) return 0;
+    } else if (g->localSize[d] < TX) {
+      // a periodic line shorter than the tile would have to wrap inside the tile: general path
       return 0;
     }
   return 1;

@@ -193,3 +193,38 @@ def test_async_transfers_match_blocking_ones():
     assert np.array_equal(out2, st.conservedVariables)
     assert not np.array_equal(out2, q0)
     st.checkpointClear()
+
+
+def test_short_periodic_lines_take_the_general_path():
+    """A periodic in-plane direction shorter than the 16-point tile cannot wrap inside the tile: the fused
+    sweeps must decline it (and the general path must still match the oracle)."""
+    import magudi_b200 as mb
+    from oracle import rhs as orhs
+    g, opt, s, rng = oracle_case((16, 15), (True, True), False, True, False, "SBP 3-6")
+    gg, o, st = gpu_case_from_oracle(g, opt, s)
+    region = mb.Region()
+    region.addState(st)
+    assert not region.usesFused(mb.FORWARD) and not region.usesFused(mb.ADJOINT)
+    s.update(g, opt)
+    st.update()
+    orhs.computeRhs(orhs.FORWARD, opt, g, s)
+    region.computeRhs(mb.FORWARD)
+    assert relerr(st.rightHandSide, s.rightHandSide) <= TOL_RHS
+
+
+def test_lines_whose_last_tile_would_split_the_left_closure_take_the_general_path():
+    """n = 22 with SBP 3-6 closures: the far-boundary-anchored last tile would own points of the left closure
+    region without holding its block, so the fused sweeps must decline the grid."""
+    import magudi_b200 as mb
+    from oracle import rhs as orhs
+    g, opt, s, rng = oracle_case((22, 21), (False, False), True, True, False, "SBP 3-6")
+    gg, o, st = gpu_case_from_oracle(g, opt, s)
+    region = mb.Region()
+    region.addState(st)
+    assert not region.usesFused(mb.FORWARD) and not region.usesFused(mb.ADJOINT)
+    s.update(g, opt)
+    st.update()
+    for mode, omode in ((mb.FORWARD, orhs.FORWARD), (mb.ADJOINT, orhs.ADJOINT)):
+        orhs.computeRhs(omode, opt, g, s)
+        region.computeRhs(mode)
+        assert relerr(st.rightHandSide, s.rightHandSide) <= TOL_RHS
