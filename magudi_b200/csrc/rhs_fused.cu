@@ -1512,7 +1512,8 @@ int fill_args(mg_state* s, FusedArgs* a) {
   }
   a->composite = (g->compositeDissipation || !g->dissipationOn) ? 1 : 0;
   a->pp = s->phys();
-  static const int pf = getenv("MG_PREFETCH") ? atoi(getenv("MG_PREFETCH")) : 2;
+  // L2 prefetch distance in planes (measured on B200: 1 is best for sweeps A and B, 2 for the dissipation sweep)
+  static const int pf = getenv("MG_PREFETCH") ? atoi(getenv("MG_PREFETCH")) : 1;
   a->prefetch = pf;
   a->dissAmount = s->opt.dissipationAmount;
   a->m = g->metrics.comp(0);
@@ -1755,6 +1756,7 @@ int mg_fused_dissipation(mg_state* s) {
   MG_TRY(upload_ops(s, 0, &a));
   a.Q = s->Q[s->cur].comp(0);
   a.diss = s->dissTerm.comp(0);
+  if (!getenv("MG_PREFETCH")) a.prefetch = 2;
   SchemeInfo si;
   scheme_of(g, &si);
   {  // dissipation sweep streams
