@@ -1529,9 +1529,13 @@ struct PfList {
   void addIn(const double* base, int n) { if (base) for (int c = 0; c < n; ++c) in.push_back(base + (size_t)c * cs); }
   void addOut(const double* base, int n) { if (base) for (int c = 0; c < n; ++c) out.push_back(base + (size_t)c * cs); }
   void finish(FusedArgs* a) {
+    // MG_PF_MASK (tuning): bit 0 = prefetch the arriving-plane streams, bit 1 = the output-plane streams
+    static const int mask = getenv("MG_PF_MASK") ? atoi(getenv("MG_PF_MASK")) : 3;
     a->pfIn = a->pfAll = 0;
-    for (const double* p : in) if (a->pfAll < MG_PF_MAX) { a->pf[a->pfAll++] = p; a->pfIn = a->pfAll; }
-    for (const double* p : out) if (a->pfAll < MG_PF_MAX) a->pf[a->pfAll++] = p;
+    if (mask & 1)
+      for (const double* p : in) if (a->pfAll < MG_PF_MAX) { a->pf[a->pfAll++] = p; a->pfIn = a->pfAll; }
+    if (mask & 2)
+      for (const double* p : out) if (a->pfAll < MG_PF_MAX) a->pf[a->pfAll++] = p;
   }
 };
 
