@@ -346,10 +346,10 @@ def run_native(args):
             state.setFromPointerAsync(core.Q_ADJOINT, hW.data_ptr())
             update_state()
             tt_ = forward_step(0.0, k)
+            core.transferFence()             # w must have landed before the adjoint march (fence BEFORE the D2H)
             # result 1 (final forward state): kept as a zero-copy slot and read back while the adjoint runs
             state.checkpointStore(4)
             state.checkpointGetToPointerAsync(4, oQ.data_ptr())
-            core.transferFence()
             if do_adjoint:
                 tt_ = adjoint_step(tt_, k)
             # result 2 (adjoint variables)
