@@ -61,6 +61,8 @@ enum {
   MG_Q_FUSED_TAUQ = 13, MG_Q_FUSED_DISSIPATION = 14,
   /* direction-3 block of the adjoint diffusion written by the first fused adjoint sweep (nU-1 comps) */
   MG_Q_FUSED_ADJOINT_DIFFUSION3 = 15,
+  /* mean pressure of the acoustic-noise functional (t_AcousticNoise data_, src/AcousticNoiseImpl.f90:60-121) */
+  MG_Q_MEAN_PRESSURE = 16,
   MG_G_COORDINATES = 100, MG_G_METRICS = 101, MG_G_JACOBIAN = 102, MG_G_NORM = 103,
   MG_G_ARC_LENGTHS = 104, MG_G_TARGET_MOLLIFIER = 105, MG_G_CONTROL_MOLLIFIER = 106
 };
@@ -164,6 +166,19 @@ int mg_p2p_connect(mg_p2p* h, int side, const void* peerHandle, int sameAsOther)
 int mg_p2p_exchange(mg_p2p* h, void* owner, int field, int width);
 int mg_p2p_check(mg_p2p* h);
 int mg_p2p_destroy(mg_p2p* h);
+
+/* ------------------------------------------------------------------ functionals / sensitivities
+ * computeQuadratureOnPatches: src/PatchFactoryImpl.f90:376-444 (mask of the patches of one type, iblank, norm);
+ * t_AcousticNoise%compute / %computeAdjointForcing: src/AcousticNoiseImpl.f90:123-280 (needs MG_Q_MEAN_PRESSURE
+ * and MG_G_TARGET_MOLLIFIER; the forcing fills "adjointForcing" of every COST_TARGET patch);
+ * t_ThermalActuator%computeSensitivity / %updateGradient: src/ThermalActuatorImpl.f90:83-159, 383-443
+ * (needs MG_G_CONTROL_MOLLIFIER; the gradient sample w_E * mollifier at the patch points, patch order).
+ * Values are the LOCAL sums (the caller reduces across ranks); patch type ids as in mg_patch_create. */
+int mg_functional_quadrature_on_patches(mg_state* s, int patchType, const double* integrand, double* value);
+int mg_functional_acoustic_noise(mg_state* s, double timeRampFactor, double* value);
+int mg_functional_acoustic_noise_forcing(mg_state* s, double timeRampFactor);
+int mg_functional_actuator_sensitivity(mg_state* s, double timeRampFactor, double* value);
+int mg_functional_actuator_gradient(mg_patch* p, double timeRampFactor, double* hostOut);
 
 /* ------------------------------------------------------------------ t_State */
 /* %setup: src/StateImpl.f90:71-170 */

@@ -74,6 +74,11 @@ SIGNATURES = {
     "mg_grid_operator": (_P, [_P, C.c_int, C.c_int]),
     "mg_halo_pack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "mg_halo_unpack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "mg_functional_quadrature_on_patches": (C.c_int, [_P, C.c_int, _P, _D]),
+    "mg_functional_acoustic_noise": (C.c_int, [_P, C.c_double, _D]),
+    "mg_functional_acoustic_noise_forcing": (C.c_int, [_P, C.c_double]),
+    "mg_functional_actuator_sensitivity": (C.c_int, [_P, C.c_double, _D]),
+    "mg_functional_actuator_gradient": (C.c_int, [_P, C.c_double, _P]),
     "mg_p2p_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "mg_p2p_handle_size": (C.c_int, []),
     "mg_p2p_get_handle": (C.c_int, [_P, _P]),

@@ -24,6 +24,7 @@ Q_CONSERVED, Q_ADJOINT, Q_TARGET, Q_RHS = 0, 1, 2, 3
 Q_SPECIFIC_VOLUME, Q_VELOCITY, Q_PRESSURE, Q_TEMPERATURE = 4, 5, 6, 7
 Q_DYNAMIC_VISCOSITY, Q_SECOND_VISCOSITY, Q_THERMAL_DIFFUSIVITY, Q_STRESS_TENSOR, Q_HEAT_FLUX = 8, 9, 10, 11, 12
 Q_FUSED_TAUQ, Q_FUSED_DISSIPATION, Q_FUSED_ADJOINT_DIFFUSION3 = 13, 14, 15
+Q_MEAN_PRESSURE = 16
 G_COORDINATES, G_METRICS, G_JACOBIAN, G_NORM, G_ARC_LENGTHS = 100, 101, 102, 103, 104
 G_TARGET_MOLLIFIER, G_CONTROL_MOLLIFIER = 105, 106
 
@@ -310,6 +311,31 @@ class State:
     velocity = property(lambda s: s.get(Q_VELOCITY))
     pressure = property(lambda s: s.get(Q_PRESSURE))
     temperature = property(lambda s: s.get(Q_TEMPERATURE))
+    meanPressure = property(lambda s: s.get(Q_MEAN_PRESSURE), lambda s, v: s.set(Q_MEAN_PRESSURE, v))
+
+    # ---- functionals / sensitivities (local sums; see include/magudi_gpu.h)
+    def computeQuadratureOnPatches(self, patchType, integrand):
+        """``computeQuadratureOnPatches`` (reference ``src/PatchFactoryImpl.f90:376-444``)."""
+        f = L.as_f(np.asarray(integrand, dtype=np.float64).reshape(self.grid.nGridPoints, 1, order="F"))
+        r = C.c_double(0.0)
+        check(L.lib().mg_functional_quadrature_on_patches(self._h, PATCH_TYPES[patchType], L.fptr(f), C.byref(r)))
+        return r.value
+
+    def computeAcousticNoise(self, timeRampFactor=1.0):
+        """``t_AcousticNoise%compute`` (``src/AcousticNoiseImpl.f90:123-206``)."""
+        r = C.c_double(0.0)
+        check(L.lib().mg_functional_acoustic_noise(self._h, float(timeRampFactor), C.byref(r)))
+        return r.value
+
+    def computeAcousticNoiseAdjointForcing(self, timeRampFactor=1.0):
+        """``t_AcousticNoise%computeAdjointForcing`` (``:208-280``): fills every COST_TARGET patch."""
+        check(L.lib().mg_functional_acoustic_noise_forcing(self._h, float(timeRampFactor)))
+
+    def computeThermalActuatorSensitivity(self, timeRampFactor=1.0):
+        """``t_ThermalActuator%computeSensitivity`` (``src/ThermalActuatorImpl.f90:83-159``)."""
+        r = C.c_double(0.0)
+        check(L.lib().mg_functional_actuator_sensitivity(self._h, float(timeRampFactor), C.byref(r)))
+        return r.value
     specificVolume = property(lambda s: s.get(Q_SPECIFIC_VOLUME))
     stressTensor = property(lambda s: s.get(Q_STRESS_TENSOR))
     heatFlux = property(lambda s: s.get(Q_HEAT_FLUX))
@@ -397,6 +423,13 @@ class Patch:
 
     def collect(self, field, name):
         check(L.lib().mg_patch_collect(self._h, field, name.encode()))
+
+    def thermalActuatorGradient(self, timeRampFactor=1.0):
+        """One gradient sample ``w_E * controlMollifier`` at the patch points
+        (``t_ThermalActuator%updateGradient``, ``src/ThermalActuatorImpl.f90:383-443``)."""
+        out = np.zeros(max(self.nPatchPoints, 0))
+        check(L.lib().mg_functional_actuator_gradient(self._h, float(timeRampFactor), out.ctypes.data_as(C.c_void_p)))
+        return out
 
 
 class Region:

@@ -376,6 +376,9 @@ static MgField* state_field(mg_state* s, int field) {
     case MG_Q_THERMAL_DIFFUSIVITY: return &s->kappa;
     case MG_Q_STRESS_TENSOR: return &s->stressTensor;
     case MG_Q_HEAT_FLUX: return &s->heatFlux;
+    case MG_Q_MEAN_PRESSURE:
+      if (!s->meanPressure.p && mg_field_alloc(s->grid, 1, &s->meanPressure) != 0) return nullptr;
+      return &s->meanPressure;
     case MG_Q_FUSED_TAUQ: return &s->tauq;
     case MG_Q_FUSED_DISSIPATION:
       if (s->fusedValid && !s->dissValid) mg_fused_dissipation(s);
@@ -576,6 +579,38 @@ int mg_patch_collect(mg_patch* p, int field, const char* name) {
   if (!f) f = grid_field(p->state->grid, field, &nc, false);
   if (!f || !f->p) MG_FAIL("mg_patch_collect: unknown or unallocated field");
   return mg_patch_collect_impl(p, f, f->nComp, name);
+}
+
+// ------------------------------------------------------------------------------ functionals
+int mg_functional_quadrature_on_patches(mg_state* s, int patchType, const double* integrand, double* value) {
+  if (!s || !integrand || !value) MG_FAIL("mg_functional_quadrature_on_patches: null argument");
+  // the integrand may live on the host: stage it on the device
+  cudaPointerAttributes at;
+  const bool onDevice = cudaPointerGetAttributes(&at, integrand) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+  cudaGetLastError();
+  if (onDevice) return mg_functional_quadrature_impl(s, patchType, integrand, value);
+  double* d = nullptr;
+  MG_CUDA(cudaMalloc(&d, s->grid->N * sizeof(double)));
+  cudaMemcpyAsync(d, integrand, s->grid->N * sizeof(double), cudaMemcpyHostToDevice, g_stream);
+  const int rc = mg_functional_quadrature_impl(s, patchType, d, value);
+  cudaFree(d);
+  return rc;
+}
+int mg_functional_acoustic_noise(mg_state* s, double timeRampFactor, double* value) {
+  if (!s || !value) MG_FAIL("mg_functional_acoustic_noise: null argument");
+  return mg_functional_acoustic_noise_impl(s, timeRampFactor, value);
+}
+int mg_functional_acoustic_noise_forcing(mg_state* s, double timeRampFactor) {
+  if (!s) MG_FAIL("mg_functional_acoustic_noise_forcing: null handle");
+  return mg_functional_acoustic_noise_forcing_impl(s, timeRampFactor);
+}
+int mg_functional_actuator_sensitivity(mg_state* s, double timeRampFactor, double* value) {
+  if (!s || !value) MG_FAIL("mg_functional_actuator_sensitivity: null argument");
+  return mg_functional_actuator_sensitivity_impl(s, timeRampFactor, value);
+}
+int mg_functional_actuator_gradient(mg_patch* p, double timeRampFactor, double* hostOut) {
+  if (!p || !hostOut) MG_FAIL("mg_functional_actuator_gradient: null argument");
+  return mg_functional_actuator_gradient_impl(p, timeRampFactor, hostOut);
 }
 
 // ------------------------------------------------------------------------------ region

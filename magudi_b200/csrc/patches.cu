@@ -649,3 +649,185 @@ int mg_patches_apply(mg_state* s, int mode) {
   }
   return 0;
 }
+
+// ------------------------------------------------------------------- functionals
+// computeQuadratureOnPatches (reference src/PatchFactoryImpl.f90:376-444), computeAcousticNoise and its adjoint
+// forcing (src/AcousticNoiseImpl.f90:123-280), computeThermalActuatorSensitivity / gradient sample
+// (src/ThermalActuatorImpl.f90:83-159, 383-443).  The reduction is deterministic: fixed grid, per-block partial
+// sums, summed on the host in block order.
+namespace {
+
+constexpr int QUAD_BLOCKS = 592, QUAD_THREADS = 256, QUAD_MAX_PATCHES = 16;
+
+struct QuadArgs {
+  int lo[QUAD_MAX_PATCHES][3], hi[QUAD_MAX_PATCHES][3];   // local boxes [lo, hi) of the patches of the wanted type
+  int nPatches;
+  int nx, ny;
+  size_t N;
+  const int* iblank;
+  const double *norm, *a, *b, *w;
+  int kind;          // 0: a        1: (a - b)^2 w   (acoustic noise)        2: (a w)^2   (thermal actuator)
+  double* partial;
+};
+
+__global__ void __launch_bounds__(QUAD_THREADS) k_quadrature(QuadArgs q) {
+  __shared__ double red[QUAD_THREADS];
+  double acc = 0.0;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < q.N; p += (size_t)gridDim.x * blockDim.x) {
+    if (q.iblank && q.iblank[p] == 0) continue;
+    const int i = (int)(p % q.nx), j = (int)((p / q.nx) % q.ny), k = (int)(p / ((size_t)q.nx * q.ny));
+    bool in = false;
+    for (int l = 0; l < q.nPatches && !in; ++l)
+      in = i >= q.lo[l][0] && i < q.hi[l][0] && j >= q.lo[l][1] && j < q.hi[l][1] && k >= q.lo[l][2] && k < q.hi[l][2];
+    if (!in) continue;
+    double v;
+    if (q.kind == 0) v = q.a[p];
+    else if (q.kind == 1) { const double d = q.a[p] - q.b[p]; v = d * d * q.w[p]; }
+    else { const double d = q.a[p] * q.w[p]; v = d * d; }
+    acc += q.norm[p] * v;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = QUAD_THREADS / 2; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) q.partial[blockIdx.x] = red[0];
+}
+
+int quadrature(mg_state* s, int patchType, int kind, const double* a, const double* b, const double* w, double* value) {
+  mg_grid* g = s->grid;
+  QuadArgs q;
+  std::memset(&q, 0, sizeof(q));
+  for (mg_patch* p : s->patches) {
+    if (p->type != patchType || p->nPatchPoints <= 0) continue;
+    if (q.nPatches >= QUAD_MAX_PATCHES) MG_FAIL("quadrature on patches: too many patches of one type");
+    for (int d = 0; d < 3; ++d) { q.lo[q.nPatches][d] = p->localLo[d]; q.hi[q.nPatches][d] = p->localLo[d] + p->localSize[d]; }
+    ++q.nPatches;
+  }
+  *value = 0.0;
+  if (q.nPatches == 0) return 0;
+  q.nx = g->localSize[0];
+  q.ny = g->localSize[1];
+  q.N = g->N;
+  q.iblank = g->iblank;
+  q.norm = g->norm.comp(0);
+  q.a = a; q.b = b; q.w = w; q.kind = kind;
+  static double* partial = nullptr;
+  if (!partial) MG_CUDA(cudaMalloc(&partial, QUAD_BLOCKS * sizeof(double)));
+  q.partial = partial;
+  k_quadrature<<<QUAD_BLOCKS, QUAD_THREADS, 0, mg_stream()>>>(q);
+  MG_CUDA(cudaGetLastError());
+  double host[QUAD_BLOCKS];
+  MG_CUDA(cudaMemcpyAsync(host, partial, sizeof(host), cudaMemcpyDeviceToHost, mg_stream()));
+  MG_CUDA(cudaStreamSynchronize(mg_stream()));
+  double sum = 0.0;
+  for (int i = 0; i < QUAD_BLOCKS; ++i) sum += host[i];
+  *value = sum;
+  return 0;
+}
+
+struct ForcingArgs {
+  PatchGeom g;
+  const int* iblank;
+  const double *pressure, *meanPressure, *mollifier, *u;
+  size_t csU;
+  int nD;
+  double gamma, ramp;
+  double* out;       // adjointForcing (nPatchPoints, nU), point fastest
+};
+
+__global__ void k_noise_forcing(ForcingArgs a) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.g.n) return;
+  const size_t p = a.g.gridIndex(q);
+  if (a.iblank && a.iblank[p] == 0) return;
+  const double F = -2.0 * a.mollifier[p] * a.ramp * (a.gamma - 1.0) * (a.pressure[p] - a.meanPressure[p]);
+  double usq = 0.0;
+  for (int d = 0; d < a.nD; ++d) {
+    const double ud = a.u[(size_t)d * a.csU + p];
+    a.out[(size_t)(d + 1) * a.g.n + q] = -ud * F;
+    usq += ud * ud;
+  }
+  a.out[(size_t)(a.nD + 1) * a.g.n + q] = F;
+  a.out[q] = 0.5 * usq * F;
+}
+
+__global__ void k_actuator_gradient(PatchGeom g, const double* wE, const double* mollifier, double ramp, double* out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= g.n) return;
+  const size_t p = g.gridIndex(q);
+  out[q] = wE[p] * (mollifier[p] * ramp);
+}
+
+}  // namespace
+
+int mg_functional_quadrature_impl(mg_state* s, int patchType, const double* integrandDevice, double* value) {
+  return quadrature(s, patchType, 0, integrandDevice, nullptr, nullptr, value);
+}
+
+int mg_functional_acoustic_noise_impl(mg_state* s, double timeRampFactor, double* value) {
+  mg_grid* g = s->grid;
+  if (!s->meanPressure.p) MG_FAIL("acoustic noise: the mean pressure has not been set");
+  if (!g->targetMollifier.p) MG_FAIL("acoustic noise: the target mollifier has not been set");
+  if (!s->dependentValid) MG_TRY(mg_state_update_impl(s, nullptr));
+  MG_TRY(quadrature(s, MG_PATCH_COST_TARGET, 1, s->pressure.comp(0), s->meanPressure.comp(0),
+                    g->targetMollifier.comp(0), value));
+  *value *= timeRampFactor;
+  return 0;
+}
+
+int mg_functional_acoustic_noise_forcing_impl(mg_state* s, double timeRampFactor) {
+  mg_grid* g = s->grid;
+  if (!s->meanPressure.p) MG_FAIL("acoustic noise: the mean pressure has not been set");
+  if (!g->targetMollifier.p) MG_FAIL("acoustic noise: the target mollifier has not been set");
+  if (!s->dependentValid) MG_TRY(mg_state_update_impl(s, nullptr));
+  for (mg_patch* p : s->patches) {
+    if (p->type != MG_PATCH_COST_TARGET || p->nPatchPoints <= 0) continue;
+    double* out = nullptr;
+    auto it = p->arrays.find("adjointForcing");
+    if (it == p->arrays.end()) MG_TRY(mg_patch_alloc_array(p, "adjointForcing", s->nU, &out));
+    else out = it->second.p;
+    ForcingArgs a;
+    a.g = geom(p);
+    a.iblank = g->iblank;
+    a.pressure = s->pressure.comp(0);
+    a.meanPressure = s->meanPressure.comp(0);
+    a.mollifier = g->targetMollifier.comp(0);
+    a.u = s->velocity.comp(0);
+    a.csU = s->velocity.compStride;
+    a.nD = s->nD;
+    a.gamma = s->opt.ratioOfSpecificHeats;
+    a.ramp = timeRampFactor;
+    a.out = out;
+    k_noise_forcing<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a);
+    MG_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int mg_functional_actuator_sensitivity_impl(mg_state* s, double timeRampFactor, double* value) {
+  mg_grid* g = s->grid;
+  if (!g->controlMollifier.p) MG_FAIL("thermal actuator: the control mollifier has not been set");
+  MG_TRY(quadrature(s, MG_PATCH_ACTUATOR, 2, s->W[s->curW].comp(s->nD + 1), nullptr, g->controlMollifier.comp(0), value));
+  *value *= timeRampFactor * timeRampFactor;
+  return 0;
+}
+
+int mg_functional_actuator_gradient_impl(mg_patch* p, double timeRampFactor, double* hostOut) {
+  mg_state* s = p->state;
+  mg_grid* g = s->grid;
+  if (p->type != MG_PATCH_ACTUATOR) MG_FAIL("thermal actuator gradient: not an ACTUATOR patch");
+  if (!g->controlMollifier.p) MG_FAIL("thermal actuator: the control mollifier has not been set");
+  if (p->nPatchPoints <= 0) return 0;
+  double* out = nullptr;
+  auto it = p->arrays.find("gradient");
+  if (it == p->arrays.end()) MG_TRY(mg_patch_alloc_array(p, "gradient", 1, &out));
+  else out = it->second.p;
+  k_actuator_gradient<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), s->W[s->curW].comp(s->nD + 1),
+                                                                      g->controlMollifier.comp(0), timeRampFactor, out);
+  MG_CUDA(cudaGetLastError());
+  MG_CUDA(cudaMemcpyAsync(hostOut, out, (size_t)p->nPatchPoints * sizeof(double), cudaMemcpyDeviceToHost, mg_stream()));
+  MG_CUDA(cudaStreamSynchronize(mg_stream()));
+  return 0;
+}

@@ -41,3 +41,10 @@ int mg_patch_get_array_impl(mg_patch* p, const char* name, int nComp, double* ho
 int mg_patch_collect_impl(mg_patch* p, const MgField* f, int nComp, const char* name);
 int mg_patch_disperse_impl(mg_patch* p, const char* name, int nComp, MgField* f);
 int mg_patches_update_impl(mg_state* s);
+
+// functionals
+int mg_functional_quadrature_impl(mg_state* s, int patchType, const double* integrandDevice, double* value);
+int mg_functional_acoustic_noise_impl(mg_state* s, double timeRampFactor, double* value);
+int mg_functional_acoustic_noise_forcing_impl(mg_state* s, double timeRampFactor);
+int mg_functional_actuator_sensitivity_impl(mg_state* s, double timeRampFactor, double* value);
+int mg_functional_actuator_gradient_impl(mg_patch* p, double timeRampFactor, double* hostOut);
