@@ -1335,6 +1335,25 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint2(FusedArgs a) {
         }
       }
     }
+    // inputs of the output plane p = s - RK: issued before the barrier so that their latency overlaps the
+    // in-plane derivative of the arriving plane
+    const int p = s - RK;
+    const bool emitNow = p >= kc0 && mine;
+    const long off = ((ND == 3) ? (long)kp * a.plane : 0) + pij;
+    double jac = 0.0, rp[NU], vb1[NU], vb2[NU], Q[NU];
+    if (emitNow) {
+      jac = __ldg(a.jac + off);
+#pragma unroll
+      for (int c = 0; c < NU; ++c) {
+        const size_t qi = (size_t)c * a.cs + off;
+        rp[c] = a.rhsIn[qi];
+        if (a.viscous) Q[c] = __ldg(a.Q + qi);
+        if (a.fuseRk) {
+          vb1[c] = (a.stage == 1) ? a.Win[qi] : ((a.stage == 4) ? 0.0 : a.b1in[qi]);
+          vb2[c] = (a.stage == 1) ? 0.0 : a.b2[qi];
+        }
+      }
+    }
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < RK; ++q)
@@ -1363,21 +1382,7 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint2(FusedArgs a) {
         rxy[RK][c] = r;
       }
     }
-    const int p = s - RK;
-    if (p >= kc0 && mine) {
-      const long off = ((ND == 3) ? (long)kp * a.plane : 0) + pij;
-      const double jac = __ldg(a.jac + off);
-      double rp[NU], vb1[NU], vb2[NU], Q[NU];
-#pragma unroll
-      for (int c = 0; c < NU; ++c) {
-        const size_t qi = (size_t)c * a.cs + off;
-        rp[c] = a.rhsIn[qi];
-        if (a.viscous) Q[c] = __ldg(a.Q + qi);
-        if (a.fuseRk) {
-          vb1[c] = (a.stage == 1) ? a.Win[qi] : ((a.stage == 4) ? 0.0 : a.b1in[qi]);
-          vb2[c] = (a.stage == 1) ? 0.0 : a.b2[qi];
-        }
-      }
+    if (emitNow) {
       if (a.viscous) {
         double t[NG];
 #pragma unroll
