@@ -780,10 +780,11 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
       for (int c = 0; c < NU; ++c) f3c[((size_t)q * NU + c) * NT] = 0.0;
   }
   // output of plane p (storage plane kpl, queue slot sp): x 1/J, dissipation, RK4 substep
-  auto emit = [&](int kpl, int sp, const double* extra) {
+  // inputs of the output plane (loaded at the top of an iteration, consumed by emit)
+  double ejac = 0.0, dss[NU], vb1[NU], vb2[NU];
+  auto emit_load = [&](int kpl) {
     const long off = ((ND == 3) ? (long)kpl * a.plane : 0) + pij;
-    const double jac = __ldg(a.jac + off);
-    double dss[NU], vb1[NU], vb2[NU];
+    ejac = __ldg(a.jac + off);
 #pragma unroll
     for (int c = 0; c < NU; ++c) {
       const size_t qi = (size_t)c * a.cs + off;
@@ -793,6 +794,10 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
         vb2[c] = (a.stage == 1) ? 0.0 : a.b2[qi];
       }
     }
+  };
+  auto emit = [&](int kpl, int sp, const double* extra) {
+    const long off = ((ND == 3) ? (long)kpl * a.plane : 0) + pij;
+    const double jac = ejac;
     double r[NU];
 #pragma unroll
     for (int c = 0; c < NU; ++c) {
@@ -822,6 +827,9 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
       if (a.wrapK) { if (kf >= a.nz) kf -= a.nz; if (kq < 0) kq += a.nz; else if (kq >= a.nz) kq -= a.nz; }
       prefetch_streams(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz),
                        (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
+    }
+    if constexpr (ND == 3) {
+      if (s - RK >= kc0 && mine) emit_load(kp);
     }
     // ---- arrival of plane s: own point (loads issued back to back, then the flux evaluation) ...
     double f3[NU];
@@ -915,7 +923,7 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
         }
         f3c[((size_t)slot * NU + c) * NT] += r;
       }
-      if constexpr (ND == 2) emit(0, 0, f3);       // f3 == 0 in 2-D
+      if constexpr (ND == 2) { emit_load(0); emit(0, 0, f3); }       // f3 == 0 in 2-D
     }
     __syncthreads();
     // advance plane bookkeeping
