@@ -1943,7 +1943,7 @@ int fill_args_adjoint(mg_state* s, FusedArgs* a) {
   a->Win = s->W[s->curW].comp(0);
   a->tauqIn = s->opt.viscosityOn ? s->tauq.comp(0) : nullptr;
   a->dissOn = s->opt.dissipationOn;
-  // measured on B200: the adjoint sweeps run faster without the L2 prefetch (their loads are already batched)
+  // measured on B200: adjoint sweep 1 runs faster without the L2 prefetch (sweep 2 overrides this with 1)
   static const int pfAdj = getenv("MG_PREFETCH_ADJ") ? atoi(getenv("MG_PREFETCH_ADJ")) : 0;
   a->prefetch = pfAdj;
   MG_TRY(upload_ops(s, 1, a));
@@ -2012,6 +2012,7 @@ int mg_fused_adjoint2(mg_state* s, int fuseRk, int stage, double dt) {
   a.rhsIn = s->rhs.comp(0);
   a.rhs = s->rhs.comp(0);
   a.diffIn = g->scratchA.comp(0);
+  if (!getenv("MG_PREFETCH_ADJ")) a.prefetch = 1;   // measured: distance 1 helps this sweep, none helps sweep 1
   a.fuseRk = fuseRk;
   const int rkStage = 5 - stage;        // adjoint stage 4 plays the role of RK stage 1, ...
   a.stage = rkStage;
