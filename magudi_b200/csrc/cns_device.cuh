@@ -35,14 +35,18 @@ __device__ __forceinline__ void dependent(const double* Q, double gamma, Prim<ND
   s.T = gg1 * s.p * s.v;
 }
 
-// computeTransportVariables (reference :89-177)
+// computeTransportVariables (reference :89-177).  FASTPOW: x^n as exp(n log x) (~2 ulp instead of pow()'s
+// < 1 ulp, at well under half the instructions; T > 0 on every admissible state).  Used where it lowers the
+// register pressure (adjoint sweep 1); sweep A keeps pow(), which allocates better there.
+template <bool FASTPOW = false>
 __device__ __forceinline__ void transport(double T, const PhysParams& pp, double& mu, double& lam, double& kap) {
   if (pp.powerLaw <= 0.0) {
     mu = pp.ReInv;
     lam = (pp.bulkRatio - 2.0 / 3.0) * pp.ReInv;
     kap = pp.ReInv * pp.PrInv;
   } else {
-    mu = pow((pp.gamma - 1.0) * T, pp.powerLaw) * pp.ReInv;
+    if (FASTPOW) mu = exp(pp.powerLaw * log((pp.gamma - 1.0) * T)) * pp.ReInv;
+    else mu = pow((pp.gamma - 1.0) * T, pp.powerLaw) * pp.ReInv;
     lam = (pp.bulkRatio - 2.0 / 3.0) * mu;
     kap = mu * pp.PrInv;
   }

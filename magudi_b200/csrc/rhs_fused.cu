@@ -1140,7 +1140,7 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
       Prim<ND> sp;
       dependent<ND>(Q, a.pp.gamma, sp);
       double mu = 0.0, lam = 0.0, kap = 0.0;
-      if (a.viscous) transport(sp.T, a.pp, mu, lam, kap);
+      if (a.viscous) transport<true>(sp.T, a.pp, mu, lam, kap);
       // adjoint first derivative of w along direction d at this point (tile for xi/eta, queue for zeta)
       auto deriv = [&](auto dI, double* dW) {
         constexpr int d = dI.value;
