@@ -280,14 +280,16 @@ def run_native(args):
             import torch.distributed as dist
             dist.barrier()
 
+    # clocks / throttle reasons are sampled from the first warm-up step to the end of the timed region (the load is
+    # the same in both; the timed region alone is shorter than nvidia-smi's start-up at small step counts)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     t = 0.0
     for w in range(args.warmup):
         t = one_step(t, w)
     barrier()
 
     # ---- timed region: device time with CUDA events on the launching stream
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     lib.mg_profile_enable(1)
     launches0 = lib.mg_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -306,7 +308,6 @@ def run_native(args):
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
     total_ms = e0.elapsed_time(e1)
     fwd_ms = sum(es[k].elapsed_time(ef[k]) for k in range(args.steps))
     adj_ms = sum(ef[k].elapsed_time(ea[k]) for k in range(args.steps))
@@ -319,6 +320,21 @@ def run_native(args):
         if n.value:
             prof[name] = {"ms": ms.value, "launches": n.value, "avg_ms": ms.value / n.value}
     lib.mg_profile_enable(0)
+    # Clock sampling: nvidia-smi may not have reported yet when the timed region is short.  Rank 0 decides how many
+    # identical, untimed steps to append (same count on every rank: the halo exchange is collective).
+    extra = 0
+    if len(sampler.rows) < 3:
+        extra = max(1, int(np.ceil(1.0 / max(wall / args.steps, 1e-3))))
+    if world > 1:
+        import torch.distributed as dist
+        ex = torch.tensor([extra], dtype=torch.int64, device=dev)
+        dist.broadcast(ex, 0)
+        extra = int(ex.item())
+    for k in range(extra):
+        t = one_step(t, args.warmup + args.steps + k)
+    barrier()
+    clocks = sampler.stop()
+    clocks["window"] = "warm-up + timed steps" + (f" + {extra} identical untimed steps" if extra else "")
 
     # max over ranks
     if world > 1:
