@@ -434,7 +434,7 @@ def run_native(args):
                    "evals_per_point_per_step": evals_per_point,
                    "forward_path": "fused sweeps A + dissipation + B" if fused_fwd else "general",
                    "adjoint_path": ("fused adjoint sweeps 1+2 (+ sweep A on the restored state)" if fused_adj else "general operator-by-operator") if do_adjoint else "not run (multi-rank adjoint needs the fused adjoint)",
-                   "parallelism": f"slab decomposition along k over {world} GPU(s)",
+                   "parallelism": f"slab decomposition along k over {world} GPU(s)" + (f", halo exchange: {halo.mode}" if halo else ""),
                    "l2_policy": "inputs larger than L2 (every field >= 134 MB per component set)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "roofline_path": path, "kernels": prof, "cpu_baseline": cpu,

@@ -95,8 +95,19 @@ class GpuHalo:
         self.plane = grid.localSize[0] * grid.localSize[1]
         self._p2p = None
         if self.mode == "p2p" and world > 1:
-            self._setup_p2p(periodic, device)
-        else:
+            ok = 1
+            try:
+                self._setup_p2p(periodic, device)
+            except Exception as exc:          # e.g. no peer access between the GPUs of this box
+                ok, self._p2p_error = 0, exc
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)       # every rank takes the same path
+            if int(flag.item()) == 0:
+                if self._p2p is not None:
+                    check(L.lib().mg_p2p_destroy(self._p2p))
+                self._p2p = None
+                self.mode = "nccl"
+        if self._p2p is None:
             self.mode = "nccl"
             # the library stream is made torch's current stream during an exchange: no host synchronisation
             stream = torch.cuda.ExternalStream(L.lib().mg_stream_handle(), device=device)
@@ -124,7 +135,6 @@ class GpuHalo:
             self._keep.append(hb)
             same = 1 if (side == 1 and prev is not None and prev == nxt) else 0
             check(lib.mg_p2p_connect(h, side, hb, same))
-        dist.barrier()
 
     def exchange(self, owner, field, ncomp, width=3):
         lib = L.lib()
