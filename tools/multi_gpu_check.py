@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run under torchrun (N ranks = N GPUs): slab-decomposed fused forward RK4 steps must reproduce the
+"""Run under torchrun (N ranks = N GPUs): slab-decomposed fused forward RK4 steps and one fused adjoint RK4 step must reproduce the
 single-GPU result of the same global problem.  Used by tests/test_gpu_multi.py and by hand:
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
 """
@@ -46,9 +46,23 @@ def run(shape, world, rank, dev, steps=2):
         for stage in range(1, 5):
             t = integ.substepForward(t, 1e-3, step, stage, updateStates=False)
             update()
+    # one adjoint RK4 step about the final forward state (fused adjoint sweeps, two-phase substep around the
+    # exchange of the k-block of the adjoint diffusion), same global adjoint field whatever the decomposition
+    Wg = np.random.default_rng(99).random(tuple(grid.globalSize) + (5,))
+    state.adjointVariables = Wg[:, :, k0:k0 + nz].reshape(-1, 5, order="F")
+    assert region.usesFused(mb.ADJOINT)
+    for stage in range(4, 0, -1):
+        update()
+        if halo:
+            halo.exchange(state, core.Q_ADJOINT, 5, R)
+            integ.substepAdjointPhase(1, t, 1e-3, steps, stage)
+            halo.exchange(state, core.Q_FUSED_ADJOINT_DIFFUSION3, 4, R)
+            t = integ.substepAdjointPhase(2, t, 1e-3, steps, stage)
+        else:
+            t = integ.substepAdjoint(t, 1e-3, steps, stage)
     if halo:
         halo.check()
-    return state.conservedVariables, grid
+    return np.concatenate([state.conservedVariables, state.adjointVariables], axis=1), grid
 
 
 def main():
@@ -68,11 +82,13 @@ def main():
         dist.all_gather_object(pieces, (grid.offset[2], grid.localSize[2], Ql))
         if rank == 0:
             Qs, _ = run(shape, 1, 0, dev)
-            Qs = Qs.reshape(tuple(shape) + (5,), order="F")
+            Qs = Qs.reshape(tuple(shape) + (10,), order="F")
             err = 0.0
             for k0, nz, q in pieces:
-                q = q.reshape((shape[0], shape[1], nz, 5), order="F")
-                err = max(err, float(np.max(np.abs(q - Qs[:, :, k0:k0 + nz])) / np.max(np.abs(Qs))))
+                q = q.reshape((shape[0], shape[1], nz, 10), order="F")
+                ref = Qs[:, :, k0:k0 + nz]
+                for sl in (slice(0, 5), slice(5, 10)):        # conserved variables, adjoint variables
+                    err = max(err, float(np.max(np.abs(q[..., sl] - ref[..., sl])) / np.max(np.abs(Qs[..., sl]))))
             print(f"multi_gpu_check: world={world} max rel diff vs single GPU = {err:.3e}")
             ok = err <= 1e-13
         dist.barrier()
