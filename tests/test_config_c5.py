@@ -1,0 +1,82 @@
+"""BASELINE config C5 — NACA0012-style O-grid (reference examples/NACA0012/magudi.inp:34-49, bc.dat): curvilinear
+body-fitted grid whose direction 1 is OVERLAP-periodic (first and last grid lines coincide), SBP 2-4, inviscid,
+non-composite dissipation 0.012, slip-wall SAT on the body (j = 1), far-field SAT + sponge on the outer boundary.
+An ellipse stands in for the airfoil (the reference's grid generator is not part of the hot path).  Metrics,
+forward and adjoint RHS on the CUDA path (general path: OVERLAP + patches) must match the oracle."""
+import numpy as np
+import pytest
+
+from helpers import gpu_case_from_oracle, relerr, relerr_global, random_state
+
+pytestmark = pytest.mark.gpu
+
+
+def build_case(ni=65, nj=40):
+    from oracle import grid as og
+    from oracle import patches as op
+    from oracle import rhs as orhs
+    g = og.Grid((ni, nj), (og.OVERLAP, og.NONE), (0.0, 0.0), isCurvilinear=True)
+    th = np.linspace(2.0 * np.pi, 0.0, ni)              # clockwise (right-handed with r); first and last lines coincide (OVERLAP)
+    r = 1.0 + 4.0 * (np.linspace(0.0, 1.0, nj) ** 1.5)
+    TH, R = np.meshgrid(th, r, indexing="ij")
+    X = R * 1.0 * np.cos(TH)                            # ellipse-like body: semi-axes 1.0 x 0.3 at the wall,
+    Y = (0.3 + (R - 1.0)) * np.sin(TH)                  # relaxing to circles away from it
+    g.coordinates[:, 0] = X.reshape(-1, order="F")
+    g.coordinates[:, 1] = Y.reshape(-1, order="F")
+    opt = orhs.SolverOptions(ratioOfSpecificHeats=1.4, viscosityOn=False, dissipationOn=True,
+                             compositeDissipation=False, dissipationAmount=0.012, useTargetState=True,
+                             discretizationType="SBP 2-4")
+    g.setupSpatialDiscretization("SBP 2-4", False, dissipationOn=True)
+    assert not g.update()
+    s = orhs.State(g, opt)
+    rng = np.random.default_rng(23)
+    N = g.nGridPoints
+    Q = random_state(N, 2, rng)
+    # the state must be single valued on the coincident grid lines i = 1 and i = ni
+    Q3 = Q.reshape((ni, nj, 4), order="F")
+    Q3[-1] = Q3[0]
+    W3 = rng.random((ni, nj, 4))
+    W3[-1] = W3[0]
+    T3 = random_state(N, 2, rng).reshape((ni, nj, 4), order="F")
+    T3[-1] = T3[0]
+    s.conservedVariables[:, :] = Q3.reshape(-1, 4, order="F")
+    s.adjointVariables[:, :] = W3.reshape(-1, 4, order="F")
+    s.targetState[:, :] = T3.reshape(-1, 4, order="F")
+    plist = [op.ImpenetrableWall("airfoil", g, 2, [1, ni, 1, 1, 1, 1], opt, 1.0),
+             op.FarFieldPatch("farField", g, -2, [1, ni, nj, nj, 1, 1], opt, 1.0, 0.0),
+             op.SpongePatch("sponge", g, -2, [1, ni, nj - 13, nj, 1, 1], 0.2, 2)]
+    specs = [("SAT_SLIP_WALL", "airfoil", 2, [1, ni, 1, 1, 1, 1], 1.0, 0.0),
+             ("SAT_FAR_FIELD", "farField", -2, [1, ni, nj, nj, 1, 1], 1.0, 0.0),
+             ("SPONGE", "sponge", -2, [1, ni, nj - 13, nj, 1, 1])]
+    op.computeSpongeStrengths(plist, g)
+    op.updatePatches(plist, opt, g, s)
+    return g, opt, s, plist, specs
+
+
+def test_ogrid_overlap_rhs_forward_and_adjoint(gpu_lib):
+    import magudi_b200 as mb
+    from magudi_b200 import core
+    from oracle import patches as op
+    from oracle import rhs as orhs
+    g, opt, s, plist, specs = build_case()
+    gg, o, st = gpu_case_from_oracle(g, opt, s)
+    assert relerr_global(gg.get(core.G_METRICS), g.metrics) <= 1e-12
+    assert relerr(gg.get(core.G_JACOBIAN), g.jacobian) <= 1e-12
+    region = mb.Region()
+    region.addState(st)
+    for spec in specs:
+        st.addPatch(*spec)
+    for po, pg in zip(plist, st.patches):
+        assert po.nPatchPoints == pg.nPatchPoints
+        if isinstance(po, op.SpongePatch):
+            pg.setArray("spongeStrength", po.spongeStrength)
+    region.updatePatches()
+    assert not region.usesFused(mb.FORWARD)
+    s.update(g, opt)
+    st.update()
+    orhs.computeRhs(orhs.FORWARD, opt, g, s, plist)
+    region.computeRhs(mb.FORWARD)
+    assert relerr(st.rightHandSide, s.rightHandSide) <= 1e-12
+    orhs.computeRhs(orhs.ADJOINT, opt, g, s, plist)
+    region.computeRhs(mb.ADJOINT)
+    assert relerr(st.rightHandSide, s.rightHandSide) <= 1e-12
