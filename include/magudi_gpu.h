@@ -250,6 +250,13 @@ void* mg_stream_handle(void);
  * duration (ms) and launch count of one kernel family ("sweepA", "sweepB", ...); reset with enable */
 int mg_profile_enable(int enable);
 int mg_profile_get(const char* name, double* milliseconds, long long* launches);
+/* tuning switches of the fused sweeps (no reference counterpart): "MG_FWD" (2 = dissipation folded into sweep
+ * B, 1 = separate dissipation sweep), "MG_ADJ1" (2 / 1 = generation of adjoint sweep 1), "MG_BD_TY",
+ * "MG_ADJ1_TY" (tile heights), "MG_CHUNKS" (k-chunks per tile column, 0 = automatic), "MG_PREFETCH",
+ * "MG_PREFETCH_ADJ", "MG_PF_MASK" (L2 prefetch).  A value set here overrides the environment variable of the
+ * same name; mg_tuning_clear() forgets every override. */
+int mg_tuning_set(const char* name, int value);
+int mg_tuning_clear(void);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,8 @@ SIGNATURES = {
     "mg_stream_handle": (C.c_void_p, []),
     "mg_profile_enable": (C.c_int, [C.c_int]),
     "mg_profile_get": (C.c_int, [C.c_char_p, _D, C.POINTER(C.c_longlong)]),
+    "mg_tuning_set": (C.c_int, [C.c_char_p, C.c_int]),
+    "mg_tuning_clear": (C.c_int, []),
     "mg_stencil_create": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "mg_stencil_update": (C.c_int, [_P, C.c_int, _I3, _I3, _I3, C.c_int]),
     "mg_stencil_get_adjoint": (C.c_int, [_P, C.POINTER(_P)]),

@@ -501,3 +501,20 @@ def transferFence():
 def transferWait():
     """The host waits for the asynchronous transfers issued so far."""
     check(L.lib().mg_transfer_wait())
+
+
+class tuning:
+    """Context manager over ``mg_tuning_set``: kernel generation, tile heights, k-chunks and L2 prefetch of the
+    fused sweeps (``with tuning(MG_FWD=1, MG_CHUNKS=3): ...``).  Overrides are dropped on exit."""
+
+    def __init__(self, **switches):
+        self.switches = switches
+
+    def __enter__(self):
+        for k, v in self.switches.items():
+            check(L.lib().mg_tuning_set(k.encode(), int(v)))
+        return self
+
+    def __exit__(self, *exc):
+        check(L.lib().mg_tuning_clear())
+        return False

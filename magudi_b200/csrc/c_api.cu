@@ -2,7 +2,9 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <cstdlib>
 
 #include "../../include/magudi_gpu.h"
 #include "grid.h"
@@ -25,6 +27,22 @@ int mg_cuda_fail(cudaError_t e, const char* file, int line) {
   return -2;
 }
 cudaStream_t mg_stream() { return g_stream; }
+
+namespace {
+std::map<std::string, int> g_tuning;
+std::mutex g_tuningMutex;
+}  // namespace
+bool mg_tuning_has(const char* name) {
+  std::lock_guard<std::mutex> lock(g_tuningMutex);
+  return g_tuning.count(name) || getenv(name);
+}
+int mg_tuning_get(const char* name, int dflt) {
+  std::lock_guard<std::mutex> lock(g_tuningMutex);
+  auto it = g_tuning.find(name);
+  if (it != g_tuning.end()) return it->second;
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 int mg_num_sms() { return g_sms; }
 void mg_count_launches(int n) { g_launches += n; }
 
@@ -123,6 +141,17 @@ int mg_profile_enable(int enable) {
   for (auto& p : g_prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
   g_prof.clear();
   g_profOn = enable != 0;
+  return 0;
+}
+int mg_tuning_set(const char* name, int value) {
+  if (!name) MG_FAIL("mg_tuning_set: null name");
+  std::lock_guard<std::mutex> lock(g_tuningMutex);
+  g_tuning[name] = value;
+  return 0;
+}
+int mg_tuning_clear(void) {
+  std::lock_guard<std::mutex> lock(g_tuningMutex);
+  g_tuning.clear();
   return 0;
 }
 int mg_profile_get(const char* name, double* ms, long long* launches) {

@@ -295,6 +295,89 @@ __device__ __forceinline__ void add_flux_jacobian_transpose_rect(const Prim<ND>&
   }
 }
 
+// Point-invariant factors of the closed-form Jacobian-transpose products below.
+template <int ND>
+struct JacFactors {
+  double phi2;      // (gamma-1)/2 |u|^2
+  double H;         // T + phi2/(gamma-1)  (total enthalpy)
+  double pw;        // powerLaw gamma v / T           (viscous)
+};
+template <int ND>
+__device__ __forceinline__ void jac_factors(const Prim<ND>& s, double gamma, bool viscous, double powerLaw,
+                                            JacFactors<ND>& f) {
+  const double g1 = gamma - 1.0;
+  double usq = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) usq = (i == 0) ? s.u[0] * s.u[0] : usq + s.u[i] * s.u[i];
+  f.phi2 = 0.5 * g1 * usq;
+  f.H = s.T + f.phi2 / g1;
+  f.pw = viscous ? powerLaw * gamma * s.v / s.T : 0.0;
+}
+
+// y += (A - B)^T x in closed form: A = inviscid flux Jacobian along the metric row m (reference
+// src/CNSHelperImpl.f90:984-1444), B = first-partial viscous Jacobian (:2344-2600).  A^T x is the gradient of
+// x . F(Q) with x frozen, which collapses to three dot products (u.x_m, m.x_m, m.u) and O(NU) work instead of
+// building the NU x NU matrix.  RECT: m = m[D] e_D (off-diagonal metrics are structurally zero).
+// cst[c] = sum_l m_l tau(l,c), chf = m . q   (only read when viscous).
+template <int ND, bool RECT, int D>
+__device__ __forceinline__ void add_flux_jacobian_transpose_cf(const Prim<ND>& s, const JacFactors<ND>& f,
+                                                               const double* m, double gamma, bool viscous,
+                                                               const double* cst, double chf, const double* x,
+                                                               double* y) {
+  constexpr int NU = ND + 2;
+  const double g1 = gamma - 1.0;
+  const double* xm = x + 1;
+  const double xE = x[NU - 1];
+  double uh, xh, ux = 0.0;
+  if constexpr (RECT) {
+    uh = m[D] * s.u[D];
+    xh = m[D] * xm[D];
+  } else {
+    uh = 0.0;
+    xh = 0.0;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      uh = (i == 0) ? m[0] * s.u[0] : uh + m[i] * s.u[i];
+      xh = (i == 0) ? m[0] * xm[0] : xh + m[i] * xm[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ND; ++i) ux = (i == 0) ? s.u[0] * xm[0] : ux + s.u[i] * xm[i];
+  const double sfac = x[0] + ux + xE * f.H;
+  const double tfac = g1 * (xh + xE * uh);
+  // (gamma-2)/(gamma-1) phi2 - T  ==  phi2 - H
+  double y0 = f.phi2 * xh - uh * ux + xE * (uh * (f.phi2 - f.H));
+  double yE = g1 * xh + gamma * (uh * xE);
+  double yb[ND];
+#pragma unroll
+  for (int b = 0; b < ND; ++b) {
+    yb[b] = uh * xm[b] - tfac * s.u[b];
+    if (!RECT || b == D) yb[b] += m[b] * sfac;
+  }
+  if (viscous) {
+    double ucst = 0.0, S = 0.0;
+#pragma unroll
+    for (int c = 0; c < ND; ++c) {
+      ucst = (c == 0) ? s.u[0] * cst[0] : ucst + s.u[c] * cst[c];
+      S = (c == 0) ? cst[0] * xm[0] : S + cst[c] * xm[c];
+    }
+    const double temp1 = ucst - chf;
+    S += temp1 * xE;
+    const double vx = s.v * xE;
+    // pw (phi2/(gamma-1) - T/gamma), phi2/(gamma-1) == H - T
+    const double t2 = f.pw * ((f.H - s.T) - s.T * (1.0 / gamma));
+    y0 -= t2 * S - vx * ucst;
+    const double pS = f.pw * S;
+#pragma unroll
+    for (int b = 0; b < ND; ++b) yb[b] += pS * s.u[b] - vx * cst[b];
+    yE -= pS;
+  }
+  y[0] += y0;
+#pragma unroll
+  for (int b = 0; b < ND; ++b) y[b + 1] += yb[b];
+  y[NU - 1] += yE;
+}
+
 // Second-partial viscous Jacobian transpose for m1 = M1 e_II, m2 = M2 e_JJ.
 template <int ND, int II, int JJ>
 __device__ __forceinline__ void add_second_partial_transpose_rect(const double* u, double mu, double lam, double kap,
@@ -328,6 +411,26 @@ __device__ __forceinline__ void add_second_partial_transpose_rect(const double* 
     y[b] += acc;
   }
   if (SAME) y[ND] += jac * (kap * temp1) * x[ND];
+}
+
+// Same product with the point-invariant factors folded: jm = mu/J', jl = lambda/J', jk = kappa/J' (J' = the
+// reference's `jacobian`, i.e. the inverse Jacobian, already multiplied in) and MM = M1 * M2.
+template <int ND, int II, int JJ>
+__device__ __forceinline__ void add_second_partial_transpose_rect_f(const double* u, double jm, double jl, double jk,
+                                                                    double MM, const double* x, double* y) {
+  const double xE = x[ND];
+  if constexpr (II == JJ) {
+    const double a = jm * MM;
+    double ux = 0.0;
+#pragma unroll
+    for (int b = 0; b < ND; ++b) y[b] += a * (x[b] + u[b] * xE);
+    (void)ux;
+    y[II] += (jm + jl) * MM * (x[II] + u[II] * xE);
+    y[ND] += jk * MM * xE;
+  } else {
+    y[II] += jm * MM * (x[JJ] + u[JJ] * xE);
+    y[JJ] += jl * MM * (x[II] + u[II] * xE);
+  }
 }
 
 // Incoming part of the inviscid flux Jacobian, A+ = R max/min(Lambda,0) L (reference :1446-2342).

@@ -118,4 +118,8 @@ int mg_field_upload(const mg_grid* g, MgField* f, const double* host);     // ho
 int mg_field_download(const mg_grid* g, const MgField* f, double* host);
 
 cudaStream_t mg_stream();
+// Tuning switches of the fused kernels (kernel generation, tile heights, k-chunks, L2 prefetch distance):
+// mg_tuning_set (C ABI) wins over the environment variable of the same name, which wins over the default.
+int mg_tuning_get(const char* name, int dflt);
+bool mg_tuning_has(const char* name);
 int mg_num_sms();

@@ -15,184 +15,9 @@
 // neighbours come from a shared-memory tile (with halo, periodic wrap or SBP boundary closures),
 // k-neighbours from a per-thread queue (registers in A, shared memory in B) so every field is read
 // from HBM once per sweep.  HBM-bound fp64 stencil/pointwise work: no tensor cores.
-#include <algorithm>
-#include <cmath>
-#include <cstdlib>
-#include <cstring>
-#include <vector>
-
-#include "grid.h"
-#include "rhs_fused.h"
-#include "stencil_apply.h"
+#include "fused_common.cuh"
 
 namespace {
-
-constexpr int TX = 16, TY = 16, NT = TX * TY;
-
-struct LineOp {                 // one 1-D operator: interior stencil + closure tables
-  int sym, lo, nInt;
-  double c[MG_MAX_INTERIOR];
-  int depth, width, hasB0, hasB1;
-  const double* b1;             // device [depth][MG_MAX_BWIDTH]
-  const double* b2;
-};
-
-struct DirInfo {
-  int n, periodic, o1, o2;      // extent, wraps?, periodicOffset(1:2)
-  int normDepth, hasB0, hasB1;
-  double norm[MG_MAX_BDEPTH];   // first-derivative norm (applyNormInverse in the dissipation)
-};
-
-struct DevOps;
-constexpr int MG_PF_MAX = 48;
-
-struct FusedArgs {
-  int nx, ny, nz;
-  long plane;
-  size_t cs;                    // component stride of every field
-  int wrapK;                    // 1: single rank, periodic in k -> wrap plane index; 0: read ghost planes
-  int kBeg, kEnd, kChunk;
-  int curvilinear, viscous;
-  DirInfo dir[3];
-  LineOp D[3], Dd[3], Dt[3];    // first derivative, dissipation, dissipation transpose
-  PhysParams pp;
-  double dissAmount;
-  const double *Q, *m, *jac, *arc;
-  double *tauq, *diss;          // sweep A outputs
-  const double *tauqIn, *dissIn;
-  // sweep B outputs
-  double *rhs;                  // when !fuseRk
-  const double *b1in; double *b1out, *b2, *Qout;
-  int fuseRk, stage;
-  double dt;
-  double rkB, rkQ;              // dt x RK4 weights of the accumulator / state update of this stage
-  int prefetch;                 // planes of L2 prefetch distance (0 = off)
-  int composite;                // composite dissipation (single operator) instead of Dt(-arc Dd)
-  const struct DevOps* ops;     // device copy of the operators for the (out-of-line) closure path
-  // L2 prefetch streams: pf[0..pfIn) are read at the arriving plane, pf[pfIn..pfAll) at the output plane
-  const double* pf[MG_PF_MAX];
-  int pfIn, pfAll;
-  // adjoint sweeps
-  const double *Win, *diffIn, *rhsIn;
-  double* diffOut;
-  int dissOn;
-};
-
-// L2 prefetch of the 128-byte line holding p: used to pull the planes the march will need two steps
-// ahead while the current plane is being processed (costs no registers, unlike a software pipeline).
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-// Pull the rows of the planes the march needs `prefetch` steps ahead into L2.  The 16 lanes of a tile row
-// share the row's streams (one 128-byte line per stream and row), so a thread issues pfAll/16 prefetches
-// per plane instead of one lane issuing all of them.
-__device__ __forceinline__ void prefetch_streams(const FusedArgs& a, int kIn, bool okIn, int kOut, bool okOut,
-                                                 long rowOff, int lane16, bool rowOk) {
-  if (!rowOk) return;
-  for (int sid = lane16; sid < a.pfAll; sid += 16) {
-    const bool in = sid < a.pfIn;
-    if (in ? okIn : okOut) prefetch_l2(a.pf[sid] + (long)(in ? kIn : kOut) * a.plane + rowOff);
-  }
-}
-
-__device__ __forceinline__ int wrap_index(int c, const DirInfo& d) {
-  if (c >= 0 && c < d.n) return c;
-  if (!d.periodic) return -1;
-  return c < 0 ? d.n + c - d.o1 : c - d.n + d.o2;
-}
-
-// Apply a 1-D operator at coordinate c of a line of extent n; get(cc) returns the value at coordinate cc.
-template <class G>
-__device__ __forceinline__ double line_apply(const LineOp& op, int c, int n, G&& get) {
-  if (op.hasB0 && c < op.depth) {
-    double r = 0.0;
-    for (int s = 0; s < op.width; ++s) r += op.b1[c * MG_MAX_BWIDTH + s] * get(s);
-    return r;
-  }
-  if (op.hasB1 && c >= n - op.depth) {
-    const int m = n - 1 - c, first = n - op.width;
-    double r = 0.0;
-    for (int s = 0; s < op.width; ++s) r += op.b2[m * MG_MAX_BWIDTH + s] * get(first + s);
-    return r;
-  }
-  double r = 0.0;
-  if (op.sym == MG_SKEW_SYMMETRIC) {
-    const int h = op.nInt / 2;
-    for (int q = 1; q <= h; ++q) r += op.c[q - op.lo] * (get(c + q) - get(c - q));
-  } else if (op.sym == MG_SYMMETRIC) {
-    const int h = op.nInt / 2;
-    for (int q = 1; q <= h; ++q) r += op.c[q - op.lo] * (get(c + q) + get(c - q));
-    r += op.c[0 - op.lo] * get(c);
-  } else {
-    for (int q = 0; q < op.nInt; ++q) r += op.c[q] * get(c + op.lo + q);
-  }
-  return r;
-}
-
-// Non-composite dissipation along a line at coordinate c (reference src/RhsHelperImpl.f90:68-77):
-//   H^-1 Dt ( -arc * (Dd q) ); getq(cc) the field, getarc(cc) the arc length.
-template <class GQ, class GA>
-__device__ __forceinline__ double line_dissipation(const LineOp& Dd, const LineOp& Dt, const DirInfo& di, int c,
-                                                   GQ&& getq, GA&& getarc) {
-  const int n = di.n;
-  double r = line_apply(Dt, c, n, [&](int cc) { return -getarc(cc) * line_apply(Dd, cc, n, getq); });
-  if (di.hasB0 && c < di.normDepth) r = r / di.norm[c];
-  if (di.hasB1 && c >= n - di.normDepth) r = r / di.norm[n - 1 - c];
-  return r;
-}
-
-// Device-resident copy of the operator tables, used by the out-of-line closure path below (keeps the
-// boundary-tile code out of the hot kernels' instruction stream and register allocation).
-struct DevOps {
-  LineOp D[3], Dd[3], Dt[3];
-  DirInfo dir[3];
-};
-
-// line[(cc - c0) * stride] holds the value at coordinate cc of the line (shared-memory tile, read
-// through generic addresses: this is the slow, rarely taken path).
-__device__ __noinline__ double g_line_apply(const LineOp* op, int c, int n, const double* line, int stride, int c0) {
-  return line_apply(*op, c, n, [&](int cc) { return line[(long)(cc - c0) * stride]; });
-}
-__device__ __noinline__ double g_line_dissipation(const LineOp* Dd, const LineOp* Dt, const DirInfo* di, int c,
-                                                  const double* q, const double* arc, int stride, int c0) {
-  return line_dissipation(*Dd, *Dt, *di, c, [&](int cc) { return q[(long)(cc - c0) * stride]; },
-                          [&](int cc) { return arc[(long)(cc - c0) * stride]; });
-}
-
-// Tile layout [field][H][W]; dirIdx 0: along columns (i), 1: along rows (j); c0 = coordinate of index 0.
-template <int W, int H>
-__device__ __forceinline__ double tile_line_apply(const LineOp* op, int c, int n, const double* T0, int f, int row,
-                                                  int col, int dirIdx, int c0) {
-  return dirIdx == 0 ? g_line_apply(op, c, n, T0 + ((size_t)f * H + row) * W, 1, c0)
-                     : g_line_apply(op, c, n, T0 + (size_t)f * H * W + col, W, c0);
-}
-template <int W, int H>
-__device__ __forceinline__ double tile_line_dissipation(const DevOps* ops, int d, int c, const double* T0, int fq,
-                                                        int fa, int row, int col, int c0) {
-  return d == 0 ? g_line_dissipation(&ops->Dd[d], &ops->Dt[d], &ops->dir[d], c, T0 + ((size_t)fq * H + row) * W,
-                                     T0 + ((size_t)fa * H + row) * W, 1, c0)
-                : g_line_dissipation(&ops->Dd[d], &ops->Dt[d], &ops->dir[d], c, T0 + (size_t)fq * H * W + col,
-                                     T0 + (size_t)fa * H * W + col, W, c0);
-}
-template <int L>
-__device__ __forceinline__ double strided_line_apply(const LineOp* op, int c, int n, const double* line, int stride,
-                                                     int c0) {
-  return g_line_apply(op, c, n, line, stride, c0);
-}
-
-// Tile placement: tiles are anchored at the origin except the last one of a direction, which is
-// anchored at the far boundary so that it always contains the whole right closure block.
-__device__ __forceinline__ void tile_origin(int t, int n, int T, int& c0, bool& isLast) {
-  const int nt = (n + T - 1) / T;
-  isLast = t == nt - 1;
-  c0 = (isLast && n >= T) ? n - T : t * T;
-}
-__device__ __forceinline__ bool owns(int c, int n, int T, bool isLast) {
-  if (c >= n) return false;
-  if (isLast) return true;
-  return (n < T) || (c < n - T) || (n % T == 0);
-}
 
 // ------------------------------------------------------------------------------- sweep A
 // t_State%update: (u, T) -> gradient -> stress tensor + heat flux.  Shared memory: an in-plane tile of
@@ -594,121 +419,6 @@ __global__ void __launch_bounds__(NT, 2) k_diss(FusedArgs a) {
   }
 }
 
-// ------------------------------------------------------------------------------- sweep B
-// index of the unique stress entry (l, c) in the compact layout written by sweep A
-template <int ND>
-__device__ __forceinline__ constexpr int tau_index(int l, int c) {
-  const int r0 = l < c ? l : c, c0 = l < c ? c : l;
-  return r0 * ND - r0 * (r0 - 1) / 2 + (c0 - r0);
-}
-
-// Raw inputs of the flux evaluation at one point; loading and computing are separate so that all
-// global loads of an iteration are issued back to back (one exposed memory latency, not one per use).
-template <int ND>
-struct RawPoint {
-  double Q[ND + 2];
-  double tq[ND * (ND + 1) / 2 + ND];
-  double m[ND * ND];
-};
-
-template <int ND, int DIRS>
-__device__ __forceinline__ constexpr bool needs_tq(int e) {
-  constexpr int NTAU = ND * (ND + 1) / 2;
-  for (int d = 0; d < ND; ++d) {
-    if (!((DIRS >> d) & 1)) continue;
-    if (e == NTAU + d) return true;
-    for (int c = 0; c < ND; ++c)
-      if (tau_index<ND>(d, c) == e) return true;
-  }
-  return false;
-}
-
-// DIRS: bit d set -> the flux along direction d will be needed.
-template <int ND, int DIRS, bool CURV>
-__device__ __forceinline__ void load_raw(const FusedArgs& a, long off, RawPoint<ND>& r) {
-  constexpr int NU = ND + 2;
-  constexpr int NTQ = ND * (ND + 1) / 2 + ND;
-  const double* __restrict__ Qp = a.Q + off;
-#pragma unroll
-  for (int c = 0; c < NU; ++c) r.Q[c] = __ldg(Qp + (size_t)c * a.cs);
-  if (a.viscous) {
-    const double* __restrict__ tq = a.tauqIn + off;
-#pragma unroll
-    for (int e = 0; e < NTQ; ++e)
-      if (CURV || needs_tq<ND, DIRS>(e)) r.tq[e] = __ldg(tq + (size_t)e * a.cs);
-  }
-  const double* __restrict__ mp = a.m + off;
-#pragma unroll
-  for (int d = 0; d < ND; ++d) {
-    if (!((DIRS >> d) & 1)) continue;
-    if constexpr (CURV) {
-#pragma unroll
-      for (int l = 0; l < ND; ++l) r.m[l + ND * d] = __ldg(mp + (size_t)(l + ND * d) * a.cs);
-    } else {
-      r.m[d + ND * d] = __ldg(mp + (size_t)(d + ND * d) * a.cs);
-    }
-  }
-}
-
-// Contravariant total fluxes from the raw inputs (reference CNSHelperImpl.f90:563-689 Cartesian
-// inviscid - viscous, :772-840 metric transform).
-template <int ND, int DIRS, bool CURV>
-__device__ __forceinline__ void fluxes_from_raw(const FusedArgs& a, const RawPoint<ND>& r, double (*Fh)[ND + 2]) {
-  constexpr int NU = ND + 2;
-  constexpr int NTAU = ND * (ND + 1) / 2;
-  const double* Q = r.Q;
-  Prim<ND> s;
-  dependent<ND>(Q, a.pp.gamma, s);
-  if constexpr (!CURV) {
-#pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      if (!((DIRS >> d) & 1)) continue;
-      double F[NU];
-      F[0] = Q[d + 1];
-#pragma unroll
-      for (int c = 0; c < ND; ++c) {
-        if (c == d) F[c + 1] = Q[d + 1] * s.u[d] + s.p;
-        else F[c + 1] = Q[(c < d ? c : d) + 1] * s.u[c < d ? d : c];
-      }
-      F[NU - 1] = s.u[d] * (Q[NU - 1] + s.p);
-      if (a.viscous) {
-        double acc = 0.0;
-#pragma unroll
-        for (int c = 0; c < ND; ++c) {
-          const double t = r.tq[tau_index<ND>(d, c)];
-          F[c + 1] = F[c + 1] - t;
-          acc = (c == 0) ? s.u[0] * t : acc + s.u[c] * t;
-        }
-        F[NU - 1] = F[NU - 1] - (acc - r.tq[NTAU + d]);
-      }
-      const double md = r.m[d + ND * d];
-#pragma unroll
-      for (int c = 0; c < NU; ++c) Fh[d][c] = md * F[c];
-    }
-  } else {
-    double tau[ND * ND], q[ND], Fc[ND][NU], Fv[NU];
-    if (a.viscous) {
-#pragma unroll
-      for (int l = 0; l < ND; ++l)
-#pragma unroll
-        for (int c = 0; c < ND; ++c) tau[l + ND * c] = r.tq[tau_index<ND>(l, c)];
-#pragma unroll
-      for (int e = 0; e < ND; ++e) q[e] = r.tq[NTAU + e];
-    }
-#pragma unroll
-    for (int l = 0; l < ND; ++l) cartesian_flux<ND>(l, Q, s, a.viscous, tau, q, Fc[l], Fv);
-#pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      if (!((DIRS >> d) & 1)) continue;
-#pragma unroll
-      for (int l = 0; l < ND; ++l) {
-        const double ml = r.m[l + ND * d];
-#pragma unroll
-        for (int c = 0; c < NU; ++c) Fh[d][c] = (l == 0) ? ml * Fc[0][c] : Fh[d][c] + ml * Fc[l][c];
-      }
-    }
-  }
-}
 
 template <int ND, int R, bool CURV, bool CLOS>
 __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
@@ -1447,123 +1157,6 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint2(FusedArgs a) {
   }
 }
 
-// --------------------------------------------------------------------------------- host
-struct SchemeInfo { int R, dlo, dn, tlo, tn; };
-
-bool scheme_of(const mg_grid* g, SchemeInfo* si) {
-  // all directions must share one scheme family
-  int R = -1;
-  for (int d = 0; d < g->nD; ++d) {
-    const mg_stencil* D = g->firstDerivative[d];
-    if (!D || D->op.symmetryType != MG_SKEW_SYMMETRIC) return false;
-    const int h = D->op.interiorWidth / 2;
-    if (R < 0) R = h;
-    if (h != R) return false;
-  }
-  if (R == 2) *si = {2, -1, 3, -1, 3};
-  else if (R == 3) *si = {3, -2, 4, -1, 4};
-  else if (R == 4) *si = {4, -2, 5, -2, 5};
-  else return false;
-  if (g->dissipationOn && !g->compositeDissipation)
-    for (int d = 0; d < g->nD; ++d) {
-      const MgDevOp& o = g->dissipation[d]->op;
-      const MgDevOp& t = g->dissipationTranspose[d]->op;
-      if (o.lo != si->dlo || o.nInterior != si->dn || t.lo != si->tlo || t.nInterior != si->tn) return false;
-    }
-  if (g->dissipationOn && g->compositeDissipation)
-    for (int d = 0; d < g->nD; ++d)
-      if (g->dissipation[d]->op.interiorWidth / 2 != R) return false;
-  return true;
-}
-
-int fill_lineop(mg_stencil* s, LineOp* o) {
-  MG_TRY(mg_stencil_upload(s));
-  const MgDevOp& op = s->op;
-  o->sym = op.symmetryType;
-  o->lo = op.lo;
-  o->nInt = op.nInterior;
-  for (int k = 0; k < MG_MAX_INTERIOR; ++k) o->c[k] = op.interior[k];
-  o->depth = op.boundaryDepth;
-  o->width = op.boundaryWidth;
-  o->hasB0 = op.hasDomainBoundary[0];
-  o->hasB1 = op.hasDomainBoundary[1];
-  o->b1 = &s->d_op->b1[0][0];
-  o->b2 = &s->d_op->b2[0][0];
-  return 0;
-}
-
-int fill_args(mg_state* s, FusedArgs* a) {
-  mg_grid* g = s->grid;
-  std::memset(a, 0, sizeof(*a));
-  a->nx = g->localSize[0];
-  a->ny = g->localSize[1];
-  a->nz = g->localSize[2];
-  a->plane = (long)g->plane;
-  a->cs = s->rhs.compStride;
-  a->wrapK = (g->nD == 3 && g->procDims[2] == 1) ? 1 : 0;
-  a->kBeg = 0;
-  a->kEnd = g->localSize[2];
-  a->kChunk = g->localSize[2];
-  a->curvilinear = g->isCurvilinear;
-  a->viscous = s->opt.viscosityOn;
-  for (int d = 0; d < g->nD; ++d) {
-    const MgDevOp& op = g->firstDerivative[d]->op;
-    DirInfo& di = a->dir[d];
-    di.n = g->localSize[d];
-    di.periodic = g->periodicityType[d] != MG_PERIODIC_NONE;
-    di.o1 = op.periodicOffset[0];
-    di.o2 = op.periodicOffset[1];
-    di.normDepth = op.normDepth;
-    di.hasB0 = op.hasDomainBoundary[0];
-    di.hasB1 = op.hasDomainBoundary[1];
-    for (int m = 0; m < MG_MAX_BDEPTH; ++m) di.norm[m] = op.normBoundary[m];
-    MG_TRY(fill_lineop(g->firstDerivative[d], &a->D[d]));
-    if (g->dissipationOn) {
-      MG_TRY(fill_lineop(g->dissipation[d], &a->Dd[d]));
-      if (!g->compositeDissipation) MG_TRY(fill_lineop(g->dissipationTranspose[d], &a->Dt[d]));
-    }
-  }
-  a->composite = (g->compositeDissipation || !g->dissipationOn) ? 1 : 0;
-  a->pp = s->phys();
-  // L2 prefetch distance in planes (measured on B200: 1 is best for sweeps A and B, 2 for the dissipation sweep)
-  static const int pf = getenv("MG_PREFETCH") ? atoi(getenv("MG_PREFETCH")) : 1;
-  a->prefetch = pf;
-  a->dissAmount = s->opt.dissipationAmount;
-  a->m = g->metrics.comp(0);
-  a->jac = g->jacobian.comp(0);
-  a->arc = g->arcLengths.comp(0);
-  return 0;
-}
-
-// L2 prefetch stream table (see prefetch_streams)
-struct PfList {
-  std::vector<const double*> in, out;
-  size_t cs;
-  void addIn(const double* base, int n) { if (base) for (int c = 0; c < n; ++c) in.push_back(base + (size_t)c * cs); }
-  void addOut(const double* base, int n) { if (base) for (int c = 0; c < n; ++c) out.push_back(base + (size_t)c * cs); }
-  void finish(FusedArgs* a) {
-    // MG_PF_MASK (tuning): bit 0 = prefetch the arriving-plane streams, bit 1 = the output-plane streams
-    static const int mask = getenv("MG_PF_MASK") ? atoi(getenv("MG_PF_MASK")) : 3;
-    a->pfIn = a->pfAll = 0;
-    if (mask & 1)
-      for (const double* p : in) if (a->pfAll < MG_PF_MAX) { a->pf[a->pfAll++] = p; a->pfIn = a->pfAll; }
-    if (mask & 2)
-      for (const double* p : out) if (a->pfAll < MG_PF_MAX) a->pf[a->pfAll++] = p;
-  }
-};
-
-// Device copy of the operator tables for the out-of-line closure path (built once per state and mode).
-int upload_ops(mg_state* s, int which, FusedArgs* a) {
-  if (!s->fusedOps[which]) {
-    DevOps h;
-    std::memset(&h, 0, sizeof(h));
-    for (int d = 0; d < 3; ++d) { h.D[d] = a->D[d]; h.Dd[d] = a->Dd[d]; h.Dt[d] = a->Dt[d]; h.dir[d] = a->dir[d]; }
-    MG_CUDA(cudaMalloc(&s->fusedOps[which], sizeof(DevOps)));
-    MG_CUDA(cudaMemcpy(s->fusedOps[which], &h, sizeof(DevOps), cudaMemcpyHostToDevice));
-  }
-  a->ops = (const DevOps*)s->fusedOps[which];
-  return 0;
-}
 
 template <int ND, int R, bool CURV, bool CLOS>
 int launchA(const FusedArgs& a, dim3 grid, cudaStream_t st) {
@@ -1622,39 +1215,6 @@ int launchB(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   return 0;
 }
 
-// Split k into chunks so that the CTA count fills whole waves of (SMs x resident CTAs); every chunk
-// re-streams 2R warm-up planes, so fewer, longer chunks are preferred when the fill is equal.
-int choose_chunks(FusedArgs* a, int R, int residentPerSm) {
-  const int tilesXY = ((a->nx + TX - 1) / TX) * ((a->ny + TY - 1) / TY);
-  int best = 1;
-  if (a->nz > 1) {
-    static const int forced = getenv("MG_CHUNKS") ? atoi(getenv("MG_CHUNKS")) : 0;
-    if (forced > 0) best = forced;
-    else {
-      const double slots = (double)mg_num_sms() * residentPerSm;
-      double bestScore = -1.0;
-      for (int n = 1; n <= 32 && n * 4 * R <= a->nz; ++n) {
-        const int chunk = (a->nz + n - 1) / n;
-        const double waves = tilesXY * (double)n / slots;
-        const double fill = waves / ceil(waves);
-        const double score = fill * chunk / (chunk + 0.6 * 2 * R);
-        if (score > bestScore + 1e-9) { bestScore = score; best = n; }
-      }
-    }
-  }
-  a->kChunk = (a->nz + best - 1) / best;
-  return (a->nz + a->kChunk - 1) / a->kChunk;
-}
-
-dim3 tiles(const FusedArgs& a, int nChunks) {
-  return dim3((a.nx + TX - 1) / TX, (a.ny + TY - 1) / TY, nChunks);
-}
-
-// true when an in-plane direction has a domain boundary (SBP closures): selects the kernel variant that
-// carries the out-of-line closure path; fully periodic in-plane grids run the variant without it.
-bool has_closures(const FusedArgs& a) {
-  return a.dir[0].hasB0 || a.dir[0].hasB1 || a.dir[1].hasB0 || a.dir[1].hasB1;
-}
 
 template <int ND, int R>
 int launchB_(const FusedArgs& a, dim3 grid, cudaStream_t st) {
@@ -1664,6 +1224,38 @@ int launchB_(const FusedArgs& a, dim3 grid, cudaStream_t st) {
 }
 
 }  // namespace
+
+// Can direction d of the grid be covered by tiles of extent T (plus a halo of R) by the fused kernels?
+static bool dir_fits_tile(const mg_grid* g, int d, int T, int R, int mode) {
+  if (g->periodicityType[d] == MG_PERIODIC_NONE) {
+    // a closure block (and its adjoint-free forward operators) must fit in one tile + halo
+    const MgDevOp& o = (mode == MG_ADJOINT ? g->adjointFirstDerivative[d] : g->firstDerivative[d])->op;
+    if (o.boundaryWidth > T + R || o.boundaryDepth > T || g->localSize[d] < 2 * o.boundaryDepth) return false;
+    // The last tile of a direction is anchored at the far boundary; when the line is not a multiple of the
+    // tile it takes over the points >= n - T from the first tile.  Every point of the LEFT closure region
+    // (widest operator used along the direction) must stay with the first tile, whose halo holds the block.
+    int depth = std::max(o.boundaryDepth, g->firstDerivative[d]->op.boundaryDepth);
+    int width = o.boundaryWidth;
+    if (g->dissipationOn) {
+      const MgDevOp& dd = g->dissipation[d]->op;
+      depth = std::max(depth, dd.boundaryDepth);
+      width = std::max(width, dd.boundaryWidth);
+      if (!g->compositeDissipation) {
+        const MgDevOp& dt = g->dissipationTranspose[d]->op;
+        depth = std::max(depth, std::max(dt.boundaryDepth + dd.boundaryWidth, g->firstDerivative[d]->op.normDepth));
+        width = std::max(width, dt.boundaryWidth);
+      }
+    }
+    const int n = g->localSize[d];
+    if (n > T && n % T != 0 && n - T < depth) return false;
+    if (depth > T || width > T + R) return false;
+    if (n < 2 * depth) return false;
+  } else if (g->localSize[d] < T) {
+    // a periodic line shorter than the tile would have to wrap inside the tile: general path
+    return false;
+  }
+  return true;
+}
 
 int mg_fused_supported(const mg_state* s, int mode) {
   const mg_grid* g = s->grid;
@@ -1676,29 +1268,7 @@ int mg_fused_supported(const mg_state* s, int mode) {
   if (!scheme_of(g, &si)) return 0;
   if (g->nD == 3 && g->localSize[2] < si.R) return 0;
   for (int d = 0; d < 2; ++d)
-    if (g->periodicityType[d] == MG_PERIODIC_NONE) {
-      // a closure block (and its adjoint-free forward operators) must fit in one 16-wide tile + halo
-      const MgDevOp& o = (mode == MG_ADJOINT ? g->adjointFirstDerivative[d] : g->firstDerivative[d])->op;
-      if (o.boundaryWidth > TX + si.R || o.boundaryDepth > TX || g->localSize[d] < 2 * o.boundaryDepth) return 0;
-      // The last tile of a direction is anchored at the far boundary; when the line is not a multiple of the
-      // tile it takes over the points >= n - 16 from the first tile.  Every point of the LEFT closure region
-      // (widest operator used along the direction) must stay with the first tile, whose halo holds the block.
-      int depth = std::max(o.boundaryDepth, g->firstDerivative[d]->op.boundaryDepth);
-      if (g->dissipationOn) {
-        const MgDevOp& dd = g->dissipation[d]->op;
-        depth = std::max(depth, dd.boundaryDepth);
-        if (!g->compositeDissipation) {
-          const MgDevOp& dt = g->dissipationTranspose[d]->op;
-          depth = std::max(depth, std::max(dt.boundaryDepth + dd.boundaryWidth, g->firstDerivative[d]->op.normDepth));
-        }
-      }
-      const int n = g->localSize[d];
-      if (n > TX && n % TX != 0 && n - TX < depth) return 0;
-      if (depth > TX) return 0;
-    } else if (g->localSize[d] < TX) {
-      // a periodic line shorter than the tile would have to wrap inside the tile: general path
-      return 0;
-    }
+    if (!dir_fits_tile(g, d, TX, si.R, mode)) return 0;
   return 1;
 }
 
@@ -1773,7 +1343,7 @@ int mg_fused_dissipation(mg_state* s) {
   MG_TRY(upload_ops(s, 0, &a));
   a.Q = s->Q[s->cur].comp(0);
   a.diss = s->dissTerm.comp(0);
-  if (!getenv("MG_PREFETCH")) a.prefetch = 2;
+  if (!mg_tuning_has("MG_PREFETCH")) a.prefetch = 2;
   SchemeInfo si;
   scheme_of(g, &si);
   {  // dissipation sweep streams
@@ -1813,16 +1383,32 @@ int mg_fused_dissipation(mg_state* s) {
 }
 
 // Sweep B: RHS (+ RK4 substep when fuseRk)
+// tile height of the folded sweep B: 12 (192 threads, 2 CTAs/SM) exists for the 3-D viscous instantiations with
+// non-composite dissipation and R <= 3, else 8 (128 threads)
+static int bd_tile_height(const mg_state* s, int R) {
+  const int tyPref = mg_tuning_get("MG_BD_TY", 12);
+  const bool hot = s->opt.viscosityOn && s->opt.dissipationOn && !s->grid->compositeDissipation;
+  return (tyPref == 12 && hot && s->nD == 3 && R <= 3) ? 12 : 8;
+}
+
 int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
   mg_grid* g = s->grid;
   if (!s->fusedValid) MG_FAIL("fused sweep B: state has not been updated (sweep A)");
-  if (s->opt.dissipationOn && !s->dissValid) MG_TRY(mg_fused_dissipation(s));
+  // MG_FWD=1 selects the first-generation three-sweep forward stage (separate dissipation sweep; kept for A/B
+  // measurements); default: dissipation folded into sweep B (fused_sweepbd.cuh), two sweeps per stage
+  SchemeInfo si;
+  scheme_of(g, &si);
+  const int genPref = mg_tuning_get("MG_FWD", 2);
+  // the folded kernel uses 16 x 12 / 16 x 8 tiles: eta closures wider than the tile stay with generation 1
+  const int gen = (genPref == 2 && dir_fits_tile(g, 1, bd_tile_height(s, si.R), si.R, MG_FORWARD)) ? 2 : 1;
+  if (gen != 2 && s->opt.dissipationOn && !s->dissValid) MG_TRY(mg_fused_dissipation(s));
   FusedArgs a;
   MG_TRY(fill_args(s, &a));
   MG_TRY(upload_ops(s, 0, &a));
   a.Q = s->Q[s->cur].comp(0);
   a.tauqIn = s->opt.viscosityOn ? s->tauq.comp(0) : nullptr;
-  a.dissIn = s->opt.dissipationOn ? s->dissTerm.comp(0) : nullptr;
+  a.dissIn = (gen != 2 && s->opt.dissipationOn) ? s->dissTerm.comp(0) : nullptr;
+  a.dissOn = s->opt.dissipationOn;
   a.rhs = s->rhs.comp(0);
   a.fuseRk = fuseRk;
   a.stage = stage;
@@ -1843,8 +1429,6 @@ int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
     }
     a.b2 = s->rk2.comp(0);
   }
-  SchemeInfo si;
-  scheme_of(g, &si);
   {  // sweep B streams
     PfList pfl; pfl.cs = a.cs;
     pfl.addIn(a.Q, s->nU);
@@ -1856,9 +1440,18 @@ int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
     if (fuseRk && (stage == 2 || stage == 3)) pfl.addOut(a.b1in, s->nU);
     pfl.finish(&a);
   }
-  const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
   cudaStream_t st = mg_stream();
   int rc = -1;
+  if (gen == 2) {
+    const bool hot = a.viscous && a.dissOn && !a.composite;
+    const int tileY = bd_tile_height(s, si.R);
+    const int resident = (tileY == 8 && si.R < 4) ? 3 : 2;
+    const int nChunks = choose_chunks(&a, si.R, resident, TX, tileY);
+    rc = hot ? mg_fused_sweepbd_hot_launch(&a, s->nD, si.R, tileY, nChunks, st)
+             : mg_fused_sweepbd_gen_launch(&a, s->nD, si.R, tileY, nChunks, st);
+    if (rc == -1) MG_FAIL("fused sweep B: unsupported configuration");
+  } else {
+  const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
   const bool clos = has_closures(a);
   (void)clos;
 #ifndef MG_DEV_ONLY_33
@@ -1877,6 +1470,7 @@ int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
 #ifndef MG_DEV_ONLY_33
   if (s->nD == 3 && si.R == 4) rc = launchB_<3, 4>(a, grid, st);
 #endif
+  }
   if (rc != 0) return rc;
   if (fuseRk) {
     if (stage == 1) {
@@ -1944,7 +1538,7 @@ int fill_args_adjoint(mg_state* s, FusedArgs* a) {
   a->tauqIn = s->opt.viscosityOn ? s->tauq.comp(0) : nullptr;
   a->dissOn = s->opt.dissipationOn;
   // measured on B200: adjoint sweep 1 runs faster without the L2 prefetch (sweep 2 overrides this with 1)
-  static const int pfAdj = getenv("MG_PREFETCH_ADJ") ? atoi(getenv("MG_PREFETCH_ADJ")) : 0;
+  const int pfAdj = mg_tuning_get("MG_PREFETCH_ADJ", 0);
   a->prefetch = pfAdj;
   MG_TRY(upload_ops(s, 1, a));
   return 0;
@@ -1972,8 +1566,23 @@ int mg_fused_adjoint1(mg_state* s) {
     if (a.dissOn && !a.composite) pfl.addOut(a.arc, s->nD);
     pfl.finish(&a);
   }
-  const dim3 grid = tiles(a, choose_chunks(&a, si.R, 2));
   cudaStream_t st = mg_stream();
+  // MG_ADJ1=1 selects the first-generation kernel (kept for A/B measurements); default: fused_adjoint1.cuh
+  const int gen = mg_tuning_get("MG_ADJ1", 2);
+  if (gen == 2) {
+    const bool hot = a.viscous && a.dissOn && !a.composite;
+    // tile height 12 (192 threads, 168 registers) exists for the 3-D hot instantiations with R <= 3
+    const int tyPref = mg_tuning_get("MG_ADJ1_TY", 16);
+    int tileY = (tyPref == 12 && hot && s->nD == 3 && si.R <= 3) ? 12 : 16;
+    if (tileY != 16 && !dir_fits_tile(g, 1, tileY, si.R, MG_ADJOINT)) tileY = 16;
+    const int nChunks2 = choose_chunks(&a, si.R, 2, TX, tileY);
+    const int rc2 = hot ? mg_fused_adjoint1_hot_launch(&a, s->nD, si.R, tileY, nChunks2, st)
+                        : mg_fused_adjoint1_gen_launch(&a, s->nD, si.R, tileY, nChunks2, st);
+    if (rc2 == -1) MG_FAIL("fused adjoint sweep 1: unsupported configuration");
+    return rc2;
+  }
+  const int nChunks = choose_chunks(&a, si.R, 2);
+  const dim3 grid = tiles(a, nChunks);
   int rc = -1;
   const bool clos = has_closures(a);
   (void)clos;
@@ -2012,7 +1621,7 @@ int mg_fused_adjoint2(mg_state* s, int fuseRk, int stage, double dt) {
   a.rhsIn = s->rhs.comp(0);
   a.rhs = s->rhs.comp(0);
   a.diffIn = g->scratchA.comp(0);
-  if (!getenv("MG_PREFETCH_ADJ")) a.prefetch = 1;   // measured: distance 1 helps this sweep, none helps sweep 1
+  if (!mg_tuning_has("MG_PREFETCH_ADJ")) a.prefetch = 1;   // measured: distance 1 helps this sweep, none helps sweep 1
   a.fuseRk = fuseRk;
   const int rkStage = 5 - stage;        // adjoint stage 4 plays the role of RK stage 1, ...
   a.stage = rkStage;
