@@ -28,7 +28,7 @@ template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV, bool CLOS,
 __global__ void __launch_bounds__(TX * TYv, 2) k_adjoint1v2(FusedArgs a) {
   constexpr int TY = TYv, NT = TX * TYv;
   const bool COMPOSITE = HOT ? false : a.composite != 0;
-  const bool viscous = HOT ? true : viscous;
+  const bool viscous = HOT ? true : (a.viscous ? true : false);
   constexpr int NU = ND + 2;
   constexpr int NTAU = ND * (ND + 1) / 2;
   constexpr int W = TX + 2 * R, H = TY + 2 * R;
@@ -102,6 +102,13 @@ __global__ void __launch_bounds__(TX * TYv, 2) k_adjoint1v2(FusedArgs a) {
   const double sigma = a.dissAmount;
 
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
+    if (ND == 3 && a.prefetch) {
+      // pull the lines of the planes needed `prefetch` steps ahead into L2 (costs no registers)
+      int kf = ks + a.prefetch, kq = ks - RK + a.prefetch;
+      if (a.wrapK) { if (kf >= a.nz) kf -= a.nz; if (kq < 0) kq += a.nz; else if (kq >= a.nz) kq -= a.nz; }
+      prefetch_streams(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz),
+                       (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
+    }
     if (inside) {
       const double* __restrict__ Wp = a.Win + ((ND == 3) ? (long)ks * a.plane : 0) + pij;
       double wv[NU];
@@ -147,6 +154,15 @@ __global__ void __launch_bounds__(TX * TYv, 2) k_adjoint1v2(FusedArgs a) {
       for (int c = 0; c < ND * ND; ++c) {
         const bool diag = (c % ND) == (c / ND);
         if (CURV || diag) M[c] = __ldg(a.m + (size_t)c * a.cs + off);
+      }
+    }
+    // 192-thread variant (168 registers): the stress / heat-flux entries are requested before the barrier too
+    constexpr bool HOIST = (TYv == 12) && !CURV;
+    double tqH[HOIST ? NTAU + ND : 1];
+    if constexpr (HOIST) {
+      if (mine && viscous) {
+#pragma unroll
+        for (int e = 0; e < NTAU + ND; ++e) tqH[e] = __ldg(a.tauqIn + (size_t)e * a.cs + off);
       }
     }
     __syncthreads();
@@ -253,9 +269,15 @@ __global__ void __launch_bounds__(TX * TYv, 2) k_adjoint1v2(FusedArgs a) {
 #pragma unroll
             for (int l = 0; l < ND; ++l) chf = (l == 0) ? M[ND * d] * tqAll[NTAU] : chf + M[l + ND * d] * tqAll[NTAU + l];
           } else {
+            if constexpr (HOIST) {
 #pragma unroll
-            for (int c = 0; c < ND; ++c) cst[c] = __ldg(a.tauqIn + (size_t)tau_index<ND>(d, c) * a.cs + off);
-            chf = __ldg(a.tauqIn + (size_t)(NTAU + d) * a.cs + off);
+              for (int c = 0; c < ND; ++c) cst[c] = tqH[tau_index<ND>(d, c)];
+              chf = tqH[NTAU + d];
+            } else {
+#pragma unroll
+              for (int c = 0; c < ND; ++c) cst[c] = __ldg(a.tauqIn + (size_t)tau_index<ND>(d, c) * a.cs + off);
+              chf = __ldg(a.tauqIn + (size_t)(NTAU + d) * a.cs + off);
+            }
           }
         }
         // ---- pointwise products of this direction

@@ -36,7 +36,6 @@ __global__ void __launch_bounds__(TX * TYv, (TYv == 8 && R < 4) ? 3 : 2) k_sweep
   static_assert(HI_D + (TLO + TN - 1) == R, "dissipation support must match the first-derivative radius");
   constexpr int NHALO = 2 * R * TY + 2 * R * TX;
   constexpr int NH = (NHALO + NT - 1) / NT;
-  const bool viscous = HOT ? true : a.viscous != 0;
   const bool dissOn = HOT ? true : a.dissOn != 0;
   const bool COMPOSITE = HOT ? false : a.composite != 0;
   extern __shared__ double smem[];
@@ -125,6 +124,13 @@ __global__ void __launch_bounds__(TX * TYv, (TYv == 8 && R < 4) ? 3 : 2) k_sweep
     const long soff = (ND == 3) ? (long)ks * a.plane : 0;
     const bool planeActive = s >= kc0 && s < kc1;
     const bool emitNow = (ND == 3) ? (s - RK >= kc0 && mine) : false;
+    if (ND == 3 && a.prefetch) {
+      // pull the lines of the planes needed `prefetch` steps ahead into L2 (costs no registers)
+      int kf = ks + a.prefetch, kq = kp + a.prefetch;
+      if (a.wrapK) { if (kf >= a.nz) kf -= a.nz; if (kq < 0) kq += a.nz; else if (kq >= a.nz) kq -= a.nz; }
+      prefetch_streams(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz),
+                       (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
+    }
     // ---- inputs of the output plane p = s - RK (consumed by the emit below; issued first)
     double ejac = 0.0, vb1[NU], vb2[NU], arcg = 0.0;
     auto emit_load = [&](int kpl) {
@@ -160,7 +166,20 @@ __global__ void __launch_bounds__(TX * TYv, (TYv == 8 && R < 4) ? 3 : 2) k_sweep
     // arc length of the g that completes now (planes below kc0 + TLO only feed outputs of another chunk)
     if (ND == 3 && dissOn && !COMPOSITE && inside && s - HI_D >= kc0 + TLO)
       arcg = __ldg(a.arc + (size_t)2 * a.cs + (long)kg * a.plane + pij);
-    // ---- arrival of plane s: own point
+    // ---- arrival of plane s: the halo points' inputs are requested first so that their latency overlaps the
+    // own-point flux evaluation
+    RawPoint<ND> rawH[NH];
+    double arcH[NH];
+    if (planeActive) {
+#pragma unroll
+      for (int n = 0; n < NH; ++n) {
+        arcH[n] = 0.0;
+        if (hkind[n] == 1) load_raw<ND, 1, CURV>(a, soff + hp[n], rawH[n]);
+        else if (hkind[n] == 2) load_raw<ND, 2, CURV>(a, soff + hp[n], rawH[n]);
+        if (hkind[n] && dissOn && !COMPOSITE) arcH[n] = __ldg(a.arc + (size_t)(hkind[n] - 1) * a.cs + soff + hp[n]);
+      }
+    }
+    // ---- own point
     double f3[NU], last[NU];
 #pragma unroll
     for (int c = 0; c < NU; ++c) { f3[c] = 0.0; last[c] = 0.0; }
@@ -246,15 +265,13 @@ __global__ void __launch_bounds__(TX * TYv, (TYv == 8 && R < 4) ? 3 : 2) k_sweep
 #pragma unroll
       for (int n = 0; n < NH; ++n) {
         if (!hkind[n]) continue;
-        RawPoint<ND> raw;
+        const RawPoint<ND>& raw = rawH[n];
         double Fh[ND][NU];
         if (hkind[n] == 1) {
-          load_raw<ND, 1, CURV>(a, soff + hp[n], raw);
           fluxes_from_raw<ND, 1, CURV>(a, raw, Fh);
 #pragma unroll
           for (int c = 0; c < NU; ++c) F1[c * TY * W + hf[n]] = Fh[0][c];
         } else {
-          load_raw<ND, 2, CURV>(a, soff + hp[n], raw);
           fluxes_from_raw<ND, 2, CURV>(a, raw, Fh);
 #pragma unroll
           for (int c = 0; c < NU; ++c) F2[c * H * TX + hf[n]] = Fh[1][c];
@@ -262,8 +279,7 @@ __global__ void __launch_bounds__(TX * TYv, (TYv == 8 && R < 4) ? 3 : 2) k_sweep
         if (dissOn) {
 #pragma unroll
           for (int c = 0; c < NU; ++c) QT[c * H * W + hq[n]] = raw.Q[c];
-          if (!COMPOSITE)
-            QT[(FA + hkind[n] - 1) * H * W + hq[n]] = __ldg(a.arc + (size_t)(hkind[n] - 1) * a.cs + soff + hp[n]);
+          if (!COMPOSITE) QT[(FA + hkind[n] - 1) * H * W + hq[n]] = arcH[n];
         }
       }
     }

@@ -1436,6 +1436,7 @@ int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
     for (int d = 0; d < s->nD; ++d) pfl.addIn(a.m + (size_t)(d + s->nD * d) * a.cs, 1);
     pfl.addOut(a.jac, 1);
     pfl.addOut(a.dissIn, s->nU);
+    if (gen == 2 && a.dissOn && !a.composite) pfl.addIn(a.arc, s->nD);
     if (fuseRk && stage != 1) pfl.addOut(a.b2, s->nU);
     if (fuseRk && (stage == 2 || stage == 3)) pfl.addOut(a.b1in, s->nU);
     pfl.finish(&a);
@@ -1538,7 +1539,9 @@ int fill_args_adjoint(mg_state* s, FusedArgs* a) {
   a->tauqIn = s->opt.viscosityOn ? s->tauq.comp(0) : nullptr;
   a->dissOn = s->opt.dissipationOn;
   // measured on B200: adjoint sweep 1 runs faster without the L2 prefetch (sweep 2 overrides this with 1)
-  const int pfAdj = mg_tuning_get("MG_PREFETCH_ADJ", 0);
+  // L2 prefetch distance of adjoint sweep 1: the second-generation kernel is latency bound and gains from it,
+  // the first generation (shared-memory bound) ran faster without
+  const int pfAdj = mg_tuning_get("MG_PREFETCH_ADJ", mg_tuning_get("MG_ADJ1", 2) == 2 ? 1 : 0);
   a->prefetch = pfAdj;
   MG_TRY(upload_ops(s, 1, a));
   return 0;
