@@ -3,7 +3,7 @@
 C3 workload of BASELINE.json (3-D periodic viscous box, SBP 3-6, 16.8 M points per GPU).
 
     python bench.py --gpus N --steps K --warmup W            # this repository (CUDA, sm_100a)
-    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: C/OpenMP restatement of the reference
 
 One "step" = one RK4 time step of the forward solve (4 RHS evaluations + state updates, storing the
 substep states for the adjoint) followed by one RK4 time step of the discrete adjoint (4 adjoint RHS
@@ -95,13 +95,15 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_port_rate(n=48, steps=1, warmup=0):
-    """Time the oracle (NumPy port of the reference algorithm, reference-faithful loop structure incl.
-    per-apply ghost copies) on a bounded sample of the same workload: an n^3 periodic box, forward +
-    adjoint RK4 step.  Returns (point-stages/s, seconds per step, description)."""
-    from oracle import grid as og
+def cpu_port_rate(n=128, steps=1, warmup=1):
+    """Time the C + OpenMP restatement of the reference algorithm (oracle/c/magudi_cpu.c: reference-faithful
+    loop structure incl. per-apply ghosted copies, one thread team over the whole domain in place of the MPI
+    ranks) on a bounded sample of the same workload: ONE n^3 periodic C3 box over all host cores, forward +
+    adjoint RK4 steps.  Returns (point-stages/s, seconds per step, threads, description)."""
+    from oracle import cport, grid as og
     from oracle import rhs as orhs
     from magudi_b200 import workload as wl
+    cport.build()
     shape = (n, n, n)
     g = og.Grid(shape, (og.PLANE,) * 3, (2 * np.pi,) * 3, isCurvilinear=False)
     g.coordinates[:, :] = wl.c3_coordinates(shape, (0, 0, 0), shape)
@@ -113,75 +115,39 @@ def cpu_port_rate(n=48, steps=1, warmup=0):
                              compositeDissipation=False, dissipationAmount=o.dissipationAmount,
                              useTargetState=False, discretizationType="SBP 3-6")
     g.setupSpatialDiscretization("SBP 3-6", False)
-    g.update()
-    s = orhs.State(g, opt)
-    s.conservedVariables[:, :] = wl.c3_initial_condition(g.coordinates)
-    s.adjointVariables[:, :] = wl.c3_adjoint_field(g.nGridPoints)
-    s.update(g, opt)
-    integ = orhs.RK4Integrator(s)
-    rhs_fn = lambda mode, ts, stage: orhs.computeRhs(mode, opt, g, s)
+    g.update()                                   # geometry / operator tables: setup, not timed
+    cp = cport.CPort(g, opt)
+    cp.set("conservedVariables", wl.c3_initial_condition(g.coordinates))
+    cp.set("adjointVariables", wl.c3_adjoint_field(g.nGridPoints))
+    cp.update()
     dt = 1e-3
-
-    def one_step(t):
-        stored = []
-        for stage in range(1, 5):
-            stored.append(s.conservedVariables.copy())
-            t = integ.substepForward(rhs_fn, s, t, dt, 0, stage)
-            s.update(g, opt)
-        for stage in range(4, 0, -1):
-            s.conservedVariables[:, :] = stored[stage - 1]
-            s.update(g, opt)
-            t = integ.substepAdjoint(rhs_fn, s, t, dt, 0, stage)
-        return t
-
-    t = 0.0
     for _ in range(warmup):
-        t = one_step(t)
+        cp.forwardAdjointStep(dt)
     t0 = time.perf_counter()
     for _ in range(steps):
-        t = one_step(t)
+        cp.forwardAdjointStep(dt)
     el = (time.perf_counter() - t0) / steps
-    return 8.0 * g.nGridPoints / el, el, f"{n}^3 periodic box, 1 forward + 1 adjoint RK4 step (8 RHS evals/point), NumPy port"
-
-
-def _cpu_worker(argv):
-    n, steps, warmup = argv
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    rate, sec, _ = cpu_port_rate(n, steps=steps, warmup=warmup)
-    return rate, sec
-
-
-def cpu_port_rate_all_cores(n=48, steps=1, warmup=0, cores=None):
-    """The port on every host core at once: one independent n^3 sample box per core (the reference's MPI
-    build decomposes the domain over the cores the same way; the boxes here do not even pay for halo
-    exchange).  Returns (aggregate point-stages/s, seconds per step, cores, description)."""
-    import multiprocessing as mp
-    cores = cores or len(os.sched_getaffinity(0))
-    if cores <= 1:
-        rate, sec, sample = cpu_port_rate(n, steps, warmup)
-        return rate, sec, 1, sample
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(n, steps, warmup)] * cores)
-    sec = max(r[1] for r in res)
-    rate = cores * 8.0 * n ** 3 / sec
-    return rate, sec, cores, (f"{cores} concurrent {n}^3 periodic boxes (one per host core, 1 NumPy thread each), "
-                              f"1 forward + 1 adjoint RK4 step each (8 RHS evals/point), NumPy port")
+    threads = cport.threads()
+    cp.close()
+    sample = (f"one {n}^3 periodic C3 box (same flags, scheme and initial condition as the GPU workload), "
+              f"{steps} forward + adjoint RK4 step(s) (8 RHS evals/point each) after {warmup} warm-up, "
+              f"C/OpenMP restatement of the reference's loop structure on {threads} threads")
+    return 8.0 * g.nGridPoints / el, el, threads, sample
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_size
-    rate, sec, cores, sample = cpu_port_rate_all_cores(n, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    rate, sec, cores, sample = cpu_port_rate(args.cpu_size, steps=max(1, args.steps), warmup=max(0, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": max(1, args.steps), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+        "steps": max(1, args.steps), "warmup": max(0, args.warmup), "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C3 3-D periodic viscous box (KolmogorovFlow flags), SBP 3-6, forward+adjoint RK4",
                    "sample": sample, "note": "the Fortran/MPI reference cannot be built in this image (no Fortran "
-                   "compiler, no MPI): this arm times the oracle port of its algorithm"},
+                   "compiler, no MPI): this arm times the C/OpenMP restatement of its algorithm (oracle/c) on the "
+                   "host cores; a step is the same forward+adjoint RK4 step as the GPU arm's on a smaller box"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -423,7 +389,7 @@ def run_native(args):
                            "note": "each adjoint stage also restores the stored forward substep state and runs sweep A on it"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, sec, cores, sample = cpu_port_rate_all_cores(args.cpu_size, steps=1, warmup=0)
+        rate, sec, cores, sample = cpu_port_rate(args.cpu_size, steps=2, warmup=1)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -450,7 +416,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--size", type=int, default=0, help="override: size^3 points per GPU")
-    ap.add_argument("--cpu-size", type=int, default=64, help="edge of the bounded CPU sample box")
+    ap.add_argument("--cpu-size", type=int, default=128, help="edge of the bounded CPU sample box")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

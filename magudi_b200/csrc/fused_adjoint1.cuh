@@ -24,8 +24,14 @@ namespace {
 // HOT: viscous + non-composite dissipation known at compile time (the benchmark / AcousticMonopole family);
 // otherwise those switches are runtime-uniform.  TYv: tile height (16 -> 256 threads, 12 -> 192 threads with a
 // 168-register budget at 2 CTAs per SM).
-template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV, bool CLOS, bool HOT, int TYv>
-__global__ void __launch_bounds__(TX * TYv, 2) k_adjoint1v2(FusedArgs a) {
+//
+// TMAQ: the arriving plane of w is fetched by the Tensor Memory Accelerator (one cp.async.bulk.tensor of a
+// 16 x TY x 1 x NU box per plane, issued by thread 0 ONE PLANE AHEAD) straight into its slot of the k-queue, whose
+// [NU][TY][16] layout is exactly the dense box layout; the threads only wait on the slot's mbarrier.  This removes
+// the exposed load -> shared-store dependency at the top of every iteration (24 % of the stall samples of the
+// plain-load variant sat on that STS) and the per-thread address arithmetic of NU loads.
+template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV, bool CLOS, bool HOT, int TYv, bool TMAQ>
+__global__ void __launch_bounds__(TX * TYv, 2) k_adjoint1v2(FusedArgs a, const __grid_constant__ CUtensorMap tmW) {
   constexpr int TY = TYv, NT = TX * TYv;
   const bool COMPOSITE = HOT ? false : a.composite != 0;
   const bool viscous = HOT ? true : (a.viscous ? true : false);
@@ -41,9 +47,11 @@ __global__ void __launch_bounds__(TX * TYv, 2) k_adjoint1v2(FusedArgs a) {
     if constexpr ((NQ & (NQ - 1)) == 0) return x & (NQ - 1);
     else return x < 0 ? x + NQ : (x >= NQ ? x - NQ : x);
   };
-  extern __shared__ double smem[];
-  double* const T0 = smem;                                   // [NF][H][W]
-  double* const WQ = smem + (size_t)NF * H * W;              // [NQ][NU][NT] k-queue of w (thread-private columns)
+  static_assert(!TMAQ || (ND == 3 && NQ == 8 && 2 * R + 1 <= 7), "TMA queue needs a free ring slot");
+  extern __shared__ __align__(1024) double smem[];
+  double* const WQ = smem;                                   // [NQ][NU][NT] k-queue of w (thread-private columns)
+  double* const T0 = smem + (size_t)NQ * NU * NT;            // [NF][H][W]
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(T0 + (size_t)NF * H * W);   // [2]
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   int i0, j0;
   bool lastI, lastJ;
@@ -100,8 +108,21 @@ __global__ void __launch_bounds__(TX * TYv, 2) k_adjoint1v2(FusedArgs a) {
   int slot = 0;                    // queue slot of the arriving plane s
   const double gamma = a.pp.gamma;
   const double sigma = a.dissAmount;
+  constexpr unsigned BOX_BYTES = (unsigned)(sizeof(double) * NU * NT);
+  if constexpr (TMAQ) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      mbar_fence_init();
+      fence_proxy_async();
+      mbar_expect_tx(&bars[0], BOX_BYTES);
+      tma_load_4d(WQ, &tmW, &bars[0], i0, j0, ks + a.ghostK, 0);
+    }
+    __syncthreads();
+  }
+  int nIter = 0;
 
-  for (int s = kc0 - RK; s < kc1 + RK; ++s) {
+  for (int s = kc0 - RK; s < kc1 + RK; ++s, ++nIter) {
     if (ND == 3 && a.prefetch) {
       // pull the lines of the planes needed `prefetch` steps ahead into L2 (costs no registers)
       int kf = ks + a.prefetch, kq = ks - RK + a.prefetch;
@@ -109,7 +130,18 @@ __global__ void __launch_bounds__(TX * TYv, 2) k_adjoint1v2(FusedArgs a) {
       prefetch_streams(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz),
                        (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
     }
-    if (inside) {
+    if constexpr (TMAQ) {
+      // request plane s + 1 (its ring slot was last read two iterations ago), then wait for plane s
+      if (threadIdx.x == 0 && s + 1 < kc1 + RK) {
+        int kn = ks + 1;
+        if (a.wrapK && kn >= a.nz) kn -= a.nz;
+        unsigned long long* bar = &bars[(nIter + 1) & 1];
+        fence_proxy_async();
+        mbar_expect_tx(bar, BOX_BYTES);
+        tma_load_4d(WQ + (size_t)ringw(slot + 1) * NU * NT, &tmW, bar, i0, j0, kn + a.ghostK, 0);
+      }
+      mbar_wait(&bars[nIter & 1], (unsigned)((nIter >> 1) & 1));
+    } else if (inside) {
       const double* __restrict__ Wp = a.Win + ((ND == 3) ? (long)ks * a.plane : 0) + pij;
       double wv[NU];
 #pragma unroll
@@ -126,7 +158,10 @@ __global__ void __launch_bounds__(TX * TYv, 2) k_adjoint1v2(FusedArgs a) {
       if (a.wrapK && ks >= a.nz) ks -= a.nz;
       slot = ringw(slot + 1);
     }
-    if (p < kc0) continue;
+    if (p < kc0) {
+      if constexpr (TMAQ) __syncthreads();   // every thread has passed its wait before the barrier is re-armed
+      continue;
+    }
     const long poff = (ND == 3) ? (long)kp * a.plane : 0;
     const long off = poff + pij;
     // ---- in-plane tile of plane p: own point from the queue, halo (and arc lengths) from global memory
@@ -313,31 +348,33 @@ __global__ void __launch_bounds__(TX * TYv, 2) k_adjoint1v2(FusedArgs a) {
   }
 }
 
-template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV, bool CLOS, bool HOT, int TYv>
-int launchAdj1v2(const FusedArgs& a, int nChunks, cudaStream_t st) {
+template <int ND, int R, int DLO, int DN, int TLO, int TN, bool CURV, bool CLOS, bool HOT, int TYv, bool TMAQ>
+int launchAdj1v2(const FusedArgs& a, int nChunks, cudaStream_t st, const CUtensorMap* tmW) {
   constexpr int NF = (ND + 2) + 2;
   constexpr int NQ = (ND == 3) ? (2 * R + 1 <= 8 ? 8 : 2 * R + 1) : 1;
   constexpr int NT = TX * TYv;
   static_assert(NT >= 2 * R * (TX + TYv), "one halo point per thread");
-  const size_t smem = sizeof(double) * ((size_t)NF * (TYv + 2 * R) * (TX + 2 * R) + (size_t)NQ * (ND + 2) * NT);
-  auto kern = k_adjoint1v2<ND, R, DLO, DN, TLO, TN, CURV, CLOS, HOT, TYv>;
+  const size_t smem = sizeof(double) * ((size_t)NF * (TYv + 2 * R) * (TX + 2 * R) + (size_t)NQ * (ND + 2) * NT) + 16;
+  auto kern = k_adjoint1v2<ND, R, DLO, DN, TLO, TN, CURV, CLOS, HOT, TYv, TMAQ>;
   MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const dim3 grid((a.nx + TX - 1) / TX, (a.ny + TYv - 1) / TYv, nChunks);
+  CUtensorMap none;
+  std::memset(&none, 0, sizeof(none));
   mg_profile_begin("adjoint1");
-  kern<<<grid, NT, smem, st>>>(a);
+  kern<<<grid, NT, smem, st>>>(a, tmW ? *tmW : none);
   mg_profile_end();
   MG_CUDA(cudaGetLastError());
   mg_count_launches(1);
   return 0;
 }
 
-template <int ND, int R, int DLO, int DN, int TLO, int TN, bool HOT, int TYv>
-int dispatchAdj1v2(const FusedArgs& a, int nChunks, cudaStream_t st) {
+template <int ND, int R, int DLO, int DN, int TLO, int TN, bool HOT, int TYv, bool TMAQ = false>
+int dispatchAdj1v2(const FusedArgs& a, int nChunks, cudaStream_t st, const CUtensorMap* tmW = nullptr) {
   const bool clos = has_closures(a);
-  return a.curvilinear ? (clos ? launchAdj1v2<ND, R, DLO, DN, TLO, TN, true, true, HOT, TYv>(a, nChunks, st)
-                               : launchAdj1v2<ND, R, DLO, DN, TLO, TN, true, false, HOT, TYv>(a, nChunks, st))
-                       : (clos ? launchAdj1v2<ND, R, DLO, DN, TLO, TN, false, true, HOT, TYv>(a, nChunks, st)
-                               : launchAdj1v2<ND, R, DLO, DN, TLO, TN, false, false, HOT, TYv>(a, nChunks, st));
+  return a.curvilinear ? (clos ? launchAdj1v2<ND, R, DLO, DN, TLO, TN, true, true, HOT, TYv, TMAQ>(a, nChunks, st, tmW)
+                               : launchAdj1v2<ND, R, DLO, DN, TLO, TN, true, false, HOT, TYv, TMAQ>(a, nChunks, st, tmW))
+                       : (clos ? launchAdj1v2<ND, R, DLO, DN, TLO, TN, false, true, HOT, TYv, TMAQ>(a, nChunks, st, tmW)
+                               : launchAdj1v2<ND, R, DLO, DN, TLO, TN, false, false, HOT, TYv, TMAQ>(a, nChunks, st, tmW));
 }
 
 }  // namespace

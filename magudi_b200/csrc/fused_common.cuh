@@ -7,6 +7,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda.h>
+
 #include "grid.h"
 #include "rhs_fused.h"
 #include "stencil_apply.h"
@@ -37,6 +39,7 @@ struct FusedArgs {
   long plane;
   size_t cs;                    // component stride of every field
   int wrapK;                    // 1: single rank, periodic in k -> wrap plane index; 0: read ghost planes
+  int ghostK;                   // ghost planes below plane 0 in storage (TMA coordinates count from the storage start)
   int kBeg, kEnd, kChunk;
   int curvilinear, viscous;
   DirInfo dir[3];
@@ -351,6 +354,7 @@ int fill_args(mg_state* s, FusedArgs* a) {
   a->plane = (long)g->plane;
   a->cs = s->rhs.compStride;
   a->wrapK = (g->nD == 3 && g->procDims[2] == 1) ? 1 : 0;
+  a->ghostK = g->gk;
   a->kBeg = 0;
   a->kEnd = g->localSize[2];
   a->kChunk = g->localSize[2];
@@ -447,6 +451,73 @@ dim3 tiles(const FusedArgs& a, int nChunks) {
 // carries the out-of-line closure path; fully periodic in-plane grids run the variant without it.
 bool has_closures(const FusedArgs& a) {
   return a.dir[0].hasB0 || a.dir[0].hasB1 || a.dir[1].hasB0 || a.dir[1].hasB1;
+}
+
+// ------------------------------------------------------------------------------ TMA (bulk tensor copies)
+// One elected thread asks the Tensor Memory Accelerator for a whole box of a field (cp.async.bulk.tensor ->
+// SASS UTMALDG); the bytes land in shared memory asynchronously and complete an mbarrier transaction the
+// consumers wait on.  No registers, no per-thread address arithmetic, and the request is issued one plane ahead.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MG_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MG_DONE_%=;\n"
+      "bra MG_WAIT_%=;\n"
+      "MG_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3) : "memory");
+}
+
+// Tensor map over a library field: dims (i, j, storage plane incl. ghost planes, component), fp64, no swizzle.
+// Returns false when the layout does not meet the TMA alignment rules (odd nx) or the driver entry point is
+// missing; the caller then launches the plain-load variant of the kernel.
+inline bool make_field_tensor_map(const mg_grid* g, const MgField& f, int boxX, int boxY, int boxC, CUtensorMap* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeFn>(fn);
+    else
+      cudaGetLastError();
+  }
+  if (!encode) return false;
+  const cuuint64_t nx = g->localSize[0], ny = g->localSize[1];
+  const cuuint64_t planes = f.compStride / g->plane;         // nz + 2 * ghost planes
+  if ((nx * sizeof(double)) % 16 || ((size_t)f.p % 16) || (f.compStride * sizeof(double)) % 16) return false;
+  const cuuint64_t dims[4] = {nx, ny, planes, (cuuint64_t)f.nComp};
+  const cuuint64_t strides[3] = {nx * sizeof(double), (cuuint64_t)g->plane * sizeof(double),
+                                 (cuuint64_t)f.compStride * sizeof(double)};
+  const cuuint32_t box[4] = {(cuuint32_t)boxX, (cuuint32_t)boxY, 1u, (cuuint32_t)boxC};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, f.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace

@@ -136,12 +136,22 @@ __global__ void __launch_bounds__(TX * TYv, (TYv == 8 && R < 4) ? 3 : 2) k_sweep
     auto emit_load = [&](int kpl) {
       const long off = ((ND == 3) ? (long)kpl * a.plane : 0) + pij;
       ejac = __ldg(a.jac + off);
-      if (a.fuseRk) {
 #pragma unroll
-        for (int c = 0; c < NU; ++c) {
-          const size_t qi = (size_t)c * a.cs + off;
-          vb1[c] = (a.stage == 1) ? __ldg(a.Q + qi) : ((a.stage == 4) ? 0.0 : a.b1in[qi]);
-          vb2[c] = (a.stage == 1) ? 0.0 : a.b2[qi];
+      for (int c = 0; c < NU; ++c) { vb1[c] = 0.0; vb2[c] = 0.0; }
+      // RK buffers: one uniform branch on the stage, not one per component
+      if (a.fuseRk) {
+        if (a.stage == 1) {
+#pragma unroll
+          for (int c = 0; c < NU; ++c) vb1[c] = __ldg(a.Q + (size_t)c * a.cs + off);
+        } else if (a.stage == 4) {
+#pragma unroll
+          for (int c = 0; c < NU; ++c) vb2[c] = a.b2[(size_t)c * a.cs + off];
+        } else {
+#pragma unroll
+          for (int c = 0; c < NU; ++c) {
+            vb1[c] = a.b1in[(size_t)c * a.cs + off];
+            vb2[c] = a.b2[(size_t)c * a.cs + off];
+          }
         }
       }
     };
@@ -153,12 +163,20 @@ __global__ void __launch_bounds__(TX * TYv, (TYv == 8 && R < 4) ? 3 : 2) k_sweep
       if (!a.fuseRk) {
 #pragma unroll
         for (int c = 0; c < NU; ++c) a.rhs[(size_t)c * a.cs + off] = r[c];
+      } else if (a.stage == 1) {
+#pragma unroll
+        for (int c = 0; c < NU; ++c) {
+          a.b2[(size_t)c * a.cs + off] = vb1[c] + a.rkB * r[c];
+          a.Qout[(size_t)c * a.cs + off] = vb1[c] + a.rkQ * r[c];
+        }
+      } else if (a.stage == 4) {
+#pragma unroll
+        for (int c = 0; c < NU; ++c) a.Qout[(size_t)c * a.cs + off] = vb2[c] + a.rkQ * r[c];
       } else {
 #pragma unroll
         for (int c = 0; c < NU; ++c) {
-          const size_t qi = (size_t)c * a.cs + off;
-          if (a.stage != 4) a.b2[qi] = ((a.stage == 1) ? vb1[c] : vb2[c]) + a.rkB * r[c];
-          a.Qout[qi] = ((a.stage == 4) ? vb2[c] : vb1[c]) + a.rkQ * r[c];
+          a.b2[(size_t)c * a.cs + off] = vb2[c] + a.rkB * r[c];
+          a.Qout[(size_t)c * a.cs + off] = vb1[c] + a.rkQ * r[c];
         }
       }
     };

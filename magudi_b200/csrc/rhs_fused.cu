@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(NT, 3) k_sweepA(FusedArgs a) {
         }
       }
       double mu, lam, kap, tau[ND * ND];
-      transport(Tp, a.pp, mu, lam, kap);
+      transport<true>(Tp, a.pp, mu, lam, kap);   // exp(n log x): ~2 ulp, well under half of pow()'s instructions
       stress_from_gradient<ND>(g, mu, lam, tau);
       int t = 0;
 #pragma unroll
@@ -1063,12 +1063,28 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint2(FusedArgs a) {
       jac = __ldg(a.jac + off);
 #pragma unroll
       for (int c = 0; c < NU; ++c) {
-        const size_t qi = (size_t)c * a.cs + off;
-        rp[c] = a.rhsIn[qi];
-        if (a.viscous) Q[c] = __ldg(a.Q + qi);
-        if (a.fuseRk) {
-          vb1[c] = (a.stage == 1) ? a.Win[qi] : ((a.stage == 4) ? 0.0 : a.b1in[qi]);
-          vb2[c] = (a.stage == 1) ? 0.0 : a.b2[qi];
+        rp[c] = a.rhsIn[(size_t)c * a.cs + off];
+        vb1[c] = 0.0;
+        vb2[c] = 0.0;
+      }
+      if (a.viscous) {
+#pragma unroll
+        for (int c = 0; c < NU; ++c) Q[c] = __ldg(a.Q + (size_t)c * a.cs + off);
+      }
+      // RK buffers: one uniform branch on the stage, not one per component
+      if (a.fuseRk) {
+        if (a.stage == 1) {
+#pragma unroll
+          for (int c = 0; c < NU; ++c) vb1[c] = a.Win[(size_t)c * a.cs + off];
+        } else if (a.stage == 4) {
+#pragma unroll
+          for (int c = 0; c < NU; ++c) vb2[c] = a.b2[(size_t)c * a.cs + off];
+        } else {
+#pragma unroll
+          for (int c = 0; c < NU; ++c) {
+            vb1[c] = a.b1in[(size_t)c * a.cs + off];
+            vb2[c] = a.b2[(size_t)c * a.cs + off];
+          }
         }
       }
     }
@@ -1139,12 +1155,20 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint2(FusedArgs a) {
       if (!a.fuseRk) {
 #pragma unroll
         for (int c = 0; c < NU; ++c) a.rhs[(size_t)c * a.cs + off] = r[c];
+      } else if (a.stage == 1) {
+#pragma unroll
+        for (int c = 0; c < NU; ++c) {
+          a.b2[(size_t)c * a.cs + off] = vb1[c] + a.rkB * r[c];
+          a.Qout[(size_t)c * a.cs + off] = vb1[c] + a.rkQ * r[c];
+        }
+      } else if (a.stage == 4) {
+#pragma unroll
+        for (int c = 0; c < NU; ++c) a.Qout[(size_t)c * a.cs + off] = vb2[c] + a.rkQ * r[c];
       } else {
 #pragma unroll
         for (int c = 0; c < NU; ++c) {
-          const size_t qi = (size_t)c * a.cs + off;
-          if (a.stage != 4) a.b2[qi] = ((a.stage == 1) ? vb1[c] : vb2[c]) + a.rkB * r[c];
-          a.Qout[qi] = ((a.stage == 4) ? vb2[c] : vb1[c]) + a.rkQ * r[c];
+          a.b2[(size_t)c * a.cs + off] = vb2[c] + a.rkB * r[c];
+          a.Qout[(size_t)c * a.cs + off] = vb1[c] + a.rkQ * r[c];
         }
       }
     }
@@ -1575,11 +1599,15 @@ int mg_fused_adjoint1(mg_state* s) {
   if (gen == 2) {
     const bool hot = a.viscous && a.dissOn && !a.composite;
     // tile height 12 (192 threads, 168 registers) exists for the 3-D hot instantiations with R <= 3
-    const int tyPref = mg_tuning_get("MG_ADJ1_TY", 16);
+    const int tyPref = mg_tuning_get("MG_ADJ1_TY", 12);
     int tileY = (tyPref == 12 && hot && s->nD == 3 && si.R <= 3) ? 12 : 16;
     if (tileY != 16 && !dir_fits_tile(g, 1, tileY, si.R, MG_ADJOINT)) tileY = 16;
     const int nChunks2 = choose_chunks(&a, si.R, 2, TX, tileY);
-    const int rc2 = hot ? mg_fused_adjoint1_hot_launch(&a, s->nD, si.R, tileY, nChunks2, st)
+    // TMA-fed k-queue (cp.async.bulk.tensor): 3-D hot instantiations with 16 x 12 tiles; MG_TMA=0 disables
+    CUtensorMap tmW;
+    const bool useTma = hot && tileY == 12 && s->nD == 3 && si.R <= 3 && mg_tuning_get("MG_TMA", 1) &&
+                        make_field_tensor_map(g, s->W[s->curW], TX, tileY, s->nU, &tmW);
+    const int rc2 = hot ? mg_fused_adjoint1_hot_launch(&a, s->nD, si.R, tileY, nChunks2, st, useTma ? &tmW : nullptr)
                         : mg_fused_adjoint1_gen_launch(&a, s->nD, si.R, tileY, nChunks2, st);
     if (rc2 == -1) MG_FAIL("fused adjoint sweep 1: unsupported configuration");
     return rc2;

@@ -6,7 +6,8 @@
 int mg_fused_supported(const mg_state* s, int mode);
 
 // Second-generation kernels living in their own translation units (args = the caller's FusedArgs block).
-int mg_fused_adjoint1_hot_launch(const void* args, int nD, int R, int tileY, int nChunks, cudaStream_t st);
+int mg_fused_adjoint1_hot_launch(const void* args, int nD, int R, int tileY, int nChunks, cudaStream_t st,
+                                 const void* tensorMapW);
 int mg_fused_adjoint1_gen_launch(const void* args, int nD, int R, int tileY, int nChunks, cudaStream_t st);
 int mg_fused_sweepbd_hot_launch(const void* args, int nD, int R, int tileY, int nChunks, cudaStream_t st);
 int mg_fused_sweepbd_gen_launch(const void* args, int nD, int R, int tileY, int nChunks, cudaStream_t st);
