@@ -164,6 +164,10 @@ int mg_p2p_handle_size(void);
 int mg_p2p_get_handle(mg_p2p* h, void* handleOut);
 int mg_p2p_connect(mg_p2p* h, int side, const void* peerHandle, int sameAsOther);
 int mg_p2p_exchange(mg_p2p* h, void* owner, int field, int width);
+/* the same exchange on a second stream, ordered after the work enqueued so far: the next fused sweep launches its
+ * interior k-chunks first (they read no ghost plane), then waits for the exchange and launches the first and the
+ * last chunk -- the counterpart of "overlapped with interior stencil work" for fillGhostPoints */
+int mg_p2p_exchange_overlapped(mg_p2p* h, void* owner, int field, int width);
 int mg_p2p_check(mg_p2p* h);
 int mg_p2p_destroy(mg_p2p* h);
 

@@ -86,6 +86,7 @@ SIGNATURES = {
     "mg_p2p_get_handle": (C.c_int, [_P, _P]),
     "mg_p2p_connect": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "mg_p2p_exchange": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "mg_p2p_exchange_overlapped": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "mg_p2p_check": (C.c_int, [_P]),
     "mg_p2p_destroy": (C.c_int, [_P]),
     "mg_state_create": (C.c_int, [_P, C.POINTER(Options), C.POINTER(_P)]),

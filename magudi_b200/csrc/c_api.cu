@@ -29,6 +29,35 @@ int mg_cuda_fail(cudaError_t e, const char* file, int line) {
 cudaStream_t mg_stream() { return g_stream; }
 
 namespace {
+cudaStream_t g_haloStream = nullptr;
+cudaEvent_t g_haloPending = nullptr;
+bool g_haloIsPending = false;
+}  // namespace
+cudaStream_t mg_halo_stream() {
+  if (!g_haloStream) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&g_haloStream, cudaStreamNonBlocking, hi) != cudaSuccess) {
+      cudaGetLastError();
+      g_haloStream = g_stream;
+    }
+  }
+  return g_haloStream;
+}
+void mg_halo_set_pending(cudaEvent_t ev) { g_haloPending = ev; g_haloIsPending = true; }
+bool mg_halo_take_pending(cudaEvent_t* ev) {
+  if (!g_haloIsPending) return false;
+  *ev = g_haloPending;
+  g_haloIsPending = false;
+  return true;
+}
+int mg_halo_wait_pending() {
+  cudaEvent_t ev;
+  if (mg_halo_take_pending(&ev)) MG_CUDA(cudaStreamWaitEvent(g_stream, ev, 0));
+  return 0;
+}
+
+namespace {
 std::map<std::string, int> g_tuning;
 std::mutex g_tuningMutex;
 }  // namespace
@@ -132,6 +161,7 @@ const char* mg_last_error(void) { return g_error.c_str(); }
 int mg_version(void) { return 100; }
 int mg_synchronize(void) {
   if (g_device < 0) MG_FAIL("mg_synchronize: mg_init has not been called");
+  MG_TRY(mg_halo_wait_pending());
   MG_CUDA(cudaStreamSynchronize(g_stream));
   return 0;
 }

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(TX * TYv, 2) k_adjoint1v2(FusedArgs a, const _
     }
   }
   double* const th = T0 + hrow * W + hcol;
-  const int kc0 = a.kBeg + blockIdx.z * a.kChunk;
+  const int kc0 = a.kBeg + (a.zOff + (int)blockIdx.z * a.zMul) * a.kChunk;
   const int kc1 = min(kc0 + a.kChunk, a.kEnd);
   auto wrapPlane = [&](int k) -> int {
     if (ND < 3 || !a.wrapK) return k;

@@ -41,6 +41,7 @@ struct FusedArgs {
   int wrapK;                    // 1: single rank, periodic in k -> wrap plane index; 0: read ghost planes
   int ghostK;                   // ghost planes below plane 0 in storage (TMA coordinates count from the storage start)
   int kBeg, kEnd, kChunk;
+  int zOff, zMul;               // k-chunk of a block = zOff + blockIdx.z * zMul (interior / boundary chunk launches)
   int curvilinear, viscous;
   DirInfo dir[3];
   LineOp D[3], Dd[3], Dt[3];    // first derivative, dissipation, dissipation transpose
@@ -358,6 +359,8 @@ int fill_args(mg_state* s, FusedArgs* a) {
   a->kBeg = 0;
   a->kEnd = g->localSize[2];
   a->kChunk = g->localSize[2];
+  a->zOff = 0;
+  a->zMul = 1;
   a->curvilinear = g->isCurvilinear;
   a->viscous = s->opt.viscosityOn;
   for (int d = 0; d < g->nD; ++d) {
@@ -451,6 +454,31 @@ dim3 tiles(const FusedArgs& a, int nChunks) {
 // carries the out-of-line closure path; fully periodic in-plane grids run the variant without it.
 bool has_closures(const FusedArgs& a) {
   return a.dir[0].hasB0 || a.dir[0].hasB1 || a.dir[1].hasB0 || a.dir[1].hasB1;
+}
+
+// Launch a sweep of nChunks k-chunks.  When an overlapped halo exchange is still in flight on the halo stream
+// (mg_p2p_exchange_overlapped), the interior chunks - which read no ghost plane - are launched first, the main
+// stream then waits for the exchange, and the first and last chunk follow: the exchange (and the skew between
+// neighbouring ranks it absorbs) hides behind the interior work.  go(args, zBlocks, label) launches the kernel.
+template <class F>
+int launch_split(FusedArgs& a, int nChunks, int R, F&& go) {
+  cudaEvent_t ev;
+  if (!mg_halo_take_pending(&ev)) return go(a, nChunks, false);
+  const bool split = nChunks >= 3 && a.kChunk >= R && a.kBeg == 0;
+  int rc = 0;
+  if (split) {
+    a.zOff = 1; a.zMul = 1;
+    rc = go(a, nChunks - 2, false);
+  }
+  MG_CUDA(cudaStreamWaitEvent(mg_stream(), ev, 0));
+  if (rc != 0) return rc;
+  if (split) {
+    a.zOff = 0; a.zMul = nChunks - 1;
+    rc = go(a, 2, true);
+    a.zOff = 0; a.zMul = 1;
+    return rc;
+  }
+  return go(a, nChunks, false);
 }
 
 // ------------------------------------------------------------------------------ TMA (bulk tensor copies)

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(TX * TYv, (TYv == 8 && R < 4) ? 3 : 2) k_sweep
       if (gj >= 0 && gi < a.nx) { hkind[n] = 2; hp[n] = (long)gi + (long)a.nx * gj; }
     }
   }
-  const int kc0 = a.kBeg + blockIdx.z * a.kChunk;
+  const int kc0 = a.kBeg + (a.zOff + (int)blockIdx.z * a.zMul) * a.kChunk;
   const int kc1 = min(kc0 + a.kChunk, a.kEnd);
   auto wrapPlane = [&](int k) -> int {
     if (ND < 3 || !a.wrapK) return k;

@@ -118,6 +118,12 @@ int mg_field_upload(const mg_grid* g, MgField* f, const double* host);     // ho
 int mg_field_download(const mg_grid* g, const MgField* f, double* host);
 
 cudaStream_t mg_stream();
+// Second (high-priority) stream for overlapped halo exchanges, and the event of the last exchange still in
+// flight on it: the next fused sweep takes it (launch_split), anything else waits through mg_halo_wait_pending.
+cudaStream_t mg_halo_stream();
+void mg_halo_set_pending(cudaEvent_t ev);
+bool mg_halo_take_pending(cudaEvent_t* ev);
+int mg_halo_wait_pending();
 // Tuning switches of the fused kernels (kernel generation, tile heights, k-chunks, L2 prefetch distance):
 // mg_tuning_set (C ABI) wins over the environment variable of the same name, which wins over the default.
 int mg_tuning_get(const char* name, int dflt);

@@ -143,6 +143,8 @@ struct mg_p2p {
   unsigned int* counters = nullptr;     // [4] local block counters
   int* error = nullptr;                 // device error flag (spin timeout)
   size_t bytes = 0;
+  cudaEvent_t evProduced = nullptr, evDone[4] = {nullptr, nullptr, nullptr, nullptr};
+  int nextDone = 0;
   Shared* flags() const { return reinterpret_cast<Shared*>(base); }
   static size_t bufOffset(size_t cap, int face, int parity) {
     return sizeof(Shared) + ((size_t)face * 2 + parity) * cap * sizeof(double);
@@ -194,8 +196,36 @@ int mg_p2p_connect(mg_p2p* h, int side, const void* peerHandle, int sameAsOther)
   return 0;
 }
 
+static int p2p_exchange_on(mg_p2p* h, void* owner, int field, int width, cudaStream_t st);
+
 // Exchange `width` ghost planes of a field with both k-neighbours.  Asynchronous on the library stream.
 int mg_p2p_exchange(mg_p2p* h, void* owner, int field, int width) {
+  MG_TRY(mg_halo_wait_pending());
+  return p2p_exchange_on(h, owner, field, width, mg_stream());
+}
+
+// The same exchange on the library's halo stream, ordered after everything enqueued so far on the main stream:
+// it overlaps with the interior k-chunks of the next fused sweep, which takes the completion event
+// (fused_common.cuh: launch_split); any other consumer waits for it in mg_synchronize / mg_p2p_exchange.
+int mg_p2p_exchange_overlapped(mg_p2p* h, void* owner, int field, int width) {
+  if (!h) MG_FAIL("mg_p2p_exchange_overlapped: null handle");
+  cudaStream_t hs = mg_halo_stream();
+  if (hs == mg_stream()) return mg_p2p_exchange(h, owner, field, width);
+  if (!h->evProduced) {
+    MG_CUDA(cudaEventCreateWithFlags(&h->evProduced, cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) MG_CUDA(cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming));
+  }
+  MG_CUDA(cudaEventRecord(h->evProduced, mg_stream()));
+  MG_CUDA(cudaStreamWaitEvent(hs, h->evProduced, 0));
+  MG_TRY(p2p_exchange_on(h, owner, field, width, hs));
+  cudaEvent_t done = h->evDone[h->nextDone];
+  h->nextDone = (h->nextDone + 1) % 4;
+  MG_CUDA(cudaEventRecord(done, hs));
+  mg_halo_set_pending(done);     // a later exchange on the same stream supersedes an earlier one
+  return 0;
+}
+
+static int p2p_exchange_on(mg_p2p* h, void* owner, int field, int width, cudaStream_t st) {
   if (!h) MG_FAIL("mg_p2p_exchange: null handle");
   mg_grid* g = h->grid;
   MgField* f = mg_lookup_field(g, owner, field);
@@ -204,7 +234,6 @@ int mg_p2p_exchange(mg_p2p* h, void* owner, int field, int width) {
   if (width > g->gk || width > g->localSize[2]) MG_FAIL("mg_p2p_exchange: width exceeds ghost capacity");
   if (f->nComp > MG_P2P_MAX_COMP || chunk * (size_t)f->nComp > h->capacity)
     MG_FAIL("mg_p2p_exchange: field exceeds the staging capacity");
-  cudaStream_t st = mg_stream();
   const unsigned long long n = h->uses[0];
   const int parity = (int)(n & 1);
   const unsigned long long use = n >> 1;
@@ -260,6 +289,7 @@ int mg_p2p_exchange(mg_p2p* h, void* owner, int field, int width) {
 int mg_p2p_check(mg_p2p* h) {
   if (!h) MG_FAIL("mg_p2p_check: null handle");
   int e = 0;
+  MG_TRY(mg_halo_wait_pending());
   MG_CUDA(cudaStreamSynchronize(mg_stream()));
   MG_CUDA(cudaMemcpy(&e, h->error, sizeof(int), cudaMemcpyDeviceToHost));
   if (e) MG_FAIL("mg_p2p: a halo exchange timed out waiting for its neighbour");

@@ -7,6 +7,7 @@ exchanged once per sweep with the two k-neighbours (periodic wrap included), and
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -136,12 +137,19 @@ class GpuHalo:
             same = 1 if (side == 1 and prev is not None and prev == nxt) else 0
             check(lib.mg_p2p_connect(h, side, hb, same))
 
-    def exchange(self, owner, field, ncomp, width=3):
+    def exchange(self, owner, field, ncomp, width=3, overlap=None):
+        """Exchange ``width`` ghost planes of a library field with both k-neighbours.  ``overlap`` (default:
+        environment ``MG_OVERLAP``, on) runs a state-field exchange on the library's halo stream so that the next
+        fused sweep computes its interior k-chunks while the planes travel; grid fields (setup) are exchanged
+        in stream order."""
         lib = L.lib()
         g = self.grid._h
         oh = owner._h if owner is not None else None
+        if overlap is None:
+            overlap = owner is not None and os.environ.get("MG_OVERLAP", "1") != "0"
         if self._p2p is not None:
-            check(lib.mg_p2p_exchange(self._p2p, oh, field, width))
+            fn = lib.mg_p2p_exchange_overlapped if overlap else lib.mg_p2p_exchange
+            check(fn(self._p2p, oh, field, width))
             return
 
         def pack(side, w, buf):
