@@ -51,10 +51,33 @@ bool mg_halo_take_pending(cudaEvent_t* ev) {
   g_haloIsPending = false;
   return true;
 }
+namespace {
+cudaEvent_t g_boundaryEv[4] = {nullptr, nullptr, nullptr, nullptr};
+int g_boundaryNext = 0;
+cudaEvent_t g_boundaryPending = nullptr;
+bool g_profSuppress = false;
+}  // namespace
+void mg_profile_suppress(bool on) { g_profSuppress = on; }
+int mg_halo_mark_boundary() {
+  if (!g_boundaryEv[0])
+    for (auto& e : g_boundaryEv) MG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaEvent_t e = g_boundaryEv[g_boundaryNext];
+  g_boundaryNext = (g_boundaryNext + 1) % 4;
+  MG_CUDA(cudaEventRecord(e, mg_halo_stream()));
+  g_boundaryPending = e;
+  return 0;
+}
+int mg_halo_wait_boundary() {
+  if (g_boundaryPending) {
+    MG_CUDA(cudaStreamWaitEvent(g_stream, g_boundaryPending, 0));
+    g_boundaryPending = nullptr;
+  }
+  return 0;
+}
 int mg_halo_wait_pending() {
   cudaEvent_t ev;
   if (mg_halo_take_pending(&ev)) MG_CUDA(cudaStreamWaitEvent(g_stream, ev, 0));
-  return 0;
+  return mg_halo_wait_boundary();
 }
 
 namespace {
@@ -83,7 +106,7 @@ bool g_profOn = false;
 }  // namespace
 bool mg_profile_on() { return g_profOn; }
 void mg_profile_begin(const char* name) {
-  if (!g_profOn) return;
+  if (!g_profOn || g_profSuppress) return;
   ProfEntry p;
   p.name = name;
   cudaEventCreate(&p.e0);
@@ -92,7 +115,7 @@ void mg_profile_begin(const char* name) {
   g_prof.push_back(p);
 }
 void mg_profile_end() {
-  if (!g_profOn || g_prof.empty()) return;
+  if (!g_profOn || g_profSuppress || g_prof.empty()) return;
   cudaEventRecord(g_prof.back().e1, g_stream);
 }
 

@@ -456,29 +456,31 @@ bool has_closures(const FusedArgs& a) {
   return a.dir[0].hasB0 || a.dir[0].hasB1 || a.dir[1].hasB0 || a.dir[1].hasB1;
 }
 
-// Launch a sweep of nChunks k-chunks.  When an overlapped halo exchange is still in flight on the halo stream
-// (mg_p2p_exchange_overlapped), the interior chunks - which read no ghost plane - are launched first, the main
-// stream then waits for the exchange, and the first and last chunk follow: the exchange (and the skew between
-// neighbouring ranks it absorbs) hides behind the interior work.  go(args, zBlocks, label) launches the kernel.
+// Launch a sweep of nChunks k-chunks.  When an overlapped halo exchange is in flight on the halo stream
+// (mg_p2p_exchange_overlapped), the interior chunks - which read no ghost plane - go to the main stream at once
+// and the first and the last chunk are queued on the HALO stream behind the exchange: they start as soon as the
+// planes have arrived and fill the SMs the interior launch frees in its tail.  The event recorded after them is
+// what the next launch on the main stream waits for.  go(args, zBlocks, stream) launches the kernel.
 template <class F>
 int launch_split(FusedArgs& a, int nChunks, int R, F&& go) {
   cudaEvent_t ev;
-  if (!mg_halo_take_pending(&ev)) return go(a, nChunks, false);
+  const bool exchange = mg_halo_take_pending(&ev);
+  MG_TRY(mg_halo_wait_boundary());          // the previous sweep's boundary chunks (halo stream) must be done
+  if (!exchange) return go(a, nChunks, mg_stream());
   const bool split = nChunks >= 3 && a.kChunk >= R && a.kBeg == 0;
-  int rc = 0;
-  if (split) {
-    a.zOff = 1; a.zMul = 1;
-    rc = go(a, nChunks - 2, false);
+  if (!split) {
+    MG_CUDA(cudaStreamWaitEvent(mg_stream(), ev, 0));
+    return go(a, nChunks, mg_stream());
   }
-  MG_CUDA(cudaStreamWaitEvent(mg_stream(), ev, 0));
+  a.zOff = 1; a.zMul = 1;
+  int rc = go(a, nChunks - 2, mg_stream());
+  a.zOff = 0; a.zMul = nChunks - 1;
+  mg_profile_suppress(true);                // the timing events live on the main stream
+  if (rc == 0) rc = go(a, 2, mg_halo_stream());
+  mg_profile_suppress(false);
+  a.zOff = 0; a.zMul = 1;
   if (rc != 0) return rc;
-  if (split) {
-    a.zOff = 0; a.zMul = nChunks - 1;
-    rc = go(a, 2, true);
-    a.zOff = 0; a.zMul = 1;
-    return rc;
-  }
-  return go(a, nChunks, false);
+  return mg_halo_mark_boundary();
 }
 
 // ------------------------------------------------------------------------------ TMA (bulk tensor copies)

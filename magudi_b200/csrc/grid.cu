@@ -35,6 +35,7 @@ int mg_field_zero(const mg_grid* g, MgField* f) {
 }
 
 int mg_field_upload(const mg_grid* g, MgField* f, const double* host) {
+  MG_TRY(mg_halo_wait_pending());   // boundary chunks / exchanges still in flight on the halo stream
   for (int c = 0; c < f->nComp; ++c)
     MG_CUDA(cudaMemcpyAsync(f->comp(c), host + (size_t)c * g->N, g->N * sizeof(double), cudaMemcpyDefault,
                             mg_stream()));
@@ -43,6 +44,7 @@ int mg_field_upload(const mg_grid* g, MgField* f, const double* host) {
 }
 
 int mg_field_download(const mg_grid* g, const MgField* f, double* host) {
+  MG_TRY(mg_halo_wait_pending());   // boundary chunks / exchanges still in flight on the halo stream
   for (int c = 0; c < f->nComp; ++c)
     MG_CUDA(cudaMemcpyAsync(host + (size_t)c * g->N, f->comp(c), g->N * sizeof(double), cudaMemcpyDefault,
                             mg_stream()));

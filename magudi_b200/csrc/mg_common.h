@@ -123,7 +123,10 @@ cudaStream_t mg_stream();
 cudaStream_t mg_halo_stream();
 void mg_halo_set_pending(cudaEvent_t ev);
 bool mg_halo_take_pending(cudaEvent_t* ev);
-int mg_halo_wait_pending();
+int mg_halo_wait_pending();       // main stream waits for the exchange AND the boundary chunks in flight
+int mg_halo_mark_boundary();      // record "boundary chunks enqueued" on the halo stream
+int mg_halo_wait_boundary();      // main stream waits for them
+void mg_profile_suppress(bool on);
 // Tuning switches of the fused kernels (kernel generation, tile heights, k-chunks, L2 prefetch distance):
 // mg_tuning_set (C ABI) wins over the environment variable of the same name, which wins over the default.
 int mg_tuning_get(const char* name, int dflt);

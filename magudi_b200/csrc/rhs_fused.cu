@@ -1330,7 +1330,7 @@ int mg_fused_sweepA(mg_state* s) {
   cudaStream_t st = mg_stream();
   const bool clos = has_closures(a);
   (void)clos;
-  auto go = [&](FusedArgs& a, int zBlocks, bool) -> int {
+  auto go = [&](FusedArgs& a, int zBlocks, cudaStream_t st) -> int {
   const dim3 grid = tiles(a, zBlocks);
   int rc = -1;
 #define MG_A(ND_, R_)                                                                                     \
@@ -1478,9 +1478,9 @@ int mg_fused_sweepB(mg_state* s, int fuseRk, int stage, double dt) {
     const int tileY = bd_tile_height(s, si.R);
     const int resident = (tileY == 8 && si.R < 4) ? 3 : 2;
     const int nChunks = choose_chunks(&a, si.R, resident, TX, tileY);
-    rc = launch_split(a, nChunks, si.R, [&](FusedArgs& aa, int zBlocks, bool) -> int {
-      return hot ? mg_fused_sweepbd_hot_launch(&aa, s->nD, si.R, tileY, zBlocks, st)
-                 : mg_fused_sweepbd_gen_launch(&aa, s->nD, si.R, tileY, zBlocks, st);
+    rc = launch_split(a, nChunks, si.R, [&](FusedArgs& aa, int zBlocks, cudaStream_t stx) -> int {
+      return hot ? mg_fused_sweepbd_hot_launch(&aa, s->nD, si.R, tileY, zBlocks, stx)
+                 : mg_fused_sweepbd_gen_launch(&aa, s->nD, si.R, tileY, zBlocks, stx);
     });
     if (rc == -1) MG_FAIL("fused sweep B: unsupported configuration");
   } else {
@@ -1616,9 +1616,9 @@ int mg_fused_adjoint1(mg_state* s) {
     CUtensorMap tmW;
     const bool useTma = hot && tileY == 12 && s->nD == 3 && si.R <= 3 && mg_tuning_get("MG_TMA", 1) &&
                         make_field_tensor_map(g, s->W[s->curW], TX, tileY, s->nU, &tmW);
-    const int rc2 = launch_split(a, nChunks2, si.R, [&](FusedArgs& aa, int zBlocks, bool) -> int {
-      return hot ? mg_fused_adjoint1_hot_launch(&aa, s->nD, si.R, tileY, zBlocks, st, useTma ? &tmW : nullptr)
-                 : mg_fused_adjoint1_gen_launch(&aa, s->nD, si.R, tileY, zBlocks, st);
+    const int rc2 = launch_split(a, nChunks2, si.R, [&](FusedArgs& aa, int zBlocks, cudaStream_t stx) -> int {
+      return hot ? mg_fused_adjoint1_hot_launch(&aa, s->nD, si.R, tileY, zBlocks, stx, useTma ? &tmW : nullptr)
+                 : mg_fused_adjoint1_gen_launch(&aa, s->nD, si.R, tileY, zBlocks, stx);
     });
     if (rc2 == -1) MG_FAIL("fused adjoint sweep 1: unsupported configuration");
     return rc2;
@@ -1698,7 +1698,7 @@ int mg_fused_adjoint2(mg_state* s, int fuseRk, int stage, double dt) {
   cudaStream_t st = mg_stream();
   const bool clos = has_closures(a);
   (void)clos;
-  auto go = [&](FusedArgs& a, int zBlocks, bool) -> int {
+  auto go = [&](FusedArgs& a, int zBlocks, cudaStream_t st) -> int {
   const dim3 grid = tiles(a, zBlocks);
   int rc = -1;
 #ifndef MG_DEV_ONLY_33

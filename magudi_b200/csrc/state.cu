@@ -413,6 +413,7 @@ void mg_state_destroy_impl(mg_state* s) {
 // updateState (reference src/StateImpl.f90:466-537)
 int mg_state_update_impl(mg_state* s, const MgField* Qoverride) {
   mg_grid* g = s->grid;
+  MG_TRY(mg_halo_wait_pending());
   const MgField& Q = Qoverride ? *Qoverride : s->Q[s->cur];
   const size_t N = g->N;
   cudaStream_t st = mg_stream();
@@ -608,6 +609,7 @@ int mg_state_compute_rhs_impl(mg_state* s, int mode) {
     MG_TRY(mg_fused_adjoint1(s));
     return mg_fused_adjoint2(s, 0, 1, 0.0);
   }
+  MG_TRY(mg_halo_wait_pending());
   // The reference's callers run state%update after every substep (src/SolverImpl.f90:831-834); here
   // it is refreshed on demand.
   if (!s->dependentValid) MG_TRY(mg_state_update_impl(s, nullptr));
