@@ -206,6 +206,11 @@ int mg_state_add_acoustic_source(mg_state* s, const double location[3], double a
                                  double radius, double phase);
 /* %update: src/StateImpl.f90:466-537 */
 int mg_state_update(mg_state* s);
+/* t_State%computeCfl / %computeTimeStepSize (reference include/State.f90:84-85, src/StateImpl.f90:548-600,
+ * src/CNSHelperImpl.f90:842-982) for the current conserved variables, local to this rank: the caller takes the
+ * MAX (cfl) / MIN (time step) over ranks as t_Region%getCfl / %getTimeStepSize do (src/RegionImpl.f90:1837-1873). */
+int mg_state_cfl(mg_state* s, double timeStepSize, double* cfl);
+int mg_state_dt(mg_state* s, double cfl, double* timeStepSize);
 /* device-resident substep buffer of the UniformCheckpointer (src/UniformCheckpointerImpl.f90:78-208):
  * keep / restore the conserved variables of a substep in HBM instead of host RAM */
 int mg_state_checkpoint_store(mg_state* s, int slot);

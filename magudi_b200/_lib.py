@@ -101,6 +101,8 @@ SIGNATURES = {
     "mg_state_set_time": (C.c_int, [_P, C.c_double]),
     "mg_state_add_acoustic_source": (C.c_int, [_P, _D, C.c_double, C.c_double, C.c_double, C.c_double]),
     "mg_state_update": (C.c_int, [_P]),
+    "mg_state_cfl": (C.c_int, [_P, C.c_double, _D]),
+    "mg_state_dt": (C.c_int, [_P, C.c_double, _D]),
     "mg_state_checkpoint_store": (C.c_int, [_P, C.c_int]),
     "mg_state_checkpoint_load": (C.c_int, [_P, C.c_int]),
     "mg_state_checkpoint_clear": (C.c_int, [_P]),

@@ -311,6 +311,12 @@ class State:
     velocity = property(lambda s: s.get(Q_VELOCITY))
     pressure = property(lambda s: s.get(Q_PRESSURE))
     temperature = property(lambda s: s.get(Q_TEMPERATURE))
+    specificVolume = property(lambda s: s.get(Q_SPECIFIC_VOLUME))
+    dynamicViscosity = property(lambda s: s.get(Q_DYNAMIC_VISCOSITY))
+    secondCoefficientOfViscosity = property(lambda s: s.get(Q_SECOND_VISCOSITY))
+    thermalDiffusivity = property(lambda s: s.get(Q_THERMAL_DIFFUSIVITY))
+    stressTensor = property(lambda s: s.get(Q_STRESS_TENSOR))
+    heatFlux = property(lambda s: s.get(Q_HEAT_FLUX))
     meanPressure = property(lambda s: s.get(Q_MEAN_PRESSURE), lambda s, v: s.set(Q_MEAN_PRESSURE, v))
 
     # ---- functionals / sensitivities (local sums; see include/magudi_gpu.h)
@@ -349,6 +355,18 @@ class State:
     def update(self):
         """``t_State%update`` (dependent variables, transport, stress tensor, heat flux)."""
         check(L.lib().mg_state_update(self._h))
+
+    def computeCfl(self, timeStepSize):
+        """``t_State%computeCfl`` for a fixed time step (local to this rank)."""
+        v = C.c_double(0.0)
+        check(L.lib().mg_state_cfl(self._h, float(timeStepSize), C.byref(v)))
+        return v.value
+
+    def computeTimeStepSize(self, cfl):
+        """``t_State%computeTimeStepSize`` for a fixed CFL number (local to this rank)."""
+        v = C.c_double(0.0)
+        check(L.lib().mg_state_dt(self._h, float(cfl), C.byref(v)))
+        return v.value
 
     def checkpointStore(self, slot):
         """Keep the conserved variables of a substep in HBM (device-resident UniformCheckpointer buffer)."""

@@ -514,10 +514,31 @@ int mg_state_set(mg_state* s, int field, const double* host) {
     for (mg_patch* p : s->patches) p->AplusReady = false;
   return mg_field_upload(s->grid, f, host);
 }
+// The fused sweeps keep the dependent variables in registers / in the compact tau-q field: the reference-layout
+// arrays (specific volume ... heat flux) are materialised on demand, before anything reads them.
+static int refresh_dependents(mg_state* s, int field) {
+  if (field >= MG_Q_SPECIFIC_VOLUME && field <= MG_Q_HEAT_FLUX && !s->dependentValid) {
+    if (!s->grid->updated) MG_FAIL("dependent variables requested before mg_grid_update");
+    MG_TRY(mg_state_update_impl(s, nullptr));
+  }
+  return 0;
+}
 int mg_state_get(mg_state* s, int field, double* host) {
   MgField* f = s ? state_field(s, field) : nullptr;
   if (!f || !f->p) MG_FAIL("mg_state_get: unknown or unallocated field");
+  MG_TRY(refresh_dependents(s, field));
   return mg_field_download(s->grid, f, host);
+}
+// computeCfl / computeTimeStepSize (reference src/StateImpl.f90:548-600 -> src/CNSHelperImpl.f90:842-982)
+int mg_state_cfl(mg_state* s, double timeStepSize, double* cfl) {
+  if (!s || !cfl) MG_FAIL("mg_state_cfl: null argument");
+  if (!(timeStepSize > 0.0)) MG_FAIL("mg_state_cfl: the time step size must be positive");
+  return mg_state_cfl_dt_impl(s, 0, timeStepSize, cfl);
+}
+int mg_state_dt(mg_state* s, double cfl, double* timeStepSize) {
+  if (!s || !timeStepSize) MG_FAIL("mg_state_dt: null argument");
+  if (!(cfl > 0.0)) MG_FAIL("mg_state_dt: the CFL number must be positive");
+  return mg_state_cfl_dt_impl(s, 1, cfl, timeStepSize);
 }
 // ---- transfers on the copy stream, overlapping the sweeps ------------------------------------------------
 namespace {
@@ -656,6 +677,7 @@ int mg_patch_get_array(mg_patch* p, const char* name, int nComp, double* host) {
 }
 int mg_patch_collect(mg_patch* p, int field, const char* name) {
   if (!p || !name) MG_FAIL("mg_patch_collect: null argument");
+  if (p && p->state) MG_TRY(refresh_dependents(p->state, field));
   MgField* f = state_field(p->state, field);
   int nc = 0;
   if (!f) f = grid_field(p->state->grid, field, &nc, false);

@@ -70,6 +70,7 @@ int mg_state_rhs_forward_general(mg_state* s);
 int mg_state_rhs_adjoint_general(mg_state* s);
 int mg_state_compute_rhs_impl(mg_state* s, int mode);
 int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int timestep, int stage);
+int mg_state_cfl_dt_impl(mg_state* s, int wantDt, double given, double* result);
 int mg_patches_apply(mg_state* s, int mode);
 int mg_patches_collect_viscous(mg_state* s);
 int mg_patches_farfield_adjoint_sources(mg_state* s, MgField* temp1);

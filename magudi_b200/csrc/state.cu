@@ -309,6 +309,59 @@ __global__ void k_rk4(RkArgs a) {
   }
 }
 
+struct CflArgs {
+  const double* Q; size_t csQ;
+  const double *m, *jac; size_t cs;
+  const int* iblank;
+  size_t N;
+  PhysParams pp;
+  double* partial;     // [gridDim.x] block maxima of the local wave speed
+};
+
+// Largest local wave speed (inviscid: J' (c |grad xi| + sum_j |u . M_j|); viscous: J'^2 |M|^2 max(2 mu, kappa)):
+// CFL = dt x max, dt = CFL / max (reference src/CNSHelperImpl.f90:842-982).  The dependent variables are
+// recomputed from Q (the fused sweeps do not materialise them); hole points are skipped.
+template <int ND>
+__global__ void __launch_bounds__(256) k_wave_speed(CflArgs a) {
+  __shared__ double sh[256];
+  double best = 0.0;
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < a.N; p += (size_t)gridDim.x * blockDim.x) {
+    if (a.iblank && a.iblank[p] == 0) continue;
+    double Q[ND + 2];
+#pragma unroll
+    for (int c = 0; c < ND + 2; ++c) Q[c] = a.Q[(size_t)c * a.csQ + p];
+    Prim<ND> s;
+    dependent<ND>(Q, a.pp.gamma, s);
+    const double c0 = sqrt((a.pp.gamma - 1.0) * s.T);
+    double msq = 0.0, conv = 0.0;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      double dot = 0.0;
+#pragma unroll
+      for (int l = 0; l < ND; ++l) {
+        const double m = a.m[(size_t)(l + ND * j) * a.cs + p];
+        msq += m * m;
+        dot += s.u[l] * m;
+      }
+      conv += fabs(dot);
+    }
+    const double J = a.jac[p];
+    best = fmax(best, J * (c0 * sqrt(msq) + conv));
+    if (a.pp.viscous) {
+      double mu, lam, kap;
+      transport(s.T, a.pp, mu, lam, kap);
+      best = fmax(best, J * J * msq * fmax(2.0 * mu, kap));
+    }
+  }
+  sh[threadIdx.x] = best;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + st]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) a.partial[blockIdx.x] = sh[0];
+}
+
 template <typename F>
 int dispatch_nd(int nD, F f) {
   if (nD == 1) return f(std::integral_constant<int, 1>());
@@ -592,6 +645,43 @@ int mg_state_rhs_adjoint_general(mg_state* s) {
     MG_TRY(mg_patches_farfield_adjoint_sources(s, &B));
     MG_TRY(finish(B, -1.0));
   }
+  return 0;
+}
+
+// wantDt = 0: result = given(dt) x max wave speed (computeCfl); 1: result = given(cfl) / max wave speed
+// (computeTimeStepSize).  Local to this rank: the caller reduces over ranks (MPI_Allreduce MAX / MIN in the
+// reference, src/RegionImpl.f90:1837-1873).
+int mg_state_cfl_dt_impl(mg_state* s, int wantDt, double given, double* result) {
+  mg_grid* g = s->grid;
+  if (!g->updated) MG_FAIL("cfl / time step: grid metrics have not been computed (mg_grid_update)");
+  MG_TRY(mg_halo_wait_pending());
+  const int blocks = 592;
+  static double* d_partial = nullptr;
+  static double* h_partial = nullptr;
+  if (!d_partial) {
+    MG_CUDA(cudaMalloc(&d_partial, blocks * sizeof(double)));
+    MG_CUDA(cudaMallocHost(&h_partial, blocks * sizeof(double)));
+  }
+  CflArgs a;
+  a.Q = s->Q[s->cur].comp(0);
+  a.csQ = s->Q[s->cur].compStride;
+  a.m = g->metrics.comp(0);
+  a.jac = g->jacobian.comp(0);
+  a.cs = g->metrics.compStride;
+  a.iblank = g->iblank;
+  a.N = g->N;
+  a.pp = s->phys();
+  a.partial = d_partial;
+  MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
+    k_wave_speed<decltype(nd)::value><<<blocks, 256, 0, mg_stream()>>>(a);
+    return 0;
+  }));
+  MG_CUDA(cudaGetLastError());
+  MG_CUDA(cudaMemcpyAsync(h_partial, d_partial, blocks * sizeof(double), cudaMemcpyDeviceToHost, mg_stream()));
+  MG_CUDA(cudaStreamSynchronize(mg_stream()));
+  double w = 0.0;
+  for (int i = 0; i < blocks; ++i) w = h_partial[i] > w ? h_partial[i] : w;
+  *result = wantDt ? given / w : given * w;
   return 0;
 }
 

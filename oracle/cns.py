@@ -369,3 +369,30 @@ def computeRoeAverage(nD, QL, QR, gamma):
     out[:, 1:nD + 1] = rho[:, None] * ur
     out[:, nD + 1] = rho * (h / gamma + 0.5 * (gamma - 1.0) / gamma * np.sum(ur ** 2, axis=1))
     return out
+
+
+def _localWaveSpeeds(nD, iblank, jacobian, metrics, velocity, temperature, gamma, mu=None, kappa=None):
+    c = np.sqrt((gamma - 1.0) * temperature)
+    msq = np.zeros_like(c)
+    conv = np.zeros_like(c)
+    for j in range(nD):
+        mj = metrics[:, nD * j:nD * (j + 1)]
+        msq = msq + np.sum(mj ** 2, axis=1)
+        conv = conv + np.abs(np.sum(velocity * mj, axis=1))
+    w = jacobian * (c * np.sqrt(msq) + conv)
+    if mu is not None:
+        w = np.maximum(w, jacobian ** 2 * np.sum(metrics ** 2, axis=1) * np.maximum(2.0 * mu, kappa))
+    return np.where(iblank == 0, 0.0, w)
+
+
+def computeCfl(nD, iblank, jacobian, metrics, velocity, temperature, timeStepSize, gamma, mu=None, kappa=None):
+    """``computeCfl`` (``src/CNSHelperImpl.f90:842-911``): max over non-hole points of the inviscid and viscous
+    local wave speeds times the time step."""
+    return float(np.max(_localWaveSpeeds(nD, iblank, jacobian, metrics, velocity, temperature, gamma, mu, kappa))
+                 * timeStepSize)
+
+
+def computeTimeStepSize(nD, iblank, jacobian, metrics, velocity, temperature, cfl, gamma, mu=None, kappa=None):
+    """``computeTimeStepSize`` (``src/CNSHelperImpl.f90:913-982``)."""
+    return float(cfl / np.max(_localWaveSpeeds(nD, iblank, jacobian, metrics, velocity, temperature, gamma, mu,
+                                               kappa)))
