@@ -31,10 +31,13 @@ UNIT = "point-stages/s"
 BYTES_FORWARD = 448.0           # two sweeps: (5+4+9) + (5+9+4+20) doubles
 BYTES_ADJOINT = 912.0           # three sweeps + checkpoint store/load
 BYTES_SWEEP_A = (5 + 4 + 9) * 8.0
-BYTES_DISS = (5 + 3 + 5) * 8.0                  # read Q 5 + arc lengths 3, write the dissipation term 5
+BYTES_DISS = (5 + 3 + 5) * 8.0                  # (first-generation separate dissipation sweep: MG_FWD=1)
 BYTES_SWEEP_B = (5 + 9 + 4 + 20) * 8.0
 BYTES_ADJ1 = (5 + 5 + 9 + 4 + 5 + 12) * 8.0     # read Q, w, tau/q, G; write partial R 5 + adjoint diffusion 12
-BYTES_ADJ2 = (12 + 5 + 5 + 4 + 20) * 8.0        # read diffusion 12, partial R 5, Q 5, G + RK 20
+BYTES_ADJ2 = (12 + 5 + 5 + 1 + 20) * 8.0        # read diffusion 12, partial R 5, Q 5, 1/J + RK 20
+# compulsory minimum (single-sweep) figures of SURVEY.md section 8(d): printed beside the contract fractions
+BYTES_MIN_FORWARD = 232.0
+BYTES_MIN_ADJOINT = 272.0
 
 
 def measured_peaks():
@@ -303,6 +306,8 @@ def run_native(args):
     clocks["window"] = "warm-up + timed steps" + (f" + {extra} identical untimed steps" if extra else "")
 
     # max over ranks
+    kernel_sum_ms = sum(v["ms"] for v in prof.values())
+    gap_ms = total_ms - kernel_sum_ms           # step time not covered by the sweeps on this rank: halo + launch gaps
     if world > 1:
         import torch.distributed as dist
         tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -366,13 +371,14 @@ def run_native(args):
         achieved = bytes_per_launch / (prof[dom]["avg_ms"] * 1e-3) / 1e9
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")) as f:
                 traffic = json.load(f)[dom]["dram_bytes_per_launch"]
         except Exception:
             traffic = None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic,
-                    "traffic_source": "ncu dram__bytes_read+write per launch (profiles/r1_kernel_traffic.json)" if traffic else None,
+                    "traffic_source": ("NOT measured in this run: ncu dram__bytes_read+write per launch of the same "
+                                       "kernel and workload, committed capture profiles/r2_kernel_traffic.json") if traffic else None,
                     "peak_source": peak_src,
                     "share_of_step": prof[dom]["ms"] / total_ms,
                     "algorithmic_bytes_per_point": bytes_per_launch / N}
@@ -380,11 +386,15 @@ def run_native(args):
     path = {}
     fwd_rate = 4 * N * args.steps / (fwd_ms * 1e-3)
     path["forward"] = {"point_stages_per_s_per_gpu": fwd_rate, "bytes_model": BYTES_FORWARD,
-                       "frac_of_hbm_peak": fwd_rate * BYTES_FORWARD / 1e9 / peak, "ms_per_step": fwd_ms / args.steps}
+                       "frac_of_hbm_peak": fwd_rate * BYTES_FORWARD / 1e9 / peak,
+                       "bytes_min": BYTES_MIN_FORWARD, "frac_of_hbm_peak_bytes_min": fwd_rate * BYTES_MIN_FORWARD / 1e9 / peak,
+                       "ms_per_step": fwd_ms / args.steps}
     if do_adjoint:
         adj_rate = 4 * N * args.steps / (adj_ms * 1e-3)
         path["adjoint"] = {"point_stages_per_s_per_gpu": adj_rate, "bytes_model": BYTES_ADJOINT,
                            "frac_of_hbm_peak": adj_rate * BYTES_ADJOINT / 1e9 / peak,
+                           "bytes_min": BYTES_MIN_ADJOINT,
+                           "frac_of_hbm_peak_bytes_min": adj_rate * BYTES_MIN_ADJOINT / 1e9 / peak,
                            "ms_per_step": adj_ms / args.steps,
                            "note": "each adjoint stage also restores the stored forward substep state and runs sweep A on it"}
     cpu = None
@@ -398,12 +408,16 @@ def run_native(args):
         "config": {"workload": f"C3 3-D periodic viscous box {shape[0]}x{shape[1]}x{shape[2]} "
                                f"({N} points/GPU), KolmogorovFlow flags, SBP 3-6, non-composite dissipation",
                    "evals_per_point_per_step": evals_per_point,
-                   "forward_path": "fused sweeps A + dissipation + B" if fused_fwd else "general",
+                   "forward_path": ("two fused sweeps per stage: A (state update) + B (fluxes, dissipation, 1/J, RK4)"
+                                    if os.environ.get("MG_FWD", "2") == "2" else "fused sweeps A + dissipation + B")
+                                   if fused_fwd else "general",
                    "adjoint_path": ("fused adjoint sweeps 1+2 (+ sweep A on the restored state)" if fused_adj else "general operator-by-operator") if do_adjoint else "not run (multi-rank adjoint needs the fused adjoint)",
                    "parallelism": f"slab decomposition along k over {world} GPU(s)" + (f", halo exchange: {halo.mode}" if halo else ""),
                    "l2_policy": "inputs larger than L2 (every field >= 134 MB per component set)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "roofline_path": path, "kernels": prof, "cpu_baseline": cpu,
+        "step_minus_kernel_sum_ms": gap_ms / args.steps,
+        "halo_overlap": (os.environ.get("MG_OVERLAP", "1") != "0") if world > 1 else None,
         "wall_s_timed_region": wall,
     }
     print(json.dumps(line))

@@ -434,6 +434,28 @@ class Patch:
         a = L.as_f(np.asarray(a, dtype=np.float64).reshape(max(self.nPatchPoints, 0), -1, order="F"))
         check(L.lib().mg_patch_set_array(self._h, name.encode(), a.shape[1], L.fptr(a)))
 
+    def gridIndices(self):
+        """0-based indices (into this rank's (N, nComp) grid arrays, point index i + nx (j + ny k)) of the patch
+        points this rank owns, in patch order (i fastest) -- the index map of ``t_Patch%collect / disperse``
+        (reference ``src/PatchImpl.f90:187-585``)."""
+        g = self.state.grid
+        gs, ls, off = g.globalSize, g.localSize, g.offset
+        lo, hi = [], []
+        for d in range(3):
+            a, b = self.extent[2 * d], self.extent[2 * d + 1]
+            n = gs[d] if d < len(gs) else 1
+            a = n + a + 1 if a < 0 else a
+            b = n + b + 1 if b < 0 else b
+            o = off[d] if d < len(off) else 0
+            l = ls[d] if d < len(ls) else 1
+            lo.append(max(a - 1, o) - o)
+            hi.append(min(b, o + l) - o)
+        nx = ls[0]
+        ny = ls[1] if len(ls) > 1 else 1
+        ii, jj, kk = np.meshgrid(np.arange(lo[0], hi[0]), np.arange(lo[1], hi[1]), np.arange(lo[2], hi[2]),
+                                 indexing="ij")
+        return (ii + nx * (jj + ny * kk)).reshape(-1, order="F")
+
     def getArray(self, name, nComp):
         a = np.zeros((self.nPatchPoints, nComp), order="F")
         check(L.lib().mg_patch_get_array(self._h, name.encode(), nComp, L.fptr(a)))

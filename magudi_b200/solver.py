@@ -1,0 +1,159 @@
+"""Solver-level forward / adjoint drivers over the C ABI: the host mirror of ``t_Solver%runForward`` /
+``%runAdjoint`` with a device-resident ``t_UniformCheckpointer`` (reference ``src/SolverImpl.f90:672-1245``,
+``src/UniformCheckpointerImpl.f90:78-208``, ``src/ThermalActuatorImpl.f90:83-233, 383-443``,
+``src/ActuatorPatchImpl.f90:226-458``).
+
+Everything numerical happens in ``libmagudi_gpu`` (RK4 substeps, functional, adjoint forcing, sensitivity, gradient
+samples); this file only sequences the calls the way the reference's time loops do:
+
+* forward: ``J = sum_steps sum_{i=1..4} norm(i) dt I(Q after substep i)`` with ``norm = (1/6, 1/3, 1/3, 1/6)``;
+  the state is checkpointed every ``saveInterval`` steps;
+* adjoint: terminal condition ``w_T = (-dt/6) F(Q_T)`` through the COST_TARGET patches, time starting at
+  ``t_end - dt/2``; per substep (4 -> 1) the forward substep state comes from a window of ``4 saveInterval``
+  states recomputed from the nearest checkpoint and kept in HBM as zero-copy slots, then gradient sample,
+  sensitivity quadrature, adjoint forcing (dropped on the very last substep) and the adjoint RK4 substep;
+* the gradient samples are stored in REVERSE time order; the control forcing of a perturbed forward run reads that
+  sequence back from its end (``zaxpy``: forcing = alpha x gradient).
+
+Constant time step, no controller time ramp (the defaults of the BASELINE configs); one grid per solver.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import core
+from .core import ADJOINT, FORWARD
+
+NORM = (1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0)
+
+
+def zaxpy(a, x, y=None):
+    """``bin/ZAXPY.f90``: z = a x + y on control-space vectors (raw fp64)."""
+    z = float(a) * np.asarray(x, dtype=np.float64)
+    return z if y is None else z + np.asarray(y, dtype=np.float64)
+
+
+def save_control_vector(filename, v):
+    """``<prefix>.gradient_<patch>.dat`` / ``.control_forcing_<patch>.dat``: raw fp64, one patch-ordered block per
+    substep, substeps in reverse time order (``src/ActuatorPatchImpl.f90:409-458``)."""
+    np.ascontiguousarray(v, dtype="<f8").tofile(filename)
+
+
+def load_control_vector(filename, nPatchPoints):
+    return np.fromfile(filename, dtype="<f8").reshape(-1, nPatchPoints)
+
+
+class Solver:
+    def __init__(self, region, state, dt, nTimesteps, saveInterval):
+        self.region, self.state = region, state
+        self.dt, self.nTimesteps, self.saveInterval = float(dt), int(nTimesteps), int(saveInterval)
+        if self.nTimesteps % self.saveInterval:
+            raise ValueError("number_of_timesteps must be a multiple of save_interval")
+        self.integ = core.RK4Integrator(region)
+        self.targets = [p for p in state.patches if p.patchType == "COST_TARGET"]
+        self.actuators = [p for p in state.patches if p.patchType == "ACTUATOR"]
+        self.checkpoints = {}
+        self.controlForcing = None
+        self.startTime = 0.0
+        self.nU = state.nUnknowns
+
+    # ---- controller%updateForcing: forward substep m reads sample 4N-1-m of the reverse-time sequence
+    def _set_forcing(self, substep):
+        if not self.actuators:
+            return
+        k = 4 * self.nTimesteps - 1 - substep
+        off = 0
+        for p in self.actuators:
+            f = np.zeros((p.nPatchPoints, self.nU))
+            if self.controlForcing is not None:
+                f[:, self.nU - 1] = self.controlForcing[k, off:off + p.nPatchPoints]
+            if self.controlForcing is not None or self._forcing_was_set:
+                p.setArray("controlForcing", f)
+            off += p.nPatchPoints
+        self._forcing_was_set = self.controlForcing is not None
+
+    _forcing_was_set = False
+
+    def runForward(self, Q0, startTimestep=0, record=True):
+        st = self.state
+        st.conservedVariables = Q0
+        time = self.startTime + startTimestep * self.dt
+        st.setTime(time)
+        if record:
+            self.checkpoints[startTimestep] = (np.array(Q0, dtype=np.float64, order="F", copy=True), time)
+        st.update()
+        J = 0.0
+        for timestep in range(startTimestep + 1, startTimestep + self.nTimesteps + 1):
+            for i in range(1, 5):
+                self._set_forcing(4 * (timestep - 1) + i - 1)
+                time = self.integ.substepForward(time, self.dt, timestep, i)
+                if self.targets:
+                    J += NORM[i - 1] * self.dt * st.computeAcousticNoise(1.0)
+            if record and timestep % self.saveInterval == 0:
+                self.checkpoints[timestep] = (st.conservedVariables, time)
+        self.endTime = time
+        return J
+
+    def _window(self, loaded):
+        """Recompute the substep states of one checkpoint window into device slots 0 .. 4 saveInterval - 1."""
+        st = self.state
+        Q, time = self.checkpoints[loaded]
+        st.conservedVariables = Q
+        st.setTime(time)                   # loadData takes the time from the checkpoint file
+        st.update()
+        st.checkpointStore(0)
+        n = 1
+        if loaded == self.nTimesteps:
+            return n
+        for timestep in range(loaded + 1, loaded + self.saveInterval + 1):
+            for i in range(1, 5):
+                self._set_forcing(4 * (timestep - 1) + i - 1)
+                time = self.integ.substepForward(time, self.dt, timestep, i)
+                if timestep == loaded + self.saveInterval and i == 4:
+                    break
+                st.checkpointStore(n)
+                n += 1
+        return n
+
+    def runAdjoint(self):
+        """Returns (cost sensitivity, gradient samples (4 nTimesteps, nActuatorPoints) in reverse time order)."""
+        st = self.state
+        N = self.nTimesteps
+        QT, tT = self.checkpoints[N]
+        st.conservedVariables = QT
+        st.update()
+        # adjoint terminal condition (src/SolverImpl.f90:378-426)
+        W = np.zeros((st.grid.nGridPoints, self.nU), order="F")
+        if self.targets:
+            st.computeAcousticNoiseAdjointForcing(1.0)
+            for p in self.targets:
+                W[p.gridIndices()] += (-self.dt / 6.0) * p.getArray("adjointForcing", self.nU)
+        st.adjointVariables = W
+        time = tT - 0.5 * self.dt
+        loaded = None
+        grad, sens = [], 0.0
+        zero = {p: np.zeros((p.nPatchPoints, self.nU)) for p in self.targets}
+        for timestep in range(N - 1, -1, -1):
+            for i in range(4, 0, -1):
+                ts_, st_ = (timestep, 4) if i == 1 else (timestep + 1, i - 1)
+                S = self.saveInterval
+                need = ts_ if (ts_ % S == 0 and st_ == 4) else (ts_ - S if ts_ % S == 0 else ts_ - ts_ % S)
+                if loaded is None or ts_ < loaded or ts_ > loaded + S or (ts_ == loaded and st_ < 4) or \
+                        (ts_ == loaded + S and st_ == 4):
+                    loaded = need
+                    self._window(need)          # the forward RK4 march leaves W and the adjoint RK buffers alone
+                st.checkpointLoad((ts_ - 1 - loaded) * 4 + st_)
+                st.update()
+                st.setTime(time)
+                if self.actuators:
+                    grad.append(np.concatenate([p.thermalActuatorGradient(1.0) for p in self.actuators]))
+                    sens += NORM[i - 1] * self.dt * st.computeThermalActuatorSensitivity(1.0)
+                if self.targets:
+                    if timestep == 0 and i == 1:
+                        for p in self.targets:
+                            p.setArray("adjointForcing", zero[p])
+                    else:
+                        st.computeAcousticNoiseAdjointForcing(1.0)
+                time = self.integ.substepAdjoint(time, self.dt, timestep, i)
+        st.checkpointClear()
+        return sens, np.array(grad)
