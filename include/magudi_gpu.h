@@ -49,6 +49,7 @@ typedef struct mg_region mg_region;     /* t_Region,          include/Region.f90
 #define MG_SAT_ISOTHERMAL_WALL 4
 #define MG_COST_TARGET 5
 #define MG_ACTUATOR 6
+#define MG_SAT_BLOCK_INTERFACE 7
 
 /* field ids for mg_state_set / mg_state_get (t_State members, include/State.f90:59-62) and
  * mg_grid_get / mg_grid_set (t_Grid members, include/Grid.f90:38-40) */
@@ -183,6 +184,12 @@ int mg_functional_acoustic_noise(mg_state* s, double timeRampFactor, double* val
 int mg_functional_acoustic_noise_forcing(mg_state* s, double timeRampFactor);
 int mg_functional_actuator_sensitivity(mg_state* s, double timeRampFactor, double* value);
 int mg_functional_actuator_gradient(mg_patch* p, double timeRampFactor, double* hostOut);
+/* t_PressureDrag%compute / %computeAdjointForcing (src/PressureDragImpl.f90:61-132, 148-267; magudi.inp
+ * drag_direction_x/y/z, normalised here): J = sum over the COST_TARGET patches (on a boundary face) of
+ * -(p - 1/gamma) patch%norm (metrics_k . direction) / normBoundary(1); the forcing (discrete or continuous
+ * adjoint per the state's options) is written to the patches' "adjointForcing". */
+int mg_functional_pressure_drag(mg_state* s, const double direction[3], double* value);
+int mg_functional_pressure_drag_forcing(mg_state* s, const double direction[3]);
 
 /* ------------------------------------------------------------------ t_State */
 /* %setup: src/StateImpl.f90:71-170 */
@@ -230,6 +237,14 @@ int mg_patch_set_array(mg_patch* p, const char* name, int nComp, const double* h
 int mg_patch_get_array(mg_patch* p, const char* name, int nComp, double* host);
 /* %collect: src/PatchImpl.f90:187-316 -- grid field of the owning state -> patch array */
 int mg_patch_collect(mg_patch* p, int field, const char* name);
+/* Block interfaces (t_BlockInterfacePatch, src/BlockInterfacePatchImpl.f90:3-929): "a conforms_with b" of
+ * readPatchInterfaceInformation (src/InterfaceHelperImpl.f90:3-112, the bc.dat / *interface_index_reorder keys):
+ * links two MG_SAT_BLOCK_INTERFACE patches of two states of ONE region; indexReorderingA is patch a's reordering
+ * (NULL = 1,2,3), patch b gets the inverted one.  The METRICS pseudo-exchange (src/SolverImpl.f90:571-603) and
+ * the per-stage exchangeInterfaceData (src/InterfaceHelperImpl.f90:115-239) run inside mg_region_compute_rhs:
+ * both blocks live on this process's device, the exchange is one gather kernel per patch with the reordering
+ * applied on the fly. */
+int mg_patch_link_interface(mg_patch* a, mg_patch* b, const int indexReorderingA[3]);
 
 /* ------------------------------------------------------------------ t_Region / t_RK4Integrator */
 int mg_region_create(mg_region** out);

@@ -81,6 +81,8 @@ SIGNATURES = {
     "mg_functional_acoustic_noise_forcing": (C.c_int, [_P, C.c_double]),
     "mg_functional_actuator_sensitivity": (C.c_int, [_P, C.c_double, _D]),
     "mg_functional_actuator_gradient": (C.c_int, [_P, C.c_double, _P]),
+    "mg_functional_pressure_drag": (C.c_int, [_P, _P, _D]),
+    "mg_functional_pressure_drag_forcing": (C.c_int, [_P, _P]),
     "mg_p2p_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "mg_p2p_handle_size": (C.c_int, []),
     "mg_p2p_get_handle": (C.c_int, [_P, _P]),
@@ -111,6 +113,7 @@ SIGNATURES = {
     "mg_patch_set_array": (C.c_int, [_P, C.c_char_p, C.c_int, _P]),
     "mg_patch_get_array": (C.c_int, [_P, C.c_char_p, C.c_int, _P]),
     "mg_patch_collect": (C.c_int, [_P, C.c_int, C.c_char_p]),
+    "mg_patch_link_interface": (C.c_int, [_P, _P, _P]),
     "mg_region_create": (C.c_int, [C.POINTER(_P)]),
     "mg_region_destroy": (C.c_int, [_P]),
     "mg_region_add_state": (C.c_int, [_P, _P]),

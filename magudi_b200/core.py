@@ -29,7 +29,7 @@ G_COORDINATES, G_METRICS, G_JACOBIAN, G_NORM, G_ARC_LENGTHS = 100, 101, 102, 103
 G_TARGET_MOLLIFIER, G_CONTROL_MOLLIFIER = 105, 106
 
 PATCH_TYPES = {"SAT_FAR_FIELD": 1, "SPONGE": 2, "SAT_SLIP_WALL": 3, "SAT_ISOTHERMAL_WALL": 4,
-               "COST_TARGET": 5, "ACTUATOR": 6}
+               "COST_TARGET": 5, "ACTUATOR": 6, "SAT_BLOCK_INTERFACE": 7}
 
 
 def pigeonhole(nPigeons, nHoles, holeIndex):
@@ -337,6 +337,18 @@ class State:
         """``t_AcousticNoise%computeAdjointForcing`` (``:208-280``): fills every COST_TARGET patch."""
         check(L.lib().mg_functional_acoustic_noise_forcing(self._h, float(timeRampFactor)))
 
+    def computePressureDrag(self, direction=(1.0, 0.0, 0.0)):
+        """``t_PressureDrag%compute`` (``src/PressureDragImpl.f90:61-132``), local to this rank."""
+        d = (C.c_double * 3)(*[float(v) for v in (tuple(direction) + (0.0, 0.0))[:3]])
+        r = C.c_double(0.0)
+        check(L.lib().mg_functional_pressure_drag(self._h, d, C.byref(r)))
+        return r.value
+
+    def computePressureDragAdjointForcing(self, direction=(1.0, 0.0, 0.0)):
+        """``t_PressureDrag%computeAdjointForcing`` (``:148-267``): fills every COST_TARGET patch."""
+        d = (C.c_double * 3)(*[float(v) for v in (tuple(direction) + (0.0, 0.0))[:3]])
+        check(L.lib().mg_functional_pressure_drag_forcing(self._h, d))
+
     def computeThermalActuatorSensitivity(self, timeRampFactor=1.0):
         """``t_ThermalActuator%computeSensitivity`` (``src/ThermalActuatorImpl.f90:83-159``)."""
         r = C.c_double(0.0)
@@ -463,6 +475,12 @@ class Patch:
 
     def collect(self, field, name):
         check(L.lib().mg_patch_collect(self._h, field, name.encode()))
+
+    def linkInterface(self, other, indexReordering=(1, 2, 3)):
+        """``self conforms_with other`` (``readPatchInterfaceInformation``, ``src/InterfaceHelperImpl.f90:3-112``):
+        both must be SAT_BLOCK_INTERFACE patches of states of one region; ``other`` gets the inverted reordering."""
+        o = (C.c_int * 3)(*[int(v) for v in indexReordering])
+        check(L.lib().mg_patch_link_interface(self._h, other._h, o))
 
     def thermalActuatorGradient(self, timeRampFactor=1.0):
         """One gradient sample ``w_E * controlMollifier`` at the patch points

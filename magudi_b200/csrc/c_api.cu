@@ -712,6 +712,14 @@ int mg_functional_actuator_sensitivity(mg_state* s, double timeRampFactor, doubl
   if (!s || !value) MG_FAIL("mg_functional_actuator_sensitivity: null argument");
   return mg_functional_actuator_sensitivity_impl(s, timeRampFactor, value);
 }
+int mg_functional_pressure_drag(mg_state* s, const double direction[3], double* value) {
+  if (!s || !direction || !value) MG_FAIL("mg_functional_pressure_drag: null argument");
+  return mg_functional_pressure_drag_impl(s, direction, value);
+}
+int mg_functional_pressure_drag_forcing(mg_state* s, const double direction[3]) {
+  if (!s || !direction) MG_FAIL("mg_functional_pressure_drag_forcing: null argument");
+  return mg_functional_pressure_drag_forcing_impl(s, direction);
+}
 int mg_functional_actuator_gradient(mg_patch* p, double timeRampFactor, double* hostOut) {
   if (!p || !hostOut) MG_FAIL("mg_functional_actuator_gradient: null argument");
   return mg_functional_actuator_gradient_impl(p, timeRampFactor, hostOut);
@@ -743,15 +751,40 @@ int mg_region_uses_fused(mg_region* r, int mode) {
   for (mg_state* s : r->states) if (!mg_fused_supported(s, mode)) return 0;
   return 1;
 }
+static bool region_has_interfaces(const mg_region* r) {
+  for (const mg_state* s : r->states) if (mg_state_has_interfaces(s)) return true;
+  return false;
+}
+// t_Region%computeRhs (reference src/RegionImpl.f90:1877-2027).  With block interfaces the evaluation is staged
+// over all the grids of the region as in the reference: RHS of every grid, interface exchange, then the viscous
+// interface adjoint penalty, 1/J, patch penalties and sources of every grid.
+static int region_compute_rhs(mg_region* r, int mode) {
+  if (!region_has_interfaces(r)) {
+    for (mg_state* s : r->states) MG_TRY(mg_state_compute_rhs_impl(s, mode));
+    return 0;
+  }
+  for (mg_state* s : r->states) MG_TRY(mg_state_rhs_pre(s, mode));
+  MG_TRY(mg_interfaces_exchange(r->states, mode));
+  for (mg_state* s : r->states) MG_TRY(mg_state_rhs_post(s, mode));
+  return 0;
+}
 int mg_region_compute_rhs(mg_region* r, int mode, int timestep, int stage) {
   (void)timestep; (void)stage;
   if (!r) MG_FAIL("mg_region_compute_rhs: null handle");
-  for (mg_state* s : r->states) MG_TRY(mg_state_compute_rhs_impl(s, mode));
-  return 0;
+  return region_compute_rhs(r, mode);
+}
+int mg_patch_link_interface(mg_patch* a, mg_patch* b, const int indexReorderingA[3]) {
+  return mg_interface_link(a, b, indexReorderingA);
 }
 int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep, int stage, int updateStates) {
   if (!r || !time) MG_FAIL("mg_rk4_substep: null argument");
   double t = *time;
+  if (region_has_interfaces(r)) {
+    if (stage < 1 || stage > 4) MG_FAIL("rk4 substep: stage must be 1..4");
+    for (mg_state* s : r->states) mg_rk4_set_times(s, mode, *time, dt, stage);
+    MG_TRY(region_compute_rhs(r, mode));
+    for (mg_state* s : r->states) s->rhsReady = true;
+  }
   for (mg_state* s : r->states) {
     t = *time;
     MG_TRY(mg_rk4_substep_impl(s, mode, &t, dt, timestep, stage));

@@ -49,6 +49,7 @@ struct mg_state {
   std::vector<Source> acousticSources;
   std::vector<mg_patch*> patches;
   bool dependentValid = false;
+  bool rhsReady = false;            // the region has already evaluated the RHS of this substep (block interfaces)
   PhysParams phys() const {
     PhysParams p;
     p.gamma = opt.ratioOfSpecificHeats;
@@ -69,6 +70,10 @@ void mg_state_pool_trim(mg_state* s);
 int mg_state_rhs_forward_general(mg_state* s);
 int mg_state_rhs_adjoint_general(mg_state* s);
 int mg_state_compute_rhs_impl(mg_state* s, int mode);
+int mg_state_rhs_pre(mg_state* s, int mode);
+int mg_state_rhs_post(mg_state* s, int mode);
+int mg_state_adjoint_finish(mg_state* s, MgField* src, double sign);
+void mg_rk4_set_times(mg_state* s, int mode, double time, double dt, int stage);
 int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int timestep, int stage);
 int mg_state_cfl_dt_impl(mg_state* s, int wantDt, double given, double* result);
 int mg_patches_apply(mg_state* s, int mode);

@@ -365,7 +365,7 @@ int mg_patch_create_impl(mg_state* s, int type, const char* name, int normalDire
     if (!s->opt.useTargetState) { delete p; MG_FAIL("mg_patch_create: no target state available for this patch type"); }
   }
   s->patches.push_back(p);
-  if (type == MG_PATCH_FARFIELD && s->opt.viscosityOn) s->keepViscousFluxes = true;
+  if ((type == MG_PATCH_FARFIELD || type == MG_PATCH_BLOCK_INTERFACE) && s->opt.viscosityOn) s->keepViscousFluxes = true;
   *out = p;
   return 0;
 }
@@ -436,7 +436,7 @@ bool mg_patches_have_farfield(const mg_state* s) {
 
 int mg_patches_collect_viscous(mg_state* s) {
   for (mg_patch* p : s->patches)
-    if (p->type == MG_PATCH_FARFIELD)
+    if (p->type == MG_PATCH_FARFIELD || p->type == MG_PATCH_BLOCK_INTERFACE)
       MG_TRY(mg_patch_collect_impl(p, &s->viscFluxCart, s->nU * s->nD, "viscousFluxes"));
   return 0;
 }
@@ -642,6 +642,9 @@ int mg_patches_apply(mg_state* s, int mode) {
         k_patch_add<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a);
         break;
       }
+      case MG_PATCH_BLOCK_INTERFACE:
+        MG_TRY(mg_interface_apply(s, p, mode));
+        break;
       default:
         MG_FAIL("patch: unknown type");
     }
@@ -760,6 +763,145 @@ __global__ void k_actuator_gradient(PatchGeom g, const double* wE, const double*
   out[q] = wE[p] * (mollifier[p] * ramp);
 }
 
+// t_PressureDrag (reference src/PressureDragImpl.f90:61-267) on the COST_TARGET patches: the integrand uses the
+// patch norm of updatePatchFactories (src/PatchFactoryImpl.f90:496-505) = SBP norm weights of the tangential
+// directions (no Jacobian), evaluated here from the norm tables instead of being stored per patch.
+constexpr int DRAG_BLOCKS = 64, DRAG_THREADS = 256;
+
+struct DragArgs {
+  PatchGeom g;
+  const int* iblank;
+  const double *pressure, *metricsK, *jac, *u, *Q, *W;
+  size_t cs, csQ, csW;
+  int nD, axis, normalDirection, continuous;
+  int n[3], depth[3], hasB0[3], hasB1[3];
+  double norm[3][MG_MAX_BDEPTH];
+  double dirv[3], factor, gamma, sigmaI;
+  double* partial;     // k_drag
+  double* out;         // k_drag_forcing: adjointForcing (nPatchPoints, nU), point fastest
+};
+
+__device__ __forceinline__ double drag_patch_norm(const DragArgs& a, int q) {
+  const int c[3] = {a.g.lo[0] + q % a.g.sz[0], a.g.lo[1] + (q / a.g.sz[0]) % a.g.sz[1],
+                    a.g.lo[2] + q / (a.g.sz[0] * a.g.sz[1])};
+  double w = 1.0;
+  for (int d = 0; d < a.nD; ++d) {
+    if (d == a.axis) continue;
+    if (a.hasB0[d] && c[d] < a.depth[d]) w *= a.norm[d][c[d]];
+    if (a.hasB1[d] && c[d] >= a.n[d] - a.depth[d]) w *= a.norm[d][a.n[d] - 1 - c[d]];
+  }
+  return w;
+}
+
+__global__ void __launch_bounds__(DRAG_THREADS) k_drag(DragArgs a) {
+  __shared__ double red[DRAG_THREADS];
+  double acc = 0.0;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < a.g.n; q += gridDim.x * blockDim.x) {
+    const size_t p = a.g.gridIndex(q);
+    if (a.iblank && a.iblank[p] == 0) continue;
+    double md = 0.0;
+    for (int l = 0; l < a.nD; ++l) md = (l == 0) ? a.metricsK[p] * a.dirv[0] : md + a.metricsK[(size_t)l * a.cs + p] * a.dirv[l];
+    acc += (0.0 - (a.pressure[p] - 1.0 / a.gamma)) * drag_patch_norm(a, q) * (md * a.factor);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = DRAG_THREADS / 2; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) a.partial[blockIdx.x] = red[0];
+}
+
+template <int ND>
+__global__ void k_drag_forcing(DragArgs a) {
+  constexpr int NU = ND + 2;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.g.n) return;
+  const size_t p = a.g.gridIndex(q);
+  if (a.iblank && a.iblank[p] == 0) return;
+  double m[ND];
+#pragma unroll
+  for (int l = 0; l < ND; ++l) m[l] = a.metricsK[(size_t)l * a.cs + p];
+  const double sgn = a.normalDirection > 0 ? 1.0 : -1.0;
+  if (a.continuous) {
+    double arc = 0.0;
+#pragma unroll
+    for (int l = 0; l < ND; ++l) arc = (l == 0) ? m[0] * m[0] : arc + m[l] * m[l];
+    arc = sqrt(arc);
+    double n[ND], Qp[NU], A[NU][NU];
+    double F = 0.0;
+#pragma unroll
+    for (int l = 0; l < ND; ++l) {
+      n[l] = m[l] / arc;
+      const double t = (a.W[(size_t)(l + 1) * a.csW + p] - sgn * fabs(a.dirv[l])) * n[l];
+      F = (l == 0) ? t : F + t;
+    }
+    F = a.jac[p] * F;
+#pragma unroll
+    for (int c = 0; c < NU; ++c) Qp[c] = a.Q[(size_t)c * a.csQ + p];
+    incoming_jacobian<ND>(Qp, m, a.gamma, -a.normalDirection, A);
+#pragma unroll
+    for (int c = 0; c < NU; ++c) {
+      double t = 0.0;
+#pragma unroll
+      for (int l = 0; l < ND; ++l) t = (l == 0) ? A[1][c] * n[0] : t + A[l + 1][c] * n[l];
+      a.out[(size_t)c * a.g.n + q] = (0.0 - a.sigmaI) * F * t;
+    }
+    return;
+  }
+  double md = 0.0, usq = 0.0;
+#pragma unroll
+  for (int l = 0; l < ND; ++l) md = (l == 0) ? m[0] * a.dirv[0] : md + m[l] * a.dirv[l];
+  const double F = a.jac[p] * (sgn * a.factor) * (a.gamma - 1.0) * md;
+#pragma unroll
+  for (int l = 0; l < ND; ++l) {
+    const double ul = a.u[(size_t)l * a.cs + p];
+    a.out[(size_t)(l + 1) * a.g.n + q] = (0.0 - ul) * F;
+    usq = (l == 0) ? ul * ul : usq + ul * ul;
+  }
+  a.out[q] = 0.5 * usq * F;
+  a.out[(size_t)(ND + 1) * a.g.n + q] = F;
+}
+
+int drag_args(mg_state* s, mg_patch* p, const double direction[3], DragArgs* a) {
+  mg_grid* g = s->grid;
+  std::memset(a, 0, sizeof(*a));
+  const int nD = s->nD;
+  const int k = std::abs(p->normalDirection);
+  if (k < 1 || k > nD) MG_FAIL("pressure drag: the COST_TARGET patch needs a normal direction");
+  double nrm = 0.0;
+  for (int l = 0; l < nD; ++l) nrm += direction[l] * direction[l];
+  if (nrm <= 2.220446049250313e-16) MG_FAIL("Unable to determine a unit vector for computing pressure drag!");
+  for (int l = 0; l < nD; ++l) a->dirv[l] = direction[l] / sqrt(nrm);
+  a->g = geom(p);
+  a->iblank = g->iblank;
+  a->pressure = s->pressure.comp(0);
+  a->metricsK = g->metrics.comp(nD * (k - 1));
+  a->jac = g->jacobian.comp(0);
+  a->u = s->velocity.comp(0);
+  a->Q = s->Q[s->cur].comp(0);
+  a->W = s->W[s->curW].comp(0);
+  a->cs = g->metrics.compStride;
+  a->csQ = s->Q[s->cur].compStride;
+  a->csW = s->W[s->curW].compStride;
+  a->nD = nD;
+  a->axis = k - 1;
+  a->normalDirection = p->normalDirection;
+  a->continuous = s->opt.useContinuousAdjoint;
+  for (int d = 0; d < nD; ++d) {
+    const MgDevOp& op = g->firstDerivative[d]->op;
+    a->n[d] = g->localSize[d];
+    a->depth[d] = op.normDepth;
+    a->hasB0[d] = op.hasDomainBoundary[0];
+    a->hasB1[d] = op.hasDomainBoundary[1];
+    for (int m = 0; m < MG_MAX_BDEPTH; ++m) a->norm[d][m] = op.normBoundary[m];
+  }
+  a->factor = 1.0 / g->firstDerivative[k - 1]->op.normBoundary[0];
+  a->gamma = s->opt.ratioOfSpecificHeats;
+  a->sigmaI = p->inviscidPenaltyAmount;
+  return 0;
+}
+
 }  // namespace
 
 int mg_functional_quadrature_impl(mg_state* s, int patchType, const double* integrandDevice, double* value) {
@@ -829,5 +971,50 @@ int mg_functional_actuator_gradient_impl(mg_patch* p, double timeRampFactor, dou
   MG_CUDA(cudaGetLastError());
   MG_CUDA(cudaMemcpyAsync(hostOut, out, (size_t)p->nPatchPoints * sizeof(double), cudaMemcpyDeviceToHost, mg_stream()));
   MG_CUDA(cudaStreamSynchronize(mg_stream()));
+  return 0;
+}
+
+// computePressureDrag (reference src/PressureDragImpl.f90:61-132); local to this rank, the caller reduces
+int mg_functional_pressure_drag_impl(mg_state* s, const double direction[3], double* value) {
+  if (!s->dependentValid) MG_TRY(mg_state_update_impl(s, nullptr));
+  static double* partial = nullptr;
+  if (!partial) MG_CUDA(cudaMalloc(&partial, DRAG_BLOCKS * sizeof(double)));
+  double sum = 0.0;
+  for (mg_patch* p : s->patches) {
+    if (p->type != MG_PATCH_COST_TARGET || p->nPatchPoints <= 0) continue;
+    DragArgs a;
+    MG_TRY(drag_args(s, p, direction, &a));
+    a.partial = partial;
+    k_drag<<<DRAG_BLOCKS, DRAG_THREADS, 0, mg_stream()>>>(a);
+    MG_CUDA(cudaGetLastError());
+    double host[DRAG_BLOCKS];
+    MG_CUDA(cudaMemcpyAsync(host, partial, sizeof(host), cudaMemcpyDeviceToHost, mg_stream()));
+    MG_CUDA(cudaStreamSynchronize(mg_stream()));
+    for (int i = 0; i < DRAG_BLOCKS; ++i) sum += host[i];
+  }
+  *value = sum;
+  return 0;
+}
+
+// computePressureDragAdjointForcing (reference :148-267) into the COST_TARGET patches' "adjointForcing"
+int mg_functional_pressure_drag_forcing_impl(mg_state* s, const double direction[3]) {
+  if (!s->dependentValid) MG_TRY(mg_state_update_impl(s, nullptr));
+  for (mg_patch* p : s->patches) {
+    if (p->type != MG_PATCH_COST_TARGET || p->nPatchPoints <= 0) continue;
+    DragArgs a;
+    MG_TRY(drag_args(s, p, direction, &a));
+    double* out = nullptr;
+    auto it = p->arrays.find("adjointForcing");
+    if (it == p->arrays.end()) {
+      MG_TRY(mg_patch_alloc_array(p, "adjointForcing", s->nU, &out));
+      MG_CUDA(cudaMemsetAsync(out, 0, (size_t)p->nPatchPoints * s->nU * sizeof(double), mg_stream()));
+    } else out = it->second.p;
+    a.out = out;
+    MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
+      k_drag_forcing<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a);
+      return 0;
+    }));
+    MG_CUDA(cudaGetLastError());
+  }
   return 0;
 }

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <map>
 #include <string>
+#include <vector>
 
 #include "grid.h"
 
@@ -14,6 +15,7 @@ enum {
   MG_PATCH_ISOTHERMAL_WALL = 4,
   MG_PATCH_COST_TARGET = 5,
   MG_PATCH_ACTUATOR = 6,
+  MG_PATCH_BLOCK_INTERFACE = 7,
 };
 
 struct mg_patch {
@@ -30,6 +32,13 @@ struct mg_patch {
   std::map<std::string, Array> arrays;     // patch-point arrays, (nPatchPoints, nComp) point fastest
   bool AplusReady = false;
   int AplusIncoming = 0;
+  // SAT_BLOCK_INTERFACE (reference include/BlockInterfacePatch.f90): the conforming patch of the other block, this
+  // patch's index reordering, and the penalty amounts / normal directions of both sides (METRICS exchange)
+  mg_patch* partner = nullptr;
+  int reorder[3] = {1, 2, 3};
+  bool metricsReady = false;
+  double sigmaIL = 0.0, sigmaIR = 0.0, sigmaVL = 0.0, sigmaVR = 0.0;
+  int normalL = 0, normalR = 0;
 };
 
 int mg_patch_create_impl(mg_state* s, int type, const char* name, int normalDirection, const int extent[6],
@@ -42,9 +51,18 @@ int mg_patch_collect_impl(mg_patch* p, const MgField* f, int nComp, const char* 
 int mg_patch_disperse_impl(mg_patch* p, const char* name, int nComp, MgField* f);
 int mg_patches_update_impl(mg_state* s);
 
+// block interfaces (interface.cu)
+bool mg_state_has_interfaces(const mg_state* s);
+int mg_interface_link(mg_patch* a, mg_patch* b, const int reorderA[3]);
+int mg_interfaces_exchange(const std::vector<mg_state*>& states, int mode);
+int mg_interface_apply(mg_state* s, mg_patch* p, int mode);
+int mg_interfaces_adjoint_sources(mg_state* s, MgField* temp1);
+
 // functionals
 int mg_functional_quadrature_impl(mg_state* s, int patchType, const double* integrandDevice, double* value);
 int mg_functional_acoustic_noise_impl(mg_state* s, double timeRampFactor, double* value);
 int mg_functional_acoustic_noise_forcing_impl(mg_state* s, double timeRampFactor);
 int mg_functional_actuator_sensitivity_impl(mg_state* s, double timeRampFactor, double* value);
 int mg_functional_actuator_gradient_impl(mg_patch* p, double timeRampFactor, double* hostOut);
+int mg_functional_pressure_drag_impl(mg_state* s, const double direction[3], double* value);
+int mg_functional_pressure_drag_forcing_impl(mg_state* s, const double direction[3]);

@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "grid.h"
+#include "patches.h"
 #include "stencil_apply.h"
 #include "rhs_fused.h"
 
@@ -571,6 +572,37 @@ int mg_state_rhs_forward_general(mg_state* s) {
   return add_dissipation_general(s, MG_FORWARD);
 }
 
+// adjointFirstDerivative of src(:, :, j) along j (into scratch A), summed over j, followed by the change of
+// variables back to the conserved adjoint; rhs -/+= sign * result (reference src/RhsHelperImpl.f90:528-570,
+// :213-247, :987-1023).
+int mg_state_adjoint_finish(mg_state* s, MgField* src, double sign) {
+  mg_grid* g = s->grid;
+  const size_t N = g->N;
+  const int nD = s->nD, nU = s->nU;
+  MgField& A = g->scratchA;
+  const MgField& Q = s->Q[s->cur];
+  for (int j = 0; j < nD; ++j)
+    MG_TRY(mg_grid_apply(g, g->adjointFirstDerivative[j], src->comp((nU - 1) * j), src->compStride,
+                         A.comp((nU - 1) * j), A.compStride, nU - 1));
+  AdjFinishArgs f;
+  f.Q = Q.comp(0);
+  f.csQ = Q.compStride;
+  f.v = s->specificVolume.comp(0);
+  f.u = s->velocity.comp(0);
+  f.d = A.comp(0);
+  f.rhs = s->rhs.comp(0);
+  f.cs = A.compStride;
+  f.N = N;
+  f.gamma = s->opt.ratioOfSpecificHeats;
+  f.sign = sign;
+  MG_TRY(dispatch_nd(nD, [&](auto nd) {
+    k_adjoint_finish<decltype(nd)::value><<<nblocks(N), 256, 0, mg_stream()>>>(f);
+    return 0;
+  }));
+  MG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // computeRhsAdjoint (reference src/RhsHelperImpl.f90:356-596)
 int mg_state_rhs_adjoint_general(mg_state* s) {
   mg_grid* g = s->grid;
@@ -614,36 +646,13 @@ int mg_state_rhs_adjoint_general(mg_state* s) {
     return 0;
   }));
   MG_CUDA(cudaGetLastError());
-  auto finish = [&](MgField& src, double sign) -> int {
-    // derivative of src(:, :, j) along j into A, then the variable change
-    for (int j = 0; j < nD; ++j)
-      MG_TRY(mg_grid_apply(g, g->adjointFirstDerivative[j], src.comp((nU - 1) * j), src.compStride,
-                           A.comp((nU - 1) * j), A.compStride, nU - 1));
-    AdjFinishArgs f;
-    f.Q = Q.comp(0);
-    f.csQ = Q.compStride;
-    f.v = s->specificVolume.comp(0);
-    f.u = s->velocity.comp(0);
-    f.d = A.comp(0);
-    f.rhs = s->rhs.comp(0);
-    f.cs = A.compStride;
-    f.N = N;
-    f.gamma = s->opt.ratioOfSpecificHeats;
-    f.sign = sign;
-    MG_TRY(dispatch_nd(nD, [&](auto nd) {
-      k_adjoint_finish<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(f);
-      return 0;
-    }));
-    MG_CUDA(cudaGetLastError());
-    return 0;
-  };
-  if (s->opt.viscosityOn) MG_TRY(finish(B, 1.0));
+  if (s->opt.viscosityOn) MG_TRY(mg_state_adjoint_finish(s, &B, 1.0));
   MG_TRY(add_dissipation_general(s, MG_ADJOINT));
   if (s->opt.viscosityOn && mg_patches_have_farfield(s)) {
     // addFarFieldAdjointPenalty (reference src/RhsHelperImpl.f90:89-250)
     MG_TRY(mg_field_zero(g, &B));
     MG_TRY(mg_patches_farfield_adjoint_sources(s, &B));
-    MG_TRY(finish(B, -1.0));
+    MG_TRY(mg_state_adjoint_finish(s, &B, -1.0));
   }
   return 0;
 }
@@ -686,25 +695,33 @@ int mg_state_cfl_dt_impl(mg_state* s, int wantDt, double given, double* result) 
 }
 
 // computeRhs for one grid/state (reference src/RegionImpl.f90:1877-2027)
-int mg_state_compute_rhs_impl(mg_state* s, int mode) {
+// computeRhs up to (not including) the multiplication by 1/J: the part that precedes the block-interface
+// exchange in the reference (src/RegionImpl.f90:1877-1925).  General path only.
+int mg_state_rhs_pre(mg_state* s, int mode) {
   mg_grid* g = s->grid;
-  const size_t N = g->N;
-  cudaStream_t st = mg_stream();
   if (!g->updated) MG_FAIL("computeRhs: grid metrics have not been computed (mg_grid_update)");
   if (mode != MG_FORWARD && mode != MG_ADJOINT) MG_FAIL("computeRhs: LINEARIZED mode is not implemented");
-  if (s->useFused && mg_fused_supported(s, mode)) {
-    // fused sweeps: the dependent variables live in the sweep-A outputs (no patches on this path)
-    if (!s->fusedValid) MG_TRY(mg_fused_sweepA(s));
-    if (mode == MG_FORWARD) return mg_fused_sweepB(s, 0, 0, 0.0);
-    MG_TRY(mg_fused_adjoint1(s));
-    return mg_fused_adjoint2(s, 0, 1, 0.0);
-  }
   MG_TRY(mg_halo_wait_pending());
   // The reference's callers run state%update after every substep (src/SolverImpl.f90:831-834); here
   // it is refreshed on demand.
   if (!s->dependentValid) MG_TRY(mg_state_update_impl(s, nullptr));
   if (mode == MG_FORWARD) MG_TRY(mg_state_rhs_forward_general(s));
   else MG_TRY(mg_state_rhs_adjoint_general(s));
+  return 0;
+}
+
+// ... and from the viscous interface adjoint penalty on (src/RegionImpl.f90:1960-2027): x 1/J, patches, sources,
+// hole masking.
+int mg_state_rhs_post(mg_state* s, int mode) {
+  mg_grid* g = s->grid;
+  const size_t N = g->N;
+  cudaStream_t st = mg_stream();
+  if (mode == MG_ADJOINT && s->opt.viscosityOn && mg_state_has_interfaces(s)) {
+    // addInterfaceAdjointPenalty (reference src/RhsHelperImpl.f90:831-1026)
+    MG_TRY(mg_field_zero(g, &g->scratchB));
+    MG_TRY(mg_interfaces_adjoint_sources(s, &g->scratchB));
+    MG_TRY(mg_state_adjoint_finish(s, &g->scratchB, -1.0));
+  }
   k_mul_jacobian<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), s->rhs.compStride, s->nU, g->jacobian.comp(0), N);
   MG_CUDA(cudaGetLastError());
   MG_TRY(mg_patches_apply(s, mode));
@@ -730,8 +747,38 @@ int mg_state_compute_rhs_impl(mg_state* s, int mode) {
   return 0;
 }
 
+int mg_state_compute_rhs_impl(mg_state* s, int mode) {
+  mg_grid* g = s->grid;
+  if (!g->updated) MG_FAIL("computeRhs: grid metrics have not been computed (mg_grid_update)");
+  if (mode != MG_FORWARD && mode != MG_ADJOINT) MG_FAIL("computeRhs: LINEARIZED mode is not implemented");
+  if (s->useFused && mg_fused_supported(s, mode)) {
+    // fused sweeps: the dependent variables live in the sweep-A outputs (no patches on this path)
+    if (!s->fusedValid) MG_TRY(mg_fused_sweepA(s));
+    if (mode == MG_FORWARD) return mg_fused_sweepB(s, 0, 0, 0.0);
+    MG_TRY(mg_fused_adjoint1(s));
+    return mg_fused_adjoint2(s, 0, 1, 0.0);
+  }
+  if (mg_state_has_interfaces(s))
+    MG_FAIL("computeRhs: a state with block-interface patches must be evaluated through its region (mg_region_compute_rhs)");
+  MG_TRY(mg_state_rhs_pre(s, mode));
+  return mg_state_rhs_post(s, mode);
+}
+
 // substepForward / substepAdjoint (reference src/RK4IntegratorImpl.f90:65-270).  The state update that
 // the reference's callers issue after every substep (src/SolverImpl.f90:831-834) stays with the caller.
+// The bookkeeping that precedes the RHS evaluation of a substep: times seen by the sources, and the stage factor
+// of the adjoint forcing (reference src/RK4IntegratorImpl.f90:106-158, :205-264).
+void mg_rk4_set_times(mg_state* s, int mode, double time, double dt, int stage) {
+  if (mode == MG_FORWARD) {
+    if (stage == 1 || stage == 3) s->timeProgressive = time + dt / 2.0;
+    if (stage == 2 || stage == 4) s->time = time + dt / 2.0;
+  } else if (mode == MG_ADJOINT) {
+    const double factor[5] = {0.0, 1.0, 0.5, 1.0, 2.0};
+    s->adjointForcingFactor = factor[stage];
+    if (stage == 4) s->timeProgressive = time - dt / 2.0;
+  }
+}
+
 int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int timestep, int stage) {
   (void)timestep;
   mg_grid* g = s->grid;
@@ -752,7 +799,8 @@ int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int time
       if (!s->fusedValid) MG_TRY(mg_fused_sweepA(s));
       return mg_fused_sweepB(s, 1, stage, dt);
     }
-    MG_TRY(mg_state_compute_rhs_impl(s, MG_FORWARD));
+    if (!s->rhsReady) MG_TRY(mg_state_compute_rhs_impl(s, MG_FORWARD));
+    s->rhsReady = false;
     MG_TRY(mg_state_make_exclusive(s, &s->Q[s->cur], true));
     MG_TRY(mg_state_make_exclusive(s, &s->rk1, true));
     a.b1 = s->rk1.comp(0);
@@ -776,7 +824,8 @@ int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int time
       if (stage == 3 || stage == 1) { *time -= dt / 2.0; s->time = *time; }
       return 0;
     }
-    MG_TRY(mg_state_compute_rhs_impl(s, MG_ADJOINT));
+    if (!s->rhsReady) MG_TRY(mg_state_compute_rhs_impl(s, MG_ADJOINT));
+    s->rhsReady = false;
     MG_TRY(mg_state_make_exclusive(s, &s->W[s->curW], true));
     MG_TRY(mg_state_make_exclusive(s, &s->rk1, true));
     a.b1 = s->rk1.comp(0);

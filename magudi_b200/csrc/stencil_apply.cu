@@ -41,8 +41,10 @@ __global__ void __launch_bounds__(256) k_apply(const MgDevOp* __restrict__ opp, 
 
   int kind = 0;   // 0 interior, 1 left closure, 2 right closure
   long m = 0;
-  if (op.hasDomainBoundary[0] && c < op.boundaryDepth) { kind = 1; m = c; }
-  else if (op.hasDomainBoundary[1] && c >= n - op.boundaryDepth) { kind = 2; m = n - 1 - c; }
+  // on a line shorter than two closure blocks the right closure wins, as in the reference, which writes the left
+  // rows first and the right rows after them (src/StencilOperatorImpl.f90:73-102)
+  if (op.hasDomainBoundary[1] && c >= n - op.boundaryDepth) { kind = 2; m = n - 1 - c; }
+  else if (op.hasDomainBoundary[0] && c < op.boundaryDepth) { kind = 1; m = c; }
   // nGhost == 0 happens only on a domain-boundary side, where the closure rows cover the points
   // whose interior stencil would reach outside: every remaining point is an interior point.
 

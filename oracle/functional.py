@@ -2,7 +2,10 @@
 
 Restates ``computeQuadratureOnPatches`` (reference ``src/PatchFactoryImpl.f90:376-444``),
 ``t_AcousticNoise%compute`` / ``%computeAdjointForcing`` (``src/AcousticNoiseImpl.f90:123-280``) and
-``t_ThermalActuator%computeSensitivity`` / ``%updateGradient`` (``src/ThermalActuatorImpl.f90:83-159, 383-443``).
+``t_ThermalActuator%computeSensitivity`` / ``%updateGradient`` (``src/ThermalActuatorImpl.f90:83-159, 383-443``),
+``t_PressureDrag%compute`` / ``%computeAdjointForcing`` (``src/PressureDragImpl.f90:61-267``) with the cost-target
+patch norm of ``updatePatchFactories`` (``src/PatchFactoryImpl.f90:496-505``) and the patch inner product
+(``src/CostTargetPatchImpl.f90:181-255``).
 """
 import numpy as np
 
@@ -52,3 +55,68 @@ def thermalActuatorGradient(grid, state, patch, timeRampFactor=1.0):
     nD = grid.nDimensions
     idx = patch.gridIndex0
     return state.adjointVariables[idx, nD + 1] * (grid.controlMollifier[idx, 0] * timeRampFactor)
+
+
+def costTargetPatchNorm(grid, patch):
+    """``patch%norm`` of a COST_TARGET patch (``src/PatchFactoryImpl.f90:496-505``): the SBP norm of every direction
+    but the patch's normal one, applied to 1 (no Jacobian), collected on the patch."""
+    nD = grid.nDimensions
+    gridNorm = np.ones((grid.nGridPoints, 1))
+    for j in range(nD):
+        if j + 1 != abs(patch.normalDirection):
+            gridNorm = grid.firstDerivative[j].applyNorm(gridNorm, grid.localSize)
+    return patch.collect(gridNorm)[:, 0]
+
+
+def unitDragDirection(nD, direction):
+    d = np.zeros(3)
+    d[:nD] = np.asarray(direction, dtype=float)[:nD]
+    return d / np.sqrt(np.sum(d ** 2))          # src/PressureDragImpl.f90:30-44
+
+
+def computePressureDrag(opt, patches, grid, state, direction):
+    """``computePressureDrag`` (``:61-132``): sum over the COST_TARGET patches (which lie on a boundary face) of
+    ``-(p - 1/gamma) . patch%norm . (metrics_k . direction) / normBoundary(1)``."""
+    nD = grid.nDimensions
+    d = unitDragDirection(nD, direction)
+    J = 0.0
+    for p in patches:
+        if p.patchType != "COST_TARGET" or p.gridIndex != grid.index:
+            continue
+        k = abs(p.normalDirection)
+        factor = 1.0 / grid.firstDerivative[k - 1].normBoundary[0]
+        F1 = -(state.pressure[:, 0] - 1.0 / opt.ratioOfSpecificHeats)
+        F2 = grid.metrics[:, nD * (k - 1):nD * k] @ d[:nD] * factor
+        idx = p.gridIndex0[p.active]
+        J += float(np.sum(F1[idx] * costTargetPatchNorm(grid, p)[p.active] * F2[idx]))
+    return J
+
+
+def computePressureDragAdjointForcing(opt, grid, state, patch, direction, inviscidPenaltyAmount=2.0):
+    """``computePressureDragAdjointForcing`` (``:148-267``), discrete and continuous-adjoint branches."""
+    from . import cns
+    nD = grid.nDimensions
+    d = unitDragDirection(nD, direction)[:nD]
+    k = abs(patch.normalDirection)
+    h = grid.firstDerivative[k - 1].normBoundary[0]
+    idx = patch.gridIndex0
+    ok = patch.active
+    m = grid.metrics[idx, nD * (k - 1):nD * k]
+    out = patch.adjointForcing
+    if opt.useContinuousAdjoint:
+        sigma = np.copysign(inviscidPenaltyAmount, float(patch.normalDirection)) / h     # CostTargetPatchImpl.f90:35-45
+        n = m / np.sqrt(np.sum(m ** 2, axis=1))[:, None]
+        F = grid.jacobian[idx, 0] * np.sum((state.adjointVariables[idx, 1:nD + 1]
+                                            - np.copysign(d, float(patch.normalDirection))) * n, axis=1)
+        A = cns.computeIncomingJacobianOfInviscidFlux(nD, state.conservedVariables[idx], m, opt.ratioOfSpecificHeats,
+                                                      -patch.normalDirection, state.specificVolume[idx, 0],
+                                                      state.velocity[idx], state.temperature[idx, 0])
+        val = -sigma * F[:, None] * np.einsum("pij,pi->pj", A[:, 1:nD + 1, :], n)
+        out[ok] = val[ok]
+        return
+    F = grid.jacobian[idx, 0] * np.copysign(1.0 / h, float(patch.normalDirection)) * \
+        (opt.ratioOfSpecificHeats - 1.0) * (m @ d)
+    u = state.velocity[idx]
+    out[ok, 0] = 0.5 * np.sum(u[ok] ** 2, axis=1) * F[ok]
+    out[ok, 1:nD + 1] = -u[ok] * F[ok, None]
+    out[ok, nD + 1] = F[ok]

@@ -1,6 +1,8 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the oracle on the same seeded
 inputs.  Tolerances: <= 1e-13 relative (max-norm scaled by the field max) on single operator applications
 and metrics, <= 1e-12 on RHS fields -- the fp64 tolerances stated in BASELINE.json:north_star."""
+import zlib
+
 import numpy as np
 import pytest
 
@@ -31,7 +33,7 @@ def test_stencil_apply(scheme, direction, periodic, overlap):
     import magudi_b200 as mb
     from oracle import stencil as ost
     n = [37, 35, 34]
-    rng = np.random.default_rng(hash((scheme, direction, periodic)) % 2**31)
+    rng = np.random.default_rng(zlib.crc32(repr((scheme, direction, periodic)).encode()))
     x = rng.standard_normal((int(np.prod(n)), 3))
     per = (periodic,) * 3
     a = mb.StencilOperator.setup(scheme).update((1, 1, 1), (0, 0, 0), per, direction, overlap)

@@ -33,6 +33,10 @@ ncu)
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s ${NCU_SKIP:-1} -c 1 -f -o $out/prof_$k \
       python bench.py --steps 1 --warmup 0 --no-cpu-baseline > $out/ncu_$k.log 2>&1
     echo "ncu $k rc=$?"
+    # the reports are too large to travel in numbers (64 MiB cap on gpurun_out): keep the raw page as CSV
+    ncu -i $out/prof_$k.ncu-rep --page raw --csv > $out/raw_$k.csv 2>/dev/null
+    ncu -i $out/prof_$k.ncu-rep --page source --csv > $out/source_$k.csv 2>/dev/null
+    [ -z "$KEEP_REP" ] && rm -f $out/prof_$k.ncu-rep
   done ;;
 launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \
