@@ -86,6 +86,64 @@ __device__ __forceinline__ void prefetch_streams(const FusedArgs& a, int kIn, bo
   }
 }
 
+// The same, with everything that does not change along the march hoisted out of it: a thread keeps the base
+// (stream + tile row) of its NPF streams; one step costs a select, a multiply-add and the prefetch per stream
+// (the loop above re-derived stream, row and validity every plane: ~70 instructions per thread and plane).
+template <int NPF, bool KEEP = true>
+struct PfItems {
+  const double* base[KEEP ? NPF : 1];
+  long rowOff;
+  int lane;
+  unsigned inMask;
+  bool ok;
+  // KEEP: the stream bases live in registers (2 per stream).  !KEEP: for the kernels that have no registers to
+  // spare the base is re-read from the argument block (one indexed constant load) every plane.
+  __device__ __forceinline__ void init(const FusedArgs& a, long rowOffset, int lane16, bool rowOk) {
+    inMask = 0u;
+    rowOff = rowOffset;
+    lane = lane16;
+    ok = rowOk;
+    if constexpr (KEEP) {
+#pragma unroll
+      for (int n = 0; n < NPF; ++n) {
+        const int sid = lane16 + 16 * n;
+        base[n] = (rowOk && sid < a.pfAll) ? a.pf[sid] + rowOffset : nullptr;
+        if (sid < a.pfIn) inMask |= 1u << n;
+      }
+    }
+  }
+  // stateless form (nothing kept across planes): the caller passes the tile-row offset again
+  __device__ static __forceinline__ void issue_stateless(const FusedArgs& a, int kIn, bool okIn, int kOut, bool okOut,
+                                                         long rowOffset, int lane16, bool rowOk) {
+    if (!rowOk) return;
+    const long offIn = rowOffset + (long)kIn * a.plane, offOut = rowOffset + (long)kOut * a.plane;
+#pragma unroll
+    for (int n = 0; n < NPF; ++n) {
+      const int sid = lane16 + 16 * n;
+      const bool in = sid < a.pfIn;
+      if (sid < a.pfAll && (in ? okIn : okOut)) prefetch_l2(a.pf[sid] + (in ? offIn : offOut));
+    }
+  }
+  __device__ __forceinline__ void issue(const FusedArgs& a, int kIn, bool okIn, int kOut, bool okOut) const {
+    if constexpr (KEEP) {
+#pragma unroll
+      for (int n = 0; n < NPF; ++n) {
+        const bool in = (inMask >> n) & 1u;
+        if (base[n] != nullptr && (in ? okIn : okOut)) prefetch_l2(base[n] + (long)(in ? kIn : kOut) * a.plane);
+      }
+    } else {
+      if (!ok) return;
+      const long offIn = rowOff + (long)kIn * a.plane, offOut = rowOff + (long)kOut * a.plane;
+#pragma unroll
+      for (int n = 0; n < NPF; ++n) {
+        const int sid = lane + 16 * n;
+        const bool in = sid < a.pfIn;
+        if (sid < a.pfAll && (in ? okIn : okOut)) prefetch_l2(a.pf[sid] + (in ? offIn : offOut));
+      }
+    }
+  }
+};
+
 __device__ __forceinline__ int wrap_index(int c, const DirInfo& d) {
   if (c >= 0 && c < d.n) return c;
   if (!d.periodic) return -1;

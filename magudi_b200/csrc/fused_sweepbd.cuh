@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(TX * TYv, (TYv == 8 && R < 4) ? 3 : 2) k_sweep
       // pull the lines of the planes needed `prefetch` steps ahead into L2 (costs no registers)
       int kf = ks + a.prefetch, kq = kp + a.prefetch;
       if (a.wrapK) { if (kf >= a.nz) kf -= a.nz; if (kq < 0) kq += a.nz; else if (kq >= a.nz) kq -= a.nz; }
-      prefetch_streams(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz),
-                       (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
+      PfItems<2, false>::issue_stateless(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz),
+                                         pij - tx, tx, i0 < a.nx && j < a.ny);
     }
     // ---- inputs of the output plane p = s - RK (consumed by the emit below; issued first)
     double ejac = 0.0, vb1[NU], vb2[NU], arcg = 0.0;

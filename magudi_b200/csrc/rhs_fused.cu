@@ -83,13 +83,14 @@ __global__ void __launch_bounds__(NT, 3) k_sweepA(FusedArgs a) {
   int ks = wrapPlane(kc0 - RK);
   int slot = 0;                    // queue slot of the arriving plane s
 
+  PfItems<1> pfi;
+  pfi.init(a, (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
     // ---- arrival of plane s
     if (ND == 3 && a.prefetch) {
       int kf = ks + a.prefetch, kq = ks - RK + a.prefetch;
       if (a.wrapK) { if (kf >= a.nz) kf -= a.nz; if (kq < 0) kq += a.nz; else if (kq >= a.nz) kq -= a.nz; }
-      prefetch_streams(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz),
-                       (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
+      pfi.issue(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz));
     }
     const int p = s - RK;
     int sp0 = slot - RK;             // slot of plane p
@@ -291,12 +292,13 @@ __global__ void __launch_bounds__(NT, 2) k_diss(FusedArgs a) {
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
     for (int c = 0; c < NU; ++c) qq[q][c] = 0.0;
+  PfItems<1> pfi;
+  pfi.init(a, (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
     if (ND == 3 && a.prefetch) {
       int kf = ks + a.prefetch, kq = ks - RK + a.prefetch;
       if (a.wrapK) { if (kf >= a.nz) kf -= a.nz; if (kq < 0) kq += a.nz; else if (kq >= a.nz) kq -= a.nz; }
-      prefetch_streams(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz),
-                       (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
+      pfi.issue(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz));
     }
 #pragma unroll
     for (int q = 0; q < NQ - 1; ++q)
@@ -529,14 +531,15 @@ __global__ void __launch_bounds__(NT, 2) k_sweepB(FusedArgs a) {
       }
     }
   };
+  PfItems<3> pfi;
+  pfi.init(a, (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
     const long soff = (ND == 3) ? (long)ks * a.plane : 0;
     const bool planeActive = s >= kc0 && s < kc1;
     if (ND == 3 && a.prefetch) {
       int kf = ks + a.prefetch, kq = kp + a.prefetch;
       if (a.wrapK) { if (kf >= a.nz) kf -= a.nz; if (kq < 0) kq += a.nz; else if (kq >= a.nz) kq -= a.nz; }
-      prefetch_streams(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz),
-                       (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
+      pfi.issue(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz));
     }
     if constexpr (ND == 3) {
       if (s - RK >= kc0 && mine) emit_load(kp);
@@ -718,12 +721,13 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint1(FusedArgs a) {
   int ks = wrapPlane(kc0 - RK);
   int slot = 0;                    // queue slot of the arriving plane s
 
+  PfItems<3> pfi;
+  pfi.init(a, (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
     if (ND == 3 && a.prefetch) {
       int kf = ks + a.prefetch, kq = ks - RK + a.prefetch;
       if (a.wrapK) { if (kf >= a.nz) kf -= a.nz; if (kq < 0) kq += a.nz; else if (kq >= a.nz) kq -= a.nz; }
-      prefetch_streams(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz),
-                       (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
+      pfi.issue(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz));
     }
     if (inside) {
       const double* __restrict__ Wp = a.Win + ((ND == 3) ? (long)ks * a.plane : 0) + pij;
@@ -1018,14 +1022,15 @@ __global__ void __launch_bounds__(NT, 2) k_adjoint2(FusedArgs a) {
   for (int q = 0; q < RK + 1; ++q)
 #pragma unroll
     for (int c = 0; c < NG; ++c) rxy[q][c] = 0.0;
+  PfItems<3> pfi;
+  pfi.init(a, (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
     const long soff = (ND == 3) ? (long)ks * a.plane : 0;
     const bool planeActive = s >= kc0 && s < kc1;
     if (ND == 3 && a.prefetch) {
       int kf = ks + a.prefetch, kq = kp + a.prefetch;
       if (a.wrapK) { if (kf >= a.nz) kf -= a.nz; if (kq < 0) kq += a.nz; else if (kq >= a.nz) kq -= a.nz; }
-      prefetch_streams(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz),
-                       (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
+      pfi.issue(a, kf, a.wrapK || s + a.prefetch < a.nz + RK, kq, a.wrapK || (kq >= 0 && kq < a.nz));
     }
     if (a.viscous) {
       if (inside) {

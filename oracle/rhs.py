@@ -7,8 +7,9 @@ Follows:
   * ``src/RhsHelperImpl.f90:10-87``      addDissipation
   * ``src/RhsHelperImpl.f90:254-354``    computeRhsForward
   * ``src/RhsHelperImpl.f90:356-596``    computeRhsAdjoint
+  * ``src/RhsHelperImpl.f90:598-829``    computeRhsLinearized
   * ``src/RegionImpl.f90:1877-2027``     computeRhs (orchestration, x 1/J, patches, sources)
-  * ``src/RK4IntegratorImpl.f90:65-270`` substepForward / substepAdjoint
+  * ``src/RK4IntegratorImpl.f90:65-369`` substepForward / substepAdjoint / substepLinearized
 """
 from __future__ import annotations
 
@@ -177,6 +178,58 @@ def computeRhsAdjoint(opt, grid, state, patches=()):
         addFarFieldAdjointPenalty(opt, grid, state, patches)
 
 
+def computeRhsLinearized(opt, grid, state, patches=()):
+    """``computeRhsLinearized`` (``src/RhsHelperImpl.f90:598-829``): the perturbation lives in
+    ``state.adjointVariables``."""
+    nD = grid.nDimensions
+    nU = nD + 2
+    N = grid.nGridPoints
+    g = opt.ratioOfSpecificHeats
+    state.rightHandSide[:, :] = 0.0
+    Q, dQ = state.conservedVariables, state.adjointVariables
+    v, u, T = state.specificVolume[:, 0], state.velocity, state.temperature[:, 0]
+    f1 = np.zeros((N, nU, nD))
+    for i in range(nD):
+        m1 = grid.metrics[:, nD * i:nD * (i + 1)]
+        A = cns.computeJacobianOfInviscidFlux(nD, Q, m1, g, v, u, T)
+        f1[:, :, i] = np.einsum("pij,pj->pi", A, dQ)
+    f2 = np.zeros((N, nU, nD))
+    if opt.viscosityOn:
+        # perturbation of (u, T) up to the factors absorbed in the second-partial Jacobians (:692-714)
+        t = np.zeros((N, nU - 1))
+        for i in range(nD):
+            t[:, i] = -u[:, i] * dQ[:, 0] + dQ[:, i + 1]
+        t[:, nU - 2] = -v * Q[:, nU - 1] * dQ[:, 0]
+        t[:, nU - 2] = t[:, nU - 2] - np.sum(u * t[:, :nD], axis=1) + dQ[:, nU - 1]
+        t[:, nU - 2] = t[:, nU - 2] * g
+        t = t * v[:, None]
+        temp = np.zeros((N, nU - 1, nD))
+        for i in range(nD):
+            temp[:, :, i] = grid.firstDerivative[i].apply(t, grid.localSize)
+        mu = state.dynamicViscosity[:, 0]
+        lam = state.secondCoefficientOfViscosity[:, 0]
+        kap = state.thermalDiffusivity[:, 0]
+        for i in range(nD):
+            m1 = grid.metrics[:, nD * i:nD * (i + 1)]
+            B1 = cns.computeFirstPartialViscousJacobian(nD, Q, m1, state.stressTensor, state.heatFlux,
+                                                        opt.powerLawExponent, g, v, u, T)
+            f2[:, :, i] += np.einsum("pij,pj->pi", B1, dQ)
+            for j in range(nD):
+                m2 = grid.metrics[:, nD * j:nD * (j + 1)]
+                B2 = cns.computeSecondPartialViscousJacobian(nD, u, mu, lam, kap, grid.jacobian[:, 0], m1, m2)
+                f2[:, 1:, i] += np.einsum("pij,pj->pi", B2, temp[:, :, j])
+        for patch in patches:
+            if hasattr(patch, "collectViscousFluxes") and patch.gridIndex == grid.index:
+                patch.collectViscousFluxes(f2)
+    f1 = f1 - f2
+    total = None
+    for i in range(nD):
+        d = grid.firstDerivative[i].apply(f1[:, :, i], grid.localSize)
+        total = d if total is None else total + d
+    state.rightHandSide -= total
+    addDissipation(LINEARIZED, opt, grid, state)
+
+
 def addAcousticSources(mode, opt, grid, state):
     """``addSources`` -> ``addAcousticSource`` (``src/StateImpl.f90:672-705``,
     ``src/AcousticSourceImpl.f90:34-64``), forward mode only."""
@@ -198,8 +251,10 @@ def computeRhs(mode, opt, grid, state, patches=(), timestep=0, stage=1):
     """``computeRhs`` for one grid (``src/RegionImpl.f90:1877-2027``)."""
     if mode == FORWARD:
         computeRhsForward(opt, grid, state, patches)
-    else:
+    elif mode == ADJOINT:
         computeRhsAdjoint(opt, grid, state, patches)
+    else:
+        computeRhsLinearized(opt, grid, state, patches)
     state.rightHandSide *= grid.jacobian
     for patch in patches:
         if patch.gridIndex == grid.index:
@@ -274,4 +329,31 @@ class RK4Integrator:
             W[:, :] = self.buffer2 - dt * state.rightHandSide / 6.0
             time = time - dt / 2.0
             state.time = time
+        return time
+
+    def substepLinearized(self, rhs_fn, state, time, dt, timestep, stage):
+        """``substepLinearizedRK4`` (``:272-369``): the forward scheme applied to ``adjointVariables``."""
+        W = state.adjointVariables
+        if stage == 1:
+            self.buffer1[:, :] = W
+            state.timeProgressive = time + dt / 2.0
+            rhs_fn(LINEARIZED, timestep, stage)
+            self.buffer2[:, :] = W + dt * state.rightHandSide / 6.0
+            W[:, :] = self.buffer1 + dt * state.rightHandSide / 2.0
+        elif stage == 2:
+            time = time + dt / 2.0
+            state.time = time
+            rhs_fn(LINEARIZED, timestep, stage)
+            self.buffer2[:, :] = self.buffer2 + dt * state.rightHandSide / 3.0
+            W[:, :] = self.buffer1 + dt * state.rightHandSide / 2.0
+        elif stage == 3:
+            state.timeProgressive = time + dt / 2.0
+            rhs_fn(LINEARIZED, timestep, stage)
+            self.buffer2[:, :] = self.buffer2 + dt * state.rightHandSide / 3.0
+            W[:, :] = self.buffer1 + dt * state.rightHandSide
+        elif stage == 4:
+            time = time + dt / 2.0
+            state.time = time
+            rhs_fn(LINEARIZED, timestep, stage)
+            W[:, :] = self.buffer2 + dt * state.rightHandSide / 6.0
         return time

@@ -13,7 +13,7 @@ properties in tests/test_block_interface.py).
 import numpy as np
 import pytest
 
-from helpers import gpu_case_from_oracle, random_state, relerr
+from helpers import gpu_case_from_oracle, random_state, relerr, relerr_global
 from test_adjoint_relation import check_adjoint_relation, delta_conserved
 from test_block_interface import two_blocks
 
@@ -128,8 +128,8 @@ def test_three_block_index_reordering(gpu_lib, nd, visc):
     # what each patch received is the partner's data under the reordering (reshapeReceivedData)
     for p, q in zip(patches, gp):
         assert relerr(q.getArray("conservedVariablesR", nd + 2), p.conservedVariablesR) <= 1e-15
-        # (3-D non-periodic metrics come from the curl form, whose cancellation amplifies FMA rounding: DESIGN 2)
-        assert relerr(q.getArray("metricsR", nd), p.metricsAlongNormalDirectionR) <= 1e-11
+        # (scaled by the largest metric entry: the off-diagonal metrics of this grid are small)
+        assert relerr_global(q.getArray("metricsR", nd), p.metricsAlongNormalDirectionR) <= 1e-12
 
 
 def test_two_block_adjoint_relation_on_the_cuda_path(gpu_lib):

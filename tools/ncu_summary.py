@@ -29,7 +29,8 @@ METRICS = [
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
 ]
-SHORT = {"k_sweepA": "sweepA", "k_diss": "dissipation", "k_sweepB": "sweepB", "k_adjoint1": "adjoint1",
+SHORT = {"k_sweepA": "sweepA", "k_diss": "dissipation", "k_sweepBD": "sweepB", "k_sweepB": "sweepB",
+         "k_adjoint1v2": "adjoint1", "k_adjoint1": "adjoint1",
          "k_adjoint2": "adjoint2"}
 
 
@@ -39,27 +40,31 @@ def to_bytes(value, unit):
 
 
 def main():
-    rows = list(csv.reader(open(sys.argv[1])))
-    hdr, units, data = rows[0], rows[1], rows[2:]
-    names = [d[hdr.index("Kernel Name")] for d in data]
+    """argv: raw.csv[,raw2.csv,...] out_summary.csv [out_traffic.json] -- several raw pages (one per capture) are
+    merged column-wise; every cell carries its own unit because ncu scales units per report."""
+    cols = []          # (kernel name, {metric: (value, unit)})
+    for path in sys.argv[1].split(","):
+        rows = list(csv.reader(open(path)))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        for d in data:
+            cols.append((d[hdr.index("Kernel Name")], {h: (v, u) for h, v, u in zip(hdr, d, units)}))
     with open(sys.argv[2], "w", newline="") as f:
         w = csv.writer(f)
-        w.writerow(["metric", "unit"] + names)
+        w.writerow(["metric"] + [n for n, _ in cols])
         for m in METRICS:
-            if m in hdr:
-                i = hdr.index(m)
-                w.writerow([m, units[i]] + [d[i] for d in data])
+            if any(m in c for _, c in cols):
+                w.writerow([m] + [(c[m][0] + (" " + c[m][1] if c[m][1] else "")) if m in c else "" for _, c in cols])
     if len(sys.argv) > 3:
         traffic = {}
-        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        it = hdr.index("gpu__time_duration.sum")
-        for d, n in zip(data, names):
+        tscale = {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}
+        for n, c in cols:
             key = next((v for k, v in SHORT.items() if k + "<" in n or k + "(" in n), None)
             if key is None:
                 continue
             e = traffic.setdefault(key, {"dram_bytes_per_launch": [], "ncu_ms": []})
-            e["dram_bytes_per_launch"].append(to_bytes(d[ir], units[ir]) + to_bytes(d[iw], units[iw]))
-            e["ncu_ms"].append(float(d[it].replace(",", "")) * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(units[it], 1.0))
+            e["dram_bytes_per_launch"].append(to_bytes(*c["dram__bytes_read.sum"]) + to_bytes(*c["dram__bytes_write.sum"]))
+            t = c["gpu__time_duration.sum"]
+            e["ncu_ms"].append(float(t[0].replace(",", "")) * tscale.get(t[1], 1.0))
         out = {k: {"dram_bytes_per_launch": sum(v["dram_bytes_per_launch"]) / len(v["dram_bytes_per_launch"]),
                    "ncu_ms": sum(v["ncu_ms"]) / len(v["ncu_ms"]), "launches_captured": len(v["ncu_ms"])}
                for k, v in traffic.items()}
