@@ -252,9 +252,12 @@ int mg_region_destroy(mg_region* r);
 int mg_region_add_state(mg_region* r, mg_state* s);
 /* updatePatchFactories: src/PatchFactoryImpl.f90:446-574 (target viscous fluxes of far-field patches) */
 int mg_region_update_patches(mg_region* r);
-/* %computeRhs(mode, timestep, stage): src/RegionImpl.f90:1877-2027 */
+/* %computeRhs(mode, timestep, stage): src/RegionImpl.f90:1877-2027.  MG_MODE_LINEARIZED evaluates
+ * computeRhsLinearized (src/RhsHelperImpl.f90:598-829) and the LINEARIZED branches of the patches: the perturbation
+ * is the state's adjointVariables, as in the reference. */
 int mg_region_compute_rhs(mg_region* r, int mode, int timestep, int stage);
-/* t_RK4Integrator%substepForward / %substepAdjoint: src/RK4IntegratorImpl.f90:65-270.  Includes the
+/* t_RK4Integrator%substepForward / %substepAdjoint / %substepLinearized: src/RK4IntegratorImpl.f90:65-369
+ * (mode selects the scheme; LINEARIZED advances the adjointVariables with the forward weights).  Includes the
  * states%update the reference's drivers issue after every substep (src/SolverImpl.f90:831-834) when
  * updateStates != 0. */
 int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep, int stage, int updateStates);

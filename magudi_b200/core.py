@@ -544,6 +544,14 @@ class RK4Integrator:
                                                    int(timestep), int(stage)))
         return t.value
 
+    def substepLinearized(self, time, timeStepSize, timestep, stage):
+        """``substepLinearizedRK4`` (``src/RK4IntegratorImpl.f90:272-369``): advances the perturbation held in
+        ``adjointVariables`` with the linearized RHS about the current conserved variables."""
+        t = C.c_double(time)
+        check(L.lib().mg_rk4_substep(self.region._h, LINEARIZED, C.byref(t), float(timeStepSize), int(timestep),
+                                     int(stage), 0))
+        return t.value
+
     def substepAdjoint(self, time, timeStepSize, timestep, stage):
         t = C.c_double(time)
         check(L.lib().mg_rk4_substep(self.region._h, ADJOINT, C.byref(t), float(timeStepSize), int(timestep),

@@ -110,12 +110,10 @@ __device__ __forceinline__ void cartesian_flux(int l, const double* Q, const Pri
 // y += A^T x with A = Jacobian of the inviscid flux along metrics m (reference :984-1444), minus
 // (if viscous) the first-partial viscous Jacobian (:2344-2600).  x, y have NU entries.
 template <int ND>
-__device__ __forceinline__ void add_flux_jacobian_transpose(const double* Q, const Prim<ND>& s, const double* m,
-                                                            double gamma, bool viscous, double powerLaw,
-                                                            const double* tau, const double* q, const double* x,
-                                                            double* y, double scale = 1.0) {
+__device__ __forceinline__ void flux_jacobian_matrix(const Prim<ND>& s, const double* m, double gamma, bool viscous,
+                                                     double powerLaw, const double* tau, const double* q,
+                                                     double (*A)[ND + 2]) {
   constexpr int NU = ND + 2;
-  double A[NU][NU];
   double uh = 0.0, usq = 0.0;
 #pragma unroll
   for (int i = 0; i < ND; ++i) {
@@ -172,12 +170,40 @@ __device__ __forceinline__ void add_flux_jacobian_transpose(const double* Q, con
     for (int c = 0; c < ND; ++c) A[c + 1][NU - 1] -= temp2 * cst[c];
     A[NU - 1][NU - 1] -= temp2 * temp1;
   }
+}
+
+template <int ND>
+__device__ __forceinline__ void add_flux_jacobian_transpose(const double* Q, const Prim<ND>& s, const double* m,
+                                                            double gamma, bool viscous, double powerLaw,
+                                                            const double* tau, const double* q, const double* x,
+                                                            double* y, double scale = 1.0) {
+  constexpr int NU = ND + 2;
+  (void)Q;
+  double A[NU][NU];
+  flux_jacobian_matrix<ND>(s, m, gamma, viscous, powerLaw, tau, q, A);
 #pragma unroll
   for (int j = 0; j < NU; ++j) {
     double acc = 0.0;
 #pragma unroll
     for (int i = 0; i < NU; ++i) acc += A[i][j] * x[i];
     y[j] += scale * acc;
+  }
+}
+
+// y += A x (the linearized fluxes, reference src/RhsHelperImpl.f90:660-690, :736-760)
+template <int ND>
+__device__ __forceinline__ void add_flux_jacobian_apply(const Prim<ND>& s, const double* m, double gamma, bool viscous,
+                                                        double powerLaw, const double* tau, const double* q,
+                                                        const double* x, double* y) {
+  constexpr int NU = ND + 2;
+  double A[NU][NU];
+  flux_jacobian_matrix<ND>(s, m, gamma, viscous, powerLaw, tau, q, A);
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < NU; ++j) acc += A[i][j] * x[j];
+    y[i] += acc;
   }
 }
 
@@ -209,6 +235,36 @@ __device__ __forceinline__ void add_second_partial_transpose(const double* u, do
     y[b] += scale * acc;
   }
   y[ND] += scale * (jac * (kap * temp1) * x[ND]);
+}
+
+// y += B x, same matrix (linearized viscous fluxes, reference src/RhsHelperImpl.f90:762-790)
+template <int ND>
+__device__ __forceinline__ void add_second_partial_apply(const double* u, double mu, double lam, double kap, double jac,
+                                                         const double* m1, const double* m2, const double* x,
+                                                         double* y) {
+  double temp1 = 0.0, d1 = 0.0, d2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    temp1 = (i == 0) ? m1[0] * m2[0] : temp1 + m1[i] * m2[i];
+    d2 = (i == 0) ? m2[0] * u[0] : d2 + m2[i] * u[i];
+    d1 = (i == 0) ? m1[0] * u[0] : d1 + m1[i] * u[i];
+  }
+  const double temp2 = mu * d2, temp3 = lam * d1;
+  double last = 0.0;
+#pragma unroll
+  for (int a = 0; a < ND; ++a) {
+    double acc = 0.0;
+#pragma unroll
+    for (int b = 0; b < ND; ++b) {
+      const double Bab = (a == b) ? mu * temp1 + (mu + lam) * m1[a] * m2[a]
+                                  : mu * m1[b] * m2[a] + lam * m1[a] * m2[b];
+      acc += jac * Bab * x[b];
+    }
+    y[a] += acc;
+    const double Blast = mu * temp1 * u[a] + m1[a] * temp2 + m2[a] * temp3;
+    last += jac * Blast * x[a];
+  }
+  y[ND] += last + jac * (kap * temp1) * x[ND];
 }
 
 // ---- rectilinear specialisations: the metric row of direction D is md * e_D, so most entries of the

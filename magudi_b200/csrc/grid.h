@@ -69,6 +69,7 @@ int mg_state_make_exclusive(mg_state* s, MgField* f, bool keepContents);
 void mg_state_pool_trim(mg_state* s);
 int mg_state_rhs_forward_general(mg_state* s);
 int mg_state_rhs_adjoint_general(mg_state* s);
+int mg_state_rhs_linearized_general(mg_state* s);
 int mg_state_compute_rhs_impl(mg_state* s, int mode);
 int mg_state_rhs_pre(mg_state* s, int mode);
 int mg_state_rhs_post(mg_state* s, int mode);

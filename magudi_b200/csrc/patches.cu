@@ -90,6 +90,22 @@ __global__ void k_farfield(FFArgs a) {
         r[c] += a.sigmaV * jac * acc;
       }
     }
+  } else if (a.mode == MG_LINEARIZED) {
+    // reference :258-268: - sigmaI (1/J) A+ dQ + sigmaV (1/J) (linearized contravariant viscous flux along dir)
+    double dq[NU];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) dq[c] = a.W[(size_t)c * a.csW + p];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < NU; ++j) acc += a.Aplus[(size_t)(i * NU + j) * a.g.n + q] * dq[j];
+      r[i] = -a.sigmaI * jac * acc;
+    }
+    if (a.viscous) {
+#pragma unroll
+      for (int c = 0; c < NU; ++c) r[c] += a.sigmaV * jac * a.Fv[(size_t)(c + NU * a.dir) * a.g.n + q];
+    }
   } else {
     double w[NU];
 #pragma unroll
@@ -181,6 +197,8 @@ __global__ void k_sponge(SpongeArgs a) {
   for (int c = 0; c < a.nU; ++c) {
     if (a.mode == MG_FORWARD)
       a.rhs[(size_t)c * a.cs + p] -= s * (a.X[(size_t)c * a.csX + p] - a.target[(size_t)c * a.cs + p]);
+    else if (a.mode == MG_LINEARIZED)
+      a.rhs[(size_t)c * a.cs + p] -= s * a.X[(size_t)c * a.csX + p];
     else
       a.rhs[(size_t)c * a.cs + p] += s * a.X[(size_t)c * a.csX + p];
   }
@@ -247,7 +265,8 @@ __global__ void k_wall(WallArgs a) {
     double y[NU];
 #pragma unroll
     for (int c = 0; c < NU; ++c) y[c] = 0.0;
-    add_flux_jacobian_transpose<ND>(Q, s, mm, a.gamma, false, 0.0, nullptr, nullptr, w, y);
+    if (a.mode == MG_LINEARIZED) add_flux_jacobian_apply<ND>(s, mm, a.gamma, false, 0.0, nullptr, nullptr, w, y);
+    else add_flux_jacobian_transpose<ND>(Q, s, mm, a.gamma, false, 0.0, nullptr, nullptr, w, y);
     double dp[NU];
     double usq = 0.0;
 #pragma unroll
@@ -256,6 +275,28 @@ __global__ void k_wall(WallArgs a) {
 #pragma unroll
     for (int i = 0; i < ND; ++i) dp[i + 1] = -u[i];
     dp[NU - 1] = 1.0;
+    if (a.mode == MG_LINEARIZED) {
+      // - sigmaI (1/J) (A - [0; m dp; 0]) dQ  (reference :187-191), w holds dQ
+      double dpw = 0.0;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) dpw += (dp[c] * (a.gamma - 1.0)) * w[c];
+#pragma unroll
+      for (int l = 0; l < ND; ++l) y[l + 1] -= mm[l] * dpw;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) r[c] = -a.sigmaI * jac * y[c];
+      if (a.isothermal && a.viscous) {
+        double pen[NU];
+        pen[0] = 0.0;
+#pragma unroll
+        for (int c = 1; c < NU; ++c) pen[c] = w[c];
+        pen[NU - 1] = pen[NU - 1] - w[0] * a.wallT[q] / a.gamma;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) r[c] -= a.sigmaV1 * (jac * pen[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < NU; ++c) a.rhs[(size_t)c * a.cs + p] += r[c];
+      return;
+    }
     double mw = 0.0;
 #pragma unroll
     for (int l = 0; l < ND; ++l) mw += mm[l] * w[l + 1];
@@ -549,6 +590,10 @@ int mg_patches_apply(mg_state* s, int mode) {
               MG_FAIL("far-field patch: viscous fluxes missing (call mg_region_update_patches after setting the target state)");
             a.Fv = fv->second.p;
             a.FvTarget = ft->second.p;
+          } else if (mode == MG_LINEARIZED) {
+            auto fv = p->arrays.find("viscousFluxes");
+            if (fv == p->arrays.end()) MG_FAIL("far-field patch: linearized viscous fluxes have not been collected");
+            a.Fv = fv->second.p;
           }
         }
         MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
@@ -626,8 +671,8 @@ int mg_patches_apply(mg_state* s, int mode) {
         break;
       }
       case MG_PATCH_ACTUATOR: {
-        if (mode != MG_FORWARD) break;
-        auto it = p->arrays.find("controlForcing");
+        if (mode == MG_ADJOINT) break;
+        auto it = p->arrays.find(mode == MG_FORWARD ? "controlForcing" : "deltaControlForcing");
         if (it == p->arrays.end()) break;
         if (!g->controlMollifier.p) MG_FAIL("actuator patch: control mollifier has not been set");
         AddArgs a;

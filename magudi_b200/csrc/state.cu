@@ -203,6 +203,100 @@ __global__ void k_adjoint_point(AdjArgs a) {
   }
 }
 
+struct LinArgs {
+  const double *Q, *W, *v, *u, *T, *tau, *q, *mu, *lam, *kap, *m, *jac;
+  const double* dT;   // derivatives of the primitive-like perturbation: component c + (NU-1)*j
+  double* t;          // phase 1 output: the perturbation, NU-1 components
+  double* Fhat;       // phase 2 output: linearized contravariant total flux, component c + NU*i
+  double* Fv;         // linearized contravariant viscous flux, component c + NU*i (may be null)
+  size_t csQ, csW, cs, N;
+  int viscous;
+  double gamma, powerLaw;
+};
+
+// computeRhsLinearized, perturbation of (u, T) up to the factors absorbed in the second-partial Jacobians
+// (reference src/RhsHelperImpl.f90:692-714); the perturbation dQ lives in the adjoint variables.
+template <int ND>
+__global__ void k_linearized_primitive(LinArgs a) {
+  constexpr int NU = ND + 2;
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= a.N) return;
+  double dq[NU], u[ND], t[NU - 1];
+#pragma unroll
+  for (int c = 0; c < NU; ++c) dq[c] = a.W[(size_t)c * a.csW + p];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) u[i] = a.u[(size_t)i * a.cs + p];
+  const double v = a.v[p];
+  double ut = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    t[i] = -u[i] * dq[0] + dq[i + 1];
+    ut = (i == 0) ? u[0] * t[0] : ut + u[i] * t[i];
+  }
+  double e = -v * a.Q[(size_t)(NU - 1) * a.csQ + p] * dq[0];
+  e = e - ut + dq[NU - 1];
+  t[NU - 2] = e * a.gamma;
+#pragma unroll
+  for (int c = 0; c < NU - 1; ++c) a.t[(size_t)c * a.cs + p] = t[c] * v;
+}
+
+// Linearized contravariant fluxes (reference :660-690 inviscid, :716-790 viscous): Fhat_i = A_i dQ - B1_i dQ
+// - [0; sum_j B2(m_i, m_j) d_j t]
+template <int ND>
+__global__ void k_linearized_flux(LinArgs a) {
+  constexpr int NU = ND + 2;
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= a.N) return;
+  double dq[NU], tau[ND * ND], q[ND], M[ND * ND];
+  Prim<ND> s;
+#pragma unroll
+  for (int c = 0; c < NU; ++c) dq[c] = a.W[(size_t)c * a.csW + p];
+  s.v = a.v[p];
+  s.T = a.T[p];
+  s.p = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) s.u[i] = a.u[(size_t)i * a.cs + p];
+#pragma unroll
+  for (int c = 0; c < ND * ND; ++c) M[c] = a.m[(size_t)c * a.cs + p];
+  double mu = 0.0, lam = 0.0, kap = 0.0, jac = 0.0;
+  double dT[ND][NU - 1];
+  if (a.viscous) {
+#pragma unroll
+    for (int c = 0; c < ND * ND; ++c) tau[c] = a.tau[(size_t)c * a.cs + p];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) q[i] = a.q[(size_t)i * a.cs + p];
+    mu = a.mu[p]; lam = a.lam[p]; kap = a.kap[p]; jac = a.jac[p];
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+#pragma unroll
+      for (int c = 0; c < NU - 1; ++c) dT[j][c] = a.dT[(size_t)(c + (NU - 1) * j) * a.cs + p];
+  }
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    double f1[NU], f2[NU];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) { f1[c] = 0.0; f2[c] = 0.0; }
+    add_flux_jacobian_apply<ND>(s, &M[ND * i], a.gamma, false, a.powerLaw, tau, q, dq, f1);        // A_i dQ
+    if (a.viscous) {
+      double ft[NU];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) ft[c] = 0.0;
+      add_flux_jacobian_apply<ND>(s, &M[ND * i], a.gamma, true, a.powerLaw, tau, q, dq, ft);       // (A_i - B1_i) dQ
+#pragma unroll
+      for (int c = 0; c < NU; ++c) f2[c] = f1[c] - ft[c];                                          // B1_i dQ
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        add_second_partial_apply<ND>(s.u, mu, lam, kap, jac, &M[ND * i], &M[ND * j], dT[j], &f2[1]);
+      if (a.Fv) {
+#pragma unroll
+        for (int c = 0; c < NU; ++c) a.Fv[(size_t)(c + NU * i) * a.cs + p] = f2[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NU; ++c) a.Fhat[(size_t)(c + NU * i) * a.cs + p] = f1[c] - f2[c];
+  }
+}
+
 struct AdjFinishArgs {
   const double *Q, *v, *u;
   const double* d;    // derivative of adjoint diffusion: component c + (NU-1)*j
@@ -695,18 +789,76 @@ int mg_state_cfl_dt_impl(mg_state* s, int wantDt, double given, double* result) 
 }
 
 // computeRhs for one grid/state (reference src/RegionImpl.f90:1877-2027)
+// computeRhsLinearized (reference src/RhsHelperImpl.f90:598-829)
+int mg_state_rhs_linearized_general(mg_state* s) {
+  mg_grid* g = s->grid;
+  const size_t N = g->N;
+  cudaStream_t st = mg_stream();
+  const int nD = s->nD, nU = s->nU;
+  MgField& A = g->scratchA;
+  MgField& B = g->scratchB;
+  const MgField& W = s->W[s->curW];
+  const MgField& Q = s->Q[s->cur];
+  if (g->procDims[2] > 1) MG_FAIL("general path: the linearized RHS is not available on slab-decomposed grids");
+  const bool keep = s->keepViscousFluxes && s->opt.viscosityOn;
+  if (keep && s->viscFluxCart.nComp < nU * nD) MG_TRY(mg_field_alloc(g, nU * nD, &s->viscFluxCart));
+  LinArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.Q = Q.comp(0); a.csQ = Q.compStride;
+  a.W = W.comp(0); a.csW = W.compStride;
+  a.v = s->specificVolume.comp(0);
+  a.u = s->velocity.comp(0);
+  a.T = s->temperature.comp(0);
+  a.m = g->metrics.comp(0);
+  a.jac = g->jacobian.comp(0);
+  a.cs = A.compStride;
+  a.N = N;
+  a.viscous = s->opt.viscosityOn;
+  a.gamma = s->opt.ratioOfSpecificHeats;
+  a.powerLaw = s->opt.powerLawExponent;
+  if (s->opt.viscosityOn) {
+    a.tau = s->stressTensor.comp(0);
+    a.q = s->heatFlux.comp(0);
+    a.mu = s->mu.comp(0);
+    a.lam = s->lambda.comp(0);
+    a.kap = s->kappa.comp(0);
+    a.t = B.comp(0);
+    MG_TRY(dispatch_nd(nD, [&](auto nd) {
+      k_linearized_primitive<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a);
+      return 0;
+    }));
+    MG_CUDA(cudaGetLastError());
+    for (int i = 0; i < nD; ++i)
+      MG_TRY(mg_grid_apply(g, g->firstDerivative[i], B.comp(0), B.compStride, A.comp((nU - 1) * i), A.compStride, nU - 1));
+    a.dT = A.comp(0);
+  }
+  a.Fhat = B.comp(0);
+  a.Fv = keep ? s->viscFluxCart.comp(0) : nullptr;
+  MG_TRY(dispatch_nd(nD, [&](auto nd) {
+    k_linearized_flux<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a);
+    return 0;
+  }));
+  MG_CUDA(cudaGetLastError());
+  if (keep) MG_TRY(mg_patches_collect_viscous(s));
+  for (int i = 0; i < nD; ++i)
+    MG_TRY(mg_grid_apply(g, g->firstDerivative[i], B.comp(nU * i), B.compStride, A.comp(nU * i), A.compStride, nU));
+  k_neg_sum<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), A.comp(0), A.compStride, nU, nD, N);
+  MG_CUDA(cudaGetLastError());
+  return add_dissipation_general(s, MG_LINEARIZED);
+}
+
 // computeRhs up to (not including) the multiplication by 1/J: the part that precedes the block-interface
 // exchange in the reference (src/RegionImpl.f90:1877-1925).  General path only.
 int mg_state_rhs_pre(mg_state* s, int mode) {
   mg_grid* g = s->grid;
   if (!g->updated) MG_FAIL("computeRhs: grid metrics have not been computed (mg_grid_update)");
-  if (mode != MG_FORWARD && mode != MG_ADJOINT) MG_FAIL("computeRhs: LINEARIZED mode is not implemented");
   MG_TRY(mg_halo_wait_pending());
   // The reference's callers run state%update after every substep (src/SolverImpl.f90:831-834); here
   // it is refreshed on demand.
   if (!s->dependentValid) MG_TRY(mg_state_update_impl(s, nullptr));
   if (mode == MG_FORWARD) MG_TRY(mg_state_rhs_forward_general(s));
-  else MG_TRY(mg_state_rhs_adjoint_general(s));
+  else if (mode == MG_ADJOINT) MG_TRY(mg_state_rhs_adjoint_general(s));
+  else MG_TRY(mg_state_rhs_linearized_general(s));
   return 0;
 }
 
@@ -750,7 +902,7 @@ int mg_state_rhs_post(mg_state* s, int mode) {
 int mg_state_compute_rhs_impl(mg_state* s, int mode) {
   mg_grid* g = s->grid;
   if (!g->updated) MG_FAIL("computeRhs: grid metrics have not been computed (mg_grid_update)");
-  if (mode != MG_FORWARD && mode != MG_ADJOINT) MG_FAIL("computeRhs: LINEARIZED mode is not implemented");
+  if (mode != MG_FORWARD && mode != MG_ADJOINT && mode != MG_LINEARIZED) MG_FAIL("computeRhs: unknown mode");
   if (s->useFused && mg_fused_supported(s, mode)) {
     // fused sweeps: the dependent variables live in the sweep-A outputs (no patches on this path)
     if (!s->fusedValid) MG_TRY(mg_fused_sweepA(s));
@@ -758,8 +910,10 @@ int mg_state_compute_rhs_impl(mg_state* s, int mode) {
     MG_TRY(mg_fused_adjoint1(s));
     return mg_fused_adjoint2(s, 0, 1, 0.0);
   }
-  if (mg_state_has_interfaces(s))
+  if (mg_state_has_interfaces(s)) {
+    if (mode == MG_LINEARIZED) MG_FAIL("computeRhs: the LINEARIZED mode of block-interface patches is not implemented");
     MG_FAIL("computeRhs: a state with block-interface patches must be evaluated through its region (mg_region_compute_rhs)");
+  }
   MG_TRY(mg_state_rhs_pre(s, mode));
   return mg_state_rhs_post(s, mode);
 }
@@ -837,8 +991,24 @@ int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int time
     k_rk4<<<nblocks(N), 256, 0, st>>>(a);
     if (stage == 4 || stage == 2) s->timeProgressive = *time;
     if (stage == 3 || stage == 1) { *time -= dt / 2.0; s->time = *time; }
+  } else if (mode == MG_LINEARIZED) {
+    // substepLinearizedRK4 (reference src/RK4IntegratorImpl.f90:272-369): the forward scheme on the perturbation
+    if (stage == 1) s->timeProgressive = *time + dt / 2.0;
+    if (stage == 2 || stage == 4) { *time += dt / 2.0; s->time = *time; }
+    if (stage == 3) s->timeProgressive = *time + dt / 2.0;
+    if (!s->rhsReady) MG_TRY(mg_state_compute_rhs_impl(s, MG_LINEARIZED));
+    s->rhsReady = false;
+    MG_TRY(mg_state_make_exclusive(s, &s->W[s->curW], true));
+    MG_TRY(mg_state_make_exclusive(s, &s->rk1, true));
+    a.b1 = s->rk1.comp(0);
+    a.R = s->rhs.comp(0);
+    a.Qin = s->W[s->curW].comp(0);
+    a.Qout = s->W[s->curW].comp(0);
+    a.stage = stage;
+    a.dt = dt;
+    k_rk4<<<nblocks(N), 256, 0, st>>>(a);
   } else {
-    MG_FAIL("rk4 substep: LINEARIZED mode is not implemented");
+    MG_FAIL("rk4 substep: unknown mode");
   }
   MG_CUDA(cudaGetLastError());
   return 0;

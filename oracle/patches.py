@@ -110,6 +110,14 @@ class FarFieldPatch(Patch):
                     state.temperature[idx, 0])
                 state.rightHandSide[idx] -= self.viscousPenaltyAmount * jac[:, None] * \
                     np.einsum("pji,pj->pi", B, w)
+        else:
+            # LINEARIZED (:258-268): the perturbation is state.adjointVariables; viscousFluxes holds the linearized
+            # contravariant viscous fluxes collected by computeRhsLinearized
+            state.rightHandSide[idx] -= self.inviscidPenaltyAmount * jac[:, None] * \
+                np.einsum("pij,pj->pi", A, state.adjointVariables[idx])
+            if opt.viscosityOn:
+                state.rightHandSide[idx] += self.viscousPenaltyAmount * jac[:, None] * \
+                    self.viscousFluxes[self.active][:, :, d]
 
 
 def addFarFieldAdjointPenalty(opt, grid, state, patches):
@@ -165,6 +173,8 @@ class SpongePatch(Patch):
             state.rightHandSide[idx] -= s * (state.conservedVariables[idx] - state.targetState[idx])
         elif mode == ADJOINT:
             state.rightHandSide[idx] += s * state.adjointVariables[idx]
+        else:
+            state.rightHandSide[idx] -= s * state.adjointVariables[idx]         # LINEARIZED (:142-160)
 
 
 def computeSpongeStrengths(patches, grid):
@@ -230,7 +240,7 @@ class ImpenetrableWall(Patch):
             pen[:, 1:nD + 1] = nm[:, None] * u
             pen[:, nD + 1] = nm * v * (Q[:, nD + 1] + state.pressure[idx, 0])
             state.rightHandSide[idx] -= self.inviscidPenaltyAmount * jac[:, None] * pen
-        elif mode == ADJOINT:
+        else:
             dp = np.zeros_like(Q)
             dp[:, 0] = 0.5 * np.sum(u ** 2, axis=1)
             dp[:, 1:nD + 1] = -u
@@ -241,8 +251,12 @@ class ImpenetrableWall(Patch):
             A = cns.computeJacobianOfInviscidFlux(nD, Q, m, g, v, uu, state.temperature[idx, 0])
             for l in range(nD):
                 A[:, l + 1, :] -= m[:, l, None] * dp
-            state.rightHandSide[idx] += self.inviscidPenaltyAmount * jac[:, None] * \
-                np.einsum("pji,pj->pi", A, state.adjointVariables[idx])
+            if mode == ADJOINT:
+                state.rightHandSide[idx] += self.inviscidPenaltyAmount * jac[:, None] * \
+                    np.einsum("pji,pj->pi", A, state.adjointVariables[idx])
+            else:                                                               # LINEARIZED (:187-191)
+                state.rightHandSide[idx] -= self.inviscidPenaltyAmount * jac[:, None] * \
+                    np.einsum("pij,pj->pi", A, state.adjointVariables[idx])
 
 
 class IsothermalWall(ImpenetrableWall):
@@ -287,6 +301,13 @@ class IsothermalWall(ImpenetrableWall):
             ap[:, 1:nD + 2] = w[:, 1:nD + 2]
             ap = jac[:, None] * ap
             state.rightHandSide[idx] += self.viscousPenaltyAmounts[0] * ap
+        else:                                                                   # LINEARIZED (:309-320)
+            dq = state.adjointVariables[idx]
+            pen = np.zeros_like(dq)
+            pen[:, 1:nD + 2] = dq[:, 1:nD + 2]
+            pen[:, nD + 1] = pen[:, nD + 1] - dq[:, 0] * Tw / g
+            pen = jac[:, None] * pen
+            state.rightHandSide[idx] -= self.viscousPenaltyAmounts[0] * pen
 
 
 class CostTargetPatch(Patch):
@@ -312,13 +333,15 @@ class ActuatorPatch(Patch):
     def __init__(self, name, grid, normalDirection, extent, opt):
         super().__init__(name, grid, normalDirection, extent)
         self.controlForcing = None      # (nPatchPoints, nU) when the controller switch is on
+        self.deltaControlForcing = None # the same for the LINEARIZED mode
 
     def updateRhs(self, mode, opt, grid, state):
         """``updateActuatorPatch`` (``src/ActuatorPatchImpl.f90:108-181``)."""
-        if mode != FORWARD or self.controlForcing is None:
+        f = self.controlForcing if mode == FORWARD else (self.deltaControlForcing if mode == LINEARIZED else None)
+        if f is None:
             return
         idx = self.gridIndex0[self.active]
-        state.rightHandSide[idx] += grid.controlMollifier[idx, 0:1] * self.controlForcing[self.active]
+        state.rightHandSide[idx] += grid.controlMollifier[idx, 0:1] * f[self.active]
 
 
 def updatePatches(patches, opt, grid, state):
