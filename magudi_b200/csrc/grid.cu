@@ -2,6 +2,7 @@
 // inner product.  Reference: src/GridImpl.f90:142-291 (setup), :487-619 (operators), :621-744
 // (coordinate derivatives), :746-1065 (updateGrid), :1067-1170 (inner products), :1172-1421 (gradient).
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 
 #include "mg_common.h"
@@ -322,6 +323,13 @@ int mg_grid_apply(mg_grid* g, mg_stencil* op, const double* in, size_t inCs, dou
   for (int i = 0; i < 3; ++i) a.n[i] = g->localSize[i];
   // direction 3 on a slab-decomposed grid reads the ghost planes of the padded field
   a.padded = (op->direction == 3 && g->procDims[2] > 1) ? 1 : 0;
+  if (a.padded) {
+    // fillGhostPoints (reference src/StencilOperatorImpl.f90:66): the input's ghost planes come from the k-neighbours
+    if (!g->halo)
+      MG_FAIL("operator application along a decomposed direction: no halo attached to the grid (mg_p2p_create); "
+              "the NCCL fallback only serves the fused sweeps");
+    MG_TRY(mg_p2p_exchange_view(g->halo, in, inCs, nComp, std::max(op->op.nGhost[0], op->op.nGhost[1])));
+  }
   return mg_apply_launch(op, a);
 }
 

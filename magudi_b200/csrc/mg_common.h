@@ -109,7 +109,11 @@ struct mg_grid {
   bool updated = false;
   // scratch
   MgField scratchA, scratchB;
+  // peer-to-peer halo of a slab-decomposed grid (set by mg_p2p_create): lets the operator-by-operator path fill
+  // the ghost planes of whatever array an operator is applied to along k
+  struct mg_p2p* halo = nullptr;
 };
+int mg_p2p_exchange_view(struct mg_p2p* h, const double* comp0, size_t compStride, int nComp, int width);
 
 int mg_field_alloc(const mg_grid* g, int nComp, MgField* f);
 void mg_field_free(MgField* f);

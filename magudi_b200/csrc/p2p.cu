@@ -11,6 +11,7 @@
 // The host only enqueues; the GPUs synchronise pairwise through the flags, so ranks may run ahead of each
 // other by up to two exchanges per face.
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
 
 #include "../../include/magudi_gpu.h"
@@ -167,6 +168,7 @@ int mg_p2p_create(mg_grid* g, int maxComp, int width, mg_p2p** out) {
   MG_CUDA(cudaMalloc(&h->error, sizeof(int)));
   MG_CUDA(cudaMemset(h->error, 0, sizeof(int)));
   MG_CUDA(cudaDeviceSynchronize());
+  g->halo = h;          // operator applications along k on this grid fill their ghost planes through it
   *out = h;
   return 0;
 }
@@ -197,6 +199,7 @@ int mg_p2p_connect(mg_p2p* h, int side, const void* peerHandle, int sameAsOther)
 }
 
 static int p2p_exchange_on(mg_p2p* h, void* owner, int field, int width, cudaStream_t st);
+static int p2p_exchange_field(mg_p2p* h, const MgField* f, int width, cudaStream_t st);
 
 // Exchange `width` ghost planes of a field with both k-neighbours.  Asynchronous on the library stream.
 int mg_p2p_exchange(mg_p2p* h, void* owner, int field, int width) {
@@ -227,9 +230,34 @@ int mg_p2p_exchange_overlapped(mg_p2p* h, void* owner, int field, int width) {
 
 static int p2p_exchange_on(mg_p2p* h, void* owner, int field, int width, cudaStream_t st) {
   if (!h) MG_FAIL("mg_p2p_exchange: null handle");
-  mg_grid* g = h->grid;
-  MgField* f = mg_lookup_field(g, owner, field);
+  MgField* f = mg_lookup_field(h->grid, owner, field);
   if (!f || !f->p) MG_FAIL("mg_p2p_exchange: unknown field");
+  return p2p_exchange_field(h, f, width, st);
+}
+
+// fillGhostPoints for an arbitrary (padded) array of the grid: what every operator application along the
+// decomposed direction does in the reference (src/StencilOperatorImpl.f90:66, src/MPIHelperImpl.f90:113-389).  Used
+// by the operator-by-operator path (mg_grid_apply); components are sent in batches that fit the staging buffers.
+int mg_p2p_exchange_view(mg_p2p* h, const double* comp0, size_t compStride, int nComp, int width) {
+  if (!h || !comp0) MG_FAIL("mg_p2p_exchange_view: null argument");
+  if (width <= 0) return 0;
+  MG_TRY(mg_halo_wait_pending());
+  const size_t chunk = h->grid->plane * (size_t)width;
+  int batch = (int)std::min<size_t>(MG_P2P_MAX_COMP, h->capacity / chunk);
+  if (batch < 1) MG_FAIL("mg_p2p_exchange_view: staging buffers are smaller than one component");
+  for (int c0 = 0; c0 < nComp; c0 += batch) {
+    MgField v;
+    v.p = const_cast<double*>(comp0) + (size_t)c0 * compStride;
+    v.nComp = std::min(batch, nComp - c0);
+    v.compStride = compStride;
+    v.interiorOffset = 0;
+    MG_TRY(p2p_exchange_field(h, &v, width, mg_stream()));
+  }
+  return 0;
+}
+
+static int p2p_exchange_field(mg_p2p* h, const MgField* f, int width, cudaStream_t st) {
+  mg_grid* g = h->grid;
   const size_t chunk = g->plane * (size_t)width;
   if (width > g->gk || width > g->localSize[2]) MG_FAIL("mg_p2p_exchange: width exceeds ghost capacity");
   if (f->nComp > MG_P2P_MAX_COMP || chunk * (size_t)f->nComp > h->capacity)
@@ -299,6 +327,7 @@ int mg_p2p_check(mg_p2p* h) {
 int mg_p2p_destroy(mg_p2p* h) {
   if (!h) return 0;
   cudaDeviceSynchronize();
+  if (h->grid && h->grid->halo == h) h->grid->halo = nullptr;
   for (int s = 0; s < 2; ++s)
     if (h->peerMapped[s] && h->peer[s]) cudaIpcCloseMemHandle(h->peer[s]);
   cudaFree(h->base);

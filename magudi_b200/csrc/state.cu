@@ -615,7 +615,6 @@ static int add_dissipation_general(mg_state* s, int mode) {
     const double* result = A.comp(0);
     if (!g->compositeDissipation) {
       k_scale_by<<<nblocks(N), 256, 0, st>>>(A.comp(0), A.compStride, s->nU, g->arcLengths.comp(i), -1.0, N);
-      if (g->procDims[2] > 1 && i == 2) MG_FAIL("general path: slab-decomposed dissipation needs the fused path");
       MG_TRY(mg_grid_apply(g, g->dissipationTranspose[i], A.comp(0), A.compStride, B.comp(0), B.compStride, s->nU));
       MG_TRY(mg_norm_launch(g->firstDerivative[i], B.comp(0), B.compStride, s->nU, g->localSize, 1, st));
       result = B.comp(0);
@@ -658,7 +657,6 @@ int mg_state_rhs_forward_general(mg_state* s) {
   MG_CUDA(cudaGetLastError());
   if (s->keepViscousFluxes && s->opt.viscosityOn) MG_TRY(mg_patches_collect_viscous(s));
   for (int i = 0; i < nD; ++i) {
-    if (g->procDims[2] > 1 && i == 2) MG_FAIL("general path: slab-decomposed flux derivative needs the fused path");
     MG_TRY(mg_grid_apply(g, g->firstDerivative[i], Fh.comp(nU * i), Fh.compStride, Dv.comp(nU * i), Dv.compStride, nU));
   }
   k_neg_sum<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), Dv.comp(0), Dv.compStride, nU, nD, N);
@@ -707,7 +705,6 @@ int mg_state_rhs_adjoint_general(mg_state* s) {
   MgField& B = g->scratchB;
   const MgField& W = s->W[s->curW];
   const MgField& Q = s->Q[s->cur];
-  if (g->procDims[2] > 1) MG_FAIL("general path: slab-decomposed adjoint needs the fused path");
   for (int i = 0; i < nD; ++i)
     MG_TRY(mg_grid_apply(g, g->adjointFirstDerivative[i], W.comp(0), W.compStride, A.comp(nU * i), A.compStride, nU));
   AdjArgs a;
@@ -799,7 +796,6 @@ int mg_state_rhs_linearized_general(mg_state* s) {
   MgField& B = g->scratchB;
   const MgField& W = s->W[s->curW];
   const MgField& Q = s->Q[s->cur];
-  if (g->procDims[2] > 1) MG_FAIL("general path: the linearized RHS is not available on slab-decomposed grids");
   const bool keep = s->keepViscousFluxes && s->opt.viscosityOn;
   if (keep && s->viscFluxCart.nComp < nU * nD) MG_TRY(mg_field_alloc(g, nU * nD, &s->viscFluxCart));
   LinArgs a;

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Run under torchrun (N ranks = N GPUs): slab-decomposed fused forward RK4 steps and one fused adjoint RK4 step must reproduce the
-single-GPU result of the same global problem.  Used by tests/test_gpu_multi.py and by hand:
+single-GPU result of the same global problem; so must the operator-by-operator path on a box with a NON-periodic k,
+curvilinear metrics, far-field / sponge / wall / cost-target patches (forward, adjoint and linearized RHS, one forward
+and one adjoint RK4 step), whose ghost planes are filled per operator application as in the reference.  Used by tests/test_gpu_multi.py and by hand:
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
 """
 import os
@@ -65,6 +67,102 @@ def run(shape, world, rank, dev, steps=2):
     return np.concatenate([state.conservedVariables, state.adjointVariables], axis=1), grid
 
 
+def general_coordinates(globalSize, offset, localSize):
+    n = globalSize
+    ax = [(offset[d] + np.arange(localSize[d])) * (2.0 * np.pi / (n[d] - 1)) for d in range(3)]
+    X, Y, Z = np.meshgrid(*ax, indexing="ij")
+    x = X + 0.05 * np.sin(Y) * 0.3
+    y = Y + 0.05 * np.sin(Z) * 0.3
+    z = Z + 0.05 * np.sin(X) * 0.3
+    return np.stack([a.reshape(-1, order="F") for a in (x, y, z)], axis=1)
+
+
+def general_fields(shape, seed):
+    """Global conserved / adjoint / target fields and sponge profile (same values whatever the decomposition)."""
+    rng = np.random.default_rng(seed)
+    N = int(np.prod(shape))
+
+    def state():
+        Q = np.zeros((N, 5))
+        Q[:, 0] = 1.0 + 0.1 * rng.random(N)
+        Q[:, 1:4] = 0.2 * (rng.random((N, 3)) - 0.5)
+        Q[:, 4] = 1.0 / 1.4 / 0.4 + 0.1 * rng.random(N) + 0.5 * np.sum(Q[:, 1:4] ** 2, axis=1) / Q[:, 0]
+        return Q.reshape(tuple(shape) + (5,), order="F")
+    return state(), rng.random(tuple(shape) + (5,)), state(), rng.random(tuple(shape)), rng.random(tuple(shape) + (5,))
+
+
+def run_general(shape, world, rank, dev):
+    """General path: SBP 2-4, viscous, curvilinear, k NOT periodic, patches on k and j faces."""
+    opt = core.SolverOptions(ratioOfSpecificHeats=1.4, viscosityOn=True, reynoldsNumberInverse=1.0 / 90.0,
+                             dissipationOn=True, compositeDissipation=False, dissipationAmount=0.01,
+                             useTargetState=True, discretizationType="SBP 2-4")
+    grid = core.Grid(1, shape, (core.NONE,) * 3, (0.0,) * 3, isCurvilinear=True, procDims=(1, 1, world),
+                     procCoords=(0, 0, rank))
+    grid.setupSpatialDiscretization(opt.discretizationType, opt.compositeDissipation, False, opt.dissipationOn)
+    grid.setCoordinates(general_coordinates(grid.globalSize, grid.offset, grid.localSize))
+    halo = par.GpuHalo(grid, rank, world, dev) if world > 1 else None
+    if halo:
+        assert halo.mode == "p2p", "the operator-by-operator path needs the P2P halo"
+        halo.exchange(None, core.G_COORDINATES, 3, 2)
+    assert not grid.update()
+    state = core.State(grid, opt)
+    region = core.Region()
+    region.addState(state)
+    region.setFused(False)
+    Qg, Wg, Tg, Sg, Fg = general_fields(shape, 7)
+    k0, nz = grid.offset[2], grid.localSize[2]
+    loc = lambda a: a[:, :, k0:k0 + nz].reshape(-1, a.shape[-1] if a.ndim == 4 else 1, order="F")
+    state.conservedVariables = loc(Qg)
+    state.adjointVariables = loc(Wg)
+    state.targetState = loc(Tg)
+    nx, ny, nzg = shape
+    specs = [("SAT_FAR_FIELD", "ff.k1", 3, [1, nx, 1, ny, 1, 1], 1.0, 0.7),
+             ("SAT_FAR_FIELD", "ff.kn", -3, [1, nx, 1, ny, nzg, nzg], 1.0, 0.7),
+             ("SPONGE", "sponge.k", -3, [1, nx, 1, ny, nzg - 9, nzg]),
+             ("SAT_ISOTHERMAL_WALL", "wall.j1", 2, [1, nx, 1, 1, 1, nzg], 1.0, 0.8),
+             ("SAT_SLIP_WALL", "wall.i1", 1, [1, 1, 1, ny, 1, nzg], 1.0, 0.0),
+             ("COST_TARGET", "target", 0, [4, nx - 3, 3, ny - 2, 5, nzg - 4])]
+    for sp in specs:
+        p = state.addPatch(*sp)
+        if p.nPatchPoints <= 0:
+            continue
+        idx = p.gridIndices()
+        if sp[0] == "SPONGE":
+            p.setArray("spongeStrength", loc(Sg)[idx, 0])
+        if sp[0] == "SAT_ISOTHERMAL_WALL":
+            p.setArray("temperature", 2.5 + 0.1 * loc(Sg)[idx, 0])
+        if sp[0] == "COST_TARGET":
+            p.setArray("adjointForcing", loc(Fg)[idx])
+    region.updatePatches()
+    out = []
+    for mode in (mb.FORWARD, mb.ADJOINT, mb.LINEARIZED):
+        region.computeRhs(mode)
+        out.append(state.rightHandSide.copy())
+    integ = mb.RK4Integrator(region)
+    t = 0.0
+    for stage in range(1, 5):
+        t = integ.substepForward(t, 2e-3, 0, stage)
+    for stage in range(4, 0, -1):
+        t = integ.substepAdjoint(t, 2e-3, 0, stage)
+    out += [state.conservedVariables, state.adjointVariables]
+    if halo:
+        halo.check()
+    return np.concatenate(out, axis=1), grid
+
+
+def compare(pieces, single, shape, ncomp, label, world, tol):
+    Qs = single.reshape(tuple(shape) + (ncomp,), order="F")
+    err = 0.0
+    for k0, nz, q in pieces:
+        q = q.reshape((shape[0], shape[1], nz, ncomp), order="F")
+        ref = Qs[:, :, k0:k0 + nz]
+        for c0 in range(0, ncomp, 5):
+            sl = slice(c0, c0 + 5)
+            err = max(err, float(np.max(np.abs(q[..., sl] - ref[..., sl])) / np.max(np.abs(Qs[..., sl]))))
+    print(f"multi_gpu_check: world={world} {label}: max rel diff vs single GPU = {err:.3e}")
+    return err <= tol
+
+
 def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -91,6 +189,15 @@ def main():
                     err = max(err, float(np.max(np.abs(q[..., sl] - ref[..., sl])) / np.max(np.abs(Qs[..., sl]))))
             print(f"multi_gpu_check: world={world} max rel diff vs single GPU = {err:.3e}")
             ok = err <= 1e-13
+        # operator-by-operator path with patches and a non-periodic k
+        gshape = (20, 18, 13 * world + 3)
+        Gl, ggrid = run_general(gshape, world, rank, dev)
+        gpieces = [None] * world
+        dist.all_gather_object(gpieces, (ggrid.offset[2], ggrid.localSize[2], Gl))
+        if rank == 0:
+            Gs, _ = run_general(gshape, 1, 0, dev)
+            ok = compare(gpieces, Gs, gshape, 25, "general path (patches, non-periodic k; fwd/adj/lin RHS + RK4)",
+                         world, 1e-12) and ok
         dist.barrier()
         dist.destroy_process_group()
     else:
