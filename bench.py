@@ -359,6 +359,15 @@ def run_native(args):
                "ms_per_step": esec * 1e3, "timer": "host wall clock around set(pinned)->step->get, max over ranks; the H2D of w overlaps the forward "
                         "step and the D2H of the final Q overlaps the adjoint step (copy stream)"}
 
+    # ---- multi-rank parity, in the same run: the slab-decomposed fused forward + adjoint RK4 steps and the
+    # operator-by-operator path with patches reproduce the single-GPU result of the same (small) global problem
+    parity = None
+    if world > 1 and not args.no_parity:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("multi_gpu_check", os.path.join(ROOT, "tools", "multi_gpu_check.py"))
+        mgc = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mgc)
+        parity = mgc.check_all(world, rank, dev)
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
@@ -418,9 +427,110 @@ def run_native(args):
         "roofline_path": path, "kernels": prof, "cpu_baseline": cpu,
         "step_minus_kernel_sum_ms": gap_ms / args.steps,
         "halo_overlap": (os.environ.get("MG_OVERLAP", "1") != "0") if world > 1 else None,
+        "parity": parity,
         "wall_s_timed_region": wall,
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ C1 / C2 workload
+# algorithmic bytes per point and stage of the 2-D viscous rectilinear case (SURVEY.md 8(d) with nU = 4, G = 3):
+# forward: sweep A (4+3+5) + sweep B (4+5+3+16) doubles; adjoint: A 12 + B' (4+4+5+3+4+6) + C (6+4+4+3+16) + checkpoint 8
+BYTES_C1_FORWARD = (12 + 28) * 8.0
+BYTES_C1_ADJOINT = (12 + 26 + 33 + 8) * 8.0
+
+
+def run_c1(args):
+    """BASELINE configs C1 / C2 (examples/AcousticMonopole, 201 x 201, 800 steps, dt 0.05, save interval 200) through
+    the forward / adjoint drivers.  Far-field + sponge patches, the monopole source, the cost functional and the
+    control gradient are all on the path, which therefore runs operator by operator (the fused sweeps do not take
+    patches yet): launch-latency bound at 40 401 points.  One "step" = one forward + one adjoint time step."""
+    import torch
+    import magudi_b200 as mb
+    from magudi_b200 import _lib, core, solver as gsol, workload as wl
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"metric": METRIC, "workload": "c1", "unavailable": "C1 is a single-GPU configuration (40 401 points)"}))
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    lib = _lib.init(0)
+    T, S = args.c1_steps, args.c1_save
+    opt, grid, state, region, Q0 = wl.build_c1(args.c1_n)
+    sol = gsol.Solver(region, state, 0.05, T, S)
+    N = grid.nGridPoints
+    sampler = ClockSampler(0)
+    sampler.start()
+    reps_w, reps = max(1, min(args.warmup, 1)), max(1, min(args.steps, 3))
+    for _ in range(reps_w):
+        sol.runForward(Q0)
+        sol.runAdjoint()
+    _lib.check(lib.mg_synchronize())
+    launches0 = lib.mg_kernel_launch_count()
+    tf = ta = 0.0
+    for _ in range(reps):
+        c0 = time.perf_counter()
+        J = sol.runForward(Q0)
+        _lib.check(lib.mg_synchronize())
+        c1 = time.perf_counter()
+        sens, grad = sol.runAdjoint()
+        _lib.check(lib.mg_synchronize())
+        c2 = time.perf_counter()
+        tf += c1 - c0
+        ta += c2 - c1
+    launches = lib.mg_kernel_launch_count() - launches0
+    clocks = sampler.stop()
+    tf /= reps
+    ta /= reps
+    peak, peak_src = measured_peaks()
+    fwd_rate = 4.0 * T * N / tf
+    # the adjoint run also replays the forward march window by window (4 T more forward evaluations): counted as work
+    adj_rate = (4.0 * T * N + 4.0 * T * N) / ta
+    value = 8.0 * T * N / (tf + ta)
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_c1_rate(args.c1_n)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": reps * T, "warmup": reps_w * T,
+        "ms_per_step": (tf + ta) / T * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C1/C2 AcousticMonopole {args.c1_n}x{args.c1_n} ({N} points), {T} time steps, dt 0.05, "
+                               f"save interval {S}: forward run (J) + adjoint run (cost sensitivity, gradient)",
+                   "path": "fused" if region.usesFused(mb.FORWARD) else "operator by operator (patches present)",
+                   "evals_per_point_per_step": 8,
+                   "l2_policy": "working set (a few MB) is L2 resident by nature of the configuration; nothing is flushed"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(N * 4 * 8 / T), "d2h_bytes_per_step": int(grad.size * 8 / T),
+                "timer": "host wall clock around Solver.runForward(host Q0) + Solver.runAdjoint() -> host gradient; the "
+                         "device-timed value IS this number: the drivers synchronise every substep for J and the gradient sample"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "whole path (no dominant kernel: ~40 small launches per stage)",
+                     "achieved": (fwd_rate * BYTES_C1_FORWARD * tf + 0.5 * adj_rate * BYTES_C1_ADJOINT * ta) / (tf + ta) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                     "note": "launch-latency bound, not bandwidth bound: 40 401 points per launch"},
+        "roofline_path": {"forward": {"point_stages_per_s_per_gpu": fwd_rate, "bytes_model": BYTES_C1_FORWARD,
+                                      "frac_of_hbm_peak": fwd_rate * BYTES_C1_FORWARD / 1e9 / peak, "s": tf},
+                          "adjoint": {"point_stages_per_s_per_gpu": 4.0 * T * N / ta, "bytes_model": BYTES_C1_ADJOINT,
+                                      "frac_of_hbm_peak": 4.0 * T * N / ta * BYTES_C1_ADJOINT / 1e9 / peak, "s": ta,
+                                      "note": "plus the forward replay of every checkpoint window"}},
+        "J": J, "cost_sensitivity": sens, "cpu_baseline": cpu,
+    }
+    line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
+    print(json.dumps(line))
+
+
+def cpu_c1_rate(n, steps=4):
+    """Bounded CPU sample of C1: the NumPy oracle drivers, `steps` forward + adjoint time steps of the same case."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import solver as osol
+    import test_solver_drivers as tsd
+    g, opt, s, plist, specs, src, meanP, Q0 = tsd.oracle_setup(n)
+    sol = osol.Solver(opt, g, s, plist, meanP, 0.05, steps, steps)
+    c0 = time.perf_counter()
+    sol.runForward(Q0)
+    sol.runAdjoint()
+    el = time.perf_counter() - c0
+    return {"value": 8.0 * steps * g.nGridPoints / el, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"NumPy oracle drivers, AcousticMonopole {n}x{n}, {steps} forward + adjoint time steps ({el:.1f} s)"}
 
 
 def main():
@@ -432,9 +542,17 @@ def main():
     ap.add_argument("--size", type=int, default=0, help="override: size^3 points per GPU")
     ap.add_argument("--cpu-size", type=int, default=128, help="edge of the bounded CPU sample box")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-rank parity check that follows the timing")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1"],
+                    help="c3: the headline 3-D periodic box (default); c1: AcousticMonopole forward + adjoint run")
+    ap.add_argument("--c1-n", type=int, default=201)
+    ap.add_argument("--c1-steps", type=int, default=800)
+    ap.add_argument("--c1-save", type=int, default=200)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c1":
+        run_c1(args)
     else:
         run_native(args)
 

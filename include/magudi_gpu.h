@@ -227,7 +227,7 @@ int mg_state_checkpoint_clear(mg_state* s);
 /* ------------------------------------------------------------------ t_Patch */
 /* %setup: src/PatchImpl.f90:3-151 and the derived types' setup; amounts are the magudi.inp values
  * (defaults/inviscid_penalty_amount, .../viscous_penalty_amount); sign and 1/normBoundary(1) are
- * applied here as in src/FarFieldPatchImpl.f90:53-69. */
+ * applied here as in src/FarFieldPatchImpl.f90:53-69.  SPONGE: sponge_amount, sponge_exponent. */
 int mg_patch_create(mg_state* s, int type, const char* name, int normalDirection, const int extent[6],
                     double inviscidPenaltyAmount, double viscousPenaltyAmount, mg_patch** out);
 int mg_patch_num_points(const mg_patch* p, int* nPatchPoints, int localSize[3], int patchOffset[3]);
@@ -252,6 +252,11 @@ int mg_region_destroy(mg_region* r);
 int mg_region_add_state(mg_region* r, mg_state* s);
 /* updatePatchFactories: src/PatchFactoryImpl.f90:446-574 (target viscous fluxes of far-field patches) */
 int mg_region_update_patches(mg_region* r);
+/* computeSpongeStrengths: src/PatchFactoryImpl.f90:161-374 -- fills the "spongeStrength" array of every SPONGE
+ * patch from the grid's arc lengths.  For SPONGE patches mg_patch_create's two amounts are sponge_amount and
+ * sponge_exponent (src/SpongePatchImpl.f90:40-45; reference defaults 1.0 and 2).  Sponges along a decomposed
+ * direction are refused (set "spongeStrength" with mg_patch_set_array instead). */
+int mg_region_compute_sponge_strengths(mg_region* r);
 /* %computeRhs(mode, timestep, stage): src/RegionImpl.f90:1877-2027.  MG_MODE_LINEARIZED evaluates
  * computeRhsLinearized (src/RhsHelperImpl.f90:598-829) and the LINEARIZED branches of the patches: the perturbation
  * is the state's adjointVariables, as in the reference. */

@@ -117,6 +117,7 @@ SIGNATURES = {
     "mg_region_create": (C.c_int, [C.POINTER(_P)]),
     "mg_region_destroy": (C.c_int, [_P]),
     "mg_region_add_state": (C.c_int, [_P, _P]),
+    "mg_region_compute_sponge_strengths": (C.c_int, [_P]),
     "mg_region_update_patches": (C.c_int, [_P]),
     "mg_region_compute_rhs": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "mg_rk4_substep": (C.c_int, [_P, C.c_int, _D, C.c_double, C.c_int, C.c_int, C.c_int]),

@@ -508,6 +508,11 @@ class Region:
     def updatePatches(self):
         check(L.lib().mg_region_update_patches(self._h))
 
+    def computeSpongeStrengths(self):
+        """``computeSpongeStrengths`` (``src/PatchFactoryImpl.f90:161-374``) for every SPONGE patch of the region
+        (``addPatch("SPONGE", name, normalDirection, extent, spongeAmount, spongeExponent)``)."""
+        check(L.lib().mg_region_compute_sponge_strengths(self._h))
+
     def computeRhs(self, mode, timestep=0, stage=1):
         check(L.lib().mg_region_compute_rhs(self._h, int(mode), int(timestep), int(stage)))
 

@@ -646,6 +646,10 @@ int mg_patch_create(mg_state* s, int type, const char* name, int normalDirection
   if (!s || !out) MG_FAIL("mg_patch_create: null argument");
   MG_TRY(mg_patch_create_impl(s, type, name, normalDirection, extent, out));
   mg_patch* p = *out;
+  if (type == MG_PATCH_SPONGE) {     // the two amounts carry sponge_amount and sponge_exponent
+    p->spongeAmount = inviscidPenaltyAmount;
+    p->spongeExponent = (int)std::lround(viscousPenaltyAmount);
+  }
   const int ad = std::abs(normalDirection);
   if (ad >= 1 && ad <= s->nD && s->grid->firstDerivative[ad - 1]) {
     const double h = s->grid->firstDerivative[ad - 1]->op.normBoundary[0];
@@ -737,6 +741,11 @@ int mg_region_add_state(mg_region* r, mg_state* s) {
 int mg_region_update_patches(mg_region* r) {
   if (!r) MG_FAIL("mg_region_update_patches: null handle");
   for (mg_state* s : r->states) MG_TRY(mg_patches_update_impl(s));
+  return 0;
+}
+int mg_region_compute_sponge_strengths(mg_region* r) {
+  if (!r) MG_FAIL("mg_region_compute_sponge_strengths: null handle");
+  for (mg_state* s : r->states) MG_TRY(mg_patches_sponge_strengths_impl(s));
   return 0;
 }
 int mg_region_set_fused(mg_region* r, int enable) {

@@ -334,7 +334,7 @@ int mg_grid_apply(mg_grid* g, mg_stencil* op, const double* in, size_t inCs, dou
 }
 
 // computeCoordinateDerivatives (reference :621-744)
-static int coordinate_derivatives(mg_grid* g, int dir, MgField* out) {
+int mg_grid_coordinate_derivatives(mg_grid* g, int dir, MgField* out) {
   mg_stencil* D = g->firstDerivative[dir];
   ApplyArgs a;
   a.in = g->coordinates.comp(0);
@@ -364,7 +364,7 @@ int mg_grid_update_impl(mg_grid* g, int* hasNegativeJacobian) {
   MgField Ji[3], F, T;
   for (int j = 0; j < nD; ++j) {
     MG_TRY(mg_field_alloc(g, nD, &Ji[j]));
-    MG_TRY(coordinate_derivatives(g, j, &Ji[j]));
+    MG_TRY(mg_grid_coordinate_derivatives(g, j, &Ji[j]));
   }
   bool anyPlane = false;
   for (int i = 0; i < nD; ++i) anyPlane = anyPlane || g->periodicityType[i] == MG_PERIODIC_PLANE;
@@ -380,7 +380,7 @@ int mg_grid_update_impl(mg_grid* g, int* hasNegativeJacobian) {
   ma.nD = nD;
   ma.curvilinear = g->isCurvilinear;
   ma.planeFormulas = anyPlane;
-  k_metrics<<<nblocks(N), 256, 0, st>>>(ma);
+  { k_metrics<<<nblocks(N), 256, 0, st>>>(ma); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   if (nD == 3) {
     if (!anyPlane) {
@@ -398,15 +398,15 @@ int mg_grid_update_impl(mg_grid* g, int* hasNegativeJacobian) {
       for (const Term& t : terms) {
         double* mq = g->metrics.comp(t.q);
         if (!g->isCurvilinear && !diag[t.q]) {
-          k_fill<<<nblocks(N), 256, 0, st>>>(mq, 0.0, N);
+          { k_fill<<<nblocks(N), 256, 0, st>>>(mq, 0.0, N); mg_count_launches(1); }
           continue;
         }
-        k_mul<<<nblocks(N), 256, 0, st>>>(F.comp(0), JiPtr(t.j1), g->coordinates.comp(t.c1), N);
+        { k_mul<<<nblocks(N), 256, 0, st>>>(F.comp(0), JiPtr(t.j1), g->coordinates.comp(t.c1), N); mg_count_launches(1); }
         MG_TRY(mg_grid_apply(g, g->firstDerivative[t.d1], F.comp(0), F.compStride, mq, g->metrics.compStride, 1));
         if (g->isCurvilinear) {
-          k_mul<<<nblocks(N), 256, 0, st>>>(F.comp(0), JiPtr(t.j2), g->coordinates.comp(t.c2), N);
+          { k_mul<<<nblocks(N), 256, 0, st>>>(F.comp(0), JiPtr(t.j2), g->coordinates.comp(t.c2), N); mg_count_launches(1); }
           MG_TRY(mg_grid_apply(g, g->firstDerivative[t.d2], F.comp(0), F.compStride, T.comp(0), T.compStride, 1));
-          k_sub<<<nblocks(N), 256, 0, st>>>(mq, T.comp(0), N);
+          { k_sub<<<nblocks(N), 256, 0, st>>>(mq, T.comp(0), N); mg_count_launches(1); }
         }
       }
       MG_CUDA(cudaGetLastError());
@@ -416,20 +416,20 @@ int mg_grid_update_impl(mg_grid* g, int* hasNegativeJacobian) {
     double** d_mp = nullptr;
     MG_CUDA(cudaMalloc(&d_mp, sizeof(mp)));
     MG_CUDA(cudaMemcpyAsync(d_mp, mp, sizeof(mp), cudaMemcpyHostToDevice, st));
-    k_arc3<<<nblocks(N), 256, 0, st>>>(d_mp, g->arcLengths.comp(0), g->arcLengths.comp(1), g->arcLengths.comp(2),
-                                       g->iblank, N, g->isCurvilinear);
+    { k_arc3<<<nblocks(N), 256, 0, st>>>(d_mp, g->arcLengths.comp(0), g->arcLengths.comp(1), g->arcLengths.comp(2),
+                                       g->iblank, N, g->isCurvilinear); mg_count_launches(1); }
     MG_CUDA(cudaGetLastError());
     MG_CUDA(cudaStreamSynchronize(st));
     cudaFree(d_mp);
   }
   // norm = prod_dir H_dir * J, then jacobian <- 1/J (reference :1054-1063)
-  k_fill<<<nblocks(N), 256, 0, st>>>(g->norm.comp(0), 1.0, N);
+  { k_fill<<<nblocks(N), 256, 0, st>>>(g->norm.comp(0), 1.0, N); mg_count_launches(1); }
   for (int i = 0; i < nD; ++i)
     MG_TRY(mg_norm_launch(g->firstDerivative[i], g->norm.comp(0), g->norm.compStride, 1, g->localSize, 0, st));
   int* d_flag = nullptr;
   MG_CUDA(cudaMalloc(&d_flag, sizeof(int)));
   MG_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
-  k_norm_finish<<<nblocks(N), 256, 0, st>>>(g->norm.comp(0), g->jacobian.comp(0), N, d_flag);
+  { k_norm_finish<<<nblocks(N), 256, 0, st>>>(g->norm.comp(0), g->jacobian.comp(0), N, d_flag); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   int flag = 0;
   MG_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -463,7 +463,7 @@ int mg_grid_gradient_dev(mg_grid* g, const double* f, size_t fCs, int nComp, MgF
   a.nComp = nComp;
   a.curvilinear = g->isCurvilinear;
   if (scratch->compStride != out->compStride) MG_FAIL("gradient: stride mismatch");
-  k_gradient<<<nblocks(g->N), 256, 0, mg_stream()>>>(a);
+  { k_gradient<<<nblocks(g->N), 256, 0, mg_stream()>>>(a); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -477,7 +477,7 @@ int mg_grid_inner_product_dev(mg_grid* g, const double* f, const double* gg, con
     MG_CUDA(cudaMalloc(&d_partial, blocks * sizeof(double)));
     MG_CUDA(cudaMallocHost(&h_partial, blocks * sizeof(double)));
   }
-  k_inner<<<blocks, 256, 0, mg_stream()>>>(f, gg, g->norm.comp(0), weight, cs, nComp, g->N, d_partial);
+  { k_inner<<<blocks, 256, 0, mg_stream()>>>(f, gg, g->norm.comp(0), weight, cs, nComp, g->N, d_partial); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   MG_CUDA(cudaMemcpyAsync(h_partial, d_partial, blocks * sizeof(double), cudaMemcpyDeviceToHost, mg_stream()));
   MG_CUDA(cudaStreamSynchronize(mg_stream()));

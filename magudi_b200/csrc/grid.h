@@ -62,6 +62,8 @@ struct mg_state {
   }
 };
 
+// computeCoordinateDerivatives (reference src/GridImpl.f90:621-744): d(coordinates)/d(xi_dir), nD components
+int mg_grid_coordinate_derivatives(mg_grid* g, int dir, MgField* out);
 int mg_state_create_impl(mg_grid* g, const mg_options_t* opt, mg_state** out);
 void mg_state_destroy_impl(mg_state* s);
 int mg_state_update_impl(mg_state* s, const MgField* Qoverride);

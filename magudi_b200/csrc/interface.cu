@@ -404,7 +404,7 @@ int collect_to(mg_patch* p, const double* f, size_t cs, int nComp, const char* n
   double* d = nullptr;
   MG_TRY(mg_patch_alloc_array(p, name, nComp, &d));
   if (p->nPatchPoints == 0) return 0;
-  k_collect<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), f, cs, nComp, d);
+  { k_collect<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), f, cs, nComp, d); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -416,8 +416,8 @@ int receive(mg_patch* p, const char* partnerName, const char* myName, int nComp)
   double* dst = nullptr;
   MG_TRY(mg_patch_alloc_array(p, myName, nComp, &dst));
   if (p->nPatchPoints == 0) return 0;
-  k_receive<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(p->globalSize[0], p->globalSize[1], p->globalSize[2],
-                                                              p->reorder[0], p->reorder[1], nComp, src, dst);
+  { k_receive<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(p->globalSize[0], p->globalSize[1], p->globalSize[2],
+                                                              p->reorder[0], p->reorder[1], nComp, src, dst); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -501,8 +501,8 @@ int mg_interfaces_exchange(const std::vector<mg_state*>& states, int mode) {
         double* out = nullptr;
         MG_TRY(mg_patch_alloc_array(p, "viscousFluxesL", s->nU, &out));
         if (p->nPatchPoints)
-          k_normal_viscous_flux<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(p->nPatchPoints, s->nU, s->nD, Fc,
-                                                                                  arr(p, "metricsL"), out);
+          { k_normal_viscous_flux<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(p->nPatchPoints, s->nU, s->nD, Fc,
+                                                                                  arr(p, "metricsL"), out); mg_count_launches(1); }
       }
     } else {
       const MgField& W = s->W[s->curW];
@@ -564,7 +564,7 @@ int mg_interface_apply(mg_state* s, mg_patch* p, int mode) {
   a.gamma = s->opt.ratioOfSpecificHeats;
   a.powerLaw = s->opt.powerLawExponent;
   MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
-    k_interface<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a);
+    { k_interface<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a); mg_count_launches(1); }
     return 0;
   }));
   MG_CUDA(cudaGetLastError());
@@ -594,7 +594,7 @@ int mg_interfaces_adjoint_sources(mg_state* s, MgField* temp1) {
     a.sigmaVL = p->sigmaVL;
     a.sigmaVR = p->sigmaVR;
     MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
-      k_interface_adjoint_source<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a);
+      { k_interface_adjoint_source<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a); mg_count_launches(1); }
       return 0;
     }));
   }

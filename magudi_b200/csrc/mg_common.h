@@ -136,3 +136,4 @@ void mg_profile_suppress(bool on);
 int mg_tuning_get(const char* name, int dflt);
 bool mg_tuning_has(const char* name);
 int mg_num_sms();
+void mg_count_launches(int n);   // kernels launched by the library (mg_kernel_launch_count)

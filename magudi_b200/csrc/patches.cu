@@ -353,6 +353,44 @@ __global__ void k_disperse(PatchGeom g, const double* in, size_t cs, int nComp, 
   for (int c = 0; c < nComp; ++c) field[(size_t)c * cs + p] = in[(size_t)c * g.n + q];
 }
 
+// computeSpongeStrengths (reference src/PatchFactoryImpl.f90:161-374): fraction of the arc length, measured along
+// the sponge's direction from its inner edge, raised to sponge_exponent and scaled by sponge_amount.
+struct SpongeSetupArgs {
+  PatchGeom g;
+  const double* arc;     // sqrt(sum (d coordinates / d xi_dir)^2), grid field
+  long stride;           // grid stride along the direction
+  int dir, eLo, eHi;     // direction, 0-based local extent [eLo, eHi] of the whole patch along it
+  int normalDirection, exponent;
+  double amount;
+  double* out;
+};
+
+__global__ void k_sponge_strength(SpongeSetupArgs a) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.g.n) return;
+  const size_t p = a.g.gridIndex(q);
+  const int cl[3] = {a.g.lo[0] + q % a.g.sz[0], a.g.lo[1] + (q / a.g.sz[0]) % a.g.sz[1], a.g.lo[2] + q / (a.g.sz[0] * a.g.sz[1])};
+  const int c = cl[a.dir];
+  const double* line = a.arc + (long)p - (long)c * a.stride;     // coordinate 0 of this grid line
+  double num = 0.0, den = 0.0;
+  if (a.normalDirection > 0) {
+    for (int l = a.eLo; l <= c - 1; ++l) num += line[(long)l * a.stride];
+    for (int l = a.eLo; l <= a.eHi - 1; ++l) den += line[(long)l * a.stride];
+  } else {
+    for (int l = c + 1; l <= a.eHi; ++l) num += line[(long)l * a.stride];
+    for (int l = a.eLo + 1; l <= a.eHi; ++l) den += line[(long)l * a.stride];
+  }
+  a.out[q] = a.amount * pow(1.0 - num / den, (double)a.exponent);
+}
+
+__global__ void k_arc_from_derivatives(const double* d, size_t cs, int nD, double* arc, size_t N) {
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  double s = 0.0;
+  for (int i = 0; i < nD; ++i) s += d[(size_t)i * cs + p] * d[(size_t)i * cs + p];
+  arc[p] = sqrt(s);
+}
+
 PatchGeom geom(const mg_patch* pt) {
   PatchGeom g;
   for (int i = 0; i < 3; ++i) { g.lo[i] = pt->localLo[i]; g.sz[i] = pt->localSize[i]; }
@@ -455,7 +493,7 @@ int mg_patch_collect_impl(mg_patch* p, const MgField* f, int nComp, const char* 
   double* d = nullptr;
   MG_TRY(mg_patch_alloc_array(p, name, nComp, &d));
   if (p->nPatchPoints == 0) return 0;
-  k_collect<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), f->comp(0), f->compStride, nComp, d);
+  { k_collect<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), f->comp(0), f->compStride, nComp, d); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -464,7 +502,7 @@ int mg_patch_disperse_impl(mg_patch* p, const char* name, int nComp, MgField* f)
   auto it = p->arrays.find(name);
   if (it == p->arrays.end() || it->second.nComp != nComp) MG_FAIL(std::string("mg_patch_disperse: no array '") + name + "'");
   if (p->nPatchPoints == 0) return 0;
-  k_disperse<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), it->second.p, f->compStride, nComp, f->comp(0));
+  { k_disperse<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), it->second.p, f->compStride, nComp, f->comp(0)); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -505,6 +543,46 @@ int mg_patches_update_impl(mg_state* s) {
   return 0;
 }
 
+int mg_patches_sponge_strengths_impl(mg_state* s) {
+  mg_grid* g = s->grid;
+  for (int dir = 0; dir < s->nD; ++dir) {
+    bool any = false;
+    for (mg_patch* p : s->patches) any = any || (p->type == MG_PATCH_SPONGE && std::abs(p->normalDirection) == dir + 1);
+    if (!any) continue;
+    if (g->procDims[dir] > 1)
+      MG_FAIL("computeSpongeStrengths: sponges along a decomposed direction need the arc length of the whole line; "
+              "set the patch array \"spongeStrength\" instead");
+    MgField cd, arc;
+    MG_TRY(mg_field_alloc(g, s->nD, &cd));
+    MG_TRY(mg_field_alloc(g, 1, &arc));
+    MG_TRY(mg_grid_coordinate_derivatives(g, dir, &cd));
+    { k_arc_from_derivatives<<<(unsigned)((g->N + 255) / 256), 256, 0, mg_stream()>>>(cd.comp(0), cd.compStride, s->nD, arc.comp(0), g->N); mg_count_launches(1); }
+    MG_CUDA(cudaGetLastError());
+    for (mg_patch* p : s->patches) {
+      if (p->type != MG_PATCH_SPONGE || std::abs(p->normalDirection) != dir + 1 || p->nPatchPoints <= 0) continue;
+      double* out = nullptr;
+      MG_TRY(mg_patch_alloc_array(p, "spongeStrength", 1, &out));
+      SpongeSetupArgs a;
+      a.g = geom(p);
+      a.arc = arc.comp(0);
+      a.stride = dir == 0 ? 1 : (dir == 1 ? (long)g->localSize[0] : (long)g->plane);
+      a.dir = dir;
+      a.eLo = p->extent[2 * dir] - 1 - g->offset[dir];
+      a.eHi = p->extent[2 * dir + 1] - 1 - g->offset[dir];
+      a.normalDirection = p->normalDirection;
+      a.exponent = p->spongeExponent;
+      a.amount = p->spongeAmount;
+      a.out = out;
+      { k_sponge_strength<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a); mg_count_launches(1); }
+      MG_CUDA(cudaGetLastError());
+    }
+    MG_CUDA(cudaStreamSynchronize(mg_stream()));
+    mg_field_free(&cd);
+    mg_field_free(&arc);
+  }
+  return 0;
+}
+
 int mg_patches_farfield_adjoint_sources(mg_state* s, MgField* temp1) {
   mg_grid* g = s->grid;
   for (mg_patch* p : s->patches) {
@@ -525,7 +603,7 @@ int mg_patches_farfield_adjoint_sources(mg_state* s, MgField* temp1) {
     a.dir = std::abs(p->normalDirection) - 1;
     a.sigmaV = p->viscousPenaltyAmount;
     MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
-      k_farfield_adjoint_source<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a);
+      { k_farfield_adjoint_source<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a); mg_count_launches(1); }
       return 0;
     }));
     MG_CUDA(cudaGetLastError());
@@ -550,9 +628,9 @@ int mg_patches_apply(mg_state* s, int mode) {
         const int incoming = (mode == MG_ADJOINT && s->opt.useContinuousAdjoint) ? -p->normalDirection : p->normalDirection;
         if (!p->AplusReady || p->AplusIncoming != incoming) {
           MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
-            k_farfield_setup<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, st>>>(
+            { k_farfield_setup<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, st>>>(
                 geom(p), s->target.comp(0), s->target.compStride, g->metrics.comp(0), g->metrics.compStride, dir,
-                s->opt.ratioOfSpecificHeats, incoming, Aplus);
+                s->opt.ratioOfSpecificHeats, incoming, Aplus); mg_count_launches(1); }
             return 0;
           }));
           p->AplusReady = true;
@@ -597,7 +675,7 @@ int mg_patches_apply(mg_state* s, int mode) {
           }
         }
         MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
-          k_farfield<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, st>>>(a);
+          { k_farfield<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, st>>>(a); mg_count_launches(1); }
           return 0;
         }));
         break;
@@ -616,7 +694,7 @@ int mg_patches_apply(mg_state* s, int mode) {
         a.cs = s->rhs.compStride;
         a.nU = s->nU;
         a.mode = mode;
-        k_sponge<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a);
+        { k_sponge<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a); mg_count_launches(1); }
         break;
       }
       case MG_PATCH_SLIP_WALL:
@@ -649,7 +727,7 @@ int mg_patches_apply(mg_state* s, int mode) {
           a.wallT = it->second.p;
         }
         MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
-          k_wall<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, st>>>(a);
+          { k_wall<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, st>>>(a); mg_count_launches(1); }
           return 0;
         }));
         break;
@@ -667,7 +745,7 @@ int mg_patches_apply(mg_state* s, int mode) {
         a.cs = s->rhs.compStride;
         a.nComp = s->nU;
         a.factor = s->opt.useContinuousAdjoint ? 1.0 : s->adjointForcingFactor;
-        k_patch_add<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a);
+        { k_patch_add<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a); mg_count_launches(1); }
         break;
       }
       case MG_PATCH_ACTUATOR: {
@@ -684,7 +762,7 @@ int mg_patches_apply(mg_state* s, int mode) {
         a.cs = s->rhs.compStride;
         a.nComp = s->nU;
         a.factor = 1.0;
-        k_patch_add<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a);
+        { k_patch_add<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a); mg_count_launches(1); }
         break;
       }
       case MG_PATCH_BLOCK_INTERFACE:
@@ -764,7 +842,7 @@ int quadrature(mg_state* s, int patchType, int kind, const double* a, const doub
   static double* partial = nullptr;
   if (!partial) MG_CUDA(cudaMalloc(&partial, QUAD_BLOCKS * sizeof(double)));
   q.partial = partial;
-  k_quadrature<<<QUAD_BLOCKS, QUAD_THREADS, 0, mg_stream()>>>(q);
+  { k_quadrature<<<QUAD_BLOCKS, QUAD_THREADS, 0, mg_stream()>>>(q); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   double host[QUAD_BLOCKS];
   MG_CUDA(cudaMemcpyAsync(host, partial, sizeof(host), cudaMemcpyDeviceToHost, mg_stream()));
@@ -987,7 +1065,7 @@ int mg_functional_acoustic_noise_forcing_impl(mg_state* s, double timeRampFactor
     a.gamma = s->opt.ratioOfSpecificHeats;
     a.ramp = timeRampFactor;
     a.out = out;
-    k_noise_forcing<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a);
+    { k_noise_forcing<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a); mg_count_launches(1); }
     MG_CUDA(cudaGetLastError());
   }
   return 0;
@@ -1011,8 +1089,8 @@ int mg_functional_actuator_gradient_impl(mg_patch* p, double timeRampFactor, dou
   auto it = p->arrays.find("gradient");
   if (it == p->arrays.end()) MG_TRY(mg_patch_alloc_array(p, "gradient", 1, &out));
   else out = it->second.p;
-  k_actuator_gradient<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), s->W[s->curW].comp(s->nD + 1),
-                                                                      g->controlMollifier.comp(0), timeRampFactor, out);
+  { k_actuator_gradient<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), s->W[s->curW].comp(s->nD + 1),
+                                                                      g->controlMollifier.comp(0), timeRampFactor, out); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   MG_CUDA(cudaMemcpyAsync(hostOut, out, (size_t)p->nPatchPoints * sizeof(double), cudaMemcpyDeviceToHost, mg_stream()));
   MG_CUDA(cudaStreamSynchronize(mg_stream()));
@@ -1030,7 +1108,7 @@ int mg_functional_pressure_drag_impl(mg_state* s, const double direction[3], dou
     DragArgs a;
     MG_TRY(drag_args(s, p, direction, &a));
     a.partial = partial;
-    k_drag<<<DRAG_BLOCKS, DRAG_THREADS, 0, mg_stream()>>>(a);
+    { k_drag<<<DRAG_BLOCKS, DRAG_THREADS, 0, mg_stream()>>>(a); mg_count_launches(1); }
     MG_CUDA(cudaGetLastError());
     double host[DRAG_BLOCKS];
     MG_CUDA(cudaMemcpyAsync(host, partial, sizeof(host), cudaMemcpyDeviceToHost, mg_stream()));
@@ -1056,7 +1134,7 @@ int mg_functional_pressure_drag_forcing_impl(mg_state* s, const double direction
     } else out = it->second.p;
     a.out = out;
     MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
-      k_drag_forcing<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a);
+      { k_drag_forcing<decltype(nd)::value><<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a); mg_count_launches(1); }
       return 0;
     }));
     MG_CUDA(cudaGetLastError());

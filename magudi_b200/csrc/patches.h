@@ -29,6 +29,8 @@ struct mg_patch {
   int localLo[3] = {0, 0, 0}, localSize[3] = {0, 0, 0}, patchOffset[3] = {0, 0, 0};
   int nPatchPoints = 0;
   double inviscidPenaltyAmount = 0.0, viscousPenaltyAmount = 0.0;   // signed, already / normBoundary(1)
+  double spongeAmount = 1.0;          // SPONGE: patches/<name>/sponge_amount, sponge_exponent (src/SpongePatchImpl.f90:40-45)
+  int spongeExponent = 2;
   std::map<std::string, Array> arrays;     // patch-point arrays, (nPatchPoints, nComp) point fastest
   bool AplusReady = false;
   int AplusIncoming = 0;
@@ -50,6 +52,7 @@ int mg_patch_get_array_impl(mg_patch* p, const char* name, int nComp, double* ho
 int mg_patch_collect_impl(mg_patch* p, const MgField* f, int nComp, const char* name);
 int mg_patch_disperse_impl(mg_patch* p, const char* name, int nComp, MgField* f);
 int mg_patches_update_impl(mg_state* s);
+int mg_patches_sponge_strengths_impl(mg_state* s);
 
 // block interfaces (interface.cu)
 bool mg_state_has_interfaces(const mg_state* s);

@@ -579,7 +579,7 @@ int mg_state_update_impl(mg_state* s, const MgField* Qoverride) {
   a.N = N;
   const PhysParams pp = s->phys();
   MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
-    k_dependent<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a, pp);
+    { k_dependent<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a, pp); mg_count_launches(1); }
     return 0;
   }));
   MG_CUDA(cudaGetLastError());
@@ -587,13 +587,13 @@ int mg_state_update_impl(mg_state* s, const MgField* Qoverride) {
     MG_TRY(mg_grid_gradient_dev(g, s->velocity.comp(0), s->velocity.compStride, s->nD, &s->stressTensor,
                                 &g->scratchA));
     MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
-      k_stress<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(s->stressTensor.comp(0), s->stressTensor.compStride,
-                                                               s->mu.comp(0), s->lambda.comp(0), N);
+      { k_stress<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(s->stressTensor.comp(0), s->stressTensor.compStride,
+                                                               s->mu.comp(0), s->lambda.comp(0), N); mg_count_launches(1); }
       return 0;
     }));
     MG_TRY(mg_grid_gradient_dev(g, s->temperature.comp(0), s->temperature.compStride, 1, &s->heatFlux,
                                 &g->scratchA));
-    k_heatflux<<<nblocks(N), 256, 0, st>>>(s->heatFlux.comp(0), s->heatFlux.compStride, s->nD, s->kappa.comp(0), N);
+    { k_heatflux<<<nblocks(N), 256, 0, st>>>(s->heatFlux.comp(0), s->heatFlux.compStride, s->nD, s->kappa.comp(0), N); mg_count_launches(1); }
     MG_CUDA(cudaGetLastError());
   }
   s->dependentValid = true;
@@ -614,12 +614,12 @@ static int add_dissipation_general(mg_state* s, int mode) {
     MG_TRY(mg_grid_apply(g, g->dissipation[i], X.comp(0), X.compStride, A.comp(0), A.compStride, s->nU));
     const double* result = A.comp(0);
     if (!g->compositeDissipation) {
-      k_scale_by<<<nblocks(N), 256, 0, st>>>(A.comp(0), A.compStride, s->nU, g->arcLengths.comp(i), -1.0, N);
+      { k_scale_by<<<nblocks(N), 256, 0, st>>>(A.comp(0), A.compStride, s->nU, g->arcLengths.comp(i), -1.0, N); mg_count_launches(1); }
       MG_TRY(mg_grid_apply(g, g->dissipationTranspose[i], A.comp(0), A.compStride, B.comp(0), B.compStride, s->nU));
       MG_TRY(mg_norm_launch(g->firstDerivative[i], B.comp(0), B.compStride, s->nU, g->localSize, 1, st));
       result = B.comp(0);
     }
-    k_axpy<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), result, s->rhs.compStride, A.compStride, s->nU, amount, N);
+    { k_axpy<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), result, s->rhs.compStride, A.compStride, s->nU, amount, N); mg_count_launches(1); }
     MG_CUDA(cudaGetLastError());
   }
   return 0;
@@ -651,7 +651,7 @@ int mg_state_rhs_forward_general(mg_state* s) {
   a.viscous = s->opt.viscosityOn;
   a.curvilinear = g->isCurvilinear;
   MG_TRY(dispatch_nd(nD, [&](auto nd) {
-    k_flux<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a);
+    { k_flux<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a); mg_count_launches(1); }
     return 0;
   }));
   MG_CUDA(cudaGetLastError());
@@ -659,7 +659,7 @@ int mg_state_rhs_forward_general(mg_state* s) {
   for (int i = 0; i < nD; ++i) {
     MG_TRY(mg_grid_apply(g, g->firstDerivative[i], Fh.comp(nU * i), Fh.compStride, Dv.comp(nU * i), Dv.compStride, nU));
   }
-  k_neg_sum<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), Dv.comp(0), Dv.compStride, nU, nD, N);
+  { k_neg_sum<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), Dv.comp(0), Dv.compStride, nU, nD, N); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   return add_dissipation_general(s, MG_FORWARD);
 }
@@ -688,7 +688,7 @@ int mg_state_adjoint_finish(mg_state* s, MgField* src, double sign) {
   f.gamma = s->opt.ratioOfSpecificHeats;
   f.sign = sign;
   MG_TRY(dispatch_nd(nD, [&](auto nd) {
-    k_adjoint_finish<decltype(nd)::value><<<nblocks(N), 256, 0, mg_stream()>>>(f);
+    { k_adjoint_finish<decltype(nd)::value><<<nblocks(N), 256, 0, mg_stream()>>>(f); mg_count_launches(1); }
     return 0;
   }));
   MG_CUDA(cudaGetLastError());
@@ -733,7 +733,7 @@ int mg_state_rhs_adjoint_general(mg_state* s) {
   a.gamma = s->opt.ratioOfSpecificHeats;
   a.powerLaw = s->opt.powerLawExponent;
   MG_TRY(dispatch_nd(nD, [&](auto nd) {
-    k_adjoint_point<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a);
+    { k_adjoint_point<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a); mg_count_launches(1); }
     return 0;
   }));
   MG_CUDA(cudaGetLastError());
@@ -773,7 +773,7 @@ int mg_state_cfl_dt_impl(mg_state* s, int wantDt, double given, double* result) 
   a.pp = s->phys();
   a.partial = d_partial;
   MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
-    k_wave_speed<decltype(nd)::value><<<blocks, 256, 0, mg_stream()>>>(a);
+    { k_wave_speed<decltype(nd)::value><<<blocks, 256, 0, mg_stream()>>>(a); mg_count_launches(1); }
     return 0;
   }));
   MG_CUDA(cudaGetLastError());
@@ -820,7 +820,7 @@ int mg_state_rhs_linearized_general(mg_state* s) {
     a.kap = s->kappa.comp(0);
     a.t = B.comp(0);
     MG_TRY(dispatch_nd(nD, [&](auto nd) {
-      k_linearized_primitive<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a);
+      { k_linearized_primitive<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a); mg_count_launches(1); }
       return 0;
     }));
     MG_CUDA(cudaGetLastError());
@@ -831,14 +831,14 @@ int mg_state_rhs_linearized_general(mg_state* s) {
   a.Fhat = B.comp(0);
   a.Fv = keep ? s->viscFluxCart.comp(0) : nullptr;
   MG_TRY(dispatch_nd(nD, [&](auto nd) {
-    k_linearized_flux<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a);
+    { k_linearized_flux<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a); mg_count_launches(1); }
     return 0;
   }));
   MG_CUDA(cudaGetLastError());
   if (keep) MG_TRY(mg_patches_collect_viscous(s));
   for (int i = 0; i < nD; ++i)
     MG_TRY(mg_grid_apply(g, g->firstDerivative[i], B.comp(nU * i), B.compStride, A.comp(nU * i), A.compStride, nU));
-  k_neg_sum<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), A.comp(0), A.compStride, nU, nD, N);
+  { k_neg_sum<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), A.comp(0), A.compStride, nU, nD, N); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   return add_dissipation_general(s, MG_LINEARIZED);
 }
@@ -870,7 +870,7 @@ int mg_state_rhs_post(mg_state* s, int mode) {
     MG_TRY(mg_interfaces_adjoint_sources(s, &g->scratchB));
     MG_TRY(mg_state_adjoint_finish(s, &g->scratchB, -1.0));
   }
-  k_mul_jacobian<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), s->rhs.compStride, s->nU, g->jacobian.comp(0), N);
+  { k_mul_jacobian<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), s->rhs.compStride, s->nU, g->jacobian.comp(0), N); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   MG_TRY(mg_patches_apply(s, mode));
   if (mode == MG_FORWARD) {
@@ -886,11 +886,11 @@ int mg_state_rhs_post(mg_state* s, int mode) {
       a.gaussianFactor = src.gaussianFactor;
       a.nD = s->nD;
       a.N = N;
-      k_acoustic<<<nblocks(N), 256, 0, st>>>(a);
+      { k_acoustic<<<nblocks(N), 256, 0, st>>>(a); mg_count_launches(1); }
     }
   }
   if (g->iblank)
-    k_mask_holes<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), s->rhs.compStride, s->nU, g->iblank, N);
+    { k_mask_holes<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), s->rhs.compStride, s->nU, g->iblank, N); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -959,7 +959,7 @@ int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int time
     a.Qout = s->Q[s->cur].comp(0);     // in place: the RHS is already materialised
     a.stage = stage;
     a.dt = dt;
-    k_rk4<<<nblocks(N), 256, 0, st>>>(a);
+    { k_rk4<<<nblocks(N), 256, 0, st>>>(a); mg_count_launches(1); }
     s->dependentValid = false;
     s->fusedValid = false;
   } else if (mode == MG_ADJOINT) {
@@ -984,7 +984,7 @@ int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int time
     a.Qout = s->W[s->curW].comp(0);
     a.stage = 5 - stage;               // adjoint stage 4 plays the role of RK stage 1, etc.
     a.dt = -dt;
-    k_rk4<<<nblocks(N), 256, 0, st>>>(a);
+    { k_rk4<<<nblocks(N), 256, 0, st>>>(a); mg_count_launches(1); }
     if (stage == 4 || stage == 2) s->timeProgressive = *time;
     if (stage == 3 || stage == 1) { *time -= dt / 2.0; s->time = *time; }
   } else if (mode == MG_LINEARIZED) {
@@ -1002,7 +1002,7 @@ int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int time
     a.Qout = s->W[s->curW].comp(0);
     a.stage = stage;
     a.dt = dt;
-    k_rk4<<<nblocks(N), 256, 0, st>>>(a);
+    { k_rk4<<<nblocks(N), 256, 0, st>>>(a); mg_count_launches(1); }
   } else {
     MG_FAIL("rk4 substep: unknown mode");
   }

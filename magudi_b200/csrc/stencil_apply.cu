@@ -171,9 +171,9 @@ int mg_apply_launch(mg_stencil* s, const ApplyArgs& a) {
   const int threads = 256;
   const unsigned blocks = (unsigned)((total + threads - 1) / threads);
   cudaStream_t st = a.stream ? a.stream : mg_stream();
-  if (d == 0) k_apply<0><<<blocks, threads, 0, st>>>(s->d_op, a);
-  else if (d == 1) k_apply<1><<<blocks, threads, 0, st>>>(s->d_op, a);
-  else k_apply<2><<<blocks, threads, 0, st>>>(s->d_op, a);
+  if (d == 0) { k_apply<0><<<blocks, threads, 0, st>>>(s->d_op, a); mg_count_launches(1); }
+  else if (d == 1) { k_apply<1><<<blocks, threads, 0, st>>>(s->d_op, a); mg_count_launches(1); }
+  else { k_apply<2><<<blocks, threads, 0, st>>>(s->d_op, a); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -187,9 +187,9 @@ int mg_norm_launch(mg_stencil* s, double* x, size_t compStride, int nComp, const
   const int threads = 256;
   const unsigned blocks = (unsigned)((total + threads - 1) / threads);
   if (!st) st = mg_stream();
-  if (d == 0) k_norm<0><<<blocks, threads, 0, st>>>(s->d_op, x, compStride, nComp, n[0], n[1], n[2], inverse);
-  else if (d == 1) k_norm<1><<<blocks, threads, 0, st>>>(s->d_op, x, compStride, nComp, n[0], n[1], n[2], inverse);
-  else k_norm<2><<<blocks, threads, 0, st>>>(s->d_op, x, compStride, nComp, n[0], n[1], n[2], inverse);
+  if (d == 0) { k_norm<0><<<blocks, threads, 0, st>>>(s->d_op, x, compStride, nComp, n[0], n[1], n[2], inverse); mg_count_launches(1); }
+  else if (d == 1) { k_norm<1><<<blocks, threads, 0, st>>>(s->d_op, x, compStride, nComp, n[0], n[1], n[2], inverse); mg_count_launches(1); }
+  else { k_norm<2><<<blocks, threads, 0, st>>>(s->d_op, x, compStride, nComp, n[0], n[1], n[2], inverse); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -204,11 +204,11 @@ int mg_boundary_launch(mg_stencil* s, const double* in, double* out, size_t comp
   const unsigned blocks = (unsigned)((total + threads - 1) / threads);
   if (!st) st = mg_stream();
   if (d == 0)
-    k_boundary<0><<<blocks, threads, 0, st>>>(s->d_op, in, out, compStride, nComp, n[0], n[1], n[2], face, applyThenProject);
+    { k_boundary<0><<<blocks, threads, 0, st>>>(s->d_op, in, out, compStride, nComp, n[0], n[1], n[2], face, applyThenProject); mg_count_launches(1); }
   else if (d == 1)
-    k_boundary<1><<<blocks, threads, 0, st>>>(s->d_op, in, out, compStride, nComp, n[0], n[1], n[2], face, applyThenProject);
+    { k_boundary<1><<<blocks, threads, 0, st>>>(s->d_op, in, out, compStride, nComp, n[0], n[1], n[2], face, applyThenProject); mg_count_launches(1); }
   else
-    k_boundary<2><<<blocks, threads, 0, st>>>(s->d_op, in, out, compStride, nComp, n[0], n[1], n[2], face, applyThenProject);
+    { k_boundary<2><<<blocks, threads, 0, st>>>(s->d_op, in, out, compStride, nComp, n[0], n[1], n[2], face, applyThenProject); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   return 0;
 }

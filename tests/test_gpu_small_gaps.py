@@ -127,3 +127,34 @@ def test_forward_control_forcing_through_the_actuator_patch():
     orhs.computeRhs(orhs.ADJOINT, opt, g, s, [pa])
     region.computeRhs(mb.ADJOINT)
     assert relerr(st.rightHandSide, s.rightHandSide) <= 1e-12     # inert in ADJOINT mode
+
+
+@pytest.mark.parametrize("shape", [(30, 26), (16, 15, 14)])
+def test_sponge_strengths_computed_on_the_device(shape):
+    """computeSpongeStrengths (reference src/PatchFactoryImpl.f90:161-374) on curvilinear grids, both orientations,
+    sponge_amount / sponge_exponent per patch: the product no longer needs the strengths as an input array."""
+    import magudi_b200 as mb
+    from oracle import patches as op
+    nd = len(shape)
+    g, opt, s, rng = oracle_case(shape, (False,) * nd, True, False, False, "SBP 2-4", seed=3)
+    n = g.globalSize
+    full = [1, n[0], 1, n[1], 1, n[2]]
+    plist, specs = [], []
+    for d in range(nd):
+        for side, amount, expo in ((+1, 0.2, 2), (-1, 0.7, 3)):
+            e = list(full)
+            e[2 * d], e[2 * d + 1] = (1, 7) if side > 0 else (n[d] - 5, n[d])
+            if d == 0:
+                e[2], e[3] = 3, n[1] - 2                      # a patch that does not span the whole face
+            plist.append(op.SpongePatch(f"sponge{d}{side}", g, side * (d + 1), e, amount, expo))
+            specs.append(("SPONGE", f"sponge{d}{side}", side * (d + 1), e, amount, expo))
+    op.computeSpongeStrengths(plist, g)
+    gg, o, st = gpu_case_from_oracle(g, opt, s)
+    region = mb.Region()
+    region.addState(st)
+    gp = [st.addPatch(*sp) for sp in specs]
+    region.computeSpongeStrengths()
+    for po, pg in zip(plist, gp):
+        got = pg.getArray("spongeStrength", 1)[:, 0]
+        assert np.max(po.spongeStrength) > 0.1
+        assert relerr(got, po.spongeStrength) <= 1e-13

@@ -150,7 +150,7 @@ def run_general(shape, world, rank, dev):
     return np.concatenate(out, axis=1), grid
 
 
-def compare(pieces, single, shape, ncomp, label, world, tol):
+def compare(pieces, single, shape, ncomp, label, world):
     Qs = single.reshape(tuple(shape) + (ncomp,), order="F")
     err = 0.0
     for k0, nz, q in pieces:
@@ -159,8 +159,30 @@ def compare(pieces, single, shape, ncomp, label, world, tol):
         for c0 in range(0, ncomp, 5):
             sl = slice(c0, c0 + 5)
             err = max(err, float(np.max(np.abs(q[..., sl] - ref[..., sl])) / np.max(np.abs(Qs[..., sl]))))
-    print(f"multi_gpu_check: world={world} {label}: max rel diff vs single GPU = {err:.3e}")
-    return err <= tol
+    print(f"multi_gpu_check: world={world} {label}: max rel diff vs single GPU = {err:.3e}", file=sys.stderr)
+    return err
+
+
+def check_all(world, rank, dev):
+    """Both checks on an initialised process group; returns {case: max rel diff} on rank 0 (None elsewhere)."""
+    shape = (32, 30, 16 * world + 5)
+    Ql, grid = run(shape, world, rank, dev)
+    pieces = [None] * world
+    dist.all_gather_object(pieces, (grid.offset[2], grid.localSize[2], Ql))
+    gshape = (20, 18, 13 * world + 3)
+    Gl, ggrid = run_general(gshape, world, rank, dev)
+    gpieces = [None] * world
+    dist.all_gather_object(gpieces, (ggrid.offset[2], ggrid.localSize[2], Gl))
+    out = None
+    if rank == 0:
+        Qs, _ = run(shape, 1, 0, dev)
+        Gs, _ = run_general(gshape, 1, 0, dev)
+        e1 = compare(pieces, Qs, shape, 10, "fused path (2 forward + 1 adjoint RK4 steps)", world)
+        e2 = compare(gpieces, Gs, gshape, 25, "general path (patches, non-periodic k; fwd/adj/lin RHS + RK4)", world)
+        out = {"fused_forward_adjoint_rk4_max_rel_diff_vs_1gpu": e1, "general_path_patches_max_rel_diff_vs_1gpu": e2,
+               "ranks": world, "tolerance": 1e-12, "ok": bool(e1 <= 1e-13 and e2 <= 1e-12)}
+    dist.barrier()
+    return out
 
 
 def main():
@@ -172,35 +194,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.init(local_rank)
-    shape = (32, 30, 16 * world + 5)
-    Ql, grid = run(shape, world, rank, dev)
     ok = True
     if world > 1:
-        pieces = [None] * world
-        dist.all_gather_object(pieces, (grid.offset[2], grid.localSize[2], Ql))
+        res = check_all(world, rank, dev)
         if rank == 0:
-            Qs, _ = run(shape, 1, 0, dev)
-            Qs = Qs.reshape(tuple(shape) + (10,), order="F")
-            err = 0.0
-            for k0, nz, q in pieces:
-                q = q.reshape((shape[0], shape[1], nz, 10), order="F")
-                ref = Qs[:, :, k0:k0 + nz]
-                for sl in (slice(0, 5), slice(5, 10)):        # conserved variables, adjoint variables
-                    err = max(err, float(np.max(np.abs(q[..., sl] - ref[..., sl])) / np.max(np.abs(Qs[..., sl]))))
-            print(f"multi_gpu_check: world={world} max rel diff vs single GPU = {err:.3e}")
-            ok = err <= 1e-13
-        # operator-by-operator path with patches and a non-periodic k
-        gshape = (20, 18, 13 * world + 3)
-        Gl, ggrid = run_general(gshape, world, rank, dev)
-        gpieces = [None] * world
-        dist.all_gather_object(gpieces, (ggrid.offset[2], ggrid.localSize[2], Gl))
-        if rank == 0:
-            Gs, _ = run_general(gshape, 1, 0, dev)
-            ok = compare(gpieces, Gs, gshape, 25, "general path (patches, non-periodic k; fwd/adj/lin RHS + RK4)",
-                         world, 1e-12) and ok
-        dist.barrier()
+            ok = res["ok"]
         dist.destroy_process_group()
     else:
+        run((32, 30, 21), 1, 0, dev)
+        run_general((20, 18, 16), 1, 0, dev)
         print("multi_gpu_check: single rank run ok")
     sys.exit(0 if ok else 1)
 
