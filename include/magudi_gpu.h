@@ -205,6 +205,12 @@ int mg_state_get(mg_state* s, int field, double* host);
 int mg_state_set_async(mg_state* s, int field, const double* pinnedHost);
 int mg_state_get_async(mg_state* s, int field, double* pinnedHost);
 int mg_state_checkpoint_get_async(mg_state* s, int slot, double* pinnedHost);
+/* Double-buffered inputs for back-to-back steps: stage the NEXT step's conserved / adjoint variables into a free
+ * device buffer while the current step computes (host->device on its own stream, device->host reads on another:
+ * both copy engines run beside the sweeps), then adopt them (pointer swap, no copy) when the step begins.  A buffer
+ * a pending device->host read still uses is never handed out as free storage. */
+int mg_state_stage_async(mg_state* s, int field, const double* pinnedHost);
+int mg_state_adopt_staged(mg_state* s, int field);
 int mg_transfer_fence(void);   /* compute stream waits for the transfers issued so far */
 int mg_transfer_wait(void);    /* host waits for the transfers issued so far */
 int mg_state_set_time(mg_state* s, double time);

@@ -96,6 +96,8 @@ SIGNATURES = {
     "mg_state_set": (C.c_int, [_P, C.c_int, _P]),
     "mg_state_get": (C.c_int, [_P, C.c_int, _P]),
     "mg_state_set_async": (C.c_int, [_P, C.c_int, _P]),
+    "mg_state_stage_async": (C.c_int, [_P, C.c_int, _P]),
+    "mg_state_adopt_staged": (C.c_int, [_P, C.c_int]),
     "mg_state_get_async": (C.c_int, [_P, C.c_int, _P]),
     "mg_state_checkpoint_get_async": (C.c_int, [_P, C.c_int, _P]),
     "mg_transfer_fence": (C.c_int, []),

@@ -401,6 +401,14 @@ class State:
     def setFromPointerAsync(self, field, ptr):
         check(L.lib().mg_state_set_async(self._h, field, C.c_void_p(ptr)))
 
+    def stageFromPointerAsync(self, field, ptr):
+        """Copy the NEXT step's conserved / adjoint variables (pinned host memory) into a free device buffer while
+        the current step computes; ``adoptStaged`` swaps it in."""
+        check(L.lib().mg_state_stage_async(self._h, field, C.c_void_p(ptr)))
+
+    def adoptStaged(self, field):
+        check(L.lib().mg_state_adopt_staged(self._h, field))
+
     def getToPointerAsync(self, field, ptr):
         check(L.lib().mg_state_get_async(self._h, field, C.c_void_p(ptr)))
 

@@ -15,7 +15,8 @@
 namespace {
 thread_local std::string g_error;
 cudaStream_t g_stream = nullptr;
-cudaStream_t g_copyStream = nullptr;   // host <-> device transfers that overlap the sweeps (mg_state_*_async)
+cudaStream_t g_copyStream = nullptr;   // host -> device transfers that overlap the sweeps (mg_state_*_async)
+cudaStream_t g_readStream = nullptr;   // device -> host transfers: the two directions use separate copy engines
 int g_device = -1;
 int g_sms = 0;
 std::atomic<long long> g_launches{0};
@@ -173,6 +174,8 @@ int mg_init(int device) {
   if (!g_stream) MG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   if (g_copyStream && g_device != device) { cudaStreamDestroy(g_copyStream); g_copyStream = nullptr; }
   if (!g_copyStream) MG_CUDA(cudaStreamCreateWithFlags(&g_copyStream, cudaStreamNonBlocking));
+  if (g_readStream && g_device != device) { cudaStreamDestroy(g_readStream); g_readStream = nullptr; }
+  if (!g_readStream) MG_CUDA(cudaStreamCreateWithFlags(&g_readStream, cudaStreamNonBlocking));
   cudaDeviceProp prop;
   MG_CUDA(cudaGetDeviceProperties(&prop, device));
   g_sms = prop.multiProcessorCount;
@@ -552,12 +555,16 @@ int stream_wait(cudaStream_t waiter, cudaStream_t on) {
   return 0;
 }
 int copy_field_async(const mg_grid* g, MgField* f, double* host, bool toDevice) {
-  MG_TRY(stream_wait(g_copyStream, g_stream));
+  cudaStream_t cs = toDevice ? g_copyStream : g_readStream;
+  MG_TRY(stream_wait(cs, g_stream));
+  // (the two directions never meet on one buffer: a buffer with a read in flight is not handed out for writing,
+  // mg_state_make_exclusive / mg_state_pool_acquire, and a field that is being written is read only after
+  // mg_transfer_fence, which orders it through the compute stream)
   for (int c = 0; c < f->nComp; ++c) {
     if (toDevice)
-      MG_CUDA(cudaMemcpyAsync(f->comp(c), host + (size_t)c * g->N, g->N * sizeof(double), cudaMemcpyDefault, g_copyStream));
+      MG_CUDA(cudaMemcpyAsync(f->comp(c), host + (size_t)c * g->N, g->N * sizeof(double), cudaMemcpyDefault, cs));
     else
-      MG_CUDA(cudaMemcpyAsync(host + (size_t)c * g->N, f->comp(c), g->N * sizeof(double), cudaMemcpyDefault, g_copyStream));
+      MG_CUDA(cudaMemcpyAsync(host + (size_t)c * g->N, f->comp(c), g->N * sizeof(double), cudaMemcpyDefault, cs));
   }
   return 0;
 }
@@ -575,20 +582,62 @@ int mg_state_set_async(mg_state* s, int field, const double* pinnedHost) {
 int mg_state_get_async(mg_state* s, int field, double* pinnedHost) {
   MgField* f = s ? state_field(s, field) : nullptr;
   if (!f || !f->p || !pinnedHost) MG_FAIL("mg_state_get_async: unknown or unallocated field");
-  return copy_field_async(s->grid, f, pinnedHost, false);
+  MG_TRY(copy_field_async(s->grid, f, pinnedHost, false));
+  if (field == MG_Q_CONSERVED || field == MG_Q_ADJOINT) mg_state_note_pending_read(s, f->p, g_readStream);
+  return 0;
 }
 int mg_state_checkpoint_get_async(mg_state* s, int slot, double* pinnedHost) {
   if (!s || !pinnedHost || slot < 0 || (size_t)slot >= s->checkpoints.size() || !s->checkpoints[slot].p)
     MG_FAIL("mg_state_checkpoint_get_async: empty slot");
-  return copy_field_async(s->grid, &s->checkpoints[slot], pinnedHost, false);
+  MG_TRY(copy_field_async(s->grid, &s->checkpoints[slot], pinnedHost, false));
+  mg_state_note_pending_read(s, s->checkpoints[slot].p, g_readStream);
+  return 0;
+}
+// Double-buffered inputs: copy the NEXT step's conserved / adjoint variables into a free buffer of the state's pool
+// while the current step computes (nothing on the compute stream reads or writes that buffer), then adopt it.
+int mg_state_stage_async(mg_state* s, int field, const double* pinnedHost) {
+  if (!s || !pinnedHost || (field != MG_Q_CONSERVED && field != MG_Q_ADJOINT))
+    MG_FAIL("mg_state_stage_async: only the conserved and the adjoint variables can be staged");
+  const int w = field == MG_Q_ADJOINT ? 1 : 0;
+  MgField* cur = state_field(s, field);
+  if (!cur || !cur->p) MG_FAIL("mg_state_stage_async: unallocated field");
+  MgField& st = s->staged[w];
+  if (!st.p) {
+    st = *cur;
+    st.owned = false;
+    st.p = nullptr;
+    st.p = mg_state_pool_acquire(s, cur->compStride * (size_t)cur->nComp * sizeof(double));
+    if (!st.p) MG_FAIL("mg_state_stage_async: out of device memory");
+  }
+  // the buffer is unreferenced, but sweeps enqueued earlier may still be reading it under its previous role
+  MG_TRY(stream_wait(g_copyStream, g_stream));
+  const mg_grid* g = s->grid;
+  for (int c = 0; c < st.nComp; ++c)
+    MG_CUDA(cudaMemcpyAsync(st.comp(c), pinnedHost + (size_t)c * g->N, g->N * sizeof(double), cudaMemcpyDefault, g_copyStream));
+  if (!s->stagedReady[w]) MG_CUDA(cudaEventCreateWithFlags(&s->stagedReady[w], cudaEventDisableTiming));
+  MG_CUDA(cudaEventRecord(s->stagedReady[w], g_copyStream));
+  return 0;
+}
+int mg_state_adopt_staged(mg_state* s, int field) {
+  if (!s || (field != MG_Q_CONSERVED && field != MG_Q_ADJOINT)) MG_FAIL("mg_state_adopt_staged: invalid argument");
+  const int w = field == MG_Q_ADJOINT ? 1 : 0;
+  if (!s->staged[w].p) MG_FAIL("mg_state_adopt_staged: nothing has been staged for this field");
+  MG_CUDA(cudaStreamWaitEvent(g_stream, s->stagedReady[w], 0));
+  MgField* cur = state_field(s, field);
+  cur->p = s->staged[w].p;          // the previous buffer goes back to the pool (unless a slot still views it)
+  s->staged[w].p = nullptr;
+  if (field == MG_Q_CONSERVED) { s->dependentValid = false; s->fusedValid = false; s->dissValid = false; }
+  return 0;
 }
 int mg_transfer_fence(void) {
   if (g_device < 0) MG_FAIL("mg_transfer_fence: mg_init has not been called");
-  return stream_wait(g_stream, g_copyStream);
+  MG_TRY(stream_wait(g_stream, g_copyStream));
+  return stream_wait(g_stream, g_readStream);
 }
 int mg_transfer_wait(void) {
   if (g_device < 0) MG_FAIL("mg_transfer_wait: mg_init has not been called");
   MG_CUDA(cudaStreamSynchronize(g_copyStream));
+  MG_CUDA(cudaStreamSynchronize(g_readStream));
   return 0;
 }
 

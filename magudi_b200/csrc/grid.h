@@ -41,6 +41,13 @@ struct mg_state {
   // writes to it (mg_state_make_exclusive).
   std::vector<MgField> checkpoints;
   std::vector<double*> pool;
+  // inputs of the NEXT step, copied from the host into free pool buffers while the current step computes
+  // (mg_state_stage_async); mg_state_adopt_staged makes them the conserved / adjoint variables (pointer swap)
+  MgField staged[2];
+  cudaEvent_t stagedReady[2] = {nullptr, nullptr};
+  // device->host reads still in flight from pooled buffers: such a buffer is not handed out as free storage
+  struct PendingRead { double* p; cudaEvent_t done; };
+  std::vector<PendingRead> pendingReads;
   bool fusedValid = false;
   bool dissValid = false;      // dissTerm holds the dissipation of the current Q
   int useFused = 1;
@@ -69,6 +76,8 @@ void mg_state_destroy_impl(mg_state* s);
 int mg_state_update_impl(mg_state* s, const MgField* Qoverride);
 int mg_state_make_exclusive(mg_state* s, MgField* f, bool keepContents);
 void mg_state_pool_trim(mg_state* s);
+double* mg_state_pool_acquire(mg_state* s, size_t bytes);        // a buffer nothing refers to and nothing is reading
+void mg_state_note_pending_read(mg_state* s, double* p, cudaStream_t readStream);
 int mg_state_rhs_forward_general(mg_state* s);
 int mg_state_rhs_adjoint_general(mg_state* s);
 int mg_state_rhs_linearized_general(mg_state* s);

@@ -509,7 +509,7 @@ int mg_state_create_impl(mg_grid* g, const mg_options_t* opt, mg_state** out) {
 namespace {
 template <class F>
 void for_each_pooled(mg_state* s, F&& fn) {
-  for (MgField* f : {&s->Q[0], &s->Q[1], &s->W[0], &s->W[1], &s->rk1}) fn(f);
+  for (MgField* f : {&s->Q[0], &s->Q[1], &s->W[0], &s->W[1], &s->rk1, &s->staged[0], &s->staged[1]}) fn(f);
   for (MgField& c : s->checkpoints) fn(&c);
 }
 bool pool_referenced(mg_state* s, const double* p, const MgField* except) {
@@ -519,18 +519,46 @@ bool pool_referenced(mg_state* s, const double* p, const MgField* except) {
 }
 }  // namespace
 
+// A device->host read of pooled buffer p has been enqueued on readStream: until it completes the buffer must not
+// be reused as free storage (re-storing a checkpoint slot or adopting a staged input drops the last reference).
+void mg_state_note_pending_read(mg_state* s, double* p, cudaStream_t readStream) {
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return;
+  cudaEventRecord(e, readStream);
+  s->pendingReads.push_back({p, e});
+}
+
+static bool read_pending(mg_state* s, const double* p) {
+  bool pending = false;
+  for (size_t i = 0; i < s->pendingReads.size();) {
+    if (cudaEventQuery(s->pendingReads[i].done) == cudaSuccess) {
+      cudaEventDestroy(s->pendingReads[i].done);
+      s->pendingReads.erase(s->pendingReads.begin() + i);
+      continue;
+    }
+    if (s->pendingReads[i].p == p) pending = true;
+    ++i;
+  }
+  cudaGetLastError();      // cudaErrorNotReady from the queries is not an error
+  return pending;
+}
+
+double* mg_state_pool_acquire(mg_state* s, size_t bytes) {
+  for (double* p : s->pool)
+    if (!pool_referenced(s, p, nullptr) && !read_pending(s, p)) return p;
+  double* fresh = nullptr;
+  if (cudaMalloc(&fresh, bytes) != cudaSuccess) return nullptr;
+  cudaMemsetAsync(fresh, 0, bytes, mg_stream());
+  s->pool.push_back(fresh);
+  return fresh;
+}
+
 // Give `f` storage that no other pooled field refers to (a shared buffer keeps serving the others).
 int mg_state_make_exclusive(mg_state* s, MgField* f, bool keepContents) {
-  if (!f->p || !pool_referenced(s, f->p, f)) return 0;
-  double* fresh = nullptr;
-  for (double* p : s->pool)
-    if (!pool_referenced(s, p, nullptr)) { fresh = p; break; }
+  if (!f->p || (!pool_referenced(s, f->p, f) && !read_pending(s, f->p))) return 0;
   const size_t bytes = f->compStride * (size_t)f->nComp * sizeof(double);
-  if (!fresh) {
-    MG_CUDA(cudaMalloc(&fresh, bytes));
-    MG_CUDA(cudaMemsetAsync(fresh, 0, bytes, mg_stream()));
-    s->pool.push_back(fresh);
-  }
+  double* fresh = mg_state_pool_acquire(s, bytes);
+  if (!fresh) MG_FAIL("out of device memory for a state buffer");
   if (keepContents) MG_CUDA(cudaMemcpyAsync(fresh, f->p, bytes, cudaMemcpyDeviceToDevice, mg_stream()));
   f->p = fresh;
   return 0;
@@ -540,7 +568,7 @@ int mg_state_make_exclusive(mg_state* s, MgField* f, bool keepContents) {
 void mg_state_pool_trim(mg_state* s) {
   std::vector<double*> keep;
   for (double* p : s->pool) {
-    if (pool_referenced(s, p, nullptr)) keep.push_back(p);
+    if (pool_referenced(s, p, nullptr) || read_pending(s, p)) keep.push_back(p);
     else cudaFree(p);
   }
   s->pool.swap(keep);

@@ -80,3 +80,47 @@ def test_dependent_getters_are_fresh_on_the_fused_path():
     s.update(g, opt)
     assert relerr(st.temperature, s.temperature) <= 1e-13
     assert relerr(st.stressTensor, s.stressTensor) <= 1e-12
+
+
+def test_staged_inputs_and_async_results_round_trip():
+    """Double-buffered inputs (mg_state_stage_async / mg_state_adopt_staged) and the asynchronous result reads on the
+    second copy stream: what is staged while a step runs becomes the state of the next step, untouched by that step,
+    and results read asynchronously are the values the step produced."""
+    import torch
+    import magudi_b200 as mb
+    from magudi_b200 import core
+    g, opt, s, rng = oracle_case((20, 19, 18), (True, True, True), False, True, False, "SBP 3-6", seed=21)
+    gg, o, st = gpu_case_from_oracle(g, opt, s)
+    region = mb.Region()
+    region.addState(st)
+    integ = mb.RK4Integrator(region)
+    N = g.nGridPoints
+    Q1 = s.conservedVariables.copy()
+    Q2 = Q1 * (1.0 + 1e-3 * rng.random(Q1.shape))
+    W2 = rng.random(Q1.shape)
+    pin = lambda a: torch.from_numpy(np.asfortranarray(a).T.copy()).pin_memory()
+    hQ2, hW2 = pin(Q2), pin(W2)
+    out = torch.empty_like(hQ2).pin_memory()
+    # step 1 on Q1, with the inputs of step 2 travelling meanwhile
+    st.stageFromPointerAsync(core.Q_CONSERVED, hQ2.data_ptr())
+    st.stageFromPointerAsync(core.Q_ADJOINT, hW2.data_ptr())
+    t = 0.0
+    for stage in range(1, 5):
+        t = integ.substepForward(t, 1e-3, 0, stage)
+    after1 = st.conservedVariables.copy()
+    st.getToPointerAsync(core.Q_CONSERVED, out.data_ptr())       # result of step 1, read beside step 2
+    st.adoptStaged(core.Q_CONSERVED)
+    st.adoptStaged(core.Q_ADJOINT)
+    assert np.array_equal(st.conservedVariables, Q2)
+    assert np.array_equal(st.adjointVariables, W2)
+    for stage in range(1, 5):
+        t = integ.substepForward(t, 1e-3, 1, stage)
+    core.transferWait()
+    assert np.array_equal(out.numpy().T, after1)                  # not clobbered by step 2's buffers
+    # step 2 really started from Q2: same result as a fresh run from Q2
+    ref = st.conservedVariables.copy()
+    st.conservedVariables = Q2
+    t = 0.0
+    for stage in range(1, 5):
+        t = integ.substepForward(t, 1e-3, 1, stage)
+    assert np.array_equal(st.conservedVariables, ref)
