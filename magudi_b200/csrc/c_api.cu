@@ -189,7 +189,7 @@ int mg_synchronize(void) {
   if (g_device < 0) MG_FAIL("mg_synchronize: mg_init has not been called");
   MG_TRY(mg_halo_wait_pending());
   MG_CUDA(cudaStreamSynchronize(g_stream));
-  return 0;
+  return mg_p2p_check_all();
 }
 long long mg_kernel_launch_count(void) { return g_launches.load(); }
 void* mg_stream_handle(void) { return (void*)g_stream; }
@@ -530,7 +530,8 @@ int mg_state_get(mg_state* s, int field, double* host) {
   MgField* f = s ? state_field(s, field) : nullptr;
   if (!f || !f->p) MG_FAIL("mg_state_get: unknown or unallocated field");
   MG_TRY(refresh_dependents(s, field));
-  return mg_field_download(s->grid, f, host);
+  MG_TRY(mg_field_download(s->grid, f, host));
+  return mg_p2p_check_all();
 }
 // computeCfl / computeTimeStepSize (reference src/StateImpl.f90:548-600 -> src/CNSHelperImpl.f90:842-982)
 int mg_state_cfl(mg_state* s, double timeStepSize, double* cfl) {

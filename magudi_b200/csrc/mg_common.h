@@ -113,6 +113,7 @@ struct mg_grid {
   // the ghost planes of whatever array an operator is applied to along k
   struct mg_p2p* halo = nullptr;
 };
+int mg_p2p_check_all();       // fails when a halo exchange of any live handle has timed out
 int mg_p2p_exchange_view(struct mg_p2p* h, const double* comp0, size_t compStride, int nComp, int width);
 
 int mg_field_alloc(const mg_grid* g, int nComp, MgField* f);

@@ -12,6 +12,7 @@
 // other by up to two exchanges per face.
 #include <cstdint>
 #include <algorithm>
+#include <vector>
 #include <cstring>
 
 #include "../../include/magudi_gpu.h"
@@ -23,7 +24,12 @@ extern "C" MgField* mg_lookup_field(mg_grid* g, void* owner, int field);   // c_
 namespace {
 
 constexpr int P2P_BLOCKS = 144, P2P_THREADS = 256;
-constexpr long long SPIN_LIMIT_CYCLES = 20LL * 1000 * 1000 * 1000;   // ~10 s: turn a protocol bug into an error
+// A wait that lasts longer than this turns a protocol bug or a dead neighbour into an error instead of a hang.
+// Legitimate rank skew (first-use allocations, host I/O, a profiler) can be long: the default is 120 s and
+// MG_P2P_TIMEOUT_S (environment / mg_tuning_set) overrides it.  The flag is host-mapped and sticky: it is checked at
+// every host synchronisation point of the library (mg_synchronize, mg_state_get, the functionals), so a timed-out
+// exchange cannot yield a result silently; the handle is dead afterwards (the use counts no longer agree).
+__device__ long long g_spinLimitCycles = 240LL * 1000 * 1000 * 1000;
 
 struct Shared {                         // layout of the flag block at the head of the shared allocation
   unsigned long long data[2][2];        // [my ghost face][parity]: uses of recv[face][parity] completed by the sender
@@ -47,7 +53,12 @@ __device__ __forceinline__ bool block_wait(const unsigned long long* flag, unsig
     ok = 1;
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < want) {
-      if (clock64() - t0 > SPIN_LIMIT_CYCLES) { ok = 0; atomicExch(error, 1); break; }
+      if (clock64() - t0 > g_spinLimitCycles) {
+        ok = 0;
+        *(volatile int*)error = 1;
+        __threadfence_system();
+        break;
+      }
       __nanosleep(100);
     }
   }
@@ -85,16 +96,18 @@ __global__ void __launch_bounds__(P2P_THREADS) k_push(const __grid_constant__ Pu
   const PushArgs& a = pp.s[blockIdx.y];
   if (!a.dst) return;
   // the previous use of this staging buffer must have been consumed by the neighbour
-  if (!block_wait(a.ackFlag, a.use, a.error)) return;
-  for (int c = 0; c < a.nComp; ++c) copy_chunk(a.dst + (size_t)c * a.chunk, a.src[c], a.chunk, a.vec != 0, false);
+  const bool ok = block_wait(a.ackFlag, a.use, a.error);
+  if (ok)
+    for (int c = 0; c < a.nComp; ++c) copy_chunk(a.dst + (size_t)c * a.chunk, a.src[c], a.chunk, a.vec != 0, false);
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    // the block counter is left at zero whatever happened (a timed-out launch does not poison the next one)
     const unsigned int done = atomicAdd(a.counter, 1u);
     if (done == gridDim.x - 1) {
       *a.counter = 0;
       __threadfence_system();
-      st_release_sys(a.dstFlag, a.use + 1);
+      if (*(volatile int*)a.error == 0) st_release_sys(a.dstFlag, a.use + 1);
     }
   }
 }
@@ -117,9 +130,10 @@ struct UnpackPair { UnpackArgs s[2]; };
 __global__ void __launch_bounds__(P2P_THREADS) k_unpack(const __grid_constant__ UnpackPair pp) {
   const UnpackArgs& a = pp.s[blockIdx.y];
   if (!a.src) return;
-  if (!block_wait(a.dataFlag, a.use + 1, a.error)) return;
+  const bool ok = block_wait(a.dataFlag, a.use + 1, a.error);
   // the staging buffer was written by the peer: read it through L2 (bypass L1)
-  for (int c = 0; c < a.nComp; ++c) copy_chunk(a.dst[c], a.src + (size_t)c * a.chunk, a.chunk, a.vec != 0, true);
+  if (ok)
+    for (int c = 0; c < a.nComp; ++c) copy_chunk(a.dst[c], a.src + (size_t)c * a.chunk, a.chunk, a.vec != 0, true);
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -127,7 +141,7 @@ __global__ void __launch_bounds__(P2P_THREADS) k_unpack(const __grid_constant__ 
     if (done == gridDim.x - 1) {
       *a.counter = 0;
       __threadfence_system();
-      st_release_sys(a.ackFlag, a.use + 1);
+      if (*(volatile int*)a.error == 0) st_release_sys(a.ackFlag, a.use + 1);
     }
   }
 }
@@ -152,6 +166,19 @@ struct mg_p2p {
   }
 };
 
+// every live handle, so that the library's host synchronisation points can look at the error flags
+static std::vector<mg_p2p*> g_handles;
+static void mg_p2p_register(mg_p2p* h, bool add) {
+  if (add) g_handles.push_back(h);
+  else g_handles.erase(std::remove(g_handles.begin(), g_handles.end(), h), g_handles.end());
+}
+int mg_p2p_check_all() {
+  for (mg_p2p* h : g_handles)
+    if (h->error && *(volatile int*)h->error)
+      MG_FAIL("mg_p2p: a halo exchange timed out waiting for its neighbour: ghost planes are stale (MG_P2P_TIMEOUT_S)");
+  return 0;
+}
+
 int mg_p2p_create(mg_grid* g, int maxComp, int width, mg_p2p** out) {
   if (!g || !out) MG_FAIL("mg_p2p_create: null argument");
   if (maxComp < 1 || maxComp > MG_P2P_MAX_COMP) MG_FAIL("mg_p2p_create: component count out of range");
@@ -165,8 +192,18 @@ int mg_p2p_create(mg_grid* g, int maxComp, int width, mg_p2p** out) {
   MG_CUDA(cudaMemset(h->base, 0, h->bytes));
   MG_CUDA(cudaMalloc(&h->counters, 4 * sizeof(unsigned int)));
   MG_CUDA(cudaMemset(h->counters, 0, 4 * sizeof(unsigned int)));
-  MG_CUDA(cudaMalloc(&h->error, sizeof(int)));
-  MG_CUDA(cudaMemset(h->error, 0, sizeof(int)));
+  MG_CUDA(cudaHostAlloc(&h->error, sizeof(int), cudaHostAllocMapped));     // host-mapped: checked without a copy
+  *h->error = 0;
+  {
+    const long long seconds = mg_tuning_get("MG_P2P_TIMEOUT_S", 120);
+    int khz = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+    const long long cycles = seconds * (long long)(khz > 0 ? khz : 2000000) * 1000LL;
+    MG_CUDA(cudaMemcpyToSymbol(g_spinLimitCycles, &cycles, sizeof(cycles)));
+  }
+  mg_p2p_register(h, true);
   MG_CUDA(cudaDeviceSynchronize());
   g->halo = h;          // operator applications along k on this grid fill their ghost planes through it
   *out = h;
@@ -316,11 +353,9 @@ static int p2p_exchange_field(mg_p2p* h, const MgField* f, int width, cudaStream
 // 0 when no spin-wait timed out so far (synchronises the library stream)
 int mg_p2p_check(mg_p2p* h) {
   if (!h) MG_FAIL("mg_p2p_check: null handle");
-  int e = 0;
   MG_TRY(mg_halo_wait_pending());
   MG_CUDA(cudaStreamSynchronize(mg_stream()));
-  MG_CUDA(cudaMemcpy(&e, h->error, sizeof(int), cudaMemcpyDeviceToHost));
-  if (e) MG_FAIL("mg_p2p: a halo exchange timed out waiting for its neighbour");
+  if (*(volatile int*)h->error) MG_FAIL("mg_p2p: a halo exchange timed out waiting for its neighbour (MG_P2P_TIMEOUT_S)");
   return 0;
 }
 
@@ -332,7 +367,8 @@ int mg_p2p_destroy(mg_p2p* h) {
     if (h->peerMapped[s] && h->peer[s]) cudaIpcCloseMemHandle(h->peer[s]);
   cudaFree(h->base);
   cudaFree(h->counters);
-  cudaFree(h->error);
+  mg_p2p_register(h, false);
+  cudaFreeHost(h->error);
   delete h;
   return 0;
 }

@@ -850,7 +850,7 @@ int quadrature(mg_state* s, int patchType, int kind, const double* a, const doub
   double sum = 0.0;
   for (int i = 0; i < QUAD_BLOCKS; ++i) sum += host[i];
   *value = sum;
-  return 0;
+  return mg_p2p_check_all();      // a functional of a state with stale ghost planes must not come back silently
 }
 
 struct ForcingArgs {
