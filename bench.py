@@ -308,8 +308,20 @@ def run_native(args):
     # max over ranks
     kernel_sum_ms = sum(v["ms"] for v in prof.values())
     gap_ms = total_ms - kernel_sum_ms           # step time not covered by the sweeps on this rank: halo + launch gaps
+    by_rank = None
     if world > 1:
         import torch.distributed as dist
+        # per-rank view: the ranks advance in lock step (two-neighbour rendez-vous before every sweep), so the job
+        # runs at the pace of its slowest GPU; kernel time and SM clock of every rank show which one that is
+        mine = torch.tensor([total_ms / args.steps, kernel_sum_ms / args.steps, float(clocks.get("sm_mhz") or 0.0)],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        by_rank = {"ms_per_step": [round(float(a[0]), 3) for a in allr],
+                   "profiled_kernel_ms_per_step": [round(float(a[1]), 3) for a in allr],
+                   "sm_mhz": [float(a[2]) for a in allr],
+                   "note": "profiled kernels = launches on the main stream (the boundary k-chunks of an overlapped "
+                           "exchange run on the halo stream and are not in this sum)"}
         tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
@@ -442,7 +454,7 @@ def run_native(args):
         "roofline_path": path, "kernels": prof, "cpu_baseline": cpu,
         "step_minus_kernel_sum_ms": gap_ms / args.steps,
         "halo_overlap": (os.environ.get("MG_OVERLAP", "1") != "0") if world > 1 else None,
-        "parity": parity,
+        "parity": parity, "by_rank": by_rank,
         "wall_s_timed_region": wall,
     }
     print(json.dumps(line))

@@ -94,3 +94,21 @@ def test_pigeonhole_matches_reference_rule():
             tot += cnt
         assert tot == n
     assert [pigeonhole(10, 3, r)[1] for r in range(3)] == [4, 3, 3]
+
+
+def test_fortran_binding_covers_every_export():
+    """include/MagudiGpu.f90 (the iso_c_binding module of INTEGRATION.md, generated from the header) binds every
+    function the header declares, and is up to date with it."""
+    import re
+    import subprocess
+    import sys
+    hdr = open(os.path.join(ROOT, "include", "magudi_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(mg_[a-z0-9_]+)\s*\(", hdr))
+    f90 = open(os.path.join(ROOT, "include", "MagudiGpu.f90")).read()
+    bound = set(re.findall(r'name="(mg_[a-z0-9_]+)"', f90))
+    assert names and names == bound, (sorted(names - bound), sorted(bound - names))
+    # regenerating gives the committed file
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_fortran_binding as gen
+    assert gen.render(gen.prototypes(os.path.join(ROOT, "include", "magudi_gpu.h"))) == f90
