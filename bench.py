@@ -49,21 +49,26 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs.  ONE nvidia-smi process per
+    job (rank 0) polls every GPU of the box: a poller per rank (8 processes x 10 Hz at N = 8) measurably perturbs a
+    lock-stepped multi-GPU run -- each NVML query briefly stalls work submission on its GPU and every rank then waits
+    for that GPU at the next halo rendez-vous (N = 8: 28.7 -> see DESIGN.md 6)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device=0):
-        self.device = device
+    def __init__(self, devices=(0,), period_ms=250):
+        self.devices = [int(d) for d in devices]
+        self.period_ms = int(period_ms)
         self.rows = []
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                ["nvidia-smi", "--id=" + ",".join(str(d) for d in self.devices), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -73,6 +78,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def samples(self):
+        return len(self.rows) // max(1, len(self.devices))
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -81,11 +89,13 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, reasons, per = [], [], set(), {}
         for r in self.rows:
             try:
+                idx = int(r[0])
                 sm.append(float(r[1]))
                 smax.append(float(r[2]))
+                per.setdefault(idx, []).append(float(r[1]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -93,8 +103,12 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+               "samples": self.samples()}
+        if len(per) > 1:
+            out["sm_mhz_by_gpu"] = [float(np.median(per[k])) for k in sorted(per)]
+            out["sm_mhz"] = float(min(out["sm_mhz_by_gpu"]))        # the slowest GPU sets the pace of the job
+        return out
 
 
 # ------------------------------------------------------------------------------------ CPU arm
@@ -182,6 +196,8 @@ def run_native(args):
         shape = (args.size, args.size, args.size * world)
     if shape is None:
         shape = (256, 256, 256 * world)
+    if os.environ.get("MG_BENCH_SHAPE"):          # experiments: any global shape, e.g. the N = 8 slab shape on 2 ranks
+        shape = tuple(int(v) for v in os.environ["MG_BENCH_SHAPE"].split(","))
     opt, grid, state, region, xyz = wl.build_c3(shape, (1, 1, world), (0, 0, rank), rank)
     halo = par.GpuHalo(grid, rank, world, dev) if world > 1 else None
     R = 3
@@ -204,12 +220,17 @@ def run_native(args):
         raise SystemExit("bench.py: the fused forward path does not cover the benchmark configuration")
     dt = 1e-3
 
-    def update_state():
+    # ghost planes a sweep really reads: sweep A takes Q; sweep B takes Q and, on this rectilinear grid, the four
+    # tau / q components of the k-direction flux; the adjoint sweeps take w and the k-block of the adjoint diffusion
+    # and no tau / q ghost plane at all (their Jacobian products are pointwise)
+    tauq_mask = par.GpuHalo.TAUQ_K_MASK_3D if not grid.isCurvilinear else None
+
+    def update_state(forward=True):
         if halo:
             halo.exchange(state, core.Q_CONSERVED, 5, R)
         state.update()
-        if halo:
-            halo.exchange(state, core.Q_FUSED_TAUQ, 9, R)
+        if halo and forward:
+            halo.exchange(state, core.Q_FUSED_TAUQ, 9, R, comps=tauq_mask)
 
     def forward_step(t, step):
         for stage in range(1, 5):
@@ -221,7 +242,7 @@ def run_native(args):
     def adjoint_step(t, step):
         for stage in range(4, 0, -1):
             state.checkpointLoad(stage - 1)
-            update_state()
+            update_state(forward=False)
             if halo:
                 halo.exchange(state, core.Q_ADJOINT, 5, R)
                 integ.substepAdjointPhase(1, t, dt, step, stage)
@@ -251,8 +272,9 @@ def run_native(args):
 
     # clocks / throttle reasons are sampled from the first warm-up step to the end of the timed region (the load is
     # the same in both; the timed region alone is shorter than nvidia-smi's start-up at small step counts)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(range(world)) if rank == 0 else None
+    if sampler:
+        sampler.start()
     t = 0.0
     for w in range(args.warmup):
         t = one_step(t, w)
@@ -292,8 +314,8 @@ def run_native(args):
     # Clock sampling: nvidia-smi may not have reported yet when the timed region is short.  Rank 0 decides how many
     # identical, untimed steps to append (same count on every rank: the halo exchange is collective).
     extra = 0
-    if len(sampler.rows) < 3:
-        extra = max(1, int(np.ceil(1.0 / max(wall / args.steps, 1e-3))))
+    if sampler and sampler.samples() < 3:
+        extra = max(1, int(np.ceil(1.5 / max(wall / args.steps, 1e-3))))
     if world > 1:
         import torch.distributed as dist
         ex = torch.tensor([extra], dtype=torch.int64, device=dev)
@@ -302,8 +324,10 @@ def run_native(args):
     for k in range(extra):
         t = one_step(t, args.warmup + args.steps + k)
     barrier()
-    clocks = sampler.stop()
-    clocks["window"] = "warm-up + timed steps" + (f" + {extra} identical untimed steps" if extra else "")
+    clocks = sampler.stop() if sampler else {}
+    if sampler:
+        clocks["window"] = "warm-up + timed steps" + (f" + {extra} identical untimed steps" if extra else "")
+        clocks["sampler"] = f"one nvidia-smi process on rank 0 polling {world} GPU(s) every {sampler.period_ms} ms"
 
     # max over ranks
     kernel_sum_ms = sum(v["ms"] for v in prof.values())
@@ -313,13 +337,12 @@ def run_native(args):
         import torch.distributed as dist
         # per-rank view: the ranks advance in lock step (two-neighbour rendez-vous before every sweep), so the job
         # runs at the pace of its slowest GPU; kernel time and SM clock of every rank show which one that is
-        mine = torch.tensor([total_ms / args.steps, kernel_sum_ms / args.steps, float(clocks.get("sm_mhz") or 0.0)],
-                            dtype=torch.float64, device=dev)
+        mine = torch.tensor([total_ms / args.steps, kernel_sum_ms / args.steps], dtype=torch.float64, device=dev)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         by_rank = {"ms_per_step": [round(float(a[0]), 3) for a in allr],
                    "profiled_kernel_ms_per_step": [round(float(a[1]), 3) for a in allr],
-                   "sm_mhz": [float(a[2]) for a in allr],
+                   "sm_mhz": clocks.get("sm_mhz_by_gpu"),
                    "note": "profiled kernels = launches on the main stream (the boundary k-chunks of an overlapped "
                            "exchange run on the halo stream and are not in this sum)"}
         tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -486,7 +509,7 @@ def run_c1(args):
     opt, grid, state, region, Q0 = wl.build_c1(args.c1_n)
     sol = gsol.Solver(region, state, 0.05, T, S)
     N = grid.nGridPoints
-    sampler = ClockSampler(0)
+    sampler = ClockSampler((0,))
     sampler.start()
     reps_w, reps = max(1, min(args.warmup, 1)), max(1, min(args.steps, 3))
     for _ in range(reps_w):

@@ -169,6 +169,10 @@ int mg_p2p_exchange(mg_p2p* h, void* owner, int field, int width);
  * interior k-chunks first (they read no ghost plane), then waits for the exchange and launches the first and the
  * last chunk -- the counterpart of "overlapped with interior stencil work" for fillGhostPoints */
 int mg_p2p_exchange_overlapped(mg_p2p* h, void* owner, int field, int width);
+/* exchange only the components selected by compMask (bit c = component c of the field): e.g. the tau / q field of
+ * the fused sweeps before sweep B on a rectilinear grid needs tau_13, tau_23, tau_33, q_3 in its ghost planes
+ * (mask 0x134), and the adjoint sweeps read no tau / q ghost plane at all.  overlapped != 0: on the halo stream. */
+int mg_p2p_exchange_masked(mg_p2p* h, void* owner, int field, int width, unsigned compMask, int overlapped);
 int mg_p2p_check(mg_p2p* h);
 int mg_p2p_destroy(mg_p2p* h);
 
@@ -280,6 +284,10 @@ int mg_rk4_substep_adjoint_phase(mg_region* r, int phase, double* time, double d
  * the configuration is covered) */
 int mg_region_set_fused(mg_region* r, int enable);
 int mg_region_uses_fused(mg_region* r, int mode);
+/* 1 when the RHS of every state is evaluated by the fused sweeps: either mg_region_uses_fused, or fused sweeps
+ * followed by the patch / source epilogue (states with SAT patches, sponges, cost-target / actuator patches, acoustic
+ * sources on one rank; the RK4 update is then a separate pointwise kernel). */
+int mg_region_uses_fused_rhs(mg_region* r, int mode);
 /* number of hot-path kernels this library has launched since mg_init (bench accounting) */
 long long mg_kernel_launch_count(void);
 /* the CUDA stream (cudaStream_t) all kernels of this rank are launched on, for event timing */

@@ -89,6 +89,7 @@ SIGNATURES = {
     "mg_p2p_connect": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "mg_p2p_exchange": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "mg_p2p_exchange_overlapped": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "mg_p2p_exchange_masked": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_uint, C.c_int]),
     "mg_p2p_check": (C.c_int, [_P]),
     "mg_p2p_destroy": (C.c_int, [_P]),
     "mg_state_create": (C.c_int, [_P, C.POINTER(Options), C.POINTER(_P)]),
@@ -125,6 +126,7 @@ SIGNATURES = {
     "mg_rk4_substep": (C.c_int, [_P, C.c_int, _D, C.c_double, C.c_int, C.c_int, C.c_int]),
     "mg_rk4_substep_adjoint_phase": (C.c_int, [_P, C.c_int, _D, C.c_double, C.c_int, C.c_int]),
     "mg_region_set_fused": (C.c_int, [_P, C.c_int]),
+    "mg_region_uses_fused_rhs": (C.c_int, [_P, C.c_int]),
     "mg_region_uses_fused": (C.c_int, [_P, C.c_int]),
 }
 

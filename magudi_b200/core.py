@@ -530,6 +530,10 @@ class Region:
     def usesFused(self, mode=FORWARD):
         return bool(L.lib().mg_region_uses_fused(self._h, int(mode)))
 
+    def usesFusedRhs(self, mode=FORWARD):
+        """The RHS comes from the fused sweeps (possibly followed by the patch / source epilogue)."""
+        return bool(L.lib().mg_region_uses_fused_rhs(self._h, int(mode)))
+
     def cleanup(self):
         if self._h is not None:
             L.load().mg_region_destroy(self._h)

@@ -45,7 +45,10 @@ cudaStream_t mg_halo_stream() {
   }
   return g_haloStream;
 }
-void mg_halo_set_pending(cudaEvent_t ev) { g_haloPending = ev; g_haloIsPending = true; }
+double g_haloPendingBytes = 0.0;
+void mg_halo_set_pending(cudaEvent_t ev, double bytesPerSide) { g_haloPending = ev; g_haloIsPending = true; g_haloPendingBytes = bytesPerSide; }
+bool mg_halo_is_pending() { return g_haloIsPending; }
+double mg_halo_pending_bytes() { return g_haloIsPending ? g_haloPendingBytes : 0.0; }
 bool mg_halo_take_pending(cudaEvent_t* ev) {
   if (!g_haloIsPending) return false;
   *ev = g_haloPending;
@@ -520,10 +523,8 @@ int mg_state_set(mg_state* s, int field, const double* host) {
 // The fused sweeps keep the dependent variables in registers / in the compact tau-q field: the reference-layout
 // arrays (specific volume ... heat flux) are materialised on demand, before anything reads them.
 static int refresh_dependents(mg_state* s, int field) {
-  if (field >= MG_Q_SPECIFIC_VOLUME && field <= MG_Q_HEAT_FLUX && !s->dependentValid) {
-    if (!s->grid->updated) MG_FAIL("dependent variables requested before mg_grid_update");
-    MG_TRY(mg_state_update_impl(s, nullptr));
-  }
+  if (field >= MG_Q_SPECIFIC_VOLUME && field <= MG_Q_HEAT_FLUX && !s->dependentValid)
+    MG_TRY(mg_state_ensure_dependents(s));
   return 0;
 }
 int mg_state_get(mg_state* s, int field, double* host) {
@@ -662,7 +663,7 @@ int mg_state_add_acoustic_source(mg_state* s, const double location[3], double a
 int mg_state_update(mg_state* s) {
   if (!s) MG_FAIL("mg_state_update: null handle");
   if (!s->grid->updated) MG_FAIL("mg_state_update: grid metrics have not been computed");
-  if (s->useFused && mg_fused_supported(s, MG_FORWARD)) return mg_fused_sweepA(s);
+  if (mg_state_uses_fused_rhs(s, MG_FORWARD)) return mg_fused_sweepA(s);
   return mg_state_update_impl(s, nullptr);
 }
 
@@ -810,6 +811,11 @@ int mg_region_uses_fused(mg_region* r, int mode) {
   for (mg_state* s : r->states) if (!mg_fused_supported(s, mode)) return 0;
   return 1;
 }
+int mg_region_uses_fused_rhs(mg_region* r, int mode) {
+  if (!r || !r->fused) return 0;
+  for (mg_state* s : r->states) if (!mg_state_uses_fused_rhs(s, mode)) return 0;
+  return 1;
+}
 static bool region_has_interfaces(const mg_region* r) {
   for (const mg_state* s : r->states) if (mg_state_has_interfaces(s)) return true;
   return false;
@@ -848,7 +854,7 @@ int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep
     t = *time;
     MG_TRY(mg_rk4_substep_impl(s, mode, &t, dt, timestep, stage));
     if (updateStates && mode == MG_FORWARD) {
-      if (s->useFused && mg_fused_supported(s, MG_FORWARD)) MG_TRY(mg_fused_sweepA(s));
+      if (mg_state_uses_fused_rhs(s, MG_FORWARD)) MG_TRY(mg_fused_sweepA(s));
       else MG_TRY(mg_state_update_impl(s, nullptr));
     }
   }

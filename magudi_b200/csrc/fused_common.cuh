@@ -42,6 +42,7 @@ struct FusedArgs {
   int ghostK;                   // ghost planes below plane 0 in storage (TMA coordinates count from the storage start)
   int kBeg, kEnd, kChunk;
   int zOff, zMul;               // k-chunk of a block = zOff + blockIdx.z * zMul (interior / boundary chunk launches)
+  int overlapPays;              // choose_chunks: splitting the sweep around the pending exchange is the cheaper plan
   int curvilinear, viscous;
   DirInfo dir[3];
   LineOp D[3], Dd[3], Dt[3];    // first derivative, dissipation, dissipation transpose
@@ -490,13 +491,34 @@ int choose_chunks(FusedArgs* a, int R, int residentPerSm, int tileX = TX, int ti
     if (forced > 0) best = forced;
     else {
       const double slots = (double)mg_num_sms() * residentPerSm;
-      double bestScore = -1.0;
+      // When an overlapped halo exchange is in flight the sweep may run as TWO launches (launch_split: interior
+      // chunks at once, the first and the last chunk behind the exchange; the second launch fills most of the tail
+      // of the first (measured: 512 x 512 x 64 slabs run fastest as 1 interior + 2 boundary chunks)) so that the exchange, E microseconds for its payload,
+      // hides behind the interior chunks; or as one launch after the exchange.  Costs in CTA-plane units (one
+      // plane of one wave ~ 5 us on B200 for these sweeps); MG_CHUNKS / MG_OVERLAP override the choice.
+      const bool pending = mg_halo_is_pending() && a->kBeg == 0;
+      const double tau = 5.0;                                           // us per plane and wave
+      const double E = pending ? (30.0 + mg_halo_pending_bytes() / 0.4e6) / tau : 0.0;
+      double bestCost = 1e300;
       for (int n = 1; n <= 32 && n * 4 * R <= a->nz; ++n) {
         const int chunk = (a->nz + n - 1) / n;
+        const double perCta = chunk + 0.6 * 2 * R;               // planes a CTA streams (warm-up planes are cheaper)
         const double waves = tilesXY * (double)n / slots;
-        const double fill = waves / ceil(waves);
-        const double score = fill * chunk / (chunk + 0.6 * 2 * R);
-        if (score > bestScore + 1e-9) { bestScore = score; best = n; }
+        double cost = ceil(waves) * perCta + E;                  // one launch, after the exchange
+        if (pending && n >= 3 && chunk >= R) {
+          const double interior = tilesXY * (double)(n - 2) / slots * perCta;
+          const double splitCost = ceil(waves) * perCta + (E > interior ? E - interior : 0.0);
+          if (splitCost < cost) cost = splitCost;
+        }
+        if (cost < bestCost - 1e-9) { bestCost = cost; best = n; }
+      }
+      a->overlapPays = 1;
+      if (pending) {
+        const int chunk = (a->nz + best - 1) / best;
+        const double perCta = chunk + 0.6 * 2 * R, waves = tilesXY * (double)best / slots;
+        const double interior = tilesXY * (double)(best - 2) / slots * perCta;
+        a->overlapPays = (best >= 3 && chunk >= R &&
+                          ceil(waves) * perCta + (E > interior ? E - interior : 0.0) < ceil(waves) * perCta + E) ? 1 : 0;
       }
     }
   }
@@ -525,7 +547,7 @@ int launch_split(FusedArgs& a, int nChunks, int R, F&& go) {
   const bool exchange = mg_halo_take_pending(&ev);
   MG_TRY(mg_halo_wait_boundary());          // the previous sweep's boundary chunks (halo stream) must be done
   if (!exchange) return go(a, nChunks, mg_stream());
-  const bool split = nChunks >= 3 && a.kChunk >= R && a.kBeg == 0;
+  const bool split = nChunks >= 3 && a.kChunk >= R && a.kBeg == 0 && (a.overlapPays || mg_tuning_get("MG_CHUNKS", 0) > 0);
   if (!split) {
     MG_CUDA(cudaStreamWaitEvent(mg_stream(), ev, 0));
     return go(a, nChunks, mg_stream());

@@ -83,8 +83,11 @@ int mg_state_rhs_adjoint_general(mg_state* s);
 int mg_state_rhs_linearized_general(mg_state* s);
 int mg_state_compute_rhs_impl(mg_state* s, int mode);
 int mg_state_rhs_pre(mg_state* s, int mode);
-int mg_state_rhs_post(mg_state* s, int mode);
-int mg_state_adjoint_finish(mg_state* s, MgField* src, double sign);
+int mg_state_rhs_post(mg_state* s, int mode, bool alreadyTimesJacobian = false);
+int mg_state_adjoint_finish(mg_state* s, MgField* src, double sign, bool timesJacobian = false);
+int mg_state_dependents_from_fused(mg_state* s);
+int mg_state_ensure_dependents(mg_state* s);
+bool mg_state_uses_fused_rhs(const mg_state* s, int mode);
 void mg_rk4_set_times(mg_state* s, int mode, double time, double dt, int stage);
 int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int timestep, int stage);
 int mg_state_cfl_dt_impl(mg_state* s, int wantDt, double given, double* result);

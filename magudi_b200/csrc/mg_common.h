@@ -126,8 +126,10 @@ cudaStream_t mg_stream();
 // Second (high-priority) stream for overlapped halo exchanges, and the event of the last exchange still in
 // flight on it: the next fused sweep takes it (launch_split), anything else waits through mg_halo_wait_pending.
 cudaStream_t mg_halo_stream();
-void mg_halo_set_pending(cudaEvent_t ev);
+void mg_halo_set_pending(cudaEvent_t ev, double bytesPerSide = 0.0);
+double mg_halo_pending_bytes();   // payload per face of the exchange in flight (sizes the overlap decision)
 bool mg_halo_take_pending(cudaEvent_t* ev);
+bool mg_halo_is_pending();
 int mg_halo_wait_pending();       // main stream waits for the exchange AND the boundary chunks in flight
 int mg_halo_mark_boundary();      // record "boundary chunks enqueued" on the halo stream
 int mg_halo_wait_boundary();      // main stream waits for them

@@ -236,7 +236,7 @@ int mg_p2p_connect(mg_p2p* h, int side, const void* peerHandle, int sameAsOther)
 }
 
 static int p2p_exchange_on(mg_p2p* h, void* owner, int field, int width, cudaStream_t st);
-static int p2p_exchange_field(mg_p2p* h, const MgField* f, int width, cudaStream_t st);
+static int p2p_exchange_field(mg_p2p* h, const MgField* f, int width, cudaStream_t st, unsigned compMask = 0xffffffffu);
 
 // Exchange `width` ghost planes of a field with both k-neighbours.  Asynchronous on the library stream.
 int mg_p2p_exchange(mg_p2p* h, void* owner, int field, int width) {
@@ -244,24 +244,50 @@ int mg_p2p_exchange(mg_p2p* h, void* owner, int field, int width) {
   return p2p_exchange_on(h, owner, field, width, mg_stream());
 }
 
+static int p2p_overlapped(mg_p2p* h, void* owner, int field, int width, unsigned compMask);
+
+// The same for a subset of the field's components (bit c of compMask = component c): a consumer that reads only some
+// components in the ghost planes -- the k-direction flux of sweep B on a rectilinear grid takes tau_13, tau_23,
+// tau_33 and q_3 of the nine tau / q components -- moves only those.
+int mg_p2p_exchange_masked(mg_p2p* h, void* owner, int field, int width, unsigned compMask, int overlapped) {
+  if (!h) MG_FAIL("mg_p2p_exchange_masked: null handle");
+  if (overlapped && mg_halo_stream() != mg_stream()) return p2p_overlapped(h, owner, field, width, compMask);
+  MG_TRY(mg_halo_wait_pending());
+  MgField* f = mg_lookup_field(h->grid, owner, field);
+  if (!f || !f->p) MG_FAIL("mg_p2p_exchange_masked: unknown field");
+  return p2p_exchange_field(h, f, width, mg_stream(), compMask);
+}
+
 // The same exchange on the library's halo stream, ordered after everything enqueued so far on the main stream:
 // it overlaps with the interior k-chunks of the next fused sweep, which takes the completion event
 // (fused_common.cuh: launch_split); any other consumer waits for it in mg_synchronize / mg_p2p_exchange.
 int mg_p2p_exchange_overlapped(mg_p2p* h, void* owner, int field, int width) {
   if (!h) MG_FAIL("mg_p2p_exchange_overlapped: null handle");
+  if (mg_halo_stream() == mg_stream()) return mg_p2p_exchange(h, owner, field, width);
+  return p2p_overlapped(h, owner, field, width, 0xffffffffu);
+}
+
+static int p2p_overlapped(mg_p2p* h, void* owner, int field, int width, unsigned compMask) {
   cudaStream_t hs = mg_halo_stream();
-  if (hs == mg_stream()) return mg_p2p_exchange(h, owner, field, width);
   if (!h->evProduced) {
     MG_CUDA(cudaEventCreateWithFlags(&h->evProduced, cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) MG_CUDA(cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming));
   }
   MG_CUDA(cudaEventRecord(h->evProduced, mg_stream()));
   MG_CUDA(cudaStreamWaitEvent(hs, h->evProduced, 0));
-  MG_TRY(p2p_exchange_on(h, owner, field, width, hs));
+  double bytes = 0.0;
+  {
+    MgField* f = mg_lookup_field(h->grid, owner, field);
+    if (!f || !f->p) MG_FAIL("mg_p2p_exchange: unknown field");
+    MG_TRY(p2p_exchange_field(h, f, width, hs, compMask));
+    int n = 0;
+    for (int c = 0; c < f->nComp && c < 32; ++c) n += (compMask >> c) & 1u;
+    bytes = (double)n * width * (double)h->grid->plane * sizeof(double);
+  }
   cudaEvent_t done = h->evDone[h->nextDone];
   h->nextDone = (h->nextDone + 1) % 4;
   MG_CUDA(cudaEventRecord(done, hs));
-  mg_halo_set_pending(done);     // a later exchange on the same stream supersedes an earlier one
+  mg_halo_set_pending(done, bytes);     // a later exchange on the same stream supersedes an earlier one
   return 0;
 }
 
@@ -293,8 +319,19 @@ int mg_p2p_exchange_view(mg_p2p* h, const double* comp0, size_t compStride, int 
   return 0;
 }
 
-static int p2p_exchange_field(mg_p2p* h, const MgField* f, int width, cudaStream_t st) {
+static int p2p_exchange_field(mg_p2p* h, const MgField* fAll, int width, cudaStream_t st, unsigned compMask) {
   mg_grid* g = h->grid;
+  // compMask selects the components whose ghost planes the consumer reads (bit c = component c)
+  int comps[MG_P2P_MAX_COMP * 2];
+  int nSel = 0;
+  for (int c = 0; c < fAll->nComp && c < 32; ++c)
+    if ((compMask >> c) & 1u) {
+      if (nSel >= MG_P2P_MAX_COMP) MG_FAIL("mg_p2p_exchange: too many components");
+      comps[nSel++] = c;
+    }
+  struct View { const MgField* f; const int* comps; int nComp; double* comp(int i) const { return f->comp(comps[i]); } };
+  const View view{fAll, comps, nSel};
+  const View* f = &view;
   const size_t chunk = g->plane * (size_t)width;
   if (width > g->gk || width > g->localSize[2]) MG_FAIL("mg_p2p_exchange: width exceeds ghost capacity");
   if (f->nComp > MG_P2P_MAX_COMP || chunk * (size_t)f->nComp > h->capacity)

@@ -1035,7 +1035,7 @@ int mg_functional_acoustic_noise_impl(mg_state* s, double timeRampFactor, double
   mg_grid* g = s->grid;
   if (!s->meanPressure.p) MG_FAIL("acoustic noise: the mean pressure has not been set");
   if (!g->targetMollifier.p) MG_FAIL("acoustic noise: the target mollifier has not been set");
-  if (!s->dependentValid) MG_TRY(mg_state_update_impl(s, nullptr));
+  MG_TRY(mg_state_ensure_dependents(s));
   MG_TRY(quadrature(s, MG_PATCH_COST_TARGET, 1, s->pressure.comp(0), s->meanPressure.comp(0),
                     g->targetMollifier.comp(0), value));
   *value *= timeRampFactor;
@@ -1046,7 +1046,7 @@ int mg_functional_acoustic_noise_forcing_impl(mg_state* s, double timeRampFactor
   mg_grid* g = s->grid;
   if (!s->meanPressure.p) MG_FAIL("acoustic noise: the mean pressure has not been set");
   if (!g->targetMollifier.p) MG_FAIL("acoustic noise: the target mollifier has not been set");
-  if (!s->dependentValid) MG_TRY(mg_state_update_impl(s, nullptr));
+  MG_TRY(mg_state_ensure_dependents(s));
   for (mg_patch* p : s->patches) {
     if (p->type != MG_PATCH_COST_TARGET || p->nPatchPoints <= 0) continue;
     double* out = nullptr;
@@ -1099,7 +1099,7 @@ int mg_functional_actuator_gradient_impl(mg_patch* p, double timeRampFactor, dou
 
 // computePressureDrag (reference src/PressureDragImpl.f90:61-132); local to this rank, the caller reduces
 int mg_functional_pressure_drag_impl(mg_state* s, const double direction[3], double* value) {
-  if (!s->dependentValid) MG_TRY(mg_state_update_impl(s, nullptr));
+  MG_TRY(mg_state_ensure_dependents(s));
   static double* partial = nullptr;
   if (!partial) MG_CUDA(cudaMalloc(&partial, DRAG_BLOCKS * sizeof(double)));
   double sum = 0.0;
@@ -1121,7 +1121,7 @@ int mg_functional_pressure_drag_impl(mg_state* s, const double direction[3], dou
 
 // computePressureDragAdjointForcing (reference :148-267) into the COST_TARGET patches' "adjointForcing"
 int mg_functional_pressure_drag_forcing_impl(mg_state* s, const double direction[3]) {
-  if (!s->dependentValid) MG_TRY(mg_state_update_impl(s, nullptr));
+  MG_TRY(mg_state_ensure_dependents(s));
   for (mg_patch* p : s->patches) {
     if (p->type != MG_PATCH_COST_TARGET || p->nPatchPoints <= 0) continue;
     DragArgs a;

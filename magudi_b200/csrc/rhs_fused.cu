@@ -1286,12 +1286,13 @@ static bool dir_fits_tile(const mg_grid* g, int d, int T, int R, int mode) {
   return true;
 }
 
-int mg_fused_supported(const mg_state* s, int mode) {
+// The fused sweeps can evaluate the RHS of this state (interior scheme + closures); patches and sources, if any,
+// are applied afterwards by the caller (state.cu: fused RHS + patch epilogue).
+int mg_fused_rhs_supported(const mg_state* s, int mode) {
   const mg_grid* g = s->grid;
   if (mode != MG_FORWARD && mode != MG_ADJOINT) return 0;
   if (g->nD < 2) return 0;
   if (g->iblank) return 0;
-  if (!s->patches.empty() || !s->acousticSources.empty()) return 0;
   if (g->nD == 3 && g->periodicityType[2] != MG_PERIODIC_PLANE) return 0;
   SchemeInfo si;
   if (!scheme_of(g, &si)) return 0;
@@ -1299,6 +1300,12 @@ int mg_fused_supported(const mg_state* s, int mode) {
   for (int d = 0; d < 2; ++d)
     if (!dir_fits_tile(g, d, TX, si.R, mode)) return 0;
   return 1;
+}
+
+// ... and can also fold the RK4 substep into the last sweep: nothing may touch the RHS after the sweeps
+int mg_fused_supported(const mg_state* s, int mode) {
+  if (!s->patches.empty() || !s->acousticSources.empty()) return 0;
+  return mg_fused_rhs_supported(s, mode);
 }
 
 int mg_fused_alloc(mg_state* s) {

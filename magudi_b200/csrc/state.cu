@@ -298,6 +298,7 @@ __global__ void k_linearized_flux(LinArgs a) {
 }
 
 struct AdjFinishArgs {
+  const double* jacScale;   // when set the contribution is multiplied by 1/J (RHS already holds R/J: fused sweeps)
   const double *Q, *v, *u;
   const double* d;    // derivative of adjoint diffusion: component c + (NU-1)*j
   double* rhs;
@@ -331,9 +332,10 @@ __global__ void k_adjoint_finish(AdjFinishArgs a) {
     t[i] = v * t[i] - u[i] * t[ND];
     ut = (i == 0) ? u[0] * t[0] : ut + u[i] * t[i];
   }
+  const double f = a.jacScale ? a.sign * a.jacScale[p] : a.sign;
 #pragma unroll
-  for (int c = 0; c < ND + 1; ++c) a.rhs[(size_t)(c + 1) * a.cs + p] -= a.sign * t[c];
-  a.rhs[p] += a.sign * (v * a.Q[(size_t)(ND + 1) * a.csQ + p] * t[ND] + ut);
+  for (int c = 0; c < ND + 1; ++c) a.rhs[(size_t)(c + 1) * a.cs + p] -= f * t[c];
+  a.rhs[p] += f * (v * a.Q[(size_t)(ND + 1) * a.csQ + p] * t[ND] + ut);
 }
 
 __global__ void k_mul_jacobian(double* rhs, size_t cs, int nU, const double* jac, size_t N) {
@@ -628,6 +630,59 @@ int mg_state_update_impl(mg_state* s, const MgField* Qoverride) {
   return 0;
 }
 
+// The fused sweep A keeps the stress tensor as its nD(nD+1)/2 unique entries followed by the heat flux: expand it
+// into the reference layout (stressTensor(N, nD^2), heatFlux(N, nD)) for the patch kernels and the getters.
+template <int ND>
+__global__ void k_expand_tauq(const double* tq, size_t cs, double* tau, double* q, size_t N) {
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  constexpr int NTAU = ND * (ND + 1) / 2;
+#pragma unroll
+  for (int l = 0; l < ND; ++l)
+#pragma unroll
+    for (int c = 0; c < ND; ++c) {
+      const int r0 = l < c ? l : c, c0 = l < c ? c : l;
+      tau[(size_t)(l + ND * c) * cs + p] = tq[(size_t)(r0 * ND - r0 * (r0 - 1) / 2 + (c0 - r0)) * cs + p];
+    }
+#pragma unroll
+  for (int d = 0; d < ND; ++d) q[(size_t)d * cs + p] = tq[(size_t)(NTAU + d) * cs + p];
+}
+
+// Dependent variables of the current state from what the fused sweep A already produced: one pointwise kernel for
+// (v, u, p, T, mu, lambda, kappa) and one that expands tau / q -- no derivative is taken again.
+int mg_state_dependents_from_fused(mg_state* s) {
+  mg_grid* g = s->grid;
+  if (!s->fusedValid) MG_FAIL("dependent variables from the fused sweep: sweep A has not run on the current state");
+  const MgField& Q = s->Q[s->cur];
+  const size_t N = g->N;
+  cudaStream_t st = mg_stream();
+  PtrSet a;
+  a.Q = Q.comp(0);
+  a.csQ = Q.compStride;
+  a.v = s->specificVolume.comp(0);
+  a.u = s->velocity.comp(0);
+  a.p = s->pressure.comp(0);
+  a.T = s->temperature.comp(0);
+  a.mu = s->opt.viscosityOn ? s->mu.comp(0) : nullptr;
+  a.lam = s->opt.viscosityOn ? s->lambda.comp(0) : nullptr;
+  a.kap = s->opt.viscosityOn ? s->kappa.comp(0) : nullptr;
+  a.cs = s->velocity.compStride;
+  a.N = N;
+  const PhysParams pp = s->phys();
+  MG_TRY(dispatch_nd(s->nD, [&](auto nd) {
+    { k_dependent<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(a, pp); mg_count_launches(1); }
+    if (s->opt.viscosityOn) {
+      k_expand_tauq<decltype(nd)::value><<<nblocks(N), 256, 0, st>>>(s->tauq.comp(0), s->tauq.compStride,
+                                                                     s->stressTensor.comp(0), s->heatFlux.comp(0), N);
+      mg_count_launches(1);
+    }
+    return 0;
+  }));
+  MG_CUDA(cudaGetLastError());
+  s->dependentValid = true;
+  return 0;
+}
+
 // addDissipation (reference src/RhsHelperImpl.f90:10-87)
 static int add_dissipation_general(mg_state* s, int mode) {
   mg_grid* g = s->grid;
@@ -695,7 +750,7 @@ int mg_state_rhs_forward_general(mg_state* s) {
 // adjointFirstDerivative of src(:, :, j) along j (into scratch A), summed over j, followed by the change of
 // variables back to the conserved adjoint; rhs -/+= sign * result (reference src/RhsHelperImpl.f90:528-570,
 // :213-247, :987-1023).
-int mg_state_adjoint_finish(mg_state* s, MgField* src, double sign) {
+int mg_state_adjoint_finish(mg_state* s, MgField* src, double sign, bool timesJacobian) {
   mg_grid* g = s->grid;
   const size_t N = g->N;
   const int nD = s->nD, nU = s->nU;
@@ -705,6 +760,7 @@ int mg_state_adjoint_finish(mg_state* s, MgField* src, double sign) {
     MG_TRY(mg_grid_apply(g, g->adjointFirstDerivative[j], src->comp((nU - 1) * j), src->compStride,
                          A.comp((nU - 1) * j), A.compStride, nU - 1));
   AdjFinishArgs f;
+  f.jacScale = timesJacobian ? g->jacobian.comp(0) : nullptr;
   f.Q = Q.comp(0);
   f.csQ = Q.compStride;
   f.v = s->specificVolume.comp(0);
@@ -888,7 +944,7 @@ int mg_state_rhs_pre(mg_state* s, int mode) {
 
 // ... and from the viscous interface adjoint penalty on (src/RegionImpl.f90:1960-2027): x 1/J, patches, sources,
 // hole masking.
-int mg_state_rhs_post(mg_state* s, int mode) {
+int mg_state_rhs_post(mg_state* s, int mode, bool alreadyTimesJacobian) {
   mg_grid* g = s->grid;
   const size_t N = g->N;
   cudaStream_t st = mg_stream();
@@ -898,7 +954,8 @@ int mg_state_rhs_post(mg_state* s, int mode) {
     MG_TRY(mg_interfaces_adjoint_sources(s, &g->scratchB));
     MG_TRY(mg_state_adjoint_finish(s, &g->scratchB, -1.0));
   }
-  { k_mul_jacobian<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), s->rhs.compStride, s->nU, g->jacobian.comp(0), N); mg_count_launches(1); }
+  if (!alreadyTimesJacobian)
+    { k_mul_jacobian<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), s->rhs.compStride, s->nU, g->jacobian.comp(0), N); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   MG_TRY(mg_patches_apply(s, mode));
   if (mode == MG_FORWARD) {
@@ -923,6 +980,65 @@ int mg_state_rhs_post(mg_state* s, int mode) {
   return 0;
 }
 
+static bool fused_rhs_then_patches(const mg_state* s, int mode);
+
+// true when computeRhs of this state runs the fused sweeps (with the RK4 substep folded in, or followed by the patch
+// epilogue): then state%update is sweep A, and the reference-layout dependent variables are expanded on demand
+bool mg_state_uses_fused_rhs(const mg_state* s, int mode) {
+  return s->useFused && (mg_fused_supported(s, mode) || fused_rhs_then_patches(s, mode));
+}
+
+// Dependent variables in the reference layout, whichever path is active: from the fused sweep A when that is what
+// state%update runs for this state, else the operator-by-operator update.
+int mg_state_ensure_dependents(mg_state* s) {
+  if (s->dependentValid) return 0;
+  if (!s->grid->updated) MG_FAIL("dependent variables requested before mg_grid_update");
+  if (mg_state_uses_fused_rhs(s, MG_FORWARD)) {
+    if (!s->fusedValid) MG_TRY(mg_fused_sweepA(s));
+    return mg_state_dependents_from_fused(s);
+  }
+  return mg_state_update_impl(s, nullptr);
+}
+
+// Cartesian viscous fluxes at the patches that take them (far-field SAT), from the dependent variables
+static int collect_patch_viscous_fluxes(mg_state* s) {
+  mg_grid* g = s->grid;
+  const int nD = s->nD, nU = s->nU;
+  if (s->viscFluxCart.nComp < nU * nD) MG_TRY(mg_field_alloc(g, nU * nD, &s->viscFluxCart));
+  FluxArgs a;
+  const MgField& Q = s->Q[s->cur];
+  a.Q = Q.comp(0);
+  a.csQ = Q.compStride;
+  a.u = s->velocity.comp(0);
+  a.pr = s->pressure.comp(0);
+  a.tau = s->stressTensor.comp(0);
+  a.q = s->heatFlux.comp(0);
+  a.m = g->metrics.comp(0);
+  a.Fhat = g->scratchA.comp(0);
+  a.Fv = s->viscFluxCart.comp(0);
+  a.cs = g->scratchA.compStride;
+  a.N = g->N;
+  a.viscous = 1;
+  a.curvilinear = g->isCurvilinear;
+  MG_TRY(dispatch_nd(nD, [&](auto nd) {
+    { k_flux<decltype(nd)::value><<<nblocks(g->N), 256, 0, mg_stream()>>>(a); mg_count_launches(1); }
+    return 0;
+  }));
+  MG_CUDA(cudaGetLastError());
+  return mg_patches_collect_viscous(s);
+}
+
+// The RHS of a state WITH patches / sources whose interior scheme the fused sweeps cover: two (forward) or three
+// (adjoint) sweeps produce R / J, then the penalties act on the patch points exactly as after the operator-by-operator
+// evaluation (they are applied after the 1/J multiplication, reference src/RegionImpl.f90:1969-1995).
+static bool fused_rhs_then_patches(const mg_state* s, int mode) {
+  if (!s->useFused || !mg_fused_rhs_supported(s, mode) || mg_fused_supported(s, mode)) return false;
+  if (mg_state_has_interfaces(s)) return false;           // staged over the region's grids (mg_region_compute_rhs)
+  const mg_grid* g = s->grid;
+  if (g->procDims[0] * g->procDims[1] * g->procDims[2] != 1) return false;   // the caller of the fused sweeps owns the halos
+  return mg_tuning_get("MG_FUSED_PATCHES", 1) != 0;
+}
+
 int mg_state_compute_rhs_impl(mg_state* s, int mode) {
   mg_grid* g = s->grid;
   if (!g->updated) MG_FAIL("computeRhs: grid metrics have not been computed (mg_grid_update)");
@@ -934,12 +1050,38 @@ int mg_state_compute_rhs_impl(mg_state* s, int mode) {
     MG_TRY(mg_fused_adjoint1(s));
     return mg_fused_adjoint2(s, 0, 1, 0.0);
   }
+  if (fused_rhs_then_patches(s, mode)) {
+    if (!s->fusedValid) MG_TRY(mg_fused_sweepA(s));
+    if (mode == MG_FORWARD) {
+      MG_TRY(mg_fused_sweepB(s, 0, 0, 0.0));
+    } else {
+      MG_TRY(mg_fused_adjoint1(s));
+      MG_TRY(mg_fused_adjoint2(s, 0, 1, 0.0));
+    }
+    if (!s->patches.empty()) {
+      // the patch kernels read the dependent variables in the reference layout: expand what sweep A produced
+      MG_TRY(mg_state_ensure_dependents(s));
+      if (mode == MG_FORWARD && s->keepViscousFluxes && s->opt.viscosityOn) MG_TRY(collect_patch_viscous_fluxes(s));
+      if (mode == MG_ADJOINT && s->opt.viscosityOn && mg_patches_have_farfield(s)) {
+        // addFarFieldAdjointPenalty (reference src/RhsHelperImpl.f90:89-250), joined after the 1/J multiplication
+        bool anyViscousPenalty = false;
+        for (const mg_patch* p : s->patches)
+          anyViscousPenalty = anyViscousPenalty || (p->type == MG_PATCH_FARFIELD && p->viscousPenaltyAmount != 0.0);
+        if (anyViscousPenalty) {
+          MG_TRY(mg_field_zero(g, &g->scratchB));
+          MG_TRY(mg_patches_farfield_adjoint_sources(s, &g->scratchB));
+          MG_TRY(mg_state_adjoint_finish(s, &g->scratchB, -1.0, true));
+        }
+      }
+    }
+    return mg_state_rhs_post(s, mode, true);
+  }
   if (mg_state_has_interfaces(s)) {
     if (mode == MG_LINEARIZED) MG_FAIL("computeRhs: the LINEARIZED mode of block-interface patches is not implemented");
     MG_FAIL("computeRhs: a state with block-interface patches must be evaluated through its region (mg_region_compute_rhs)");
   }
   MG_TRY(mg_state_rhs_pre(s, mode));
-  return mg_state_rhs_post(s, mode);
+  return mg_state_rhs_post(s, mode, false);
 }
 
 // substepForward / substepAdjoint (reference src/RK4IntegratorImpl.f90:65-270).  The state update that

@@ -137,17 +137,24 @@ class GpuHalo:
             same = 1 if (side == 1 and prev is not None and prev == nxt) else 0
             check(lib.mg_p2p_connect(h, side, hb, same))
 
-    def exchange(self, owner, field, ncomp, width=3, overlap=None):
+    # tau / q components of the fused sweeps (compact layout t11 t12 t13 t22 t23 t33 q1 q2 q3) that sweep B reads in
+    # the k ghost planes of a RECTILINEAR 3-D grid: the k-direction flux takes t13, t23, t33, q3
+    TAUQ_K_MASK_3D = (1 << 2) | (1 << 4) | (1 << 5) | (1 << 8)
+
+    def exchange(self, owner, field, ncomp, width=3, overlap=None, comps=None):
         """Exchange ``width`` ghost planes of a library field with both k-neighbours.  ``overlap`` (default:
         environment ``MG_OVERLAP``, on) runs a state-field exchange on the library's halo stream so that the next
         fused sweep computes its interior k-chunks while the planes travel; grid fields (setup) are exchanged
-        in stream order."""
+        in stream order.  ``comps``: bit mask of the components the consumer reads in the ghost planes (default all)."""
         lib = L.lib()
         g = self.grid._h
         oh = owner._h if owner is not None else None
         if overlap is None:
             overlap = owner is not None and os.environ.get("MG_OVERLAP", "1") != "0"
         if self._p2p is not None:
+            if comps is not None:
+                check(lib.mg_p2p_exchange_masked(self._p2p, oh, field, width, int(comps), int(bool(overlap))))
+                return
             fn = lib.mg_p2p_exchange_overlapped if overlap else lib.mg_p2p_exchange
             check(fn(self._p2p, oh, field, width))
             return

@@ -61,9 +61,12 @@ def main():
     sync()
     tx = sorted(e[0].elapsed_time(e[1]) * 1e3 for e in evs)
     ta = sorted(e[1].elapsed_time(e[2]) * 1e3 for e in evs)
+    allm = [None] * world
+    dist.all_gather_object(allm, (round(tx[reps // 2], 1), round(tx[0], 1), round(ta[reps // 2], 1)))
     if rank == 0:
         print(f"halo_bench[{halo.mode}] interleaved: exchange median {tx[reps // 2]:.1f} us (min {tx[0]:.1f}, "
               f"max {tx[-1]:.1f}); sweep A median {ta[reps // 2]:.1f} us (min {ta[0]:.1f}, max {ta[-1]:.1f})")
+        print(f"halo_bench[{halo.mode}] by rank (exchange median, exchange min, sweep A median) us: {allm}")
     halo.check()
     halo.close()
     dist.barrier()

@@ -35,12 +35,13 @@ def run(shape, world, rank, dev, steps=2):
     assert region.usesFused(mb.FORWARD)
     integ = mb.RK4Integrator(region)
 
-    def update():
+    def update(forward=True):
+        # as bench.py: only the ghost planes the next sweep reads (sweep B: four tau / q components; adjoint: none)
         if halo:
             halo.exchange(state, core.Q_CONSERVED, 5, R)
         state.update()
-        if halo:
-            halo.exchange(state, core.Q_FUSED_TAUQ, 9, R)
+        if halo and forward:
+            halo.exchange(state, core.Q_FUSED_TAUQ, 9, R, comps=par.GpuHalo.TAUQ_K_MASK_3D)
 
     update()
     t = 0.0
@@ -54,7 +55,7 @@ def run(shape, world, rank, dev, steps=2):
     state.adjointVariables = Wg[:, :, k0:k0 + nz].reshape(-1, 5, order="F")
     assert region.usesFused(mb.ADJOINT)
     for stage in range(4, 0, -1):
-        update()
+        update(forward=False)
         if halo:
             halo.exchange(state, core.Q_ADJOINT, 5, R)
             integ.substepAdjointPhase(1, t, 1e-3, steps, stage)
