@@ -546,14 +546,16 @@ def run_c1(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"C1/C2 AcousticMonopole {args.c1_n}x{args.c1_n} ({N} points), {T} time steps, dt 0.05, "
                                f"save interval {S}: forward run (J) + adjoint run (cost sensitivity, gradient)",
-                   "path": "fused" if region.usesFused(mb.FORWARD) else "operator by operator (patches present)",
+                   "path": ("fused sweeps incl. RK4" if region.usesFused(mb.FORWARD) else
+                            "fused sweeps (A, B / adjoint 1, 2) + patch and source epilogue + pointwise RK4"
+                            if region.usesFusedRhs(mb.FORWARD) else "operator by operator"),
                    "evals_per_point_per_step": 8,
                    "l2_policy": "working set (a few MB) is L2 resident by nature of the configuration; nothing is flushed"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(N * 4 * 8 / T), "d2h_bytes_per_step": int(grad.size * 8 / T),
                 "timer": "host wall clock around Solver.runForward(host Q0) + Solver.runAdjoint() -> host gradient; the "
                          "device-timed value IS this number: the drivers synchronise every substep for J and the gradient sample"},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "whole path (no dominant kernel: ~40 small launches per stage)",
+        "roofline": {"bound": "hbm", "kernel": "whole path (no dominant kernel: small launches, 40 401 points each)",
                      "achieved": (fwd_rate * BYTES_C1_FORWARD * tf + 0.5 * adj_rate * BYTES_C1_ADJOINT * ta) / (tf + ta) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
                      "note": "launch-latency bound, not bandwidth bound: 40 401 points per launch"},
