@@ -120,7 +120,7 @@ def cpu_port_rate(n=128, steps=1, warmup=1):
     from oracle import cport, grid as og
     from oracle import rhs as orhs
     from magudi_b200 import workload as wl
-    cport.build()
+    cport.build(force=True)     # -march=native: always built for the host the baseline runs on
     shape = (n, n, n)
     g = og.Grid(shape, (og.PLANE,) * 3, (2 * np.pi,) * 3, isCurvilinear=False)
     g.coordinates[:, :] = wl.c3_coordinates(shape, (0, 0, 0), shape)
