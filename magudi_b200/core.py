@@ -484,6 +484,21 @@ class Patch:
     def collect(self, field, name):
         check(L.lib().mg_patch_collect(self._h, field, name.encode()))
 
+    def gatherData(self, local, root=0):
+        """``t_Patch%gatherData`` (``src/PatchImpl.f90:587-736``): local patch arrays of all ranks -> the patch-global
+        array on ``root`` (``None`` elsewhere)."""
+        from . import parallel
+        e = self.extent
+        return parallel.gather_patch_data((e[1] - e[0] + 1, e[3] - e[2] + 1, e[5] - e[4] + 1), self.localSize,
+                                          self.patchOffset, local, root)
+
+    def scatterData(self, patchGlobal, nComp, root=0):
+        """``t_Patch%scatterData`` (``src/PatchImpl.f90:738-886``)."""
+        from . import parallel
+        e = self.extent
+        return parallel.scatter_patch_data((e[1] - e[0] + 1, e[3] - e[2] + 1, e[5] - e[4] + 1), self.localSize,
+                                           self.patchOffset, patchGlobal, nComp, root)
+
     def linkInterface(self, other, indexReordering=(1, 2, 3)):
         """``self conforms_with other`` (``readPatchInterfaceInformation``, ``src/InterfaceHelperImpl.f90:3-112``):
         both must be SAT_BLOCK_INTERFACE patches of states of one region; ``other`` gets the inverted reordering."""

@@ -194,3 +194,64 @@ def all_reduce_max(value, device=None):
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---------------------------------------------------------------------------------- patch collectives
+def _patch_box(localSize, patchOffset):
+    """slices of the patch-global (n1, n2, n3) box that this rank's local part covers"""
+    return tuple(slice(int(o), int(o) + int(n)) for o, n in zip(patchOffset, localSize))
+
+
+def gather_patch_data(globalSize, localSize, patchOffset, local, root=0, group=None):
+    """``t_Patch%gatherData`` (reference ``src/PatchImpl.f90:587-736``): the ranks' local parts ``local``
+    (nLocalPatchPoints, nComp), patch order (i fastest), are assembled on ``root`` into the patch-global array
+    (prod(globalSize), nComp) in patch-global Fortran order; other ranks get ``None``.  ``localSize`` /
+    ``patchOffset`` are what ``Patch.localSize`` / ``Patch.patchOffset`` report (``mg_patch_num_points``); a rank
+    that holds no point of the patch passes an empty array.  Host-side (the callers are gradient / forcing I/O and
+    setup, as in the reference); works with any ``torch.distributed`` backend."""
+    import numpy as np
+    local = np.asarray(local, dtype=np.float64)
+    nComp = local.shape[1] if local.ndim == 2 else 1
+    piece = (tuple(int(v) for v in localSize), tuple(int(v) for v in patchOffset),
+             np.ascontiguousarray(local.reshape(-1, nComp)))
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        pieces = [piece]
+        me = root
+    else:
+        me = dist.get_rank(group)
+        pieces = [None] * dist.get_world_size(group) if me == root else None
+        dist.gather_object(piece, pieces, dst=root, group=group)
+    if me != root:
+        return None
+    g = tuple(int(v) for v in globalSize)
+    out = np.zeros(g + (nComp,))
+    for ls, po, a in pieces:
+        if int(np.prod(ls)) == 0:
+            continue
+        out[_patch_box(ls, po)] = a.reshape(ls + (a.shape[1],), order="F")
+    return out.reshape(-1, nComp, order="F")
+
+
+def scatter_patch_data(globalSize, localSize, patchOffset, patchGlobal, nComp, root=0, group=None):
+    """``t_Patch%scatterData`` (``src/PatchImpl.f90:738-886``): the inverse -- ``root`` holds the patch-global array
+    (prod(globalSize), nComp); every rank receives its local part (nLocalPatchPoints, nComp) in patch order."""
+    import numpy as np
+    ls = tuple(int(v) for v in localSize)
+    po = tuple(int(v) for v in patchOffset)
+    single = not dist.is_initialized() or dist.get_world_size(group) == 1
+    me = root if single else dist.get_rank(group)
+    if single:
+        boxes = [(ls, po)]
+    else:
+        boxes = [None] * dist.get_world_size(group) if me == root else None
+        dist.gather_object((ls, po), boxes, dst=root, group=group)
+    parts = None
+    if me == root:
+        g = tuple(int(v) for v in globalSize)
+        G = np.asarray(patchGlobal, dtype=np.float64).reshape(g + (nComp,), order="F")
+        parts = [np.ascontiguousarray(G[_patch_box(l, p)].reshape(-1, nComp, order="F")) for l, p in boxes]
+    if single:
+        return parts[0]
+    out = [None]
+    dist.scatter_object_list(out, parts, src=root, group=group)
+    return out[0]

@@ -85,3 +85,57 @@ def test_patch_extents_follow_reference_intersection_rule():
         if b >= a:
             covered += list(range(a, b + 1))
     assert covered == list(range(ext[0], ext[1] + 1))
+
+
+def _patch_worker(rank, world, port, ok):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from magudi_b200.parallel import gather_patch_data, scatter_patch_data
+        from magudi_b200 import pigeonhole
+        # a patch [3..9] x [2..6] x [5..30] of a 12 x 8 x 37 grid split in slabs along k (setupPatch's intersection)
+        nzg, ext = 37, (3, 9, 2, 6, 5, 30)
+        gsize = (ext[1] - ext[0] + 1, ext[3] - ext[2] + 1, ext[5] - ext[4] + 1)
+        off, n = pigeonhole(nzg, world, rank)
+        a, b = max(ext[4], off + 1), min(ext[5], off + n)
+        nk = max(0, b - a + 1)
+        lsize = (gsize[0], gsize[1], nk) if nk else (0, 0, 0)
+        poff = (0, 0, a - ext[4]) if nk else (0, 0, 0)
+        full = np.random.default_rng(3).standard_normal(gsize + (2,))
+        local = full[:, :, poff[2]:poff[2] + nk].reshape(-1, 2, order="F") if nk else np.zeros((0, 2))
+        G = gather_patch_data(gsize, lsize, poff, local)
+        good = True
+        if rank == 0:
+            good &= np.array_equal(G, full.reshape(-1, 2, order="F"))
+        else:
+            good &= G is None
+        back = scatter_patch_data(gsize, lsize, poff, G, 2)
+        good &= np.array_equal(back, local)
+        ok[rank] = 1 if good else 0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_patch_gather_scatter_gloo(world):
+    """t_Patch%gatherData / %scatterData (reference src/PatchImpl.f90:587-886; its test/patch_collectives.f90): the
+    local parts of a patch split over the slabs assemble into the patch-global array on the root, and scatter back."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ok = ctx.Array("i", [0] * world)
+    procs = [ctx.Process(target=_patch_worker, args=(r, world, port, ok)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(ok) == [1] * world
+
+
+def test_patch_gather_scatter_single_process():
+    from magudi_b200.parallel import gather_patch_data, scatter_patch_data
+    a = np.arange(24.0).reshape(12, 2)
+    G = gather_patch_data((3, 4, 1), (3, 4, 1), (0, 0, 0), a)
+    assert np.array_equal(G, a)
+    assert np.array_equal(scatter_patch_data((3, 4, 1), (3, 4, 1), (0, 0, 0), G, 2), a)
