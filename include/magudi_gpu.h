@@ -161,6 +161,12 @@ int mg_halo_unpack(mg_grid* g, void* owner, int field, int side, int width, cons
  * stream and synchronise with the neighbours on the device (sequence flags); mg_p2p_check reports a timeout. */
 typedef struct mg_p2p mg_p2p;
 int mg_p2p_create(mg_grid* g, int maxComp, int width, mg_p2p** out);
+/* the same for bricks split along direction `direction` (0-based): 0 / 1 = faces normal to i / j travel as packed
+ * buffers (reference fillGhostPoints, src/MPIHelperImpl.f90:175-296), 2 = mg_p2p_create.  Serves the operator-by-
+ * operator path (every operator application along a decomposed direction fills its ghost points through it); the
+ * fused sweeps need slabs along direction 3.  Connect with mg_p2p_connect to the previous / next rank ALONG that
+ * direction. */
+int mg_p2p_create_dir(mg_grid* g, int direction, int maxComp, int width, mg_p2p** out);
 int mg_p2p_handle_size(void);
 int mg_p2p_get_handle(mg_p2p* h, void* handleOut);
 int mg_p2p_connect(mg_p2p* h, int side, const void* peerHandle, int sameAsOther);

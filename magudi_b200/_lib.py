@@ -84,6 +84,7 @@ SIGNATURES = {
     "mg_functional_pressure_drag": (C.c_int, [_P, _P, _D]),
     "mg_functional_pressure_drag_forcing": (C.c_int, [_P, _P]),
     "mg_p2p_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "mg_p2p_create_dir": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "mg_p2p_handle_size": (C.c_int, []),
     "mg_p2p_get_handle": (C.c_int, [_P, _P]),
     "mg_p2p_connect": (C.c_int, [_P, C.c_int, _P, C.c_int]),

@@ -235,7 +235,7 @@ int mg_grid_create_impl(int index, int nD, const int globalSize[3], const int lo
     g->procDims[i] = procDims[i];
     g->procCoords[i] = procCoords[i];
     if (localSize[i] <= 0) { delete g; MG_FAIL("mg_grid_create: local size must be positive"); }
-    if (i < 2 && procDims[i] != 1) { delete g; MG_FAIL("mg_grid_create: only slab decomposition along direction 3 is supported"); }
+    if (procDims[i] < 1 || procCoords[i] < 0 || procCoords[i] >= procDims[i]) { delete g; MG_FAIL("mg_grid_create: invalid process grid"); }
   }
   for (int i = nD; i < 3; ++i)
     if (globalSize[i] != 1) { delete g; MG_FAIL("mg_grid_create: extent beyond nDimensions must be 1"); }
@@ -312,6 +312,29 @@ int mg_grid_setup_discretization_impl(mg_grid* g, const char* const schemes[3], 
 }
 
 // Generic operator application on a padded field (general path).
+// fillGhostPoints + apply (reference src/StencilOperatorImpl.f90:52-104): along a decomposed direction the ghost
+// points of the input come from the neighbours -- direction 3: ghost planes of the padded field, filled in place;
+// directions 1 and 2: packed faces received into explicit ghost buffers.
+static int apply_with_halo(mg_grid* g, mg_stencil* op, ApplyArgs& a) {
+  const int dir = op->direction - 1;
+  const int w = std::max(op->op.nGhost[0], op->op.nGhost[1]);
+  if (dir >= 0 && dir < 3 && g->procDims[dir] > 1) {
+    if (dir == 2) {
+      a.padded = 1;
+      if (!g->halo)
+        MG_FAIL("operator application along a decomposed direction: no halo attached to the grid (mg_p2p_create); "
+                "the NCCL fallback only serves the fused sweeps");
+      MG_TRY(mg_p2p_exchange_view(g->halo, a.in, a.inCompStride, a.nComp, w));
+    } else {
+      if (!g->haloDir[dir])
+        MG_FAIL("operator application along a decomposed direction: no halo attached to the grid for this "
+                "direction (mg_p2p_create_dir)");
+      MG_TRY(mg_p2p_exchange_faces(g->haloDir[dir], a.in, a.inCompStride, a.nComp, w, &a.ghostPrev, &a.ghostNext));
+    }
+  }
+  return mg_apply_launch(op, a);
+}
+
 int mg_grid_apply(mg_grid* g, mg_stencil* op, const double* in, size_t inCs, double* out, size_t outCs,
                   int nComp) {
   ApplyArgs a;
@@ -321,16 +344,7 @@ int mg_grid_apply(mg_grid* g, mg_stencil* op, const double* in, size_t inCs, dou
   a.outCompStride = outCs;
   a.nComp = nComp;
   for (int i = 0; i < 3; ++i) a.n[i] = g->localSize[i];
-  // direction 3 on a slab-decomposed grid reads the ghost planes of the padded field
-  a.padded = (op->direction == 3 && g->procDims[2] > 1) ? 1 : 0;
-  if (a.padded) {
-    // fillGhostPoints (reference src/StencilOperatorImpl.f90:66): the input's ghost planes come from the k-neighbours
-    if (!g->halo)
-      MG_FAIL("operator application along a decomposed direction: no halo attached to the grid (mg_p2p_create); "
-              "the NCCL fallback only serves the fused sweeps");
-    MG_TRY(mg_p2p_exchange_view(g->halo, in, inCs, nComp, std::max(op->op.nGhost[0], op->op.nGhost[1])));
-  }
-  return mg_apply_launch(op, a);
+  return apply_with_halo(g, op, a);
 }
 
 // computeCoordinateDerivatives (reference :621-744)
@@ -343,7 +357,6 @@ int mg_grid_coordinate_derivatives(mg_grid* g, int dir, MgField* out) {
   a.outCompStride = out->compStride;
   a.nComp = g->nD;
   for (int i = 0; i < 3; ++i) a.n[i] = g->localSize[i];
-  a.padded = (dir == 2 && g->procDims[2] > 1) ? 1 : 0;
   if (g->periodicityType[dir] == MG_PERIODIC_PLANE) {
     a.interiorOnly = 1;
     a.shiftComp = dir;
@@ -351,6 +364,10 @@ int mg_grid_coordinate_derivatives(mg_grid* g, int dir, MgField* out) {
     a.shiftPrev = g->procCoords[dir] == 0;
     a.shiftNext = g->procCoords[dir] == g->procDims[dir] - 1;
   }
+  // bricks split along i / j: the coordinates' ghost points arrive as packed faces; slabs along k keep the
+  // explicit exchange of the coordinate field the caller issues before mg_grid_update (ghost planes, in place)
+  if (dir < 2) return apply_with_halo(g, D, a);
+  a.padded = (g->procDims[2] > 1) ? 1 : 0;
   return mg_apply_launch(D, a);
 }
 

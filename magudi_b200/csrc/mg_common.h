@@ -112,7 +112,10 @@ struct mg_grid {
   // peer-to-peer halo of a slab-decomposed grid (set by mg_p2p_create): lets the operator-by-operator path fill
   // the ghost planes of whatever array an operator is applied to along k
   struct mg_p2p* halo = nullptr;
+  struct mg_p2p* haloDir[2] = {nullptr, nullptr};   // the same for bricks split along i / j (packed faces)
 };
+int mg_p2p_exchange_faces(struct mg_p2p* h, const double* in, size_t inCs, int nComp, int width,
+                          const double** ghostPrev, const double** ghostNext);
 int mg_p2p_check_all();       // fails when a halo exchange of any live handle has timed out
 int mg_p2p_exchange_view(struct mg_p2p* h, const double* comp0, size_t compStride, int nComp, int width);
 

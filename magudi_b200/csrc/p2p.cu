@@ -150,6 +150,9 @@ __global__ void __launch_bounds__(P2P_THREADS) k_unpack(const __grid_constant__ 
 
 struct mg_p2p {
   mg_grid* grid = nullptr;
+  int direction = 2;                    // 0 / 1: faces normal to i / j travel as packed buffers; 2: contiguous k planes
+  double* faceSend[2] = {nullptr, nullptr};   // packed first / last `width` points of every line (directions 0, 1)
+  double* faceRecv[2] = {nullptr, nullptr};   // ghost buffers in the layout k_apply reads (reference fillGhostPoints)
   size_t capacity = 0;                  // doubles per staging buffer
   char* base = nullptr;                 // my shared allocation
   char* peer[2] = {nullptr, nullptr};   // mapped allocations of prev (0) / next (1)
@@ -387,6 +390,143 @@ static int p2p_exchange_field(mg_p2p* h, const MgField* fAll, int width, cudaStr
   return 0;
 }
 
+// Exchange explicit device buffers with the two neighbours: sendLo -> prev's recvHi, sendHi -> next's recvLo
+// (count doubles each).  Same staging / flag protocol as the plane exchange.
+static int p2p_exchange_buffers(mg_p2p* h, const double* sendLo, const double* sendHi, double* recvLo, double* recvHi,
+                                size_t count, cudaStream_t st) {
+  if (count > h->capacity) MG_FAIL("mg_p2p: face payload exceeds the staging capacity");
+  const unsigned long long n = h->uses[0];
+  const int parity = (int)(n & 1);
+  const unsigned long long use = n >> 1;
+  PushPair pp;
+  std::memset(&pp, 0, sizeof(pp));
+  for (int side = 0; side < 2; ++side) {
+    if (!h->peer[side]) continue;
+    PushArgs& a = pp.s[side];
+    a.nComp = 1;
+    a.chunk = count;
+    a.src[0] = side == 0 ? sendLo : sendHi;
+    const int peerFace = 1 - side;
+    a.dst = reinterpret_cast<double*>(h->peer[side] + mg_p2p::bufOffset(h->capacity, peerFace, parity));
+    a.dstFlag = &reinterpret_cast<Shared*>(h->peer[side])->data[peerFace][parity];
+    a.ackFlag = &h->flags()->ack[side][parity];
+    a.use = use;
+    a.counter = h->counters + side;
+    a.error = h->error;
+    a.vec = (count % 2 == 0) && ((uintptr_t)a.dst % 16 == 0) && ((uintptr_t)a.src[0] % 16 == 0);
+  }
+  k_push<<<dim3(P2P_BLOCKS, 2), P2P_THREADS, 0, st>>>(pp);
+  UnpackPair up;
+  std::memset(&up, 0, sizeof(up));
+  for (int face = 0; face < 2; ++face) {
+    if (!h->peer[face]) continue;
+    UnpackArgs& a = up.s[face];
+    a.nComp = 1;
+    a.chunk = count;
+    a.dst[0] = face == 0 ? recvLo : recvHi;
+    a.src = reinterpret_cast<const double*>(h->base + mg_p2p::bufOffset(h->capacity, face, parity));
+    a.dataFlag = &h->flags()->data[face][parity];
+    a.ackFlag = &reinterpret_cast<Shared*>(h->peer[face])->ack[1 - face][parity];
+    a.use = use;
+    a.counter = h->counters + 2 + face;
+    a.error = h->error;
+    a.vec = (count % 2 == 0) && ((uintptr_t)a.src % 16 == 0) && ((uintptr_t)a.dst[0] % 16 == 0);
+  }
+  k_unpack<<<dim3(P2P_BLOCKS, 2), P2P_THREADS, 0, st>>>(up);
+  MG_CUDA(cudaGetLastError());
+  mg_count_launches(2);
+  h->uses[0] = h->uses[1] = n + 1;
+  return 0;
+}
+
+namespace {
+// pack the first (side 0) and last (side 1) `w` points of every grid line along DIR, for nComp components, in the
+// ghost-buffer layout of the reference (src/MPIHelperImpl.f90:175-296): q + w * (line + lines * component)
+template <int DIR>
+__global__ void k_pack_faces(const double* x, size_t cs, int nComp, long nx, long ny, long nz, int w, double* lo,
+                             double* hi) {
+  const long n = DIR == 0 ? nx : ny;
+  const long lines = DIR == 0 ? ny * nz : nx * nz;
+  const long total = (long)w * lines * nComp;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int q = (int)(t % w);
+    const long line = (t / w) % lines;
+    const int l = (int)(t / ((long)w * lines));
+    long p0;      // index of the line's first point
+    long stride;
+    if (DIR == 0) { p0 = nx * line; stride = 1; }                       // line = j + ny k
+    else { const long i = line % nx, k = line / nx; p0 = i + nx * ny * k; stride = nx; }   // line = i + nx k
+    const double* xl = x + (size_t)l * cs;
+    lo[t] = xl[p0 + (long)q * stride];
+    hi[t] = xl[p0 + (n - w + q) * stride];
+  }
+}
+}  // namespace
+
+// fillGhostPoints along direction 0 or 1 (reference src/MPIHelperImpl.f90:113-296) for an operator application:
+// returns device pointers to the received ghost buffers (null on a side without a neighbour).
+int mg_p2p_exchange_faces(mg_p2p* h, const double* in, size_t inCs, int nComp, int width, const double** ghostPrev,
+                          const double** ghostNext) {
+  if (!h || !in) MG_FAIL("mg_p2p_exchange_faces: null argument");
+  mg_grid* g = h->grid;
+  const int dir = h->direction;
+  if (dir > 1) MG_FAIL("mg_p2p_exchange_faces: the handle serves direction 3 (plane exchange)");
+  *ghostPrev = nullptr;
+  *ghostNext = nullptr;
+  if (width <= 0) return 0;
+  MG_TRY(mg_halo_wait_pending());
+  const long lines = (long)(g->N / g->localSize[dir]);
+  const size_t count = (size_t)width * lines * nComp;
+  if (count > h->capacity) MG_FAIL("mg_p2p_exchange_faces: more components than the halo was created for");
+  if (width > g->localSize[dir]) MG_FAIL("mg_p2p_exchange_faces: the rank's extent is smaller than the stencil half-width");
+  cudaStream_t st = mg_stream();
+  const unsigned blocks = (unsigned)std::min<size_t>((count + 255) / 256, 4096);
+  if (dir == 0)
+    k_pack_faces<0><<<blocks, 256, 0, st>>>(in, inCs, nComp, g->localSize[0], g->localSize[1], g->localSize[2], width,
+                                            h->faceSend[0], h->faceSend[1]);
+  else
+    k_pack_faces<1><<<blocks, 256, 0, st>>>(in, inCs, nComp, g->localSize[0], g->localSize[1], g->localSize[2], width,
+                                            h->faceSend[0], h->faceSend[1]);
+  MG_CUDA(cudaGetLastError());
+  mg_count_launches(1);
+  MG_TRY(p2p_exchange_buffers(h, h->faceSend[0], h->faceSend[1], h->faceRecv[0], h->faceRecv[1], count, st));
+  if (h->peer[0]) *ghostPrev = h->faceRecv[0];
+  if (h->peer[1]) *ghostNext = h->faceRecv[1];
+  return 0;
+}
+
+// A halo handle for direction `direction` (0, 1: packed faces; 2: k planes = mg_p2p_create).
+int mg_p2p_create_dir(mg_grid* g, int direction, int maxComp, int width, mg_p2p** out) {
+  if (direction == 2) return mg_p2p_create(g, maxComp, width, out);
+  if (!g || !out) MG_FAIL("mg_p2p_create_dir: null argument");
+  if (direction < 0 || direction > 1) MG_FAIL("mg_p2p_create_dir: direction must be 0, 1 or 2");
+  if (maxComp < 1 || maxComp > MG_P2P_MAX_COMP) MG_FAIL("mg_p2p_create_dir: component count out of range");
+  if (width < 1 || width > g->localSize[direction]) MG_FAIL("mg_p2p_create_dir: width exceeds the local extent");
+  if (g->periodicityType[direction] == MG_PERIODIC_OVERLAP && g->procDims[direction] > 1)
+    MG_FAIL("mg_p2p_create_dir: OVERLAP periodicity along a decomposed direction is not supported");
+  mg_p2p* h = new mg_p2p;
+  h->grid = g;
+  h->direction = direction;
+  h->capacity = (g->N / g->localSize[direction]) * (size_t)width * (size_t)maxComp;
+  h->capacity += h->capacity % 2;
+  h->bytes = sizeof(Shared) + 4 * h->capacity * sizeof(double);
+  MG_CUDA(cudaMalloc(&h->base, h->bytes));
+  MG_CUDA(cudaMemset(h->base, 0, h->bytes));
+  MG_CUDA(cudaMalloc(&h->counters, 4 * sizeof(unsigned int)));
+  MG_CUDA(cudaMemset(h->counters, 0, 4 * sizeof(unsigned int)));
+  MG_CUDA(cudaHostAlloc(&h->error, sizeof(int), cudaHostAllocMapped));
+  *h->error = 0;
+  for (int i = 0; i < 2; ++i) {
+    MG_CUDA(cudaMalloc(&h->faceSend[i], h->capacity * sizeof(double)));
+    MG_CUDA(cudaMalloc(&h->faceRecv[i], h->capacity * sizeof(double)));
+  }
+  mg_p2p_register(h, true);
+  MG_CUDA(cudaDeviceSynchronize());
+  g->haloDir[direction] = h;
+  *out = h;
+  return 0;
+}
+
 // 0 when no spin-wait timed out so far (synchronises the library stream)
 int mg_p2p_check(mg_p2p* h) {
   if (!h) MG_FAIL("mg_p2p_check: null handle");
@@ -400,6 +540,9 @@ int mg_p2p_destroy(mg_p2p* h) {
   if (!h) return 0;
   cudaDeviceSynchronize();
   if (h->grid && h->grid->halo == h) h->grid->halo = nullptr;
+  for (int d = 0; d < 2; ++d)
+    if (h->grid && h->grid->haloDir[d] == h) h->grid->haloDir[d] = nullptr;
+  for (int i = 0; i < 2; ++i) { cudaFree(h->faceSend[i]); cudaFree(h->faceRecv[i]); }
   for (int s = 0; s < 2; ++s)
     if (h->peerMapped[s] && h->peer[s]) cudaIpcCloseMemHandle(h->peer[s]);
   cudaFree(h->base);

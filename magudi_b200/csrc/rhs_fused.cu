@@ -1293,6 +1293,7 @@ int mg_fused_rhs_supported(const mg_state* s, int mode) {
   if (mode != MG_FORWARD && mode != MG_ADJOINT) return 0;
   if (g->nD < 2) return 0;
   if (g->iblank) return 0;
+  if (g->procDims[0] != 1 || g->procDims[1] != 1) return 0;       // bricks split along i / j: operator path
   if (g->nD == 3 && g->periodicityType[2] != MG_PERIODIC_PLANE) return 0;
   SchemeInfo si;
   if (!scheme_of(g, &si)) return 0;

@@ -76,6 +76,16 @@ class HaloExchanger:
             unpack(0, width, recv_lo)
 
 
+def cart_rank(coords, dims):
+    """Global rank of process-grid position ``coords`` (first direction fastest) -- the mapping ``GpuHalo`` assumes
+    between ``torch.distributed`` ranks and the Cartesian ``processCoordinates`` of the reference."""
+    return int(coords[0] + dims[0] * (coords[1] + dims[1] * coords[2]))
+
+
+def cart_coords(rank, dims):
+    return (rank % dims[0], (rank // dims[0]) % dims[1], rank // (dims[0] * dims[1]))
+
+
 class GpuHalo:
     """Halo exchange of library-owned fields along k.
 
@@ -87,11 +97,16 @@ class GpuHalo:
 
     MAX_COMP = 12
 
-    def __init__(self, grid, rank, world, device, mode=None):
+    def __init__(self, grid, rank, world, device, mode=None, direction=2):
+        """``direction`` (0-based): 2 = slabs along k (fused sweeps and operator path); 0 / 1 = bricks split along
+        i / j (operator path only: packed faces, ``mg_p2p_create_dir``).  For 0 / 1 ``rank`` / ``world`` are the
+        position and extent of the process grid ALONG that direction and the neighbours' global ranks follow
+        ``cart_rank``."""
         import os
         self.grid = grid
+        self.direction = direction
         self.rank, self.world = rank, world
-        periodic = grid.periodicityType[2] != 0
+        periodic = grid.periodicityType[direction] != 0
         self.mode = mode or os.environ.get("MG_HALO", "p2p")
         self.plane = grid.localSize[0] * grid.localSize[1]
         self._p2p = None
@@ -109,6 +124,8 @@ class GpuHalo:
                 self._p2p = None
                 self.mode = "nccl"
         if self._p2p is None:
+            if direction != 2 and world > 1:
+                raise RuntimeError("bricks split along i / j need the P2P halo (no NCCL fallback on the operator path)")
             self.mode = "nccl"
             # the library stream is made torch's current stream during an exchange: no host synchronisation
             stream = torch.cuda.ExternalStream(L.lib().mg_stream_handle(), device=device)
@@ -117,16 +134,26 @@ class GpuHalo:
     def _setup_p2p(self, periodic, device):
         lib = L.lib()
         h = C.c_void_p()
-        check(lib.mg_p2p_create(self.grid._h, self.MAX_COMP, min(4, self.grid.localSize[2]), C.byref(h)))
+        d = self.direction
+        check(lib.mg_p2p_create_dir(self.grid._h, d, self.MAX_COMP, min(4, self.grid.localSize[d]), C.byref(h)))
         self._p2p = h
         n = lib.mg_p2p_handle_size()
         buf = C.create_string_buffer(n)
         check(lib.mg_p2p_get_handle(h, buf))
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(buf.raw))
+        handles = [None] * dist.get_world_size()
+        dist.all_gather_object(handles, bytes(buf.raw))       # indexed by GLOBAL rank
         rank, world = self.rank, self.world
         prev = (rank - 1) % world if (periodic or rank > 0) else None
         nxt = (rank + 1) % world if (periodic or rank < world - 1) else None
+        if d != 2 or tuple(self.grid.procDims[:2]) != (1, 1):
+            # position along d -> global rank of that neighbour in the process grid
+            def glob(c):
+                if c is None:
+                    return None
+                cc = list(self.grid.procCoords)
+                cc[d] = c
+                return cart_rank(cc, self.grid.procDims)
+            prev, nxt = glob(prev), glob(nxt)
         self._keep = []
         for side, peer in ((0, prev), (1, nxt)):
             if peer is None:

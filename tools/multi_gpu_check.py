@@ -92,27 +92,34 @@ def general_fields(shape, seed):
     return state(), rng.random(tuple(shape) + (5,)), state(), rng.random(tuple(shape)), rng.random(tuple(shape) + (5,))
 
 
-def run_general(shape, world, rank, dev):
-    """General path: SBP 2-4, viscous, curvilinear, k NOT periodic, patches on k and j faces."""
+def run_general(shape, dims, rank, dev):
+    """Operator-by-operator path: SBP 2-4, viscous, curvilinear, NOT periodic, patches on k, j and i faces; the
+    process grid ``dims`` may split any direction (slabs along k: ghost planes; bricks along i / j: packed faces)."""
+    world = int(np.prod(dims))
+    coords = par.cart_coords(rank, dims) if world > 1 else (0, 0, 0)
     opt = core.SolverOptions(ratioOfSpecificHeats=1.4, viscosityOn=True, reynoldsNumberInverse=1.0 / 90.0,
                              dissipationOn=True, compositeDissipation=False, dissipationAmount=0.01,
                              useTargetState=True, discretizationType="SBP 2-4")
-    grid = core.Grid(1, shape, (core.NONE,) * 3, (0.0,) * 3, isCurvilinear=True, procDims=(1, 1, world),
-                     procCoords=(0, 0, rank))
+    grid = core.Grid(1, shape, (core.NONE,) * 3, (0.0,) * 3, isCurvilinear=True, procDims=dims, procCoords=coords)
     grid.setupSpatialDiscretization(opt.discretizationType, opt.compositeDissipation, False, opt.dissipationOn)
     grid.setCoordinates(general_coordinates(grid.globalSize, grid.offset, grid.localSize))
-    halo = par.GpuHalo(grid, rank, world, dev) if world > 1 else None
-    if halo:
-        assert halo.mode == "p2p", "the operator-by-operator path needs the P2P halo"
-        halo.exchange(None, core.G_COORDINATES, 3, 2)
+    halos = []
+    for d in range(3):
+        if dims[d] > 1:
+            h = par.GpuHalo(grid, coords[d], dims[d], dev, direction=d)
+            assert h.mode == "p2p", "the operator-by-operator path needs the P2P halo"
+            halos.append(h)
+            if d == 2:
+                h.exchange(None, core.G_COORDINATES, 3, 2)
     assert not grid.update()
     state = core.State(grid, opt)
     region = core.Region()
     region.addState(state)
     region.setFused(False)
     Qg, Wg, Tg, Sg, Fg = general_fields(shape, 7)
-    k0, nz = grid.offset[2], grid.localSize[2]
-    loc = lambda a: a[:, :, k0:k0 + nz].reshape(-1, a.shape[-1] if a.ndim == 4 else 1, order="F")
+    o, n = grid.offset, grid.localSize
+    loc = lambda a: a[o[0]:o[0] + n[0], o[1]:o[1] + n[1], o[2]:o[2] + n[2]].reshape(
+        -1, a.shape[-1] if a.ndim == 4 else 1, order="F")
     state.conservedVariables = loc(Qg)
     state.adjointVariables = loc(Wg)
     state.targetState = loc(Tg)
@@ -122,6 +129,7 @@ def run_general(shape, world, rank, dev):
              ("SPONGE", "sponge.k", -3, [1, nx, 1, ny, nzg - 9, nzg]),
              ("SAT_ISOTHERMAL_WALL", "wall.j1", 2, [1, nx, 1, 1, 1, nzg], 1.0, 0.8),
              ("SAT_SLIP_WALL", "wall.i1", 1, [1, 1, 1, ny, 1, nzg], 1.0, 0.0),
+             ("SAT_FAR_FIELD", "ff.in", -1, [nx, nx, 1, ny, 1, nzg], 1.0, 0.7),
              ("COST_TARGET", "target", 0, [4, nx - 3, 3, ny - 2, 5, nzg - 4])]
     for sp in specs:
         p = state.addPatch(*sp)
@@ -146,17 +154,18 @@ def run_general(shape, world, rank, dev):
     for stage in range(4, 0, -1):
         t = integ.substepAdjoint(t, 2e-3, 0, stage)
     out += [state.conservedVariables, state.adjointVariables]
-    if halo:
-        halo.check()
+    for h in halos:
+        h.check()
     return np.concatenate(out, axis=1), grid
 
 
 def compare(pieces, single, shape, ncomp, label, world):
+    """pieces: (offset[3], localSize[3], local (nLocal, ncomp)) of every rank"""
     Qs = single.reshape(tuple(shape) + (ncomp,), order="F")
     err = 0.0
-    for k0, nz, q in pieces:
-        q = q.reshape((shape[0], shape[1], nz, ncomp), order="F")
-        ref = Qs[:, :, k0:k0 + nz]
+    for o, n, q in pieces:
+        q = q.reshape(tuple(n) + (ncomp,), order="F")
+        ref = Qs[o[0]:o[0] + n[0], o[1]:o[1] + n[1], o[2]:o[2] + n[2]]
         for c0 in range(0, ncomp, 5):
             sl = slice(c0, c0 + 5)
             err = max(err, float(np.max(np.abs(q[..., sl] - ref[..., sl])) / np.max(np.abs(Qs[..., sl]))))
@@ -165,23 +174,38 @@ def compare(pieces, single, shape, ncomp, label, world):
 
 
 def check_all(world, rank, dev):
-    """Both checks on an initialised process group; returns {case: max rel diff} on rank 0 (None elsewhere)."""
+    """All checks on an initialised process group; returns {case: max rel diff} on rank 0 (None elsewhere)."""
+    def gathered(local, grid):
+        pieces = [None] * world
+        dist.all_gather_object(pieces, (tuple(grid.offset), tuple(grid.localSize), local))
+        return pieces
     shape = (32, 30, 16 * world + 5)
     Ql, grid = run(shape, world, rank, dev)
-    pieces = [None] * world
-    dist.all_gather_object(pieces, (grid.offset[2], grid.localSize[2], Ql))
+    pieces = gathered(Ql, grid)
     gshape = (20, 18, 13 * world + 3)
-    Gl, ggrid = run_general(gshape, world, rank, dev)
-    gpieces = [None] * world
-    dist.all_gather_object(gpieces, (ggrid.offset[2], ggrid.localSize[2], Gl))
+    Gl, ggrid = run_general(gshape, (1, 1, world), rank, dev)
+    gpieces = gathered(Gl, ggrid)
+    # bricks split along i, along j and (4+ ranks) along both: packed-face halos of the operator path
+    bshape = (13 * world + 2, 12 * world + 1, 14)
+    brick = {"i": (world, 1, 1), "j": (1, world, 1)}
+    if world % 2 == 0 and world >= 4:
+        brick["ij"] = (2, world // 2, 1)
+    bpieces = {}
+    for k, dims in brick.items():
+        Bl, bgrid = run_general(bshape, dims, rank, dev)
+        bpieces[k] = gathered(Bl, bgrid)
     out = None
     if rank == 0:
         Qs, _ = run(shape, 1, 0, dev)
-        Gs, _ = run_general(gshape, 1, 0, dev)
+        Gs, _ = run_general(gshape, (1, 1, 1), 0, dev)
+        Bs, _ = run_general(bshape, (1, 1, 1), 0, dev)
         e1 = compare(pieces, Qs, shape, 10, "fused path (2 forward + 1 adjoint RK4 steps)", world)
-        e2 = compare(gpieces, Gs, gshape, 25, "general path (patches, non-periodic k; fwd/adj/lin RHS + RK4)", world)
+        e2 = compare(gpieces, Gs, gshape, 25, "operator path, slabs along k (patches, non-periodic; fwd/adj/lin RHS + RK4)", world)
+        eb = {k: compare(v, Bs, bshape, 25, f"operator path, bricks split along {k} {brick[k]}", world)
+              for k, v in bpieces.items()}
         out = {"fused_forward_adjoint_rk4_max_rel_diff_vs_1gpu": e1, "general_path_patches_max_rel_diff_vs_1gpu": e2,
-               "ranks": world, "tolerance": 1e-12, "ok": bool(e1 <= 1e-13 and e2 <= 1e-12)}
+               "bricks_max_rel_diff_vs_1gpu": eb, "ranks": world, "tolerance": 1e-12,
+               "ok": bool(e1 <= 1e-13 and e2 <= 1e-12 and all(e <= 1e-12 for e in eb.values()))}
     dist.barrier()
     return out
 
@@ -203,7 +227,7 @@ def main():
         dist.destroy_process_group()
     else:
         run((32, 30, 21), 1, 0, dev)
-        run_general((20, 18, 16), 1, 0, dev)
+        run_general((20, 18, 16), (1, 1, 1), 0, dev)
         print("multi_gpu_check: single rank run ok")
     sys.exit(0 if ok else 1)
 
