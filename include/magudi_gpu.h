@@ -261,6 +261,21 @@ int mg_patch_collect(mg_patch* p, int field, const char* name);
  * both blocks live on this process's device, the exchange is one gather kernel per patch with the reordering
  * applied on the fly. */
 int mg_patch_link_interface(mg_patch* a, mg_patch* b, const int indexReorderingA[3]);
+/* The conforming patch belongs to a block held by ANOTHER process (another GPU of the node; the reference's
+ * exchangeInterfaceData between block communicators, src/InterfaceHelperImpl.f90:115-239): creates a two-party
+ * P2P link of 2 * nUnknowns * nPatchPoints doubles each way.  The host swaps the links' IPC handles
+ * (mg_p2p_get_handle) between the two processes and connects BOTH sides of the link to the partner's handle
+ * (mg_p2p_connect(link, 0, h, 0); mg_p2p_connect(link, 1, h, 1)).  indexReordering is THIS patch's reordering
+ * (the inverse of the partner's); the partner's penalty amounts (its mg_patch_penalty_amounts) and normal
+ * direction are what the METRICS pseudo-exchange carries besides the metrics
+ * (src/BlockInterfacePatchImpl.f90:667-703).  Per stage the collected face arrays travel as remote NVLink stores
+ * sequenced by device flags; every process pushes on all its links before it waits on any.  The link is destroyed
+ * with the patch. */
+/* the patch's penalty amounts as the SAT kernels use them: signed by the normal direction and divided by the
+ * boundary norm weight (src/BlockInterfacePatchImpl.f90:70-96); viscous = 0 when the state's viscosity is off */
+int mg_patch_penalty_amounts(mg_patch* p, double* inviscid, double* viscous);
+int mg_patch_link_interface_remote(mg_patch* p, const int indexReordering[3], double partnerInviscidPenaltyAmount,
+                                   double partnerViscousPenaltyAmount, int partnerNormalDirection, mg_p2p** link);
 
 /* ------------------------------------------------------------------ t_Region / t_RK4Integrator */
 int mg_region_create(mg_region** out);

@@ -118,6 +118,8 @@ SIGNATURES = {
     "mg_patch_get_array": (C.c_int, [_P, C.c_char_p, C.c_int, _P]),
     "mg_patch_collect": (C.c_int, [_P, C.c_int, C.c_char_p]),
     "mg_patch_link_interface": (C.c_int, [_P, _P, _P]),
+    "mg_patch_penalty_amounts": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mg_patch_link_interface_remote": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_int, C.POINTER(_P)]),
     "mg_region_create": (C.c_int, [C.POINTER(_P)]),
     "mg_region_destroy": (C.c_int, [_P]),
     "mg_region_add_state": (C.c_int, [_P, _P]),

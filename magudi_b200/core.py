@@ -437,6 +437,8 @@ class Patch:
         self.name = name
         self.normalDirection = int(normalDirection)
         self.extent = tuple(int(e) for e in extent)
+        self.inviscidPenaltyAmount = float(inviscidPenaltyAmount)
+        self.viscousPenaltyAmount = float(viscousPenaltyAmount)
         h = C.c_void_p()
         ext = (C.c_int * 6)(*self.extent)
         check(L.lib().mg_patch_create(state._h, PATCH_TYPES[patchType], name.encode(), self.normalDirection, ext,

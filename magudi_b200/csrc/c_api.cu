@@ -841,6 +841,17 @@ int mg_region_compute_rhs(mg_region* r, int mode, int timestep, int stage) {
 int mg_patch_link_interface(mg_patch* a, mg_patch* b, const int indexReorderingA[3]) {
   return mg_interface_link(a, b, indexReorderingA);
 }
+int mg_patch_penalty_amounts(mg_patch* p, double* inviscid, double* viscous) {
+  if (!p || !inviscid || !viscous) MG_FAIL("mg_patch_penalty_amounts: null argument");
+  *inviscid = p->inviscidPenaltyAmount;
+  *viscous = p->state->opt.viscosityOn ? p->viscousPenaltyAmount : 0.0;
+  return 0;
+}
+int mg_patch_link_interface_remote(mg_patch* p, const int indexReordering[3], double partnerInviscidPenaltyAmount,
+                                   double partnerViscousPenaltyAmount, int partnerNormalDirection, mg_p2p** link) {
+  return mg_interface_link_remote(p, indexReordering, partnerInviscidPenaltyAmount, partnerViscousPenaltyAmount,
+                                  partnerNormalDirection, link);
+}
 int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep, int stage, int updateStates) {
   if (!r || !time) MG_FAIL("mg_rk4_substep: null argument");
   double t = *time;

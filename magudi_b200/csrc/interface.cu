@@ -422,6 +422,39 @@ int receive(mg_patch* p, const char* partnerName, const char* myName, int nComp)
   return 0;
 }
 
+// remote partner: ship the named patch arrays (in order) through the link, then reshape what arrived
+int send_remote(mg_patch* p, const char* const* names, const int* nComps, int nArrays) {
+  double* box = mg_p2p_pair_outbox(p->remote);
+  size_t off = 0;
+  const size_t n = (size_t)p->nPatchPoints;
+  for (int a = 0; a < nArrays; ++a) {
+    double* src = arr(p, names[a]);
+    if (!src) MG_FAIL(std::string("block interface '") + p->name + "': '" + names[a] + "' has not been collected");
+    MG_CUDA(cudaMemcpyAsync(box + off, src, n * nComps[a] * sizeof(double), cudaMemcpyDeviceToDevice, mg_stream()));
+    off += n * nComps[a];
+  }
+  return mg_p2p_exchange_pair(p->remote, off, 1);
+}
+
+int receive_remote(mg_patch* p, const char* const* names, const int* nComps, int nArrays) {
+  const double* box = mg_p2p_pair_inbox(p->remote);
+  size_t off = 0;
+  const size_t n = (size_t)p->nPatchPoints;
+  for (int a = 0; a < nArrays; ++a) off += n * nComps[a];
+  MG_TRY(mg_p2p_exchange_pair(p->remote, off, 2));
+  off = 0;
+  for (int a = 0; a < nArrays; ++a) {
+    double* dst = nullptr;
+    MG_TRY(mg_patch_alloc_array(p, names[a], nComps[a], &dst));
+    if (p->nPatchPoints)
+      { k_receive<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(p->globalSize[0], p->globalSize[1], p->globalSize[2],
+                                                                  p->reorder[0], p->reorder[1], nComps[a], box + off, dst); mg_count_launches(1); }
+    off += n * nComps[a];
+  }
+  MG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 
 bool mg_state_has_interfaces(const mg_state* s) {
@@ -459,6 +492,35 @@ int mg_interface_link(mg_patch* a, mg_patch* b, const int reorderA[3]) {
   return 0;
 }
 
+// The conforming patch lives in another process (another GPU of the box): the two exchange their collected face
+// data through a two-party P2P link.  `reorder` is THIS patch's index reordering (the inverse of the partner's);
+// the partner's signed penalty amounts and normal direction -- what the METRICS pseudo-exchange carries besides the
+// metrics (src/BlockInterfacePatchImpl.f90:667-703) -- are passed by the host, which swaps them when it swaps the
+// IPC handles.
+int mg_interface_link_remote(mg_patch* p, const int reorder[3], double partnerInviscidAmount,
+                             double partnerViscousAmount, int partnerNormalDirection, mg_p2p** link) {
+  if (!p || !link || p->type != MG_PATCH_BLOCK_INTERFACE)
+    MG_FAIL("mg_patch_link_interface_remote: not a SAT_BLOCK_INTERFACE patch");
+  const int nD = p->state->nD;
+  for (int j = 0; j < 3; ++j) {
+    const int o = reorder ? reorder[j] : j + 1;
+    if (o == 0 || std::abs(o) > 3 || (j < nD && std::abs(o) > nD)) MG_FAIL("mg_patch_link_interface_remote: invalid index reordering");
+    if (j == 2 && o != 3) MG_FAIL("mg_patch_link_interface_remote: reordering of the third index is not supported");
+    p->reorder[j] = o;
+  }
+  const mg_grid* g = p->state->grid;
+  if (g->procDims[0] * g->procDims[1] * g->procDims[2] != 1)
+    MG_FAIL("mg_patch_link_interface_remote: a block with interfaces must live in one process");
+  p->sigmaIR = partnerInviscidAmount;
+  p->sigmaVR = partnerViscousAmount;
+  p->normalR = partnerNormalDirection;
+  p->partner = nullptr;
+  p->metricsReady = false;
+  if (!p->remote) MG_TRY(mg_p2p_create_pair((size_t)std::max(1, p->nPatchPoints) * 2 * p->state->nU, &p->remote));
+  *link = p->remote;
+  return 0;
+}
+
 // collectInterfaceData -> exchange (+ reshape) -> disperseInterfaceData for every interface patch of the region
 // (reference src/RegionImpl.f90:1927-1958); the METRICS pseudo-mode (src/SolverImpl.f90:571-603) runs once.
 int mg_interfaces_exchange(const std::vector<mg_state*>& states, int mode) {
@@ -466,7 +528,8 @@ int mg_interfaces_exchange(const std::vector<mg_state*>& states, int mode) {
   for (mg_state* s : states)
     for (mg_patch* p : s->patches)
       if (p->type == MG_PATCH_BLOCK_INTERFACE) {
-        if (!p->partner) MG_FAIL(std::string("block interface '") + p->name + "' has no partner (mg_patch_link_interface)");
+        if (!p->partner && !p->remote)
+          MG_FAIL(std::string("block interface '") + p->name + "' has no partner (mg_patch_link_interface)");
         ifs.push_back(p);
       }
   if (ifs.empty()) return 0;
@@ -482,12 +545,23 @@ int mg_interfaces_exchange(const std::vector<mg_state*>& states, int mode) {
       p->sigmaVL = s->opt.viscosityOn ? p->viscousPenaltyAmount : 0.0;
       p->normalL = p->normalDirection;
     }
-    for (mg_patch* p : ifs) {
-      MG_TRY(receive(p, "metricsL", "metricsR", p->state->nD));
-      p->sigmaIR = p->partner->sigmaIL;
-      p->sigmaVR = p->partner->sigmaVL;
-      p->normalR = p->partner->normalL;
-      p->metricsReady = true;
+    {
+      static const char* const sendN[1] = {"metricsL"};
+      static const char* const recvN[1] = {"metricsR"};
+      for (mg_patch* p : ifs)
+        if (p->remote) { const int nc[1] = {p->state->nD}; MG_TRY(send_remote(p, sendN, nc, 1)); }
+      for (mg_patch* p : ifs) {
+        if (p->remote) {
+          const int nc[1] = {p->state->nD};
+          MG_TRY(receive_remote(p, recvN, nc, 1));      // sigma / normal of the partner came with the link
+        } else {
+          MG_TRY(receive(p, "metricsL", "metricsR", p->state->nD));
+          p->sigmaIR = p->partner->sigmaIL;
+          p->sigmaVR = p->partner->sigmaVL;
+          p->normalR = p->partner->normalL;
+        }
+        p->metricsReady = true;
+      }
     }
   }
   for (mg_patch* p : ifs) {
@@ -509,8 +583,26 @@ int mg_interfaces_exchange(const std::vector<mg_state*>& states, int mode) {
       MG_TRY(collect_to(p, W.comp(0), W.compStride, s->nU, "adjointVariablesL"));
     }
   }
+  // what travels per mode (reference collectInterfaceData, src/BlockInterfacePatchImpl.f90:592-700)
+  static const char* const sendF[2] = {"conservedVariablesL", "viscousFluxesL"};
+  static const char* const recvF[2] = {"conservedVariablesR", "viscousFluxesR"};
+  static const char* const sendA[2] = {"conservedVariablesL", "adjointVariablesL"};
+  static const char* const recvA[2] = {"conservedVariablesR", "adjointVariablesR"};
+  for (mg_patch* p : ifs) {
+    if (!p->remote) continue;
+    mg_state* s = p->state;
+    const int nc[2] = {s->nU, s->nU};
+    if (mode == MG_FORWARD) MG_TRY(send_remote(p, sendF, nc, s->opt.viscosityOn ? 2 : 1));
+    else MG_TRY(send_remote(p, sendA, nc, 2));
+  }
   for (mg_patch* p : ifs) {
     mg_state* s = p->state;
+    if (p->remote) {
+      const int nc[2] = {s->nU, s->nU};
+      if (mode == MG_FORWARD) MG_TRY(receive_remote(p, recvF, nc, s->opt.viscosityOn ? 2 : 1));
+      else MG_TRY(receive_remote(p, recvA, nc, 2));
+      continue;
+    }
     MG_TRY(receive(p, "conservedVariablesL", "conservedVariablesR", s->nU));
     if (mode == MG_FORWARD) {
       if (s->opt.viscosityOn) MG_TRY(receive(p, "viscousFluxesL", "viscousFluxesR", s->nU));

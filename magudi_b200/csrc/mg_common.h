@@ -116,6 +116,11 @@ struct mg_grid {
 };
 int mg_p2p_exchange_faces(struct mg_p2p* h, const double* in, size_t inCs, int nComp, int width,
                           const double** ghostPrev, const double** ghostNext);
+int mg_p2p_create_pair(size_t capacity, struct mg_p2p** out);
+double* mg_p2p_pair_outbox(struct mg_p2p* h);
+const double* mg_p2p_pair_inbox(struct mg_p2p* h);
+int mg_p2p_exchange_pair(struct mg_p2p* h, size_t count, int phase);   // phase 1: push, 2: wait + unpack
+extern "C" int mg_p2p_destroy(struct mg_p2p* h);
 int mg_p2p_check_all();       // fails when a halo exchange of any live handle has timed out
 int mg_p2p_exchange_view(struct mg_p2p* h, const double* comp0, size_t compStride, int nComp, int width);
 

@@ -393,7 +393,9 @@ static int p2p_exchange_field(mg_p2p* h, const MgField* fAll, int width, cudaStr
 // Exchange explicit device buffers with the two neighbours: sendLo -> prev's recvHi, sendHi -> next's recvLo
 // (count doubles each).  Same staging / flag protocol as the plane exchange.
 static int p2p_exchange_buffers(mg_p2p* h, const double* sendLo, const double* sendHi, double* recvLo, double* recvHi,
-                                size_t count, cudaStream_t st) {
+                                size_t count, cudaStream_t st, bool pairOnly = false, int phase = 3) {
+  // pairOnly: a two-party link (block interface): both parties push through side 0 into the other's face-1 staging.
+  // phase: bit 0 = push, bit 1 = unpack (a process with several links pushes on all of them before it waits on any)
   if (count > h->capacity) MG_FAIL("mg_p2p: face payload exceeds the staging capacity");
   const unsigned long long n = h->uses[0];
   const int parity = (int)(n & 1);
@@ -401,7 +403,7 @@ static int p2p_exchange_buffers(mg_p2p* h, const double* sendLo, const double* s
   PushPair pp;
   std::memset(&pp, 0, sizeof(pp));
   for (int side = 0; side < 2; ++side) {
-    if (!h->peer[side]) continue;
+    if (!h->peer[side] || (pairOnly && side == 1)) continue;
     PushArgs& a = pp.s[side];
     a.nComp = 1;
     a.chunk = count;
@@ -415,11 +417,15 @@ static int p2p_exchange_buffers(mg_p2p* h, const double* sendLo, const double* s
     a.error = h->error;
     a.vec = (count % 2 == 0) && ((uintptr_t)a.dst % 16 == 0) && ((uintptr_t)a.src[0] % 16 == 0);
   }
-  k_push<<<dim3(P2P_BLOCKS, 2), P2P_THREADS, 0, st>>>(pp);
+  if (phase & 1) {
+    k_push<<<dim3(P2P_BLOCKS, 2), P2P_THREADS, 0, st>>>(pp);
+    mg_count_launches(1);
+  }
+  if (!(phase & 2)) { MG_CUDA(cudaGetLastError()); return 0; }
   UnpackPair up;
   std::memset(&up, 0, sizeof(up));
   for (int face = 0; face < 2; ++face) {
-    if (!h->peer[face]) continue;
+    if (!h->peer[face] || (pairOnly && face == 0)) continue;
     UnpackArgs& a = up.s[face];
     a.nComp = 1;
     a.chunk = count;
@@ -434,7 +440,7 @@ static int p2p_exchange_buffers(mg_p2p* h, const double* sendLo, const double* s
   }
   k_unpack<<<dim3(P2P_BLOCKS, 2), P2P_THREADS, 0, st>>>(up);
   MG_CUDA(cudaGetLastError());
-  mg_count_launches(2);
+  mg_count_launches(1);
   h->uses[0] = h->uses[1] = n + 1;
   return 0;
 }
@@ -525,6 +531,40 @@ int mg_p2p_create_dir(mg_grid* g, int direction, int maxComp, int width, mg_p2p*
   g->haloDir[direction] = h;
   *out = h;
   return 0;
+}
+
+// A two-party link for block interfaces whose blocks live in different processes: `capacity` doubles each way.
+// Connect BOTH sides to the partner (mg_p2p_connect(h, 0, partner, 0); mg_p2p_connect(h, 1, partner, 1)).
+int mg_p2p_create_pair(size_t capacity, mg_p2p** out) {
+  if (!out || capacity == 0) MG_FAIL("mg_p2p_create_pair: invalid argument");
+  mg_p2p* h = new mg_p2p;
+  h->grid = nullptr;
+  h->direction = -1;
+  h->capacity = capacity + capacity % 2;
+  h->bytes = sizeof(Shared) + 4 * h->capacity * sizeof(double);
+  MG_CUDA(cudaMalloc(&h->base, h->bytes));
+  MG_CUDA(cudaMemset(h->base, 0, h->bytes));
+  MG_CUDA(cudaMalloc(&h->counters, 4 * sizeof(unsigned int)));
+  MG_CUDA(cudaMemset(h->counters, 0, 4 * sizeof(unsigned int)));
+  MG_CUDA(cudaHostAlloc(&h->error, sizeof(int), cudaHostAllocMapped));
+  *h->error = 0;
+  for (int i = 0; i < 2; ++i) {
+    MG_CUDA(cudaMalloc(&h->faceSend[i], h->capacity * sizeof(double)));
+    MG_CUDA(cudaMalloc(&h->faceRecv[i], h->capacity * sizeof(double)));
+  }
+  mg_p2p_register(h, true);
+  MG_CUDA(cudaDeviceSynchronize());
+  *out = h;
+  return 0;
+}
+double* mg_p2p_pair_outbox(mg_p2p* h) { return h ? h->faceSend[0] : nullptr; }
+const double* mg_p2p_pair_inbox(mg_p2p* h) { return h ? h->faceRecv[1] : nullptr; }
+// phase 1: send the first `count` doubles of the outbox; phase 2: the partner's land in the inbox (stream-ordered,
+// no host synchronisation).  A process pushes on all its links before it waits on any of them.
+int mg_p2p_exchange_pair(mg_p2p* h, size_t count, int phase) {
+  if (!h || !h->peer[0] || !h->peer[1]) MG_FAIL("mg_p2p_exchange_pair: the link is not connected to its partner");
+  MG_TRY(mg_halo_wait_pending());
+  return p2p_exchange_buffers(h, h->faceSend[0], nullptr, nullptr, h->faceRecv[1], count, mg_stream(), true, phase);
 }
 
 // 0 when no spin-wait timed out so far (synchronises the library stream)

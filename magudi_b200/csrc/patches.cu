@@ -452,6 +452,7 @@ int mg_patch_create_impl(mg_state* s, int type, const char* name, int normalDire
 void mg_patch_destroy_impl(mg_patch* p) {
   if (!p) return;
   for (auto& kv : p->arrays) cudaFree(kv.second.p);
+  if (p->remote) mg_p2p_destroy(p->remote);
   delete p;
 }
 

@@ -37,6 +37,7 @@ struct mg_patch {
   // SAT_BLOCK_INTERFACE (reference include/BlockInterfacePatch.f90): the conforming patch of the other block, this
   // patch's index reordering, and the penalty amounts / normal directions of both sides (METRICS exchange)
   mg_patch* partner = nullptr;
+  struct mg_p2p* remote = nullptr;     // the conforming patch lives in another process: two-party P2P link
   int reorder[3] = {1, 2, 3};
   bool metricsReady = false;
   double sigmaIL = 0.0, sigmaIR = 0.0, sigmaVL = 0.0, sigmaVR = 0.0;
@@ -57,6 +58,8 @@ int mg_patches_sponge_strengths_impl(mg_state* s);
 // block interfaces (interface.cu)
 bool mg_state_has_interfaces(const mg_state* s);
 int mg_interface_link(mg_patch* a, mg_patch* b, const int reorderA[3]);
+int mg_interface_link_remote(mg_patch* p, const int reorder[3], double partnerInviscidAmount,
+                             double partnerViscousAmount, int partnerNormalDirection, struct mg_p2p** link);
 int mg_interfaces_exchange(const std::vector<mg_state*>& states, int mode);
 int mg_interface_apply(mg_state* s, mg_patch* p, int mode);
 int mg_interfaces_adjoint_sources(mg_state* s, MgField* temp1);

@@ -206,6 +206,75 @@ class GpuHalo:
             self._p2p = None
 
 
+def invert_reordering(order):
+    """The partner's index reordering (``readPatchInterfaceInformation``, ``src/InterfaceHelperImpl.f90:96-105``)."""
+    inv = [0, 0, 0]
+    for l in (1, 2, 3):
+        for k in (1, 2, 3):
+            if abs(order[k - 1]) == l:
+                inv[l - 1] = -k if order[k - 1] < 0 else k
+                break
+    return tuple(inv)
+
+
+def _patch_global_size(patch):
+    gs = patch.state.grid.globalSize
+    out = []
+    for d in range(3):
+        a, b = patch.extent[2 * d], patch.extent[2 * d + 1]
+        n = gs[d] if d < len(gs) else 1
+        a = n + a + 1 if a < 0 else a
+        b = n + b + 1 if b < 0 else b
+        out.append(b - a + 1)
+    return tuple(out)
+
+
+def link_interfaces_remote(links):
+    """Couple SAT_BLOCK_INTERFACE patches whose conforming patches belong to blocks held by OTHER processes
+    (other GPUs of the node): the reference's ``exchangeInterfaceData`` between block communicators
+    (``src/InterfaceHelperImpl.f90:115-239``) as direct P2P stores.  Collective over the default group.
+
+    ``links``: this process's list of ``(patch, partnerRank, partnerPatchName, indexReordering)`` --
+    ``indexReordering`` is THIS patch's reordering (the partner passes the inverse).  ``torch.distributed`` is only
+    used here, once, to swap the IPC handles and the partners' penalty amounts / normal directions."""
+    lib = L.lib()
+    n = lib.mg_p2p_handle_size()
+    mine = {}
+    for patch, partnerRank, partnerName, _ in links:
+        sI, sV = C.c_double(0.0), C.c_double(0.0)
+        check(lib.mg_patch_penalty_amounts(patch._h, C.byref(sI), C.byref(sV)))
+        mine[patch.name] = (sI.value, sV.value, int(patch.normalDirection), _patch_global_size(patch))
+    table = [None] * dist.get_world_size()
+    dist.all_gather_object(table, mine)
+    handles = {}
+    for patch, partnerRank, partnerName, order in links:
+        if partnerName not in table[partnerRank]:
+            raise RuntimeError("rank %d holds no interface patch %r" % (partnerRank, partnerName))
+        sI, sV, nrm, size = table[partnerRank][partnerName]
+        mySize = _patch_global_size(patch)
+        if abs(order[0]) == 2 and abs(order[1]) == 1:
+            size = (size[1], size[0], size[2])
+        if tuple(size) != tuple(mySize):
+            raise RuntimeError("interface patches %r and %r do not conform" % (patch.name, partnerName))
+        o = (C.c_int * 3)(*[int(v) for v in order])
+        h = C.c_void_p()
+        check(lib.mg_patch_link_interface_remote(patch._h, o, sI, sV, nrm, C.byref(h)))
+        buf = C.create_string_buffer(n)
+        check(lib.mg_p2p_get_handle(h, buf))
+        handles[patch.name] = (h, bytes(buf.raw))
+    table = [None] * dist.get_world_size()
+    dist.all_gather_object(table, {k: v[1] for k, v in handles.items()})
+    keep = []
+    for patch, partnerRank, partnerName, _ in links:
+        h = handles[patch.name][0]
+        hb = C.create_string_buffer(table[partnerRank][partnerName], n)
+        keep.append(hb)
+        check(lib.mg_p2p_connect(h, 0, hb, 0))
+        check(lib.mg_p2p_connect(h, 1, hb, 1))
+    dist.barrier()
+    return keep
+
+
 def all_reduce_sum(value, device=None):
     """Sum a host scalar over ranks (inner products, cost functional)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:

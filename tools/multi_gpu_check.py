@@ -159,6 +159,77 @@ def run_general(shape, dims, rank, dev):
     return np.concatenate(out, axis=1), grid
 
 
+def run_blocks(world, rank, dev):
+    """Three curvilinear blocks coupled by SAT_BLOCK_INTERFACE patches with index reorderings (a transposing one and
+    one with both in-face indices reversed), block b on rank b % world: at world = 2 block 1's two interfaces are one
+    link to the other GPU (two-party P2P link) and one link inside the process.  Returns {block: forward / adjoint
+    RHS, then Q and w after one forward and one adjoint RK4 step} of the blocks this rank holds."""
+    shapes = [(12, 13, 12), (13, 12, 13), (12, 13, 14)]
+    orders = [(2, -1, 3), (-1, -2, 3)]
+    opt = core.SolverOptions(ratioOfSpecificHeats=1.4, viscosityOn=True, reynoldsNumberInverse=1.0 / 60.0,
+                             dissipationOn=True, compositeDissipation=False, dissipationAmount=0.01,
+                             useTargetState=False, discretizationType="SBP 2-4")
+    region = core.Region()
+    states, owner = {}, {}
+    for b, shp in enumerate(shapes):
+        owner[b] = b % world
+        if owner[b] != rank:
+            continue
+        grid = core.Grid(b + 1, shp, (core.NONE,) * 3, (0.0,) * 3, isCurvilinear=True)
+        grid.setupSpatialDiscretization(opt.discretizationType, opt.compositeDissipation, False, opt.dissipationOn)
+        grid.setCoordinates(general_coordinates(shp, (0, 0, 0), shp) + 0.1 * b)
+        assert not grid.update()
+        st = core.State(grid, opt)
+        Qg, Wg, _, _, _ = general_fields(shp, 20 + b)
+        st.conservedVariables = Qg.reshape(-1, 5, order="F")
+        st.adjointVariables = Wg.reshape(-1, 5, order="F")
+        region.addState(st)
+        states[b] = st
+
+    def face(shp, high):
+        k = shp[2] if high else 1
+        return [1, shp[0], 1, shp[1], k, k]
+    # (name, block, normal, extent); interface a <-> b with a's reordering
+    spec = {"b1.high": (0, -3, face(shapes[0], True)), "b2.low": (1, 3, face(shapes[1], False)),
+            "b1.low": (0, 3, face(shapes[0], False)), "b3.high": (2, -3, face(shapes[2], True))}
+    pairs = [("b1.high", "b2.low", orders[0]), ("b1.low", "b3.high", orders[1])]
+    patches = {}
+    for name, (b, nrm, ext) in spec.items():
+        if b in states:
+            patches[name] = states[b].addPatch("SAT_BLOCK_INTERFACE", name, nrm, ext, 1.0, 0.5)
+    remote = []
+    for a, b, order in pairs:
+        ra, rb = owner[spec[a][0]], owner[spec[b][0]]
+        if ra == rb:
+            if ra == rank:
+                patches[a].linkInterface(patches[b], order)
+        else:
+            if ra == rank:
+                remote.append((patches[a], rb, b, order))
+            if rb == rank:
+                remote.append((patches[b], ra, a, par.invert_reordering(order)))
+    keep = par.link_interfaces_remote(remote) if world > 1 else None
+    if not states:          # more ranks than blocks
+        return {}
+    region.setFused(False)
+    out = {b: [] for b in states}
+    for mode in (mb.FORWARD, mb.ADJOINT):
+        region.computeRhs(mode)
+        for b, st in states.items():
+            out[b].append(st.rightHandSide.copy())
+    integ = mb.RK4Integrator(region)
+    t = 0.0
+    for stage in range(1, 5):
+        t = integ.substepForward(t, 2e-3, 0, stage)
+    for stage in range(4, 0, -1):
+        t = integ.substepAdjoint(t, 2e-3, 0, stage)
+    for b, st in states.items():
+        out[b] += [st.conservedVariables, st.adjointVariables]
+    _lib.check(_lib.lib().mg_synchronize())
+    del keep
+    return {b: np.concatenate(v, axis=1) for b, v in out.items()}
+
+
 def compare(pieces, single, shape, ncomp, label, world):
     """pieces: (offset[3], localSize[3], local (nLocal, ncomp)) of every rank"""
     Qs = single.reshape(tuple(shape) + (ncomp,), order="F")
@@ -194,6 +265,8 @@ def check_all(world, rank, dev):
     for k, dims in brick.items():
         Bl, bgrid = run_general(bshape, dims, rank, dev)
         bpieces[k] = gathered(Bl, bgrid)
+    blocks = [None] * world
+    dist.all_gather_object(blocks, run_blocks(world, rank, dev))
     out = None
     if rank == 0:
         Qs, _ = run(shape, 1, 0, dev)
@@ -203,9 +276,19 @@ def check_all(world, rank, dev):
         e2 = compare(gpieces, Gs, gshape, 25, "operator path, slabs along k (patches, non-periodic; fwd/adj/lin RHS + RK4)", world)
         eb = {k: compare(v, Bs, bshape, 25, f"operator path, bricks split along {k} {brick[k]}", world)
               for k, v in bpieces.items()}
-        out = {"fused_forward_adjoint_rk4_max_rel_diff_vs_1gpu": e1, "general_path_patches_max_rel_diff_vs_1gpu": e2,
+        one = run_blocks(1, 0, dev)
+        ei = 0.0
+        for part in blocks:
+            for b, v in part.items():
+                for c0 in range(0, v.shape[1], 5):
+                    ei = max(ei, float(np.max(np.abs(v[:, c0:c0 + 5] - one[b][:, c0:c0 + 5])) /
+                                       np.max(np.abs(one[b][:, c0:c0 + 5]))))
+        print(f"multi_gpu_check: world={world} three blocks with SAT_BLOCK_INTERFACE patches on different GPUs "
+              f"(fwd/adj RHS + RK4): max rel diff vs single GPU = {ei:.3e}", file=sys.stderr)
+        out = {"block_interfaces_across_gpus_max_rel_diff_vs_1gpu": ei,
+               "fused_forward_adjoint_rk4_max_rel_diff_vs_1gpu": e1, "general_path_patches_max_rel_diff_vs_1gpu": e2,
                "bricks_max_rel_diff_vs_1gpu": eb, "ranks": world, "tolerance": 1e-12,
-               "ok": bool(e1 <= 1e-13 and e2 <= 1e-12 and all(e <= 1e-12 for e in eb.values()))}
+               "ok": bool(e1 <= 1e-13 and e2 <= 1e-12 and ei <= 1e-12 and all(e <= 1e-12 for e in eb.values()))}
     dist.barrier()
     return out
 
