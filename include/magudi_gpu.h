@@ -50,6 +50,10 @@ typedef struct mg_region mg_region;     /* t_Region,          include/Region.f90
 #define MG_COST_TARGET 5
 #define MG_ACTUATOR 6
 #define MG_SAT_BLOCK_INTERFACE 7
+#define MG_KOLMOGOROV_FORCING 8   /* src/KolmogorovForcingPatchImpl.f90 */
+#define MG_JET_EXCITATION 9       /* src/JetExcitationPatchImpl.f90 (a sponge-shaped patch) */
+#define MG_PROBE 10               /* src/ProbePatchImpl.f90 */
+#define MG_SAT_ADIABATIC_WALL 11  /* src/AdiabaticWallImpl.f90: its viscous penalties are zero in the reference */
 
 /* field ids for mg_state_set / mg_state_get (t_State members, include/State.f90:59-62) and
  * mg_grid_get / mg_grid_set (t_Grid members, include/Grid.f90:38-40) */
@@ -301,6 +305,50 @@ int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep
  * phase 1 = first adjoint sweep (needs ghost planes of the adjoint variables), phase 2 = second sweep +
  * RK4 update (needs ghost planes of MG_Q_FUSED_ADJOINT_DIFFUSION3).  Fused path only. */
 int mg_rk4_substep_adjoint_phase(mg_region* r, int phase, double* time, double dt, int timestep, int stage);
+/* t_JamesonRK3Integrator%substepForward (src/JamesonRK3IntegratorImpl.f90:56-131; the reference's adjoint and
+ * linearized RK3 substeps are empty): stage 1..3, same conventions as mg_rk4_substep. */
+int mg_rk3_substep(mg_region* r, double* time, double dt, int timestep, int stage, int updateStates);
+
+/* ------------------------------------------------------------------ remaining patch types, limits, filter
+ * KOLMOGOROV_FORCING: forcePerUnitMass = amplitude sin(2 pi wavenumber y) at the patch points
+ * (setupKolmogorovForcingPatch, src/KolmogorovForcingPatchImpl.f90:3-68; the keys patches/<name>/amplitude,
+ * /wavenumber); mg_patch_set_array("forcePerUnitMass") overrides it.  updateRhs: FORWARD / ADJOINT / LINEARIZED. */
+int mg_patch_kolmogorov_setup(mg_patch* p, double amplitude, int wavenumber);
+/* JET_EXCITATION (src/JetExcitationPatchImpl.f90:3-187): create it like a SPONGE (amounts = amplitude, exponent;
+ * mg_region_compute_sponge_strengths fills its spongeStrength), give the eigenmodes with
+ * mg_patch_set_array("perturbationReal" | "perturbationImag", nUnknowns * nModes) -- (nPatchPoints, nUnknowns, nModes)
+ * as read from <prefix>-NN.eigenmode_real/imag.q -- and their angular frequencies (aux(2) of those files) here. */
+int mg_patch_set_jet_modes(mg_patch* p, int nModes, const double* angularFrequencies);
+/* PROBE (src/ProbePatchImpl.f90:3-183, saveProbeData src/RegionImpl.f90:2211-2281): the probe buffer
+ * (nPatchPoints, nUnknowns, probe_buffer_size) lives on the device.  record collects the conserved (FORWARD) or
+ * adjoint (ADJOINT) variables into the next slot and tells when the buffer is full; flush copies the nRecords filled
+ * slots to the host (the caller appends them to <prefix>.probe_<name>.dat) and empties the buffer. */
+int mg_patch_probe_setup(mg_patch* p, int probeBufferSize);
+int mg_patch_probe_record(mg_patch* p, int mode, int* bufferIsFull);
+int mg_patch_probe_flush(mg_patch* p, double* host, int* nRecords);
+/* findMinimum / findMaximum (src/GridImpl.f90:1423-1577) of the density (variable 0) or the temperature (1) of the
+ * conserved variables on this rank: values and the 1-based global (i, j, k) of the first point attaining them.  The
+ * host combines ranks and applies isVariableWithinRange / checkSolutionLimits (src/GridImpl.f90:1579-1623,
+ * src/SolverImpl.f90:189-304: out of range when min <= minValue or max >= maxValue). */
+int mg_state_extrema(mg_state* s, int variable, double* vMin, int ijkMin[3], double* vMax, int ijkMax[3]);
+/* this rank's share of computeSolutionLimitPenalty BEFORE the penalty factor (src/RegionImpl.f90:1001-1092): the
+ * norm-weighted <f, f> of every variable whose range test failed on the whole grid */
+int mg_state_solution_limit_penalty(mg_state* s, const double densityRange[2], const double temperatureRange[2],
+                                    int densityOutOfRange, int temperatureOutOfRange, double* value);
+/* soft_solution_limits: computeRhs(ADJOINT) adds addSolutionLimitPenaltyAdjointForcing after the patch penalties
+ * (src/RegionImpl.f90:2002-2005, :1094-1221) while the switch is on (the adjoint driver turns it off for the terminal
+ * step).  Call after the states have been added.  The range test is done on this rank unless the host gives the
+ * result for the whole (decomposed) grid with mg_state_set_solution_limit_flags (-1, -1 = test locally again). */
+int mg_region_set_solution_limits(mg_region* r, int soft, const double densityRange[2],
+                                  const double temperatureRange[2], double penaltyFactor);
+int mg_region_solution_limit_forcing_switch(mg_region* r, int on);
+int mg_state_set_solution_limit_flags(mg_state* s, int densityOutOfRange, int temperatureOutOfRange);
+/* filter_solution (src/GridImpl.f90:603-615, applyFilter :1625-1663): "<filteringScheme> filter" operators
+ * ("Standard 5-point", "DRP 9-point"; NULL removes them) and their application to the conserved or adjoint
+ * variables, the directions visited in the order that rotates with the timestep */
+int mg_grid_setup_filter(mg_grid* g, const char* filteringScheme);
+int mg_state_apply_filter(mg_state* s, int field, int timestep);
+
 /* select the implementation: 0 = general operator-by-operator path, 1 = fused sweeps (default when
  * the configuration is covered) */
 int mg_region_set_fused(mg_region* r, int enable);

@@ -118,6 +118,19 @@ SIGNATURES = {
     "mg_patch_get_array": (C.c_int, [_P, C.c_char_p, C.c_int, _P]),
     "mg_patch_collect": (C.c_int, [_P, C.c_int, C.c_char_p]),
     "mg_patch_link_interface": (C.c_int, [_P, _P, _P]),
+    "mg_rk3_substep": (C.c_int, [_P, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int]),
+    "mg_patch_kolmogorov_setup": (C.c_int, [_P, C.c_double, C.c_int]),
+    "mg_patch_set_jet_modes": (C.c_int, [_P, C.c_int, _P]),
+    "mg_patch_probe_setup": (C.c_int, [_P, C.c_int]),
+    "mg_patch_probe_record": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
+    "mg_patch_probe_flush": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
+    "mg_state_extrema": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), _P, C.POINTER(C.c_double), _P]),
+    "mg_state_solution_limit_penalty": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "mg_region_set_solution_limits": (C.c_int, [_P, C.c_int, _P, _P, C.c_double]),
+    "mg_region_solution_limit_forcing_switch": (C.c_int, [_P, C.c_int]),
+    "mg_state_set_solution_limit_flags": (C.c_int, [_P, C.c_int, C.c_int]),
+    "mg_grid_setup_filter": (C.c_int, [_P, C.c_char_p]),
+    "mg_state_apply_filter": (C.c_int, [_P, C.c_int, C.c_int]),
     "mg_patch_penalty_amounts": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mg_patch_link_interface_remote": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_int, C.POINTER(_P)]),
     "mg_region_create": (C.c_int, [C.POINTER(_P)]),

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmagudi_gpu.so")
-SOURCES = ["c_api.cu", "stencil_host.cpp", "stencil_apply.cu", "grid.cu", "state.cu", "patches.cu", "interface.cu", "rhs_fused.cu", "fused_sweepbd_hot.cu", "fused_sweepbd_gen.cu", "fused_adjoint1_hot.cu", "fused_adjoint1_gen.cu", "p2p.cu"]
+SOURCES = ["c_api.cu", "stencil_host.cpp", "stencil_apply.cu", "grid.cu", "state.cu", "patches.cu", "interface.cu", "limits.cu", "rhs_fused.cu", "fused_sweepbd_hot.cu", "fused_sweepbd_gen.cu", "fused_adjoint1_hot.cu", "fused_adjoint1_gen.cu", "p2p.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -29,7 +29,8 @@ G_COORDINATES, G_METRICS, G_JACOBIAN, G_NORM, G_ARC_LENGTHS = 100, 101, 102, 103
 G_TARGET_MOLLIFIER, G_CONTROL_MOLLIFIER = 105, 106
 
 PATCH_TYPES = {"SAT_FAR_FIELD": 1, "SPONGE": 2, "SAT_SLIP_WALL": 3, "SAT_ISOTHERMAL_WALL": 4,
-               "COST_TARGET": 5, "ACTUATOR": 6, "SAT_BLOCK_INTERFACE": 7}
+               "COST_TARGET": 5, "ACTUATOR": 6, "SAT_BLOCK_INTERFACE": 7, "KOLMOGOROV_FORCING": 8,
+               "JET_EXCITATION": 9, "PROBE": 10, "SAT_ADIABATIC_WALL": 11}
 
 
 def pigeonhole(nPigeons, nHoles, holeIndex):
@@ -202,6 +203,11 @@ class Grid:
             self._h, s[0].encode(), s[1].encode(), s[2].encode(), int(dissipationOn), int(compositeDissipation),
             int(useContinuousAdjoint)))
 
+    def setupFilter(self, filteringScheme):
+        """Filter operators ``"<filteringScheme> filter"`` (``src/GridImpl.f90:603-615``): "Standard 5-point" or
+        "DRP 9-point"; ``None`` removes them."""
+        check(L.lib().mg_grid_setup_filter(self._h, filteringScheme.encode() if filteringScheme else None))
+
     def operator(self, which, direction):
         kinds = {"firstDerivative": 0, "adjointFirstDerivative": 1, "dissipation": 2, "dissipationTranspose": 3}
         h = L.lib().mg_grid_operator(self._h, kinds[which], int(direction))
@@ -336,6 +342,30 @@ class State:
     def computeAcousticNoiseAdjointForcing(self, timeRampFactor=1.0):
         """``t_AcousticNoise%computeAdjointForcing`` (``:208-280``): fills every COST_TARGET patch."""
         check(L.lib().mg_functional_acoustic_noise_forcing(self._h, float(timeRampFactor)))
+
+    def extrema(self, variable="density"):
+        """``findMinimum`` / ``findMaximum`` (``src/GridImpl.f90:1423-1577``) of the density or the temperature on
+        this rank: ``(min, (i, j, k), max, (i, j, k))`` with 1-based global indices of the first point attaining them."""
+        lo, hi = C.c_double(0.0), C.c_double(0.0)
+        ilo, ihi = (C.c_int * 3)(), (C.c_int * 3)()
+        check(L.lib().mg_state_extrema(self._h, {"density": 0, "temperature": 1}[variable], C.byref(lo), ilo,
+                                       C.byref(hi), ihi))
+        return lo.value, tuple(ilo), hi.value, tuple(ihi)
+
+    def isVariableWithinRange(self, variable, minValue=None, maxValue=None):
+        """``isVariableWithinRange`` (``src/GridImpl.f90:1579-1623``) on this rank:
+        ``(inRange, fOutsideRange, (i, j, k))``."""
+        lo, ilo, hi, ihi = self.extrema(variable)
+        ok, f, ijk = True, None, None
+        if minValue is not None and lo <= minValue:
+            ok, f, ijk = False, lo, ilo
+        if maxValue is not None and hi >= maxValue:
+            ok, f, ijk = False, hi, ihi
+        return ok, f, ijk
+
+    def applyFilter(self, field, timestep):
+        """``t_Grid%applyFilter`` (``src/GridImpl.f90:1625-1663``) on the conserved or adjoint variables."""
+        check(L.lib().mg_state_apply_filter(self._h, int(field), int(timestep)))
 
     def computePressureDrag(self, direction=(1.0, 0.0, 0.0)):
         """``t_PressureDrag%compute`` (``src/PressureDragImpl.f90:61-132``), local to this rank."""
@@ -501,6 +531,42 @@ class Patch:
         return parallel.scatter_patch_data((e[1] - e[0] + 1, e[3] - e[2] + 1, e[5] - e[4] + 1), self.localSize,
                                            self.patchOffset, patchGlobal, nComp, root)
 
+    def setupKolmogorovForcing(self, amplitude, wavenumber):
+        """``setupKolmogorovForcingPatch`` (``src/KolmogorovForcingPatchImpl.f90:3-68``): the keys
+        ``patches/<name>/amplitude`` and ``/wavenumber``."""
+        check(L.lib().mg_patch_kolmogorov_setup(self._h, float(amplitude), int(wavenumber)))
+
+    def setJetModes(self, angularFrequencies, perturbationReal, perturbationImag):
+        """Eigenmodes of a JET_EXCITATION patch (``src/JetExcitationPatchImpl.f90:47-111``):
+        ``perturbationReal / Imag`` are (nPatchPoints, nUnknowns, nModes)."""
+        w = np.ascontiguousarray(angularFrequencies, dtype=np.float64)
+        nU = self.state.nUnknowns
+        check(L.lib().mg_patch_set_jet_modes(self._h, int(w.size), w.ctypes.data_as(C.c_void_p)))
+        if w.size:
+            self.setArray("perturbationReal", np.asarray(perturbationReal).reshape(-1, nU * w.size, order="F"))
+            self.setArray("perturbationImag", np.asarray(perturbationImag).reshape(-1, nU * w.size, order="F"))
+
+    def setupProbe(self, probeBufferSize=1):
+        """``setupProbePatch`` (``src/ProbePatchImpl.f90:3-43``): ``probe_buffer_size`` slots on the device."""
+        check(L.lib().mg_patch_probe_setup(self._h, int(probeBufferSize)))
+        self._probeHost = np.zeros(max(self.nPatchPoints, 1) * self.state.nUnknowns * int(probeBufferSize))
+        self.probeFileOffset = 0
+
+    def probeRecord(self, mode=FORWARD):
+        """One slot of ``saveProbeData`` (``src/RegionImpl.f90:2259-2270``); True when the buffer is full."""
+        full = C.c_int(0)
+        check(L.lib().mg_patch_probe_record(self._h, int(mode), C.byref(full)))
+        return bool(full.value)
+
+    def probeFlush(self):
+        """The filled slots as (nPatchPoints, nUnknowns, nRecords) -- what ``saveSolutionOnProbe`` writes
+        (``src/ProbePatchImpl.f90:131-183``) -- and an empty buffer afterwards."""
+        nU = self.state.nUnknowns
+        n = C.c_int(0)
+        buf = self._probeHost
+        check(L.lib().mg_patch_probe_flush(self._h, buf.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return np.array(buf[:self.nPatchPoints * nU * n.value]).reshape((self.nPatchPoints, nU, n.value), order="F")
+
     def linkInterface(self, other, indexReordering=(1, 2, 3)):
         """``self conforms_with other`` (``readPatchInterfaceInformation``, ``src/InterfaceHelperImpl.f90:3-112``):
         both must be SAT_BLOCK_INTERFACE patches of states of one region; ``other`` gets the inverted reordering."""
@@ -540,6 +606,93 @@ class Region:
 
     def computeRhs(self, mode, timestep=0, stage=1):
         check(L.lib().mg_region_compute_rhs(self._h, int(mode), int(timestep), int(stage)))
+
+    def setSolutionLimits(self, densityRange, temperatureRange, soft=False, penaltyFactor=0.0):
+        """``enable_solution_limits`` / ``soft_solution_limits`` with ``solverOptions%densityRange``,
+        ``%temperatureRange`` and ``%solutionLimitPenaltyFactor``.  With ``soft``, ``computeRhs(ADJOINT)`` adds
+        ``addSolutionLimitPenaltyAdjointForcing`` (``src/RegionImpl.f90:2002-2005``)."""
+        self.densityRange = tuple(float(v) for v in densityRange)
+        self.temperatureRange = tuple(float(v) for v in temperatureRange)
+        self.softSolutionLimits = bool(soft)
+        self.solutionLimitPenaltyFactor = float(penaltyFactor)
+        d = (C.c_double * 2)(*self.densityRange)
+        t = (C.c_double * 2)(*self.temperatureRange)
+        check(L.lib().mg_region_set_solution_limits(self._h, int(soft), d, t, float(penaltyFactor)))
+
+    def setSolutionLimitForcingSwitch(self, on):
+        """``region%solutionLimitPenaltyAdjointForcingSwitch`` (off for the terminal adjoint step)."""
+        check(L.lib().mg_region_solution_limit_forcing_switch(self._h, int(bool(on))))
+
+    def checkSolutionLimits(self):
+        """``checkSolutionLimits`` (``src/SolverImpl.f90:189-304``): ``None`` when the solution is admissible, else the
+        reference's message (soft limits: density / temperature must stay positive; hard limits: inside the ranges)."""
+        from . import parallel
+        msg = None
+        for g, s in zip(self.grids, self.states):
+            for var, rng in (("density", self.densityRange), ("temperature", self.temperatureRange)):
+                lo, ilo, hi, ihi = parallel.combine_extrema(s.extrema(var))
+                name = var.capitalize()
+                if self.softSolutionLimits:
+                    if lo <= 0.0:
+                        msg = "%s on grid %d at (%d, %d, %d): %9.2E is not positive!" % ((name, g.index) + ilo + (lo,))
+                else:
+                    f, ijk = None, None
+                    if lo <= rng[0]:
+                        f, ijk = lo, ilo
+                    if hi >= rng[1]:
+                        f, ijk = hi, ihi
+                    if f is not None:
+                        msg = "%s on grid %d at (%d, %d, %d): %9.2E out of range (%9.2E, %9.2E)!" % (
+                            (name, g.index) + ijk + (f, rng[0], rng[1]))
+                if msg:
+                    return msg
+        return None
+
+    def computeSolutionLimitPenalty(self):
+        """``computeSolutionLimitPenalty`` (``src/RegionImpl.f90:1001-1092``), summed over ranks."""
+        from . import parallel
+        total = 0.0
+        d = (C.c_double * 2)(*self.densityRange)
+        t = (C.c_double * 2)(*self.temperatureRange)
+        for s in self.states:
+            flags = []
+            for var, rng in (("density", self.densityRange), ("temperature", self.temperatureRange)):
+                lo, _, hi, _ = parallel.combine_extrema(s.extrema(var))
+                flags.append(int(lo <= rng[0] or hi >= rng[1]))
+            if not any(flags):
+                continue
+            r = C.c_double(0.0)
+            check(L.lib().mg_state_solution_limit_penalty(s._h, d, t, flags[0], flags[1], C.byref(r)))
+            total += r.value
+        return self.solutionLimitPenaltyFactor * parallel.all_reduce_sum(total)
+
+    def saveProbeData(self, mode=FORWARD, finish=False, outputPrefix=None):
+        """``saveProbeData`` (``src/RegionImpl.f90:2211-2281``): every PROBE patch records the conserved (FORWARD) or
+        adjoint variables; a full buffer (or ``finish``) is appended to ``<outputPrefix>.probe_<name>.dat`` as raw
+        fp64 in patch-global Fortran order (``saveSolutionOnProbe``, ``src/ProbePatchImpl.f90:131-183``).  Returns
+        the flushed arrays by patch name."""
+        out = {}
+        for s in self.states:
+            for p in s.patches:
+                if p.patchType != "PROBE" or p.nPatchPoints <= 0:
+                    continue
+                full = False if finish else p.probeRecord(mode)
+                if finish or full:
+                    data = p.probeFlush()
+                    if data.shape[2] == 0:
+                        continue
+                    out[p.name] = data
+                    if outputPrefix is not None:
+                        e = p.extent
+                        g = (e[1] - e[0] + 1, e[3] - e[2] + 1, e[5] - e[4] + 1)
+                        glob = p.gatherData(data.reshape(p.nPatchPoints, -1, order="F")) if tuple(p.localSize) != g \
+                            else data.reshape(p.nPatchPoints, -1, order="F")
+                        if glob is not None:
+                            with open("%s.probe_%s.dat" % (outputPrefix, p.name), "r+b" if p.probeFileOffset else "wb") as f:
+                                f.seek(p.probeFileOffset)
+                                f.write(np.asfortranarray(glob).tobytes(order="F"))
+                        p.probeFileOffset += 8 * int(np.prod(g)) * data.shape[1] * data.shape[2]
+        return out
 
     def setFused(self, enable=True):
         check(L.lib().mg_region_set_fused(self._h, int(bool(enable))))
@@ -590,6 +743,21 @@ class RK4Integrator:
         t = C.c_double(time)
         check(L.lib().mg_rk4_substep(self.region._h, ADJOINT, C.byref(t), float(timeStepSize), int(timestep),
                                      int(stage), 0))
+        return t.value
+
+
+class JamesonRK3Integrator:
+    """``t_JamesonRK3Integrator`` (``src/JamesonRK3IntegratorImpl.f90``): forward substeps only, like the reference."""
+    nStages = 3
+    norm = (0.0, 0.0, 1.0)
+
+    def __init__(self, region: Region):
+        self.region = region
+
+    def substepForward(self, time, timeStepSize, timestep, stage, updateStates=True):
+        t = C.c_double(time)
+        check(L.lib().mg_rk3_substep(self.region._h, C.byref(t), float(timeStepSize), int(timestep), int(stage),
+                                     int(updateStates)))
         return t.value
 
 

@@ -697,7 +697,8 @@ int mg_patch_create(mg_state* s, int type, const char* name, int normalDirection
   if (!s || !out) MG_FAIL("mg_patch_create: null argument");
   MG_TRY(mg_patch_create_impl(s, type, name, normalDirection, extent, out));
   mg_patch* p = *out;
-  if (type == MG_PATCH_SPONGE) {     // the two amounts carry sponge_amount and sponge_exponent
+  if (type == MG_PATCH_SPONGE || type == MG_PATCH_JET_EXCITATION) {     // the two amounts carry sponge_amount (jet
+    // excitation: patches/<name>/amplitude, src/JetExcitationPatchImpl.f90:47-49) and sponge_exponent
     p->spongeAmount = inviscidPenaltyAmount;
     p->spongeExponent = (int)std::lround(viscousPenaltyAmount);
   }
@@ -865,6 +866,105 @@ int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep
     t = *time;
     MG_TRY(mg_rk4_substep_impl(s, mode, &t, dt, timestep, stage));
     if (updateStates && mode == MG_FORWARD) {
+      if (mg_state_uses_fused_rhs(s, MG_FORWARD)) MG_TRY(mg_fused_sweepA(s));
+      else MG_TRY(mg_state_update_impl(s, nullptr));
+    }
+  }
+  *time = t;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ SURVEY 8 f4
+int mg_patch_kolmogorov_setup(mg_patch* p, double amplitude, int wavenumber) {
+  if (!p) MG_FAIL("mg_patch_kolmogorov_setup: null handle");
+  return mg_patch_kolmogorov_setup_impl(p, amplitude, wavenumber);
+}
+int mg_patch_set_jet_modes(mg_patch* p, int nModes, const double* angularFrequencies) {
+  if (!p || p->type != MG_PATCH_JET_EXCITATION) MG_FAIL("mg_patch_set_jet_modes: not a JET_EXCITATION patch");
+  if (nModes < 0 || (nModes > 0 && !angularFrequencies)) MG_FAIL("mg_patch_set_jet_modes: invalid argument");
+  nModes = std::min(nModes, MG_JET_MAX_MODES);        // src/JetExcitationPatchImpl.f90:53
+  p->angularFrequencies.assign(angularFrequencies, angularFrequencies + nModes);
+  return 0;
+}
+int mg_patch_probe_setup(mg_patch* p, int probeBufferSize) {
+  if (!p) MG_FAIL("mg_patch_probe_setup: null handle");
+  return mg_patch_probe_setup_impl(p, probeBufferSize);
+}
+int mg_patch_probe_record(mg_patch* p, int mode, int* bufferIsFull) {
+  if (!p) MG_FAIL("mg_patch_probe_record: null handle");
+  return mg_patch_probe_record_impl(p, mode, bufferIsFull);
+}
+int mg_patch_probe_flush(mg_patch* p, double* host, int* nRecords) {
+  if (!p) MG_FAIL("mg_patch_probe_flush: null handle");
+  return mg_patch_probe_flush_impl(p, host, nRecords);
+}
+int mg_state_extrema(mg_state* s, int variable, double* vMin, int ijkMin[3], double* vMax, int ijkMax[3]) {
+  if (!s) MG_FAIL("mg_state_extrema: null handle");
+  return mg_state_extrema_impl(s, variable, vMin, ijkMin, vMax, ijkMax);
+}
+int mg_state_solution_limit_penalty(mg_state* s, const double densityRange[2], const double temperatureRange[2],
+                                    int densityOutOfRange, int temperatureOutOfRange, double* value) {
+  if (!s || !densityRange || !temperatureRange || !value) MG_FAIL("mg_state_solution_limit_penalty: null argument");
+  return mg_state_limit_penalty_impl(s, densityRange, temperatureRange, densityOutOfRange, temperatureOutOfRange, value);
+}
+int mg_region_set_solution_limits(mg_region* r, int soft, const double densityRange[2],
+                                  const double temperatureRange[2], double penaltyFactor) {
+  if (!r) MG_FAIL("mg_region_set_solution_limits: null handle");
+  if (soft && (!densityRange || !temperatureRange)) MG_FAIL("mg_region_set_solution_limits: null range");
+  for (mg_state* s : r->states) {
+    s->limits.soft = soft != 0;
+    if (soft) {
+      for (int i = 0; i < 2; ++i) { s->limits.densityRange[i] = densityRange[i]; s->limits.temperatureRange[i] = temperatureRange[i]; }
+      s->limits.penaltyFactor = penaltyFactor;
+    }
+  }
+  return 0;
+}
+int mg_region_solution_limit_forcing_switch(mg_region* r, int on) {
+  if (!r) MG_FAIL("mg_region_solution_limit_forcing_switch: null handle");
+  for (mg_state* s : r->states) s->limits.forcingSwitch = on != 0;
+  return 0;
+}
+int mg_state_set_solution_limit_flags(mg_state* s, int densityOutOfRange, int temperatureOutOfRange) {
+  if (!s) MG_FAIL("mg_state_set_solution_limit_flags: null handle");
+  s->limits.rhoOut = densityOutOfRange;
+  s->limits.tOut = temperatureOutOfRange;
+  return 0;
+}
+int mg_grid_setup_filter(mg_grid* g, const char* filteringScheme) {
+  if (!g) MG_FAIL("mg_grid_setup_filter: null handle");
+  return mg_grid_setup_filter_impl(g, filteringScheme);
+}
+int mg_state_apply_filter(mg_state* s, int field, int timestep) {
+  if (!s) MG_FAIL("mg_state_apply_filter: null handle");
+  if (field != MG_Q_CONSERVED && field != MG_Q_ADJOINT) MG_FAIL("mg_state_apply_filter: field must be the conserved or adjoint variables");
+  MgField* f = state_field(s, field);
+  if (!f || !f->p) MG_FAIL("mg_state_apply_filter: the field has not been set");
+  MG_TRY(mg_state_make_exclusive(s, f, true));
+  MG_TRY(mg_grid_apply_filter_impl(s->grid, f, timestep));
+  if (field == MG_Q_CONSERVED) { s->dependentValid = false; s->fusedValid = false; }
+  return 0;
+}
+// t_JamesonRK3Integrator%substepForward (reference src/JamesonRK3IntegratorImpl.f90:56-131); the adjoint and
+// linearized substeps of the reference are empty.
+int mg_rk3_substep(mg_region* r, double* time, double dt, int timestep, int stage, int updateStates) {
+  (void)timestep;
+  if (!r || !time) MG_FAIL("mg_rk3_substep: null argument");
+  if (stage < 1 || stage > 3) MG_FAIL("mg_rk3_substep: stage must be 1..3");
+  double t = *time;
+  if (region_has_interfaces(r)) {
+    for (mg_state* s : r->states) {
+      if (stage == 1) s->timeProgressive = *time + dt / 2.0;
+      if (stage == 2) { s->time = *time + dt / 2.0; s->timeProgressive = *time + dt; }
+      if (stage == 3) s->time = *time + dt / 2.0;
+    }
+    MG_TRY(region_compute_rhs(r, MG_FORWARD));
+    for (mg_state* s : r->states) s->rhsReady = true;
+  }
+  for (mg_state* s : r->states) {
+    t = *time;
+    MG_TRY(mg_rk3_substep_impl(s, &t, dt, stage));
+    if (updateStates) {
       if (mg_state_uses_fused_rhs(s, MG_FORWARD)) MG_TRY(mg_fused_sweepA(s));
       else MG_TRY(mg_state_update_impl(s, nullptr));
     }

@@ -266,7 +266,7 @@ void mg_grid_destroy_impl(mg_grid* g) {
   if (g->iblank) cudaFree(g->iblank);
   for (int i = 0; i < 3; ++i) {
     for (mg_stencil* s : {g->firstDerivative[i], g->adjointFirstDerivative[i], g->dissipation[i],
-                          g->dissipationTranspose[i]})
+                          g->dissipationTranspose[i], g->filter[i]})
       if (s) {
         if (s->d_op) cudaFree(s->d_op);
         delete s;

@@ -57,6 +57,12 @@ struct mg_state {
   std::vector<mg_patch*> patches;
   bool dependentValid = false;
   bool rhsReady = false;            // the region has already evaluated the RHS of this substep (block interfaces)
+  // soft solution limits (reference src/RegionImpl.f90:1094-1221, :2002-2005): adjoint forcing of the penalty
+  struct SolutionLimits {
+    bool soft = false, forcingSwitch = true;
+    double densityRange[2] = {0.0, 0.0}, temperatureRange[2] = {0.0, 0.0}, penaltyFactor = 0.0;
+    int rhoOut = -1, tOut = -1;     // range test of the whole grid given by the host (decomposed grids); -1: test here
+  } limits;
   PhysParams phys() const {
     PhysParams p;
     p.gamma = opt.ratioOfSpecificHeats;
@@ -91,6 +97,14 @@ bool mg_state_uses_fused_rhs(const mg_state* s, int mode);
 void mg_rk4_set_times(mg_state* s, int mode, double time, double dt, int stage);
 int mg_rk4_substep_impl(mg_state* s, int mode, double* time, double dt, int timestep, int stage);
 int mg_state_cfl_dt_impl(mg_state* s, int wantDt, double given, double* result);
+int mg_state_extrema_impl(mg_state* s, int which, double* vMin, int ijkMin[3], double* vMax, int ijkMax[3]);
+int mg_state_limit_penalty_impl(mg_state* s, const double densityRange[2], const double temperatureRange[2],
+                                int rhoOut, int tOut, double* value);
+int mg_state_limit_forcing_impl(mg_state* s, const double densityRange[2], const double temperatureRange[2],
+                                int rhoOut, int tOut, double penaltyFactor);
+int mg_grid_setup_filter_impl(mg_grid* g, const char* filteringScheme);
+int mg_grid_apply_filter_impl(mg_grid* g, MgField* f, int timestep);
+int mg_rk3_substep_impl(mg_state* s, double* time, double dt, int stage);
 int mg_patches_apply(mg_state* s, int mode);
 int mg_patches_collect_viscous(mg_state* s);
 int mg_patches_farfield_adjoint_sources(mg_state* s, MgField* temp1);

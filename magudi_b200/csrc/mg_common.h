@@ -101,6 +101,7 @@ struct mg_grid {
   mg_stencil* adjointFirstDerivative[3] = {nullptr, nullptr, nullptr};
   mg_stencil* dissipation[3] = {nullptr, nullptr, nullptr};
   mg_stencil* dissipationTranspose[3] = {nullptr, nullptr, nullptr};
+  mg_stencil* filter[3] = {nullptr, nullptr, nullptr};      // applyFilter (src/GridImpl.f90:603-615, 1625-1663)
   int compositeDissipation = 1;
   int dissipationOn = 0;
   MgField coordinates, metrics, jacobian, norm, arcLengths, targetMollifier, controlMollifier;

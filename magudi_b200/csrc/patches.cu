@@ -339,6 +339,64 @@ __global__ void k_patch_add(AddArgs a) {
   for (int c = 0; c < a.nComp; ++c) a.rhs[(size_t)c * a.cs + p] += f * a.data[(size_t)c * a.g.n + q];
 }
 
+// addKolmogorovForcing (reference src/KolmogorovForcingPatchImpl.f90:86-176): a body force per unit mass along x
+struct KolmogorovArgs {
+  PatchGeom g;
+  const double* force;      // forcePerUnitMass at the patch points
+  const double *Q, *W;
+  size_t csQ, csW, cs;
+  const int* iblank;
+  double* rhs;
+  int mode;
+};
+
+__global__ void k_kolmogorov(KolmogorovArgs a) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.g.n) return;
+  const size_t p = a.g.gridIndex(q);
+  if (a.iblank && a.iblank[p] == 0) return;
+  const double f = a.force[q];
+  if (a.mode == MG_FORWARD) a.rhs[a.cs + p] += a.Q[p] * f;
+  else if (a.mode == MG_ADJOINT) a.rhs[p] -= a.W[a.csW + p] * f;
+  else a.rhs[a.cs + p] += a.W[p] * f;
+}
+
+// forcePerUnitMass = amplitude sin(2 pi n y) (src/KolmogorovForcingPatchImpl.f90:47-66)
+__global__ void k_kolmogorov_setup(PatchGeom g, const double* y, const int* iblank, double amplitude, double twoPiN,
+                                   double* out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= g.n) return;
+  const size_t p = g.gridIndex(q);
+  out[q] = (iblank && iblank[p] == 0) ? 0.0 : amplitude * sin(twoPiN * y[p]);
+}
+
+// addJetExcitation (reference src/JetExcitationPatchImpl.f90:128-187)
+struct JetArgs {
+  PatchGeom g;
+  const double *strength, *re, *im;   // re / im: (nPatchPoints, nUnknowns, nModes), point fastest
+  const int* iblank;
+  double* rhs;
+  size_t cs;
+  int nU, nModes;
+  double c[MG_JET_MAX_MODES], s[MG_JET_MAX_MODES];
+};
+
+__global__ void k_jet_excitation(const __grid_constant__ JetArgs a) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.g.n) return;
+  const size_t p = a.g.gridIndex(q);
+  if (a.iblank && a.iblank[p] == 0) return;
+  const double st = a.strength[q];
+  for (int c = 0; c < a.nU; ++c) {
+    double r = a.rhs[(size_t)c * a.cs + p];
+    for (int l = 0; l < a.nModes; ++l) {
+      const size_t e = ((size_t)l * a.nU + c) * a.g.n + q;
+      r -= st * (a.re[e] * a.c[l] - a.im[e] * a.s[l]);
+    }
+    a.rhs[(size_t)c * a.cs + p] = r;
+  }
+}
+
 __global__ void k_collect(PatchGeom g, const double* field, size_t cs, int nComp, double* out) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= g.n) return;
@@ -433,14 +491,21 @@ int mg_patch_create_impl(mg_state* s, int type, const char* name, int normalDire
   if (empty) { for (int d = 0; d < 3; ++d) { p->localLo[d] = 0; p->localSize[d] = 0; } }
   p->nPatchPoints = p->localSize[0] * p->localSize[1] * p->localSize[2];
   const int ad = std::abs(normalDirection);
-  if (type != MG_PATCH_SPONGE && type != MG_PATCH_ACTUATOR && type != MG_PATCH_COST_TARGET) {
+  if (type < MG_PATCH_FARFIELD || type > MG_PATCH_ADIABATIC_WALL) { delete p; MG_FAIL("mg_patch_create: unknown patch type"); }
+  if (type != MG_PATCH_SPONGE && type != MG_PATCH_ACTUATOR && type != MG_PATCH_COST_TARGET &&
+      type != MG_PATCH_KOLMOGOROV_FORCING && type != MG_PATCH_JET_EXCITATION && type != MG_PATCH_PROBE) {
     if (ad < 1 || ad > g->nD) { delete p; MG_FAIL("mg_patch_create: normal direction is invalid"); }
     if (extent[2 * (ad - 1)] != extent[2 * (ad - 1) + 1]) {
       delete p;
       MG_FAIL("mg_patch_create: patch extends more than 1 grid point along normal direction");
     }
   }
-  if (type == MG_PATCH_FARFIELD || type == MG_PATCH_SPONGE) {
+  if (type == MG_PATCH_KOLMOGOROV_FORCING) {     // verifyKolmogorovForcingPatchUsage (:178-237)
+    if (g->nD == 1) { delete p; MG_FAIL("mg_patch_create: KOLMOGOROV_FORCING can't be used with a 1D grid"); }
+    for (int d = 0; d < g->nD; ++d)
+      if (extent[2 * d] == extent[2 * d + 1]) { delete p; MG_FAIL("mg_patch_create: KOLMOGOROV_FORCING expects a patch of the grid's dimension"); }
+  }
+  if (type == MG_PATCH_FARFIELD || type == MG_PATCH_SPONGE || type == MG_PATCH_JET_EXCITATION) {
     if (!s->opt.useTargetState) { delete p; MG_FAIL("mg_patch_create: no target state available for this patch type"); }
   }
   s->patches.push_back(p);
@@ -452,6 +517,7 @@ int mg_patch_create_impl(mg_state* s, int type, const char* name, int normalDire
 void mg_patch_destroy_impl(mg_patch* p) {
   if (!p) return;
   for (auto& kv : p->arrays) cudaFree(kv.second.p);
+  cudaFree(p->probeBuffer);
   if (p->remote) mg_p2p_destroy(p->remote);
   delete p;
 }
@@ -548,7 +614,7 @@ int mg_patches_sponge_strengths_impl(mg_state* s) {
   mg_grid* g = s->grid;
   for (int dir = 0; dir < s->nD; ++dir) {
     bool any = false;
-    for (mg_patch* p : s->patches) any = any || (p->type == MG_PATCH_SPONGE && std::abs(p->normalDirection) == dir + 1);
+    for (mg_patch* p : s->patches) any = any || ((p->type == MG_PATCH_SPONGE || p->type == MG_PATCH_JET_EXCITATION) && std::abs(p->normalDirection) == dir + 1);
     if (!any) continue;
     if (g->procDims[dir] > 1)
       MG_FAIL("computeSpongeStrengths: sponges along a decomposed direction need the arc length of the whole line; "
@@ -560,7 +626,8 @@ int mg_patches_sponge_strengths_impl(mg_state* s) {
     { k_arc_from_derivatives<<<(unsigned)((g->N + 255) / 256), 256, 0, mg_stream()>>>(cd.comp(0), cd.compStride, s->nD, arc.comp(0), g->N); mg_count_launches(1); }
     MG_CUDA(cudaGetLastError());
     for (mg_patch* p : s->patches) {
-      if (p->type != MG_PATCH_SPONGE || std::abs(p->normalDirection) != dir + 1 || p->nPatchPoints <= 0) continue;
+      if ((p->type != MG_PATCH_SPONGE && p->type != MG_PATCH_JET_EXCITATION) || std::abs(p->normalDirection) != dir + 1 ||
+          p->nPatchPoints <= 0) continue;
       double* out = nullptr;
       MG_TRY(mg_patch_alloc_array(p, "spongeStrength", 1, &out));
       SpongeSetupArgs a;
@@ -698,7 +765,52 @@ int mg_patches_apply(mg_state* s, int mode) {
         { k_sponge<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a); mg_count_launches(1); }
         break;
       }
-      case MG_PATCH_SLIP_WALL:
+      case MG_PATCH_KOLMOGOROV_FORCING: {
+        auto it = p->arrays.find("forcePerUnitMass");
+        if (it == p->arrays.end()) MG_FAIL("Kolmogorov forcing patch: forcePerUnitMass has not been set (mg_patch_kolmogorov_setup)");
+        KolmogorovArgs a;
+        a.g = geom(p);
+        a.force = it->second.p;
+        a.Q = Q.comp(0); a.csQ = Q.compStride;
+        a.W = W.p ? W.comp(0) : nullptr; a.csW = W.compStride;
+        a.iblank = g->iblank;
+        a.rhs = s->rhs.comp(0);
+        a.cs = s->rhs.compStride;
+        a.mode = mode;
+        { k_kolmogorov<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a); mg_count_launches(1); }
+        break;
+      }
+      case MG_PATCH_JET_EXCITATION: {
+        if (mode != MG_FORWARD) break;          // src/JetExcitationPatchImpl.f90:160
+        const int nModes = (int)p->angularFrequencies.size();
+        if (nModes == 0) break;
+        auto is = p->arrays.find("spongeStrength"), ir = p->arrays.find("perturbationReal"),
+             ii = p->arrays.find("perturbationImag");
+        if (is == p->arrays.end()) MG_FAIL("jet excitation patch: spongeStrength has not been set");
+        if (ir == p->arrays.end() || ii == p->arrays.end() || ir->second.nComp != s->nU * nModes ||
+            ii->second.nComp != s->nU * nModes)
+          MG_FAIL("jet excitation patch: perturbationReal / perturbationImag (nPatchPoints, nUnknowns * nModes) have not been set");
+        JetArgs a;
+        a.g = geom(p);
+        a.strength = is->second.p;
+        a.re = ir->second.p;
+        a.im = ii->second.p;
+        a.iblank = g->iblank;
+        a.rhs = s->rhs.comp(0);
+        a.cs = s->rhs.compStride;
+        a.nU = s->nU;
+        a.nModes = nModes;
+        for (int l = 0; l < nModes; ++l) {
+          a.c[l] = std::cos(p->angularFrequencies[l] * s->time);
+          a.s[l] = std::sin(p->angularFrequencies[l] * s->time);
+        }
+        { k_jet_excitation<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a); mg_count_launches(1); }
+        break;
+      }
+      case MG_PATCH_PROBE:
+        break;                                  // updateProbePatch is empty (src/ProbePatchImpl.f90:71-97)
+      case MG_PATCH_ADIABATIC_WALL:             // the reference's adiabatic viscous penalties are identically zero
+      case MG_PATCH_SLIP_WALL:                  // (src/AdiabaticWallImpl.f90:128): what is left is the slip wall
       case MG_PATCH_ISOTHERMAL_WALL: {
         if (mode == MG_ADJOINT && s->opt.useContinuousAdjoint) break;
         WallArgs a;
@@ -774,6 +886,67 @@ int mg_patches_apply(mg_state* s, int mode) {
     }
     MG_CUDA(cudaGetLastError());
   }
+  return 0;
+}
+
+// setupKolmogorovForcingPatch (reference src/KolmogorovForcingPatchImpl.f90:3-68): the keys
+// patches/<name>/amplitude and patches/<name>/wavenumber
+int mg_patch_kolmogorov_setup_impl(mg_patch* p, double amplitude, int wavenumber) {
+  if (p->type != MG_PATCH_KOLMOGOROV_FORCING) MG_FAIL("mg_patch_kolmogorov_setup: not a KOLMOGOROV_FORCING patch");
+  mg_grid* g = p->state->grid;
+  double* d = nullptr;
+  MG_TRY(mg_patch_alloc_array(p, "forcePerUnitMass", 1, &d));
+  if (p->nPatchPoints == 0) return 0;
+  if (!g->coordinates.p) MG_FAIL("mg_patch_kolmogorov_setup: grid coordinates have not been set");
+  const double pi = 4.0 * std::atan(1.0);
+  const int n = std::max(0, wavenumber);
+  { k_kolmogorov_setup<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), g->coordinates.comp(1), g->iblank, amplitude,
+                                                                          2.0 * pi * n, d); mg_count_launches(1); }
+  MG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// t_ProbePatch (reference src/ProbePatchImpl.f90:3-60, saveProbeData src/RegionImpl.f90:2211-2281): the probe buffer
+// lives on the device; a record is one collect kernel, the flush one device -> host copy of the filled part.
+int mg_patch_probe_setup_impl(mg_patch* p, int bufferSize) {
+  if (p->type != MG_PATCH_PROBE) MG_FAIL("mg_patch_probe_setup: not a PROBE patch");
+  if (bufferSize < 1) MG_FAIL("mg_patch_probe_setup: probe_buffer_size must be positive");
+  cudaFree(p->probeBuffer);
+  p->probeBuffer = nullptr;
+  p->probeCapacity = bufferSize;
+  p->probeCount = 0;
+  if (p->nPatchPoints > 0)
+    MG_CUDA(cudaMalloc(&p->probeBuffer, sizeof(double) * (size_t)p->nPatchPoints * p->state->nU * bufferSize));
+  return 0;
+}
+
+int mg_patch_probe_record_impl(mg_patch* p, int mode, int* full) {
+  if (p->type != MG_PATCH_PROBE || p->probeCapacity < 1) MG_FAIL("mg_patch_probe_record: the probe has not been set up");
+  if (mode != MG_FORWARD && mode != MG_ADJOINT) MG_FAIL("mg_patch_probe_record: mode must be FORWARD or ADJOINT");
+  if (p->probeCount >= p->probeCapacity) MG_FAIL("mg_patch_probe_record: the probe buffer is full (flush it)");
+  mg_state* s = p->state;
+  const MgField& X = mode == MG_FORWARD ? s->Q[s->cur] : s->W[s->curW];
+  if (p->nPatchPoints > 0) {
+    if (!X.p) MG_FAIL("mg_patch_probe_record: the field has not been set");
+    double* dst = p->probeBuffer + (size_t)p->probeCount * p->nPatchPoints * s->nU;
+    { k_collect<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), X.comp(0), X.compStride, s->nU, dst); mg_count_launches(1); }
+    MG_CUDA(cudaGetLastError());
+  }
+  ++p->probeCount;
+  if (full) *full = p->probeCount == p->probeCapacity;
+  return 0;
+}
+
+int mg_patch_probe_flush_impl(mg_patch* p, double* host, int* count) {
+  if (p->type != MG_PATCH_PROBE) MG_FAIL("mg_patch_probe_flush: not a PROBE patch");
+  if (count) *count = p->probeCount;
+  if (p->probeCount > 0 && p->nPatchPoints > 0) {
+    if (!host) MG_FAIL("mg_patch_probe_flush: null host buffer");
+    MG_CUDA(cudaMemcpyAsync(host, p->probeBuffer, sizeof(double) * (size_t)p->nPatchPoints * p->state->nU * p->probeCount,
+                            cudaMemcpyDefault, mg_stream()));
+    MG_CUDA(cudaStreamSynchronize(mg_stream()));
+  }
+  p->probeCount = 0;
   return 0;
 }
 

@@ -16,7 +16,12 @@ enum {
   MG_PATCH_COST_TARGET = 5,
   MG_PATCH_ACTUATOR = 6,
   MG_PATCH_BLOCK_INTERFACE = 7,
+  MG_PATCH_KOLMOGOROV_FORCING = 8,
+  MG_PATCH_JET_EXCITATION = 9,
+  MG_PATCH_PROBE = 10,
+  MG_PATCH_ADIABATIC_WALL = 11,
 };
+constexpr int MG_JET_MAX_MODES = 99;    // src/JetExcitationPatchImpl.f90:53
 
 struct mg_patch {
   struct Array { double* p = nullptr; int nComp = 0; };
@@ -31,6 +36,11 @@ struct mg_patch {
   double inviscidPenaltyAmount = 0.0, viscousPenaltyAmount = 0.0;   // signed, already / normBoundary(1)
   double spongeAmount = 1.0;          // SPONGE: patches/<name>/sponge_amount, sponge_exponent (src/SpongePatchImpl.f90:40-45)
   int spongeExponent = 2;
+  // JET_EXCITATION (src/JetExcitationPatchImpl.f90): a sponge-shaped patch that adds eigenmode perturbations
+  std::vector<double> angularFrequencies;
+  // PROBE (src/ProbePatchImpl.f90): ring of collected solutions, (nPatchPoints, nUnknowns, probeCapacity)
+  double* probeBuffer = nullptr;
+  int probeCapacity = 0, probeCount = 0;
   std::map<std::string, Array> arrays;     // patch-point arrays, (nPatchPoints, nComp) point fastest
   bool AplusReady = false;
   int AplusIncoming = 0;
@@ -54,6 +64,10 @@ int mg_patch_collect_impl(mg_patch* p, const MgField* f, int nComp, const char* 
 int mg_patch_disperse_impl(mg_patch* p, const char* name, int nComp, MgField* f);
 int mg_patches_update_impl(mg_state* s);
 int mg_patches_sponge_strengths_impl(mg_state* s);
+int mg_patch_kolmogorov_setup_impl(mg_patch* p, double amplitude, int wavenumber);
+int mg_patch_probe_setup_impl(mg_patch* p, int bufferSize);
+int mg_patch_probe_record_impl(mg_patch* p, int mode, int* full);
+int mg_patch_probe_flush_impl(mg_patch* p, double* host, int* count);
 
 // block interfaces (interface.cu)
 bool mg_state_has_interfaces(const mg_state* s);

@@ -1306,6 +1306,7 @@ int mg_fused_rhs_supported(const mg_state* s, int mode) {
 // ... and can also fold the RK4 substep into the last sweep: nothing may touch the RHS after the sweeps
 int mg_fused_supported(const mg_state* s, int mode) {
   if (!s->patches.empty() || !s->acousticSources.empty()) return 0;
+  if (mode == MG_ADJOINT && s->limits.soft) return 0;        // the solution-limit forcing joins after the sweeps
   return mg_fused_rhs_supported(s, mode);
 }
 

@@ -958,6 +958,19 @@ int mg_state_rhs_post(mg_state* s, int mode, bool alreadyTimesJacobian) {
     { k_mul_jacobian<<<nblocks(N), 256, 0, st>>>(s->rhs.comp(0), s->rhs.compStride, s->nU, g->jacobian.comp(0), N); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   MG_TRY(mg_patches_apply(s, mode));
+  if (mode == MG_ADJOINT && s->limits.soft && s->limits.forcingSwitch) {
+    // addSolutionLimitPenaltyAdjointForcing (reference src/RegionImpl.f90:2002-2005, :1094-1221)
+    int rhoOut = s->limits.rhoOut, tOut = s->limits.tOut;
+    if (rhoOut < 0 || tOut < 0) {
+      double lo, hi;
+      MG_TRY(mg_state_extrema_impl(s, 0, &lo, nullptr, &hi, nullptr));
+      rhoOut = lo <= s->limits.densityRange[0] || hi >= s->limits.densityRange[1];
+      MG_TRY(mg_state_extrema_impl(s, 1, &lo, nullptr, &hi, nullptr));
+      tOut = lo <= s->limits.temperatureRange[0] || hi >= s->limits.temperatureRange[1];
+    }
+    MG_TRY(mg_state_limit_forcing_impl(s, s->limits.densityRange, s->limits.temperatureRange, rhoOut, tOut,
+                                       s->limits.penaltyFactor));
+  }
   if (mode == MG_FORWARD) {
     for (const auto& src : s->acousticSources) {
       SrcArgs a;

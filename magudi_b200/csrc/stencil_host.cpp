@@ -69,6 +69,8 @@ typedef void (*TableFn)(Builder&);
 const std::map<std::string, TableFn>& tables() {
   static const std::map<std::string, TableFn> t = {
       {"null matrix", t_null},
+      {"Standard 5-point filter", t_std5_filter},
+      {"DRP 9-point filter", t_drp9_filter},
       {"SBP 1-2 first derivative", t_12_first},
       {"SBP 1-2 second derivative", t_12_second},
       {"SBP 1-2 composite dissipation", t_12_compdiss},

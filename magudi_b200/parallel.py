@@ -275,6 +275,18 @@ def link_interfaces_remote(links):
     return keep
 
 
+def combine_extrema(local):
+    """``findMinimum`` / ``findMaximum`` over the ranks of a grid (``src/GridImpl.f90:1479-1494``: all-gather, then the
+    first rank holding the extremum): ``local = (min, ijk, max, ijk)`` of this rank."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    allv = [None] * dist.get_world_size()
+    dist.all_gather_object(allv, local)
+    lo = min(range(len(allv)), key=lambda r: (allv[r][0], r))
+    hi = min(range(len(allv)), key=lambda r: (-allv[r][2], r))
+    return allv[lo][0], allv[lo][1], allv[hi][2], allv[hi][3]
+
+
 def all_reduce_sum(value, device=None):
     """Sum a host scalar over ranks (inner products, cost functional)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:

@@ -14,6 +14,10 @@ Follows:
   * ``src/IsothermalWallImpl.f90:3-337``    SAT_ISOTHERMAL_WALL
   * ``src/CostTargetPatchImpl.f90:3-136``   COST_TARGET
   * ``src/ActuatorPatchImpl.f90:108-181``   ACTUATOR
+  * ``src/KolmogorovForcingPatchImpl.f90:3-176``  KOLMOGOROV_FORCING
+  * ``src/JetExcitationPatchImpl.f90:3-187``      JET_EXCITATION
+  * ``src/ProbePatchImpl.f90:3-183``, ``src/RegionImpl.f90:2211-2281``  PROBE
+  * ``src/AdiabaticWallImpl.f90:3-151``           SAT_ADIABATIC_WALL
 """
 from __future__ import annotations
 
@@ -175,6 +179,29 @@ class SpongePatch(Patch):
             state.rightHandSide[idx] += s * state.adjointVariables[idx]
         else:
             state.rightHandSide[idx] -= s * state.adjointVariables[idx]         # LINEARIZED (:142-160)
+
+
+class JetExcitationPatch(SpongePatch):
+    """``t_JetExcitationPatch`` extends ``t_SpongePatch`` (its strength profile) but only adds the eigenmode
+    perturbations: ``addJetExcitation`` (``src/JetExcitationPatchImpl.f90:128-187``), FORWARD only."""
+    patchType = "JET_EXCITATION"
+
+    def __init__(self, name, grid, normalDirection, extent, amplitude=0.0, spongeExponent=2):
+        super().__init__(name, grid, normalDirection, extent, amplitude, spongeExponent)
+        self.angularFrequencies = np.zeros(0)
+        self.perturbationReal = None      # (nPatchPoints, nUnknowns, nModes)
+        self.perturbationImag = None
+
+    def updateRhs(self, mode, opt, grid, state):
+        if mode != FORWARD or self.angularFrequencies.size == 0:
+            return
+        c = np.cos(self.angularFrequencies * state.time)
+        sn = np.sin(self.angularFrequencies * state.time)
+        idx = self.gridIndex0[self.active]
+        st = self.spongeStrength[self.active][:, None]
+        for l in range(self.angularFrequencies.size):
+            state.rightHandSide[idx] = state.rightHandSide[idx] - st * (
+                self.perturbationReal[self.active, :, l] * c[l] - self.perturbationImag[self.active, :, l] * sn[l])
 
 
 def computeSpongeStrengths(patches, grid):
@@ -342,6 +369,58 @@ class ActuatorPatch(Patch):
             return
         idx = self.gridIndex0[self.active]
         state.rightHandSide[idx] += grid.controlMollifier[idx, 0:1] * f[self.active]
+
+
+class AdiabaticWall(ImpenetrableWall):
+    """``t_AdiabaticWall`` (``src/AdiabaticWallImpl.f90:51-151``): the impenetrable-wall penalty; the viscous
+    penalties are identically zero in the reference (``viscousPenalties(:,:) = 0``, ``:128``)."""
+    patchType = "SAT_ADIABATIC_WALL"
+
+
+class KolmogorovForcingPatch(Patch):
+    patchType = "KOLMOGOROV_FORCING"
+
+    def __init__(self, name, grid, normalDirection, extent, amplitude, wavenumber):
+        """``setupKolmogorovForcingPatch`` (``src/KolmogorovForcingPatchImpl.f90:3-68``)."""
+        super().__init__(name, grid, normalDirection, extent)
+        n = max(0, int(wavenumber))
+        pi = 4.0 * np.arctan(1.0)
+        self.forcePerUnitMass = np.zeros(self.nPatchPoints)
+        y = grid.coordinates[self.gridIndex0, 1]
+        self.forcePerUnitMass[self.active] = amplitude * np.sin(2.0 * pi * n * y[self.active])
+
+    def updateRhs(self, mode, opt, grid, state):
+        """``addKolmogorovForcing`` (``:86-176``)."""
+        idx = self.gridIndex0[self.active]
+        f = self.forcePerUnitMass[self.active]
+        if mode == FORWARD:
+            state.rightHandSide[idx, 1] += state.conservedVariables[idx, 0] * f
+        elif mode == ADJOINT:
+            state.rightHandSide[idx, 0] -= state.adjointVariables[idx, 1] * f
+        else:
+            state.rightHandSide[idx, 1] += state.adjointVariables[idx, 0] * f
+
+
+class ProbePatch(Patch):
+    """``t_ProbePatch``: ``updateRhs`` is empty; ``record`` / ``flush`` restate the patch's part of
+    ``saveProbeData`` (``src/RegionImpl.f90:2211-2281``)."""
+    patchType = "PROBE"
+
+    def __init__(self, name, grid, normalDirection, extent, nUnknowns, probeBufferSize=1):
+        super().__init__(name, grid, normalDirection, extent)
+        self.probeBuffer = np.zeros((self.nPatchPoints, nUnknowns, probeBufferSize))
+        self.iProbeBuffer = 0
+
+    def record(self, mode, state):
+        self.iProbeBuffer += 1
+        src = state.conservedVariables if mode == FORWARD else state.adjointVariables
+        self.probeBuffer[:, :, self.iProbeBuffer - 1] = self.collect(src)
+        return self.iProbeBuffer == self.probeBuffer.shape[2]
+
+    def flush(self):
+        out = np.array(self.probeBuffer[:, :, :self.iProbeBuffer], copy=True)
+        self.iProbeBuffer = 0
+        return out
 
 
 def updatePatches(patches, opt, grid, state):

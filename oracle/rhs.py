@@ -247,8 +247,10 @@ def addAcousticSources(mode, opt, grid, state):
         state.rightHandSide[:, nD + 1] += a * np.exp(-gaussianFactor * r2)
 
 
-def computeRhs(mode, opt, grid, state, patches=(), timestep=0, stage=1):
-    """``computeRhs`` for one grid (``src/RegionImpl.f90:1877-2027``)."""
+def computeRhs(mode, opt, grid, state, patches=(), timestep=0, stage=1, softLimits=None):
+    """``computeRhs`` for one grid (``src/RegionImpl.f90:1877-2027``).  ``softLimits`` =
+    ``(densityRange, temperatureRange, penaltyFactor)`` switches the soft solution-limit adjoint forcing on
+    (``:2002-2005``)."""
     if mode == FORWARD:
         computeRhsForward(opt, grid, state, patches)
     elif mode == ADJOINT:
@@ -259,6 +261,9 @@ def computeRhs(mode, opt, grid, state, patches=(), timestep=0, stage=1):
     for patch in patches:
         if patch.gridIndex == grid.index:
             patch.updateRhs(mode, opt, grid, state)
+    if mode == ADJOINT and softLimits is not None:
+        from . import limits
+        limits.addSolutionLimitPenaltyAdjointForcing(opt, [grid], [state], *softLimits)
     addAcousticSources(mode, opt, grid, state)
     state.rightHandSide[grid.iblank == 0, :] = 0.0
 

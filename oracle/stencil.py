@@ -35,6 +35,7 @@ SCHEMES = (
     "SBP 3-6 dissipation transpose", "SBP 3-6 composite dissipation",
     "SBP 4-8 first derivative", "SBP 4-8 dissipation", "SBP 4-8 dissipation transpose",
     "SBP 4-8 composite dissipation",
+    "Standard 5-point filter", "DRP 9-point filter",
     "null matrix",
 )
 
@@ -704,8 +705,26 @@ def _t_48_disst(s):          # :1913-1932
     b[6, 4:5] = c[0:1]
 
 
+def _t_std5_filter(s):       # :1346-1360
+    s._allocate(SYMMETRIC, 5, 3, 2)
+    s._set_interior_half([1.0 / 4.0, -1.0 / 16.0], center=5.0 / 8.0)
+    s._row(1, 1, [1.0 / 4.0, 1.0 / 2.0, 1.0 / 4.0])
+    s._row(1, 2, [1.0 / 4.0, 1.0 / 2.0, 1.0 / 4.0])
+
+
+def _t_drp9_filter(s):       # :1961-1981
+    s._allocate(SYMMETRIC, 9, 7, 4)
+    s._set_interior_half([0.204788880640, -0.120007591680, 0.045211119360, -0.008228661760], center=0.75647250688)
+    s._row(1, 1, [1.0])
+    s._row(1, 2, [1.0 / 4.0, 1.0 / 2.0, 1.0 / 4.0])
+    s._row(1, 3, [-1.0 / 16.0, 1.0 / 4.0, 5.0 / 8.0, 1.0 / 4.0, -1.0 / 16.0])
+    s._row(1, 4, [1.0 / 64.0, -3.0 / 32.0, 15.0 / 64.0, 11.0 / 16.0, 15.0 / 64.0, -3.0 / 32.0, 1.0 / 64.0])
+
+
 _TABLES = {
     "null matrix": _t_null,
+    "Standard 5-point filter": _t_std5_filter,
+    "DRP 9-point filter": _t_drp9_filter,
     "SBP 1-2 first derivative": _t_12_first,
     "SBP 1-2 second derivative": _t_12_second,
     "SBP 1-2 composite dissipation": _t_12_compdiss,
