@@ -68,6 +68,8 @@ enum {
   MG_Q_FUSED_ADJOINT_DIFFUSION3 = 15,
   /* mean pressure of the acoustic-noise functional (t_AcousticNoise data_, src/AcousticNoiseImpl.f90:60-121) */
   MG_Q_MEAN_PRESSURE = 16,
+  /* mean velocity of the Reynolds-stress functional (t_ReynoldsStress data_, src/ReynoldsStressImpl.f90:31-66), nD */
+  MG_Q_MEAN_VELOCITY = 17,
   MG_G_COORDINATES = 100, MG_G_METRICS = 101, MG_G_JACOBIAN = 102, MG_G_NORM = 103,
   MG_G_ARC_LENGTHS = 104, MG_G_TARGET_MOLLIFIER = 105, MG_G_CONTROL_MOLLIFIER = 106
 };
@@ -204,6 +206,20 @@ int mg_functional_actuator_gradient(mg_patch* p, double timeRampFactor, double* 
  * adjoint per the state's options) is written to the patches' "adjointForcing". */
 int mg_functional_pressure_drag(mg_state* s, const double direction[3], double* value);
 int mg_functional_pressure_drag_forcing(mg_state* s, const double direction[3]);
+/* t_DragForce%compute (src/DragForceImpl.f90:61-146): the viscous drag sum_l direction_l (metrics_k . tau_l) /
+ * normBoundary(1) on the COST_TARGET patches, weighted by the target mollifier; 0 for an inviscid state.  (The
+ * reference's computeDragForceAdjointForcing, :159-209, is hard-wired to metrics(:,1) / metrics(:,5) of a 3-D grid;
+ * the host composes it from mg_stencil_project_boundary_and_apply / mg_stencil_apply_norm.) */
+int mg_functional_drag_force(mg_state* s, const double direction[3], double* value);
+/* t_ReynoldsStress%compute / %computeAdjointForcing (src/ReynoldsStressImpl.f90:121-195, 211-284): needs
+ * MG_Q_MEAN_VELOCITY and MG_G_TARGET_MOLLIFIER; directions as reynolds_stress_direction1/2_x/y/z, normalised here.
+ * The forcing reproduces the reference's assignments literally (its second pair overwrites the first). */
+int mg_functional_reynolds_stress(mg_state* s, const double direction1[3], const double direction2[3], double* value);
+int mg_functional_reynolds_stress_forcing(mg_state* s, const double direction1[3], const double direction2[3]);
+/* t_MomentumActuator%computeSensitivity / %updateGradient (src/MomentumActuatorImpl.f90:81-163, 351-412):
+ * direction 0 = all momentum components (nD gradient components per patch point), d > 0 = component d only. */
+int mg_functional_momentum_actuator_sensitivity(mg_state* s, int direction, double* value);
+int mg_functional_momentum_actuator_gradient(mg_patch* p, int direction, double* hostOut);
 
 /* ------------------------------------------------------------------ t_State */
 /* %setup: src/StateImpl.f90:71-170 */

@@ -118,6 +118,11 @@ SIGNATURES = {
     "mg_patch_get_array": (C.c_int, [_P, C.c_char_p, C.c_int, _P]),
     "mg_patch_collect": (C.c_int, [_P, C.c_int, C.c_char_p]),
     "mg_patch_link_interface": (C.c_int, [_P, _P, _P]),
+    "mg_functional_drag_force": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
+    "mg_functional_reynolds_stress": (C.c_int, [_P, _P, _P, C.POINTER(C.c_double)]),
+    "mg_functional_reynolds_stress_forcing": (C.c_int, [_P, _P, _P]),
+    "mg_functional_momentum_actuator_sensitivity": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "mg_functional_momentum_actuator_gradient": (C.c_int, [_P, C.c_int, _P]),
     "mg_rk3_substep": (C.c_int, [_P, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int]),
     "mg_patch_kolmogorov_setup": (C.c_int, [_P, C.c_double, C.c_int]),
     "mg_patch_set_jet_modes": (C.c_int, [_P, C.c_int, _P]),

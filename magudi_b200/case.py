@@ -204,6 +204,11 @@ def load_case(directory, inp="magudi.inp"):
             if t == "SPONGE":
                 a1 = deck.get(key + "sponge_amount", deck.get("defaults/sponge_amount", 1.0))
                 a2 = deck.get(key + "sponge_exponent", deck.get("defaults/sponge_exponent", 2))
+            elif t == "JET_EXCITATION":                     # src/JetExcitationPatchImpl.f90:47-49 over the sponge setup
+                a1 = deck.get(key + "amplitude", deck.get("defaults/jet_excitation/amplitude", 0.0))
+                a2 = deck.get(key + "sponge_exponent", deck.get("defaults/sponge_exponent", 2))
+            elif t in ("KOLMOGOROV_FORCING", "PROBE"):
+                a1 = a2 = 0.0
             else:
                 a1 = deck.get(key + "inviscid_penalty_amount", deck.get("defaults/inviscid_penalty_amount",
                                                                         2.0 if t == "COST_TARGET" else 1.0))
@@ -213,6 +218,27 @@ def load_case(directory, inp="magudi.inp"):
                     a2 = deck.get(key + "viscous_penalty_amount1", a2)
             p = c.states[row["grid"] - 1].addPatch(t, name, row["normalDirection"], row["extent"], a1, a2)
             c.patches[name] = p
+            if t == "KOLMOGOROV_FORCING":                    # required keys (src/KolmogorovForcingPatchImpl.f90:38-44)
+                p.setupKolmogorovForcing(deck.require(key + "amplitude", 0.0), deck.require(key + "wavenumber", 0))
+            if t == "PROBE":
+                p.setupProbe(deck.get("probe_buffer_size", 1))
+            if t == "JET_EXCITATION":
+                nModes = min(max(0, deck.get(key + "number_of_modes",
+                                             deck.get("defaults/jet_excitation/number_of_modes", 0))), 99)
+                prefix = deck.get("jet_excitation_prefix", deck.get("output_prefix", "magudi"))
+                if nModes > 0 and p.nPatchPoints > 0:
+                    w, re, im = [], [], []
+                    for m in range(1, nModes + 1):
+                        # <prefix>-NN.eigenmode_real.q / _imag.q hold one block per grid of the patch's size; aux(2)
+                        # is the angular frequency (src/JetExcitationPatchImpl.f90:63-109)
+                        sr, ar, _ = plot3d.read_solution(path("%s-%02d.eigenmode_real.q" % (prefix, m)))
+                        si, ai, _ = plot3d.read_solution(path("%s-%02d.eigenmode_imag.q" % (prefix, m)))
+                        if abs(ar[row["grid"] - 1][1] - ai[row["grid"] - 1][1]) > 0.0:
+                            raise ValueError("jet excitation: mismatch in angular frequencies")
+                        w.append(float(ar[row["grid"] - 1][1]))
+                        re.append(np.asarray(sr[row["grid"] - 1]))
+                        im.append(np.asarray(si[row["grid"] - 1]))
+                    p.setJetModes(w, np.stack(re, axis=2), np.stack(im, axis=2))
             if t == "SAT_ISOTHERMAL_WALL" and p.nPatchPoints > 0:
                 Tw = deck.get(key + "temperature", 1.0 / (gamma - 1.0))
                 p.setArray("temperature", np.full(p.nPatchPoints, Tw))
@@ -230,6 +256,18 @@ def load_case(directory, inp="magudi.inp"):
                                  deck.require(k + "radius", 0.0), deck.get(k + "phase", 0.0))
     c.region.computeSpongeStrengths()
     c.region.updatePatches()
+    # solution limits and filter (src/SimulationFlagsImpl.f90:34-37, src/SolverOptionsImpl.f90)
+    c.enableSolutionLimits = bool(deck.get("enable_solution_limits", False))
+    if c.enableSolutionLimits:
+        soft = bool(deck.get("soft_solution_limits", False))
+        # required keys when the limits are on (src/SolverOptionsImpl.f90:73-82)
+        c.region.setSolutionLimits((deck.require("minimum_density", 0.0), deck.require("maximum_density", 0.0)),
+                                   (deck.require("minimum_temperature", 0.0), deck.require("maximum_temperature", 0.0)),
+                                   soft=soft, penaltyFactor=deck.get("solution_limit_penalty_factor", 1.0))
+    c.filterOn = bool(deck.get("filter_solution", False))
+    if c.filterOn:
+        for g in c.grids:
+            g.setupFilter(deck.get("defaults/filtering_scheme", opt.discretizationType))
     c.timeStepSize = deck.get("time_step_size", 0.0)
     c.numberOfTimesteps = deck.get("number_of_timesteps", 1000)
     c.saveInterval = deck.get("save_interval", -1)

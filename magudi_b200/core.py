@@ -25,6 +25,7 @@ Q_SPECIFIC_VOLUME, Q_VELOCITY, Q_PRESSURE, Q_TEMPERATURE = 4, 5, 6, 7
 Q_DYNAMIC_VISCOSITY, Q_SECOND_VISCOSITY, Q_THERMAL_DIFFUSIVITY, Q_STRESS_TENSOR, Q_HEAT_FLUX = 8, 9, 10, 11, 12
 Q_FUSED_TAUQ, Q_FUSED_DISSIPATION, Q_FUSED_ADJOINT_DIFFUSION3 = 13, 14, 15
 Q_MEAN_PRESSURE = 16
+Q_MEAN_VELOCITY = 17
 G_COORDINATES, G_METRICS, G_JACOBIAN, G_NORM, G_ARC_LENGTHS = 100, 101, 102, 103, 104
 G_TARGET_MOLLIFIER, G_CONTROL_MOLLIFIER = 105, 106
 
@@ -289,7 +290,7 @@ class State:
         nd, nu = self.nDimensions, self.nUnknowns
         if field in (Q_CONSERVED, Q_ADJOINT, Q_TARGET, Q_RHS):
             return nu
-        if field in (Q_VELOCITY, Q_HEAT_FLUX):
+        if field in (Q_VELOCITY, Q_HEAT_FLUX, Q_MEAN_VELOCITY):
             return nd
         if field == Q_STRESS_TENSOR:
             return nd * nd
@@ -324,6 +325,7 @@ class State:
     stressTensor = property(lambda s: s.get(Q_STRESS_TENSOR))
     heatFlux = property(lambda s: s.get(Q_HEAT_FLUX))
     meanPressure = property(lambda s: s.get(Q_MEAN_PRESSURE), lambda s, v: s.set(Q_MEAN_PRESSURE, v))
+    meanVelocity = property(lambda s: s.get(Q_MEAN_VELOCITY), lambda s, v: s.set(Q_MEAN_VELOCITY, v))
 
     # ---- functionals / sensitivities (local sums; see include/magudi_gpu.h)
     def computeQuadratureOnPatches(self, patchType, integrand):
@@ -378,6 +380,33 @@ class State:
         """``t_PressureDrag%computeAdjointForcing`` (``:148-267``): fills every COST_TARGET patch."""
         d = (C.c_double * 3)(*[float(v) for v in (tuple(direction) + (0.0, 0.0))[:3]])
         check(L.lib().mg_functional_pressure_drag_forcing(self._h, d))
+
+    @staticmethod
+    def _vec3(v):
+        return (C.c_double * 3)(*[float(x) for x in (tuple(v) + (0.0, 0.0))[:3]])
+
+    def computeDragForce(self, direction=(1.0, 0.0, 0.0)):
+        """``t_DragForce%compute`` (``src/DragForceImpl.f90:61-146``), local to this rank."""
+        r = C.c_double(0.0)
+        check(L.lib().mg_functional_drag_force(self._h, self._vec3(direction), C.byref(r)))
+        return r.value
+
+    def computeReynoldsStress(self, direction1=(1.0, 0.0, 0.0), direction2=(1.0, 0.0, 0.0)):
+        """``t_ReynoldsStress%compute`` (``src/ReynoldsStressImpl.f90:121-195``); needs ``meanVelocity``."""
+        r = C.c_double(0.0)
+        check(L.lib().mg_functional_reynolds_stress(self._h, self._vec3(direction1), self._vec3(direction2),
+                                                    C.byref(r)))
+        return r.value
+
+    def computeReynoldsStressAdjointForcing(self, direction1=(1.0, 0.0, 0.0), direction2=(1.0, 0.0, 0.0)):
+        """``t_ReynoldsStress%computeAdjointForcing`` (``:211-284``): fills every COST_TARGET patch."""
+        check(L.lib().mg_functional_reynolds_stress_forcing(self._h, self._vec3(direction1), self._vec3(direction2)))
+
+    def computeMomentumActuatorSensitivity(self, direction=0):
+        """``t_MomentumActuator%computeSensitivity`` (``src/MomentumActuatorImpl.f90:81-163``)."""
+        r = C.c_double(0.0)
+        check(L.lib().mg_functional_momentum_actuator_sensitivity(self._h, int(direction), C.byref(r)))
+        return r.value
 
     def computeThermalActuatorSensitivity(self, timeRampFactor=1.0):
         """``t_ThermalActuator%computeSensitivity`` (``src/ThermalActuatorImpl.f90:83-159``)."""
@@ -578,6 +607,15 @@ class Patch:
         (``t_ThermalActuator%updateGradient``, ``src/ThermalActuatorImpl.f90:383-443``)."""
         out = np.zeros(max(self.nPatchPoints, 0))
         check(L.lib().mg_functional_actuator_gradient(self._h, float(timeRampFactor), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+
+    def momentumActuatorGradient(self, direction=0):
+        """One gradient sample ``w_{k+1} * controlMollifier`` at the patch points, (nPatchPoints, nComponents)
+        (``t_MomentumActuator%updateGradient``, ``src/MomentumActuatorImpl.f90:351-412``)."""
+        nc = self.state.nDimensions if direction == 0 else 1
+        out = np.zeros((max(self.nPatchPoints, 0), nc), order="F")
+        check(L.lib().mg_functional_momentum_actuator_gradient(self._h, int(direction), L.fptr(out)))
         return out
 
 

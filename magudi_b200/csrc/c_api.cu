@@ -467,6 +467,9 @@ static MgField* state_field(mg_state* s, int field) {
     case MG_Q_MEAN_PRESSURE:
       if (!s->meanPressure.p && mg_field_alloc(s->grid, 1, &s->meanPressure) != 0) return nullptr;
       return &s->meanPressure;
+    case MG_Q_MEAN_VELOCITY:
+      if (!s->meanVelocity.p && mg_field_alloc(s->grid, s->nD, &s->meanVelocity) != 0) return nullptr;
+      return &s->meanVelocity;
     case MG_Q_FUSED_TAUQ: return &s->tauq;
     case MG_Q_FUSED_DISSIPATION:
       if (s->fusedValid && !s->dissValid) mg_fused_dissipation(s);
@@ -875,6 +878,30 @@ int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep
 }
 
 // ------------------------------------------------------------------------------ SURVEY 8 f4
+int mg_functional_drag_force(mg_state* s, const double direction[3], double* value) {
+  if (!s || !direction || !value) MG_FAIL("mg_functional_drag_force: null argument");
+  double d[3] = {direction[0], s->nD >= 2 ? direction[1] : 0.0, s->nD == 3 ? direction[2] : 0.0};
+  const double n2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  if (n2 <= 2.220446049250313e-16) MG_FAIL("Unable to determine a unit vector for computing drag force!");
+  for (double& v : d) v /= std::sqrt(n2);
+  return mg_functional_drag_force_impl(s, d, value);
+}
+int mg_functional_reynolds_stress(mg_state* s, const double direction1[3], const double direction2[3], double* value) {
+  if (!s || !direction1 || !direction2 || !value) MG_FAIL("mg_functional_reynolds_stress: null argument");
+  return mg_functional_reynolds_stress_impl(s, direction1, direction2, value);
+}
+int mg_functional_reynolds_stress_forcing(mg_state* s, const double direction1[3], const double direction2[3]) {
+  if (!s || !direction1 || !direction2) MG_FAIL("mg_functional_reynolds_stress_forcing: null argument");
+  return mg_functional_reynolds_stress_forcing_impl(s, direction1, direction2);
+}
+int mg_functional_momentum_actuator_sensitivity(mg_state* s, int direction, double* value) {
+  if (!s || !value) MG_FAIL("mg_functional_momentum_actuator_sensitivity: null argument");
+  return mg_functional_momentum_actuator_sensitivity_impl(s, direction, value);
+}
+int mg_functional_momentum_actuator_gradient(mg_patch* p, int direction, double* hostOut) {
+  if (!p || !hostOut) MG_FAIL("mg_functional_momentum_actuator_gradient: null argument");
+  return mg_functional_momentum_actuator_gradient_impl(p, direction, hostOut);
+}
 int mg_patch_kolmogorov_setup(mg_patch* p, double amplitude, int wavenumber) {
   if (!p) MG_FAIL("mg_patch_kolmogorov_setup: null handle");
   return mg_patch_kolmogorov_setup_impl(p, amplitude, wavenumber);

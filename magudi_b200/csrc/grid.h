@@ -28,6 +28,7 @@ struct mg_state {
   int curW = 0;
   MgField target, rhs;
   MgField meanPressure;         // mean pressure of the acoustic-noise functional (AcousticNoise data_)
+  MgField meanVelocity;         // mean velocity of the Reynolds-stress functional (ReynoldsStress data_)
   MgField specificVolume, velocity, pressure, temperature, mu, lambda, kappa, stressTensor, heatFlux;
   MgField rk1, rk2;             // RK4 buffers (reference RK4IntegratorImpl.f90:32-35)
   MgField viscFluxCart;         // Cartesian viscous fluxes (nU*nD), kept only when a patch needs them

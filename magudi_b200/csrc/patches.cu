@@ -6,6 +6,7 @@
 //
 // One thread per patch point; patch points are numbered in the patch-local Fortran order of the
 // reference (i fastest inside the part of the patch owned by this rank).
+#include <cfloat>
 #include <cstring>
 
 #include "grid.h"
@@ -1069,7 +1070,9 @@ struct DragArgs {
   PatchGeom g;
   const int* iblank;
   const double *pressure, *metricsK, *jac, *u, *Q, *W;
+  const double *tau = nullptr, *mollifier = nullptr;   // kind 1 (DragForce): stress tensor and target mollifier
   size_t cs, csQ, csW;
+  int kind = 0;                                         // 0: PRESSURE_DRAG, 1: DRAG (viscous)
   int nD, axis, normalDirection, continuous;
   int n[3], depth[3], hasB0[3], hasB1[3];
   double norm[3][MG_MAX_BDEPTH];
@@ -1096,6 +1099,18 @@ __global__ void __launch_bounds__(DRAG_THREADS) k_drag(DragArgs a) {
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < a.g.n; q += gridDim.x * blockDim.x) {
     const size_t p = a.g.gridIndex(q);
     if (a.iblank && a.iblank[p] == 0) continue;
+    if (a.kind == 1) {
+      // computeDragForce (reference src/DragForceImpl.f90:108-127): F = nbf sum_l dir_l (metrics_k . tau_l), weight =
+      // target mollifier
+      double F = 0.0;
+      for (int l = 0; l < a.nD; ++l) {
+        double mt = 0.0;
+        for (int j = 0; j < a.nD; ++j) mt += a.metricsK[(size_t)j * a.cs + p] * a.tau[(size_t)(l * a.nD + j) * a.cs + p];
+        F += a.dirv[l] * mt;
+      }
+      acc += (a.factor * F) * drag_patch_norm(a, q) * a.mollifier[p];
+      continue;
+    }
     double md = 0.0;
     for (int l = 0; l < a.nD; ++l) md = (l == 0) ? a.metricsK[p] * a.dirv[0] : md + a.metricsK[(size_t)l * a.cs + p] * a.dirv[l];
     acc += (0.0 - (a.pressure[p] - 1.0 / a.gamma)) * drag_patch_norm(a, q) * (md * a.factor);
@@ -1290,6 +1305,171 @@ int mg_functional_pressure_drag_impl(mg_state* s, const double direction[3], dou
     for (int i = 0; i < DRAG_BLOCKS; ++i) sum += host[i];
   }
   *value = sum;
+  return 0;
+}
+
+// computeDragForce (reference src/DragForceImpl.f90:61-146): the viscous drag on the COST_TARGET patches; 0 when the
+// flow is inviscid.  Local to this rank.
+int mg_functional_drag_force_impl(mg_state* s, const double direction[3], double* value) {
+  mg_grid* g = s->grid;
+  *value = 0.0;
+  if (!s->opt.viscosityOn) return 0;
+  if (!g->targetMollifier.p) MG_FAIL("drag force: the target mollifier has not been set");
+  MG_TRY(mg_state_ensure_dependents(s));
+  static double* partial = nullptr;
+  if (!partial) MG_CUDA(cudaMalloc(&partial, DRAG_BLOCKS * sizeof(double)));
+  double sum = 0.0;
+  for (mg_patch* p : s->patches) {
+    if (p->type != MG_PATCH_COST_TARGET || p->nPatchPoints <= 0) continue;
+    DragArgs a;
+    MG_TRY(drag_args(s, p, direction, &a));
+    if (s->stressTensor.compStride != a.cs) MG_FAIL("drag force: unexpected field layout");
+    a.kind = 1;
+    a.tau = s->stressTensor.comp(0);
+    a.mollifier = g->targetMollifier.comp(0);
+    a.partial = partial;
+    { k_drag<<<DRAG_BLOCKS, DRAG_THREADS, 0, mg_stream()>>>(a); mg_count_launches(1); }
+    MG_CUDA(cudaGetLastError());
+    double host[DRAG_BLOCKS];
+    MG_CUDA(cudaMemcpyAsync(host, partial, sizeof(host), cudaMemcpyDeviceToHost, mg_stream()));
+    MG_CUDA(cudaStreamSynchronize(mg_stream()));
+    for (int i = 0; i < DRAG_BLOCKS; ++i) sum += host[i];
+  }
+  *value = sum;
+  return 0;
+}
+
+namespace {
+struct ReArgs {
+  PatchGeom g;
+  const int* iblank;
+  const double *Q, *meanU, *mollifier;
+  size_t csQ, csM, N;
+  int nD;
+  double d1[3], d2[3];
+  double* out;
+};
+
+// integrand of computeReynoldsStress (reference src/ReynoldsStressImpl.f90:146-156), times the target mollifier
+__global__ void k_reynolds_integrand(ReArgs a) {
+  const size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= a.N) return;
+  const double v = 1.0 / a.Q[p];
+  double s1 = 0.0, s2 = 0.0;
+  for (int l = 0; l < a.nD; ++l) {
+    const double du = v * a.Q[(size_t)(l + 1) * a.csQ + p] - a.meanU[(size_t)l * a.csM + p];
+    s1 += du * a.d1[l];
+    s2 += du * a.d2[l];
+  }
+  a.out[p] = 0.5 * s1 * s2 * a.mollifier[p];
+}
+
+// computeReynoldsStressAdjointForcing (reference :211-284).  As in the reference the second pair of assignments
+// OVERWRITES the first: what is left is the firstDirection x F(secondDirection) term; the energy entry is not touched.
+__global__ void k_reynolds_forcing(ReArgs a, int nU) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.g.n) return;
+  const size_t p = a.g.gridIndex(q);
+  if (a.iblank && a.iblank[p] == 0) return;
+  const double v = 1.0 / a.Q[p];
+  double u[3] = {0.0, 0.0, 0.0}, s2 = 0.0, d1u = 0.0;
+  for (int l = 0; l < a.nD; ++l) {
+    u[l] = v * a.Q[(size_t)(l + 1) * a.csQ + p];
+    s2 += a.d2[l] * (u[l] - a.meanU[(size_t)l * a.csM + p]);
+    d1u += a.d1[l] * u[l];
+  }
+  const double F = -0.5 * a.mollifier[p] * v * s2;
+  for (int l = 0; l < a.nD; ++l) a.out[(size_t)(l + 1) * a.g.n + q] = a.d1[l] * F;
+  a.out[q] = (0.0 - d1u) * F;
+  (void)nU;
+}
+
+int reynolds_args(mg_state* s, const double d1[3], const double d2[3], ReArgs* a) {
+  mg_grid* g = s->grid;
+  if (!s->meanVelocity.p) MG_FAIL("Reynolds stress: the mean velocity has not been set (MG_Q_MEAN_VELOCITY)");
+  if (!g->targetMollifier.p) MG_FAIL("Reynolds stress: the target mollifier has not been set");
+  std::memset(a, 0, sizeof(*a));
+  a->iblank = g->iblank;
+  a->Q = s->Q[s->cur].comp(0); a->csQ = s->Q[s->cur].compStride;
+  a->meanU = s->meanVelocity.comp(0); a->csM = s->meanVelocity.compStride;
+  a->mollifier = g->targetMollifier.comp(0);
+  a->N = g->N;
+  a->nD = s->nD;
+  double n1 = 0.0, n2 = 0.0;
+  for (int l = 0; l < s->nD; ++l) { n1 += d1[l] * d1[l]; n2 += d2[l] * d2[l]; }
+  if (n1 <= DBL_EPSILON || n2 <= DBL_EPSILON) MG_FAIL("Unable to determine unit vectors for computing Reynolds stress!");
+  for (int l = 0; l < s->nD; ++l) { a->d1[l] = d1[l] / std::sqrt(n1); a->d2[l] = d2[l] / std::sqrt(n2); }
+  return 0;
+}
+}  // namespace
+
+int mg_functional_reynolds_stress_impl(mg_state* s, const double d1[3], const double d2[3], double* value) {
+  mg_grid* g = s->grid;
+  ReArgs a;
+  MG_TRY(reynolds_args(s, d1, d2, &a));
+  a.out = g->scratchA.comp(0);
+  { k_reynolds_integrand<<<(unsigned)((g->N + 255) / 256), 256, 0, mg_stream()>>>(a); mg_count_launches(1); }
+  MG_CUDA(cudaGetLastError());
+  return quadrature(s, MG_PATCH_COST_TARGET, 0, a.out, nullptr, nullptr, value);
+}
+
+int mg_functional_reynolds_stress_forcing_impl(mg_state* s, const double d1[3], const double d2[3]) {
+  for (mg_patch* p : s->patches) {
+    if (p->type != MG_PATCH_COST_TARGET || p->nPatchPoints <= 0) continue;
+    ReArgs a;
+    MG_TRY(reynolds_args(s, d1, d2, &a));
+    a.g = geom(p);
+    double* out = nullptr;
+    auto it = p->arrays.find("adjointForcing");
+    if (it == p->arrays.end()) {
+      MG_TRY(mg_patch_alloc_array(p, "adjointForcing", s->nU, &out));
+      MG_CUDA(cudaMemsetAsync(out, 0, (size_t)p->nPatchPoints * s->nU * sizeof(double), mg_stream()));
+    } else out = it->second.p;
+    a.out = out;
+    { k_reynolds_forcing<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a, s->nU); mg_count_launches(1); }
+    MG_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// t_MomentumActuator (reference src/MomentumActuatorImpl.f90:81-163, 351-412): direction 0 = all momentum components,
+// d > 0 = component d only.  Sensitivity = quadrature over the ACTUATOR patches of sum_j (w_{j+1} mollifier)^2; a
+// gradient sample = mollifier x w_{k+1} at the patch points, (nPatchPoints, nComponents).
+int mg_functional_momentum_actuator_sensitivity_impl(mg_state* s, int direction, double* value) {
+  mg_grid* g = s->grid;
+  if (!g->controlMollifier.p) MG_FAIL("momentum actuator: the control mollifier has not been set");
+  if (direction < 0 || direction > s->nD) MG_FAIL("momentum actuator: invalid direction");
+  *value = 0.0;
+  for (int j = 1; j <= s->nD; ++j) {
+    if (direction != 0 && j != direction) continue;
+    double r = 0.0;
+    MG_TRY(quadrature(s, MG_PATCH_ACTUATOR, 2, s->W[s->curW].comp(j), nullptr, g->controlMollifier.comp(0), &r));
+    *value += r;
+  }
+  return 0;
+}
+
+int mg_functional_momentum_actuator_gradient_impl(mg_patch* p, int direction, double* hostOut) {
+  mg_state* s = p->state;
+  mg_grid* g = s->grid;
+  if (p->type != MG_PATCH_ACTUATOR) MG_FAIL("momentum actuator gradient: not an ACTUATOR patch");
+  if (!g->controlMollifier.p) MG_FAIL("momentum actuator: the control mollifier has not been set");
+  if (direction < 0 || direction > s->nD) MG_FAIL("momentum actuator: invalid direction");
+  if (p->nPatchPoints <= 0) return 0;
+  const int nComp = direction == 0 ? s->nD : 1;
+  double* out = nullptr;
+  MG_TRY(mg_patch_alloc_array(p, "momentumGradient", nComp, &out));
+  int c = 0;
+  for (int k = 1; k <= s->nD; ++k) {
+    if (direction != 0 && k != direction) continue;
+    { k_actuator_gradient<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), s->W[s->curW].comp(k),
+                                                                        g->controlMollifier.comp(0), 1.0,
+                                                                        out + (size_t)c * p->nPatchPoints); mg_count_launches(1); }
+    ++c;
+  }
+  MG_CUDA(cudaGetLastError());
+  MG_CUDA(cudaMemcpyAsync(hostOut, out, (size_t)p->nPatchPoints * nComp * sizeof(double), cudaMemcpyDeviceToHost, mg_stream()));
+  MG_CUDA(cudaStreamSynchronize(mg_stream()));
   return 0;
 }
 

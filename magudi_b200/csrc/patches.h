@@ -86,3 +86,8 @@ int mg_functional_actuator_sensitivity_impl(mg_state* s, double timeRampFactor, 
 int mg_functional_actuator_gradient_impl(mg_patch* p, double timeRampFactor, double* hostOut);
 int mg_functional_pressure_drag_impl(mg_state* s, const double direction[3], double* value);
 int mg_functional_pressure_drag_forcing_impl(mg_state* s, const double direction[3]);
+int mg_functional_drag_force_impl(mg_state* s, const double direction[3], double* value);
+int mg_functional_reynolds_stress_impl(mg_state* s, const double d1[3], const double d2[3], double* value);
+int mg_functional_reynolds_stress_forcing_impl(mg_state* s, const double d1[3], const double d2[3]);
+int mg_functional_momentum_actuator_sensitivity_impl(mg_state* s, int direction, double* value);
+int mg_functional_momentum_actuator_gradient_impl(mg_patch* p, int direction, double* hostOut);

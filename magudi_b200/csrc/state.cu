@@ -581,7 +581,7 @@ void mg_state_destroy_impl(mg_state* s) {
   for (MgField* f : {&s->Q[0], &s->Q[1], &s->W[0], &s->W[1], &s->target, &s->rhs, &s->specificVolume,
                      &s->velocity, &s->pressure, &s->temperature, &s->mu, &s->lambda, &s->kappa,
                      &s->stressTensor, &s->heatFlux, &s->rk1, &s->rk2, &s->viscFluxCart, &s->tauq, &s->dissTerm,
-                     &s->meanPressure})
+                     &s->meanPressure, &s->meanVelocity})
     mg_field_free(f);
   for (void* p : s->fusedOps) if (p) cudaFree(p);
   for (double* p : s->pool) cudaFree(p);

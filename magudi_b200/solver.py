@@ -56,6 +56,13 @@ class Solver:
         self.controlForcing = None
         self.startTime = 0.0
         self.nU = state.nUnknowns
+        # optional per-timestep companions of the march (src/SolverImpl.f90:805-880): limits, filter, probes
+        self.enableSolutionLimits = False      # region.setSolutionLimits(...) gives the ranges
+        self.filterOn = False                  # grid.setupFilter(...) gives the operators
+        self.probeInterval = 0
+        self.outputPrefix = None
+        self.solutionLimitPenalty = 0.0
+        self.crashMessage = None
 
     # ---- controller%updateForcing: forward substep m reads sample 4N-1-m of the reverse-time sequence
     def _set_forcing(self, substep):
@@ -83,16 +90,32 @@ class Solver:
             self.checkpoints[startTimestep] = (np.array(Q0, dtype=np.float64, order="F", copy=True), time)
         st.update()
         J = 0.0
+        soft = self.enableSolutionLimits and getattr(self.region, "softSolutionLimits", False)
+        self.solutionLimitPenalty = 0.0
+        self.crashMessage = None
         for timestep in range(startTimestep + 1, startTimestep + self.nTimesteps + 1):
             for i in range(1, 5):
+                if self.enableSolutionLimits:          # checkSolutionLimits (src/SolverImpl.f90:812-819)
+                    self.crashMessage = self.region.checkSolutionLimits()
+                    if self.crashMessage:
+                        return float(np.finfo(np.float64).max)
                 self._set_forcing(4 * (timestep - 1) + i - 1)
                 time = self.integ.substepForward(time, self.dt, timestep, i)
                 if self.targets:
                     J += NORM[i - 1] * self.dt * st.computeAcousticNoise(1.0)
+                if soft:                               # time-integrated soft-limit penalty (:843-848)
+                    self.solutionLimitPenalty += NORM[i - 1] * self.dt * self.region.computeSolutionLimitPenalty()
+            if self.probeInterval > 0 and timestep % max(1, self.probeInterval) == 0:
+                self.region.saveProbeData(FORWARD, outputPrefix=self.outputPrefix)
             if record and timestep % self.saveInterval == 0:
                 self.checkpoints[timestep] = (st.conservedVariables, time)
+            if self.filterOn:                          # :872-877, after the save
+                st.applyFilter(core.Q_CONSERVED, timestep)
+                st.update()
+        if self.probeInterval > 0:
+            self.region.saveProbeData(FORWARD, finish=True, outputPrefix=self.outputPrefix)
         self.endTime = time
-        return J
+        return J + self.solutionLimitPenalty
 
     def _window(self, loaded):
         """Recompute the substep states of one checkpoint window into device slots 0 .. 4 saveInterval - 1."""

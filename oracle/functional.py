@@ -120,3 +120,74 @@ def computePressureDragAdjointForcing(opt, grid, state, patch, direction, invisc
     out[ok, 0] = 0.5 * np.sum(u[ok] ** 2, axis=1) * F[ok]
     out[ok, 1:nD + 1] = -u[ok] * F[ok, None]
     out[ok, nD + 1] = F[ok]
+
+
+def computeDragForce(opt, patches, grid, state, direction):
+    """``computeDragForce`` (``src/DragForceImpl.f90:61-146``): viscous drag on the COST_TARGET patches."""
+    nD = grid.nDimensions
+    d = unitDragDirection(nD, direction)
+    total = 0.0
+    for p in patches:
+        if p.patchType != "COST_TARGET" or p.gridIndex != grid.index:
+            continue
+        k = abs(p.normalDirection)
+        nbf = 1.0 / grid.firstDerivative[k - 1].normBoundary[0]
+        F = np.zeros(grid.nGridPoints)
+        for l in range(nD):
+            if opt.viscosityOn:
+                F = F + d[l] * np.sum(grid.metrics[:, nD * (k - 1):nD * k] *
+                                      state.stressTensor[:, nD * l:nD * (l + 1)], axis=1)
+        F = nbf * F
+        # patch%computeInnerProduct (src/CostTargetPatchImpl.f90:138-196): sum f norm g over the active patch points
+        idx = p.gridIndex0[p.active]
+        total += float(np.sum(F[idx] * costTargetPatchNorm(grid, p)[p.active] * grid.targetMollifier[idx, 0]))
+    return total
+
+
+def _unit(nD, v):
+    v = np.asarray((tuple(v) + (0.0, 0.0))[:3], dtype=np.float64)[:nD]
+    return v / np.sqrt(np.sum(v ** 2))
+
+
+def computeReynoldsStress(patches, grid, state, meanVelocity, direction1, direction2):
+    """``computeReynoldsStress`` (``src/ReynoldsStressImpl.f90:121-195``)."""
+    nD = grid.nDimensions
+    d1, d2 = _unit(nD, direction1), _unit(nD, direction2)
+    du = state.velocity - meanVelocity
+    F = 0.5 * (du @ d1) * (du @ d2)
+    return computeQuadratureOnPatches(patches, "COST_TARGET", grid, F * grid.targetMollifier[:, 0])
+
+
+def computeReynoldsStressAdjointForcing(grid, state, patch, meanVelocity, direction1, direction2):
+    """``computeReynoldsStressAdjointForcing`` (``:211-284``), assignment by assignment: the second pair of
+    assignments overwrites the first, the energy entry keeps its previous value."""
+    nD = grid.nDimensions
+    d1, d2 = _unit(nD, direction1), _unit(nD, direction2)
+    idx = patch.gridIndex0[patch.active]
+    u = state.velocity[idx]
+    du = u - meanVelocity[idx]
+    v = state.specificVolume[idx, 0]
+    moll = grid.targetMollifier[idx, 0]
+    out = patch.adjointForcing
+    F = -0.5 * moll * v * (du @ d1)
+    out[patch.active, 1:nD + 1] = d2[None, :] * F[:, None]
+    out[patch.active, 0] = -(u @ d2) * F
+    F = -0.5 * moll * v * (du @ d2)
+    out[patch.active, 1:nD + 1] = d1[None, :] * F[:, None]
+    out[patch.active, 0] = -(u @ d1) * F
+
+
+def computeMomentumActuatorSensitivity(patches, grid, state, direction=0):
+    """``computeMomentumActuatorSensitivity`` (``src/MomentumActuatorImpl.f90:81-163``)."""
+    nD = grid.nDimensions
+    comps = range(1, nD + 1) if direction == 0 else [direction]
+    F = np.stack([state.adjointVariables[:, j] * grid.controlMollifier[:, 0] for j in comps], axis=1)
+    return computeQuadratureOnPatches(patches, "ACTUATOR", grid, np.sum(F ** 2, axis=1))
+
+
+def momentumActuatorGradient(grid, state, patch, direction=0):
+    """One sample of ``updateMomentumActuatorGradient`` (``:351-412``): (nPatchPoints, nComponents)."""
+    nD = grid.nDimensions
+    comps = range(1, nD + 1) if direction == 0 else [direction]
+    m = patch.collect(grid.controlMollifier[:, 0])
+    return np.stack([m * patch.collect(state.adjointVariables[:, k]) for k in comps], axis=1)

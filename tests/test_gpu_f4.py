@@ -266,3 +266,124 @@ def test_jameson_rk3_step(shape, periodic, fused):
             t_g = a.substepForward(t_g, 2e-3, step, stage)
     assert abs(t_o - t_g) <= 1e-15 and abs(t_o - 4e-3) <= 1e-15
     assert relerr(st.conservedVariables, s.conservedVariables) <= 1e-12
+
+
+def test_forward_driver_with_limits_filter_and_probes(tmp_path):
+    """The per-timestep companions of runForward (reference src/SolverImpl.f90:805-905): soft solution-limit penalty
+    integrated with the RK4 quadrature weights, probe records every probe_interval steps, filter after each step."""
+    import magudi_b200 as mb
+    from magudi_b200 import solver as gsolver
+    from oracle import limits as ol
+    from oracle import patches as op
+    from oracle import rhs as orhs
+    g, opt, s, rng = oracle_case((34, 32), (True, True), False, True, False, "SBP 2-4", seed=14)
+    n = g.globalSize
+    ext = [5, 20, 7, 7, 1, 1]
+    po = op.ProbePatch("line", g, 0, ext, 4, probeBufferSize=2)
+    filters = ol.setupFilter(g, "Standard 5-point")
+    s.update(g, opt)
+    rho, T = s.conservedVariables[:, 0], s.temperature[:, 0]
+    dR = (float(np.quantile(rho, 0.1)), float(np.quantile(rho, 0.9)))
+    tR = (float(np.quantile(T, 0.1)), float(np.quantile(T, 0.9)))
+    factor, dt, nSteps = 0.4, 2e-3, 3
+    gg, o, st = gpu_case_from_oracle(g, opt, s)
+    gg.setupFilter("Standard 5-point")
+    region = _region(st)
+    st.addPatch("PROBE", "line", 0, ext).setupProbe(2)
+    region.setSolutionLimits(dR, tR, soft=True, penaltyFactor=factor)
+    drv = gsolver.Solver(region, st, dt, nSteps, nSteps)
+    drv.enableSolutionLimits = True
+    drv.filterOn = True
+    drv.probeInterval = 1
+    drv.outputPrefix = str(tmp_path / "run")
+    Q0 = s.conservedVariables.copy()
+    J = drv.runForward(Q0, record=False)
+    # the same march from the oracle's pieces
+    rk = orhs.RK4Integrator(s)
+    t, pen, records = 0.0, 0.0, []
+    for timestep in range(1, nSteps + 1):
+        for i in range(1, 5):
+            t = rk.substepForward(lambda m, ts, sg: orhs.computeRhs(orhs.FORWARD, opt, g, s, []), s, t, dt, timestep, i)
+            s.update(g, opt)
+            pen += gsolver.NORM[i - 1] * dt * ol.computeSolutionLimitPenalty([g], [s], dR, tR, factor)
+        if po.record(orhs.FORWARD, s):
+            records.append(po.flush())
+        s.conservedVariables[:, :] = ol.applyFilter(g, filters, s.conservedVariables, timestep)
+        s.update(g, opt)
+    records.append(po.flush())
+    assert drv.crashMessage is None
+    assert pen > 0 and abs(J - pen) <= 1e-11 * pen
+    assert relerr(st.conservedVariables, s.conservedVariables) <= 1e-12
+    raw = np.fromfile(drv.outputPrefix + ".probe_line.dat")
+    ref = np.concatenate([r.reshape(-1, order="F") for r in records])
+    assert raw.shape == ref.shape and relerr(raw, ref) <= 1e-12
+    # hard limits: a density outside the range stops the march with the reference's message
+    region.setSolutionLimits(dR, tR, soft=False)
+    J = drv.runForward(Q0, record=False)
+    assert J == np.finfo(np.float64).max and "out of range" in drv.crashMessage
+
+
+@pytest.mark.parametrize("shape", [(30, 26), (16, 15, 14)])
+def test_drag_force_and_reynolds_stress_functionals(shape):
+    """t_DragForce%compute, t_ReynoldsStress%compute / %computeAdjointForcing (reference src/DragForceImpl.f90:61-146,
+    src/ReynoldsStressImpl.f90:121-284); J within 1e-10."""
+    import magudi_b200 as mb
+    from magudi_b200 import core
+    from oracle import functional as of
+    from oracle import patches as op
+    nd = len(shape)
+    g, opt, s, rng = oracle_case(shape, (False,) * nd, True, True, False, "SBP 2-4", seed=19)
+    n = g.globalSize
+    g.targetMollifier[:, 0] = rng.random(g.nGridPoints)
+    wall = [1, n[0], 1, 1, 1, n[2]]                       # on the j = 1 face
+    box = [4, n[0] - 3, 3, n[1] - 4, 1, n[2]]
+    pw = op.CostTargetPatch("wallTarget", g, 2, wall, opt)
+    pb = op.CostTargetPatch("boxTarget", g, 0, box, opt)
+    s.update(g, opt)
+    meanU = 0.1 * rng.standard_normal((g.nGridPoints, nd))
+    gg, o, st = gpu_case_from_oracle(g, opt, s)
+    gg.set(core.G_TARGET_MOLLIFIER, g.targetMollifier)
+    region = _region(st)
+    direction = (0.6, -0.3, 0.2)
+    # drag on the wall patch
+    qw = st.addPatch("COST_TARGET", "wallTarget", 2, wall)
+    st.update()
+    J = of.computeDragForce(opt, [pw], g, s, direction)
+    assert abs(J) > 1e-6 and abs(st.computeDragForce(direction) - J) <= 1e-10 * abs(J)
+    # Reynolds stress on a volume patch of a second state (a COST_TARGET patch of another kind)
+    gg2, o2, st2 = gpu_case_from_oracle(g, opt, s)
+    gg2.set(core.G_TARGET_MOLLIFIER, g.targetMollifier)
+    qb = st2.addPatch("COST_TARGET", "boxTarget", 0, box)
+    st2.meanVelocity = meanU
+    st2.update()
+    d1, d2 = (1.0, 0.5, 0.0), (0.2, -1.0, 0.3)
+    R = of.computeReynoldsStress([pb], g, s, meanU, d1, d2)
+    assert abs(R) > 1e-8 and abs(st2.computeReynoldsStress(d1, d2) - R) <= 1e-10 * abs(R)
+    pb.adjointForcing[:, :] = 0.0
+    of.computeReynoldsStressAdjointForcing(g, s, pb, meanU, d1, d2)
+    st2.computeReynoldsStressAdjointForcing(d1, d2)
+    assert np.max(np.abs(pb.adjointForcing)) > 1e-4
+    assert relerr(qb.getArray("adjointForcing", nd + 2), pb.adjointForcing) <= 1e-12
+
+
+@pytest.mark.parametrize("shape,direction", [((30, 26), 0), ((30, 26), 2), ((16, 15, 14), 0), ((16, 15, 14), 3)])
+def test_momentum_actuator_sensitivity_and_gradient(shape, direction):
+    """t_MomentumActuator%computeSensitivity / %updateGradient (reference src/MomentumActuatorImpl.f90:81-163, 351-412)."""
+    import magudi_b200 as mb
+    from magudi_b200 import core
+    from oracle import functional as of
+    from oracle import patches as op
+    nd = len(shape)
+    g, opt, s, rng = oracle_case(shape, (False,) * nd, True, False, False, "SBP 2-4", seed=29)
+    n = g.globalSize
+    g.controlMollifier[:, 0] = rng.random(g.nGridPoints)
+    ext = [5, 14, 4, 11, 1, n[2]]
+    pa = op.ActuatorPatch("control", g, 0, ext, opt)
+    gg, o, st = gpu_case_from_oracle(g, opt, s)
+    gg.set(core.G_CONTROL_MOLLIFIER, g.controlMollifier)
+    q = st.addPatch("ACTUATOR", "control", 0, ext)
+    S = of.computeMomentumActuatorSensitivity([pa], g, s, direction)
+    assert S > 0 and abs(st.computeMomentumActuatorSensitivity(direction) - S) <= 1e-10 * S
+    G = of.momentumActuatorGradient(g, s, pa, direction)
+    got = q.momentumActuatorGradient(direction)
+    assert got.shape == G.shape and relerr(got, G) <= 1e-14
