@@ -200,6 +200,21 @@ int mg_functional_acoustic_noise(mg_state* s, double timeRampFactor, double* val
 int mg_functional_acoustic_noise_forcing(mg_state* s, double timeRampFactor);
 int mg_functional_actuator_sensitivity(mg_state* s, double timeRampFactor, double* value);
 int mg_functional_actuator_gradient(mg_patch* p, double timeRampFactor, double* hostOut);
+/* The same quantities WITHOUT a host synchronisation per substep (launch-bound cases such as the 201 x 201
+ * AcousticMonopole): the time quadratures J += norm(i) dt I (src/SolverImpl.f90:837-841) and
+ * sensitivity += norm(i) dt S (:1181-1185) are accumulated on the device -- which = 0: acoustic noise, 1: thermal
+ * actuator sensitivity; value added = weight * functional -- and read (and optionally reset) once at the end; the
+ * gradient samples go to a device-side gradientBuffer (src/ActuatorPatchImpl.f90:226-458) read back in blocks of
+ * controller_buffer_size; the control forcing of a substep is selected on the device from the uploaded
+ * "controlForcingBuffer" array ((nPatchPoints, nComponents, nSlots) via mg_patch_set_array) into components
+ * [firstComponent, firstComponent + nComponents) of "controlForcing", the others zero (updateForcing,
+ * src/ThermalActuatorImpl.f90:161-233).  Bit-identical to the synchronising calls. */
+int mg_functional_accumulate(mg_state* s, int which, double weight, double timeRampFactor);
+int mg_functional_accumulator_get(mg_state* s, int which, double* value, int reset);
+int mg_patch_gradient_buffer_setup(mg_patch* p, int nSlots);
+int mg_functional_actuator_gradient_record(mg_patch* p, double timeRampFactor, int* bufferIsFull);
+int mg_patch_gradient_buffer_flush(mg_patch* p, double* host, int* nRecords);
+int mg_patch_control_forcing_from_buffer(mg_patch* p, int slot, int firstComponent, int nComponents);
 /* t_PressureDrag%compute / %computeAdjointForcing (src/PressureDragImpl.f90:61-132, 148-267; magudi.inp
  * drag_direction_x/y/z, normalised here): J = sum over the COST_TARGET patches (on a boundary face) of
  * -(p - 1/gamma) patch%norm (metrics_k . direction) / normBoundary(1); the forcing (discrete or continuous

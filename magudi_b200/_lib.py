@@ -118,6 +118,12 @@ SIGNATURES = {
     "mg_patch_get_array": (C.c_int, [_P, C.c_char_p, C.c_int, _P]),
     "mg_patch_collect": (C.c_int, [_P, C.c_int, C.c_char_p]),
     "mg_patch_link_interface": (C.c_int, [_P, _P, _P]),
+    "mg_functional_accumulate": (C.c_int, [_P, C.c_int, C.c_double, C.c_double]),
+    "mg_functional_accumulator_get": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_int]),
+    "mg_patch_gradient_buffer_setup": (C.c_int, [_P, C.c_int]),
+    "mg_functional_actuator_gradient_record": (C.c_int, [_P, C.c_double, C.POINTER(C.c_int)]),
+    "mg_patch_gradient_buffer_flush": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
+    "mg_patch_control_forcing_from_buffer": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "mg_functional_drag_force": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     "mg_functional_reynolds_stress": (C.c_int, [_P, _P, _P, C.POINTER(C.c_double)]),
     "mg_functional_reynolds_stress_forcing": (C.c_int, [_P, _P, _P]),

@@ -408,6 +408,22 @@ class State:
         check(L.lib().mg_functional_momentum_actuator_sensitivity(self._h, int(direction), C.byref(r)))
         return r.value
 
+    # ---- device-resident time quadratures (no host synchronisation per substep)
+    ACC_COST_FUNCTIONAL, ACC_SENSITIVITY = 0, 1
+
+    def accumulateAcousticNoise(self, weight, timeRampFactor=1.0):
+        """``runningTimeQuadrature += weight * functional%compute`` on the device (``src/SolverImpl.f90:837-841``)."""
+        check(L.lib().mg_functional_accumulate(self._h, self.ACC_COST_FUNCTIONAL, float(weight), float(timeRampFactor)))
+
+    def accumulateThermalActuatorSensitivity(self, weight, timeRampFactor=1.0):
+        """``runningTimeQuadrature += weight * controller%computeSensitivity`` on the device (``:1181-1185``)."""
+        check(L.lib().mg_functional_accumulate(self._h, self.ACC_SENSITIVITY, float(weight), float(timeRampFactor)))
+
+    def accumulatorGet(self, which, reset=True):
+        r = C.c_double(0.0)
+        check(L.lib().mg_functional_accumulator_get(self._h, int(which), C.byref(r), int(bool(reset))))
+        return r.value
+
     def computeThermalActuatorSensitivity(self, timeRampFactor=1.0):
         """``t_ThermalActuator%computeSensitivity`` (``src/ThermalActuatorImpl.f90:83-159``)."""
         r = C.c_double(0.0)
@@ -609,6 +625,37 @@ class Patch:
         check(L.lib().mg_functional_actuator_gradient(self._h, float(timeRampFactor), out.ctypes.data_as(C.c_void_p)))
         return out
 
+
+    def setupGradientBuffer(self, nSlots):
+        """Device-side ``gradientBuffer`` (``src/ActuatorPatchImpl.f90:226-458``) of ``nSlots`` samples."""
+        check(L.lib().mg_patch_gradient_buffer_setup(self._h, int(nSlots)))
+        self._gradHost = np.zeros(max(self.nPatchPoints, 1) * int(nSlots))
+
+    def recordThermalActuatorGradient(self, timeRampFactor=1.0):
+        """``thermalActuatorGradient`` into the next slot of the device buffer; True when the buffer is full."""
+        full = C.c_int(0)
+        check(L.lib().mg_functional_actuator_gradient_record(self._h, float(timeRampFactor), C.byref(full)))
+        return bool(full.value)
+
+    def flushGradientBuffer(self):
+        """The recorded samples as (nRecords, nPatchPoints), in recording order; empties the buffer."""
+        n = C.c_int(0)
+        buf = self._gradHost
+        check(L.lib().mg_patch_gradient_buffer_flush(self._h, buf.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return np.array(buf[:self.nPatchPoints * n.value]).reshape(n.value, self.nPatchPoints)
+
+    def setControlForcingBuffer(self, samples):
+        """Upload the control forcing of every substep at once: ``samples`` is (nSlots, nPatchPoints[, nComponents])."""
+        a = np.asarray(samples, dtype=np.float64)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        nSlots, n, nc = a.shape
+        # device layout (nPatchPoints, nComponents, nSlots), point fastest
+        self.setArray("controlForcingBuffer", np.transpose(a, (1, 2, 0)).reshape(n, nc * nSlots, order="F"))
+
+    def controlForcingFromBuffer(self, slot, firstComponent, nComponents=1):
+        """``controller%updateForcing`` of one substep, on the device (0-based ``slot`` and ``firstComponent``)."""
+        check(L.lib().mg_patch_control_forcing_from_buffer(self._h, int(slot), int(firstComponent), int(nComponents)))
 
     def momentumActuatorGradient(self, direction=0):
         """One gradient sample ``w_{k+1} * controlMollifier`` at the patch points, (nPatchPoints, nComponents)

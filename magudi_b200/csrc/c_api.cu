@@ -691,7 +691,9 @@ int mg_state_checkpoint_load(mg_state* s, int slot) {
 int mg_state_checkpoint_clear(mg_state* s) {
   if (!s) MG_FAIL("mg_state_checkpoint_clear: null handle");
   s->checkpoints.clear();
-  mg_state_pool_trim(s);
+  // The buffers stay in the state's pool: the next checkpoint window reuses them (cudaFree / cudaMalloc of a window's
+  // worth of buffers costs more than the window's march on small grids).  MG_POOL_TRIM=1 gives the memory back.
+  if (mg_tuning_get("MG_POOL_TRIM", 0)) mg_state_pool_trim(s);
   return 0;
 }
 // ------------------------------------------------------------------------------- patch
@@ -877,6 +879,31 @@ int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep
   return 0;
 }
 
+// device-resident time quadratures and control buffers (no host synchronisation per substep)
+int mg_functional_accumulate(mg_state* s, int which, double weight, double timeRampFactor) {
+  if (!s) MG_FAIL("mg_functional_accumulate: null handle");
+  return mg_functional_accumulate_impl(s, which, weight, timeRampFactor);
+}
+int mg_functional_accumulator_get(mg_state* s, int which, double* value, int reset) {
+  if (!s || !value) MG_FAIL("mg_functional_accumulator_get: null argument");
+  return mg_functional_accumulator_get_impl(s, which, value, reset);
+}
+int mg_patch_gradient_buffer_setup(mg_patch* p, int nSlots) {
+  if (!p) MG_FAIL("mg_patch_gradient_buffer_setup: null handle");
+  return mg_patch_gradient_buffer_setup_impl(p, nSlots);
+}
+int mg_functional_actuator_gradient_record(mg_patch* p, double timeRampFactor, int* bufferIsFull) {
+  if (!p) MG_FAIL("mg_functional_actuator_gradient_record: null handle");
+  return mg_functional_actuator_gradient_record_impl(p, timeRampFactor, bufferIsFull);
+}
+int mg_patch_gradient_buffer_flush(mg_patch* p, double* host, int* nRecords) {
+  if (!p) MG_FAIL("mg_patch_gradient_buffer_flush: null handle");
+  return mg_patch_gradient_buffer_flush_impl(p, host, nRecords);
+}
+int mg_patch_control_forcing_from_buffer(mg_patch* p, int slot, int firstComponent, int nComponents) {
+  if (!p) MG_FAIL("mg_patch_control_forcing_from_buffer: null handle");
+  return mg_patch_control_forcing_from_buffer_impl(p, slot, firstComponent, nComponents);
+}
 // ------------------------------------------------------------------------------ SURVEY 8 f4
 int mg_functional_drag_force(mg_state* s, const double direction[3], double* value) {
   if (!s || !direction || !value) MG_FAIL("mg_functional_drag_force: null argument");

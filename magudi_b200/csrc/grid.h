@@ -17,6 +17,7 @@ int mg_grid_inner_product_dev(mg_grid* g, const double* f, const double* gg, con
                               int nComp, double* result);
 
 struct mg_patch;
+constexpr int MG_STATE_ACCUMULATORS = 2;
 
 struct mg_state {
   mg_grid* grid = nullptr;
@@ -42,6 +43,7 @@ struct mg_state {
   // writes to it (mg_state_make_exclusive).
   std::vector<MgField> checkpoints;
   std::vector<double*> pool;
+  size_t poolCursor = 0;        // where the search for a free pooled buffer resumes
   // inputs of the NEXT step, copied from the host into free pool buffers while the current step computes
   // (mg_state_stage_async); mg_state_adopt_staged makes them the conserved / adjoint variables (pointer swap)
   MgField staged[2];
@@ -56,6 +58,7 @@ struct mg_state {
   struct Source { double loc[3], amplitude, angularFrequency, gaussianFactor, phase; };
   std::vector<Source> acousticSources;
   std::vector<mg_patch*> patches;
+  double* accumulators = nullptr;   // device-resident time quadratures: [0] cost functional, [1] sensitivity
   bool dependentValid = false;
   bool rhsReady = false;            // the region has already evaluated the RHS of this substep (block interfaces)
   // soft solution limits (reference src/RegionImpl.f90:1094-1221, :2002-2005): adjoint forcing of the penalty

@@ -519,6 +519,7 @@ void mg_patch_destroy_impl(mg_patch* p) {
   if (!p) return;
   for (auto& kv : p->arrays) cudaFree(kv.second.p);
   cudaFree(p->probeBuffer);
+  cudaFree(p->gradientBuffer);
   if (p->remote) mg_p2p_destroy(p->remote);
   delete p;
 }
@@ -996,7 +997,16 @@ __global__ void __launch_bounds__(QUAD_THREADS) k_quadrature(QuadArgs q) {
   if (threadIdx.x == 0) q.partial[blockIdx.x] = red[0];
 }
 
-int quadrature(mg_state* s, int patchType, int kind, const double* a, const double* b, const double* w, double* value) {
+// sum of the block partials in block order (the order of the host-side sum), then acc += weight * (sum * scale): no
+// fused multiply-add, so that the device-accumulated functional equals the host-accumulated one bit for bit
+__global__ void k_quad_accumulate(const double* partial, int n, double scale, double weight, double* acc) {
+  double sum = 0.0;
+  for (int i = 0; i < n; ++i) sum = __dadd_rn(sum, partial[i]);
+  *acc = __dadd_rn(*acc, __dmul_rn(weight, __dmul_rn(sum, scale)));
+}
+
+int quadrature(mg_state* s, int patchType, int kind, const double* a, const double* b, const double* w, double* value,
+               double* devAcc = nullptr, double scale = 1.0, double weight = 1.0) {
   mg_grid* g = s->grid;
   QuadArgs q;
   std::memset(&q, 0, sizeof(q));
@@ -1006,7 +1016,7 @@ int quadrature(mg_state* s, int patchType, int kind, const double* a, const doub
     for (int d = 0; d < 3; ++d) { q.lo[q.nPatches][d] = p->localLo[d]; q.hi[q.nPatches][d] = p->localLo[d] + p->localSize[d]; }
     ++q.nPatches;
   }
-  *value = 0.0;
+  if (value) *value = 0.0;
   if (q.nPatches == 0) return 0;
   q.nx = g->localSize[0];
   q.ny = g->localSize[1];
@@ -1019,6 +1029,11 @@ int quadrature(mg_state* s, int patchType, int kind, const double* a, const doub
   q.partial = partial;
   { k_quadrature<<<QUAD_BLOCKS, QUAD_THREADS, 0, mg_stream()>>>(q); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
+  if (devAcc) {      // device-resident accumulation: no host synchronisation
+    { k_quad_accumulate<<<1, 1, 0, mg_stream()>>>(partial, QUAD_BLOCKS, scale, weight, devAcc); mg_count_launches(1); }
+    MG_CUDA(cudaGetLastError());
+    return 0;
+  }
   double host[QUAD_BLOCKS];
   MG_CUDA(cudaMemcpyAsync(host, partial, sizeof(host), cudaMemcpyDeviceToHost, mg_stream()));
   MG_CUDA(cudaStreamSynchronize(mg_stream()));
@@ -1283,6 +1298,113 @@ int mg_functional_actuator_gradient_impl(mg_patch* p, double timeRampFactor, dou
   MG_CUDA(cudaGetLastError());
   MG_CUDA(cudaMemcpyAsync(hostOut, out, (size_t)p->nPatchPoints * sizeof(double), cudaMemcpyDeviceToHost, mg_stream()));
   MG_CUDA(cudaStreamSynchronize(mg_stream()));
+  return 0;
+}
+
+// Time quadrature of the cost functional / sensitivity on the device (J += norm(i) dt I, reference
+// src/SolverImpl.f90:837-841, :1181-1185): which = 0 acoustic noise, 1 thermal-actuator sensitivity.
+int mg_functional_accumulate_impl(mg_state* s, int which, double weight, double timeRampFactor) {
+  mg_grid* g = s->grid;
+  if (which < 0 || which >= MG_STATE_ACCUMULATORS) MG_FAIL("mg_functional_accumulate: unknown accumulator");
+  if (!s->accumulators) {
+    MG_CUDA(cudaMalloc(&s->accumulators, MG_STATE_ACCUMULATORS * sizeof(double)));
+    MG_CUDA(cudaMemsetAsync(s->accumulators, 0, MG_STATE_ACCUMULATORS * sizeof(double), mg_stream()));
+  }
+  if (which == 0) {
+    if (!s->meanPressure.p) MG_FAIL("acoustic noise: the mean pressure has not been set");
+    if (!g->targetMollifier.p) MG_FAIL("acoustic noise: the target mollifier has not been set");
+    MG_TRY(mg_state_ensure_dependents(s));
+    return quadrature(s, MG_PATCH_COST_TARGET, 1, s->pressure.comp(0), s->meanPressure.comp(0),
+                      g->targetMollifier.comp(0), nullptr, s->accumulators + 0, timeRampFactor, weight);
+  }
+  if (!g->controlMollifier.p) MG_FAIL("thermal actuator: the control mollifier has not been set");
+  return quadrature(s, MG_PATCH_ACTUATOR, 2, s->W[s->curW].comp(s->nD + 1), nullptr, g->controlMollifier.comp(0),
+                    nullptr, s->accumulators + 1, timeRampFactor * timeRampFactor, weight);
+}
+
+int mg_functional_accumulator_get_impl(mg_state* s, int which, double* value, int reset) {
+  if (which < 0 || which >= MG_STATE_ACCUMULATORS) MG_FAIL("mg_functional_accumulator: unknown accumulator");
+  *value = 0.0;
+  if (!s->accumulators) return 0;
+  MG_CUDA(cudaMemcpyAsync(value, s->accumulators + which, sizeof(double), cudaMemcpyDeviceToHost, mg_stream()));
+  if (reset) MG_CUDA(cudaMemsetAsync(s->accumulators + which, 0, sizeof(double), mg_stream()));
+  MG_CUDA(cudaStreamSynchronize(mg_stream()));
+  return mg_p2p_check_all();
+}
+
+// gradientBuffer of t_ActuatorPatch (reference src/ActuatorPatchImpl.f90:226-458) on the device: samples are recorded
+// without a host synchronisation and read back in blocks.
+int mg_patch_gradient_buffer_setup_impl(mg_patch* p, int nSlots) {
+  if (p->type != MG_PATCH_ACTUATOR) MG_FAIL("mg_patch_gradient_buffer_setup: not an ACTUATOR patch");
+  if (nSlots < 1) MG_FAIL("mg_patch_gradient_buffer_setup: controller_buffer_size must be positive");
+  cudaFree(p->gradientBuffer);
+  p->gradientBuffer = nullptr;
+  p->gradientCapacity = nSlots;
+  p->gradientCount = 0;
+  if (p->nPatchPoints > 0) MG_CUDA(cudaMalloc(&p->gradientBuffer, sizeof(double) * (size_t)p->nPatchPoints * nSlots));
+  return 0;
+}
+
+int mg_functional_actuator_gradient_record_impl(mg_patch* p, double timeRampFactor, int* full) {
+  mg_state* s = p->state;
+  mg_grid* g = s->grid;
+  if (p->type != MG_PATCH_ACTUATOR || p->gradientCapacity < 1) MG_FAIL("actuator gradient record: the gradient buffer has not been set up");
+  if (!g->controlMollifier.p) MG_FAIL("thermal actuator: the control mollifier has not been set");
+  if (p->gradientCount >= p->gradientCapacity) MG_FAIL("actuator gradient record: the gradient buffer is full (flush it)");
+  if (p->nPatchPoints > 0) {
+    { k_actuator_gradient<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(
+          geom(p), s->W[s->curW].comp(s->nD + 1), g->controlMollifier.comp(0), timeRampFactor,
+          p->gradientBuffer + (size_t)p->gradientCount * p->nPatchPoints); mg_count_launches(1); }
+    MG_CUDA(cudaGetLastError());
+  }
+  ++p->gradientCount;
+  if (full) *full = p->gradientCount == p->gradientCapacity;
+  return 0;
+}
+
+int mg_patch_gradient_buffer_flush_impl(mg_patch* p, double* host, int* count) {
+  if (p->type != MG_PATCH_ACTUATOR) MG_FAIL("mg_patch_gradient_buffer_flush: not an ACTUATOR patch");
+  if (count) *count = p->gradientCount;
+  if (p->gradientCount > 0 && p->nPatchPoints > 0) {
+    if (!host) MG_FAIL("mg_patch_gradient_buffer_flush: null host buffer");
+    MG_CUDA(cudaMemcpyAsync(host, p->gradientBuffer, sizeof(double) * (size_t)p->nPatchPoints * p->gradientCount,
+                            cudaMemcpyDefault, mg_stream()));
+    MG_CUDA(cudaStreamSynchronize(mg_stream()));
+  }
+  p->gradientCount = 0;
+  return 0;
+}
+
+namespace {
+// controlForcing(:, :) = 0; controlForcing(:, first : first + nComp - 1) = controlForcingBuffer(:, :, slot)
+// (updateForcing of the controllers, reference src/ThermalActuatorImpl.f90:161-233, src/MomentumActuatorImpl.f90:165-224)
+__global__ void k_forcing_from_buffer(int n, int nU, int first, int nComp, const double* buffer, double* forcing) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  for (int c = 0; c < nU; ++c) {
+    const int b = c - first;
+    forcing[(size_t)c * n + q] = (b >= 0 && b < nComp) ? buffer[(size_t)b * n + q] : 0.0;
+  }
+}
+}  // namespace
+
+int mg_patch_control_forcing_from_buffer_impl(mg_patch* p, int slot, int firstComponent, int nComponents) {
+  mg_state* s = p->state;
+  if (p->type != MG_PATCH_ACTUATOR) MG_FAIL("mg_patch_control_forcing_from_buffer: not an ACTUATOR patch");
+  auto it = p->arrays.find("controlForcingBuffer");
+  if (it == p->arrays.end()) MG_FAIL("mg_patch_control_forcing_from_buffer: controlForcingBuffer has not been set");
+  if (nComponents < 1 || firstComponent < 0 || firstComponent + nComponents > s->nU)
+    MG_FAIL("mg_patch_control_forcing_from_buffer: component range out of bounds");
+  if (slot < 0 || (slot + 1) * nComponents > it->second.nComp) MG_FAIL("mg_patch_control_forcing_from_buffer: slot out of range");
+  double* forcing = nullptr;
+  MG_TRY(mg_patch_alloc_array(p, "controlForcing", s->nU, &forcing));
+  it = p->arrays.find("controlForcingBuffer");      // the map may have rehashed nothing, but stay safe
+  if (p->nPatchPoints > 0) {
+    { k_forcing_from_buffer<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(
+          p->nPatchPoints, s->nU, firstComponent, nComponents,
+          it->second.p + (size_t)slot * nComponents * p->nPatchPoints, forcing); mg_count_launches(1); }
+    MG_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 

@@ -41,6 +41,9 @@ struct mg_patch {
   // PROBE (src/ProbePatchImpl.f90): ring of collected solutions, (nPatchPoints, nUnknowns, probeCapacity)
   double* probeBuffer = nullptr;
   int probeCapacity = 0, probeCount = 0;
+  // ACTUATOR: gradientBuffer (reference include/ActuatorPatch.f90), (nPatchPoints, gradientCapacity) on the device
+  double* gradientBuffer = nullptr;
+  int gradientCapacity = 0, gradientCount = 0;
   std::map<std::string, Array> arrays;     // patch-point arrays, (nPatchPoints, nComp) point fastest
   bool AplusReady = false;
   int AplusIncoming = 0;
@@ -86,6 +89,12 @@ int mg_functional_actuator_sensitivity_impl(mg_state* s, double timeRampFactor, 
 int mg_functional_actuator_gradient_impl(mg_patch* p, double timeRampFactor, double* hostOut);
 int mg_functional_pressure_drag_impl(mg_state* s, const double direction[3], double* value);
 int mg_functional_pressure_drag_forcing_impl(mg_state* s, const double direction[3]);
+int mg_functional_accumulate_impl(mg_state* s, int which, double weight, double timeRampFactor);
+int mg_functional_accumulator_get_impl(mg_state* s, int which, double* value, int reset);
+int mg_patch_gradient_buffer_setup_impl(mg_patch* p, int nSlots);
+int mg_functional_actuator_gradient_record_impl(mg_patch* p, double timeRampFactor, int* full);
+int mg_patch_gradient_buffer_flush_impl(mg_patch* p, double* host, int* count);
+int mg_patch_control_forcing_from_buffer_impl(mg_patch* p, int slot, int firstComponent, int nComponents);
 int mg_functional_drag_force_impl(mg_state* s, const double direction[3], double* value);
 int mg_functional_reynolds_stress_impl(mg_state* s, const double d1[3], const double d2[3], double* value);
 int mg_functional_reynolds_stress_forcing_impl(mg_state* s, const double d1[3], const double d2[3]);

@@ -9,6 +9,8 @@
 #include <cstring>
 
 #include "grid.h"
+#include <unordered_set>
+
 #include "patches.h"
 #include "stencil_apply.h"
 #include "rhs_fused.h"
@@ -546,12 +548,28 @@ static bool read_pending(mg_state* s, const double* p) {
 }
 
 double* mg_state_pool_acquire(mg_state* s, size_t bytes) {
-  for (double* p : s->pool)
-    if (!pool_referenced(s, p, nullptr) && !read_pending(s, p)) return p;
+  // buffers are handed out in rotation: the one after the last hit is usually free (a checkpoint window takes them in
+  // order), which keeps the search O(references) instead of O(pool x references) per substep
+  const size_t P = s->pool.size();
+  for (size_t probe = 0; probe < std::min<size_t>(P, 2); ++probe) {
+    const size_t i = (s->poolCursor + probe) % P;
+    double* p = s->pool[i];
+    if (!pool_referenced(s, p, nullptr) && !read_pending(s, p)) { s->poolCursor = (i + 1) % P; return p; }
+  }
+  if (P > 2) {
+    std::unordered_set<const double*> used;
+    for_each_pooled(s, [&](MgField* f) { if (f->p) used.insert(f->p); });
+    for (size_t k = 0; k < P; ++k) {
+      const size_t i = (s->poolCursor + k) % P;
+      double* p = s->pool[i];
+      if (!used.count(p) && !read_pending(s, p)) { s->poolCursor = (i + 1) % P; return p; }
+    }
+  }
   double* fresh = nullptr;
   if (cudaMalloc(&fresh, bytes) != cudaSuccess) return nullptr;
   cudaMemsetAsync(fresh, 0, bytes, mg_stream());
   s->pool.push_back(fresh);
+  s->poolCursor = 0;
   return fresh;
 }
 
@@ -568,6 +586,7 @@ int mg_state_make_exclusive(mg_state* s, MgField* f, bool keepContents) {
 
 // Release pooled buffers nothing refers to any more.
 void mg_state_pool_trim(mg_state* s) {
+  s->poolCursor = 0;
   std::vector<double*> keep;
   for (double* p : s->pool) {
     if (pool_referenced(s, p, nullptr) || read_pending(s, p)) keep.push_back(p);
@@ -585,6 +604,7 @@ void mg_state_destroy_impl(mg_state* s) {
     mg_field_free(f);
   for (void* p : s->fusedOps) if (p) cudaFree(p);
   for (double* p : s->pool) cudaFree(p);
+  cudaFree(s->accumulators);
   delete s;
 }
 

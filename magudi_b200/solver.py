@@ -63,6 +63,12 @@ class Solver:
         self.outputPrefix = None
         self.solutionLimitPenalty = 0.0
         self.crashMessage = None
+        # J, the sensitivity, the gradient samples and the control forcing stay on the device during a march: the host
+        # only enqueues (no synchronisation per substep).  False = the round-trip-per-substep calls (same results,
+        # bit for bit: tests/test_solver_drivers.py)
+        self.deviceAccumulate = True
+        self.controllerBufferSize = None       # gradient samples per device -> host block (default: the whole run)
+        self._forcing_uploaded = None
 
     # ---- controller%updateForcing: forward substep m reads sample 4N-1-m of the reverse-time sequence
     def _set_forcing(self, substep):
@@ -70,6 +76,17 @@ class Solver:
             return
         k = 4 * self.nTimesteps - 1 - substep
         off = 0
+        if self.deviceAccumulate and self.controlForcing is not None:
+            if self._forcing_uploaded is not self.controlForcing:
+                o = 0
+                for p in self.actuators:
+                    p.setControlForcingBuffer(np.asarray(self.controlForcing)[:, o:o + p.nPatchPoints])
+                    o += p.nPatchPoints
+                self._forcing_uploaded = self.controlForcing
+            for p in self.actuators:
+                p.controlForcingFromBuffer(k, self.nU - 1, 1)
+            self._forcing_was_set = True
+            return
         for p in self.actuators:
             f = np.zeros((p.nPatchPoints, self.nU))
             if self.controlForcing is not None:
@@ -98,11 +115,16 @@ class Solver:
                 if self.enableSolutionLimits:          # checkSolutionLimits (src/SolverImpl.f90:812-819)
                     self.crashMessage = self.region.checkSolutionLimits()
                     if self.crashMessage:
+                        if self.deviceAccumulate:
+                            st.accumulatorGet(st.ACC_COST_FUNCTIONAL)        # drop the partial quadrature
                         return float(np.finfo(np.float64).max)
                 self._set_forcing(4 * (timestep - 1) + i - 1)
                 time = self.integ.substepForward(time, self.dt, timestep, i)
                 if self.targets:
-                    J += NORM[i - 1] * self.dt * st.computeAcousticNoise(1.0)
+                    if self.deviceAccumulate:
+                        st.accumulateAcousticNoise(NORM[i - 1] * self.dt, 1.0)
+                    else:
+                        J += NORM[i - 1] * self.dt * st.computeAcousticNoise(1.0)
                 if soft:                               # time-integrated soft-limit penalty (:843-848)
                     self.solutionLimitPenalty += NORM[i - 1] * self.dt * self.region.computeSolutionLimitPenalty()
             if self.probeInterval > 0 and timestep % max(1, self.probeInterval) == 0:
@@ -115,6 +137,8 @@ class Solver:
         if self.probeInterval > 0:
             self.region.saveProbeData(FORWARD, finish=True, outputPrefix=self.outputPrefix)
         self.endTime = time
+        if self.targets and self.deviceAccumulate:
+            J = st.accumulatorGet(st.ACC_COST_FUNCTIONAL)
         return J + self.solutionLimitPenalty
 
     def _window(self, loaded):
@@ -156,6 +180,11 @@ class Solver:
         loaded = None
         grad, sens = [], 0.0
         zero = {p: np.zeros((p.nPatchPoints, self.nU)) for p in self.targets}
+        dev = self.deviceAccumulate
+        blocks = {p: [] for p in self.actuators}
+        if dev:
+            for p in self.actuators:
+                p.setupGradientBuffer(self.controllerBufferSize or 4 * N)
         for timestep in range(N - 1, -1, -1):
             for i in range(4, 0, -1):
                 ts_, st_ = (timestep, 4) if i == 1 else (timestep + 1, i - 1)
@@ -168,7 +197,12 @@ class Solver:
                 st.checkpointLoad((ts_ - 1 - loaded) * 4 + st_)
                 st.update()
                 st.setTime(time)
-                if self.actuators:
+                if self.actuators and dev:
+                    for p in self.actuators:
+                        if p.recordThermalActuatorGradient(1.0):
+                            blocks[p].append(p.flushGradientBuffer())
+                    st.accumulateThermalActuatorSensitivity(NORM[i - 1] * self.dt, 1.0)
+                elif self.actuators:
                     grad.append(np.concatenate([p.thermalActuatorGradient(1.0) for p in self.actuators]))
                     sens += NORM[i - 1] * self.dt * st.computeThermalActuatorSensitivity(1.0)
                 if self.targets:
@@ -179,4 +213,10 @@ class Solver:
                         st.computeAcousticNoiseAdjointForcing(1.0)
                 time = self.integ.substepAdjoint(time, self.dt, timestep, i)
         st.checkpointClear()
+        if dev and self.actuators:
+            for p in self.actuators:
+                blocks[p].append(p.flushGradientBuffer())
+            grad = np.concatenate([np.concatenate(blocks[p], axis=0) for p in self.actuators], axis=1)
+            sens = st.accumulatorGet(st.ACC_SENSITIVITY)
+            return sens, grad
         return sens, np.array(grad)

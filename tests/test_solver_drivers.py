@@ -115,7 +115,22 @@ def test_gpu_drivers_match_oracle_and_pass_the_fd_check(gpu_lib):
     # the perturbed forward run itself matches the oracle's
     osolver.controlForcing = alphas[0] * grad_o
     J1_o = osolver.runForward(Q0, record=False)
-    assert abs(forward_with(alphas[0] * grad_g) - J1_o) <= 1e-10 * abs(J1_o)
+    J1_g = forward_with(alphas[0] * grad_g)
+    assert abs(J1_g - J1_o) <= 1e-10 * abs(J1_o)
+    # the round-trip-per-substep calls (host-side quadrature, one gradient sample and one forcing upload per substep)
+    # give the same numbers bit for bit as the device-resident accumulators / buffers used above
+    assert sol.deviceAccumulate
+    sol.deviceAccumulate = False
+    assert sol.runForward(Q0) == J_g
+    sens_h, grad_h = sol.runAdjoint()
+    assert sens_h == sens_g and np.array_equal(grad_h, grad_g)
+    assert forward_with(alphas[0] * grad_g) == J1_g
+    # gradient samples read back in blocks of controller_buffer_size
+    sol.deviceAccumulate = True
+    sol.controllerBufferSize = 7
+    sol.runForward(Q0)
+    sens_b, grad_b = sol.runAdjoint()
+    assert sens_b == sens_g and np.array_equal(grad_b, grad_g)
 
 
 def test_control_vector_files_round_trip(tmp_path):
