@@ -999,9 +999,14 @@ __global__ void __launch_bounds__(QUAD_THREADS) k_quadrature(QuadArgs q) {
 
 // sum of the block partials in block order (the order of the host-side sum), then acc += weight * (sum * scale): no
 // fused multiply-add, so that the device-accumulated functional equals the host-accumulated one bit for bit
-__global__ void k_quad_accumulate(const double* partial, int n, double scale, double weight, double* acc) {
+__global__ void __launch_bounds__(QUAD_BLOCKS > 1024 ? 1024 : QUAD_BLOCKS)
+k_quad_accumulate(const double* partial, int n, double scale, double weight, double* acc) {
+  __shared__ double sh[QUAD_BLOCKS];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = partial[i];      // one parallel read of the partials ...
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   double sum = 0.0;
-  for (int i = 0; i < n; ++i) sum = __dadd_rn(sum, partial[i]);
+  for (int i = 0; i < n; ++i) sum = __dadd_rn(sum, sh[i]);                   // ... summed in block order
   *acc = __dadd_rn(*acc, __dmul_rn(weight, __dmul_rn(sum, scale)));
 }
 
@@ -1030,7 +1035,7 @@ int quadrature(mg_state* s, int patchType, int kind, const double* a, const doub
   { k_quadrature<<<QUAD_BLOCKS, QUAD_THREADS, 0, mg_stream()>>>(q); mg_count_launches(1); }
   MG_CUDA(cudaGetLastError());
   if (devAcc) {      // device-resident accumulation: no host synchronisation
-    { k_quad_accumulate<<<1, 1, 0, mg_stream()>>>(partial, QUAD_BLOCKS, scale, weight, devAcc); mg_count_launches(1); }
+    { k_quad_accumulate<<<1, (QUAD_BLOCKS > 1024 ? 1024 : QUAD_BLOCKS), 0, mg_stream()>>>(partial, QUAD_BLOCKS, scale, weight, devAcc); mg_count_launches(1); }
     MG_CUDA(cudaGetLastError());
     return 0;
   }
