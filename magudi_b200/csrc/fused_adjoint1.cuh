@@ -356,7 +356,13 @@ int launchAdj1v2(const FusedArgs& a, int nChunks, cudaStream_t st, const CUtenso
   static_assert(NT >= 2 * R * (TX + TYv), "one halo point per thread");
   const size_t smem = sizeof(double) * ((size_t)NF * (TYv + 2 * R) * (TX + 2 * R) + (size_t)NQ * (ND + 2) * NT) + 16;
   auto kern = k_adjoint1v2<ND, R, DLO, DN, TLO, TN, CURV, CLOS, HOT, TYv, TMAQ>;
-  MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static int configuredDevice = -1;      // per template instantiation and device
+  int device = 0;
+  cudaGetDevice(&device);
+  if (configuredDevice != device) {
+    MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configuredDevice = device;
+  }
   const dim3 grid((a.nx + TX - 1) / TX, (a.ny + TYv - 1) / TYv, nChunks);
   CUtensorMap none;
   std::memset(&none, 0, sizeof(none));

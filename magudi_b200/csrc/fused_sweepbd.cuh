@@ -400,7 +400,13 @@ int launchBD(const FusedArgs& a, int nChunks, cudaStream_t st) {
   const size_t smem = sizeof(double) * ((size_t)(NU + 2) * H * W + (size_t)NU * TYv * W + (size_t)NU * H * TX +
                                         (size_t)NQ * NU * NT);
   auto kern = k_sweepBD<ND, R, DLO, DN, TLO, TN, CURV, CLOS, HOT, TYv>;
-  MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static int configuredDevice = -1;      // per template instantiation and device
+  int device = 0;
+  cudaGetDevice(&device);
+  if (configuredDevice != device) {
+    MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configuredDevice = device;
+  }
   const dim3 grid((a.nx + TX - 1) / TX, (a.ny + TYv - 1) / TYv, nChunks);
   mg_profile_begin("sweepB");
   kern<<<grid, NT, smem, st>>>(a);

@@ -1193,10 +1193,12 @@ int launchA(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
   const size_t smem = sizeof(double) * ((size_t)NP * (TY + 2 * R) * (TX + 2 * R) + (size_t)NQ * NP * NT);
   auto kern = k_sweepA<ND, R, CURV, CLOS>;
-  static bool configured = false;
-  if (!configured) {
+  static int configuredDevice = -1;      // the attribute is per device: a second mg_init on another GPU sets it again
+  int device = 0;
+  cudaGetDevice(&device);
+  if (configuredDevice != device) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configuredDevice = device;
   }
   mg_profile_begin("sweepA");
   kern<<<grid, NT, smem, st>>>(a);
@@ -1211,10 +1213,12 @@ int launchD(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NF = (ND + 2) + 2;
   const size_t smem = sizeof(double) * (size_t)NF * (TY + 2 * R) * (TX + 2 * R);
   auto kern = k_diss<ND, R, DLO, DN, TLO, TN, CLOS>;
-  static bool configured = false;
-  if (!configured) {
+  static int configuredDevice = -1;      // the attribute is per device: a second mg_init on another GPU sets it again
+  int device = 0;
+  cudaGetDevice(&device);
+  if (configuredDevice != device) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configuredDevice = device;
   }
   mg_profile_begin("dissipation");
   kern<<<grid, NT, smem, st>>>(a);
@@ -1231,10 +1235,12 @@ int launchB(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   const size_t smem = sizeof(double) * ((size_t)NU * TY * (TX + 2 * R) + (size_t)NU * (TY + 2 * R) * TX +
                                         (size_t)NQ * NU * NT);
   auto kern = k_sweepB<ND, R, CURV, CLOS>;
-  static bool configured = false;
-  if (!configured) {
+  static int configuredDevice = -1;      // the attribute is per device: a second mg_init on another GPU sets it again
+  int device = 0;
+  cudaGetDevice(&device);
+  if (configuredDevice != device) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configuredDevice = device;
   }
   mg_profile_begin("sweepB");
   kern<<<grid, NT, smem, st>>>(a);
@@ -1544,10 +1550,12 @@ int launchAdj1(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
   const size_t smem = sizeof(double) * ((size_t)NF * (TY + 2 * R) * (TX + 2 * R) + (size_t)NQ * (ND + 2) * NT);
   auto kern = k_adjoint1<ND, R, DLO, DN, TLO, TN, CURV, CLOS>;
-  static bool configured = false;
-  if (!configured) {
+  static int configuredDevice = -1;      // the attribute is per device: a second mg_init on another GPU sets it again
+  int device = 0;
+  cudaGetDevice(&device);
+  if (configuredDevice != device) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configuredDevice = device;
   }
   mg_profile_begin("adjoint1");
   kern<<<grid, NT, smem, st>>>(a);
@@ -1564,10 +1572,12 @@ int launchAdj2(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   const size_t smem = sizeof(double) * ((size_t)NG * TY * (TX + 2 * R) + (size_t)NG * (TY + 2 * R) * TX +
                                         (size_t)NQ * NG * NT);
   auto kern = k_adjoint2<ND, R, CLOS>;
-  static bool configured = false;
-  if (!configured) {
+  static int configuredDevice = -1;      // the attribute is per device: a second mg_init on another GPU sets it again
+  int device = 0;
+  cudaGetDevice(&device);
+  if (configuredDevice != device) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configuredDevice = device;
   }
   mg_profile_begin("adjoint2");
   kern<<<grid, NT, smem, st>>>(a);
