@@ -139,3 +139,39 @@ def test_patch_gather_scatter_single_process():
     G = gather_patch_data((3, 4, 1), (3, 4, 1), (0, 0, 0), a)
     assert np.array_equal(G, a)
     assert np.array_equal(scatter_patch_data((3, 4, 1), (3, 4, 1), (0, 0, 0), G, 2), a)
+
+
+def _extrema_worker(rank, world, port, ok):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from magudi_b200.parallel import combine_extrema, invert_reordering
+        # slabs of a line of values: the global minimum is attained on ranks 1 AND 2 (the first rank wins, as the
+        # reference's minloc over the gathered values does), the maximum on the last rank only
+        lo = [0.5, -1.0, -1.0, 0.25][rank % 4]
+        hi = 1.0 + rank
+        got = combine_extrema((lo, (rank + 1, 2, 3), hi, (4, 5, rank + 1)))
+        good = got[0] == -1.0 and got[1] == (2, 2, 3) and got[2] == float(world) and got[3] == (4, 5, world)
+        for order in [(1, 2, 3), (2, -1, 3), (-1, -2, 3), (-2, 1, 3), (2, 1, 3)]:
+            inv = invert_reordering(order)
+            good &= invert_reordering(inv) == tuple(order)
+        ok[rank] = 1 if good else 0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [3])
+def test_extrema_over_ranks_and_interface_reordering_gloo(world):
+    """findMinimum / findMaximum across the ranks of a grid (reference src/GridImpl.f90:1479-1494) and the inverse
+    index reordering the partner of a block interface gets (src/InterfaceHelperImpl.f90:96-105)."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ok = ctx.Array("i", [0] * world)
+    procs = [ctx.Process(target=_extrema_worker, args=(r, world, port, ok)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(ok) == [1] * world
