@@ -390,9 +390,13 @@ def run_native(args):
         barrier()
         c0 = time.perf_counter()
         e2e_begin()
+        trace = []
         for k in range(esteps):
             e2e_step(k, k == esteps - 1)
+            trace.append(time.perf_counter() - c0)
         core.transferWait()          # every result of every step has landed in host memory
+        if os.environ.get("MG_E2E_TRACE"):
+            sys.stderr.write("e2e enqueue times (s): %s, done %.4f\n" % ([round(t, 4) for t in trace], time.perf_counter() - c0))
         barrier()
         esec = (time.perf_counter() - c0) / esteps
         if world > 1:
