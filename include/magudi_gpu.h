@@ -232,7 +232,8 @@ int mg_functional_drag_force(mg_state* s, const double direction[3], double* val
 int mg_functional_reynolds_stress(mg_state* s, const double direction1[3], const double direction2[3], double* value);
 int mg_functional_reynolds_stress_forcing(mg_state* s, const double direction1[3], const double direction2[3]);
 /* t_MomentumActuator%computeSensitivity / %updateGradient (src/MomentumActuatorImpl.f90:81-163, 351-412):
- * direction 0 = all momentum components (nD gradient components per patch point), d > 0 = component d only. */
+ * direction 0 = all momentum components (nD gradient components per patch point), d > 0 = component d only,
+ * -1 = t_GenericActuator (src/GenericActuatorImpl.f90:77-149, 319-376): every unknown (nUnknowns components). */
 int mg_functional_momentum_actuator_sensitivity(mg_state* s, int direction, double* value);
 int mg_functional_momentum_actuator_gradient(mg_patch* p, int direction, double* hostOut);
 

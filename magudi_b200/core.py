@@ -391,6 +391,33 @@ class State:
         check(L.lib().mg_functional_drag_force(self._h, self._vec3(direction), C.byref(r)))
         return r.value
 
+    def computeDragForceAdjointForcing(self):
+        """``t_DragForce%computeAdjointForcing`` (``src/DragForceImpl.f90:159-209``) for every COST_TARGET patch, composed
+        from C-ABI operators exactly as the reference writes it: it uses ``metrics(:,1)`` and ``metrics(:,5)``, so it
+        is defined on 3-D grids only.  Setup-rate code (host arrays, a handful of operator applications)."""
+        g = self.grid
+        if g.nDimensions != 3:
+            raise NotImplementedError("computeDragForceAdjointForcing: the reference indexes metrics(:,5) (3-D grids)")
+        nU, n = self.nUnknowns, tuple(g.localSize)
+        jac, met = g.get(G_JACOBIAN)[:, 0], g.get(G_METRICS)
+        self.update()
+        mu, v = self.dynamicViscosity[:, 0], self.specificVolume[:, 0]
+        d1, a1, a2 = g.operator("firstDerivative", 1), g.operator("adjointFirstDerivative", 1), \
+            g.operator("adjointFirstDerivative", 2)
+        for p in self.patches:
+            if p.patchType != "COST_TARGET" or p.nPatchPoints <= 0:
+                continue
+            k = abs(p.normalDirection)
+            nbf = 1.0 / g.operator("firstDerivative", k).coefficients()["normBoundary"][0]
+            temp1 = np.zeros((g.nGridPoints, nU))
+            t2 = a1.projectOnBoundaryAndApply((jac * met[:, 0] * mu).reshape(-1, 1), n, p.normalDirection)
+            t2 = d1.applyNorm(t2, n)
+            temp1[:, 2] = jac * v * t2[:, 0]
+            t2 = a2.projectOnBoundaryAndApply((jac * met[:, 4] * mu).reshape(-1, 1), n, p.normalDirection)
+            t2 = d1.applyNorm(t2, n)
+            temp1[:, 1] = jac * v * t2[:, 0]
+            p.setArray("adjointForcing", temp1[p.gridIndices()] * nbf)
+
     def computeReynoldsStress(self, direction1=(1.0, 0.0, 0.0), direction2=(1.0, 0.0, 0.0)):
         """``t_ReynoldsStress%compute`` (``src/ReynoldsStressImpl.f90:121-195``); needs ``meanVelocity``."""
         r = C.c_double(0.0)
@@ -403,7 +430,8 @@ class State:
         check(L.lib().mg_functional_reynolds_stress_forcing(self._h, self._vec3(direction1), self._vec3(direction2)))
 
     def computeMomentumActuatorSensitivity(self, direction=0):
-        """``t_MomentumActuator%computeSensitivity`` (``src/MomentumActuatorImpl.f90:81-163``)."""
+        """``t_MomentumActuator%computeSensitivity`` (``src/MomentumActuatorImpl.f90:81-163``); ``direction=-1``:
+        ``t_GenericActuator%computeSensitivity`` (``src/GenericActuatorImpl.f90:77-149``), every unknown."""
         r = C.c_double(0.0)
         check(L.lib().mg_functional_momentum_actuator_sensitivity(self._h, int(direction), C.byref(r)))
         return r.value
@@ -660,7 +688,7 @@ class Patch:
     def momentumActuatorGradient(self, direction=0):
         """One gradient sample ``w_{k+1} * controlMollifier`` at the patch points, (nPatchPoints, nComponents)
         (``t_MomentumActuator%updateGradient``, ``src/MomentumActuatorImpl.f90:351-412``)."""
-        nc = self.state.nDimensions if direction == 0 else 1
+        nc = self.state.nUnknowns if direction < 0 else (self.state.nDimensions if direction == 0 else 1)
         out = np.zeros((max(self.nPatchPoints, 0), nc), order="F")
         check(L.lib().mg_functional_momentum_actuator_gradient(self._h, int(direction), L.fptr(out)))
         return out

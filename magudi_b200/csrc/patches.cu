@@ -1565,10 +1565,11 @@ int mg_functional_reynolds_stress_forcing_impl(mg_state* s, const double d1[3], 
 int mg_functional_momentum_actuator_sensitivity_impl(mg_state* s, int direction, double* value) {
   mg_grid* g = s->grid;
   if (!g->controlMollifier.p) MG_FAIL("momentum actuator: the control mollifier has not been set");
-  if (direction < 0 || direction > s->nD) MG_FAIL("momentum actuator: invalid direction");
+  if (direction < -1 || direction > s->nD) MG_FAIL("momentum actuator: invalid direction");
   *value = 0.0;
-  for (int j = 1; j <= s->nD; ++j) {
-    if (direction != 0 && j != direction) continue;
+  // direction -1: t_GenericActuator (reference src/GenericActuatorImpl.f90:77-149), every unknown
+  for (int j = (direction < 0 ? 0 : 1); j <= (direction < 0 ? s->nU - 1 : s->nD); ++j) {
+    if (direction > 0 && j != direction) continue;
     double r = 0.0;
     MG_TRY(quadrature(s, MG_PATCH_ACTUATOR, 2, s->W[s->curW].comp(j), nullptr, g->controlMollifier.comp(0), &r));
     *value += r;
@@ -1581,14 +1582,14 @@ int mg_functional_momentum_actuator_gradient_impl(mg_patch* p, int direction, do
   mg_grid* g = s->grid;
   if (p->type != MG_PATCH_ACTUATOR) MG_FAIL("momentum actuator gradient: not an ACTUATOR patch");
   if (!g->controlMollifier.p) MG_FAIL("momentum actuator: the control mollifier has not been set");
-  if (direction < 0 || direction > s->nD) MG_FAIL("momentum actuator: invalid direction");
+  if (direction < -1 || direction > s->nD) MG_FAIL("momentum actuator: invalid direction");
   if (p->nPatchPoints <= 0) return 0;
-  const int nComp = direction == 0 ? s->nD : 1;
+  const int nComp = direction < 0 ? s->nU : (direction == 0 ? s->nD : 1);
   double* out = nullptr;
   MG_TRY(mg_patch_alloc_array(p, "momentumGradient", nComp, &out));
   int c = 0;
-  for (int k = 1; k <= s->nD; ++k) {
-    if (direction != 0 && k != direction) continue;
+  for (int k = (direction < 0 ? 0 : 1); k <= (direction < 0 ? s->nU - 1 : s->nD); ++k) {
+    if (direction > 0 && k != direction) continue;
     { k_actuator_gradient<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(geom(p), s->W[s->curW].comp(k),
                                                                         g->controlMollifier.comp(0), 1.0,
                                                                         out + (size_t)c * p->nPatchPoints); mg_count_launches(1); }

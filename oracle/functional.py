@@ -178,9 +178,10 @@ def computeReynoldsStressAdjointForcing(grid, state, patch, meanVelocity, direct
 
 
 def computeMomentumActuatorSensitivity(patches, grid, state, direction=0):
-    """``computeMomentumActuatorSensitivity`` (``src/MomentumActuatorImpl.f90:81-163``)."""
+    """``computeMomentumActuatorSensitivity`` (``src/MomentumActuatorImpl.f90:81-163``); ``direction = -1``:
+    ``computeGenericActuatorSensitivity`` (``src/GenericActuatorImpl.f90:77-149``)."""
     nD = grid.nDimensions
-    comps = range(1, nD + 1) if direction == 0 else [direction]
+    comps = range(nD + 2) if direction < 0 else (range(1, nD + 1) if direction == 0 else [direction])
     F = np.stack([state.adjointVariables[:, j] * grid.controlMollifier[:, 0] for j in comps], axis=1)
     return computeQuadratureOnPatches(patches, "ACTUATOR", grid, np.sum(F ** 2, axis=1))
 
@@ -188,6 +189,27 @@ def computeMomentumActuatorSensitivity(patches, grid, state, direction=0):
 def momentumActuatorGradient(grid, state, patch, direction=0):
     """One sample of ``updateMomentumActuatorGradient`` (``:351-412``): (nPatchPoints, nComponents)."""
     nD = grid.nDimensions
-    comps = range(1, nD + 1) if direction == 0 else [direction]
+    comps = range(nD + 2) if direction < 0 else (range(1, nD + 1) if direction == 0 else [direction])
     m = patch.collect(grid.controlMollifier[:, 0])
     return np.stack([m * patch.collect(state.adjointVariables[:, k]) for k in comps], axis=1)
+
+
+def computeDragForceAdjointForcing(opt, grid, state, patch):
+    """``computeDragForceAdjointForcing`` (``src/DragForceImpl.f90:159-209``), statement by statement (3-D grids:
+    the reference indexes ``metrics(:,5)``)."""
+    nD = grid.nDimensions
+    assert nD == 3
+    k = abs(patch.normalDirection)
+    nbf = 1.0 / grid.firstDerivative[k - 1].normBoundary[0]
+    n = grid.localSize
+    J, mu, v = grid.jacobian[:, 0], state.dynamicViscosity[:, 0], state.specificVolume[:, 0]
+    temp1 = np.zeros((grid.nGridPoints, nD + 2))
+    t2 = (J * grid.metrics[:, 0] * mu).reshape(-1, 1)
+    t2 = grid.adjointFirstDerivative[0].projectOnBoundaryAndApply(t2, n, patch.normalDirection)
+    t2 = grid.firstDerivative[0].applyNorm(t2, n)
+    temp1[:, 2] = J * v * t2[:, 0]
+    t2 = (J * grid.metrics[:, 4] * mu).reshape(-1, 1)
+    t2 = grid.adjointFirstDerivative[1].projectOnBoundaryAndApply(t2, n, patch.normalDirection)
+    t2 = grid.firstDerivative[0].applyNorm(t2, n)
+    temp1[:, 1] = J * v * t2[:, 0]
+    patch.adjointForcing = patch.collect(temp1) * nbf

@@ -350,6 +350,11 @@ def test_drag_force_and_reynolds_stress_functionals(shape):
     st.update()
     J = of.computeDragForce(opt, [pw], g, s, direction)
     assert abs(J) > 1e-6 and abs(st.computeDragForce(direction) - J) <= 1e-10 * abs(J)
+    if nd == 3:      # the reference's DRAG adjoint forcing indexes metrics(:,5): 3-D grids only
+        of.computeDragForceAdjointForcing(opt, g, s, pw)
+        st.computeDragForceAdjointForcing()
+        assert np.max(np.abs(pw.adjointForcing)) > 1e-6
+        assert relerr(qw.getArray("adjointForcing", nd + 2), pw.adjointForcing) <= 1e-12
     # Reynolds stress on a volume patch of a second state (a COST_TARGET patch of another kind)
     gg2, o2, st2 = gpu_case_from_oracle(g, opt, s)
     gg2.set(core.G_TARGET_MOLLIFIER, g.targetMollifier)
@@ -366,9 +371,11 @@ def test_drag_force_and_reynolds_stress_functionals(shape):
     assert relerr(qb.getArray("adjointForcing", nd + 2), pb.adjointForcing) <= 1e-12
 
 
-@pytest.mark.parametrize("shape,direction", [((30, 26), 0), ((30, 26), 2), ((16, 15, 14), 0), ((16, 15, 14), 3)])
+@pytest.mark.parametrize("shape,direction", [((30, 26), 0), ((30, 26), 2), ((16, 15, 14), 0), ((16, 15, 14), 3),
+                                             ((30, 26), -1), ((16, 15, 14), -1)])
 def test_momentum_actuator_sensitivity_and_gradient(shape, direction):
-    """t_MomentumActuator%computeSensitivity / %updateGradient (reference src/MomentumActuatorImpl.f90:81-163, 351-412)."""
+    """t_MomentumActuator%computeSensitivity / %updateGradient (reference src/MomentumActuatorImpl.f90:81-163, 351-412);
+    direction -1: t_GenericActuator (src/GenericActuatorImpl.f90:77-149, 319-376)."""
     import magudi_b200 as mb
     from magudi_b200 import core
     from oracle import functional as of
