@@ -718,7 +718,29 @@ class Region:
         check(L.lib().mg_region_compute_sponge_strengths(self._h))
 
     def computeRhs(self, mode, timestep=0, stage=1):
+        if mode == ADJOINT:
+            self._update_limit_flags()
         check(L.lib().mg_region_compute_rhs(self._h, int(mode), int(timestep), int(stage)))
+
+    softSolutionLimits = False
+
+    def _update_limit_flags(self):
+        """Soft solution limits on a decomposed grid: the range test of ``isVariableWithinRange`` is collective over the
+        grid's ranks (``src/GridImpl.f90:1479-1494``), so the host reduces the extrema and hands the result to the
+        library before an adjoint RHS evaluation; on one rank the library tests locally."""
+        from . import parallel
+        if not self.softSolutionLimits:
+            return
+        if not parallel.collectives_active():
+            for s in self.states:
+                check(L.lib().mg_state_set_solution_limit_flags(s._h, -1, -1))     # the library tests locally
+            return
+        for s in self.states:
+            flags = []
+            for var, rng in (("density", self.densityRange), ("temperature", self.temperatureRange)):
+                lo, _, hi, _ = parallel.combine_extrema(s.extrema(var))
+                flags.append(int(lo <= rng[0] or hi >= rng[1]))
+            check(L.lib().mg_state_set_solution_limit_flags(s._h, flags[0], flags[1]))
 
     def setSolutionLimits(self, densityRange, temperatureRange, soft=False, penaltyFactor=0.0):
         """``enable_solution_limits`` / ``soft_solution_limits`` with ``solverOptions%densityRange``,
@@ -854,6 +876,7 @@ class RK4Integrator:
 
     def substepAdjoint(self, time, timeStepSize, timestep, stage):
         t = C.c_double(time)
+        self.region._update_limit_flags()
         check(L.lib().mg_rk4_substep(self.region._h, ADJOINT, C.byref(t), float(timeStepSize), int(timestep),
                                      int(stage), 0))
         return t.value

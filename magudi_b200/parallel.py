@@ -275,10 +275,33 @@ def link_interfaces_remote(links):
     return keep
 
 
+# Host-side reductions of this module run over the default process group.  A caller that holds a whole (undecomposed)
+# problem inside a multi-process job -- tools/multi_gpu_check.py's single-GPU reference run on rank 0 -- switches them off.
+_COLLECTIVES = True
+
+
+class single_process:
+    """Context manager: inside it ``combine_extrema`` / ``all_reduce_sum`` return their local argument."""
+
+    def __enter__(self):
+        global _COLLECTIVES
+        self._saved, _COLLECTIVES = _COLLECTIVES, False
+        return self
+
+    def __exit__(self, *exc):
+        global _COLLECTIVES
+        _COLLECTIVES = self._saved
+        return False
+
+
+def collectives_active():
+    return _COLLECTIVES and dist.is_initialized() and dist.get_world_size() > 1
+
+
 def combine_extrema(local):
     """``findMinimum`` / ``findMaximum`` over the ranks of a grid (``src/GridImpl.f90:1479-1494``: all-gather, then the
     first rank holding the extremum): ``local = (min, ijk, max, ijk)`` of this rank."""
-    if not dist.is_initialized() or dist.get_world_size() == 1:
+    if not collectives_active():
         return local
     allv = [None] * dist.get_world_size()
     dist.all_gather_object(allv, local)
@@ -289,16 +312,20 @@ def combine_extrema(local):
 
 def all_reduce_sum(value, device=None):
     """Sum a host scalar over ranks (inner products, cost functional)."""
-    if not dist.is_initialized() or dist.get_world_size() == 1:
+    if not collectives_active():
         return value
+    if device is None and dist.get_backend() == "nccl":
+        device = torch.device("cuda", torch.cuda.current_device())
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
 
 
 def all_reduce_max(value, device=None):
-    if not dist.is_initialized() or dist.get_world_size() == 1:
+    if not collectives_active():
         return value
+    if device is None and dist.get_backend() == "nccl":
+        device = torch.device("cuda", torch.cuda.current_device())
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
