@@ -33,6 +33,18 @@ def zaxpy(a, x, y=None):
     return z if y is None else z + np.asarray(y, dtype=np.float64)
 
 
+def zaxpy_files(zFilename, a, xFilename, yFilename=None):
+    """``ZAXPY`` of the control-space advancer on files (``src/ControlSpaceAdvancerImpl.f90``, ``bin/ZAXPY.f90``; the
+    reference's ``test/testZAXPY.f90``): Z = a X + Y on raw fp64 streams of equal length, Y optional."""
+    x = np.fromfile(xFilename, dtype="<f8")
+    y = None
+    if yFilename:
+        y = np.fromfile(yFilename, dtype="<f8")
+        if y.size != x.size:
+            raise ValueError("ZAXPY: %s and %s do not have the same size" % (xFilename, yFilename))
+    np.ascontiguousarray(zaxpy(a, x, y), dtype="<f8").tofile(zFilename)
+
+
 def save_control_vector(filename, v):
     """``<prefix>.gradient_<patch>.dat`` / ``.control_forcing_<patch>.dat``: raw fp64, one patch-ordered block per
     substep, substeps in reverse time order (``src/ActuatorPatchImpl.f90:409-458``)."""

@@ -140,3 +140,21 @@ def test_control_vector_files_round_trip(tmp_path):
     gsol.save_control_vector(f, g)
     assert np.array_equal(gsol.load_control_vector(f, 5), g)
     assert np.array_equal(gsol.zaxpy(2.0, g, g), 3.0 * g)
+
+
+def test_zaxpy_on_files(tmp_path):
+    """The reference's ``test/testZAXPY.f90``: Z = a X + Y through files reproduces the in-memory result exactly."""
+    from magudi_b200 import solver as gsol
+    rng = np.random.default_rng(0)
+    n = 1000
+    X, Y, a = rng.random(n), rng.random(n), float(rng.random())
+    fx, fy, fz = (str(tmp_path / f) for f in ("x.dat", "y.dat", "z.dat"))
+    X.tofile(fx)
+    Y.tofile(fy)
+    gsol.zaxpy_files(fz, a, fx, fy)
+    assert np.array_equal(np.fromfile(fz), a * X + Y)
+    gsol.zaxpy_files(fz, a, fx)
+    assert np.array_equal(np.fromfile(fz), a * X)
+    with pytest.raises(ValueError):
+        Y[:10].tofile(fy)
+        gsol.zaxpy_files(fz, a, fx, fy)
