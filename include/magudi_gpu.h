@@ -337,6 +337,13 @@ int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep
  * phase 1 = first adjoint sweep (needs ghost planes of the adjoint variables), phase 2 = second sweep +
  * RK4 update (needs ghost planes of MG_Q_FUSED_ADJOINT_DIFFUSION3).  Fused path only. */
 int mg_rk4_substep_adjoint_phase(mg_region* r, int phase, double* time, double dt, int timestep, int stage);
+/* enable_body_force (src/SimulationFlagsImpl.f90:42, src/SolverImpl.f90:760-765, addBodyForce src/RegionImpl.f90:732-851):
+ * the x-momentum conserving body force that mg_region_compute_rhs / mg_rk4_substep add after the sources.  Call after
+ * the states (with their grids updated) have been added; initialMomentumPerVolume is body_force/initial_momentum.  The
+ * stage argument of mg_region_compute_rhs is the reference's: the loss is re-evaluated at stage 1, the adjoint
+ * bookkeeping runs over stages 4..1.  One process per grid (the region integrals are not reduced over ranks). */
+int mg_region_set_body_force(mg_region* r, int enable, double initialMomentumPerVolume, double timeStepSize);
+int mg_region_get_body_force(mg_region* r, double* momentumLossPerVolume, double* adjointMomentumLossPerVolume);
 /* t_JamesonRK3Integrator%substepForward (src/JamesonRK3IntegratorImpl.f90:56-131; the reference's adjoint and
  * linearized RK3 substeps are empty): stage 1..3, same conventions as mg_rk4_substep. */
 int mg_rk3_substep(mg_region* r, double* time, double dt, int timestep, int stage, int updateStates);

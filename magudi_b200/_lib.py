@@ -129,6 +129,8 @@ SIGNATURES = {
     "mg_functional_reynolds_stress_forcing": (C.c_int, [_P, _P, _P]),
     "mg_functional_momentum_actuator_sensitivity": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "mg_functional_momentum_actuator_gradient": (C.c_int, [_P, C.c_int, _P]),
+    "mg_region_set_body_force": (C.c_int, [_P, C.c_int, C.c_double, C.c_double]),
+    "mg_region_get_body_force": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mg_rk3_substep": (C.c_int, [_P, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int, C.c_int]),
     "mg_patch_kolmogorov_setup": (C.c_int, [_P, C.c_double, C.c_int]),
     "mg_patch_set_jet_modes": (C.c_int, [_P, C.c_int, _P]),

@@ -264,6 +264,8 @@ def load_case(directory, inp="magudi.inp"):
         c.region.setSolutionLimits((deck.require("minimum_density", 0.0), deck.require("maximum_density", 0.0)),
                                    (deck.require("minimum_temperature", 0.0), deck.require("maximum_temperature", 0.0)),
                                    soft=soft, penaltyFactor=deck.get("solution_limit_penalty_factor", 1.0))
+    if deck.get("enable_body_force", False):                  # src/SimulationFlagsImpl.f90:42, src/SolverImpl.f90:760-765
+        c.region.setBodyForce(deck.require("body_force/initial_momentum", 0.0), deck.get("time_step_size", 0.0))
     c.filterOn = bool(deck.get("filter_solution", False))
     if c.filterOn:
         for g in c.grids:

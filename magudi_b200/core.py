@@ -742,6 +742,19 @@ class Region:
                 flags.append(int(lo <= rng[0] or hi >= rng[1]))
             check(L.lib().mg_state_set_solution_limit_flags(s._h, flags[0], flags[1]))
 
+    def setBodyForce(self, initialMomentumPerVolume, timeStepSize, enable=True):
+        """``enable_body_force`` with ``body_force/initial_momentum`` (``src/SolverImpl.f90:760-765``): ``computeRhs``
+        and the RK4 substeps add ``addBodyForce`` (``src/RegionImpl.f90:732-851``) with the stage they are given."""
+        check(L.lib().mg_region_set_body_force(self._h, int(bool(enable)), float(initialMomentumPerVolume),
+                                               float(timeStepSize)))
+
+    @property
+    def bodyForce(self):
+        """``(momentumLossPerVolume, adjointMomentumLossPerVolume)`` of the region."""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        check(L.lib().mg_region_get_body_force(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def setSolutionLimits(self, densityRange, temperatureRange, soft=False, penaltyFactor=0.0):
         """``enable_solution_limits`` / ``soft_solution_limits`` with ``solverOptions%densityRange``,
         ``%temperatureRange`` and ``%solutionLimitPenaltyFactor``.  With ``soft``, ``computeRhs(ADJOINT)`` adds

@@ -126,6 +126,12 @@ void mg_profile_end() {
 struct mg_region {
   std::vector<mg_state*> states;
   int fused = 1;
+  // x-momentum conserving body force (reference include/Region.f90:44-45, src/RegionImpl.f90:732-851)
+  struct BodyForce {
+    bool enabled = false;
+    double initialXmomentum = 0.0, oneOverVolume = 0.0, dt = 0.0;
+    double momentumLoss = 0.0, adjointMomentumLoss = 0.0;
+  } bf;
 };
 
 static bool is_device_pointer(const void* p) {
@@ -829,20 +835,90 @@ static bool region_has_interfaces(const mg_region* r) {
 // t_Region%computeRhs (reference src/RegionImpl.f90:1877-2027).  With block interfaces the evaluation is staged
 // over all the grids of the region as in the reference: RHS of every grid, interface exchange, then the viscous
 // interface adjoint penalty, 1/J, patch penalties and sources of every grid.
-static int region_compute_rhs(mg_region* r, int mode) {
+// addBodyForce (reference src/RegionImpl.f90:732-851): region integrals on the device (two-stage deterministic
+// reductions, one host synchronisation each, as the reference's MPI reductions), pointwise adds in one kernel per state
+static int region_add_body_force(mg_region* r, int mode, int stage) {
+  mg_region::BodyForce& bf = r->bf;
+  auto integral = [&](int which, double* out) -> int {
+    *out = 0.0;
+    for (mg_state* s : r->states) {
+      double v = 0.0;
+      MG_TRY(mg_state_integral_impl(s, which, &v));
+      *out += v;
+    }
+    return 0;
+  };
+  if (stage == 1) {
+    double current = 0.0;
+    MG_TRY(integral(1, &current));
+    bf.momentumLoss = bf.oneOverVolume / bf.dt * (bf.initialXmomentum - current);
+    if (mode == MG_LINEARIZED) {
+      double dmom = 0.0;
+      MG_TRY(integral(2, &dmom));
+      bf.adjointMomentumLoss = 0.0 - bf.oneOverVolume / bf.dt * dmom;
+    }
+  }
+  double stage1Term = 0.0;
+  if (mode == MG_ADJOINT) {
+    const double factor = (stage == 2 || stage == 3) ? 2.0 : 1.0;
+    double wmom = 0.0, wx = 0.0;
+    MG_TRY(integral(2, &wmom));
+    MG_TRY(integral(3, &wx));
+    bf.adjointMomentumLoss = bf.adjointMomentumLoss - factor * (wmom + wx);
+    if (stage == 1) stage1Term = bf.adjointMomentumLoss * bf.oneOverVolume / bf.dt;
+  }
+  for (mg_state* s : r->states)
+    MG_TRY(mg_state_add_body_force_impl(s, mode, bf.momentumLoss, bf.adjointMomentumLoss, stage == 1, stage1Term));
+  if (mode == MG_ADJOINT && stage == 1) bf.adjointMomentumLoss = 0.0;
+  return 0;
+}
+
+static int region_compute_rhs(mg_region* r, int mode, int stage = 1) {
   if (!region_has_interfaces(r)) {
     for (mg_state* s : r->states) MG_TRY(mg_state_compute_rhs_impl(s, mode));
-    return 0;
+  } else {
+    for (mg_state* s : r->states) MG_TRY(mg_state_rhs_pre(s, mode));
+    MG_TRY(mg_interfaces_exchange(r->states, mode));
+    for (mg_state* s : r->states) MG_TRY(mg_state_rhs_post(s, mode));
   }
-  for (mg_state* s : r->states) MG_TRY(mg_state_rhs_pre(s, mode));
-  MG_TRY(mg_interfaces_exchange(r->states, mode));
-  for (mg_state* s : r->states) MG_TRY(mg_state_rhs_post(s, mode));
+  // the body force joins after the sources; hole points stay zero (src/RegionImpl.f90:2012-2023)
+  if (r->bf.enabled) MG_TRY(region_add_body_force(r, mode, stage));
+  return 0;
+}
+int mg_region_set_body_force(mg_region* r, int enable, double initialMomentumPerVolume, double timeStepSize) {
+  if (!r) MG_FAIL("mg_region_set_body_force: null handle");
+  r->bf = mg_region::BodyForce();
+  for (mg_state* s : r->states) s->bodyForce = enable != 0;
+  if (!enable) return 0;
+  if (!(timeStepSize > 0.0)) MG_FAIL("mg_region_set_body_force: the time step size must be positive");
+  for (mg_state* s : r->states) {
+    const mg_grid* g = s->grid;
+    if (g->procDims[0] * g->procDims[1] * g->procDims[2] != 1)
+      MG_FAIL("mg_region_set_body_force: region integrals of a decomposed grid are not reduced over ranks yet");
+  }
+  double volume = 0.0;
+  for (mg_state* s : r->states) {
+    double v = 0.0;
+    MG_TRY(mg_state_integral_impl(s, 0, &v));
+    volume += v;
+  }
+  // src/SolverImpl.f90:760-765: body_force/initial_momentum is per unit volume
+  r->bf.enabled = true;
+  r->bf.initialXmomentum = initialMomentumPerVolume * volume;
+  r->bf.oneOverVolume = 1.0 / volume;
+  r->bf.dt = timeStepSize;
+  return 0;
+}
+int mg_region_get_body_force(mg_region* r, double* momentumLossPerVolume, double* adjointMomentumLossPerVolume) {
+  if (!r) MG_FAIL("mg_region_get_body_force: null handle");
+  if (momentumLossPerVolume) *momentumLossPerVolume = r->bf.momentumLoss;
+  if (adjointMomentumLossPerVolume) *adjointMomentumLossPerVolume = r->bf.adjointMomentumLoss;
   return 0;
 }
 int mg_region_compute_rhs(mg_region* r, int mode, int timestep, int stage) {
-  (void)timestep; (void)stage;
+  (void)timestep;
   if (!r) MG_FAIL("mg_region_compute_rhs: null handle");
-  return region_compute_rhs(r, mode);
+  return region_compute_rhs(r, mode, stage);
 }
 int mg_patch_link_interface(mg_patch* a, mg_patch* b, const int indexReorderingA[3]) {
   return mg_interface_link(a, b, indexReorderingA);
@@ -861,10 +937,10 @@ int mg_patch_link_interface_remote(mg_patch* p, const int indexReordering[3], do
 int mg_rk4_substep(mg_region* r, int mode, double* time, double dt, int timestep, int stage, int updateStates) {
   if (!r || !time) MG_FAIL("mg_rk4_substep: null argument");
   double t = *time;
-  if (region_has_interfaces(r)) {
+  if (region_has_interfaces(r) || r->bf.enabled) {
     if (stage < 1 || stage > 4) MG_FAIL("rk4 substep: stage must be 1..4");
     for (mg_state* s : r->states) mg_rk4_set_times(s, mode, *time, dt, stage);
-    MG_TRY(region_compute_rhs(r, mode));
+    MG_TRY(region_compute_rhs(r, mode, stage));
     for (mg_state* s : r->states) s->rhsReady = true;
   }
   for (mg_state* s : r->states) {
@@ -1006,13 +1082,13 @@ int mg_rk3_substep(mg_region* r, double* time, double dt, int timestep, int stag
   if (!r || !time) MG_FAIL("mg_rk3_substep: null argument");
   if (stage < 1 || stage > 3) MG_FAIL("mg_rk3_substep: stage must be 1..3");
   double t = *time;
-  if (region_has_interfaces(r)) {
+  if (region_has_interfaces(r) || r->bf.enabled) {
     for (mg_state* s : r->states) {
       if (stage == 1) s->timeProgressive = *time + dt / 2.0;
       if (stage == 2) { s->time = *time + dt / 2.0; s->timeProgressive = *time + dt; }
       if (stage == 3) s->time = *time + dt / 2.0;
     }
-    MG_TRY(region_compute_rhs(r, MG_FORWARD));
+    MG_TRY(region_compute_rhs(r, MG_FORWARD, stage));
     for (mg_state* s : r->states) s->rhsReady = true;
   }
   for (mg_state* s : r->states) {

@@ -58,6 +58,7 @@ struct mg_state {
   struct Source { double loc[3], amplitude, angularFrequency, gaussianFactor, phase; };
   std::vector<Source> acousticSources;
   std::vector<mg_patch*> patches;
+  bool bodyForce = false;           // the region adds the x-momentum body force after the RHS: no RK-fused sweeps
   double* accumulators = nullptr;   // device-resident time quadratures: [0] cost functional, [1] sensitivity
   bool dependentValid = false;
   bool rhsReady = false;            // the region has already evaluated the RHS of this substep (block interfaces)
@@ -109,6 +110,9 @@ int mg_state_limit_forcing_impl(mg_state* s, const double densityRange[2], const
 int mg_grid_setup_filter_impl(mg_grid* g, const char* filteringScheme);
 int mg_grid_apply_filter_impl(mg_grid* g, MgField* f, int timestep);
 int mg_rk3_substep_impl(mg_state* s, double* time, double dt, int stage);
+int mg_state_integral_impl(mg_state* s, int which, double* value);
+int mg_state_add_body_force_impl(mg_state* s, int mode, double momentumLoss, double adjointMomentumLoss, bool stage1,
+                                 double stage1Term);
 int mg_patches_apply(mg_state* s, int mode);
 int mg_patches_collect_viscous(mg_state* s);
 int mg_patches_farfield_adjoint_sources(mg_state* s, MgField* temp1);

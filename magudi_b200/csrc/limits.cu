@@ -175,7 +175,90 @@ __global__ void k_rk3(Rk3Args a) {
 
 inline unsigned nblocks(size_t n) { return (unsigned)((n + 255) / 256); }
 
+// integrands of computeRegionIntegral / computeAdjointXmomentum (src/RegionImpl.f90:605-730): out = the quantity, the
+// norm-weighted sum is the grid inner product with 1
+__global__ void k_bf_integrand(const double* Q, size_t csQ, const double* W, size_t csW, int nD, int which, size_t N,
+                               double* out, double* one) {
+  const size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  one[p] = 1.0;
+  double f = 1.0;
+  if (which == 1) f = Q[csQ + p];
+  else if (which == 2) f = W[csW + p];
+  else if (which == 3) f = W[(size_t)(nD + 1) * csW + p] * ((1.0 / Q[p]) * Q[csQ + p]);
+  out[p] = f;
+}
+
+struct BfArgs {
+  const double *Q, *W;
+  size_t csQ, csW, cs, N;
+  int nD, mode, stage1;
+  double mL, aL, stage1Term;
+  const int* iblank;
+  double* rhs;
+};
+
+// addBodyForce, pointwise part (src/RegionImpl.f90:787-847)
+__global__ void k_body_force(BfArgs a) {
+  const size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= a.N) return;
+  if (a.iblank && a.iblank[p] == 0) return;          // the RHS of a hole is zeroed afterwards in the reference
+  const double v = 1.0 / a.Q[p];
+  const double ux = v * a.Q[a.csQ + p];
+  const size_t e = (size_t)(a.nD + 1);
+  if (a.mode == MG_FORWARD) {
+    a.rhs[a.cs + p] = a.rhs[a.cs + p] + a.mL;
+    a.rhs[e * a.cs + p] = a.rhs[e * a.cs + p] + a.mL * ux;
+  } else if (a.mode == MG_ADJOINT) {
+    const double temp = a.mL * v * a.W[e * a.csW + p];
+    double r1 = a.rhs[a.cs + p] - temp;
+    a.rhs[p] = a.rhs[p] + temp * ux;
+    if (a.stage1) r1 = r1 - a.stage1Term;
+    a.rhs[a.cs + p] = r1;
+  } else {
+    double temp = (0.0 - ux) * a.W[p] + a.W[a.csW + p];
+    temp = temp * v;
+    a.rhs[a.cs + p] = a.rhs[a.cs + p] + a.aL;
+    a.rhs[e * a.cs + p] = a.rhs[e * a.cs + p] + a.aL * ux + a.mL * temp;
+  }
+}
+
 }  // namespace
+
+// which: 0 volume, 1 integral of rho u, 2 integral of the second adjoint (or perturbation) variable,
+// 3 <w_E, u_x> (computeAdjointXmomentum); local to this rank
+int mg_state_integral_impl(mg_state* s, int which, double* value) {
+  mg_grid* g = s->grid;
+  if (!g->updated) MG_FAIL("region integral: grid metrics have not been computed (mg_grid_update)");
+  const MgField& Q = s->Q[s->cur];
+  const MgField& W = s->W[s->curW];
+  if (which != 0 && !Q.p) MG_FAIL("region integral: conserved variables have not been set");
+  if (which >= 2 && !W.p) MG_FAIL("region integral: adjoint variables have not been set");
+  MG_TRY(mg_halo_wait_pending());
+  MgField& B = g->scratchB;
+  if (B.nComp < 2) MG_FAIL("region integral: scratch field is too small");
+  { k_bf_integrand<<<nblocks(g->N), 256, 0, mg_stream()>>>(Q.p ? Q.comp(0) : nullptr, Q.compStride, W.p ? W.comp(0) : nullptr,
+                                                          W.compStride, s->nD, which, g->N, B.comp(0), B.comp(1)); mg_count_launches(1); }
+  MG_CUDA(cudaGetLastError());
+  return mg_grid_inner_product_dev(g, B.comp(0), B.comp(1), nullptr, B.compStride, 1, value);
+}
+
+int mg_state_add_body_force_impl(mg_state* s, int mode, double momentumLoss, double adjointMomentumLoss, bool stage1,
+                                 double stage1Term) {
+  mg_grid* g = s->grid;
+  BfArgs a;
+  a.Q = s->Q[s->cur].comp(0); a.csQ = s->Q[s->cur].compStride;
+  a.W = s->W[s->curW].p ? s->W[s->curW].comp(0) : nullptr; a.csW = s->W[s->curW].compStride;
+  if (mode != MG_FORWARD && !a.W) MG_FAIL("body force: adjoint variables have not been set");
+  a.cs = s->rhs.compStride; a.N = g->N;
+  a.nD = s->nD; a.mode = mode; a.stage1 = stage1 ? 1 : 0;
+  a.mL = momentumLoss; a.aL = adjointMomentumLoss; a.stage1Term = stage1Term;
+  a.iblank = g->iblank;
+  a.rhs = s->rhs.comp(0);
+  { k_body_force<<<nblocks(g->N), 256, 0, mg_stream()>>>(a); mg_count_launches(1); }
+  MG_CUDA(cudaGetLastError());
+  return 0;
+}
 
 // Local extrema of density (which = 0) or temperature (1) of the conserved variables, with the 1-based GLOBAL
 // (i, j, k) of the first point attaining each; the caller combines ranks (MPI_Allgather + minloc in the reference).

@@ -1313,6 +1313,7 @@ int mg_fused_rhs_supported(const mg_state* s, int mode) {
 int mg_fused_supported(const mg_state* s, int mode) {
   if (!s->patches.empty() || !s->acousticSources.empty()) return 0;
   if (mode == MG_ADJOINT && s->limits.soft) return 0;        // the solution-limit forcing joins after the sweeps
+  if (s->bodyForce) return 0;                                // the region's body force joins after the sweeps
   return mg_fused_rhs_supported(s, mode);
 }
 

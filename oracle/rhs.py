@@ -247,10 +247,11 @@ def addAcousticSources(mode, opt, grid, state):
         state.rightHandSide[:, nD + 1] += a * np.exp(-gaussianFactor * r2)
 
 
-def computeRhs(mode, opt, grid, state, patches=(), timestep=0, stage=1, softLimits=None):
+def computeRhs(mode, opt, grid, state, patches=(), timestep=0, stage=1, softLimits=None, bodyForce=None):
     """``computeRhs`` for one grid (``src/RegionImpl.f90:1877-2027``).  ``softLimits`` =
     ``(densityRange, temperatureRange, penaltyFactor)`` switches the soft solution-limit adjoint forcing on
-    (``:2002-2005``)."""
+    (``:2002-2005``); ``bodyForce`` (an ``oracle.bodyforce.BodyForce``) the x-momentum conserving body force
+    (``:2012-2014``)."""
     if mode == FORWARD:
         computeRhsForward(opt, grid, state, patches)
     elif mode == ADJOINT:
@@ -265,6 +266,9 @@ def computeRhs(mode, opt, grid, state, patches=(), timestep=0, stage=1, softLimi
         from . import limits
         limits.addSolutionLimitPenaltyAdjointForcing(opt, [grid], [state], *softLimits)
     addAcousticSources(mode, opt, grid, state)
+    if bodyForce is not None:
+        from . import bodyforce
+        bodyforce.addBodyForce(bodyForce, mode, stage, [grid], [state])
     state.rightHandSide[grid.iblank == 0, :] = 0.0
 
 
