@@ -88,6 +88,7 @@ typedef struct mg_options {
   double dissipationAmount;
   int useTargetState;
   int useContinuousAdjoint;
+  int steadyStateSimulation;   /* steady_state_simulation: the adjoint forcing factors are 1 (src/CostTargetPatchImpl.f90:108) */
 } mg_options;
 
 /* ------------------------------------------------------------------ library */

@@ -32,6 +32,7 @@ class Options(C.Structure):
         ("dissipationAmount", C.c_double),
         ("useTargetState", C.c_int),
         ("useContinuousAdjoint", C.c_int),
+        ("steadyStateSimulation", C.c_int),
     ]
 
 

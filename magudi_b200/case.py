@@ -106,6 +106,7 @@ def solver_options(deck: InputDeck):
         dissipationAmount=deck.require("dissipation_amount", 0.0) if diss else 0.0,
         useTargetState=deck.get("use_target_state", True),
         useContinuousAdjoint=deck.get("use_continuous_adjoint", False),
+        steadyStateSimulation=deck.get("steady_state_simulation", False),
         discretizationType=deck.get("defaults/discretization_scheme", "SBP 4-8"))
 
 

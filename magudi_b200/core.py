@@ -153,6 +153,7 @@ class SolverOptions:
         self.dissipationAmount = 0.0
         self.useTargetState = True
         self.useContinuousAdjoint = False
+        self.steadyStateSimulation = False
         self.discretizationType = "SBP 4-8"
         for k, v in kw.items():
             if not hasattr(self, k):
@@ -163,7 +164,7 @@ class SolverOptions:
         return Options(self.ratioOfSpecificHeats, int(self.viscosityOn), self.reynoldsNumberInverse,
                        self.prandtlNumberInverse, self.powerLawExponent, self.bulkViscosityRatio,
                        int(self.dissipationOn), int(self.compositeDissipation), self.dissipationAmount,
-                       int(self.useTargetState), int(self.useContinuousAdjoint))
+                       int(self.useTargetState), int(self.useContinuousAdjoint), int(self.steadyStateSimulation))
 
 
 class Grid:

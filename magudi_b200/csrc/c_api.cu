@@ -507,6 +507,7 @@ int mg_state_create(mg_grid* g, const mg_options* o, mg_state** out) {
   t.dissipationAmount = o->dissipationAmount;
   t.useTargetState = o->useTargetState;
   t.useContinuousAdjoint = o->useContinuousAdjoint;
+  t.steadyStateSimulation = o->steadyStateSimulation;
   if (!(t.ratioOfSpecificHeats > 1.0)) MG_FAIL("mg_state_create: ratio of specific heats must exceed 1");
   if (t.viscosityOn && !(t.reynoldsNumberInverse > 0.0)) MG_FAIL("mg_state_create: viscous terms need a positive Reynolds number");
   if (t.dissipationOn != g->dissipationOn || (t.dissipationOn && t.compositeDissipation != g->compositeDissipation))

@@ -345,7 +345,7 @@ int mg_state_limit_forcing_impl(mg_state* s, const double densityRange[2], const
   a.gamma = s->opt.ratioOfSpecificHeats;
   a.rhoMin = densityRange[0]; a.rhoMax = densityRange[1];
   a.TMin = temperatureRange[0]; a.TMax = temperatureRange[1];
-  a.factor = (s->opt.useContinuousAdjoint ? 1.0 : s->adjointForcingFactor) * penaltyFactor;
+  a.factor = ((s->opt.useContinuousAdjoint || s->opt.steadyStateSimulation) ? 1.0 : s->adjointForcingFactor) * penaltyFactor;
   a.iblank = g->iblank;
   a.rhs = s->rhs.comp(0);
   { k_limit_forcing<<<nblocks(g->N), 256, 0, mg_stream()>>>(a); mg_count_launches(1); }

@@ -74,6 +74,7 @@ struct mg_options_t {
   double dissipationAmount = 0.0;
   int useTargetState = 1;
   int useContinuousAdjoint = 0;
+  int steadyStateSimulation = 0;
 };
 
 // A device field: nComp components, each (nz + 2*gk) planes of nx*ny doubles.

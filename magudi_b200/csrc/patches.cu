@@ -859,7 +859,7 @@ int mg_patches_apply(mg_state* s, int mode) {
         a.rhs = s->rhs.comp(0);
         a.cs = s->rhs.compStride;
         a.nComp = s->nU;
-        a.factor = s->opt.useContinuousAdjoint ? 1.0 : s->adjointForcingFactor;
+        a.factor = (s->opt.useContinuousAdjoint || s->opt.steadyStateSimulation) ? 1.0 : s->adjointForcingFactor;
         { k_patch_add<<<nblocks(p->nPatchPoints), 128, 0, st>>>(a); mg_count_launches(1); }
         break;
       }

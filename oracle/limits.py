@@ -84,7 +84,7 @@ def addSolutionLimitPenaltyAdjointForcing(opt, grids, states, densityRange, temp
         TIn = isVariableWithinRange(g, T, *temperatureRange)[0]
         if rhoIn and TIn:
             continue
-        factor = (1.0 if opt.useContinuousAdjoint else s.adjointForcingFactor) * penaltyFactor
+        factor = (1.0 if (opt.useContinuousAdjoint or opt.steadyStateSimulation) else s.adjointForcingFactor) * penaltyFactor
         fRho, dfRho = _f_df(rho, *densityRange) if not rhoIn else (np.zeros_like(rho), np.zeros_like(rho))
         fT, dfT = _f_df(T, *temperatureRange) if not TIn else (np.zeros_like(T), np.zeros_like(T))
         hole = g.iblank == 0

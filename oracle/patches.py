@@ -349,7 +349,7 @@ class CostTargetPatch(Patch):
         """``addAdjointForcing`` (``src/CostTargetPatchImpl.f90:72-136``)."""
         if mode == FORWARD:
             return
-        f = 1.0 if opt.useContinuousAdjoint else state.adjointForcingFactor
+        f = 1.0 if (opt.useContinuousAdjoint or opt.steadyStateSimulation) else state.adjointForcingFactor
         idx = self.gridIndex0[self.active]
         state.rightHandSide[idx] += f * self.adjointForcing[self.active]
 

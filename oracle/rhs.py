@@ -37,6 +37,7 @@ class SolverOptions:
     dissipationAmount: float = 0.0
     useTargetState: bool = True
     useContinuousAdjoint: bool = False
+    steadyStateSimulation: bool = False
     discretizationType: str = "SBP 4-8"
     nUnknowns: int = 0
     # acoustic sources: list of dicts {location, amplitude, frequency, radius, phase}

@@ -63,6 +63,7 @@ def gpu_case_from_oracle(g, opt, s, procDims=(1, 1, 1), procCoords=(0, 0, 0)):
                          bulkViscosityRatio=opt.bulkViscosityRatio, dissipationOn=opt.dissipationOn,
                          compositeDissipation=opt.compositeDissipation, dissipationAmount=opt.dissipationAmount,
                          useTargetState=opt.useTargetState, useContinuousAdjoint=opt.useContinuousAdjoint,
+                         steadyStateSimulation=getattr(opt, "steadyStateSimulation", False),
                          discretizationType=opt.discretizationType)
     st = mb.State(gg, o)
     st.conservedVariables = s.conservedVariables

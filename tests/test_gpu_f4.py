@@ -394,3 +394,45 @@ def test_momentum_actuator_sensitivity_and_gradient(shape, direction):
     G = of.momentumActuatorGradient(g, s, pa, direction)
     got = q.momentumActuatorGradient(direction)
     assert got.shape == G.shape and relerr(got, G) <= 1e-14
+
+
+@pytest.mark.parametrize("steady", [False, True])
+def test_steady_state_forcing_factors(steady):
+    """steady_state_simulation: the COST_TARGET adjoint forcing and the soft-limit adjoint forcing enter with factor 1
+    instead of the RK stage factor (reference src/CostTargetPatchImpl.f90:108-112, src/RegionImpl.f90:1134-1140)."""
+    import magudi_b200 as mb
+    from oracle import patches as op
+    from oracle import rhs as orhs
+    g, opt, s, rng = oracle_case((26, 24), (False, False), True, True, False, "SBP 2-4", seed=41)
+    opt.steadyStateSimulation = steady
+    s.update(g, opt)
+    rho, T = s.conservedVariables[:, 0], s.temperature[:, 0]
+    dR = (float(np.quantile(rho, 0.2)), float(np.quantile(rho, 0.85)))
+    tR = (float(np.quantile(T, 0.3)), float(np.quantile(T, 0.7)))
+    ext = [6, 15, 5, 18, 1, 1]
+    po = op.CostTargetPatch("targetRegion", g, 0, ext, opt)
+    po.adjointForcing = rng.standard_normal(po.adjointForcing.shape)
+    gg, o, st = gpu_case_from_oracle(g, opt, s)
+    pg = st.addPatch("COST_TARGET", "targetRegion", 0, ext)
+    pg.setArray("adjointForcing", po.adjointForcing)
+    region = _region(st)
+    region.setSolutionLimits(dR, tR, soft=True, penaltyFactor=0.6)
+    results = []
+    for fused in (True, False):
+        region.setFused(fused)
+        st.adjointVariables = s.adjointVariables
+        W0 = s.adjointVariables.copy()
+        integ = mb.RK4Integrator(region)
+        rk = orhs.RK4Integrator(s)
+        f = lambda m, ts, sg: orhs.computeRhs(orhs.ADJOINT, opt, g, s, [po], softLimits=(dR, tR, 0.6))
+        rk.substepAdjoint(f, s, 1.0, 0.01, 0, 4)       # stage 4: forcing factor 2 unless steady
+        integ.substepAdjoint(1.0, 0.01, 0, 4)
+        assert relerr(st.adjointVariables, s.adjointVariables) <= 1e-12
+        results.append(s.adjointVariables.copy())
+        s.adjointVariables[:] = W0
+    # the flag changes the answer (the stage-4 factor differs from 1)
+    opt.steadyStateSimulation = not steady
+    rk = orhs.RK4Integrator(s)
+    rk.substepAdjoint(lambda m, ts, sg: orhs.computeRhs(orhs.ADJOINT, opt, g, s, [po], softLimits=(dR, tR, 0.6)),
+                      s, 1.0, 0.01, 0, 4)
+    assert np.max(np.abs(s.adjointVariables - results[0])) > 1e-6
