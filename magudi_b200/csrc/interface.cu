@@ -102,17 +102,49 @@ __device__ void roe_average_dual(const double* QL, const double* QR, double gamm
   roe[NU - 1] = (h + (0.5 * (gamma - 1.0)) * (msq / roe[0])) / gamma;
 }
 
+// computeRoeAverage with deltaConservedVariablesL = diag(dQL), deltaConservedVariablesR = diag(dQR) (the LINEARIZED
+// branch of addBlockInterfacePenalty, reference src/BlockInterfacePatchImpl.f90:470-481): summed over its columns the
+// reference's deltaRoeAverage is the directional derivative of the Roe state along (dQL, dQR) = roe[c].d[0]
+template <int ND>
+__device__ void roe_average_directional(const double* QL, const double* QR, const double* dQL, const double* dQR,
+                                        double gamma, Dual<1>* roe) {
+  constexpr int NU = ND + 2;
+  typedef Dual<1> D;
+  D ql[NU], qr[NU];
+#pragma unroll
+  for (int c = 0; c < NU; ++c) {
+    ql[c].v = QL[c]; ql[c].d[0] = dQL[c];
+    qr[c].v = QR[c]; qr[c].d[0] = dQR[c];
+  }
+  const D sL = dsqrt(ql[0]), sR = dsqrt(qr[0]);
+  const D vL = 1.0 / ql[0], vR = 1.0 / qr[0];
+  D mL = ql[1] * ql[1], mR = qr[1] * qr[1];
+#pragma unroll
+  for (int i = 1; i < ND; ++i) { mL = mL + ql[i + 1] * ql[i + 1]; mR = mR + qr[i + 1] * qr[i + 1]; }
+  const D hL = gamma * ql[NU - 1] - (0.5 * (gamma - 1.0)) * (vL * mL);
+  const D hR = gamma * qr[NU - 1] - (0.5 * (gamma - 1.0)) * (vR * mR);
+  const D den = sL + sR;
+  roe[0] = sL * sR;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) roe[i + 1] = (sR * ql[i + 1] + sL * qr[i + 1]) / den;
+  D h = (sR * hL + sL * hR) / den;
+  D msq = roe[1] * roe[1];
+#pragma unroll
+  for (int i = 1; i < ND; ++i) msq = msq + roe[i + 1] * roe[i + 1];
+  roe[NU - 1] = (h + (0.5 * (gamma - 1.0)) * (msq / roe[0])) / gamma;
+}
+
 // computeIncomingJacobianOfInviscidFlux{1,2,3}D with its variation (reference :1446-2342): the operations of
 // cns_device.cuh:incoming_jacobian on dual numbers.
-template <int ND>
-__device__ void incoming_jacobian_dual(const Dual<ND + 2>* Q, const double* m, double gamma, int incomingDirection,
-                                       Dual<ND + 2> (*A)[ND + 2]) {
+template <int ND, int M>
+__device__ void incoming_jacobian_dual(const Dual<M>* Q, const double* m, double gamma, int incomingDirection,
+                                       Dual<M> (*A)[ND + 2]) {
   constexpr int NU = ND + 2;
-  typedef Dual<NU> D;
+  typedef Dual<M> D;
   const D rho = Q[0];
   const D v = 1.0 / rho;
   D u[ND];
-  D usq = dconst<NU>(0.0);
+  D usq = dconst<M>(0.0);
 #pragma unroll
   for (int i = 0; i < ND; ++i) {
     u[i] = v * Q[i + 1];
@@ -124,7 +156,7 @@ __device__ void incoming_jacobian_dual(const Dual<ND + 2>* Q, const double* m, d
   for (int i = 0; i < ND; ++i) arc = (i == 0) ? m[0] * m[0] : arc + m[i] * m[i];
   arc = (ND == 1) ? fabs(m[0]) : sqrt(arc);
   double n[ND];
-  D uh = dconst<NU>(0.0);
+  D uh = dconst<M>(0.0);
 #pragma unroll
   for (int i = 0; i < ND; ++i) {
     n[i] = m[i] / arc;
@@ -141,10 +173,10 @@ __device__ void incoming_jacobian_dual(const Dual<ND + 2>* Q, const double* m, d
 #pragma unroll
   for (int i = 0; i < NU; ++i) {
     ev[i] = arc * ev[i];
-    if (incomingDirection * ev[i].v < 0.0) ev[i] = dconst<NU>(0.0);
+    if (incomingDirection * ev[i].v < 0.0) ev[i] = dconst<M>(0.0);
   }
   D R[NU][NU], L[NU][NU];
-  const D zero = dconst<NU>(0.0), one = dconst<NU>(1.0);
+  const D zero = dconst<M>(0.0), one = dconst<M>(1.0);
 #pragma unroll
   for (int i = 0; i < NU; ++i)
 #pragma unroll
@@ -183,11 +215,11 @@ __device__ void incoming_jacobian_dual(const Dual<ND + 2>* Q, const double* m, d
   } else {
     const double n1 = n[0], n2 = n[1], n3 = n[2];
     const D u1 = u[0], u2 = u[1], u3 = u[2];
-    R[0][0] = dconst<NU>(n1); R[1][0] = n1 * u1; R[2][0] = n1 * u2 + rho * n3; R[3][0] = n1 * u3 - rho * n2;
+    R[0][0] = dconst<M>(n1); R[1][0] = n1 * u1; R[2][0] = n1 * u2 + rho * n3; R[3][0] = n1 * u3 - rho * n2;
     R[4][0] = rho * (n3 * u2 - n2 * u3) + (phi2 / g1) * n1;
-    R[0][1] = dconst<NU>(n2); R[1][1] = n2 * u1 - rho * n3; R[2][1] = n2 * u2; R[3][1] = n2 * u3 + rho * n1;
+    R[0][1] = dconst<M>(n2); R[1][1] = n2 * u1 - rho * n3; R[2][1] = n2 * u2; R[3][1] = n2 * u3 + rho * n1;
     R[4][1] = rho * (n1 * u3 - n3 * u1) + (phi2 / g1) * n2;
-    R[0][2] = dconst<NU>(n3); R[1][2] = n3 * u1 + rho * n2; R[2][2] = n3 * u2 - rho * n1; R[3][2] = n3 * u3;
+    R[0][2] = dconst<M>(n3); R[1][2] = n3 * u1 + rho * n2; R[2][2] = n3 * u2 - rho * n1; R[3][2] = n3 * u3;
     R[4][2] = rho * (n2 * u1 - n1 * u2) + (phi2 / g1) * n3;
     R[0][3] = one; R[1][3] = u1 + n1 * c; R[2][3] = u2 + n2 * c; R[3][3] = u3 + n3 * c; R[4][3] = H + c * uh;
     R[0][4] = one; R[1][4] = u1 - n1 * c; R[2][4] = u2 - n2 * c; R[3][4] = u3 - n3 * c; R[4][4] = H - c * uh;
@@ -297,6 +329,27 @@ __global__ void __launch_bounds__(128) k_interface(IfArgs a) {
 #pragma unroll
       for (int c = 1; c < NU; ++c) r[c] += jac * (vL * a.FvL[(size_t)c * n + q] + vR * a.FvR[(size_t)c * n + q]);
     }
+  } else if (a.mode == MG_LINEARIZED) {
+    // :470-516: - sigmaI J [ A+ (dQL - dQR) + dA+ (QL - QR) ] + J (sigmaVL FvL + sigmaVR FvR), the perturbations
+    // travel in the adjoint-variable slots and Fv is the linearized viscous flux along the normal
+    double dL[NU], dR[NU], mm[ND];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) { dL[c] = a.WL[(size_t)c * n + q]; dR[c] = a.WR[(size_t)c * n + q]; }
+#pragma unroll
+    for (int i = 0; i < ND; ++i) mm[i] = a.m[(size_t)(i + ND * a.dir) * a.cs + p];
+    Dual<1> roe1[NU], A1[NU][NU];
+    roe_average_directional<ND>(QL, QR, dL, dR, a.gamma, roe1);
+    incoming_jacobian_dual<ND, 1>(roe1, mm, a.gamma, a.normal, A1);
+    for (int i = 0; i < NU; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < NU; ++j) acc += A1[i][j].v * (dL[j] - dR[j]) + A1[i][j].d[0] * (QL[j] - QR[j]);
+      r[i] = -a.sigmaI * jac * acc;
+    }
+    if (a.viscous) {
+      const double vL = copysign(a.sigmaV, (double)a.normalL), vR = copysign(a.sigmaV, (double)a.normalR);
+#pragma unroll
+      for (int c = 1; c < NU; ++c) r[c] += jac * (vL * a.FvL[(size_t)c * n + q] + vR * a.FvR[(size_t)c * n + q]);
+    }
   } else {
     double dq[NU];
 #pragma unroll
@@ -313,7 +366,7 @@ __global__ void __launch_bounds__(128) k_interface(IfArgs a) {
 #pragma unroll
       for (int c = 0; c < NU; ++c) w[c] = wp[(size_t)c * n + q];
       D A[NU][NU];
-      incoming_jacobian_dual<ND>(roe, mm, a.gamma, inc, A);
+      incoming_jacobian_dual<ND, NU>(roe, mm, a.gamma, inc, A);
       // + sI [ A^T w + sum_ij dA_ij/dQL_l dq_j w_i ]
       for (int l = 0; l < NU; ++l) {
         double acc = 0.0;
@@ -516,7 +569,7 @@ int mg_interface_link_remote(mg_patch* p, const int reorder[3], double partnerIn
   p->normalR = partnerNormalDirection;
   p->partner = nullptr;
   p->metricsReady = false;
-  if (!p->remote) MG_TRY(mg_p2p_create_pair((size_t)std::max(1, p->nPatchPoints) * 2 * p->state->nU, &p->remote));
+  if (!p->remote) MG_TRY(mg_p2p_create_pair((size_t)std::max(1, p->nPatchPoints) * 3 * p->state->nU, &p->remote));
   *link = p->remote;
   return 0;
 }
@@ -581,6 +634,18 @@ int mg_interfaces_exchange(const std::vector<mg_state*>& states, int mode) {
     } else {
       const MgField& W = s->W[s->curW];
       MG_TRY(collect_to(p, W.comp(0), W.compStride, s->nU, "adjointVariablesL"));
+      if (mode == MG_LINEARIZED && s->opt.viscosityOn) {
+        // computeRhsLinearized collected the linearized viscous fluxes (nU x nD); the interface keeps the ones along
+        // its normal direction (reference src/RhsHelperImpl.f90:803-806)
+        double* Fc = arr(p, "viscousFluxes");
+        if (!Fc) MG_FAIL("block interface: linearized viscous fluxes have not been collected");
+        double* out = nullptr;
+        MG_TRY(mg_patch_alloc_array(p, "viscousFluxesL", s->nU, &out));
+        const int dir = std::abs(p->normalDirection) - 1;
+        if (p->nPatchPoints)
+          MG_CUDA(cudaMemcpyAsync(out, Fc + (size_t)s->nU * dir * p->nPatchPoints,
+                                  (size_t)s->nU * p->nPatchPoints * sizeof(double), cudaMemcpyDeviceToDevice, mg_stream()));
+      }
     }
   }
   // what travels per mode (reference collectInterfaceData, src/BlockInterfacePatchImpl.f90:592-700)
@@ -588,18 +653,22 @@ int mg_interfaces_exchange(const std::vector<mg_state*>& states, int mode) {
   static const char* const recvF[2] = {"conservedVariablesR", "viscousFluxesR"};
   static const char* const sendA[2] = {"conservedVariablesL", "adjointVariablesL"};
   static const char* const recvA[2] = {"conservedVariablesR", "adjointVariablesR"};
+  static const char* const sendL[3] = {"conservedVariablesL", "adjointVariablesL", "viscousFluxesL"};
+  static const char* const recvL[3] = {"conservedVariablesR", "adjointVariablesR", "viscousFluxesR"};
   for (mg_patch* p : ifs) {
     if (!p->remote) continue;
     mg_state* s = p->state;
-    const int nc[2] = {s->nU, s->nU};
+    const int nc[3] = {s->nU, s->nU, s->nU};
     if (mode == MG_FORWARD) MG_TRY(send_remote(p, sendF, nc, s->opt.viscosityOn ? 2 : 1));
+    else if (mode == MG_LINEARIZED) MG_TRY(send_remote(p, sendL, nc, s->opt.viscosityOn ? 3 : 2));
     else MG_TRY(send_remote(p, sendA, nc, 2));
   }
   for (mg_patch* p : ifs) {
     mg_state* s = p->state;
     if (p->remote) {
-      const int nc[2] = {s->nU, s->nU};
+      const int nc[3] = {s->nU, s->nU, s->nU};
       if (mode == MG_FORWARD) MG_TRY(receive_remote(p, recvF, nc, s->opt.viscosityOn ? 2 : 1));
+      else if (mode == MG_LINEARIZED) MG_TRY(receive_remote(p, recvL, nc, s->opt.viscosityOn ? 3 : 2));
       else MG_TRY(receive_remote(p, recvA, nc, 2));
       continue;
     }
@@ -608,6 +677,7 @@ int mg_interfaces_exchange(const std::vector<mg_state*>& states, int mode) {
       if (s->opt.viscosityOn) MG_TRY(receive(p, "viscousFluxesL", "viscousFluxesR", s->nU));
     } else {
       MG_TRY(receive(p, "adjointVariablesL", "adjointVariablesR", s->nU));
+      if (mode == MG_LINEARIZED && s->opt.viscosityOn) MG_TRY(receive(p, "viscousFluxesL", "viscousFluxesR", s->nU));
     }
   }
   MG_CUDA(cudaGetLastError());
@@ -631,8 +701,8 @@ int mg_interface_apply(mg_state* s, mg_patch* p, int mode) {
   a.FvR = arr(p, "viscousFluxesR");
   a.mL = arr(p, "metricsL");
   a.mR = arr(p, "metricsR");
-  if (mode == MG_ADJOINT && (!a.WL || !a.WR)) MG_FAIL("block interface: adjoint interface data have not been exchanged");
-  if (mode == MG_FORWARD && s->opt.viscosityOn && (!a.FvL || !a.FvR))
+  if (mode != MG_FORWARD && (!a.WL || !a.WR)) MG_FAIL("block interface: adjoint interface data have not been exchanged");
+  if (mode != MG_ADJOINT && s->opt.viscosityOn && (!a.FvL || !a.FvR))
     MG_FAIL("block interface: viscous interface fluxes have not been exchanged");
   a.m = g->metrics.comp(0);
   a.jac = g->jacobian.comp(0);

@@ -1110,7 +1110,6 @@ int mg_state_compute_rhs_impl(mg_state* s, int mode) {
     return mg_state_rhs_post(s, mode, true);
   }
   if (mg_state_has_interfaces(s)) {
-    if (mode == MG_LINEARIZED) MG_FAIL("computeRhs: the LINEARIZED mode of block-interface patches is not implemented");
     MG_FAIL("computeRhs: a state with block-interface patches must be evaluated through its region (mg_region_compute_rhs)");
   }
   MG_TRY(mg_state_rhs_pre(s, mode));

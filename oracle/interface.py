@@ -27,7 +27,7 @@ from . import cns
 from . import rhs as orhs
 from .patches import Patch, _penalty_amount
 
-FORWARD, ADJOINT = orhs.FORWARD, orhs.ADJOINT
+FORWARD, ADJOINT, LINEARIZED = orhs.FORWARD, orhs.ADJOINT, orhs.LINEARIZED
 
 
 # ----------------------------------------------------------------------------------------- dual numbers
@@ -276,6 +276,10 @@ class BlockInterfacePatch(Patch):
     def collectViscousFluxes(self, fluxes2):
         self.cartesianViscousFluxesL = np.array(fluxes2[self.gridIndex0], copy=True)
 
+    # computeRhsLinearized hands over the linearized viscous flux along the patch normal (src/RhsHelperImpl.f90:803-806)
+    def collectLinearizedViscousFluxes(self, fluxes2):
+        self.viscousFluxesL = np.array(fluxes2[self.gridIndex0, :, abs(self.normalDirection) - 1], copy=True)
+
     def collectInterfaceData(self, mode, opt, grid, state):
         """Returns the data to be sent, (nPatchPoints, nExchangedVariables) in this patch's ordering."""
         nD, nU = grid.nDimensions, grid.nDimensions + 2
@@ -302,6 +306,8 @@ class BlockInterfacePatch(Patch):
                 return np.concatenate([self.conservedVariablesL, self.viscousFluxesL], axis=1)
             return self.conservedVariablesL.copy()
         self.adjointVariablesL = self.collect(state.adjointVariables)
+        if mode == LINEARIZED and opt.viscosityOn:          # :667-689, :721-724: the fluxes collected by the RHS
+            return np.concatenate([self.conservedVariablesL, self.adjointVariablesL, self.viscousFluxesL], axis=1)
         return np.concatenate([self.conservedVariablesL, self.adjointVariablesL], axis=1)
 
     def disperseInterfaceData(self, mode, opt, received):
@@ -319,6 +325,8 @@ class BlockInterfacePatch(Patch):
                 self.viscousFluxesR = received[:, nU:2 * nU].copy()
         else:
             self.adjointVariablesR = received[:, nU:2 * nU].copy()
+            if mode == LINEARIZED and opt.viscosityOn:
+                self.viscousFluxesR = received[:, 2 * nU:3 * nU].copy()
 
     def reshapeReceivedData(self, data):
         """``reshapeReceivedData`` (``:812-929``): the partner's patch-ordered buffer -> this patch's ordering."""
@@ -352,6 +360,23 @@ class BlockInterfacePatch(Patch):
             m = grid.metrics[idx, nD * (d - 1):nD * d]
             A = computeIncomingJacobian(nD, roe, m, g, self.normalDirection)
             pen = -self.inviscidPenaltyAmount * J[:, None] * np.einsum("pij,pj->pi", A, QL - QR)
+            if opt.viscosityOn:
+                vL = np.copysign(self.viscousPenaltyAmount, float(self.normalDirectionL))
+                vR = np.copysign(self.viscousPenaltyAmount, float(self.normalDirectionR))
+                pen[:, 1:] += J[:, None] * (vL * self.viscousFluxesL[:, 1:] + vR * self.viscousFluxesR[:, 1:])
+            state.rightHandSide[idx[act]] += pen[act]
+            return
+        if mode == LINEARIZED:
+            # :470-516: the perturbations travel in adjointVariablesL / R; deltaConservedVariablesL / R = diag(dQ),
+            # so that sum(deltaIncomingJacobianOfInviscidFlux, dim=3) is the directional derivative of A+
+            dQL, dQR = self.adjointVariablesL, self.adjointVariablesR
+            roe, dRoeL = computeRoeAverage(nD, QL, QR, g, withDelta=True)
+            dRoeR = computeRoeAverage(nD, QR, QL, g, withDelta=True)[1]      # the R branch mirrors the L branch (:289-343)
+            dRoe = dRoeL * dQL[:, None, :] + dRoeR * dQR[:, None, :]
+            m = grid.metrics[idx, nD * (d - 1):nD * d]
+            A, dA = computeIncomingJacobianWithVariation(nD, roe, dRoe, m, g, self.normalDirection)
+            pen = -self.inviscidPenaltyAmount * J[:, None] * np.einsum("pij,pj->pi", A, dQL - dQR)
+            pen -= self.inviscidPenaltyAmount * J[:, None] * np.einsum("pij,pj->pi", dA.sum(axis=3), QL - QR)
             if opt.viscosityOn:
                 vL = np.copysign(self.viscousPenaltyAmount, float(self.normalDirectionL))
                 vR = np.copysign(self.viscousPenaltyAmount, float(self.normalDirectionR))
@@ -448,8 +473,10 @@ def computeRhsRegion(mode, opt, grids, states, patches):
         mine = [p for p in patches if p.gridIndex == g.index]
         if mode == FORWARD:
             orhs.computeRhsForward(opt, g, s, mine)
-        else:
+        elif mode == ADJOINT:
             orhs.computeRhsAdjoint(opt, g, s, mine)
+        else:
+            orhs.computeRhsLinearized(opt, g, s, mine)
     exchangeInterfaceData(mode, opt, grids, states, patches)
     if mode == ADJOINT and opt.viscosityOn:
         for g, s in zip(grids, states):

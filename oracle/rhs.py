@@ -220,7 +220,11 @@ def computeRhsLinearized(opt, grid, state, patches=()):
                 B2 = cns.computeSecondPartialViscousJacobian(nD, u, mu, lam, kap, grid.jacobian[:, 0], m1, m2)
                 f2[:, 1:, i] += np.einsum("pij,pj->pi", B2, temp[:, :, j])
         for patch in patches:
-            if hasattr(patch, "collectViscousFluxes") and patch.gridIndex == grid.index:
+            if patch.gridIndex != grid.index:
+                continue
+            if hasattr(patch, "collectLinearizedViscousFluxes"):       # block interfaces: the normal component (:803-806)
+                patch.collectLinearizedViscousFluxes(f2)
+            elif hasattr(patch, "collectViscousFluxes"):
                 patch.collectViscousFluxes(f2)
     f1 = f1 - f2
     total = None

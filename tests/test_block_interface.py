@@ -131,6 +131,39 @@ def test_oracle_two_block_adjoint_relation(nd, visc, scheme):
     check_adjoint_relation(lambda Q: run(oi.FORWARD, Q), lambda Q, w: run(oi.ADJOINT, Q, w), inner, Q0, W, dQ)
 
 
+@pytest.mark.parametrize("nd,visc,scheme", [(2, False, "SBP 2-4"), (2, True, "SBP 2-4"), (2, True, "SBP 3-6"),
+                                            (3, True, "SBP 2-4")])
+def test_oracle_two_block_linearized_relation(nd, visc, scheme):
+    """test/linearized_relation/SAT_block_interface_linearized.f90 restated on the full two-block RHS: <w, L dQ> against
+    finite differences of R, and the duality <w, L dQ> = -<R^dagger w, dQ> with the discrete adjoint (the interface
+    adjoint is the exact transpose)."""
+    from oracle import interface as oi
+    from test_linearized_relation import check_linearized_relation
+    n1, n2 = ((18, 16), (15, 16)) if scheme == "SBP 2-4" else ((26, 20), (25, 20))
+    opt, grids, states, patches, rng = two_blocks(nd, visc, True, scheme, n1, n2)
+    sizes = [g.nGridPoints for g in grids]
+    Q0 = np.concatenate([s.conservedVariables for s in states])
+    W = rng.random(Q0.shape)
+    dQ = delta_conserved(Q0, rng, opt.ratioOfSpecificHeats)
+    split = lambda a: np.split(a, [sizes[0]])
+
+    def run(mode, Q, w=None):
+        for s, g, q in zip(states, grids, split(Q)):
+            s.conservedVariables[:, :] = q
+            s.update(g, opt)
+        if w is not None:
+            for s, ww in zip(states, split(w)):
+                s.adjointVariables[:, :] = ww
+        oi.computeRhsRegion(mode, opt, grids, states, patches)
+        return np.concatenate([s.rightHandSide for s in states])
+
+    inner = lambda f, g_: sum(gr.computeInnerProduct(a, b) for gr, a, b in zip(grids, split(f), split(g_)))
+    check_linearized_relation(lambda Q: run(oi.FORWARD, Q), lambda Q, dq: run(oi.LINEARIZED, Q, dq), inner, Q0, W, dQ)
+    a = inner(W, run(oi.LINEARIZED, Q0, dQ))
+    b = inner(run(oi.ADJOINT, Q0, W), dQ)
+    assert abs(a + b) <= 1e-10 * max(abs(a), 1.0)
+
+
 def test_index_reordering_round_trip():
     """reshapeReceivedData with every supported reordering.  Sign-only reorderings reverse the stated axis; for every
     reordering (incl. the transposing ones) what B sends arrives at A and, sent back through the inverted reordering

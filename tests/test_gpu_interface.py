@@ -2,8 +2,8 @@
 (oracle/interface.py; parity unpinned against the compiled reference -- the oracle itself is pinned by the
 properties in tests/test_block_interface.py).
 
-* two blocks joined along direction 1 (the fixture of test/adjoint_relation/SAT_block_interface.f90): forward and
-  adjoint region RHS <= 1e-12, inviscid / viscous, 2-D / 3-D, SBP 2-4 / 3-6;
+* two blocks joined along direction 1 (the fixture of test/adjoint_relation/SAT_block_interface.f90): forward,
+  adjoint and linearized region RHS <= 1e-12, inviscid / viscous, 2-D / 3-D, SBP 2-4 / 3-6;
 * three blocks whose interfaces use the index reorderings of reshapeReceivedData
   (src/BlockInterfacePatchImpl.f90:812-929), incl. a transposing one;
 * the adjoint relation of the two-block discrete adjoint on the CUDA path;
@@ -43,7 +43,8 @@ def gpu_region(opt, grids, states, patches, links):
 def compare_region_rhs(opt, grids, states, patches, region, gstates, tol=1e-12):
     import magudi_b200 as mb
     from oracle import interface as oi
-    for mode, gmode in ((oi.FORWARD, mb.FORWARD), (oi.ADJOINT, mb.ADJOINT)):
+    # LINEARIZED: the perturbation travels in the adjoint-variable slots (src/BlockInterfacePatchImpl.f90:470-516)
+    for mode, gmode in ((oi.FORWARD, mb.FORWARD), (oi.ADJOINT, mb.ADJOINT), (oi.LINEARIZED, mb.LINEARIZED)):
         for g, s in zip(grids, states):
             s.update(g, opt)
         oi.computeRhsRegion(mode, opt, grids, states, patches)

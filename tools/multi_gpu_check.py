@@ -226,7 +226,7 @@ def run_blocks(world, rank, dev):
         return {}
     region.setFused(False)
     out = {b: [] for b in states}
-    for mode in (mb.FORWARD, mb.ADJOINT):
+    for mode in (mb.FORWARD, mb.ADJOINT, mb.LINEARIZED):   # LINEARIZED ships 3 nU values per interface point
         region.computeRhs(mode)
         for b, st in states.items():
             out[b].append(st.rightHandSide.copy())
