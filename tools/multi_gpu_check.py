@@ -303,7 +303,7 @@ def check_all(world, rank, dev):
                     ei = max(ei, float(np.max(np.abs(v[:, c0:c0 + 5] - one[b][:, c0:c0 + 5])) /
                                        np.max(np.abs(one[b][:, c0:c0 + 5]))))
         print(f"multi_gpu_check: world={world} three blocks with SAT_BLOCK_INTERFACE patches on different GPUs "
-              f"(fwd/adj RHS + RK4): max rel diff vs single GPU = {ei:.3e}", file=sys.stderr)
+              f"(fwd/adj/lin RHS + RK4): max rel diff vs single GPU = {ei:.3e}", file=sys.stderr)
         out = {"solution_limits_max_rel_diff_vs_1gpu": el,
                "block_interfaces_across_gpus_max_rel_diff_vs_1gpu": ei,
                "fused_forward_adjoint_rk4_max_rel_diff_vs_1gpu": e1, "general_path_patches_max_rel_diff_vs_1gpu": e2,
