@@ -255,6 +255,16 @@ def load_case(directory, inp="magudi.inp"):
         for st in c.states:
             st.addAcousticSource(loc, deck.require(k + "amplitude", 0.0), deck.require(k + "frequency", 0.0),
                                  deck.require(k + "radius", 0.0), deck.get(k + "phase", 0.0))
+    # the tail of setupBoundaryConditions (src/RegionImpl.f90:1480-1483): mollifiers are normalised by their quadrature
+    # over the ACTUATOR / COST_TARGET patches (without a mollifier file they are 1, src/SolverImpl.f90:524-550)
+    c.enableController = bool(deck.get("enable_controller", False))
+    c.enableFunctional = bool(deck.get("enable_functional", False))
+    c.controlMollifierNorm = c.targetMollifierNorm = None
+    if c.enableController:
+        c.controlMollifierNorm = c.region.normalizeControlMollifier(
+            deck.get("controller_norm", "L1"), deck.get("time_step_size", 0.0), deck.get("controller_factor", 12.0))
+    if c.enableFunctional:
+        c.targetMollifierNorm = c.region.normalizeTargetMollifier()
     c.region.computeSpongeStrengths()
     c.region.updatePatches()
     # solution limits and filter (src/SimulationFlagsImpl.f90:34-37, src/SolverOptionsImpl.f90)

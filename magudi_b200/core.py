@@ -797,6 +797,47 @@ class Region:
                     return msg
         return None
 
+    def normalizeTargetMollifier(self):
+        """``normalizeTargetMollifier`` (``src/RegionImpl.f90:545-603``, called by ``setupBoundaryConditions`` when the
+        functional is enabled): the target mollifier of every grid is divided by its quadrature over the COST_TARGET
+        patches of the region (summed over ranks).  Returns the norm."""
+        from . import parallel
+        norm = 0.0
+        for s in self.states:
+            m = s.grid.get(G_TARGET_MOLLIFIER)
+            if np.any(m < 0.0):
+                raise RuntimeError(f"Target mollifying support function on grid {s.grid.index} is not non-negative everywhere!")
+            norm += s.computeQuadratureOnPatches("COST_TARGET", m[:, 0])
+        norm = parallel.all_reduce_sum(norm)
+        if not norm > 0.0:
+            raise RuntimeError("Target mollifying support is trivial! Is a cost target patch present?")
+        for s in self.states:
+            s.grid.set(G_TARGET_MOLLIFIER, s.grid.get(G_TARGET_MOLLIFIER) / norm)
+        return norm
+
+    def normalizeControlMollifier(self, controllerNorm="L1", timeStepSize=0.0, controllerFactor=12.0):
+        """``normalizeControlMollifier`` (``src/RegionImpl.f90:459-543``): ``controller_norm = "L1"`` (default) divides
+        the control mollifier by its quadrature over the ACTUATOR patches, ``"L_Inf_with_timestep"`` by
+        ``sqrt(dt / controller_factor) * max(mollifier)``; reduced over ranks.  Returns the norm."""
+        from . import parallel
+        if controllerNorm not in ("L1", "L_Inf_with_timestep"):
+            raise RuntimeError("Solver Option 'controller_norm' is not specified!")
+        norm = 0.0
+        for s in self.states:
+            m = s.grid.get(G_CONTROL_MOLLIFIER)
+            if np.any(m < 0.0):
+                raise RuntimeError(f"Control mollifying support function on grid {s.grid.index} is not non-negative everywhere!")
+            if controllerNorm == "L1":
+                norm += s.computeQuadratureOnPatches("ACTUATOR", m[:, 0])
+            else:
+                norm = max(norm, float(np.sqrt(timeStepSize / controllerFactor)) * float(np.max(m)) if m.size else 0.0)
+        norm = parallel.all_reduce_sum(norm) if controllerNorm == "L1" else parallel.all_reduce_max(norm)
+        if not norm > 0.0:
+            raise RuntimeError("Control mollifying support is trivial! Is an actuator patch present?")
+        for s in self.states:
+            s.grid.set(G_CONTROL_MOLLIFIER, s.grid.get(G_CONTROL_MOLLIFIER) / norm)
+        return norm
+
     def computeSolutionLimitPenalty(self):
         """``computeSolutionLimitPenalty`` (``src/RegionImpl.f90:1001-1092``), summed over ranks."""
         from . import parallel

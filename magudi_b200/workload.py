@@ -70,13 +70,72 @@ C1_SOURCE = dict(location=(-3.0, 0.0, 0.0), amplitude=0.01, frequency=0.47746482
                  radius=2.1213203435596424, phase=0.0)
 
 
+# The target / control mollifiers and patch extents of the example (reference examples/AcousticMonopole/config.py:16-58
+# with the support functions of utils/magudi_utils/src/magudi_utils/plot3dnasa.py:20-24, :779-808; bc.dat of the example).
+# Pure NumPy (no device): pinned against the reference's own script by tests/golden/acoustic_monopole_c1.npz.
+C1_TARGET_BOX = (-1.0, 1.0, -10.0, 10.0)      # x_min, x_max, y_min, y_max
+C1_CONTROL_BOX = (1.0, 5.0, -2.0, 2.0)
+
+
+def _cardinal_cubic_bspline(t):
+    """The cubic B-spline on the knots -2..2 (value 2/3 at 0), zero outside."""
+    a = np.abs(t)
+    return np.where(a < 1.0, 2.0 / 3.0 - a * a + 0.5 * a ** 3, np.where(a <= 2.0, (2.0 - a) ** 3 / 6.0, 0.0))
+
+
+def _snap(x, lo, hi):
+    """The 'strict' mode of the support functions: the window ends move to the nearest grid coordinates."""
+    return x[np.argmin(np.abs(x - lo))], x[np.argmin(np.abs(x - hi))]
+
+
+def c1_cubic_bspline_support(x, lo, hi):
+    if x.max() < lo or x.min() > hi:
+        return np.zeros_like(x)
+    lo, hi = _snap(x, lo, hi)
+    return np.where((x < lo) | (x > hi), 0.0, _cardinal_cubic_bspline(4.0 * (x - lo) / (hi - lo) - 2.0))
+
+
+def c1_tanh_support(x, lo, hi, sigma, xi):
+    if x.max() < lo or x.min() > hi:
+        return np.zeros_like(x)
+    lo, hi = _snap(x, lo, hi)
+    f = lambda t: np.tanh(sigma * (t + 1.0 - 0.5 * xi)) - np.tanh(sigma * (t - 1.0 + 0.5 * xi))
+    return np.where((x < lo) | (x > hi), 0.0, f(2.0 * (x - lo) / (hi - lo) - 1.0) - f(-1.0))
+
+
+def c1_mollifiers(n=201):
+    """(target, control) mollifier fields on the n x n grid, shape (n, n) indexed [i, j], before normalisation."""
+    x = np.linspace(-14.0, 14.0, n)
+    bx0, bx1, by0, by1 = C1_TARGET_BOX
+    target = np.outer(c1_cubic_bspline_support(x, bx0, bx1), c1_tanh_support(x, by0, by1, 40.0, 0.2))
+    bx0, bx1, by0, by1 = C1_CONTROL_BOX
+    control = np.outer(c1_cubic_bspline_support(x, bx0, bx1), c1_cubic_bspline_support(x, by0, by1))
+    return target, control
+
+
+def c1_extents(n=201):
+    """1-based patch extents [iMin, iMax, jMin, jMax, 1, 1] of the COST_TARGET and ACTUATOR patches: the points inside
+    the mollifier boxes (config.py ``find_extents``) widened by one point on every side, which is what the example's
+    bc.dat holds (targetRegion 93 109 29 173, controlRegion 108 137 86 116 at n = 201)."""
+    x = np.linspace(-14.0, 14.0, n)
+
+    def box(b):
+        e = []
+        for lo, hi in ((b[0], b[1]), (b[2], b[3])):
+            inside = np.where((x >= lo) & (x <= hi))[0]
+            e += [max(1, int(inside[0]) + 1 - 1), min(n, int(inside[-1]) + 1 + 1)]
+        return e + [1, 1]
+    return box(C1_TARGET_BOX), box(C1_CONTROL_BOX)
+
+
 def build_c1(n=201, with_control=True):
     """BASELINE configs C1 / C2, ``examples/AcousticMonopole`` of the reference (``config.py``, ``magudi.inp``, ``bc.dat``):
     n x n rectilinear grid on [-14, 14]^2, SBP 3-6, viscous (Re 200, Pr 0.7, constant viscosity), non-composite
     dissipation 1e-4, SAT far-field on the four sides (viscous penalty 0), four sponges 29 points deep (amount 0.2,
     exponent 2), one acoustic monopole, quiescent initial and target state, mean pressure 1/gamma; with
-    ``with_control`` also the cost-target and actuator regions with Gaussian mollifiers that the forward / adjoint
-    drivers (``magudi_b200.solver.Solver``) use.  Host-side setup only; returns (opt, grid, state, region, Q0)."""
+    ``with_control`` also the cost-target and actuator regions of the example with its own mollifiers
+    (``c1_mollifiers``, ``c1_extents``), normalised as ``setupBoundaryConditions`` does (``src/RegionImpl.f90:1480-1483``),
+    that the forward / adjoint drivers (``magudi_b200.solver.Solver``) use.  Returns (opt, grid, state, region, Q0)."""
     opt = core.SolverOptions(ratioOfSpecificHeats=C1_GAMMA, viscosityOn=True, reynoldsNumberInverse=1.0 / 200.0,
                              prandtlNumberInverse=1.0 / 0.7, powerLawExponent=0.0, bulkViscosityRatio=0.0,
                              dissipationOn=True, compositeDissipation=False, dissipationAmount=1e-4,
@@ -109,12 +168,15 @@ def build_c1(n=201, with_control=True):
             e[2 * d], e[2 * d + 1] = (1, depth) if side > 0 else (n - depth + 1, n)
             state.addPatch("SPONGE", f"sponge{d}{side}", nrm, list(e), 0.2, 2)
     if with_control:
-        grid.set(core.G_CONTROL_MOLLIFIER, np.exp(-((xy[:, 0] + 1.0) ** 2 + xy[:, 1] ** 2) / 4.0))
-        grid.set(core.G_TARGET_MOLLIFIER, np.exp(-((xy[:, 0] - 1.5) ** 2 + xy[:, 1] ** 2) / 6.0))
+        target, control = c1_mollifiers(n)
+        grid.set(core.G_TARGET_MOLLIFIER, target.reshape(-1, order="F"))
+        grid.set(core.G_CONTROL_MOLLIFIER, control.reshape(-1, order="F"))
         state.meanPressure = np.full(N, 1.0 / C1_GAMMA)
-        c = n // 2
-        state.addPatch("COST_TARGET", "targetRegion", 0, [c - 2, c + 9, c - 7, c + 7, 1, 1])
-        state.addPatch("ACTUATOR", "controlRegion", 0, [c - 8, c + 2, c - 6, c + 6, 1, 1])
+        te, ce = c1_extents(n)
+        state.addPatch("COST_TARGET", "targetRegion", 0, te)
+        state.addPatch("ACTUATOR", "controlRegion", 0, ce)
+        region.normalizeControlMollifier("L1")
+        region.normalizeTargetMollifier()
     s = C1_SOURCE
     state.addAcousticSource(s["location"], s["amplitude"], s["frequency"], s["radius"], s["phase"])
     region.computeSpongeStrengths()

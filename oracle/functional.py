@@ -25,6 +25,39 @@ def computeQuadratureOnPatches(patches, patchType, grid, integrand):
     return grid.computeInnerProduct(patchMask(patches, patchType, grid), np.asarray(integrand).reshape(-1))
 
 
+def normalizeTargetMollifier(grids, patches):
+    """``normalizeTargetMollifier`` (``src/RegionImpl.f90:545-603``; called by ``setupBoundaryConditions`` ``:1482-1483``
+    when the functional is enabled): every grid's target mollifier is divided by its quadrature over the COST_TARGET
+    patches of the region.  Returns the norm."""
+    norm = 0.0
+    for g in grids:
+        if np.any(g.targetMollifier[:, 0] < 0.0):
+            raise ValueError(f"Target mollifying support function on grid {g.index} is not non-negative everywhere!")
+        norm += computeQuadratureOnPatches(patches, "COST_TARGET", g, g.targetMollifier[:, 0])
+    for g in grids:
+        g.targetMollifier = g.targetMollifier / norm
+    return norm
+
+
+def normalizeControlMollifier(grids, patches, controllerNorm="L1", timeStepSize=0.0, controllerFactor=12.0):
+    """``normalizeControlMollifier`` (``src/RegionImpl.f90:459-543``): ``controller_norm = "L1"`` (the default,
+    ``src/SolverOptionsImpl.f90:114-115``) divides by the quadrature over the ACTUATOR patches,
+    ``"L_Inf_with_timestep"`` by ``sqrt(dt / controller_factor) * max(mollifier)``.  Returns the norm."""
+    if controllerNorm not in ("L1", "L_Inf_with_timestep"):
+        raise ValueError("Solver Option 'controller_norm' is not specified!")
+    norm = 0.0
+    for g in grids:
+        if np.any(g.controlMollifier[:, 0] < 0.0):
+            raise ValueError(f"Control mollifying support function on grid {g.index} is not non-negative everywhere!")
+        if controllerNorm == "L1":
+            norm += computeQuadratureOnPatches(patches, "ACTUATOR", g, g.controlMollifier[:, 0])
+        else:
+            norm = max(norm, np.sqrt(timeStepSize / controllerFactor) * float(np.max(g.controlMollifier[:, 0])))
+    for g in grids:
+        g.controlMollifier = g.controlMollifier / norm
+    return norm
+
+
 def computeAcousticNoise(patches, grid, state, meanPressure, timeRampFactor=1.0):
     F = state.pressure[:, 0] - np.asarray(meanPressure).reshape(-1)
     return timeRampFactor * computeQuadratureOnPatches(patches, "COST_TARGET", grid,

@@ -53,8 +53,8 @@ BC = """# Name                 Type                  Grid normDir iMin iMax jMin
   sponge.S             SPONGE                   1       2    1   -1    1    8    1   -1
   farField.N           SAT_FAR_FIELD            1      -2    1   -1   -1   -1    1   -1
   sponge.N             SPONGE                   1      -2    1   -1   -8   -1    1   -1
-  targetRegion         COST_TARGET              1       0   28   39   23   37    1   -1
-  controlRegion        ACTUATOR                 1       0   22   32   24   36    1   -1
+  targetRegion         COST_TARGET              1       0   28   34    9   53    1   -1
+  controlRegion        ACTUATOR                 1       0   33   42   26   36    1   -1
 """
 
 

@@ -16,20 +16,35 @@ from test_config_c1 import GAMMA, build_case
 N_STEPS, SAVE = 12, 4
 
 
-def oracle_setup(n=41):
+def oracle_setup(n=41, example_inputs=False):
+    """``example_inputs``: the mollifiers and COST_TARGET / ACTUATOR extents of examples/AcousticMonopole itself
+    (magudi_b200.workload.c1_mollifiers / c1_extents, pinned by tests/golden/acoustic_monopole_c1.npz), normalised as
+    setupBoundaryConditions does; otherwise small smooth test mollifiers."""
     from oracle import patches as op
     g, opt, s, plist, specs, src = build_case(n)
     x, y = g.coordinates[:, 0], g.coordinates[:, 1]
-    # smooth compact mollifiers: the control region sits next to the monopole, the target region beside it
-    g.controlMollifier[:, 0] = np.exp(-((x + 1.0) ** 2 + y ** 2) / 4.0)
-    g.targetMollifier[:, 0] = np.exp(-((x - 1.5) ** 2 + y ** 2) / 6.0)
     meanP = np.full(g.nGridPoints, 1.0 / GAMMA)
     c = n // 2
-    tgt = op.CostTargetPatch("targetRegion", g, 0, [c - 2, c + 9, c - 7, c + 7, 1, 1], opt)
-    act = op.ActuatorPatch("controlRegion", g, 0, [c - 8, c + 2, c - 6, c + 6, 1, 1], opt)
+    if example_inputs:
+        from magudi_b200 import workload as wl
+        target, control = wl.c1_mollifiers(n)
+        g.targetMollifier[:, 0] = target.reshape(-1, order="F")
+        g.controlMollifier[:, 0] = control.reshape(-1, order="F")
+        te, ce = wl.c1_extents(n)
+    else:
+        # smooth compact mollifiers: the control region sits next to the monopole, the target region beside it
+        g.controlMollifier[:, 0] = np.exp(-((x + 1.0) ** 2 + y ** 2) / 4.0)
+        g.targetMollifier[:, 0] = np.exp(-((x - 1.5) ** 2 + y ** 2) / 6.0)
+        te, ce = [c - 2, c + 9, c - 7, c + 7, 1, 1], [c - 8, c + 2, c - 6, c + 6, 1, 1]
+    tgt = op.CostTargetPatch("targetRegion", g, 0, te, opt)
+    act = op.ActuatorPatch("controlRegion", g, 0, ce, opt)
     plist = plist + [tgt, act]
     specs = specs + [("COST_TARGET", "targetRegion", 0, tgt.extent), ("ACTUATOR", "controlRegion", 0, act.extent)]
     op.updatePatches(plist, opt, g, s)
+    if example_inputs:
+        from oracle import functional as of
+        of.normalizeControlMollifier([g], plist)
+        of.normalizeTargetMollifier([g], plist)
     Q0 = np.zeros((g.nGridPoints, 4))
     Q0[:, 0] = 1.0
     Q0[:, 3] = 1.0 / GAMMA / (GAMMA - 1.0)

@@ -25,6 +25,11 @@ def main():
     ap.add_argument("--steps", type=int, default=800)
     ap.add_argument("--save", type=int, default=200)
     ap.add_argument("--oracle", action="store_true")
+    ap.add_argument("--test-mollifiers", action="store_true",
+                    help="small Gaussian test mollifiers instead of the example's own (normalised) ones")
+    ap.add_argument("--oracle-cache", default="",
+                    help="npz holding the oracle's J / sensitivity / gradient of this case: read if present, else written")
+    ap.add_argument("--oracle-only", action="store_true", help="run only the NumPy oracle drivers (no GPU) into --oracle-cache")
     ap.add_argument("--fd", type=int, default=20)
     ap.add_argument("--out", default="gpurun_out/c2.json")
     args = ap.parse_args()
@@ -34,8 +39,29 @@ def main():
     from oracle import solver as osol
     from helpers import gpu_case_from_oracle
     import test_solver_drivers as tsd
+    g, opt, s, plist, specs, src, meanP, Q0 = tsd.oracle_setup(args.n, example_inputs=not args.test_mollifiers)
+    tag = np.array([args.n, args.steps, args.save, int(args.test_mollifiers)])
+
+    def run_oracle():
+        if args.oracle_cache and os.path.exists(args.oracle_cache):
+            z = np.load(args.oracle_cache)
+            if np.array_equal(z["tag"], tag):
+                return float(z["J"]), float(z["sens"]), z["grad"], float(z["seconds"])
+        t0 = time.perf_counter()
+        os_ = osol.Solver(opt, g, s, plist, meanP, 0.05, args.steps, args.save)
+        Jo = os_.runForward(Q0)
+        so, go = os_.runAdjoint()
+        dt = time.perf_counter() - t0
+        if args.oracle_cache:
+            os.makedirs(os.path.dirname(args.oracle_cache) or ".", exist_ok=True)
+            np.savez(args.oracle_cache, tag=tag, J=Jo, sens=so, grad=go, seconds=dt)
+        return Jo, so, go, dt
+
+    if args.oracle_only:
+        Jo, so, go, dt = run_oracle()
+        print(json.dumps({"oracle_J": Jo, "oracle_cost_sensitivity": so, "oracle_s": dt, "gradient_shape": list(go.shape)}))
+        return
     _lib.init(0)
-    g, opt, s, plist, specs, src, meanP, Q0 = tsd.oracle_setup(args.n)
     gg, o, st = gpu_case_from_oracle(g, opt, s)
     gg.set(core.G_TARGET_MOLLIFIER, g.targetMollifier)
     gg.set(core.G_CONTROL_MOLLIFIER, g.controlMollifier)
@@ -51,6 +77,9 @@ def main():
     region.updatePatches()
     sol = gsol.Solver(region, st, 0.05, args.steps, args.save)
     log = {"case": f"AcousticMonopole {args.n}x{args.n}, {args.steps} steps, dt 0.05, save interval {args.save}",
+           "inputs": ("small Gaussian test mollifiers" if args.test_mollifiers else
+                      "the example's own mollifiers and COST_TARGET / ACTUATOR extents (pinned by tests/golden/"
+                      "acoustic_monopole_c1.npz), normalised as setupBoundaryConditions does"),
            "path": "fused" if region.usesFused(mb.FORWARD) else "general (patches present)"}
     t0 = time.perf_counter()
     J = sol.runForward(Q0)
@@ -70,11 +99,9 @@ def main():
         fd.append({"alpha": a, "J1": J1, "error": abs((J1 - J) / a - sens) / abs(sens)})
     log["fd"] = fd
     if args.oracle:
-        t0 = time.perf_counter()
-        os_ = osol.Solver(opt, g, s, plist, meanP, 0.05, args.steps, args.save)
-        Jo = os_.runForward(Q0)
-        so, go = os_.runAdjoint()
-        log["oracle_s"] = time.perf_counter() - t0
+        Jo, so, go, log["oracle_s"] = run_oracle()
+        log["oracle_source"] = ("NumPy oracle drivers, precomputed on the build container's CPU (" + args.oracle_cache + ")"
+                                if args.oracle_cache else "NumPy oracle drivers, run beside the GPU run")
         log["oracle_J"], log["oracle_cost_sensitivity"] = Jo, so
         log["rel_err_J"] = abs(J - Jo) / abs(Jo)
         log["rel_err_sensitivity"] = abs(sens - so) / abs(so)
