@@ -281,6 +281,13 @@ def load_case(directory, inp="magudi.inp"):
     if c.filterOn:
         for g in c.grids:
             g.setupFilter(deck.get("defaults/filtering_scheme", opt.discretizationType))
+    # time stepping mode (src/SimulationFlagsImpl.f90:36, src/SolverOptionsImpl.f90:88-93): constant CFL (the reference default) or constant time step
+    c.useConstantCflMode = bool(deck.get("use_constant_CFL_mode", True))
+    c.cfl = deck.get("cfl", 0.5) if c.useConstantCflMode else None
+    c.steadyStateSimulation = bool(deck.get("steady_state_simulation", False))
+    # functional (src/PressureDragImpl.f90:33-35: drag direction)
+    c.costFunctionalType = deck.get("cost_functional_type", "SOUND") if c.enableFunctional else None
+    c.dragDirection = tuple(deck.get("drag_direction_" + ax, 1.0 if ax == "x" else 0.0) for ax in "xyz")
     c.timeStepSize = deck.get("time_step_size", 0.0)
     c.numberOfTimesteps = deck.get("number_of_timesteps", 1000)
     c.saveInterval = deck.get("save_interval", -1)

@@ -80,3 +80,69 @@ def test_ogrid_overlap_rhs_forward_and_adjoint(gpu_lib):
     orhs.computeRhs(orhs.ADJOINT, opt, g, s, plist)
     region.computeRhs(mb.ADJOINT)
     assert relerr(st.rightHandSide, s.rightHandSide) <= 1e-12
+
+
+def test_c5_drag_functional_steady_adjoint_march(gpu_lib):
+    """The rest of the example's deck on the same O-grid: the COST_TARGET patch on the body with
+    ``cost_functional_type = "PRESSURE_DRAG"`` (drag direction x), ``steady_state_simulation = true`` (the adjoint
+    forcing enters with factor 1 at every stage, src/CostTargetPatchImpl.f90:108) and ``use_constant_CFL_mode`` with
+    ``cfl = 0.7`` (the time step follows from the state, src/StateImpl.f90:548-600): J, the forcing, the time step and
+    one forward + one adjoint RK4 step against the oracle."""
+    import magudi_b200 as mb
+    from oracle import cns
+    from oracle import functional as of
+    from oracle import patches as op
+    from oracle import rhs as orhs
+    g, opt, s, plist, specs = build_case()
+    opt.steadyStateSimulation = True
+    ni = g.globalSize[0]
+    tgt = op.CostTargetPatch("targetRegion", g, 2, [1, ni, 1, 1, 1, 1], opt)
+    plist = plist + [tgt]
+    op.updatePatches(plist, opt, g, s)
+    gg, o, st = gpu_case_from_oracle(g, opt, s)
+    region = mb.Region()
+    region.addState(st)
+    for spec in specs:
+        st.addPatch(*spec)
+    for po, pg in zip(plist, st.patches):
+        if isinstance(po, op.SpongePatch):
+            pg.setArray("spongeStrength", po.spongeStrength)
+    gt = st.addPatch("COST_TARGET", "targetRegion", 2, [1, ni, 1, 1, 1, 1], 1.0, 0.0)
+    region.updatePatches()
+    direction = (1.0, 0.0)
+    s.update(g, opt)
+    st.update()
+    # J and the adjoint forcing
+    Jo = of.computePressureDrag(opt, [tgt], g, s, direction)
+    Jg = st.computePressureDrag(direction)
+    assert abs(Jo) > 1e-3 and abs(Jg - Jo) <= 1e-10 * abs(Jo)
+    of.computePressureDragAdjointForcing(opt, g, s, tgt, direction, inviscidPenaltyAmount=1.0)
+    st.computePressureDragAdjointForcing(direction)
+    assert relerr(gt.getArray("adjointForcing", 4), tgt.adjointForcing) <= 1e-12
+    # constant-CFL mode
+    dt_o = cns.computeTimeStepSize(2, g.iblank, g.jacobian[:, 0], g.metrics, s.velocity, s.temperature[:, 0], 0.7,
+                                   opt.ratioOfSpecificHeats)
+    dt_g = st.computeTimeStepSize(0.7)
+    assert abs(dt_g - dt_o) <= 1e-13 * dt_o
+    assert abs(st.computeCfl(dt_g) - 0.7) <= 1e-12
+    # one forward and one adjoint step; in steady-state mode the forcing is not scaled by the stage factor
+    integ = mb.RK4Integrator(region)
+    oint = orhs.RK4Integrator(s)
+    f = lambda mode, ts, sg: orhs.computeRhs(mode, opt, g, s, plist)
+    t = tg = 0.0
+    for stage in range(1, 5):
+        t = oint.substepForward(f, s, t, dt_o, 0, stage)
+        s.update(g, opt)
+        tg = integ.substepForward(tg, dt_o, 0, stage)
+    assert relerr(st.conservedVariables, s.conservedVariables) <= 1e-12
+    W0 = s.adjointVariables.copy()
+    for stage in range(4, 0, -1):
+        t = oint.substepAdjoint(f, s, t, dt_o, 0, stage)
+        tg = integ.substepAdjoint(tg, dt_o, 0, stage)
+    assert relerr(st.adjointVariables, s.adjointVariables) <= 1e-12
+    # ... and it matters: the unsteady factors (2, 1, 1/2, 1) give a different adjoint state
+    opt.steadyStateSimulation = False
+    s.adjointVariables[:, :] = W0
+    for stage in range(4, 0, -1):
+        t = oint.substepAdjoint(f, s, t, dt_o, 0, stage)
+    assert relerr(st.adjointVariables, s.adjointVariables) > 1e-8
