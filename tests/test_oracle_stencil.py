@@ -32,6 +32,21 @@ def test_first_derivative_matches_reference_python_golden(scheme):
     np.testing.assert_allclose(y, g[key + "_axis1"], rtol=0, atol=16 * EPS * np.abs(g[key + "_axis1"]).max())
 
 
+@pytest.mark.parametrize("scheme,half", [("SBP 1-2", 1), ("SBP 2-4", 2), ("SBP 3-6", 3), ("SBP 4-8", 4)])
+def test_interior_coefficients_match_reference_fdcoeff(scheme, half):
+    """Interior rows against the reference's own Taylor-table solve (plot3dnasa.fdcoeff, executed unmodified by
+    tests/golden/make_golden_fdcoeff.py): first derivative of every scheme, second derivative where the reference
+    defines one (SBP 1-2, 2-4, 3-6: src/StencilOperatorImpl.f90:1197-1216, :1246-1280, :1423-1470)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fd_interior_coefficients.npz"))
+    D = StencilOperator.setup(scheme + " first derivative")
+    assert D.rhsInterior.size == 2 * half + 1
+    np.testing.assert_allclose(D.rhsInterior, g[f"first_{half}"], rtol=0, atol=32 * EPS)     # round-off of the reference's 9 x 9 solve
+    if half <= 3:
+        D2 = StencilOperator.setup(scheme + " second derivative")
+        assert D2.rhsInterior.size == 2 * half + 1
+        np.testing.assert_allclose(D2.rhsInterior, g[f"second_{half}"], rtol=0, atol=32 * EPS)
+
+
 @pytest.mark.parametrize("scheme,interior,boundary", [("SBP 1-2", 2, 1), ("SBP 2-4", 4, 2), ("SBP 3-6", 6, 3),
                                                       ("SBP 4-8", 8, 4)])
 def test_first_derivative_order_conditions(scheme, interior, boundary):
