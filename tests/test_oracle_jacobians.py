@@ -56,3 +56,18 @@ def test_incoming_plus_outgoing_jacobian_is_the_full_jacobian(nD):
     Ap = cns.computeIncomingJacobianOfInviscidFlux(nD, Q, m, GAMMA, +1, v, u, T)
     Am = cns.computeIncomingJacobianOfInviscidFlux(nD, Q, m, GAMMA, -1, v, u, T)
     assert np.max(np.abs(Ap + Am - A)) <= 1e-12 * np.max(np.abs(A))
+
+
+def test_dependent_variables_match_reference_python_golden():
+    """Velocity and pressure of computeDependentVariables (src/CNSHelperImpl.f90:3-87) against the reference's own
+    Python utility (plot3dnasa.Solution.toprimitive, executed unmodified by tests/golden/make_golden_primitive.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "primitive_variables.npz"))
+    gamma = float(g["gamma"])
+    Q = g["conserved"].reshape(-1, 5, order="F")
+    prim = g["primitive_round_trip"].reshape(-1, 5, order="F")
+    v, u, p, T = cns.computeDependentVariables(3, Q, gamma)
+    assert np.max(np.abs(u - prim[:, 1:4])) <= 4e-16 * np.max(np.abs(prim[:, 1:4]))
+    assert np.max(np.abs(p - prim[:, 4]) / Q[:, 4]) <= 4e-16        # relative to rho E (the difference cancels)
+    assert np.max(np.abs(v * prim[:, 0] - 1.0)) <= 4e-16
+    assert np.max(np.abs(T - gamma * prim[:, 4] / ((gamma - 1.0) * prim[:, 0])) * prim[:, 0] / Q[:, 4]) <= 2e-15
