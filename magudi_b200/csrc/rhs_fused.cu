@@ -17,6 +17,10 @@
 // from HBM once per sweep.  HBM-bound fp64 stencil/pointwise work: no tensor cores.
 #include "fused_common.cuh"
 
+#ifndef MG_SWEEPA_PIPE_DEFAULT
+#define MG_SWEEPA_PIPE_DEFAULT 0
+#endif
+
 namespace {
 
 // ------------------------------------------------------------------------------- sweep A
@@ -24,7 +28,10 @@ namespace {
 // (u, T) on a (TY+2R) x (TX+2R) box (corners unused) for the output plane, plus the k-queue of (u, T) for
 // the 2R+1 planes in flight (thread-private columns).  Nothing of the queue lives in registers, so three
 // CTAs fit per SM.
-template <int ND, int R, bool CURV, bool CLOS>
+// PIPE: the loads of the next arriving plane (own point and halo point) are issued right after the barrier that
+// publishes the tile, so that they are in flight during the stencil arithmetic of the current output plane instead
+// of stalling the first instruction of the next iteration (MG_SWEEPA_PIPE; same arithmetic, same results).
+template <int ND, int R, bool CURV, bool CLOS, bool PIPE = false>
 __global__ void __launch_bounds__(NT, 3) k_sweepA(FusedArgs a) {
   constexpr int NU = ND + 2;
   constexpr int NTAU = ND * (ND + 1) / 2;
@@ -85,6 +92,23 @@ __global__ void __launch_bounds__(NT, 3) k_sweepA(FusedArgs a) {
 
   PfItems<1> pfi;
   pfi.init(a, (long)i0 + (long)a.nx * j, tx, i0 < a.nx && j < a.ny);
+  double Qs[NU], Qh[NU];
+  // loads of the arriving plane s_ (storage plane ks_) and of the halo point of plane s_ - RK
+  auto issueLoads = [&](int s_, int ks_) {
+    if (inside) {
+      const double* __restrict__ Qp = a.Q + ((ND == 3) ? (long)ks_ * a.plane : 0) + pij;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) Qs[c] = __ldg(Qp + (size_t)c * a.cs);
+    }
+    if (hk && s_ - RK >= kc0) {
+      int kp_ = ks_ - RK;
+      if (ND == 3 && a.wrapK && kp_ < 0) kp_ += a.nz;
+      const double* __restrict__ Qp = a.Q + ((ND == 3) ? (long)kp_ * a.plane : 0) + hp;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) Qh[c] = __ldg(Qp + (size_t)c * a.cs);
+    }
+  };
+  if (PIPE) issueLoads(kc0 - RK, ks);
   for (int s = kc0 - RK; s < kc1 + RK; ++s) {
     // ---- arrival of plane s
     if (ND == 3 && a.prefetch) {
@@ -99,18 +123,8 @@ __global__ void __launch_bounds__(NT, 3) k_sweepA(FusedArgs a) {
     if (ND == 3 && a.wrapK && kp < 0) kp += a.nz;
     const long poff = (ND == 3) ? (long)kp * a.plane : 0;
     // issue the loads of the arriving own point and of the halo point of plane p together
-    double Qs[NU], Qh[NU];
     const bool doHalo = hk && p >= kc0;
-    if (inside) {
-      const double* __restrict__ Qp = a.Q + ((ND == 3) ? (long)ks * a.plane : 0) + pij;
-#pragma unroll
-      for (int c = 0; c < NU; ++c) Qs[c] = __ldg(Qp + (size_t)c * a.cs);
-    }
-    if (doHalo) {
-      const double* __restrict__ Qp = a.Q + poff + hp;
-#pragma unroll
-      for (int c = 0; c < NU; ++c) Qh[c] = __ldg(Qp + (size_t)c * a.cs);
-    }
+    if (!PIPE) issueLoads(s, ks);
     if (inside) {
       Prim<ND> sa;
       dependent<ND>(Qs, gamma, sa);
@@ -123,7 +137,10 @@ __global__ void __launch_bounds__(NT, 3) k_sweepA(FusedArgs a) {
       if (a.wrapK && ks >= a.nz) ks -= a.nz;
       if (++slot >= NQ) slot = 0;
     }
-    if (p < kc0) continue;
+    if (p < kc0) {
+      if (PIPE && s + 1 < kc1 + RK) issueLoads(s + 1, ks);
+      continue;
+    }
     // ---- output plane p: in-plane tile (own point from the queue, halo from global memory)
     double Tp = 0.0;
     if (inside) {
@@ -143,6 +160,7 @@ __global__ void __launch_bounds__(NT, 3) k_sweepA(FusedArgs a) {
       th[ND * H * W] = sh.T;
     }
     __syncthreads();
+    if (PIPE && s + 1 < kc1 + RK) issueLoads(s + 1, ks);
     if (mine && a.viscous) {
       const long off = poff + pij;
       // geometry loads first (latency overlaps the stencil arithmetic)
@@ -1192,13 +1210,16 @@ int launchA(const FusedArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int NP = ND + 1;
   constexpr int NQ = (ND == 3) ? 2 * R + 1 : 1;
   const size_t smem = sizeof(double) * ((size_t)NP * (TY + 2 * R) * (TX + 2 * R) + (size_t)NQ * NP * NT);
-  auto kern = k_sweepA<ND, R, CURV, CLOS>;
-  static int configuredDevice = -1;      // the attribute is per device: a second mg_init on another GPU sets it again
+  // the software-pipelined variant exists for the closure-free instantiations (the benched ones)
+  const bool pipe = !CLOS && mg_tuning_get("MG_SWEEPA_PIPE", MG_SWEEPA_PIPE_DEFAULT) != 0;
+  auto kern = k_sweepA<ND, R, CURV, CLOS, false>;
+  if (pipe) kern = k_sweepA<ND, R, CURV, CLOS, !CLOS>;
+  static int configuredDevice[2] = {-1, -1};   // the attribute is per device and per kernel
   int device = 0;
   cudaGetDevice(&device);
-  if (configuredDevice != device) {
+  if (configuredDevice[pipe] != device) {
     MG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configuredDevice = device;
+    configuredDevice[pipe] = device;
   }
   mg_profile_begin("sweepA");
   kern<<<grid, NT, smem, st>>>(a);
