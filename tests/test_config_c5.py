@@ -11,7 +11,7 @@ from helpers import gpu_case_from_oracle, relerr, relerr_global, random_state
 pytestmark = pytest.mark.gpu
 
 
-def build_case(ni=65, nj=40):
+def build_case(ni=65, nj=40, viscous=False):
     from oracle import grid as og
     from oracle import patches as op
     from oracle import rhs as orhs
@@ -23,7 +23,9 @@ def build_case(ni=65, nj=40):
     Y = (0.3 + (R - 1.0)) * np.sin(TH)                  # relaxing to circles away from it
     g.coordinates[:, 0] = X.reshape(-1, order="F")
     g.coordinates[:, 1] = Y.reshape(-1, order="F")
-    opt = orhs.SolverOptions(ratioOfSpecificHeats=1.4, viscosityOn=False, dissipationOn=True,
+    # viscous = the BASELINE wording of C5 ("isothermal-wall SAT"): the body becomes a SAT_ISOTHERMAL_WALL patch
+    opt = orhs.SolverOptions(ratioOfSpecificHeats=1.4, viscosityOn=viscous,
+                             reynoldsNumberInverse=1.0 / 150.0 if viscous else 0.0, dissipationOn=True,
                              compositeDissipation=False, dissipationAmount=0.012, useTargetState=True,
                              discretizationType="SBP 2-4")
     g.setupSpatialDiscretization("SBP 2-4", False, dissipationOn=True)
@@ -42,10 +44,16 @@ def build_case(ni=65, nj=40):
     s.conservedVariables[:, :] = Q3.reshape(-1, 4, order="F")
     s.adjointVariables[:, :] = W3.reshape(-1, 4, order="F")
     s.targetState[:, :] = T3.reshape(-1, 4, order="F")
-    plist = [op.ImpenetrableWall("airfoil", g, 2, [1, ni, 1, 1, 1, 1], opt, 1.0),
+    if viscous:
+        wall = op.IsothermalWall("airfoil", g, 2, [1, ni, 1, 1, 1, 1], opt, 1.0, 0.9)
+        wspec = ("SAT_ISOTHERMAL_WALL", "airfoil", 2, [1, ni, 1, 1, 1, 1], 1.0, 0.9)
+    else:
+        wall = op.ImpenetrableWall("airfoil", g, 2, [1, ni, 1, 1, 1, 1], opt, 1.0)
+        wspec = ("SAT_SLIP_WALL", "airfoil", 2, [1, ni, 1, 1, 1, 1], 1.0, 0.0)
+    plist = [wall,
              op.FarFieldPatch("farField", g, -2, [1, ni, nj, nj, 1, 1], opt, 1.0, 0.0),
              op.SpongePatch("sponge", g, -2, [1, ni, nj - 13, nj, 1, 1], 0.2, 2)]
-    specs = [("SAT_SLIP_WALL", "airfoil", 2, [1, ni, 1, 1, 1, 1], 1.0, 0.0),
+    specs = [wspec,
              ("SAT_FAR_FIELD", "farField", -2, [1, ni, nj, nj, 1, 1], 1.0, 0.0),
              ("SPONGE", "sponge", -2, [1, ni, nj - 13, nj, 1, 1])]
     op.computeSpongeStrengths(plist, g)
@@ -53,12 +61,13 @@ def build_case(ni=65, nj=40):
     return g, opt, s, plist, specs
 
 
-def test_ogrid_overlap_rhs_forward_and_adjoint(gpu_lib):
+@pytest.mark.parametrize("viscous", [False, True])
+def test_ogrid_overlap_rhs_forward_and_adjoint(gpu_lib, viscous):
     import magudi_b200 as mb
     from magudi_b200 import core
     from oracle import patches as op
     from oracle import rhs as orhs
-    g, opt, s, plist, specs = build_case()
+    g, opt, s, plist, specs = build_case(viscous=viscous)
     gg, o, st = gpu_case_from_oracle(g, opt, s)
     assert relerr_global(gg.get(core.G_METRICS), g.metrics) <= 1e-12
     assert relerr(gg.get(core.G_JACOBIAN), g.jacobian) <= 1e-12
@@ -70,6 +79,8 @@ def test_ogrid_overlap_rhs_forward_and_adjoint(gpu_lib):
         assert po.nPatchPoints == pg.nPatchPoints
         if isinstance(po, op.SpongePatch):
             pg.setArray("spongeStrength", po.spongeStrength)
+        if isinstance(po, op.IsothermalWall):
+            pg.setArray("temperature", po.temperature)
     region.updatePatches()
     assert not region.usesFused(mb.FORWARD)
     s.update(g, opt)
@@ -82,7 +93,8 @@ def test_ogrid_overlap_rhs_forward_and_adjoint(gpu_lib):
     assert relerr(st.rightHandSide, s.rightHandSide) <= 1e-12
 
 
-def test_c5_drag_functional_steady_adjoint_march(gpu_lib):
+@pytest.mark.parametrize("viscous", [False, True])
+def test_c5_drag_functional_steady_adjoint_march(gpu_lib, viscous):
     """The rest of the example's deck on the same O-grid: the COST_TARGET patch on the body with
     ``cost_functional_type = "PRESSURE_DRAG"`` (drag direction x), ``steady_state_simulation = true`` (the adjoint
     forcing enters with factor 1 at every stage, src/CostTargetPatchImpl.f90:108) and ``use_constant_CFL_mode`` with
@@ -93,7 +105,7 @@ def test_c5_drag_functional_steady_adjoint_march(gpu_lib):
     from oracle import functional as of
     from oracle import patches as op
     from oracle import rhs as orhs
-    g, opt, s, plist, specs = build_case()
+    g, opt, s, plist, specs = build_case(viscous=viscous)
     opt.steadyStateSimulation = True
     ni = g.globalSize[0]
     tgt = op.CostTargetPatch("targetRegion", g, 2, [1, ni, 1, 1, 1, 1], opt)
@@ -107,6 +119,8 @@ def test_c5_drag_functional_steady_adjoint_march(gpu_lib):
     for po, pg in zip(plist, st.patches):
         if isinstance(po, op.SpongePatch):
             pg.setArray("spongeStrength", po.spongeStrength)
+        if isinstance(po, op.IsothermalWall):
+            pg.setArray("temperature", po.temperature)
     gt = st.addPatch("COST_TARGET", "targetRegion", 2, [1, ni, 1, 1, 1, 1], 1.0, 0.0)
     region.updatePatches()
     direction = (1.0, 0.0)
@@ -120,8 +134,9 @@ def test_c5_drag_functional_steady_adjoint_march(gpu_lib):
     st.computePressureDragAdjointForcing(direction)
     assert relerr(gt.getArray("adjointForcing", 4), tgt.adjointForcing) <= 1e-12
     # constant-CFL mode
+    visc_args = (s.dynamicViscosity[:, 0], s.thermalDiffusivity[:, 0]) if viscous else ()
     dt_o = cns.computeTimeStepSize(2, g.iblank, g.jacobian[:, 0], g.metrics, s.velocity, s.temperature[:, 0], 0.7,
-                                   opt.ratioOfSpecificHeats)
+                                   opt.ratioOfSpecificHeats, *visc_args)
     dt_g = st.computeTimeStepSize(0.7)
     assert abs(dt_g - dt_o) <= 1e-13 * dt_o
     assert abs(st.computeCfl(dt_g) - 0.7) <= 1e-12
