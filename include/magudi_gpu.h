@@ -323,8 +323,17 @@ int mg_region_update_patches(mg_region* r);
 /* computeSpongeStrengths: src/PatchFactoryImpl.f90:161-374 -- fills the "spongeStrength" array of every SPONGE
  * patch from the grid's arc lengths.  For SPONGE patches mg_patch_create's two amounts are sponge_amount and
  * sponge_exponent (src/SpongePatchImpl.f90:40-45; reference defaults 1.0 and 2).  Sponges along a decomposed
- * direction are refused (set "spongeStrength" with mg_patch_set_array instead). */
+ * direction are refused here: use the two calls below around the host's gatherAlongDirection. */
 int mg_region_compute_sponge_strengths(mg_region* r);
+/* computeSpongeStrengths on a grid decomposed along `direction` (1-based), split around the reference's
+ * gatherAlongDirection (src/PatchFactoryImpl.f90:213-226, src/MPIHelperImpl.f90:298-402):
+ * mg_state_sponge_arc_length writes the rank's arc lengths sqrt(sum (d coordinates / d xi_direction)^2) to the host
+ * array arcLength (nGridPoints, i fastest); the host gathers them along the direction;
+ * mg_state_sponge_strengths_gathered takes the gathered lines (local sizes in the other directions,
+ * globalSize(direction) along it, i fastest) and fills "spongeStrength" of the state's SPONGE / JET_EXCITATION patches
+ * whose normal is +-direction (src/PatchFactoryImpl.f90:232-363).  Also valid on an undecomposed direction. */
+int mg_state_sponge_arc_length(mg_state* s, int direction, double* arcLength);
+int mg_state_sponge_strengths_gathered(mg_state* s, int direction, const double* arcLengthsAlongDirection);
 /* %computeRhs(mode, timestep, stage): src/RegionImpl.f90:1877-2027.  MG_MODE_LINEARIZED evaluates
  * computeRhsLinearized (src/RhsHelperImpl.f90:598-829) and the LINEARIZED branches of the patches: the perturbation
  * is the state's adjointVariables, as in the reference. */

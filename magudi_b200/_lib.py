@@ -151,6 +151,8 @@ SIGNATURES = {
     "mg_region_destroy": (C.c_int, [_P]),
     "mg_region_add_state": (C.c_int, [_P, _P]),
     "mg_region_compute_sponge_strengths": (C.c_int, [_P]),
+    "mg_state_sponge_arc_length": (C.c_int, [_P, C.c_int, _P]),
+    "mg_state_sponge_strengths_gathered": (C.c_int, [_P, C.c_int, _P]),
     "mg_region_update_patches": (C.c_int, [_P]),
     "mg_region_compute_rhs": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "mg_rk4_substep": (C.c_int, [_P, C.c_int, _D, C.c_double, C.c_int, C.c_int, C.c_int]),

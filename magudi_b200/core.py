@@ -715,8 +715,29 @@ class Region:
 
     def computeSpongeStrengths(self):
         """``computeSpongeStrengths`` (``src/PatchFactoryImpl.f90:161-374``) for every SPONGE patch of the region
-        (``addPatch("SPONGE", name, normalDirection, extent, spongeAmount, spongeExponent)``)."""
-        check(L.lib().mg_region_compute_sponge_strengths(self._h))
+        (``addPatch("SPONGE", name, normalDirection, extent, spongeAmount, spongeExponent)``).  Along a decomposed
+        direction the arc lengths of the sponge layers are gathered over the ranks of the pencil
+        (``gatherAlongDirection``, ``src/PatchFactoryImpl.f90:221-226``): collective over the ranks of the grid."""
+        if all(d == 1 for st in self.states for d in st.grid.procDims):
+            check(L.lib().mg_region_compute_sponge_strengths(self._h))
+            return
+        from . import parallel
+        for st in self.states:
+            g = st.grid
+            gs, ls, off = g.globalSize, g.localSize, g.offset
+            for d in range(g.nDimensions):
+                layers = [p.extent[2 * d:2 * d + 2] for p in st.patches
+                          if p.patchType in ("SPONGE", "JET_EXCITATION") and abs(p.normalDirection) == d + 1]
+                if not layers:
+                    continue
+                ends = [(gs[d] + a + 1 if a < 0 else a, gs[d] + b + 1 if b < 0 else b) for a, b in layers]
+                needed = (min(a for a, _ in ends) - 1, max(b for _, b in ends))
+                arc = np.zeros(int(np.prod(ls)))
+                check(L.lib().mg_state_sponge_arc_length(st._h, d + 1, L.fptr(arc)))
+                lines = parallel.gather_along_direction(arc.reshape(ls, order="F"), d, g.procDims, g.procCoords,
+                                                        off[d], gs[d], needed)
+                lines = np.ascontiguousarray(lines.reshape(-1, order="F"))
+                check(L.lib().mg_state_sponge_strengths_gathered(st._h, d + 1, L.fptr(lines)))
 
     def computeRhs(self, mode, timestep=0, stage=1):
         if mode == ADJOINT:

@@ -812,6 +812,16 @@ int mg_region_compute_sponge_strengths(mg_region* r) {
   for (mg_state* s : r->states) MG_TRY(mg_patches_sponge_strengths_impl(s));
   return 0;
 }
+int mg_state_sponge_arc_length(mg_state* s, int direction, double* arcLength) {
+  if (!s || !arcLength) MG_FAIL("mg_state_sponge_arc_length: null argument");
+  if (direction < 1 || direction > s->nD) MG_FAIL("mg_state_sponge_arc_length: direction out of range");
+  return mg_patches_sponge_arc_length_impl(s, direction - 1, arcLength);
+}
+int mg_state_sponge_strengths_gathered(mg_state* s, int direction, const double* arcLengthsAlongDirection) {
+  if (!s || !arcLengthsAlongDirection) MG_FAIL("mg_state_sponge_strengths_gathered: null argument");
+  if (direction < 1 || direction > s->nD) MG_FAIL("mg_state_sponge_strengths_gathered: direction out of range");
+  return mg_patches_sponge_strengths_gathered_impl(s, direction - 1, arcLengthsAlongDirection);
+}
 int mg_region_set_fused(mg_region* r, int enable) {
   if (!r) MG_FAIL("mg_region_set_fused: null handle");
   r->fused = enable;

@@ -416,9 +416,10 @@ __global__ void k_disperse(PatchGeom g, const double* in, size_t cs, int nComp, 
 // the sponge's direction from its inner edge, raised to sponge_exponent and scaled by sponge_amount.
 struct SpongeSetupArgs {
   PatchGeom g;
-  const double* arc;     // sqrt(sum (d coordinates / d xi_dir)^2), grid field
-  long stride;           // grid stride along the direction
-  int dir, eLo, eHi;     // direction, 0-based local extent [eLo, eHi] of the whole patch along it
+  const double* arc;     // sqrt(sum (d coordinates / d xi_dir)^2): the rank's grid field, or the lines gathered along dir
+  int n0, n1;            // first two sizes of the arc array (the local sizes, the global one along a gathered direction)
+  int dir, eLo, eHi;     // direction, 0-based extent [eLo, eHi] of the whole patch along it, in the arc array's index
+  int cOffset;           // index of the rank's first point along dir in the arc array (0 unless gathered)
   int normalDirection, exponent;
   double amount;
   double* out;
@@ -427,17 +428,18 @@ struct SpongeSetupArgs {
 __global__ void k_sponge_strength(SpongeSetupArgs a) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= a.g.n) return;
-  const size_t p = a.g.gridIndex(q);
-  const int cl[3] = {a.g.lo[0] + q % a.g.sz[0], a.g.lo[1] + (q / a.g.sz[0]) % a.g.sz[1], a.g.lo[2] + q / (a.g.sz[0] * a.g.sz[1])};
-  const int c = cl[a.dir];
-  const double* line = a.arc + (long)p - (long)c * a.stride;     // coordinate 0 of this grid line
+  int cl[3] = {a.g.lo[0] + q % a.g.sz[0], a.g.lo[1] + (q / a.g.sz[0]) % a.g.sz[1], a.g.lo[2] + q / (a.g.sz[0] * a.g.sz[1])};
+  const int c = cl[a.dir] + a.cOffset;
+  cl[a.dir] = 0;
+  const long stride = a.dir == 0 ? 1 : (a.dir == 1 ? (long)a.n0 : (long)a.n0 * a.n1);
+  const double* line = a.arc + ((long)cl[0] + (long)a.n0 * ((long)cl[1] + (long)a.n1 * cl[2]));   // coordinate 0 of this line
   double num = 0.0, den = 0.0;
   if (a.normalDirection > 0) {
-    for (int l = a.eLo; l <= c - 1; ++l) num += line[(long)l * a.stride];
-    for (int l = a.eLo; l <= a.eHi - 1; ++l) den += line[(long)l * a.stride];
+    for (int l = a.eLo; l <= c - 1; ++l) num += line[(long)l * stride];
+    for (int l = a.eLo; l <= a.eHi - 1; ++l) den += line[(long)l * stride];
   } else {
-    for (int l = c + 1; l <= a.eHi; ++l) num += line[(long)l * a.stride];
-    for (int l = a.eLo + 1; l <= a.eHi; ++l) den += line[(long)l * a.stride];
+    for (int l = c + 1; l <= a.eHi; ++l) num += line[(long)l * stride];
+    for (int l = a.eLo + 1; l <= a.eHi; ++l) den += line[(long)l * stride];
   }
   a.out[q] = a.amount * pow(1.0 - num / den, (double)a.exponent);
 }
@@ -612,45 +614,92 @@ int mg_patches_update_impl(mg_state* s) {
   return 0;
 }
 
+static bool sponge_along(const mg_state* s, int dir) {
+  for (const mg_patch* p : s->patches)
+    if ((p->type == MG_PATCH_SPONGE || p->type == MG_PATCH_JET_EXCITATION) && std::abs(p->normalDirection) == dir + 1) return true;
+  return false;
+}
+
+// local arc length along dir (src/PatchFactoryImpl.f90:213-218)
+static int sponge_arc_field(mg_state* s, int dir, MgField* arc) {
+  mg_grid* g = s->grid;
+  MgField cd;
+  MG_TRY(mg_field_alloc(g, s->nD, &cd));
+  MG_TRY(mg_field_alloc(g, 1, arc));
+  MG_TRY(mg_grid_coordinate_derivatives(g, dir, &cd));
+  { k_arc_from_derivatives<<<(unsigned)((g->N + 255) / 256), 256, 0, mg_stream()>>>(cd.comp(0), cd.compStride, s->nD, arc->comp(0), g->N); mg_count_launches(1); }
+  MG_CUDA(cudaGetLastError());
+  MG_CUDA(cudaStreamSynchronize(mg_stream()));
+  mg_field_free(&cd);
+  return 0;
+}
+
+// strengths of the sponges along dir from arc lengths whose lines hold `lineLength` points along dir, the rank's first
+// point being number cOffset of them (src/PatchFactoryImpl.f90:232-363)
+static int sponge_strengths_along(mg_state* s, int dir, const double* arc, int lineLength, int cOffset) {
+  mg_grid* g = s->grid;
+  for (mg_patch* p : s->patches) {
+    if ((p->type != MG_PATCH_SPONGE && p->type != MG_PATCH_JET_EXCITATION) || std::abs(p->normalDirection) != dir + 1 ||
+        p->nPatchPoints <= 0) continue;
+    double* out = nullptr;
+    MG_TRY(mg_patch_alloc_array(p, "spongeStrength", 1, &out));
+    SpongeSetupArgs a;
+    a.g = geom(p);
+    a.arc = arc;
+    a.n0 = dir == 0 ? lineLength : g->localSize[0];
+    a.n1 = dir == 1 ? lineLength : g->localSize[1];
+    a.dir = dir;
+    a.cOffset = cOffset;
+    a.eLo = p->extent[2 * dir] - 1 - g->offset[dir] + cOffset;
+    a.eHi = p->extent[2 * dir + 1] - 1 - g->offset[dir] + cOffset;
+    a.normalDirection = p->normalDirection;
+    a.exponent = p->spongeExponent;
+    a.amount = p->spongeAmount;
+    a.out = out;
+    { k_sponge_strength<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a); mg_count_launches(1); }
+    MG_CUDA(cudaGetLastError());
+  }
+  MG_CUDA(cudaStreamSynchronize(mg_stream()));
+  return 0;
+}
+
 int mg_patches_sponge_strengths_impl(mg_state* s) {
   mg_grid* g = s->grid;
   for (int dir = 0; dir < s->nD; ++dir) {
-    bool any = false;
-    for (mg_patch* p : s->patches) any = any || ((p->type == MG_PATCH_SPONGE || p->type == MG_PATCH_JET_EXCITATION) && std::abs(p->normalDirection) == dir + 1);
-    if (!any) continue;
+    if (!sponge_along(s, dir)) continue;
     if (g->procDims[dir] > 1)
-      MG_FAIL("computeSpongeStrengths: sponges along a decomposed direction need the arc length of the whole line; "
-              "set the patch array \"spongeStrength\" instead");
-    MgField cd, arc;
-    MG_TRY(mg_field_alloc(g, s->nD, &cd));
-    MG_TRY(mg_field_alloc(g, 1, &arc));
-    MG_TRY(mg_grid_coordinate_derivatives(g, dir, &cd));
-    { k_arc_from_derivatives<<<(unsigned)((g->N + 255) / 256), 256, 0, mg_stream()>>>(cd.comp(0), cd.compStride, s->nD, arc.comp(0), g->N); mg_count_launches(1); }
-    MG_CUDA(cudaGetLastError());
-    for (mg_patch* p : s->patches) {
-      if ((p->type != MG_PATCH_SPONGE && p->type != MG_PATCH_JET_EXCITATION) || std::abs(p->normalDirection) != dir + 1 ||
-          p->nPatchPoints <= 0) continue;
-      double* out = nullptr;
-      MG_TRY(mg_patch_alloc_array(p, "spongeStrength", 1, &out));
-      SpongeSetupArgs a;
-      a.g = geom(p);
-      a.arc = arc.comp(0);
-      a.stride = dir == 0 ? 1 : (dir == 1 ? (long)g->localSize[0] : (long)g->plane);
-      a.dir = dir;
-      a.eLo = p->extent[2 * dir] - 1 - g->offset[dir];
-      a.eHi = p->extent[2 * dir + 1] - 1 - g->offset[dir];
-      a.normalDirection = p->normalDirection;
-      a.exponent = p->spongeExponent;
-      a.amount = p->spongeAmount;
-      a.out = out;
-      { k_sponge_strength<<<nblocks(p->nPatchPoints), 128, 0, mg_stream()>>>(a); mg_count_launches(1); }
-      MG_CUDA(cudaGetLastError());
-    }
-    MG_CUDA(cudaStreamSynchronize(mg_stream()));
-    mg_field_free(&cd);
+      MG_FAIL("computeSpongeStrengths: sponges along a decomposed direction need the arc length of the whole line: "
+              "gather mg_state_sponge_arc_length along the direction and call mg_state_sponge_strengths_gathered");
+    MgField arc;
+    MG_TRY(sponge_arc_field(s, dir, &arc));
+    const int rc = sponge_strengths_along(s, dir, arc.comp(0), g->localSize[dir], 0);
     mg_field_free(&arc);
+    if (rc) return rc;
   }
   return 0;
+}
+
+int mg_patches_sponge_arc_length_impl(mg_state* s, int dir, double* hostOut) {
+  MgField arc;
+  MG_TRY(sponge_arc_field(s, dir, &arc));
+  const cudaError_t e = cudaMemcpy(hostOut, arc.comp(0), s->grid->N * sizeof(double), cudaMemcpyDeviceToHost);
+  mg_field_free(&arc);
+  MG_CUDA(e);
+  return 0;
+}
+
+int mg_patches_sponge_strengths_gathered_impl(mg_state* s, int dir, const double* arcGathered) {
+  mg_grid* g = s->grid;
+  if (!sponge_along(s, dir)) return 0;
+  const size_t n = g->N / (size_t)g->localSize[dir] * (size_t)g->globalSize[dir];
+  double* d = nullptr;
+  MG_CUDA(cudaMalloc(&d, n * sizeof(double)));
+  cudaError_t e = cudaMemcpy(d, arcGathered, n * sizeof(double), cudaMemcpyHostToDevice);
+  int rc = 0;
+  if (e == cudaSuccess) rc = sponge_strengths_along(s, dir, d, g->globalSize[dir], g->offset[dir]);
+  cudaFree(d);
+  MG_CUDA(e);
+  return rc;
 }
 
 int mg_patches_farfield_adjoint_sources(mg_state* s, MgField* temp1) {

@@ -67,6 +67,8 @@ int mg_patch_collect_impl(mg_patch* p, const MgField* f, int nComp, const char* 
 int mg_patch_disperse_impl(mg_patch* p, const char* name, int nComp, MgField* f);
 int mg_patches_update_impl(mg_state* s);
 int mg_patches_sponge_strengths_impl(mg_state* s);
+int mg_patches_sponge_arc_length_impl(mg_state* s, int dir, double* hostOut);
+int mg_patches_sponge_strengths_gathered_impl(mg_state* s, int dir, const double* arcGathered);
 int mg_patch_kolmogorov_setup_impl(mg_patch* p, double amplitude, int wavenumber);
 int mg_patch_probe_setup_impl(mg_patch* p, int bufferSize);
 int mg_patch_probe_record_impl(mg_patch* p, int mode, int* full);

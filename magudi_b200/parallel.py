@@ -331,6 +331,42 @@ def all_reduce_max(value, device=None):
     return float(t.item())
 
 
+def gather_along_direction(local, direction, procDims, procCoords, offset, globalSize, needed=None, group=None):
+    """``gatherAlongDirection`` (reference ``src/MPIHelperImpl.f90:298-402``): ``local`` is this rank's brick
+    (n1, n2, n3) of a grid field; the result holds, for the lines through this brick, all ``globalSize`` points along
+    ``direction`` (0-based) -- shape = the local shape with ``globalSize`` along that direction.  The ranks of a pencil
+    (equal process coordinates in the other directions) exchange their pieces; every rank of the grid must call it.
+    ``needed = (lo, hi)``: only the global 0-based index range [lo, hi) along the direction travels, the rest of the
+    result is zero (``computeSpongeStrengths`` reads the sponge layers only).  Host-side: setup-time data."""
+    import numpy as np
+    local = np.asarray(local)
+    d = int(direction)
+    out_shape = list(local.shape)
+    out_shape[d] = int(globalSize)
+    out = np.zeros(out_shape, dtype=local.dtype)
+    lo, hi = (0, int(globalSize)) if needed is None else (max(int(needed[0]), 0), min(int(needed[1]), int(globalSize)))
+
+    def window(o, n):
+        return max(lo, o), min(hi, o + n)
+    a, b = window(int(offset), local.shape[d])
+    sl = [slice(None)] * local.ndim
+    sl[d] = slice(a - int(offset), max(b, a) - int(offset))
+    mine = np.ascontiguousarray(local[tuple(sl)])
+    if int(procDims[d]) == 1 or not collectives_active():
+        pieces = [(tuple(int(c) for c in procCoords), int(offset), mine)]
+    else:
+        pieces = [None] * dist.get_world_size(group)
+        dist.all_gather_object(pieces, (tuple(int(c) for c in procCoords), int(offset), mine), group=group)
+    me = tuple(int(c) for c in procCoords)
+    for coords, o, piece in pieces:
+        if any(coords[e] != me[e] for e in range(len(me)) if e != d) or piece.shape[d] == 0:
+            continue
+        a = max(lo, o)
+        sl[d] = slice(a, a + piece.shape[d])
+        out[tuple(sl)] = piece
+    return out
+
+
 # ---------------------------------------------------------------------------------- patch collectives
 def _patch_box(localSize, patchOffset):
     """slices of the patch-global (n1, n2, n3) box that this rank's local part covers"""

@@ -158,3 +158,16 @@ def test_sponge_strengths_computed_on_the_device(shape):
         got = pg.getArray("spongeStrength", 1)[:, 0]
         assert np.max(po.spongeStrength) > 0.1
         assert relerr(got, po.spongeStrength) <= 1e-13
+    # the two-call form around the host's gatherAlongDirection (what a decomposed direction uses; here the gathered
+    # lines are the rank's own): same strengths, bit for bit
+    from magudi_b200 import _lib as L
+    first = [pg.getArray("spongeStrength", 1)[:, 0].copy() for pg in gp]
+    for pg in gp:
+        pg.setArray("spongeStrength", np.zeros(pg.nPatchPoints))
+    for d in range(nd):
+        arc = np.zeros(gg.nGridPoints)
+        L.check(L.lib().mg_state_sponge_arc_length(st._h, d + 1, L.fptr(arc)))
+        assert np.min(arc) > 0.0
+        L.check(L.lib().mg_state_sponge_strengths_gathered(st._h, d + 1, L.fptr(arc)))
+    for a, pg in zip(first, gp):
+        assert np.array_equal(pg.getArray("spongeStrength", 1)[:, 0], a)

@@ -175,3 +175,56 @@ def test_extrema_over_ranks_and_interface_reordering_gloo(world):
         p.join(120)
         assert p.exitcode == 0
     assert list(ok) == [1] * world
+
+
+def _gather_worker(rank, world, port, ok):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from magudi_b200.core import pigeonhole
+        from magudi_b200.parallel import cart_coords, gather_along_direction
+        # process grids that split the gathered direction and another one: pencils are the ranks with equal
+        # coordinates in the other directions
+        gs = (7, 9, 11)
+        G = np.arange(int(np.prod(gs)), dtype=np.float64).reshape(gs, order="F")
+        good = True
+        for dims, d in (((1, 1, world), 2), ((1, world, 1), 1), ((2, 1, world // 2), 2), ((2, 1, world // 2), 0)):
+            if int(np.prod(dims)) != world:
+                continue
+            coords = cart_coords(rank, dims)
+            on = [pigeonhole(gs[e], dims[e], coords[e]) for e in range(3)]
+            box = tuple(slice(o, o + n) for o, n in on)
+            local = G[box]
+            for needed in (None, (0, 4), (gs[d] - 5, gs[d]), (2, gs[d] - 1)):
+                got = gather_along_direction(local, d, dims, coords, on[d][0], gs[d], needed)
+                full = list(box)
+                full[d] = slice(None)
+                want = G[tuple(full)].copy()
+                if needed is not None:
+                    mask = [slice(None)] * 3
+                    mask[d] = slice(0, needed[0])
+                    want[tuple(mask)] = 0.0
+                    mask[d] = slice(needed[1], None)
+                    want[tuple(mask)] = 0.0
+                good &= got.shape == want.shape and np.array_equal(got, want)
+        ok[rank] = 1 if good else 0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_gather_along_direction_gloo(world):
+    """gatherAlongDirection (reference src/MPIHelperImpl.f90:298-402) as computeSpongeStrengths uses it
+    (src/PatchFactoryImpl.f90:221-226): whole lines along a decomposed direction, per pencil, optionally only the
+    sponge layers' index window."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ok = ctx.Array("i", [0] * world)
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, ok)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(ok) == [1] * world

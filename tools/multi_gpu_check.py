@@ -134,14 +134,22 @@ def _run_general(shape, dims, rank, dev):
     specs = [("SAT_FAR_FIELD", "ff.k1", 3, [1, nx, 1, ny, 1, 1], 1.0, 0.7),
              ("SAT_FAR_FIELD", "ff.kn", -3, [1, nx, 1, ny, nzg, nzg], 1.0, 0.7),
              ("SPONGE", "sponge.k", -3, [1, nx, 1, ny, nzg - 9, nzg]),
+             # strengths from computeSpongeStrengths: layers that straddle rank boundaries of every decomposition
+             ("SPONGE", "sponge.k1", 3, [1, nx, 1, ny, 1, nzg // 2 + 3], 0.3, 2),
+             ("SPONGE", "sponge.jn", -2, [1, nx, ny // 2 - 2, ny, 1, nzg], 0.2, 3),
+             ("SPONGE", "sponge.i1", 1, [1, nx // 2 + 2, 2, ny - 1, 1, nzg], 0.25, 2),
              ("SAT_ISOTHERMAL_WALL", "wall.j1", 2, [1, nx, 1, 1, 1, nzg], 1.0, 0.8),
              ("SAT_SLIP_WALL", "wall.i1", 1, [1, 1, 1, ny, 1, nzg], 1.0, 0.0),
              ("SAT_FAR_FIELD", "ff.in", -1, [nx, nx, 1, ny, 1, nzg], 1.0, 0.7),
              ("COST_TARGET", "target", 0, [4, nx - 3, 3, ny - 2, 5, nzg - 4])]
-    for sp in specs:
-        p = state.addPatch(*sp)
+    patches = [state.addPatch(*sp) for sp in specs]
+    region.computeSpongeStrengths()         # collective; "sponge.k" then gets an explicit profile instead
+    strengths = {}
+    for sp, p in zip(specs, patches):
         if p.nPatchPoints <= 0:
             continue
+        if sp[0] == "SPONGE" and len(sp) > 4:
+            strengths[sp[1]] = (p.gridIndices(), p.getArray("spongeStrength", 1)[:, 0])
         idx = p.gridIndices()
         if sp[0] == "SPONGE":
             p.setArray("spongeStrength", loc(Sg)[idx, 0])
@@ -166,6 +174,11 @@ def _run_general(shape, dims, rank, dev):
     for stage in range(4, 0, -1):
         t = integ.substepAdjoint(t, 2e-3, 0, stage)
     out += [state.conservedVariables, state.adjointVariables]
+    S = np.zeros((grid.nGridPoints, 5))     # the computed sponge strengths as grid fields, compared like the rest
+    for c, name in enumerate(("sponge.k1", "sponge.jn", "sponge.i1")):
+        if name in strengths:
+            S[strengths[name][0], c] = strengths[name][1]
+    out.append(S)
     for h in halos:
         h.check()
     grid.limitsCheck = (extrema, penalty)
@@ -292,8 +305,8 @@ def check_all(world, rank, dev):
               f"max rel diff vs single GPU = {el:.3e}", file=sys.stderr)
         Bs, _ = run_general(bshape, (1, 1, 1), 0, dev)
         e1 = compare(pieces, Qs, shape, 10, "fused path (2 forward + 1 adjoint RK4 steps)", world)
-        e2 = compare(gpieces, Gs, gshape, 25, "operator path, slabs along k (patches, non-periodic, soft solution limits; fwd/adj/lin RHS + RK4)", world)
-        eb = {k: compare(v, Bs, bshape, 25, f"operator path, bricks split along {k} {brick[k]}", world)
+        e2 = compare(gpieces, Gs, gshape, 30, "operator path, slabs along k (computed sponge strengths, patches, non-periodic, soft solution limits; fwd/adj/lin RHS + RK4)", world)
+        eb = {k: compare(v, Bs, bshape, 30, f"operator path, bricks split along {k} {brick[k]}", world)
               for k, v in bpieces.items()}
         one = run_blocks(1, 0, dev)
         ei = 0.0
