@@ -1,4 +1,4 @@
-out=gpurun_out/r3e; mkdir -p $out
+out=gpurun_out/${1:-r4c}; mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/smi.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > $out/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $out/pytest.log
 timeout 300 python __graft_entry__.py --smoke > $out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $out/smoke.log
