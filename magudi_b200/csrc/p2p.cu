@@ -336,7 +336,11 @@ static int p2p_exchange_field(mg_p2p* h, const MgField* fAll, int width, cudaStr
   const View view{fAll, comps, nSel};
   const View* f = &view;
   const size_t chunk = g->plane * (size_t)width;
-  if (width > g->gk || width > g->localSize[2]) MG_FAIL("mg_p2p_exchange: width exceeds ghost capacity");
+  // OVERLAP periodicity: the first and the last point of the direction coincide, so the first rank skips its first
+  // plane and the last rank its last one (periodicOffset of src/MPIHelperImpl.f90:203-296, set by updateOperator)
+  const bool ovl = g->periodicityType[2] == MG_PERIODIC_OVERLAP;
+  const int ovLo = (ovl && g->procCoords[2] == 0) ? 1 : 0, ovHi = (ovl && g->procCoords[2] == g->procDims[2] - 1) ? 1 : 0;
+  if (width > g->gk || width + std::max(ovLo, ovHi) > g->localSize[2]) MG_FAIL("mg_p2p_exchange: width exceeds ghost capacity");
   if (f->nComp > MG_P2P_MAX_COMP || chunk * (size_t)f->nComp > h->capacity)
     MG_FAIL("mg_p2p_exchange: field exceeds the staging capacity");
   const unsigned long long n = h->uses[0];
@@ -352,7 +356,7 @@ static int p2p_exchange_field(mg_p2p* h, const MgField* fAll, int width, cudaStr
     a.nComp = f->nComp;
     a.chunk = chunk;
     for (int c = 0; c < f->nComp; ++c)
-      a.src[c] = f->comp(c) + (side == 0 ? 0 : g->plane * (size_t)(g->localSize[2] - width));
+      a.src[c] = f->comp(c) + (side == 0 ? g->plane * (size_t)ovLo : g->plane * (size_t)(g->localSize[2] - width - ovHi));
     const int peerFace = 1 - side;
     a.dst = reinterpret_cast<double*>(h->peer[side] + mg_p2p::bufOffset(h->capacity, peerFace, parity));
     a.dstFlag = &reinterpret_cast<Shared*>(h->peer[side])->data[peerFace][parity];
@@ -449,8 +453,8 @@ namespace {
 // pack the first (side 0) and last (side 1) `w` points of every grid line along DIR, for nComp components, in the
 // ghost-buffer layout of the reference (src/MPIHelperImpl.f90:175-296): q + w * (line + lines * component)
 template <int DIR>
-__global__ void k_pack_faces(const double* x, size_t cs, int nComp, long nx, long ny, long nz, int w, double* lo,
-                             double* hi) {
+__global__ void k_pack_faces(const double* x, size_t cs, int nComp, long nx, long ny, long nz, int w, int ovLo, int ovHi,
+                             double* lo, double* hi) {
   const long n = DIR == 0 ? nx : ny;
   const long lines = DIR == 0 ? ny * nz : nx * nz;
   const long total = (long)w * lines * nComp;
@@ -463,8 +467,8 @@ __global__ void k_pack_faces(const double* x, size_t cs, int nComp, long nx, lon
     if (DIR == 0) { p0 = nx * line; stride = 1; }                       // line = j + ny k
     else { const long i = line % nx, k = line / nx; p0 = i + nx * ny * k; stride = nx; }   // line = i + nx k
     const double* xl = x + (size_t)l * cs;
-    lo[t] = xl[p0 + (long)q * stride];
-    hi[t] = xl[p0 + (n - w + q) * stride];
+    lo[t] = xl[p0 + (long)(q + ovLo) * stride];
+    hi[t] = xl[p0 + (n - w + q - ovHi) * stride];
   }
 }
 }  // namespace
@@ -484,15 +488,19 @@ int mg_p2p_exchange_faces(mg_p2p* h, const double* in, size_t inCs, int nComp, i
   const long lines = (long)(g->N / g->localSize[dir]);
   const size_t count = (size_t)width * lines * nComp;
   if (count > h->capacity) MG_FAIL("mg_p2p_exchange_faces: more components than the halo was created for");
-  if (width > g->localSize[dir]) MG_FAIL("mg_p2p_exchange_faces: the rank's extent is smaller than the stencil half-width");
+  // OVERLAP periodicity: the first rank's first point and the last rank's last point are one point; the duplicate
+  // does not travel (periodicOffset of src/MPIHelperImpl.f90:203-296)
+  const bool ovl = g->periodicityType[dir] == MG_PERIODIC_OVERLAP;
+  const int ovLo = (ovl && g->procCoords[dir] == 0) ? 1 : 0, ovHi = (ovl && g->procCoords[dir] == g->procDims[dir] - 1) ? 1 : 0;
+  if (width + std::max(ovLo, ovHi) > g->localSize[dir]) MG_FAIL("mg_p2p_exchange_faces: the rank's extent is smaller than the stencil half-width");
   cudaStream_t st = mg_stream();
   const unsigned blocks = (unsigned)std::min<size_t>((count + 255) / 256, 4096);
   if (dir == 0)
     k_pack_faces<0><<<blocks, 256, 0, st>>>(in, inCs, nComp, g->localSize[0], g->localSize[1], g->localSize[2], width,
-                                            h->faceSend[0], h->faceSend[1]);
+                                            ovLo, ovHi, h->faceSend[0], h->faceSend[1]);
   else
     k_pack_faces<1><<<blocks, 256, 0, st>>>(in, inCs, nComp, g->localSize[0], g->localSize[1], g->localSize[2], width,
-                                            h->faceSend[0], h->faceSend[1]);
+                                            ovLo, ovHi, h->faceSend[0], h->faceSend[1]);
   MG_CUDA(cudaGetLastError());
   mg_count_launches(1);
   MG_TRY(p2p_exchange_buffers(h, h->faceSend[0], h->faceSend[1], h->faceRecv[0], h->faceRecv[1], count, st));
@@ -508,8 +516,6 @@ int mg_p2p_create_dir(mg_grid* g, int direction, int maxComp, int width, mg_p2p*
   if (direction < 0 || direction > 1) MG_FAIL("mg_p2p_create_dir: direction must be 0, 1 or 2");
   if (maxComp < 1 || maxComp > MG_P2P_MAX_COMP) MG_FAIL("mg_p2p_create_dir: component count out of range");
   if (width < 1 || width > g->localSize[direction]) MG_FAIL("mg_p2p_create_dir: width exceeds the local extent");
-  if (g->periodicityType[direction] == MG_PERIODIC_OVERLAP && g->procDims[direction] > 1)
-    MG_FAIL("mg_p2p_create_dir: OVERLAP periodicity along a decomposed direction is not supported");
   mg_p2p* h = new mg_p2p;
   h->grid = g;
   h->direction = direction;

@@ -185,6 +185,57 @@ def _run_general(shape, dims, rank, dev):
     return np.concatenate(out, axis=1), grid
 
 
+def run_overlap(shape, dims, rank, dev, pdir):
+    """Operator path on an annulus whose angular direction ``pdir`` (1: j, 2: k) is OVERLAP-periodic (first and last
+    point coincide) AND decomposed: the duplicate point does not travel in the halo (``periodicOffset``,
+    src/MPIHelperImpl.f90:203-296).  Radial direction i with a slip wall and a far field; fwd / adj / lin RHS."""
+    world = int(np.prod(dims))
+    coords = par.cart_coords(rank, dims) if world > 1 else (0, 0, 0)
+    opt = core.SolverOptions(ratioOfSpecificHeats=1.4, viscosityOn=True, reynoldsNumberInverse=1.0 / 90.0,
+                             dissipationOn=True, compositeDissipation=False, dissipationAmount=0.01,
+                             useTargetState=True, discretizationType="SBP 2-4")
+    ptype = [core.NONE] * 3
+    ptype[pdir] = core.OVERLAP
+    grid = core.Grid(1, shape, tuple(ptype), (0.0,) * 3, isCurvilinear=True, procDims=dims, procCoords=coords)
+    grid.setupSpatialDiscretization(opt.discretizationType, opt.compositeDissipation, False, opt.dissipationOn)
+    o, n = grid.offset, grid.localSize
+    idx = np.meshgrid(*[np.arange(o[d], o[d] + n[d], dtype=np.float64) for d in range(3)], indexing="ij")
+    r = 1.0 + 1.5 * idx[0] / (shape[0] - 1) + 0.05 * np.sin(0.7 * idx[3 - pdir])
+    th = 2.0 * np.pi * idx[pdir] / (shape[pdir] - 1)
+    z = 0.1 * idx[3 - pdir] + 0.02 * np.sin(th)
+    xyz = (r * np.cos(th), r * np.sin(th), z) if pdir == 1 else (r * np.cos(th), z, r * np.sin(th))
+    grid.setCoordinates(np.stack([a.reshape(-1, order="F") for a in xyz], axis=1))
+    halos = []
+    for d in range(3):
+        if dims[d] > 1:
+            h = par.GpuHalo(grid, coords[d], dims[d], dev, direction=d)
+            assert h.mode == "p2p"
+            halos.append(h)
+            if d == 2:
+                h.exchange(None, core.G_COORDINATES, 3, 2)
+    assert not grid.update()
+    state = core.State(grid, opt)
+    region = core.Region()
+    region.addState(state)
+    region.setFused(False)
+    Qg, Wg, Tg, Sg, Fg = general_fields(shape, 11)
+    loc = lambda a: a[o[0]:o[0] + n[0], o[1]:o[1] + n[1], o[2]:o[2] + n[2]].reshape(-1, a.shape[-1], order="F")
+    state.conservedVariables = loc(Qg)
+    state.adjointVariables = loc(Wg)
+    state.targetState = loc(Tg)
+    nx, ny, nz = shape
+    state.addPatch("SAT_SLIP_WALL", "wall.i1", 1, [1, 1, 1, ny, 1, nz], 1.0, 0.0)
+    state.addPatch("SAT_FAR_FIELD", "ff.in", -1, [nx, nx, 1, ny, 1, nz], 1.0, 0.7)
+    region.updatePatches()
+    out = []
+    for mode in (mb.FORWARD, mb.ADJOINT, mb.LINEARIZED):
+        region.computeRhs(mode)
+        out.append(state.rightHandSide.copy())
+    for h in halos:
+        h.check()
+    return np.concatenate(out, axis=1), grid
+
+
 def run_blocks(world, rank, dev):
     """Three curvilinear blocks coupled by SAT_BLOCK_INTERFACE patches with index reorderings (a transposing one and
     one with both in-face indices reversed), block b on rank b % world: at world = 2 block 1's two interfaces are one
@@ -291,6 +342,13 @@ def check_all(world, rank, dev):
     for k, dims in brick.items():
         Bl, bgrid = run_general(bshape, dims, rank, dev)
         bpieces[k] = gathered(Bl, bgrid)
+    # OVERLAP periodicity along the decomposed direction: bricks along j, slabs along k
+    oshape = {1: (14, 9 * world + 4, 13), 2: (14, 13, 9 * world + 4)}
+    odims = {1: (1, world, 1), 2: (1, 1, world)}
+    opieces = {}
+    for pd in (1, 2):
+        Ol, ogrid = run_overlap(oshape[pd], odims[pd], rank, dev, pd)
+        opieces[pd] = gathered(Ol, ogrid)
     blocks = [None] * world
     dist.all_gather_object(blocks, run_blocks(world, rank, dev))
     out = None
@@ -308,6 +366,12 @@ def check_all(world, rank, dev):
         e2 = compare(gpieces, Gs, gshape, 30, "operator path, slabs along k (computed sponge strengths, patches, non-periodic, soft solution limits; fwd/adj/lin RHS + RK4)", world)
         eb = {k: compare(v, Bs, bshape, 30, f"operator path, bricks split along {k} {brick[k]}", world)
               for k, v in bpieces.items()}
+        eo = 0.0
+        for pd in (1, 2):
+            with par.single_process():
+                Os, _ = run_overlap(oshape[pd], (1, 1, 1), 0, dev, pd)
+            eo = max(eo, compare(opieces[pd], Os, oshape[pd], 15,
+                                 f"operator path, OVERLAP periodicity along the decomposed direction {'ijk'[pd]} {odims[pd]}", world))
         one = run_blocks(1, 0, dev)
         ei = 0.0
         for part in blocks:
@@ -320,8 +384,8 @@ def check_all(world, rank, dev):
         out = {"solution_limits_max_rel_diff_vs_1gpu": el,
                "block_interfaces_across_gpus_max_rel_diff_vs_1gpu": ei,
                "fused_forward_adjoint_rk4_max_rel_diff_vs_1gpu": e1, "general_path_patches_max_rel_diff_vs_1gpu": e2,
-               "bricks_max_rel_diff_vs_1gpu": eb, "ranks": world, "tolerance": 1e-12,
-               "ok": bool(e1 <= 1e-13 and e2 <= 1e-12 and ei <= 1e-12 and el <= 1e-12 and all(e <= 1e-12 for e in eb.values()))}
+               "bricks_max_rel_diff_vs_1gpu": eb, "overlap_periodic_decomposed_max_rel_diff_vs_1gpu": eo, "ranks": world, "tolerance": 1e-12,
+               "ok": bool(e1 <= 1e-13 and e2 <= 1e-12 and ei <= 1e-12 and el <= 1e-12 and eo <= 1e-12 and all(e <= 1e-12 for e in eb.values()))}
     dist.barrier()
     return out
 
